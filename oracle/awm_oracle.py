@@ -1,0 +1,1105 @@
+"""awm_oracle -- CPU restatement of the reference's spectral watermark path.
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg may import this module, and only as the checker.  The product
+(audiowmark_b200/) never imports it and has no CPU fallback.
+
+What it restates (citations are /root/reference/src/<file>:<lines>):
+  * keyed PRNG                     random.cc:97-161, random.hh:53-113
+  * key-derived tables             wmcommon.hh:91-123,165-185, wmcommon.cc:143-202,
+                                   syncfinder.cc:30-77, wmadd.cc:49-162
+  * convolutional code             convcode.cc:42-125 (encoder), :128-213 (Viterbi, in oracle_c.cc)
+  * embed (add)                    wmcommon.cc:68-121, wmadd.cc:61-84,169-351,520-589, limiter.cc:33-124
+  * sync search                    syncfinder.cc:80-658
+  * block / clip decode, results   wmget.cc:40-161,163-474,492-939, wavchunkloader.cc:54-163
+
+Parity pin: the float32 inner loops live in oracle_c.cc and use the same in-repo FFT
+that backs the reference build oracle/_ref/audiowmark (the reference's own FFT is
+FFTW, a third-party library that is not installed and not vendored), so this oracle
+reproduces that binary's output exactly; tests/test_oracle_vs_reference.py and the
+fixtures in tests/golden/ (made by tests/golden/make_golden.py with oracle/_ref)
+check that.  Against a reference built on real FFTW the pin is behavioural only
+(SURVEY.md section 8c): payload bits, block types and match counts.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("build_oracle", os.path.join(_HERE, "build_oracle.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build_liboracle()
+        _LIB = ctypes.CDLL(path)
+        _LIB.orc_viterbi.restype = ctypes.c_float
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# --------------------------------------------------------------------------- params
+
+@dataclass
+class Params:
+    """wmcommon.hh:33-89 / wmcommon.cc:27-58 (defaults)."""
+    frame_size: int = 1024
+    frames_per_bit: int = 2
+    bands_per_frame: int = 30
+    max_band: int = 100
+    min_band: int = 20
+    water_delta: float = 0.01
+    mix: bool = True
+    hard: bool = False
+    payload_size: int = 128
+    payload_short: bool = False
+    sync_bits: int = 6
+    sync_frames_per_bit: int = 85
+    sync_search_step: int = 256
+    sync_search_fine: int = 8
+    sync_threshold2: float = 0.35
+    get_n_best: int = 8
+    frames_pad_start: int = 250
+    mark_sample_rate: int = 44100
+    limiter_block_size_ms: int = 1000
+    limiter_ceiling: float = 0.99
+    get_chunk_size: float = 30.0
+    test_no_limiter: bool = False
+
+    @property
+    def n_bands(self):
+        return self.max_band - self.min_band + 1
+
+
+A, B, AB = 0, 1, 2          # ConvBlockType (convcode.hh:24)
+BLOCK, CLIP = 0, 1          # SyncFinder::Mode
+STREAM_DATA_UP_DOWN, STREAM_SYNC_UP_DOWN, STREAM_SPEED_CLIP, STREAM_MIX, STREAM_BIT_ORDER, STREAM_FRAME_POSITION = 1, 2, 3, 4, 5, 6
+
+
+# --------------------------------------------------------------------------- keyed PRNG
+
+class Key:
+    """random.hh:27-47; default key = 16 zero bytes, name ''."""
+
+    def __init__(self, aes_key: bytes = bytes(16), name: str = ""):
+        assert len(aes_key) == 16
+        self.aes_key = bytes(aes_key)
+        self.name = name
+
+    @staticmethod
+    def test_key(n: int) -> "Key":           # random.cc:202-207
+        return Key(struct.pack(">Q", n) + bytes(8), "test-key-%d" % n)
+
+    def __eq__(self, o):
+        return self.aes_key == o.aes_key and self.name == o.name
+
+    def __hash__(self):
+        return hash((self.aes_key, self.name))
+
+
+class Random:
+    """AES-128 CTR keystream as big-endian u64 words (random.cc:97-161)."""
+
+    def __init__(self, key: Key, seed: int, stream: int):
+        from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+        self._Cipher, self._alg, self._modes = Cipher, algorithms.AES(key.aes_key), modes
+        self._ecb = Cipher(self._alg, modes.ECB()).encryptor()
+        self.seed(seed, stream)
+
+    def seed(self, seed: int, stream: int):          # random.cc:116-136
+        plain = struct.pack(">Q", seed & 0xFFFFFFFFFFFFFFFF) + bytes([stream]) + bytes(7)
+        iv = self._ecb.update(plain)
+        self._ctr = self._Cipher(self._alg, self._modes.CTR(iv)).encryptor()
+        self._buf = ()
+        self._pos = 0
+
+    def __call__(self) -> int:                       # random.hh:73-80, random.cc:144-161
+        if self._pos == len(self._buf):
+            self._buf = struct.unpack(">32Q", self._ctr.update(bytes(256)))
+            self._pos = 0
+        v = self._buf[self._pos]
+        self._pos += 1
+        return v
+
+    def bulk_u64(self, n: int) -> np.ndarray:
+        """n consecutive outputs (only valid on a freshly seeded generator)."""
+        assert self._pos == len(self._buf)
+        nbytes = ((n + 31) // 32) * 256
+        return np.frombuffer(self._ctr.update(bytes(nbytes)), dtype=">u8")[:n].astype(np.uint64)
+
+    def shuffle(self, seq: list):                    # random.hh:102-113
+        n = len(seq)
+        for i in range(n):
+            j = i + self() % (n - i)
+            seq[i], seq[j] = seq[j], seq[i]
+
+    def random_double(self) -> float:                # random.hh:93-98 (libstdc++ generate_canonical, one draw)
+        r = float(self()) / 18446744073709551616.0
+        return math.nextafter(1.0, 0.0) if r >= 1.0 else r
+
+
+def u64_to_unit_double(u: np.ndarray) -> np.ndarray:
+    r = u.astype(np.float64) / 18446744073709551616.0
+    return np.where(r >= 1.0, np.nextafter(1.0, 0.0), r)
+
+
+def gen_noise(seconds: float, rate: int = 44100, key: Key | None = None) -> np.ndarray:
+    """test_gen_noise (audiowmark.cc:399-417): stereo, Random(key, 0, data_up_down), 2u-1 -> float."""
+    key = key or Key()
+    n = int(rate * seconds) * 2
+    rng = Random(key, 0, STREAM_DATA_UP_DOWN)
+    d = u64_to_unit_double(rng.bulk_u64(n)) * 2 - 1
+    return d.astype(np.float32).reshape(-1, 2)
+
+
+# --------------------------------------------------------------------------- sample format helpers
+
+def float_to_int_clip(f: np.ndarray, bits: int) -> np.ndarray:
+    """rawconverter.hh:34-50."""
+    inorm = 1 << (bits - 1)
+    snorm = f.astype(np.float32) * np.float32(inorm)
+    out = np.trunc(np.clip(snorm, -float(inorm), float(inorm))).astype(np.int64)
+    out = np.where(snorm >= np.float32(inorm - 1), inorm - 1, out)
+    out = np.where(snorm <= np.float32(-inorm), -inorm, out)
+    return out
+
+
+def quantize_sndfile16(samples: np.ndarray) -> np.ndarray:
+    """16-bit file write as the reference does through libsndfile's int API
+    (sfoutputstream.cc:148-155: float_to_int_clip<32>, file keeps the top 16 bits)."""
+    return (float_to_int_clip(samples, 32) >> 16).astype(np.int16)
+
+
+def int16_to_float(pcm: np.ndarray) -> np.ndarray:
+    """sfinputstream.cc:189-210 / rawconverter.cc:257-263: left-justified int32 * 2^-31."""
+    return (pcm.astype(np.int32).astype(np.float32) * np.float32(65536.0)) * np.float32(1.0 / 0x80000000)
+
+
+def write_wav16(path: str, samples: np.ndarray, rate: int = 44100):
+    pcm = quantize_sndfile16(samples)
+    nch = pcm.shape[1]
+    data = pcm.astype("<i2").tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, nch, rate, rate * nch * 2, nch * 2, 16)
+    hdr += b"data" + struct.pack("<I", len(data))
+    with open(path, "wb") as f:
+        f.write(hdr + data)
+
+
+def read_wav(path: str):
+    """Minimal RIFF reader (PCM16/24/32, float32) -> (float32 [n, ch], rate, bits)."""
+    raw = open(path, "rb").read()
+    assert raw[:4] in (b"RIFF", b"RF64") and raw[8:12] == b"WAVE"
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= len(raw):
+        cid, sz = raw[pos:pos + 4], struct.unpack("<I", raw[pos + 4:pos + 8])[0]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", raw[pos + 8:pos + 24])
+        elif cid == b"data":
+            data = raw[pos + 8:] if sz == 0xFFFFFFFF else raw[pos + 8:pos + 8 + sz]
+            break
+        pos += 8 + sz + (sz & 1)
+    tag, nch, rate, _, _, bits = fmt
+    if tag == 3:
+        x = np.frombuffer(data[:len(data) // 4 * 4], "<f4").astype(np.float32)
+    elif bits == 16:
+        x = int16_to_float(np.frombuffer(data[:len(data) // 2 * 2], "<i2"))
+    elif bits == 32:
+        x = np.frombuffer(data[:len(data) // 4 * 4], "<i4").astype(np.float32) * np.float32(1.0 / 0x80000000)
+    elif bits == 24:
+        b = np.frombuffer(data[:len(data) // 3 * 3], np.uint8).reshape(-1, 3).astype(np.int32)
+        v = (b[:, 0] << 8) | (b[:, 1] << 16) | (b[:, 2] << 24)
+        x = v.astype(np.int32).astype(np.float32) * np.float32(1.0 / 0x80000000)
+    else:
+        raise ValueError("unsupported wav")
+    n = len(x) // nch
+    return x[:n * nch].reshape(n, nch), rate, bits
+
+
+# --------------------------------------------------------------------------- bits / payload
+
+def bit_str_to_vec(s: str) -> list:                  # utils.cc:95-111
+    out = []
+    for ch in s:
+        try:
+            c = int(ch, 16)
+        except ValueError:
+            return []
+        out += [(c >> 3) & 1, (c >> 2) & 1, (c >> 1) & 1, c & 1]
+    return out
+
+
+def bit_vec_to_str(v) -> str:                        # utils.cc:113-133
+    s = ""
+    for pos in range(0, len(v) - 3, 4):
+        nib = 0
+        for j in range(4):
+            if v[pos + j]:
+                nib |= 1 << (3 - j)
+        s += "0123456789abcdef"[nib]
+    return s
+
+
+def parse_payload(bits: str, P: Params) -> list:     # wmcommon.cc:210-238
+    v = bit_str_to_vec(bits)
+    if not v or len(v) > P.payload_size:
+        return []
+    if len(v) < P.payload_size:
+        v = [v[i % len(v)] for i in range(P.payload_size)]
+    return v
+
+
+# --------------------------------------------------------------------------- convolutional code
+
+AB_GENERATORS = [0o66561, 0o75211, 0o71545, 0o54435, 0o63635, 0o52475,
+                 0o63543, 0o75307, 0o52547, 0o45627, 0o67657, 0o51757]   # convcode.cc:42-46
+ORDER = 15
+
+
+def block_generators(block_type: int) -> list:       # convcode.cc:77-98
+    if block_type == A:
+        return AB_GENERATORS[0::2]
+    if block_type == B:
+        return AB_GENERATORS[1::2]
+    return list(AB_GENERATORS)
+
+
+def conv_code_size(block_type: int, msg_size: int) -> int:   # convcode.cc:65-75
+    return (msg_size + ORDER) * 12 // 2 if block_type in (A, B) else (msg_size + ORDER) * 12
+
+
+def conv_encode(block_type: int, in_bits: list) -> list:     # convcode.cc:100-125
+    gens = block_generators(block_type)
+    out, reg = [], 0
+    for b in list(in_bits) + [0] * ORDER:
+        reg = ((reg << 1) | b) & 0xFFFFFFFF
+        for poly in gens:
+            out.append(bin(reg & poly).count("1") & 1)
+    return out
+
+
+def conv_decode_soft(block_type: int, coded: np.ndarray):    # convcode.cc:128-213
+    gens = np.array(block_generators(block_type), dtype=np.uint32)
+    coded = np.ascontiguousarray(coded, dtype=np.float32)
+    steps = len(coded) // len(gens)
+    dec = np.zeros(steps, dtype=np.int32)
+    err = lib().orc_viterbi(_p(gens), ctypes.c_int(len(gens)), ctypes.c_int(ORDER), _p(coded), ctypes.c_int64(len(coded)), _p(dec))
+    return [int(b) for b in dec[:steps - ORDER]], float(err)
+
+
+# --------------------------------------------------------------------------- key-derived tables
+
+def mark_data_frame_count(P: Params) -> int:         # wmcommon.cc:167-171
+    return conv_code_size(A, P.payload_size) * P.frames_per_bit
+
+
+def mark_sync_frame_count(P: Params) -> int:         # wmcommon.cc:173-177
+    return P.sync_bits * P.sync_frames_per_bit
+
+
+def frames_per_block(P: Params) -> int:
+    return mark_data_frame_count(P) + mark_sync_frame_count(P)
+
+
+class UpDownGen:                                     # wmcommon.hh:91-123
+    def __init__(self, key: Key, stream: int, P: Params):
+        self.stream, self.P = stream, P
+        self.random = Random(key, 0, stream)
+
+    def get(self, f: int):
+        P = self.P
+        bands = list(range(P.min_band, P.max_band + 1))
+        self.random.seed(f, self.stream)
+        self.random.shuffle(bands)
+        return bands[:P.bands_per_frame], bands[P.bands_per_frame:2 * P.bands_per_frame]
+
+
+class BitPosGen:                                     # wmcommon.cc:143-165
+    def __init__(self, key: Key, P: Params):
+        self.P = P
+        self.pos = list(range(frames_per_block(P)))
+        Random(key, 0, STREAM_FRAME_POSITION).shuffle(self.pos)
+
+    def sync_frame(self, f):
+        return self.pos[f]
+
+    def data_frame(self, f):
+        return self.pos[f + mark_sync_frame_count(self.P)]
+
+
+def gen_mix_entries(key: Key, P: Params) -> list:    # wmcommon.cc:179-202
+    udg, bpg = UpDownGen(key, STREAM_DATA_UP_DOWN, P), BitPosGen(key, P)
+    entries = []
+    for f in range(mark_data_frame_count(P)):
+        idx = bpg.data_frame(f)
+        up, down = udg.get(f)
+        entries += [(idx, u, d) for u, d in zip(up, down)]
+    Random(key, 0, STREAM_MIX).shuffle(entries)
+    return entries
+
+
+def randomize_bit_order(key: Key, vec, encode: bool):  # wmcommon.hh:165-185
+    order = list(range(len(vec)))
+    Random(key, 0, STREAM_BIT_ORDER).shuffle(order)
+    out = [0] * len(vec)
+    for i in range(len(vec)):
+        if encode:
+            out[i] = vec[order[i]]
+        else:
+            out[order[i]] = vec[i]
+    return out
+
+
+KEEP, UP, DOWN = 0, 1, 2
+
+
+def init_frame_mod(key: Key, ab: int, bitvec: list, P: Params) -> np.ndarray:
+    """wmadd.cc:49-59,86-162 -> uint8 [frames_per_block][max_band+1]."""
+    fm = np.zeros((frames_per_block(P), P.max_band + 1), dtype=np.uint8)
+    fec = randomize_bit_order(key, conv_encode(B if ab else A, bitvec), True)
+    # mark_sync (wmadd.cc:129-146)
+    udg, bpg = UpDownGen(key, STREAM_SYNC_UP_DOWN, P), BitPosGen(key, P)
+    for f in range(mark_sync_frame_count(P)):
+        idx = bpg.sync_frame(f)
+        bit = (f // P.sync_frames_per_bit + ab) & 1
+        up, down = udg.get(f)
+        fm[idx, up] = UP if bit else DOWN
+        fm[idx, down] = DOWN if bit else UP
+    # mark_data (wmadd.cc:86-127)
+    if P.mix:
+        mix = gen_mix_entries(key, P)
+        for f in range(mark_data_frame_count(P)):
+            bit = fec[f // P.frames_per_bit]
+            for fb in range(P.bands_per_frame):
+                idx, u, d = mix[f * P.bands_per_frame + fb]
+                fm[idx, u] = UP if bit else DOWN
+                fm[idx, d] = DOWN if bit else UP
+    else:
+        udg = UpDownGen(key, STREAM_DATA_UP_DOWN, P)
+        for f in range(mark_data_frame_count(P)):
+            idx = bpg.data_frame(f)
+            bit = fec[f // P.frames_per_bit]
+            up, down = udg.get(f)
+            fm[idx, up] = UP if bit else DOWN
+            fm[idx, down] = DOWN if bit else UP
+    return fm
+
+
+@dataclass
+class SyncBits:
+    """syncfinder.cc:30-77 flattened: bit b owns entries off[b]..off[b+1]."""
+    off: np.ndarray
+    frame: np.ndarray
+    up: np.ndarray
+    down: np.ndarray
+
+
+def get_sync_bits(key: Key, mode: int, P: Params) -> SyncBits:
+    first_block_end = frames_per_block(P)
+    block_count = 2 if mode == CLIP else 1
+    udg, bpg = UpDownGen(key, STREAM_SYNC_UP_DOWN, P), BitPosGen(key, P)
+    off, frames, ups, downs = [0], [], [], []
+    for bit in range(P.sync_bits):
+        fbs = []
+        for f in range(P.sync_frames_per_bit):
+            fu, fd = udg.get(f + bit * P.sync_frames_per_bit)
+            for block in range(block_count):
+                fr = bpg.sync_frame(f + bit * P.sync_frames_per_bit) + block * first_block_end
+                u = [x - P.min_band for x in (fu if block == 0 else fd)]
+                d = [x - P.min_band for x in (fd if block == 0 else fu)]
+                fbs.append((fr, sorted(u), sorted(d)))
+        fbs.sort(key=lambda t: t[0])
+        for fr, u, d in fbs:
+            frames.append(fr); ups.append(u); downs.append(d)
+        off.append(len(frames))
+    return SyncBits(np.array(off, np.int32), np.array(frames, np.int32),
+                    np.array(ups, np.int32).reshape(-1), np.array(downs, np.int32).reshape(-1))
+
+
+# --------------------------------------------------------------------------- FFT analysis
+
+def window_cos(x):                                   # wmcommon.hh:187-193
+    return np.where(np.abs(x) > 1, 0.0, 0.5 * np.cos(x * np.pi) + 0.5)
+
+
+def gen_normalized_window(n: int) -> np.ndarray:     # wmcommon.cc:68-89
+    i = np.arange(n, dtype=np.float64)
+    win = window_cos((i - n / 2.0) / (n / 2.0)).astype(np.float32)   # window[i] = win (float store)
+    weight = 0.0
+    for w in window_cos((i - n / 2.0) / (n / 2.0)):                  # double running sum
+        weight += w
+    return (win.astype(np.float64) * (2.0 / weight)).astype(np.float32)  # window[i] *= 2.0 / weight
+
+
+_WINDOWS = {}
+
+
+def analysis_window(n: int) -> np.ndarray:
+    if n not in _WINDOWS:
+        _WINDOWS[n] = gen_normalized_window(n)
+    return _WINDOWS[n]
+
+
+def analyze_frames(samples: np.ndarray, starts, n: int = 1024) -> np.ndarray:
+    """FFTAnalyzer::run_fft for many start positions -> complex64 [jobs][ch][n/2+1]."""
+    samples = np.ascontiguousarray(samples, dtype=np.float32)
+    nch = samples.shape[1]
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    assert len(starts) == 0 or (starts.min() >= 0 and starts.max() + n <= samples.shape[0])
+    out = np.zeros((len(starts), nch, n + 2), dtype=np.float32)
+    win = analysis_window(n)
+    lib().orc_analyze_frames(_p(samples), ctypes.c_int(nch), _p(starts), ctypes.c_int64(len(starts)), _p(win), ctypes.c_int(n), _p(out))
+    return out
+
+
+def db_bands(spect: np.ndarray, P: Params) -> np.ndarray:
+    jobs, nch, n2 = spect.shape
+    out = np.zeros((jobs, P.n_bands), dtype=np.float32)
+    lib().orc_db_bands(_p(np.ascontiguousarray(spect)), ctypes.c_int64(jobs), ctypes.c_int(nch), ctypes.c_int(n2 - 2),
+                       ctypes.c_int(P.min_band), ctypes.c_int(P.max_band), _p(out))
+    return out
+
+
+# --------------------------------------------------------------------------- embed
+
+def synth_window(P: Params) -> np.ndarray:           # wmadd.cc:177-206
+    n = P.frame_size
+    i = np.arange(3 * n, dtype=np.float64)
+    norm_pos = (i - n) / n
+    norm_pos = np.where(norm_pos > 0.5, 1 - norm_pos, norm_pos)
+    overlap = 0.1
+    tri = np.where(norm_pos < -overlap, 0.0, np.where(norm_pos < overlap, 0.5 + norm_pos / (2 * overlap), 1.0))
+    return ((np.cos(tri * np.pi + np.pi) + 1) * 0.5).astype(np.float32)
+
+
+def limiter(x: np.ndarray, rate: int, P: Params) -> np.ndarray:
+    """limiter.cc:33-124 on a zero-extended signal x [n, ch] (see add_stream_watermark :539-546)."""
+    n, nch = x.shape
+    bs = rate * P.limiter_block_size_ms // 1000
+    ceiling = np.float32(P.limiter_ceiling)
+    nblocks = (n + bs - 1) // bs
+    bm = np.full(nblocks + 2, ceiling, dtype=np.float32)          # bm[b+1] = block b, bm[0] = "last" before start
+    for b in range(nblocks):
+        seg = x[b * bs:(b + 1) * bs]
+        if seg.size:
+            bm[b + 1] = max(ceiling, np.float32(np.abs(seg).max()))
+    out = np.empty_like(x)
+    i_f = np.arange(bs, dtype=np.float32)
+    for b in range(nblocks):
+        last, cur, nxt = bm[b], bm[b + 1], bm[b + 2]
+        scale_start = ceiling / max(last, cur)
+        scale_end = ceiling / max(cur, nxt)
+        scale_step = np.float32(scale_end - scale_start) / np.float32(bs)
+        scale = scale_start + i_f * scale_step
+        seg = x[b * bs:(b + 1) * bs]
+        out[b * bs:(b + 1) * bs] = seg * scale[:len(seg), None]
+    return out
+
+
+@dataclass
+class EmbedResult:
+    samples: np.ndarray
+    data_blocks: int
+    snr_db: float
+    wm: np.ndarray = None
+
+
+def embed(samples: np.ndarray, key: Key, bits: str, P: Params | None = None, rate: int = 44100, keep_wm: bool = False) -> EmbedResult:
+    """add_stream_watermark (wmadd.cc:448-618) at 44.1 kHz (no resampler), zero_frames = 0."""
+    P = P or Params()
+    assert rate == P.mark_sample_rate, "oracle covers the 44.1 kHz path only (resampler is out of scope)"
+    bitvec = parse_payload(bits, P)
+    assert bitvec, "bad payload"
+    samples = np.ascontiguousarray(samples, dtype=np.float32)
+    n, nch = samples.shape
+    N = P.frame_size
+    F = (n + N - 1) // N
+    fpb = frames_per_block(P)
+    ext = np.zeros(((F + 1) * N, nch), dtype=np.float32)
+    ext[:n] = samples
+
+    fm_tab = [init_frame_mod(key, 0, bitvec, P), init_frame_mod(key, 1, bitvec, P)]
+    spect = analyze_frames(ext, np.arange(F, dtype=np.int64) * N, N)          # [F][ch][N+2]
+    delta = np.zeros_like(spect)
+    L = lib()
+    for f in range(F):
+        r = (2 * fpb - P.frames_pad_start + f) % (2 * fpb)                  # wmadd.cc:295,326-344
+        fm = fm_tab[1][r - fpb] if r >= fpb else fm_tab[0][r]
+        for ch in range(nch):
+            L.orc_apply_frame_mod(_p(fm), ctypes.c_int(len(fm)), _p(spect[f, ch]), _p(delta[f, ch]), ctypes.c_double(P.water_delta))
+    wmf = np.zeros((F + 2, nch, N), dtype=np.float32)                        # wmf[f+1] = ifft of frame f; wmf[0], wmf[F+1] = 0
+    tmp = np.zeros((F * nch, N), dtype=np.float32)
+    L.orc_irfft(_p(delta), _p(tmp), ctypes.c_int(N), ctypes.c_int64(F * nch))
+    wmf[1:F + 1] = tmp.reshape(F, nch, N)
+
+    w = synth_window(P)
+    w0, w1, w2 = w[:N], w[N:2 * N], w[2 * N:]
+    # output frame m = ((0 + wm[m-1]*w2) + wm[m]*w1) + wm[m+1]*w0      (wmadd.cc:215-250, one frame of delay)
+    a = wmf[0:F + 1] * w2
+    b = wmf[1:F + 2] * w1
+    wm = (a + b)
+    wm[:F] = wm[:F] + wmf[2:F + 2] * w0
+    wm = np.ascontiguousarray(wm.transpose(0, 2, 1)).reshape((F + 1) * N, nch)
+    mixed = wm + ext                                                          # wmadd.cc:564-565
+    d = wm.astype(np.float64)          # the loop also sums the zero-padded tail (wmadd.cc:553-563)
+    o = samples.astype(np.float64)
+    snr = 10 * math.log10((o * o).sum() / max((d * d).sum(), 1e-300))
+    out = mixed if P.test_no_limiter else limiter(mixed, rate, P)
+    # data block counter (wmadd.cc:311-313,345-350): number of WatermarkGen::run calls made by the loop
+    bs = rate * P.limiter_block_size_ms // 1000
+    runs = embed_gen_runs(n, N, not P.test_no_limiter, bs)
+    f0 = 2 * fpb - P.frames_pad_start
+    m_data_blocks = (f0 + runs) // fpb - f0 // fpb
+    return EmbedResult(out[:n].copy(), max(m_data_blocks - 1, 0), snr, wm[:n].copy() if keep_wm else None)
+
+
+def embed_gen_runs(n: int, N: int, limiter_on: bool, bs: int) -> int:
+    """How often the loop wmadd.cc:520-589 calls WatermarkGen::run: zero frames keep being fed
+    after EOF until total_output == total_input; the synth delays by one frame (wmadd.cc:240-249)
+    and the limiter holds back until two complete blocks are buffered (limiter.cc:53-58)."""
+    if n == 0:
+        return 0
+    if not limiter_on:
+        return 1 + (n + N - 1) // N
+    need = ((n + bs - 1) // bs + 1) * bs
+    return 1 + (need + N - 1) // N
+
+
+# --------------------------------------------------------------------------- sync finder
+
+@dataclass
+class SearchScore:
+    index: int
+    raw_quality: float
+    local_mean: float = 0.0
+
+    def abs_quality(self):
+        return abs(self.raw_quality - self.local_mean)
+
+
+@dataclass
+class Score:
+    index: int
+    quality: float
+    block_type: int
+
+
+class SyncFinder:
+    local_mean_distance = 20
+
+    def __init__(self, P: Params):
+        self.P = P
+        self.first = 0
+        self.last = 0
+
+    # -- sync_fft (syncfinder.cc:560-605)
+    def sync_fft(self, samples, index, frame_count, want):
+        P, N = self.P, self.P.frame_size
+        n, nch = samples.shape
+        if n * nch < (index + frame_count * N) * nch:
+            return None, None
+        f = np.arange(frame_count, dtype=np.int64)
+        f_first = (index + f * N) * nch
+        f_last = (index + (f + 1) * N) * nch
+        ok = ~((f_last < self.first) | (f_first > self.last))
+        if want is not None:
+            ok &= want.astype(bool)
+        db = np.zeros((frame_count, P.n_bands), dtype=np.float32)
+        sel = np.nonzero(ok)[0]
+        if len(sel):
+            for c0 in range(0, len(sel), 8192):
+                s = sel[c0:c0 + 8192]
+                db[s] = db_bands(analyze_frames(samples, index + s * N, N), P)
+        return db, ok.astype(np.int8)
+
+    def sync_decode(self, sb: SyncBits, start_frames, db, have):
+        start_frames = np.ascontiguousarray(start_frames, dtype=np.int64)
+        q = np.zeros(len(start_frames), dtype=np.float64)
+        P = self.P
+        lib().orc_sync_decode(_p(db), _p(have), ctypes.c_int(P.n_bands), ctypes.c_int(P.sync_bits), _p(sb.off), _p(sb.frame),
+                              _p(sb.up), _p(sb.down), ctypes.c_int(P.bands_per_frame), _p(start_frames),
+                              ctypes.c_int64(len(start_frames)), ctypes.c_double(P.water_delta), _p(q))
+        return q
+
+    # -- search_approx (syncfinder.cc:171-256)
+    def search_approx(self, sb: SyncBits, samples, mode):
+        P, N = self.P, self.P.frame_size
+        n, nch = samples.shape
+        fc = (n * nch) // nch // N
+        total = frames_per_block(P) * (2 if mode == CLIP else 1)
+        idx_all, q_all = [], []
+        for shift in range(0, N, P.sync_search_step):
+            nfr = max(fc - 1, 0)
+            if nfr == 0:
+                continue
+            db, have = self.sync_fft(samples, shift, nfr, None)
+            starts = np.arange(max(fc, 0), dtype=np.int64)
+            starts = starts[(starts + total) * P.n_bands < nfr * P.n_bands]
+            if len(starts) == 0:
+                continue
+            q = self.sync_decode(sb, starts, db, have)
+            idx_all.append(starts * N + shift)
+            q_all.append(q)
+        if not idx_all:
+            return []
+        idx = np.concatenate(idx_all)
+        q = np.concatenate(q_all)
+        order = np.argsort(idx, kind="stable")
+        idx, q = idx[order], q[order]
+        # local mean (:234-254): sequential double sum over j = -20..20, |j| >= 4
+        m = len(q)
+        lm = np.zeros(m)
+        cnt = np.zeros(m, dtype=np.int64)
+        for j in range(-self.local_mean_distance, self.local_mean_distance + 1):
+            if abs(j) >= 4:
+                lo, hi = max(0, -j), min(m, m - j)
+                if hi > lo:
+                    lm[lo:hi] += q[lo + j:hi + j]
+                    cnt[lo:hi] += 1
+        lm = np.where(cnt > 0, lm / np.maximum(cnt, 1), lm)
+        return [SearchScore(int(i), float(r), float(l)) for i, r, l in zip(idx, q, lm)]
+
+    # -- selectors (syncfinder.cc:258-391)
+    @staticmethod
+    def select_local_maxima(scores):
+        out, i, m = [], 0, len(scores)
+        while i < m:
+            qv = scores[i].abs_quality()
+            ql = scores[i - 1].abs_quality() if i > 0 else 0
+            qn = scores[i + 1].abs_quality() if i + 1 < m else 0
+            if qv >= ql and qv >= qn:
+                out.append(scores[i])
+                i += 1
+            i += 1
+        return out
+
+    def mask_avg_false_positives(self, scores):
+        mask_distance, mask_factor = self.local_mean_distance + 3, 3
+        m = len(scores)
+        if m == 0:
+            return scores
+        idx = np.array([s.index for s in scores], dtype=np.int64)
+        d = np.array([s.raw_quality - s.local_mean for s in scores])
+        aq = np.abs(d)
+        sign = np.where(d < 0, -1, 1)
+        masked = np.zeros(m, dtype=bool)
+        for dd in range(-mask_distance, mask_distance + 1):
+            if dd == 0:
+                continue
+            lo, hi = max(0, -dd), min(m, m - dd)
+            if hi <= lo:
+                continue
+            i = np.arange(lo, hi)
+            j = i + dd
+            dist = np.abs(idx[i] - idx[j]) // self.P.sync_search_step
+            cond = (dist <= mask_distance) & (aq[j] > aq[i] * mask_factor) & (sign[j] != sign[i])
+            masked[i] |= cond
+        return [s for s, mk in zip(scores, masked) if not mk]
+
+    def select_threshold_and_n_best(self, scores, threshold):
+        scores = sorted(scores, key=lambda s: -s.abs_quality())
+        i = 0
+        while i < len(scores) and scores[i].abs_quality() > threshold:
+            i += 1
+        if i >= self.P.get_n_best:
+            return scores[:i]
+        if len(scores) > self.P.get_n_best:
+            return scores[:self.P.get_n_best]
+        return scores
+
+    @staticmethod
+    def select_truncate_n(scores, n):
+        return sorted(scores, key=lambda s: -s.abs_quality())[:n]
+
+    # -- search_refine (syncfinder.cc:393-458)
+    def search_refine(self, samples, mode, scores, sb: SyncBits, key: Key):
+        P = self.P
+        total = frames_per_block(P)
+        first_block_end = total
+        if mode == CLIP:
+            total *= 2
+        bpg = BitPosGen(key, P)
+        want = np.zeros(total, dtype=np.int8)
+        for f in range(mark_sync_frame_count(P)):
+            want[bpg.sync_frame(f)] = 1
+            if mode == CLIP:
+                want[first_block_end + bpg.sync_frame(f)] = 1
+        out = []
+        for sc in scores:
+            best_q, best_i = sc.raw_quality, sc.index
+            start = max(int(sc.index) - P.sync_search_step, 0)
+            end = sc.index + P.sync_search_step
+            for fine in range(start, end + 1, P.sync_search_fine):
+                db, have = self.sync_fft(samples, fine, total, want)
+                if db is not None:
+                    q = float(self.sync_decode(sb, [0], db, have)[0])
+                    if abs(q - sc.local_mean) > abs(best_q - sc.local_mean):
+                        best_q, best_i = q, fine
+            out.append(SearchScore(best_i, best_q, sc.local_mean))
+        out.sort(key=lambda s: s.index)
+        return out
+
+    # -- search (syncfinder.cc:487-558)
+    def search(self, key: Key, samples, mode, stages: dict | None = None):
+        P = self.P
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        flat = samples.reshape(-1)
+        if mode == CLIP:                             # scan_silence :155-169
+            nz = np.nonzero(flat)[0]
+            if len(nz):
+                self.first, self.last = int(nz[0]), int(nz[-1]) + 1
+            else:
+                self.first, self.last = len(flat), len(flat)
+        else:
+            self.first, self.last = 0, len(flat)
+        sb = get_sync_bits(key, mode, P)
+        scores = self.search_approx(sb, samples, mode)
+        if stages is not None:
+            stages["approx"] = scores
+        scores = self.select_local_maxima(scores)
+        scores = self.mask_avg_false_positives(scores)
+        scores = self.select_threshold_and_n_best(scores, P.sync_threshold2 * 0.75)
+        if mode == CLIP:
+            scores = self.select_truncate_n(scores, max(P.get_n_best, 5))
+        if stages is not None:
+            stages["selected"] = list(scores)
+        scores = self.search_refine(samples, mode, scores, sb, key)
+        if stages is not None:
+            stages["refined"] = list(scores)
+        scores = self.select_threshold_and_n_best(scores, P.sync_threshold2)
+        scores.sort(key=lambda s: s.index)
+        out = []
+        for s in scores:
+            q = s.raw_quality - s.local_mean
+            out.append(Score(s.index, abs(q), A if q > 0 else B))
+        return out
+
+
+# --------------------------------------------------------------------------- decode
+
+def fft_range(samples, index, count, P: Params):     # wmcommon.cc:123-141
+    n, nch = samples.shape
+    if n * nch < (index + count * P.frame_size) * nch:
+        return None
+    sp = analyze_frames(samples, index + np.arange(count, dtype=np.int64) * P.frame_size, P.frame_size)
+    return sp.reshape(count * nch, P.frame_size + 2)
+
+
+_MIX_CACHE = {}
+
+
+def _mix_arrays(key: Key, P: Params):
+    k = (key.aes_key, P.payload_size, P.frames_per_bit, P.payload_short)
+    if k not in _MIX_CACHE:
+        m = gen_mix_entries(key, P)
+        _MIX_CACHE[k] = tuple(np.array([e[i] for e in m], dtype=np.int32) for i in range(3))
+    return _MIX_CACHE[k]
+
+
+def mix_decode(key: Key, spect, nch, P: Params) -> np.ndarray:      # wmget.cc:67-108
+    fc = mark_data_frame_count(P)
+    mf, mu, md = _mix_arrays(key, P)
+    out = np.zeros(fc // P.frames_per_bit, dtype=np.float32)
+    lib().orc_mix_decode(_p(spect), ctypes.c_int64(spect.shape[0]), ctypes.c_int(P.frame_size), ctypes.c_int(nch),
+                         _p(mf), _p(mu), _p(md), ctypes.c_int(fc), ctypes.c_int(P.bands_per_frame), ctypes.c_int(P.frames_per_bit), _p(out))
+    return out
+
+
+def linear_decode(key: Key, spect, nch, P: Params) -> np.ndarray:   # wmget.cc:110-152
+    fc = mark_data_frame_count(P)
+    udg, bpg = UpDownGen(key, STREAM_DATA_UP_DOWN, P), BitPosGen(key, P)
+    df, up, down = [], [], []
+    for f in range(fc):
+        df.append(bpg.data_frame(f))
+        u, d = udg.get(f)
+        up += u; down += d
+    df, up, down = (np.array(x, dtype=np.int32) for x in (df, up, down))
+    out = np.zeros(fc // P.frames_per_bit, dtype=np.float32)
+    lib().orc_linear_decode(_p(spect), ctypes.c_int64(spect.shape[0]), ctypes.c_int(P.frame_size), ctypes.c_int(nch),
+                            _p(df), _p(up), _p(down), ctypes.c_int(fc), ctypes.c_int(P.bands_per_frame), ctypes.c_int(P.frames_per_bit), _p(out))
+    return out
+
+
+def raw_bits_for_block(key: Key, samples, index, P: Params):
+    sp = fft_range(samples, index, frames_per_block(P), P)
+    if sp is None:
+        return None
+    raw = mix_decode(key, sp, samples.shape[1], P) if P.mix else linear_decode(key, sp, samples.shape[1], P)
+    return np.array(randomize_bit_order(key, list(raw), False), dtype=np.float32)
+
+
+def normalize_soft_bits(soft, P: Params) -> np.ndarray:             # wmget.cc:40-65
+    soft = np.asarray(soft, dtype=np.float32)
+    if P.hard:
+        return (soft > 0).astype(np.float32)
+    mean = float(np.cumsum(np.abs(soft).astype(np.float64))[-1]) / len(soft)
+    return (0.5 * (soft.astype(np.float64) / mean + 1)).astype(np.float32)
+
+
+TYPE_BLOCK, TYPE_CLIP, TYPE_ALL = 0, 1, 2
+
+
+@dataclass
+class Pattern:
+    key: Key
+    time: float
+    bit_vec: list
+    decode_error: float
+    sync_score: Score
+    type: int
+    speed: float = 1.0
+    rating: float = 0.0
+
+    def approx_match(self, p):                       # wmget.cc:178-190
+        time_delta = 1024 / 44100.0
+        return (self.key == p.key and (abs(self.time - p.time) < time_delta or self.type == TYPE_ALL)
+                and self.bit_vec == p.bit_vec and self.sync_score.block_type == p.sync_score.block_type
+                and self.type == p.type and abs(self.speed - p.speed) < 0.01)
+
+    def block_str(self):
+        s = {A: "A", B: "B", AB: "AB"}[self.sync_score.block_type]
+        if self.type == TYPE_CLIP:
+            s = "CLIP-" + s
+        if self.speed != 1:
+            s += "-SPEED"
+        return s
+
+
+class ResultSet:                                     # wmget.cc:163-474
+    def __init__(self):
+        self.patterns = []
+        self.debug_sync = ""
+
+    def add_pattern(self, key, time, sync_score, bit_vec, decode_error, ptype, speed=1.0):
+        self.patterns.append(Pattern(key, time, list(bit_vec), np.float32(decode_error), sync_score, ptype, speed))
+
+    def apply_time_offset(self, off):
+        for p in self.patterns:
+            p.time += off
+
+    def merge(self, other):
+        for p in sorted(other.patterns, key=lambda p: p.time):
+            if not any(mp.approx_match(p) for mp in self.patterns):
+                self.patterns.append(p)
+        if not self.debug_sync:
+            self.debug_sync = other.debug_sync
+
+    def sort(self, key_list):
+        for key in key_list:
+            rating = {}
+            for p in self.patterns:
+                if p.key == key:
+                    bits = bit_vec_to_str(p.bit_vec)
+                    # map<string,float> accumulation (wmget.cc:184-200)
+                    rating[bits] = np.float32(float(rating.get(bits, 0.0)) + p.sync_score.quality * (2.0 if p.type == TYPE_ALL else 1.0))
+            for p in self.patterns:
+                if p.key == key:
+                    p.rating = float(rating[bit_vec_to_str(p.bit_vec)])
+        self.patterns.sort(key=lambda p: (p.key.name, -p.rating, 1 if p.type == TYPE_ALL else 0, p.time,
+                                          p.sync_score.block_type, bit_vec_to_str(p.bit_vec)))
+
+    def lines(self):                                 # print() wmget.cc:384-441
+        out, last_key = [], ""
+        for p in self.patterns:
+            if p.key.name != last_key:
+                out.append("key %s" % p.key.name)
+                last_key = p.key.name
+            if p.type == TYPE_ALL:
+                out.append("pattern   all %s %.3f %.3f%s" % (bit_vec_to_str(p.bit_vec), p.sync_score.quality, p.decode_error, " SPEED" if p.speed != 1 else ""))
+            else:
+                sec = int(p.time)
+                out.append("pattern %2d:%02d %s %.3f %.3f %s" % (sec // 60, sec % 60, bit_vec_to_str(p.bit_vec), p.sync_score.quality, p.decode_error, p.block_str()))
+        return out
+
+    def match_count(self, orig_bits):
+        return sum(1 for p in self.patterns if p.bit_vec == orig_bits)
+
+
+@dataclass
+class RawBits:
+    index: int
+    quality: float
+    raw: np.ndarray
+    block_type: int
+
+
+def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=44100, trace: dict | None = None):
+    """BlockDecoder::run (wmget.cc:502-706) for one key."""
+    sf = SyncFinder(P)
+    stages = {} if trace is not None else None
+    sync_scores = sf.search(key, samples, BLOCK, stages)
+    if trace is not None:
+        trace["sync_scores"] = sync_scores
+        trace["stages"] = stages
+    count = frames_per_block(P)
+    prv = []
+    for sc in sync_scores:
+        raw = raw_bits_for_block(key, samples, sc.index, P)
+        if raw is None:
+            continue
+        prv.append(RawBits(sc.index, sc.quality, raw, sc.block_type))
+        bits, err = conv_decode_soft(sc.block_type, normalize_soft_bits(raw, P))
+        result_set.add_pattern(key, sc.index / rate, sc, bits, err, TYPE_BLOCK)
+    if trace is not None:
+        trace["raw_bits"] = prv
+    # AB (:554-604)
+    for i in range(len(prv)):
+        if prv[i].block_type == B:
+            best_j, best_abs = -1, P.frame_size // 2
+            for j in range(i):
+                if prv[j].block_type == A:
+                    ad = abs(int(prv[i].index - prv[j].index) - count * P.frame_size)
+                    if ad < best_abs:
+                        best_j, best_abs = j, ad
+            if best_j >= 0:
+                a, b = prv[best_j], prv[i]
+                ab = np.empty(len(a.raw) * 2, dtype=np.float32)
+                ab[0::2], ab[1::2] = a.raw, b.raw
+                bits, err = conv_decode_soft(AB, normalize_soft_bits(ab, P))
+                result_set.add_pattern(key, b.index / rate, Score(b.index, (a.quality + b.quality) / 2, AB), bits, err, TYPE_BLOCK)
+    # all (:606-701)
+    best_all = []
+
+    def sync_sum(blocks):
+        s = np.float32(0)
+        for bi in blocks:
+            s = np.float32(float(s) + prv[bi].quality)
+        return s
+    for i in range(len(prv)):
+        max_block_idx = int(round_half_even(prv[-1].index / float(count * P.frame_size) + 0.5))
+        all_blocks = [i]
+        block_idx = 1
+        while block_idx <= max_block_idx:
+            expect_start = prv[all_blocks[-1]].index + block_idx * (count * P.frame_size)
+            best_j, best_abs = -1, block_idx * P.frame_size // 2
+            ebt = prv[all_blocks[-1]].block_type
+            if block_idx & 1:
+                ebt = B if ebt == A else A
+            for j in range(all_blocks[-1], len(prv)):
+                ad = abs(int(expect_start) - int(prv[j].index))
+                if ad < best_abs and prv[j].block_type == ebt:
+                    best_j, best_abs = j, ad
+            if best_j >= 0:
+                all_blocks.append(best_j)
+                block_idx = 1
+            else:
+                block_idx += 1
+        if sync_sum(all_blocks) > sync_sum(best_all):
+            best_all = all_blocks
+    if len(best_all) > 1:
+        raw_all = np.zeros(conv_code_size(AB, P.payload_size), dtype=np.float32)
+        norm = [0, 0]
+        q = 0.0
+        for bi in best_all:
+            p = prv[bi]
+            q += p.quality
+            ab = 1 if p.block_type == B else 0
+            raw_all[ab::2] = raw_all[ab::2] + p.raw
+            norm[ab] += 1
+        raw_all[0::2] = raw_all[0::2] / np.float32(max(norm[0], 1))
+        raw_all[1::2] = raw_all[1::2] / np.float32(max(norm[1], 1))
+        q /= norm[0] + norm[1]
+        bits, err = conv_decode_soft(AB, normalize_soft_bits(raw_all, P))
+        result_set.add_pattern(key, 0.0, Score(0, q, A), bits, err, TYPE_ALL)
+    return sync_scores
+
+
+def round_half_even(x):
+    return np.rint(x)     # lrint with the default rounding mode
+
+
+def clip_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=44100):
+    """ClipDecoder::run (wmget.cc:764-884) for one key."""
+    fpb = frames_per_block(P)
+    n, nch = samples.shape
+    wav_frames = (n * nch) // (P.frame_size * nch)
+    if not wav_frames < fpb * 3.1:
+        return
+    nvals = n * nch
+    flat = samples.reshape(-1)
+    npad = (fpb + 5) * P.frame_size * nch
+    for pos in ("START", "END"):
+        pad_start = pad_end = npad
+        if pos == "START":
+            first, last = 0, min(npad, nvals)
+            if last < npad:
+                pad_start += npad - last
+        else:
+            if nvals <= npad:
+                continue
+            first, last = nvals - npad, nvals
+        time_offset = float(first) / rate / nch
+        ext = np.concatenate([np.zeros(pad_start, np.float32), flat[first:last], np.zeros(pad_end, np.float32)]).reshape(-1, nch)
+        sf = SyncFinder(P)
+        for sc in sf.search(key, ext, CLIP):
+            r1 = raw_bits_for_block(key, ext, sc.index, P)
+            r2 = raw_bits_for_block(key, ext, sc.index + fpb * P.frame_size, P)
+            if r1 is None or r2 is None:
+                continue
+            raw = np.empty(len(r1) * 2, dtype=np.float32)
+            if sc.block_type == A:
+                raw[0::2], raw[1::2] = r1, r2
+            else:
+                raw[0::2], raw[1::2] = r2, r1
+            bits, err = conv_decode_soft(AB, normalize_soft_bits(raw, P))
+            result_set.add_pattern(key, time_offset, Score(int(time_offset * rate), sc.quality, sc.block_type), bits, err, TYPE_CLIP)
+
+
+def chunk_ranges(n_frames: int, P: Params, rate=44100):
+    """WavChunkLoader (wavchunkloader.cc:54-163) for a file of known length at 44.1 kHz:
+    yields (first_frame, n_frames_in_chunk, time_offset)."""
+    max_frames = int(np.rint(P.get_chunk_size * 60 * rate))
+    overlap = int(np.rint(2 * (frames_per_block(P) * P.frame_size / float(P.mark_sample_rate)) * 1.3 * rate))
+    out, start, time_offset = [], 0, 0.0
+    have = min(max_frames, n_frames)
+    if have == 0:
+        return out
+    out.append((0, have, 0.0))
+    end = have
+    # the loader reaches EOF only when a refill returns nothing: a file that exactly fills the
+    # chunk produces one more (overlap-only) chunk, like the reference.
+    eof = have < max_frames
+    while not eof:
+        time_offset += (end - start - overlap) / float(rate)
+        start = end - overlap
+        new_end = min(start + max_frames, n_frames)
+        eof = (new_end - start) < max_frames
+        end = new_end
+        out.append((start, end - start, time_offset))
+    return out
+
+
+def get_watermark(samples, key_list, P: Params | None = None, rate=44100) -> ResultSet:
+    """get_watermark / decode (wmget.cc:886-939,971-1013) without speed detection."""
+    P = P or Params()
+    samples = np.ascontiguousarray(samples, dtype=np.float32)
+    rs = ResultSet()
+    first = True
+    for start, cnt, toff in chunk_ranges(samples.shape[0], P, rate):
+        chunk = samples[start:start + cnt]
+        crs = ResultSet()
+        for key in key_list:
+            block_decoder_run(key, chunk, crs, P, rate)
+        if first:
+            for key in key_list:
+                clip_decoder_run(key, chunk, crs, P, rate)
+        crs.apply_time_offset(toff)
+        rs.merge(crs)
+        first = False
+    rs.sort(key_list)
+    return rs
