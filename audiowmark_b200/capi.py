@@ -1,0 +1,192 @@
+"""ctypes binding of the C ABI (include/awm_b200.h) exported by lib/libawm_b200.so.
+
+Thin by design: arguments are numpy arrays (host) or raw device pointers (ints, e.g.
+torch.Tensor.data_ptr()).  Nothing here computes; if the CUDA library is missing or no
+device is usable every call fails loudly -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libawm_b200.so")
+
+FRAME = 1024
+N_BANDS = 81
+MODE_BLOCK, MODE_CLIP = 0, 1
+BLOCK_A, BLOCK_B, BLOCK_AB = 0, 1, 2
+
+SYNC_ENTRY = np.dtype([("frame", "<u2"), ("up", "u1", (30,)), ("down", "u1", (30,))])       # awm_sync_entry
+MIX_ENTRY = np.dtype([("frame", "<u2"), ("up", "u1"), ("down", "u1")])                      # awm_mix_entry
+SEARCH_SCORE = np.dtype([("index", "<u8"), ("raw_quality", "<f8"), ("local_mean", "<f8")])  # awm_search_score
+
+EXPORTS = [
+    "awm_create", "awm_destroy", "awm_last_error", "awm_launch_count", "awm_stream", "awm_synchronize",
+    "awm_fft_r2c", "awm_fft_c2r", "awm_set_embed_tables", "awm_set_sync_tables", "awm_set_mix_tables",
+    "awm_pcm_bind", "awm_embed", "awm_sync_approx", "awm_sync_refine", "awm_decode_blocks", "awm_viterbi",
+]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the CUDA extension is mandatory, there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.awm_last_error.restype = ctypes.c_char_p
+        lib.awm_launch_count.restype = ctypes.c_uint64
+        lib.awm_stream.restype = ctypes.c_void_p
+        _lib = lib
+    return _lib
+
+
+def _ptr(x):
+    """numpy array -> host pointer, int -> device pointer."""
+    if x is None:
+        return ctypes.c_void_p(0)
+    if isinstance(x, (int, np.integer)):
+        return ctypes.c_void_p(int(x))
+    assert x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data_as(ctypes.c_void_p)
+
+
+class AwmError(RuntimeError):
+    pass
+
+
+class Context:
+    """One awm_ctx (device + stream)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = ctypes.c_void_p()
+        rc = self.lib.awm_create(ctypes.c_int(device), ctypes.byref(h))
+        if rc != 0 or not h:
+            raise AwmError("awm_create failed (rc=%d): no usable CUDA device; this package has no CPU fallback" % rc)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.awm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise AwmError(self.lib.awm_last_error(self.h).decode())
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.awm_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.awm_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._ck(self.lib.awm_synchronize(self.h))
+
+    # ---- FFTProcessor
+    def fft_r2c(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, FRAME)
+        out = np.empty((x.shape[0], FRAME + 2), np.float32)
+        self._ck(self.lib.awm_fft_r2c(self.h, _ptr(x), _ptr(out), ctypes.c_size_t(x.shape[0]), ctypes.c_int(FRAME)))
+        return out.view(np.complex64)
+
+    def fft_c2r(self, spec: np.ndarray) -> np.ndarray:
+        s = np.ascontiguousarray(spec, np.complex64).reshape(-1, FRAME // 2 + 1).view(np.float32)
+        out = np.empty((s.shape[0], FRAME), np.float32)
+        self._ck(self.lib.awm_fft_c2r(self.h, _ptr(s), _ptr(out), ctypes.c_size_t(s.shape[0]), ctypes.c_int(FRAME)))
+        return out
+
+    # ---- tables
+    def set_embed_tables(self, frame_mod_ab: np.ndarray):
+        fm = np.ascontiguousarray(frame_mod_ab, np.uint8)
+        assert fm.ndim == 3 and fm.shape[0] == 2 and fm.shape[2] == 101
+        self._ck(self.lib.awm_set_embed_tables(self.h, _ptr(fm), ctypes.c_int(fm.shape[1])))
+
+    def set_sync_tables(self, key_slot: int, mode: int, entries: np.ndarray, bit_offsets: np.ndarray):
+        e = np.ascontiguousarray(entries, SYNC_ENTRY)
+        off = np.ascontiguousarray(bit_offsets, np.int32)
+        self._ck(self.lib.awm_set_sync_tables(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), _ptr(e), ctypes.c_int(len(e)),
+                                              _ptr(off), ctypes.c_int(len(off) - 1)))
+
+    def set_mix_tables(self, key_slot: int, entries: np.ndarray, bit_order: np.ndarray, frames_per_bit: int, frames_per_block: int):
+        e = np.ascontiguousarray(entries, MIX_ENTRY)
+        o = np.ascontiguousarray(bit_order, np.uint16)
+        self._ck(self.lib.awm_set_mix_tables(self.h, ctypes.c_int(key_slot), _ptr(e), ctypes.c_int(len(e)), _ptr(o), ctypes.c_int(len(o)),
+                                             ctypes.c_int(frames_per_bit), ctypes.c_int(frames_per_block)))
+
+    # ---- PCM
+    def pcm_bind(self, pcm, n_frames: int | None = None, channels: int | None = None, pad_start: int = 0, pad_end: int = 0):
+        if isinstance(pcm, np.ndarray):
+            pcm = np.ascontiguousarray(pcm, np.float32)
+            n_frames, channels = pcm.shape
+            self._keep = pcm
+        self._ck(self.lib.awm_pcm_bind(self.h, _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
+                                       ctypes.c_size_t(pad_start), ctypes.c_size_t(pad_end)))
+        self.synchronize()
+
+    # ---- embed
+    def embed(self, pcm_in, pcm_out=None, n_frames=None, channels=None, first_frame_number=0, frames_pad_start=250,
+              water_delta=0.01, limiter_block=44100, limiter_ceiling=0.99, want_snr=False):
+        if isinstance(pcm_in, np.ndarray):
+            pcm_in = np.ascontiguousarray(pcm_in, np.float32)
+            n_frames, channels = pcm_in.shape
+            if pcm_out is None:
+                pcm_out = np.empty_like(pcm_in)
+        snr = (ctypes.c_double * 2)()
+        self._ck(self.lib.awm_embed(self.h, _ptr(pcm_in), _ptr(pcm_out), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
+                                    ctypes.c_uint64(first_frame_number), ctypes.c_int(frames_pad_start), ctypes.c_double(water_delta),
+                                    ctypes.c_int(limiter_block), ctypes.c_float(limiter_ceiling), snr if want_snr else None))
+        return (pcm_out, (snr[0], snr[1])) if want_snr else pcm_out
+
+    # ---- sync
+    def sync_approx(self, key_slot=0, mode=MODE_BLOCK, wav_first=0, wav_last=None, water_delta=0.01) -> np.ndarray:
+        if wav_last is None:
+            wav_last = 0xFFFFFFFFFFFFFFF
+        n = ctypes.c_size_t()
+        self._ck(self.lib.awm_sync_approx(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), ctypes.c_uint64(wav_first), ctypes.c_uint64(wav_last),
+                                          ctypes.c_double(water_delta), None, ctypes.c_size_t(0), ctypes.byref(n)))
+        out = np.zeros(n.value, SEARCH_SCORE)
+        if n.value:
+            self._ck(self.lib.awm_sync_approx(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), ctypes.c_uint64(wav_first), ctypes.c_uint64(wav_last),
+                                              ctypes.c_double(water_delta), _ptr(out), ctypes.c_size_t(n.value), ctypes.byref(n)))
+        return out
+
+    def sync_refine(self, scores: np.ndarray, key_slot=0, mode=MODE_BLOCK, wav_first=0, wav_last=None, water_delta=0.01) -> np.ndarray:
+        if wav_last is None:
+            wav_last = 0xFFFFFFFFFFFFFFF
+        s = np.ascontiguousarray(scores, SEARCH_SCORE).copy()
+        self._ck(self.lib.awm_sync_refine(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), ctypes.c_uint64(wav_first), ctypes.c_uint64(wav_last),
+                                          ctypes.c_double(water_delta), _ptr(s), ctypes.c_size_t(len(s))))
+        return s
+
+    # ---- decode
+    def decode_blocks(self, indices, n_coded: int, key_slot=0):
+        idx = np.ascontiguousarray(indices, np.uint64)
+        raw = np.zeros((len(idx), n_coded), np.float32)
+        valid = np.zeros(len(idx), np.int32)
+        self._ck(self.lib.awm_decode_blocks(self.h, ctypes.c_int(key_slot), _ptr(idx), ctypes.c_size_t(len(idx)), _ptr(raw), _ptr(valid)))
+        return raw, valid
+
+    def viterbi(self, raw_bits: np.ndarray, block_types, hard=False):
+        raw = np.ascontiguousarray(raw_bits, np.float32)
+        if raw.ndim == 1:
+            raw = raw[None]
+        bt = np.ascontiguousarray(block_types, np.int32).reshape(-1)
+        n_jobs, n_coded = raw.shape
+        rate = 12 if bt[0] == BLOCK_AB else 6
+        n_msg = n_coded // rate - 15
+        bits = np.zeros((n_jobs, n_msg), np.uint8)
+        err = np.zeros(n_jobs, np.float32)
+        self._ck(self.lib.awm_viterbi(self.h, _ptr(raw), ctypes.c_size_t(n_jobs), ctypes.c_int(n_coded), _ptr(bt), ctypes.c_int(1 if hard else 0),
+                                      _ptr(bits), _ptr(err)))
+        return bits, err

@@ -1,0 +1,759 @@
+// awm_capi.cu -- implementation of the C ABI declared in include/awm_b200.h.
+//
+// One context = one device + one stream + growable device buffers.  Host pointers are staged
+// through context-owned device memory; device pointers are used in place.  There is no CPU
+// fallback: every entry point launches the sm_100a kernels of awm_kernels.cuh or fails.
+#include "awm_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace awm;
+
+namespace {
+
+struct DevBuf
+{
+  void  *p = nullptr;
+  size_t cap = 0;
+  cudaError_t
+  reserve (size_t bytes)
+  {
+    if (bytes <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFree (p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc (&p, want);
+    if (e == cudaSuccess)
+      cap = want;
+    return e;
+  }
+  void
+  release()
+  {
+    if (p)
+      cudaFree (p);
+    p = nullptr;
+    cap = 0;
+  }
+  template<class T> T *as() { return static_cast<T *> (p); }
+};
+
+struct SyncTab
+{
+  DevBuf ent, off;
+  int n_ent = 0, n_bits = 0, total_frames = 0;
+  std::vector<awm_sync_entry> h_ent;
+  std::vector<int> h_off;
+};
+
+struct KeyTab
+{
+  SyncTab sync[2];
+  DevBuf mix, order;
+  int n_mix = 0, n_coded = 0, frames_per_bit = 0, fpb = 0;
+};
+
+} // namespace
+
+struct awm_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+
+  DevBuf tw, win, synth;             // constant tables
+  DevBuf frame_mod; int embed_fpb = 0;
+  KeyTab keys[AWM_MAX_KEYS];
+
+  // bound PCM
+  const float *pcm = nullptr; size_t pcm_frames = 0; int pcm_ch = 0;
+  DevBuf pcm_own;
+
+  DevBuf dbT, have, q, scores;       // approx
+  DevBuf cand_start, cand_noff, S, Hv, rq, rvalid;   // refine
+  DevBuf blk_start, D, raw;          // decode
+  DevBuf vit_raw, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
+  DevBuf emb_in, emb_out, peaks, snr;
+};
+
+namespace {
+
+int
+fail (awm_ctx *ctx, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start (ap, fmt);
+  vsnprintf (buf, sizeof (buf), fmt, ap);
+  va_end (ap);
+  if (ctx)
+    ctx->err = buf;
+  return 1;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail (ctx, "%s: %s", #call, cudaGetErrorString (e_)); } while (0)
+#define LAUNCH_CHECK(name) do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail (ctx, "launch %s: %s", name, cudaGetErrorString (e_)); } while (0)
+
+bool
+is_device_ptr (const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes (&a, p) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return false;
+    }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+double
+window_cos (double x)    // von Hann, reference src/wmcommon.hh:187-193
+{
+  if (fabs (x) > 1)
+    return 0;
+  return 0.5 * cos (x * M_PI) + 0.5;
+}
+
+int
+init_tables (awm_ctx *ctx)
+{
+  // twiddles exp(-2 pi i k1 t / 1024) at [k1*32 + t]
+  std::vector<float2> tw (1024);
+  for (int k1 = 0; k1 < 32; k1++)
+    for (int t = 0; t < 32; t++)
+      {
+        const double a = -2.0 * M_PI * double (k1 * t) / 1024.0;
+        tw[k1 * 32 + t] = make_float2 (float (cos (a)), float (sin (a)));
+      }
+  // FFTAnalyzer::gen_normalized_window (src/wmcommon.cc:68-89)
+  std::vector<float> win (kFrame);
+  double weight = 0;
+  for (int i = 0; i < kFrame; i++)
+    {
+      const double w = window_cos ((i - kFrame / 2.0) / (kFrame / 2.0));
+      win[i] = w;
+      weight += w;
+    }
+  for (int i = 0; i < kFrame; i++)
+    win[i] *= 2.0 / weight;
+  // WatermarkSynth::generate_window (src/wmadd.cc:177-206)
+  std::vector<float> synth (3 * kFrame);
+  for (int i = 0; i < 3 * kFrame; i++)
+    {
+      const double overlap = 0.1;
+      double norm_pos = (double (i) - kFrame) / kFrame;
+      if (norm_pos > 0.5)
+        norm_pos = 1 - norm_pos;
+      double tri;
+      if (norm_pos < -overlap)
+        tri = 0;
+      else if (norm_pos < overlap)
+        tri = 0.5 + norm_pos / (2 * overlap);
+      else
+        tri = 1;
+      synth[i] = (cos (tri * M_PI + M_PI) + 1) * 0.5;
+    }
+  CK (ctx->tw.reserve (tw.size() * sizeof (float2)));
+  CK (ctx->win.reserve (win.size() * sizeof (float)));
+  CK (ctx->synth.reserve (synth.size() * sizeof (float)));
+  CK (cudaMemcpy (ctx->tw.p, tw.data(), tw.size() * sizeof (float2), cudaMemcpyHostToDevice));
+  CK (cudaMemcpy (ctx->win.p, win.data(), win.size() * sizeof (float), cudaMemcpyHostToDevice));
+  CK (cudaMemcpy (ctx->synth.p, synth.data(), synth.size() * sizeof (float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+template<class K> int
+set_smem (awm_ctx *ctx, K kernel, size_t bytes)
+{
+  CK (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int (bytes)));
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int
+awm_create (int device, awm_ctx **out)
+{
+  if (!out)
+    return 1;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount (&n_dev) != cudaSuccess || n_dev <= 0)
+    return 2;          // no CUDA device: the product has no CPU fallback
+  if (device < 0 || device >= n_dev)
+    return 3;
+  awm_ctx *ctx = new awm_ctx();
+  ctx->device = device;
+  if (cudaSetDevice (device) != cudaSuccess || cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+      delete ctx;
+      return 4;
+    }
+  if (init_tables (ctx))
+    {
+      fprintf (stderr, "awm_create: %s\n", ctx->err.c_str());
+      delete ctx;
+      return 5;
+    }
+  *out = ctx;
+  return 0;
+}
+
+void
+awm_destroy (awm_ctx *ctx)
+{
+  if (!ctx)
+    return;
+  cudaSetDevice (ctx->device);
+  cudaStreamSynchronize (ctx->stream);
+  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores,
+                     &ctx->cand_start, &ctx->cand_noff, &ctx->S, &ctx->Hv, &ctx->rq, &ctx->rvalid, &ctx->blk_start, &ctx->D, &ctx->raw,
+                     &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
+                     &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr };
+  for (DevBuf *b : bufs)
+    b->release();
+  for (KeyTab& k : ctx->keys)
+    {
+      for (SyncTab& s : k.sync)
+        {
+          s.ent.release();
+          s.off.release();
+        }
+      k.mix.release();
+      k.order.release();
+    }
+  cudaStreamDestroy (ctx->stream);
+  delete ctx;
+}
+
+const char *
+awm_last_error (const awm_ctx *ctx)
+{
+  return ctx ? ctx->err.c_str() : "no context (is a CUDA device present? there is no CPU fallback)";
+}
+
+uint64_t
+awm_launch_count (const awm_ctx *ctx)
+{
+  return ctx ? ctx->launches : 0;
+}
+
+void *
+awm_stream (awm_ctx *ctx)
+{
+  return ctx ? (void *) ctx->stream : nullptr;
+}
+
+int
+awm_synchronize (awm_ctx *ctx)
+{
+  CK (cudaSetDevice (ctx->device));
+  CK (cudaStreamSynchronize (ctx->stream));
+  return 0;
+}
+
+/* ---------------------------------------------------------------- FFTProcessor */
+
+static int
+fft_batch (awm_ctx *ctx, const float *in, float *out, size_t count, int n, bool inverse)
+{
+  if (n != kFrame)
+    return fail (ctx, "awm_fft: only n = 1024 is supported (got %d)", n);
+  if (count == 0)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  const size_t in_elems = count * (inverse ? kFrame + 2 : kFrame), out_elems = count * (inverse ? kFrame : kFrame + 2);
+  const float *d_in = in;
+  float *d_out = out;
+  const bool in_dev = is_device_ptr (in), out_dev = is_device_ptr (out);
+  if (!in_dev)
+    {
+      CK (ctx->emb_in.reserve (in_elems * sizeof (float)));
+      CK (cudaMemcpyAsync (ctx->emb_in.p, in, in_elems * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
+      d_in = ctx->emb_in.as<float>();
+    }
+  if (!out_dev)
+    {
+      CK (ctx->emb_out.reserve (out_elems * sizeof (float)));
+      d_out = ctx->emb_out.as<float>();
+    }
+  const size_t smem = fft_smem_bytes (kFftWarps);
+  const unsigned grid = unsigned (((count + 1) / 2 + kFftWarps - 1) / kFftWarps);
+  if (inverse)
+    {
+      if (set_smem (ctx, k_fft_c2r, smem)) return 1;
+      k_fft_c2r<<<grid, kFftWarps * 32, smem, ctx->stream>>> (d_in, d_out, (long long) count, ctx->tw.as<float2>());
+    }
+  else
+    {
+      if (set_smem (ctx, k_fft_r2c, smem)) return 1;
+      k_fft_r2c<<<grid, kFftWarps * 32, smem, ctx->stream>>> (d_in, d_out, (long long) count, ctx->tw.as<float2>());
+    }
+  LAUNCH_CHECK ("k_fft");
+  if (!out_dev)
+    CK (cudaMemcpyAsync (out, d_out, out_elems * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  return 0;
+}
+
+int awm_fft_r2c (awm_ctx *ctx, const float *in, float *out, size_t count, int n) { return fft_batch (ctx, in, out, count, n, false); }
+int awm_fft_c2r (awm_ctx *ctx, const float *in, float *out, size_t count, int n) { return fft_batch (ctx, in, out, count, n, true); }
+
+/* ---------------------------------------------------------------- tables */
+
+int
+awm_set_embed_tables (awm_ctx *ctx, const uint8_t *frame_mod_ab, int frames_per_block)
+{
+  if (!frame_mod_ab || frames_per_block <= 0)
+    return fail (ctx, "awm_set_embed_tables: bad arguments");
+  CK (cudaSetDevice (ctx->device));
+  const size_t bytes = size_t (2) * frames_per_block * (kMaxBand + 1);
+  CK (ctx->frame_mod.reserve (bytes));
+  CK (cudaMemcpyAsync (ctx->frame_mod.p, frame_mod_ab, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  ctx->embed_fpb = frames_per_block;
+  return 0;
+}
+
+int
+awm_set_sync_tables (awm_ctx *ctx, int key_slot, int mode, const awm_sync_entry *entries, int n_entries,
+                     const int *bit_offsets, int n_bits)
+{
+  if (key_slot < 0 || key_slot >= AWM_MAX_KEYS || mode < 0 || mode > 1 || !entries || n_entries <= 0 || !bit_offsets || n_bits <= 0)
+    return fail (ctx, "awm_set_sync_tables: bad arguments");
+  if (bit_offsets[0] != 0 || bit_offsets[n_bits] != n_entries)
+    return fail (ctx, "awm_set_sync_tables: bit_offsets must run from 0 to n_entries");
+  for (int i = 0; i < n_entries; i++)
+    for (int j = 0; j < kUD; j++)
+      if (entries[i].up[j] >= kBands || entries[i].down[j] >= kBands)
+        return fail (ctx, "awm_set_sync_tables: band index out of range");
+  CK (cudaSetDevice (ctx->device));
+  SyncTab& t = ctx->keys[key_slot].sync[mode];
+  CK (t.ent.reserve (sizeof (awm_sync_entry) * n_entries));
+  CK (t.off.reserve (sizeof (int) * (n_bits + 1)));
+  CK (cudaMemcpyAsync (t.ent.p, entries, sizeof (awm_sync_entry) * n_entries, cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaMemcpyAsync (t.off.p, bit_offsets, sizeof (int) * (n_bits + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  t.n_ent = n_entries;
+  t.n_bits = n_bits;
+  t.h_ent.assign (entries, entries + n_entries);
+  t.h_off.assign (bit_offsets, bit_offsets + n_bits + 1);
+  return 0;
+}
+
+int
+awm_set_mix_tables (awm_ctx *ctx, int key_slot, const awm_mix_entry *entries, int n_entries,
+                    const uint16_t *bit_order, int n_coded_bits, int frames_per_bit, int frames_per_block)
+{
+  if (key_slot < 0 || key_slot >= AWM_MAX_KEYS || !entries || !bit_order || n_coded_bits <= 0 || frames_per_bit <= 0
+      || n_entries != n_coded_bits * frames_per_bit * kUD || frames_per_block <= 0)
+    return fail (ctx, "awm_set_mix_tables: bad arguments");
+  for (int i = 0; i < n_entries; i++)
+    if (entries[i].frame >= frames_per_block || entries[i].up < kMinBand || entries[i].up > kMaxBand
+        || entries[i].down < kMinBand || entries[i].down > kMaxBand)
+      return fail (ctx, "awm_set_mix_tables: entry %d out of range", i);
+  for (int i = 0; i < n_coded_bits; i++)
+    if (bit_order[i] >= n_coded_bits)
+      return fail (ctx, "awm_set_mix_tables: bit_order out of range");
+  CK (cudaSetDevice (ctx->device));
+  KeyTab& k = ctx->keys[key_slot];
+  CK (k.mix.reserve (sizeof (awm_mix_entry) * n_entries));
+  CK (k.order.reserve (sizeof (uint16_t) * n_coded_bits));
+  CK (cudaMemcpyAsync (k.mix.p, entries, sizeof (awm_mix_entry) * n_entries, cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaMemcpyAsync (k.order.p, bit_order, sizeof (uint16_t) * n_coded_bits, cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  k.n_mix = n_entries;
+  k.n_coded = n_coded_bits;
+  k.frames_per_bit = frames_per_bit;
+  k.fpb = frames_per_block;
+  return 0;
+}
+
+/* ---------------------------------------------------------------- PCM */
+
+int
+awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end)
+{
+  if (channels <= 0 || (!pcm && n_frames))
+    return fail (ctx, "awm_pcm_bind: bad arguments");
+  CK (cudaSetDevice (ctx->device));
+  const bool dev = pcm && is_device_ptr (pcm);
+  if (dev && pad_start == 0 && pad_end == 0)
+    {
+      ctx->pcm = pcm;
+    }
+  else
+    {
+      const size_t total = (pad_start + n_frames + pad_end) * channels;
+      CK (ctx->pcm_own.reserve (std::max<size_t> (total, 1) * sizeof (float)));
+      float *d = ctx->pcm_own.as<float>();
+      if (pad_start)
+        CK (cudaMemsetAsync (d, 0, pad_start * channels * sizeof (float), ctx->stream));
+      if (n_frames)
+        CK (cudaMemcpyAsync (d + pad_start * channels, pcm, n_frames * channels * sizeof (float),
+                             dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+      if (pad_end)
+        CK (cudaMemsetAsync (d + (pad_start + n_frames) * channels, 0, pad_end * channels * sizeof (float), ctx->stream));
+      ctx->pcm = d;
+    }
+  ctx->pcm_frames = pad_start + n_frames + pad_end;
+  ctx->pcm_ch = channels;
+  return 0;
+}
+
+/* ---------------------------------------------------------------- embed */
+
+int
+awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels,
+           uint64_t first_frame_number, int frames_pad_start, double water_delta,
+           int limiter_block, float limiter_ceiling, double *snr_power)
+{
+  if (!ctx->embed_fpb)
+    return fail (ctx, "awm_embed: awm_set_embed_tables has not been called");
+  if (channels <= 0 || (n_frames && (!in || !out)))
+    return fail (ctx, "awm_embed: bad arguments");
+  if (snr_power)
+    snr_power[0] = snr_power[1] = 0;
+  if (n_frames == 0)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  const size_t n_val = n_frames * channels;
+  const bool in_dev = is_device_ptr (in), out_dev = is_device_ptr (out);
+  const float *d_in = in;
+  float *d_out = out;
+  if (!in_dev)
+    {
+      CK (ctx->emb_in.reserve (n_val * sizeof (float)));
+      CK (cudaMemcpyAsync (ctx->emb_in.p, in, n_val * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
+      d_in = ctx->emb_in.as<float>();
+    }
+  if (!out_dev)
+    {
+      CK (ctx->emb_out.reserve (n_val * sizeof (float)));
+      d_out = ctx->emb_out.as<float>();
+    }
+  const long long n_real = (long long) ((n_frames + kFrame - 1) / kFrame);
+  const long long n_proc = n_real + 1;
+  long long n_blocks = 0;
+  if (limiter_block > 0)
+    {
+      n_blocks = (n_proc * kFrame + limiter_block - 1) / limiter_block + 1;
+      CK (ctx->peaks.reserve (n_blocks * sizeof (unsigned)));
+      CK (cudaMemsetAsync (ctx->peaks.p, 0, n_blocks * sizeof (unsigned), ctx->stream));
+    }
+  if (snr_power)
+    {
+      CK (ctx->snr.reserve (2 * sizeof (double)));
+      CK (cudaMemsetAsync (ctx->snr.p, 0, 2 * sizeof (double), ctx->stream));
+    }
+  EmbedArgs A;
+  A.in = d_in;
+  A.out = d_out;
+  A.n_frames = (long long) n_frames;
+  A.C = channels;
+  A.n_proc = n_proc;
+  A.fpb = ctx->embed_fpb;
+  A.frame_number0 = (long long) (first_frame_number % (2ull * A.fpb)) + 2LL * A.fpb - frames_pad_start;
+  A.frame_mod = ctx->frame_mod.as<uint8_t>();
+  A.pow_up = float (-water_delta * 1);       // powf (mag, -Params::water_delta * data_bit_sign), src/wmadd.cc:79
+  A.pow_down = float (-water_delta * -1);
+  A.limiter_block = limiter_block;
+  A.peaks = ctx->peaks.as<unsigned>();
+  A.snr = snr_power ? ctx->snr.as<double>() : nullptr;
+  A.tw = ctx->tw.as<float2>();
+  A.win = ctx->win.as<float>();
+  A.synth = ctx->synth.as<float>();
+  const size_t smem = fft_smem_bytes (kEmbedWarps) + 3 * kFrame * sizeof (float) + 2 * size_t (kEmbedWarps) * kEdge * sizeof (float2);
+  if (set_smem (ctx, k_embed, smem)) return 1;
+  const unsigned grid = unsigned ((n_proc + kEmbedTile - 1) / kEmbedTile);
+  k_embed<<<grid, kEmbedWarps * 32, smem, ctx->stream>>> (A);
+  LAUNCH_CHECK ("k_embed");
+  if (limiter_block > 0)
+    {
+      const unsigned g2 = unsigned ((n_frames + 255) / 256);
+      k_limiter<<<g2, 256, 0, ctx->stream>>> (d_out, (long long) n_frames, channels, limiter_block, limiter_ceiling,
+                                              ctx->peaks.as<unsigned>(), n_blocks);
+      LAUNCH_CHECK ("k_limiter");
+    }
+  if (!out_dev)
+    CK (cudaMemcpyAsync (out, d_out, n_val * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (snr_power)
+    CK (cudaMemcpyAsync (snr_power, ctx->snr.p, 2 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!out_dev || snr_power)
+    CK (cudaStreamSynchronize (ctx->stream));
+  return 0;
+}
+
+/* ---------------------------------------------------------------- sync search */
+
+int
+awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
+                 double water_delta, awm_search_score *scores_out, size_t max_scores, size_t *n_scores)
+{
+  if (key_slot < 0 || key_slot >= AWM_MAX_KEYS || mode < 0 || mode > 1 || !n_scores)
+    return fail (ctx, "awm_sync_approx: bad arguments");
+  SyncTab& t = ctx->keys[key_slot].sync[mode];
+  const int fpb = ctx->keys[key_slot].fpb;
+  if (!t.n_ent || !fpb)
+    return fail (ctx, "awm_sync_approx: tables for key slot %d / mode %d not set", key_slot, mode);
+  if (!ctx->pcm_ch)
+    return fail (ctx, "awm_sync_approx: no PCM bound");
+  CK (cudaSetDevice (ctx->device));
+  const int total = fpb * (mode == AWM_MODE_CLIP ? 2 : 1);
+  const long long fc = (long long) (ctx->pcm_frames / kFrame);           // frame_count (wav_data)
+  const long long n_out = fc > 0 ? fc - 1 : 0;                           // sync_fft_parallel: frame_count - 1 frames per shift
+  const long long n_starts = fc - total - 1 > 0 ? fc - total - 1 : 0;    // (start + total) * n_bands < fft_db.size()
+  *n_scores = size_t (n_starts) * 4;
+  if (!scores_out || n_starts == 0)
+    return 0;
+  if (max_scores < size_t (n_starts) * 4)
+    return fail (ctx, "awm_sync_approx: scores_out too small (%zu < %lld)", max_scores, n_starts * 4);
+  const int ld = int ((n_out + 31) / 32 * 32);
+  CK (ctx->dbT.reserve (size_t (4) * kBands * ld * sizeof (float)));
+  CK (ctx->have.reserve (size_t (4) * ld));
+  CK (ctx->q.reserve (size_t (n_starts) * 4 * sizeof (double)));
+  CK (ctx->scores.reserve (size_t (n_starts) * 4 * sizeof (awm_search_score)));
+  {
+    const size_t smem = fft_smem_bytes (kStftWarps) + kBands * (kStftWarps + 1) * sizeof (float);
+    if (set_smem (ctx, k_stft_db, smem)) return 1;
+    dim3 grid (unsigned ((n_out + kStftWarps - 1) / kStftWarps), 4);
+    k_stft_db<<<grid, kStftWarps * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
+                                                            ctx->dbT.as<float>(), ctx->have.as<unsigned char>(),
+                                                            (long long) wav_first, (long long) wav_last,
+                                                            ctx->tw.as<float2>(), ctx->win.as<float>());
+    LAUNCH_CHECK ("k_stft_db");
+  }
+  const double norm_div = water_delta < 0.080 ? water_delta : 0.080;     // normalize_sync_quality, src/syncfinder.cc:90
+  {
+    const size_t smem = sizeof (awm_sync_entry) * t.n_ent;
+    dim3 grid (unsigned ((n_starts + kApproxThreads - 1) / kApproxThreads), 4);
+    if (mode == AWM_MODE_CLIP)
+      {
+        if (set_smem (ctx, k_sync_approx<true>, smem)) return 1;
+        k_sync_approx<true><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_starts),
+                                                                        t.ent.as<awm_sync_entry>(), t.n_ent, t.off.as<int>(), t.n_bits,
+                                                                        norm_div, ctx->q.as<double>());
+      }
+    else
+      {
+        if (set_smem (ctx, k_sync_approx<false>, smem)) return 1;
+        k_sync_approx<false><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_starts),
+                                                                         t.ent.as<awm_sync_entry>(), t.n_ent, t.off.as<int>(), t.n_bits,
+                                                                         norm_div, ctx->q.as<double>());
+      }
+    LAUNCH_CHECK ("k_sync_approx");
+  }
+  {
+    const long long n = n_starts * 4;
+    k_local_mean<<<unsigned ((n + 255) / 256), 256, 0, ctx->stream>>> (ctx->q.as<double>(), n, ctx->scores.as<awm_search_score>());
+    LAUNCH_CHECK ("k_local_mean");
+  }
+  CK (cudaMemcpyAsync (scores_out, ctx->scores.p, size_t (n_starts) * 4 * sizeof (awm_search_score), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  return 0;
+}
+
+int
+awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
+                 double water_delta, awm_search_score *scores, size_t n_scores)
+{
+  if (key_slot < 0 || key_slot >= AWM_MAX_KEYS || mode < 0 || mode > 1 || (n_scores && !scores))
+    return fail (ctx, "awm_sync_refine: bad arguments");
+  SyncTab& t = ctx->keys[key_slot].sync[mode];
+  const int fpb = ctx->keys[key_slot].fpb;
+  if (!t.n_ent || !fpb)
+    return fail (ctx, "awm_sync_refine: tables for key slot %d / mode %d not set", key_slot, mode);
+  if (!ctx->pcm_ch)
+    return fail (ctx, "awm_sync_refine: no PCM bound");
+  if (n_scores == 0)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  const int total = fpb * (mode == AWM_MODE_CLIP ? 2 : 1);
+  const double norm_div = water_delta < 0.080 ? water_delta : 0.080;
+
+  // bound the scratch (S is n_cand * n_ent * 60 * 72 floats): process candidates in batches
+  const size_t per_cand = size_t (t.n_ent) * 60 * kOffPad * sizeof (float);
+  size_t batch = std::max<size_t> (1, (size_t (3) << 30) / per_cand);
+  batch = std::min (batch, n_scores);
+  CK (ctx->S.reserve (batch * per_cand));
+  CK (ctx->Hv.reserve (batch * t.n_ent * kOffPad));
+  CK (ctx->rq.reserve (batch * kOffPad * sizeof (double)));
+  CK (ctx->rvalid.reserve (batch * kOffPad));
+  CK (ctx->cand_start.reserve (batch * sizeof (long long)));
+  CK (ctx->cand_noff.reserve (batch * sizeof (int)));
+  const size_t smem = fft_smem_bytes (kRefineWarps) + kRefineWarps * 96 * sizeof (float);
+  if (set_smem (ctx, k_refine_fft, smem)) return 1;
+
+  std::vector<long long> h_start (batch);
+  std::vector<int> h_noff (batch);
+  std::vector<double> h_q (batch * kOffPad);
+  std::vector<unsigned char> h_valid (batch * kOffPad);
+  for (size_t c0 = 0; c0 < n_scores; c0 += batch)
+    {
+      const size_t nc = std::min (batch, n_scores - c0);
+      for (size_t c = 0; c < nc; c++)
+        {
+          // int start = max (int (index) - sync_search_step, 0); end = index + sync_search_step; step sync_search_fine
+          const long long idx = (long long) scores[c0 + c].index;
+          const long long start = std::max<long long> (idx - 256, 0), end = idx + 256;
+          h_start[c] = start;
+          h_noff[c] = int ((end - start) / 8 + 1);
+        }
+      CK (cudaMemcpyAsync (ctx->cand_start.p, h_start.data(), nc * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+      CK (cudaMemcpyAsync (ctx->cand_noff.p, h_noff.data(), nc * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+      const long long jobs = (long long) nc * t.n_ent * kOffsets;
+      k_refine_fft<<<unsigned ((jobs + kRefineWarps - 1) / kRefineWarps), kRefineWarps * 32, smem, ctx->stream>>> (
+        ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
+        t.ent.as<awm_sync_entry>(), t.n_ent, total, (long long) wav_first, (long long) wav_last,
+        ctx->S.as<float>(), ctx->Hv.as<unsigned char>(), ctx->tw.as<float2>(), ctx->win.as<float>());
+      LAUNCH_CHECK ("k_refine_fft");
+      k_refine_sum<<<unsigned (nc), kOffPad + 24, 0, ctx->stream>>> (
+        ctx->S.as<float>(), ctx->Hv.as<unsigned char>(), ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
+        t.n_ent, t.off.as<int>(), t.n_bits, total, (long long) ctx->pcm_frames, norm_div, ctx->rq.as<double>(), ctx->rvalid.as<unsigned char>());
+      LAUNCH_CHECK ("k_refine_sum");
+      CK (cudaMemcpyAsync (h_q.data(), ctx->rq.p, nc * kOffPad * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaMemcpyAsync (h_valid.data(), ctx->rvalid.p, nc * kOffPad, cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaStreamSynchronize (ctx->stream));
+      for (size_t c = 0; c < nc; c++)
+        {
+          awm_search_score& sc = scores[c0 + c];
+          double best_quality = sc.raw_quality;
+          uint64_t best_index = sc.index;
+          for (int o = 0; o < h_noff[c] && o < kOffsets; o++)
+            if (h_valid[c * kOffPad + o])
+              {
+                const double q = h_q[c * kOffPad + o];
+                if (fabs (q - sc.local_mean) > fabs (best_quality - sc.local_mean))   // src/syncfinder.cc:436-440
+                  {
+                    best_quality = q;
+                    best_index = uint64_t (h_start[c] + 8LL * o);
+                  }
+              }
+          sc.index = best_index;
+          sc.raw_quality = best_quality;
+        }
+    }
+  return 0;
+}
+
+/* ---------------------------------------------------------------- block decode */
+
+int
+awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size_t n_blocks, float *raw_bits_out, int *valid_out)
+{
+  if (key_slot < 0 || key_slot >= AWM_MAX_KEYS || (n_blocks && (!indices || !raw_bits_out || !valid_out)))
+    return fail (ctx, "awm_decode_blocks: bad arguments");
+  KeyTab& k = ctx->keys[key_slot];
+  if (!k.n_mix)
+    return fail (ctx, "awm_decode_blocks: mix tables for key slot %d not set", key_slot);
+  if (!ctx->pcm_ch)
+    return fail (ctx, "awm_decode_blocks: no PCM bound");
+  if (n_blocks == 0)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  const int C = ctx->pcm_ch;
+  std::vector<long long> starts;
+  std::vector<size_t> which;
+  for (size_t i = 0; i < n_blocks; i++)
+    {
+      // fft_range: empty result if samples.size() < (start_index + frame_count * frame_size) * n_channels
+      const bool ok = indices[i] + uint64_t (k.fpb) * kFrame <= ctx->pcm_frames;
+      valid_out[i] = ok ? 1 : 0;
+      if (ok)
+        {
+          starts.push_back ((long long) indices[i]);
+          which.push_back (i);
+        }
+    }
+  const size_t per_blk = size_t (k.fpb) * C * kBands * sizeof (float);
+  size_t batch = std::max<size_t> (1, (size_t (1) << 30) / per_blk);
+  const size_t smem = fft_smem_bytes (kDecodeWarps);
+  if (set_smem (ctx, k_decode_fft, smem)) return 1;
+  std::vector<float> h_raw;
+  for (size_t b0 = 0; b0 < starts.size(); b0 += batch)
+    {
+      const size_t nb = std::min (batch, starts.size() - b0);
+      CK (ctx->D.reserve (nb * per_blk));
+      CK (ctx->blk_start.reserve (nb * sizeof (long long)));
+      CK (ctx->raw.reserve (nb * k.n_coded * sizeof (float)));
+      CK (cudaMemcpyAsync (ctx->blk_start.p, starts.data() + b0, nb * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+      const int pairs = (C + 1) / 2;
+      const long long jobs = (long long) nb * k.fpb * pairs;
+      k_decode_fft<<<unsigned ((jobs + kDecodeWarps - 1) / kDecodeWarps), kDecodeWarps * 32, smem, ctx->stream>>> (
+        ctx->pcm, (long long) ctx->pcm_frames, C, ctx->blk_start.as<long long>(), int (nb), k.fpb, ctx->D.as<float>(),
+        ctx->tw.as<float2>(), ctx->win.as<float>());
+      LAUNCH_CHECK ("k_decode_fft");
+      dim3 grid (unsigned ((k.n_coded + 127) / 128), unsigned (nb));
+      k_mix_decode<<<grid, 128, 0, ctx->stream>>> (ctx->D.as<float>(), int (nb), C, k.fpb, k.mix.as<awm_mix_entry>(), k.frames_per_bit,
+                                                   k.n_coded, k.order.as<uint16_t>(), ctx->raw.as<float>());
+      LAUNCH_CHECK ("k_mix_decode");
+      h_raw.resize (nb * k.n_coded);
+      CK (cudaMemcpyAsync (h_raw.data(), ctx->raw.p, nb * k.n_coded * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaStreamSynchronize (ctx->stream));
+      for (size_t b = 0; b < nb; b++)
+        memcpy (raw_bits_out + which[b0 + b] * k.n_coded, h_raw.data() + b * k.n_coded, k.n_coded * sizeof (float));
+    }
+  return 0;
+}
+
+/* ---------------------------------------------------------------- Viterbi */
+
+int
+awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_coded, const int *block_types,
+             int hard, uint8_t *bits_out, float *error_out)
+{
+  if (n_jobs == 0)
+    return 0;
+  if (!raw_bits || !block_types || !bits_out || !error_out || n_coded <= 0)
+    return fail (ctx, "awm_viterbi: bad arguments");
+  int n_msg = -1;
+  for (size_t j = 0; j < n_jobs; j++)
+    {
+      const int rate = block_types[j] == AWM_BLOCK_AB ? 12 : 6;
+      if (block_types[j] < 0 || block_types[j] > 2 || n_coded % rate || n_coded / rate <= AWM_VITERBI_ORDER)
+        return fail (ctx, "awm_viterbi: n_coded %d does not fit block type %d", n_coded, block_types[j]);
+      const int m = n_coded / rate - AWM_VITERBI_ORDER;
+      if (n_msg >= 0 && m != n_msg)
+        return fail (ctx, "awm_viterbi: all jobs of one call must have the same rate");
+      n_msg = m;
+    }
+  CK (cudaSetDevice (ctx->device));
+  const int steps = n_msg + AWM_VITERBI_ORDER;
+  const size_t max_jobs = 256;
+  const size_t smem = size_t (n_coded) * sizeof (float);
+  if (set_smem (ctx, k_viterbi, smem)) return 1;
+  for (size_t j0 = 0; j0 < n_jobs; j0 += max_jobs)
+    {
+      const size_t nj = std::min (max_jobs, n_jobs - j0);
+      CK (ctx->vit_raw.reserve (nj * n_coded * sizeof (float)));
+      CK (ctx->vit_types.reserve (nj * sizeof (int)));
+      CK (ctx->vit_delta.reserve (nj * 2 * kVitStates * sizeof (float)));
+      CK (ctx->vit_dec.reserve (nj * steps * kVitWords * sizeof (uint32_t)));
+      CK (ctx->vit_bits.reserve (nj * n_msg));
+      CK (ctx->vit_err.reserve (nj * sizeof (float)));
+      CK (cudaMemcpyAsync (ctx->vit_raw.p, raw_bits + j0 * n_coded, nj * n_coded * sizeof (float), cudaMemcpyDefault, ctx->stream));
+      CK (cudaMemcpyAsync (ctx->vit_types.p, block_types + j0, nj * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+      k_viterbi<<<unsigned (nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), n_coded, ctx->vit_types.as<int>(), hard,
+                                                                  ctx->vit_delta.as<float>(), ctx->vit_dec.as<uint32_t>(),
+                                                                  ctx->vit_bits.as<unsigned char>(), ctx->vit_err.as<float>());
+      LAUNCH_CHECK ("k_viterbi");
+      CK (cudaMemcpyAsync (bits_out + j0 * n_msg, ctx->vit_bits.p, nj * n_msg, cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaMemcpyAsync (error_out + j0, ctx->vit_err.p, nj * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaStreamSynchronize (ctx->stream));
+    }
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,891 @@
+// awm_kernels.cuh -- sm_100a kernels of the spectral watermark hot path.
+//
+// Every kernel is "one warp = one 1024-point packed FFT" (awm_fft.cuh); what differs is where
+// the samples come from and what is kept of the spectrum.  Reference loops replaced are cited
+// per kernel (paths relative to the reference tree).
+#pragma once
+#include "awm_fft.cuh"
+#include "../../include/awm_b200.h"
+#include <math.h>
+
+namespace awm {
+
+// ---------------------------------------------------------------------------------------------
+// shared memory carve-up common to all FFT kernels:
+//   [ tw: 1024 float2 ][ win: 1024 float ][ per-warp transpose buffers ][ kernel specific ... ]
+struct FftSmem
+{
+  float2 *tw;
+  float  *win;
+  float  *xbuf;       // this warp's transpose buffer
+  float  *extra;      // first byte after all transpose buffers
+};
+
+constexpr size_t fft_smem_bytes (int warps) { return 1024 * sizeof (float2) + 1024 * sizeof (float) + size_t (warps) * kWarpFftSmemFloats * sizeof (float); }
+
+__device__ __forceinline__ FftSmem
+fft_smem_setup (unsigned char *smem, const float2 *g_tw, const float *g_win, int warps)
+{
+  FftSmem s;
+  s.tw = reinterpret_cast<float2 *> (smem);
+  s.win = reinterpret_cast<float *> (smem + 1024 * sizeof (float2));
+  float *x0 = s.win + 1024;
+  s.xbuf = x0 + (threadIdx.x >> 5) * kWarpFftSmemFloats;
+  s.extra = x0 + warps * kWarpFftSmemFloats;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+    {
+      s.tw[i] = g_tw[i];
+      s.win[i] = g_win ? g_win[i] : 1.0f;
+    }
+  __syncthreads();
+  return s;
+}
+
+// load (and window) one pair of real sequences: re <- channel chA, im <- channel chB (or 0)
+// from interleaved PCM, sample-frames [start, start+1024), zero beyond n_frames.
+__device__ __forceinline__ void
+load_pair (const float *__restrict__ pcm, long long n_frames, int C, long long start, int chA, int chB,
+           const float *win, float (&re)[32], float (&im)[32], int lane)
+{
+  if (C == 2 && chB == 1)
+    {
+      const float2 *p2 = reinterpret_cast<const float2 *> (pcm);
+#pragma unroll
+      for (int j = 0; j < 32; j++)
+        {
+          const int n = 32 * j + lane;
+          const long long pos = start + n;
+          float2 v = make_float2 (0.f, 0.f);
+          if (pos >= 0 && pos < n_frames)
+            v = __ldg (p2 + pos);
+          const float w = win[n];
+          re[j] = v.x * w;
+          im[j] = v.y * w;
+        }
+    }
+  else
+    {
+#pragma unroll
+      for (int j = 0; j < 32; j++)
+        {
+          const int n = 32 * j + lane;
+          const long long pos = start + n;
+          float a = 0.f, b = 0.f;
+          if (pos >= 0 && pos < n_frames)
+            {
+              a = __ldg (pcm + pos * C + chA);
+              if (chB >= 0)
+                b = __ldg (pcm + pos * C + chB);
+            }
+          const float w = win[n];
+          re[j] = a * w;
+          im[j] = b * w;
+        }
+    }
+}
+
+// channel-summed band dB of one frame (SyncFinder::sync_fft inner loop, src/syncfinder.cc:590-598):
+// acc[K2] of lane k1 is the band value for bin k1 + 32*K2 (valid where 20 <= bin <= 100).
+__device__ __forceinline__ void
+frame_db_sum (const float *__restrict__ pcm, long long n_frames, int C, long long start,
+              const FftSmem& s, int lane, float (&acc)[4])
+{
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+  for (int chA = 0; chA < C; chA += 2)
+    {
+      const int chB = (chA + 1 < C) ? chA + 1 : -1;
+      float re[32], im[32];
+      load_pair (pcm, n_frames, C, start, chA, chB, s.win, re, im, lane);
+      fft1024_warp (re, im, s.tw, s.xbuf, lane);
+      float ar, ai, br, bi;
+      unpack_pair<0> (re, im, lane, ar, ai, br, bi);
+      acc[0] += db_from_complex (ar, ai, -96.f);
+      if (chB >= 0) acc[0] += db_from_complex (br, bi, -96.f);
+      unpack_pair<1> (re, im, lane, ar, ai, br, bi);
+      acc[1] += db_from_complex (ar, ai, -96.f);
+      if (chB >= 0) acc[1] += db_from_complex (br, bi, -96.f);
+      unpack_pair<2> (re, im, lane, ar, ai, br, bi);
+      acc[2] += db_from_complex (ar, ai, -96.f);
+      if (chB >= 0) acc[2] += db_from_complex (br, bi, -96.f);
+      unpack_pair<3> (re, im, lane, ar, ai, br, bi);
+      acc[3] += db_from_complex (ar, ai, -96.f);
+      if (chB >= 0) acc[3] += db_from_complex (br, bi, -96.f);
+    }
+}
+
+// scatter the (up to 4) band values a lane holds into a dense 81-entry array
+__device__ __forceinline__ void
+bands_to_array (const float (&acc)[4], int lane, float *dst, int stride)
+{
+#pragma unroll
+  for (int k2 = 0; k2 < 4; k2++)
+    {
+      const int band = lane + 32 * k2 - kMinBand;
+      if (band >= 0 && band < kBands)
+        dst[band * stride] = acc[k2];
+    }
+}
+
+// =============================================================================================
+// FFTProcessor::fft / ifft, batched (src/fft.cc:82-118).  One warp = two consecutive transforms.
+// =============================================================================================
+constexpr int kFftWarps = 8;
+
+__global__ void __launch_bounds__ (kFftWarps * 32)
+k_fft_r2c (const float *__restrict__ in, float *__restrict__ out, long long count, const float2 *g_tw)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  FftSmem s = fft_smem_setup (smem, g_tw, nullptr, kFftWarps);
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long) blockIdx.x * kFftWarps + (threadIdx.x >> 5);
+  if (2 * p >= count)
+    return;
+  const bool have_b = 2 * p + 1 < count;
+  const float *a = in + 2 * p * kFrame, *b = a + kFrame;
+  float re[32], im[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++)
+    {
+      re[j] = a[32 * j + lane];
+      im[j] = have_b ? b[32 * j + lane] : 0.f;
+    }
+  fft1024_warp (re, im, s.tw, s.xbuf, lane);
+  float2 *oa = reinterpret_cast<float2 *> (out + 2 * p * (kFrame + 2)), *ob = oa + (kFrame / 2 + 1);
+  auto emit = [&] (int k, bool pred, float ar, float ai, float br, float bi)
+    {
+      if (pred)
+        {
+          oa[k] = make_float2 (ar, ai);
+          if (have_b)
+            ob[k] = make_float2 (br, bi);
+        }
+    };
+  float ar, ai, br, bi;
+#define AWM_EMIT(K2) unpack_pair<K2> (re, im, lane, ar, ai, br, bi); emit (lane + 32 * K2, true, ar, ai, br, bi);
+  AWM_EMIT (0) AWM_EMIT (1) AWM_EMIT (2) AWM_EMIT (3) AWM_EMIT (4) AWM_EMIT (5) AWM_EMIT (6) AWM_EMIT (7)
+  AWM_EMIT (8) AWM_EMIT (9) AWM_EMIT (10) AWM_EMIT (11) AWM_EMIT (12) AWM_EMIT (13) AWM_EMIT (14) AWM_EMIT (15)
+#undef AWM_EMIT
+  unpack_pair<16> (re, im, lane, ar, ai, br, bi);
+  emit (512, lane == 0, ar, ai, br, bi);
+}
+
+__global__ void __launch_bounds__ (kFftWarps * 32)
+k_fft_c2r (const float *__restrict__ in, float *__restrict__ out, long long count, const float2 *g_tw)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  FftSmem s = fft_smem_setup (smem, g_tw, nullptr, kFftWarps);
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long) blockIdx.x * kFftWarps + (threadIdx.x >> 5);
+  if (2 * p >= count)
+    return;
+  const bool have_b = 2 * p + 1 < count;
+  const float2 *A = reinterpret_cast<const float2 *> (in + 2 * p * (kFrame + 2)), *B = A + (kFrame / 2 + 1);
+  float re[32], im[32];
+  // D[k] = A[k] + i B[k] (k <= 512), D[k] = conj A[N-k] + i conj B[N-k] (k > 512); inverse = swap (FFT (swap D))
+#pragma unroll
+  for (int j = 0; j < 32; j++)
+    {
+      const int k = 32 * j + lane;
+      const int ks = k <= 512 ? k : kFrame - k;
+      float2 a = A[ks], b = have_b ? B[ks] : make_float2 (0.f, 0.f);
+      if (ks == 0 || ks == 512)     // c2r ignores the imaginary part of DC / Nyquist
+        a.y = b.y = 0.f;
+      if (k > 512)
+        {
+          a.y = -a.y;
+          b.y = -b.y;
+        }
+      const float dr = a.x - b.y, di = a.y + b.x;
+      re[j] = di;
+      im[j] = dr;
+    }
+  fft1024_warp (re, im, s.tw, s.xbuf, lane);
+  float *oa = out + 2 * p * kFrame, *ob = oa + kFrame;
+#pragma unroll
+  for (int i = 0; i < 32; i++)
+    {
+      const int n = lane + 32 * brev5 (i);
+      oa[n] = im[i];
+      if (have_b)
+        ob[n] = re[i];
+    }
+}
+
+// =============================================================================================
+// SyncFinder::sync_fft / sync_fft_parallel for all four 256-sample shifts
+// (src/syncfinder.cc:560-657): db[shift][band][frame] (band-major so the per-candidate gathers of
+// k_sync_approx are coalesced over consecutive start frames) and have[shift][frame].
+// grid = (ceil(n_out/8), 4 shifts), 8 warps, warp = one frame.
+// =============================================================================================
+constexpr int kStftWarps = 8;
+
+__global__ void __launch_bounds__ (kStftWarps * 32, 2)
+k_stft_db (const float *__restrict__ pcm, long long n_frames, int C, int n_out, int ld,
+           float *__restrict__ dbT, unsigned char *__restrict__ have,
+           long long wav_first, long long wav_last, const float2 *g_tw, const float *g_win)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  FftSmem s = fft_smem_setup (smem, g_tw, g_win, kStftWarps);
+  float *tile = s.extra;                               // [81][kStftWarps + 1]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int shift_idx = blockIdx.y;
+  const int f = blockIdx.x * kStftWarps + w;
+  const long long start = (long long) shift_idx * 256 + (long long) f * kFrame;
+
+  bool ok = f < n_out;
+  if (ok)
+    {
+      const long long f_first = start * C, f_last = (start + kFrame) * C;
+      if (f_last < wav_first || f_first > wav_last)   // frame in leading / trailing digital silence
+        ok = false;
+    }
+  float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+  if (ok)
+    frame_db_sum (pcm, n_frames, C, start, s, lane, acc);
+  bands_to_array (acc, lane, tile + w, kStftWarps + 1);
+  if (lane == 0 && f < n_out)
+    have[(size_t) shift_idx * ld + f] = ok ? 1 : 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBands * kStftWarps; i += blockDim.x)
+    {
+      const int band = i / kStftWarps, ww = i % kStftWarps;
+      const int ff = blockIdx.x * kStftWarps + ww;
+      if (ff < n_out)
+        dbT[((size_t) shift_idx * kBands + band) * ld + ff] = tile[band * (kStftWarps + 1) + ww];
+    }
+}
+
+// =============================================================================================
+// SyncFinder::sync_decode for every start frame (src/syncfinder.cc:116-153, bit_quality :94-114,
+// normalize_sync_quality :80-91).  One thread = one candidate; float sums in reference order.
+// out[s*4 + shift] so that the array is already sorted by index = s*1024 + shift*256.
+// =============================================================================================
+constexpr int kApproxThreads = 128;
+
+template<bool CHECK_HAVE> __global__ void __launch_bounds__ (kApproxThreads)
+k_sync_approx (const float *__restrict__ dbT, const unsigned char *__restrict__ have, int ld, int n_starts,
+               const awm_sync_entry *__restrict__ g_ent, int n_ent, const int *__restrict__ g_bit_off, int n_bits,
+               double norm_div, double *__restrict__ out)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  awm_sync_entry *ent = reinterpret_cast<awm_sync_entry *> (smem);
+  {
+    const uint16_t *src = reinterpret_cast<const uint16_t *> (g_ent);
+    uint16_t *dst = reinterpret_cast<uint16_t *> (smem);
+    const int n16 = n_ent * int (sizeof (awm_sync_entry) / 2);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
+      dst[i] = src[i];
+  }
+  __syncthreads();
+  const int shift_idx = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_starts)
+    return;
+  const float *db = dbT + (size_t) shift_idx * kBands * ld;
+  const unsigned char *hv = have + (size_t) shift_idx * ld;
+  double sync_quality = 0;
+  int bit_count = 0;
+  for (int bit = 0; bit < n_bits; bit++)
+    {
+      float umag = 0, dmag = 0;
+      int frame_bit_count = 0;
+      const int e1 = g_bit_off[bit + 1];
+      for (int e = g_bit_off[bit]; e < e1; e++)
+        {
+          const int f = s + ent[e].frame;
+          if (!CHECK_HAVE || hv[f])
+            {
+              const float *col = db + f;
+#pragma unroll
+              for (int i = 0; i < kUD; i++)
+                {
+                  umag += col[(size_t) ent[e].up[i] * ld];
+                  dmag += col[(size_t) ent[e].down[i] * ld];
+                }
+              frame_bit_count++;
+            }
+        }
+      double raw_bit;
+      if (umag == 0 || dmag == 0)
+        raw_bit = 0;
+      else if (umag < dmag)
+        raw_bit = 1 - double (umag) / double (dmag);
+      else
+        raw_bit = double (dmag) / double (umag) - 1;
+      sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * frame_bit_count;
+      bit_count += frame_bit_count;
+    }
+  if (bit_count)
+    sync_quality /= bit_count;
+  out[(size_t) s * 4 + shift_idx] = sync_quality / norm_div / 2.9;
+}
+
+// local mean of SyncFinder::search_approx (src/syncfinder.cc:234-254) + packing of the score list
+__global__ void
+k_local_mean (const double *__restrict__ q, long long n, awm_search_score *__restrict__ scores)
+{
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  double avg = 0;
+  int cnt = 0;
+  for (int j = -20; j <= 20; j++)
+    if (j <= -4 || j >= 4)
+      {
+        const long long idx = i + j;
+        if (idx >= 0 && idx < n)
+          {
+            avg += q[idx];
+            cnt++;
+          }
+      }
+  if (cnt > 0)
+    avg /= cnt;
+  scores[i].index = (unsigned long long) (i >> 2) * kFrame + (unsigned long long) (i & 3) * 256;
+  scores[i].raw_quality = q[i];
+  scores[i].local_mean = avg;
+}
+
+// =============================================================================================
+// SyncFinder::search_refine (src/syncfinder.cc:393-458), stage 1: for candidate c, fine offset o
+// and wanted sync frame e one warp computes the channel-summed dB of the frame at sample
+// cand_start[c] + 8*o + frame(e)*1024 and stores the 30 up + 30 down values the sync pattern
+// reads, laid out [c][e][60][kOffPad] so that stage 2 (one thread per offset) is coalesced.
+// =============================================================================================
+constexpr int kOffsets = 65;
+constexpr int kOffPad = 72;
+constexpr int kRefineWarps = 8;
+
+__global__ void __launch_bounds__ (kRefineWarps * 32, 2)
+k_refine_fft (const float *__restrict__ pcm, long long n_frames, int C,
+              const long long *__restrict__ cand_start, const int *__restrict__ cand_noff, int n_cand,
+              const awm_sync_entry *__restrict__ g_ent, int n_ent, int total_frame_count,
+              long long wav_first, long long wav_last,
+              float *__restrict__ S, unsigned char *__restrict__ Hv, const float2 *g_tw, const float *g_win)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  FftSmem s = fft_smem_setup (smem, g_tw, g_win, kRefineWarps);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *sband = s.extra + w * 96;                      // [81] per warp
+  const long long job = (long long) blockIdx.x * kRefineWarps + w;
+  const long long per_cand = (long long) n_ent * kOffsets;
+  if (job >= per_cand * n_cand)
+    return;
+  const int c = int (job / per_cand);
+  const int e = int ((job % per_cand) / kOffsets);
+  const int o = int (job % kOffsets);
+  if (o >= cand_noff[c])
+    return;
+  const long long fine = cand_start[c] + 8LL * o;
+  if (fine + (long long) total_frame_count * kFrame > n_frames)   // sync_fft: read past end -> no result for this offset
+    return;
+  const awm_sync_entry *en = g_ent + e;
+  const long long start = fine + (long long) en->frame * kFrame;
+  const long long f_first = start * C, f_last = (start + kFrame) * C;
+  const bool ok = !(f_last < wav_first || f_first > wav_last);
+  const size_t ce = (size_t) c * n_ent + e;
+  if (lane == 0)
+    Hv[ce * kOffPad + o] = ok ? 1 : 0;
+  if (!ok)
+    return;
+  float acc[4];
+  frame_db_sum (pcm, n_frames, C, start, s, lane, acc);
+  bands_to_array (acc, lane, sband, 1);
+  __syncwarp();
+  float *dst = S + ce * 60 * kOffPad + o;
+  if (lane < kUD)
+    {
+      dst[(size_t) lane * kOffPad] = sband[en->up[lane]];
+      dst[(size_t) (kUD + lane) * kOffPad] = sband[en->down[lane]];
+    }
+}
+
+// stage 2: one thread per (candidate, offset): sync_decode (start_frame 0) in reference order
+__global__ void
+k_refine_sum (const float *__restrict__ S, const unsigned char *__restrict__ Hv,
+              const long long *__restrict__ cand_start, const int *__restrict__ cand_noff, int n_cand,
+              int n_ent, const int *__restrict__ g_bit_off, int n_bits, int total_frame_count, long long n_frames,
+              double norm_div, double *__restrict__ q_out, unsigned char *__restrict__ q_valid)
+{
+  const int c = blockIdx.x, o = threadIdx.x;
+  if (o >= kOffPad)
+    return;
+  bool valid = o < cand_noff[c];
+  if (valid)
+    {
+      const long long fine = cand_start[c] + 8LL * o;
+      if (fine + (long long) total_frame_count * kFrame > n_frames)
+        valid = false;
+    }
+  q_valid[c * kOffPad + o] = valid ? 1 : 0;
+  if (!valid)
+    return;
+  double sync_quality = 0;
+  int bit_count = 0;
+  for (int bit = 0; bit < n_bits; bit++)
+    {
+      float umag = 0, dmag = 0;
+      int frame_bit_count = 0;
+      for (int e = g_bit_off[bit]; e < g_bit_off[bit + 1]; e++)
+        {
+          const size_t ce = (size_t) c * n_ent + e;
+          if (Hv[ce * kOffPad + o])
+            {
+              const float *src = S + ce * 60 * kOffPad + o;
+#pragma unroll 6
+              for (int i = 0; i < kUD; i++)
+                {
+                  umag += src[(size_t) i * kOffPad];
+                  dmag += src[(size_t) (kUD + i) * kOffPad];
+                }
+              frame_bit_count++;
+            }
+        }
+      double raw_bit;
+      if (umag == 0 || dmag == 0)
+        raw_bit = 0;
+      else if (umag < dmag)
+        raw_bit = 1 - double (umag) / double (dmag);
+      else
+        raw_bit = double (dmag) / double (umag) - 1;
+      sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * frame_bit_count;
+      bit_count += frame_bit_count;
+    }
+  if (bit_count)
+    sync_quality /= bit_count;
+  q_out[c * kOffPad + o] = sync_quality / norm_div / 2.9;
+}
+
+// =============================================================================================
+// block decode, stage 1: FFTAnalyzer::fft_range (src/wmcommon.cc:123-141) reduced to what
+// mix_decode reads: per (block, frame, channel) the dB of bins 20..100 -> D[blk][frame*C+ch][81].
+// =============================================================================================
+constexpr int kDecodeWarps = 8;
+
+__global__ void __launch_bounds__ (kDecodeWarps * 32, 2)
+k_decode_fft (const float *__restrict__ pcm, long long n_frames, int C, const long long *__restrict__ blk_start,
+              int n_blk, int frames_per_block, float *__restrict__ D, const float2 *g_tw, const float *g_win)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  FftSmem s = fft_smem_setup (smem, g_tw, g_win, kDecodeWarps);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int pairs = (C + 1) / 2;
+  const long long job = (long long) blockIdx.x * kDecodeWarps + w;
+  const long long per_blk = (long long) frames_per_block * pairs;
+  if (job >= per_blk * n_blk)
+    return;
+  const int b = int (job / per_blk);
+  const int f = int ((job % per_blk) / pairs);
+  const int chA = int (job % pairs) * 2, chB = chA + 1 < C ? chA + 1 : -1;
+  const long long start = blk_start[b] + (long long) f * kFrame;
+  float re[32], im[32];
+  load_pair (pcm, n_frames, C, start, chA, chB, s.win, re, im, lane);
+  fft1024_warp (re, im, s.tw, s.xbuf, lane);
+  float *da = D + (((size_t) b * frames_per_block + f) * C + chA) * kBands;
+  float *dbb = da + kBands;
+  float ar, ai, br, bi;
+#define AWM_DB(K2) \
+  unpack_pair<K2> (re, im, lane, ar, ai, br, bi); \
+  { const int band = lane + 32 * K2 - kMinBand; \
+    if (band >= 0 && band < kBands) { da[band] = db_from_complex (ar, ai, -96.f); if (chB >= 0) dbb[band] = db_from_complex (br, bi, -96.f); } }
+  AWM_DB (0) AWM_DB (1) AWM_DB (2) AWM_DB (3)
+#undef AWM_DB
+}
+
+// stage 2: mix_decode (src/wmget.cc:67-108) + randomize_bit_order (decode, src/wmcommon.hh:165-185).
+// One thread = one coded bit; double accumulators, entries in reference order.
+__global__ void
+k_mix_decode (const float *__restrict__ D, int n_blk, int C, int frames_per_block,
+              const awm_mix_entry *__restrict__ mix, int frames_per_bit, int n_coded,
+              const uint16_t *__restrict__ bit_order, float *__restrict__ raw_out)
+{
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (o >= n_coded)
+    return;
+  const float *Db = D + (size_t) b * frames_per_block * C * kBands;
+  const long long n_spect = (long long) frames_per_block * C;
+  double umag = 0, dmag = 0;
+  for (int f = o * frames_per_bit; f < (o + 1) * frames_per_bit; f++)
+    for (int ch = 0; ch < C; ch++)
+      for (int fb = 0; fb < kUD; fb++)
+        {
+          const awm_mix_entry me = mix[f * kUD + fb];
+          const long long index = (long long) me.frame * C + ch;
+          const long long next_index = (index + C) < n_spect ? index + C : index - C;
+          const long long prev_index = (index - C) >= 0 ? index - C : index + C;
+          const int u = me.up - kMinBand, d = me.down - kMinBand;
+          umag += Db[index * kBands + u];
+          umag -= double (__fadd_rn (Db[prev_index * kBands + u], Db[next_index * kBands + u])) * 0.5;
+          dmag += Db[index * kBands + d];
+          dmag -= double (__fadd_rn (Db[prev_index * kBands + d], Db[next_index * kBands + d])) * 0.5;
+        }
+  raw_out[(size_t) b * n_coded + bit_order[o]] = float (umag - dmag);
+}
+
+// =============================================================================================
+// normalize_soft_bits (src/wmget.cc:40-65) + conv_decode_soft (src/convcode.cc:128-213).
+// One CTA = one code word; decision word u (32 consecutive new states 32u..32u+31) is computed by one thread.
+//   new_state ns has predecessors ps0 = ns>>1 and ps1 = ps0 + 2^14; the reference visits old
+//   states in ascending order and replaces only on strict '<', so ps1 wins only if strictly better.
+//   path metric: delta = (((old + m_0) + m_1) + ...) in float, m_p = (c_p - s_p)^2 as the reference.
+// =============================================================================================
+constexpr int kVitStates = 1 << AWM_VITERBI_ORDER;
+constexpr int kVitThreads = 512;      // CTA size; each thread owns two groups of 32 new states
+constexpr int kVitWords = kVitStates / 32;   // decision words per trellis step
+__constant__ unsigned c_ab_generators[12] = { 066561, 075211, 071545, 054435, 063635, 052475,
+                                              063543, 075307, 052547, 045627, 067657, 051757 };  // src/convcode.cc:42-46
+
+// one trellis step for the 32 new states owned by thread tid; returns the 32 decision bits
+template<int RATE> __device__ __forceinline__ uint32_t
+viterbi_step (const float *__restrict__ d_old, float *__restrict__ d_new, int gen_off,
+              const float *m0, const float *m1, int tid)
+{
+  uint32_t word = 0;
+#pragma unroll
+  for (int v = 0; v < 4; v++)                                // 8 new states <- 4 + 4 predecessors
+    {
+      const float4 x = *reinterpret_cast<const float4 *> (d_old + 16 * tid + 4 * v);
+      const float4 y = *reinterpret_cast<const float4 *> (d_old + 16 * tid + 4 * v + (kVitStates >> 1));
+      const float a0[4] = { x.x, x.y, x.z, x.w }, a1[4] = { y.x, y.y, y.z, y.w };
+      float outv[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        {
+          const unsigned ns = 32u * tid + 8u * v + q;
+          float d0 = a0[q >> 1], d1 = a1[q >> 1];
+#pragma unroll
+          for (int p = 0; p < RATE; p++)
+            {
+              const float m = (__popc (ns & c_ab_generators[(RATE == 12 ? p : 2 * p) + gen_off]) & 1) ? m1[p] : m0[p];
+              d0 = __fadd_rn (d0, m);
+              d1 = __fadd_rn (d1, m);
+            }
+          const bool take1 = d1 < d0;
+          outv[q] = take1 ? d1 : d0;
+          word |= (take1 ? 1u : 0u) << (8 * v + q);
+        }
+      float4 *on = reinterpret_cast<float4 *> (d_new + 32 * tid + 8 * v);
+      on[0] = make_float4 (outv[0], outv[1], outv[2], outv[3]);
+      on[1] = make_float4 (outv[4], outv[5], outv[6], outv[7]);
+    }
+  return word;
+}
+
+__global__ void __launch_bounds__ (kVitThreads)
+k_viterbi (const float *__restrict__ raw, int n_coded, const int *__restrict__ block_types, int hard,
+           float *__restrict__ delta_buf /* [job][2][32768] */, uint32_t *__restrict__ dec_buf /* [job][steps][kVitWords] */,
+           unsigned char *__restrict__ bits_out, float *__restrict__ err_out)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  float *coded = reinterpret_cast<float *> (smem);          // [n_coded] normalised soft bits
+  __shared__ float m0[12], m1[12];
+  __shared__ double s_mean;
+  const int job = blockIdx.x, tid = threadIdx.x;
+  const int btype = block_types[job];
+  const int rate = (btype == AWM_BLOCK_AB) ? 12 : 6;
+  const int steps = n_coded / rate;
+  const int gen_off = (btype == AWM_BLOCK_B) ? 1 : 0;      // A: even generators, B: odd, AB: all (src/convcode.cc:77-98)
+
+  const float *rj = raw + (size_t) job * n_coded;
+  if (tid == 0)
+    {
+      double mean = 0;
+      for (int i = 0; i < n_coded; i++)
+        mean += fabs (double (rj[i]));
+      s_mean = mean / n_coded;
+    }
+  __syncthreads();
+  for (int i = tid; i < n_coded; i += blockDim.x)
+    coded[i] = hard ? (rj[i] > 0 ? 1.0f : 0.0f) : float (0.5 * (double (rj[i]) / s_mean + 1));
+
+  float *d_old = delta_buf + (size_t) job * 2 * kVitStates, *d_new = d_old + kVitStates;
+  uint32_t *dec = dec_buf + (size_t) job * steps * kVitWords;
+  for (int i = tid; i < kVitStates; i += blockDim.x)
+    d_old[i] = (i == 0) ? 0.f : INFINITY;
+  __syncthreads();
+
+  for (int t = 0; t < steps; t++)
+    {
+      if (tid < rate)
+        {
+          const float c = coded[t * rate + tid];
+          m0[tid] = __fmul_rn (c, c);                       // (c - 0)^2
+          m1[tid] = __fmul_rn (c - 1.0f, c - 1.0f);         // (c - 1)^2
+        }
+      __syncthreads();
+      for (int u = tid; u < kVitWords; u += kVitThreads)
+        {
+          uint32_t word;
+          if (rate == 6)
+            word = viterbi_step<6> (d_old, d_new, gen_off, m0, m1, u);
+          else
+            word = viterbi_step<12> (d_old, d_new, 0, m0, m1, u);
+          dec[(size_t) t * kVitWords + u] = word;
+        }
+      __syncthreads();
+      float *tmp = d_old; d_old = d_new; d_new = tmp;
+    }
+  if (tid == 0)
+    {
+      err_out[job] = d_old[0] / float (n_coded);
+      unsigned state = 0;
+      const int n_msg = steps - AWM_VITERBI_ORDER;
+      for (int t = steps; t > 0; t--)
+        {
+          const uint32_t word = dec[(size_t) (t - 1) * kVitWords + (state >> 5)];
+          const unsigned sel = (word >> (state & 31)) & 1u;
+          if (t - 1 < n_msg)
+            bits_out[(size_t) job * n_msg + (t - 1)] = state & 1u;
+          state = (state >> 1) | (sel << (AWM_VITERBI_ORDER - 1));
+        }
+    }
+}
+
+// =============================================================================================
+// embed: FFTAnalyzer::run_fft (src/wmcommon.cc:91-121) + apply_frame_mod (src/wmadd.cc:61-84) +
+// WatermarkSynth::run (src/wmadd.cc:215-250) + "samples[i] += orig_samples[i]" (src/wmadd.cc:564-565)
+// + Limiter::block_max (src/limiter.cc:90-97), fused.  CTA = 16 warps = 14 output frames + one halo
+// frame on each side (output frame m needs the synthesis-window tails of frames m-1 and m+1,
+// ~103 samples each, which travel through shared memory).
+// =============================================================================================
+constexpr int kEmbedWarps = 16;
+constexpr int kEmbedTile = kEmbedWarps - 2;
+constexpr int kEdge = 104;            // synthesis window is non-zero for x < 103 (tail) and x > 921 (head)
+constexpr int kEdgeHi = kFrame - kEdge;
+
+struct EmbedArgs
+{
+  const float *in;
+  float *out;
+  long long n_frames;          // valid input sample-frames
+  int C;
+  long long n_proc;            // 1024-frames to process = ceil(n/1024) + 1 (tail spill)
+  long long frame_number0;     // table row counter of frame 0: first_frame_number + 2*fpb - pad_start
+  int fpb;
+  const uint8_t *frame_mod;    // [2][fpb][101]
+  float pow_up, pow_down;      // exponents -delta*(+1), -delta*(-1) as float
+  int limiter_block;           // 0 = no peak tracking
+  unsigned *peaks;             // [n_blocks] float bits, atomicMax
+  double *snr;                 // [2] or null
+  const float2 *tw;
+  const float *win;
+  const float *synth;          // [3072] synthesis window
+};
+
+__global__ void __launch_bounds__ (kEmbedWarps * 32, 1)
+k_embed (EmbedArgs A)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  FftSmem s = fft_smem_setup (smem, A.tw, A.win, kEmbedWarps);
+  float *synth = s.extra;                                   // [3072]
+  float2 *elo = reinterpret_cast<float2 *> (synth + 3 * kFrame);  // [warps][kEdge]   samples x < kEdge
+  float2 *ehi = elo + kEmbedWarps * kEdge;                  // [warps][kEdge]   samples x >= kEdgeHi
+  for (int i = threadIdx.x; i < 3 * kFrame; i += blockDim.x)
+    synth[i] = A.synth[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long m = (long long) blockIdx.x * kEmbedTile - 1 + w;      // frame handled by this warp
+  const long long n_real = (A.n_frames + kFrame - 1) / kFrame;          // frames that contain input
+  const bool exists = m >= 0 && m < n_real;
+  const bool emits = w >= 1 && w <= kEmbedTile && m >= 0 && m < A.n_proc;
+  const int C = A.C;
+  float pk0 = 0.f, pk1 = 0.f;
+  double snr_d = 0, snr_s = 0;
+  long long blk_lo = 0, boundary = 0;
+  if (A.limiter_block > 0 && emits)
+    {
+      blk_lo = (m * kFrame) / A.limiter_block;
+      boundary = (blk_lo + 1) * A.limiter_block - m * kFrame;          // x >= boundary belongs to the next block
+    }
+
+  for (int chA = 0; chA < C; chA += 2)
+    {
+      const int chB = chA + 1 < C ? chA + 1 : -1;
+      float re[32], im[32];
+      __syncthreads();                                      // synth[] ready / previous pair's edges consumed
+      if (exists)
+        {
+          load_pair (A.in, A.n_frames, C, m * kFrame, chA, chB, s.win, re, im, lane);
+          fft1024_warp (re, im, s.tw, s.xbuf, lane);
+          const long long r = (A.frame_number0 + m) % (2LL * A.fpb);
+          const uint8_t *fm = A.frame_mod + (size_t) r * (kMaxBand + 1);   // rows [0,fpb) = A, [fpb,2fpb) = B
+          float inr[32], ini[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            inr[j] = ini[j] = 0.f;
+          // own bins k = lane + 32*K2 at register K2, mirrored bins N-k arrive from lane (32-lane)&31
+#define AWM_MOD(K2) \
+          { \
+            float ar, ai, br, bi; \
+            unpack_pair<K2> (re, im, lane, ar, ai, br, bi); \
+            const int k = lane + 32 * K2; \
+            float dar = 0.f, dai = 0.f, dbr = 0.f, dbi = 0.f; \
+            if (k >= kMinBand && k <= kMaxBand) \
+              { \
+                const int mod = fm[k]; \
+                if (mod != 0) \
+                  { \
+                    const float ex = (mod == 1) ? A.pow_up : A.pow_down; \
+                    const float ma = hypotf (ar, ai); \
+                    if (ma > 1e-7f) { const float f = powf (ma, ex) - 1.0f; dar = ar * f; dai = ai * f; } \
+                    if (chB >= 0) \
+                      { \
+                        const float mb = hypotf (br, bi); \
+                        if (mb > 1e-7f) { const float f = powf (mb, ex) - 1.0f; dbr = br * f; dbi = bi * f; } \
+                      } \
+                  } \
+              } \
+            /* D[k] = dA + i dB ; D[N-k] = conj dA + i conj dB ; registers hold the re<->im swapped input */ \
+            inr[K2] = dai + dbr; \
+            ini[K2] = dar - dbi; \
+            const float mr = dar + dbi, mi = dbr - dai; \
+            const int src = (32 - lane) & 31; \
+            const float gr = __shfl_sync (0xffffffffu, mr, src), gi = __shfl_sync (0xffffffffu, mi, src); \
+            if (lane == 0) { inr[(32 - K2) & 31] = (K2 == 0) ? inr[0] : gi; ini[(32 - K2) & 31] = (K2 == 0) ? ini[0] : gr; } \
+            else           { inr[31 - K2] = gi; ini[31 - K2] = gr; } \
+          }
+          AWM_MOD (0) AWM_MOD (1) AWM_MOD (2) AWM_MOD (3)
+#undef AWM_MOD
+          fft1024_warp (inr, ini, s.tw, s.xbuf, lane);
+          // inverse result: sample x = lane + 32*brev5(i): channel A = ini[i], channel B = inr[i]
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            {
+              re[i] = ini[i];
+              im[i] = inr[i];
+            }
+        }
+      else
+        {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            re[i] = im[i] = 0.f;
+        }
+      // publish the window tails
+#pragma unroll
+      for (int i = 0; i < 32; i++)
+        {
+          const int x = lane + 32 * brev5 (i);
+          if (x < kEdge)
+            elo[w * kEdge + x] = make_float2 (re[i], im[i]);
+          if (x >= kEdgeHi)
+            ehi[w * kEdge + (x - kEdgeHi)] = make_float2 (re[i], im[i]);
+        }
+      __syncthreads();
+      if (emits)
+        {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            {
+              const int x = lane + 32 * brev5 (i);
+              // wm = ((0 + prev*w2) + cur*w1) + next*w0, every product and sum rounded separately (src/wmadd.cc:228-238)
+              float wa = __fmul_rn (re[i], synth[kFrame + x]);
+              float wb = __fmul_rn (im[i], synth[kFrame + x]);
+              if (x < kEdge)
+                {
+                  const float2 p = elo[(w - 1) * kEdge + x];
+                  wa = __fadd_rn (__fmul_rn (p.x, synth[2 * kFrame + x]), wa);
+                  wb = __fadd_rn (__fmul_rn (p.y, synth[2 * kFrame + x]), wb);
+                }
+              if (x >= kEdgeHi)
+                {
+                  const float2 nx = ehi[(w + 1) * kEdge + (x - kEdgeHi)];
+                  wa = __fadd_rn (wa, __fmul_rn (nx.x, synth[x]));
+                  wb = __fadd_rn (wb, __fmul_rn (nx.y, synth[x]));
+                }
+              const long long pos = m * kFrame + x;
+              float oa = 0.f, ob = 0.f;
+              if (pos < A.n_frames)
+                {
+                  if (C == 2)
+                    {
+                      const float2 v = __ldg (reinterpret_cast<const float2 *> (A.in) + pos);
+                      oa = v.x; ob = v.y;
+                    }
+                  else
+                    {
+                      oa = __ldg (A.in + pos * C + chA);
+                      if (chB >= 0)
+                        ob = __ldg (A.in + pos * C + chB);
+                    }
+                }
+              const float ya = __fadd_rn (wa, oa), yb = __fadd_rn (wb, ob);
+              if (A.snr)
+                {
+                  snr_d += double (wa) * double (wa) + (chB >= 0 ? double (wb) * double (wb) : 0.0);
+                  snr_s += double (oa) * double (oa) + (chB >= 0 ? double (ob) * double (ob) : 0.0);
+                }
+              float mx = fabsf (ya);
+              if (chB >= 0)
+                mx = fmaxf (mx, fabsf (yb));
+              if (x < boundary) pk0 = fmaxf (pk0, mx); else pk1 = fmaxf (pk1, mx);
+              if (pos < A.n_frames)
+                {
+                  if (C == 2)
+                    reinterpret_cast<float2 *> (A.out)[pos] = make_float2 (ya, yb);
+                  else
+                    {
+                      A.out[pos * C + chA] = ya;
+                      if (chB >= 0)
+                        A.out[pos * C + chB] = yb;
+                    }
+                }
+            }
+        }
+    }
+  if (A.limiter_block > 0 && emits)
+    {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+        {
+          pk0 = fmaxf (pk0, __shfl_xor_sync (0xffffffffu, pk0, off));
+          pk1 = fmaxf (pk1, __shfl_xor_sync (0xffffffffu, pk1, off));
+        }
+      if (lane == 0)
+        {
+          atomicMax (A.peaks + blk_lo, __float_as_uint (pk0));
+          if (boundary < kFrame)
+            atomicMax (A.peaks + blk_lo + 1, __float_as_uint (pk1));
+        }
+    }
+  if (A.snr && emits)
+    {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+        {
+          snr_d += __shfl_xor_sync (0xffffffffu, snr_d, off);
+          snr_s += __shfl_xor_sync (0xffffffffu, snr_s, off);
+        }
+      if (lane == 0)
+        {
+          atomicAdd (A.snr, snr_d);
+          atomicAdd (A.snr + 1, snr_s);
+        }
+    }
+}
+
+// Limiter::process_block (src/limiter.cc:99-124): gain ramps linearly over each block between
+// ceiling / max (bm[b-1], bm[b]) and ceiling / max (bm[b], bm[b+1]); bm[b] = max (ceiling, peak[b]).
+__global__ void
+k_limiter (float *__restrict__ x, long long n_frames, int C, int block, float ceiling,
+           const unsigned *__restrict__ peaks, long long n_blocks)
+{
+  const long long pos = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n_frames)
+    return;
+  const long long b = pos / block;
+  const int i = int (pos - b * block);
+  const float cur = fmaxf (ceiling, __uint_as_float (peaks[b]));
+  const float last = b > 0 ? fmaxf (ceiling, __uint_as_float (peaks[b - 1])) : ceiling;
+  const float next = b + 1 < n_blocks ? fmaxf (ceiling, __uint_as_float (peaks[b + 1])) : ceiling;
+  const float scale_start = __fdiv_rn (ceiling, fmaxf (last, cur));
+  const float scale_end = __fdiv_rn (ceiling, fmaxf (cur, next));
+  if (scale_start == 1.0f && scale_end == 1.0f)
+    return;                                                 // x * 1.0f == x
+  const float scale_step = __fdiv_rn (__fsub_rn (scale_end, scale_start), float (block));
+  const float scale = __fadd_rn (scale_start, __fmul_rn (float (i), scale_step));
+  for (int c = 0; c < C; c++)
+    x[pos * C + c] = __fmul_rn (x[pos * C + c], scale);
+}
+
+} // namespace awm

@@ -1,0 +1,155 @@
+/* awm_b200.h -- C ABI of the B200-native spectral watermark hot path.
+ *
+ * The reference (swesterfeld/audiowmark) has no FFI: its hot path is reached through
+ * C++ classes and three free functions.  This header is the boundary a maintainer would
+ * bind instead; every entry point names the reference interface it replaces
+ * (paths relative to the reference tree).  Plain pointers and sizes only.
+ *
+ * Conventions
+ *  - every function returns 0 on success, nonzero on error; awm_last_error (ctx) gives the text
+ *  - a context owns one CUDA device + stream; single-owner, calls are stream ordered
+ *  - PCM is interleaved fp32 in [-1,1) (what AudioInputStream::read_frames delivers,
+ *    src/audiostream.hh:41-52); pointers may be host or device memory
+ *  - "frame" in argument names is one PCM sample-frame (one sample per channel)
+ *  - there is NO CPU fallback: without a usable CUDA device awm_create fails
+ */
+#ifndef AWM_B200_H
+#define AWM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct awm_ctx awm_ctx;
+
+#define AWM_FRAME_SIZE   1024   /* Params::frame_size      src/wmcommon.hh:36 */
+#define AWM_MIN_BAND     20     /* Params::min_band        src/wmcommon.hh:40 */
+#define AWM_MAX_BAND     100    /* Params::max_band        src/wmcommon.hh:39 */
+#define AWM_N_BANDS      81
+#define AWM_BANDS_PER_FRAME 30  /* Params::bands_per_frame src/wmcommon.hh:38 */
+#define AWM_VITERBI_ORDER 15    /* src/convcode.cc:49 */
+
+enum { AWM_MODE_BLOCK = 0, AWM_MODE_CLIP = 1 };           /* SyncFinder::Mode, src/syncfinder.hh:71 */
+enum { AWM_BLOCK_A = 0, AWM_BLOCK_B = 1, AWM_BLOCK_AB = 2 }; /* ConvBlockType, src/convcode.hh:24 */
+
+/* One sync frame: SyncFinder::FrameBit (src/syncfinder.hh:78-83); band indices are bin - AWM_MIN_BAND */
+typedef struct {
+  uint16_t frame;
+  uint8_t  up[AWM_BANDS_PER_FRAME];
+  uint8_t  down[AWM_BANDS_PER_FRAME];
+} awm_sync_entry;
+
+/* One mix entry: MixEntry (src/wmcommon.hh:149-154); up/down are FFT bin numbers */
+typedef struct {
+  uint16_t frame;
+  uint8_t  up;
+  uint8_t  down;
+} awm_mix_entry;
+
+/* SyncFinder::SearchScore (src/syncfinder.hh:89-98) */
+typedef struct {
+  uint64_t index;
+  double   raw_quality;
+  double   local_mean;
+} awm_search_score;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int         awm_create (int device, awm_ctx **out);
+void        awm_destroy (awm_ctx *ctx);
+const char *awm_last_error (const awm_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t    awm_launch_count (const awm_ctx *ctx);
+/* CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
+void       *awm_stream (awm_ctx *ctx);
+int         awm_synchronize (awm_ctx *ctx);
+
+/* ---- FFTProcessor (src/fft.hh:25-44, src/fft.cc:82-118) ------------------------------------
+ * batched r2c / unnormalised c2r, n must be 1024.  in/out layouts as FFTW:
+ *   r2c: in [count][1024] real  -> out [count][1026] (513 complex, re/im interleaved)
+ *   c2r: in [count][1026]       -> out [count][1024] (sum over the Hermitian extension, not divided by n)
+ */
+int awm_fft_r2c (awm_ctx *ctx, const float *in, float *out, size_t count, int n);
+int awm_fft_c2r (awm_ctx *ctx, const float *in, float *out, size_t count, int n);
+
+/* ---- key / payload derived tables (built on the host, the AES key never reaches the GPU) ----
+ * embed : FrameMod table of init_frame_mod_vec (src/wmadd.cc:148-162): uint8 [2 (A,B)][frames_per_block][101],
+ *         0 keep / 1 up / 2 down
+ * sync  : SyncFinder::get_sync_bits (src/syncfinder.cc:30-77) flattened bit-major; bit b owns
+ *         entries bit_offsets[b] .. bit_offsets[b+1]-1, entries sorted by frame inside a bit
+ * mix   : gen_mix_entries (src/wmcommon.cc:179-202) and the bit order permutation of
+ *         randomize_bit_order (src/wmcommon.hh:165-185): out[bit_order[i]] = in[i] on decode
+ * key_slot selects one of AWM_MAX_KEYS table sets (audiowmark get accepts several --key options).
+ */
+#define AWM_MAX_KEYS 16
+int awm_set_embed_tables (awm_ctx *ctx, const uint8_t *frame_mod_ab, int frames_per_block);
+int awm_set_sync_tables (awm_ctx *ctx, int key_slot, int mode, const awm_sync_entry *entries, int n_entries,
+                         const int *bit_offsets, int n_bits);
+int awm_set_mix_tables (awm_ctx *ctx, int key_slot, const awm_mix_entry *entries, int n_entries,
+                        const uint16_t *bit_order, int n_coded_bits, int frames_per_bit, int frames_per_block);
+
+/* ---- PCM residency (WavData::samples, src/wavdata.hh:27-74) ---------------------------------
+ * Binds the audio the following sync / decode calls work on.  A host pointer is copied to a
+ * context-owned device buffer (pinned or pageable, async on the context stream); a device
+ * pointer is used in place and must stay valid until the next bind.
+ * pad_start/pad_end: that many zero sample-frames are logically prepended / appended
+ * (ClipDecoder::run_block zero padding, src/wmget.cc:823-866) without the caller materialising them.
+ */
+int awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end);
+
+/* ---- embed: add_stream_watermark main loop (src/wmadd.cc:520-589) = FFTAnalyzer::run_fft
+ * (src/wmcommon.cc:91-121) + apply_frame_mod (src/wmadd.cc:61-84) + WatermarkSynth::run
+ * (src/wmadd.cc:215-250) + mix + Limiter::process (src/limiter.cc:45-124), for a whole buffer
+ * at 44.1 kHz.  in/out: [n_frames][channels]; first_frame_number = index of the first 1024-frame
+ * of this buffer in the stream (0 unless the caller shards; WatermarkGen starts its table row
+ * at 2*frames_per_block - frames_pad_start, src/wmadd.cc:295).  limiter_block = sample_rate *
+ * 1000 / 1000 frames (src/limiter.cc:33-37); limiter_block = 0 disables the limiter
+ * (--test-no-limiter).  snr_power (optional, 2 doubles) receives sum(delta^2), sum(orig^2)
+ * as --snr accumulates them (src/wmadd.cc:553-563).
+ */
+int awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels,
+               uint64_t first_frame_number, int frames_pad_start, double water_delta,
+               int limiter_block, float limiter_ceiling, double *snr_power);
+
+/* ---- sync search on the bound PCM --------------------------------------------------------
+ * awm_sync_approx = SyncFinder::search_approx (src/syncfinder.cc:171-256): for the four
+ * 256-sample shifts the channel-summed dB spectrogram (sync_fft, :560-605), sync_decode (:116-153)
+ * for every start frame, and the local mean (:234-254).  scores_out (device->host) receives
+ * *n_scores entries sorted by index.  wav_first/wav_last: non-silent value range
+ * [first,last) as scan_silence computes it (:155-169) in interleaved-value units of the padded
+ * signal; pass 0 / n_values for BLOCK mode.
+ * Passing scores_out = NULL only returns the count.
+ */
+int awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
+                     double water_delta, awm_search_score *scores_out, size_t max_scores, size_t *n_scores);
+
+/* awm_sync_refine = SyncFinder::search_refine (src/syncfinder.cc:393-458): for each candidate the
+ * fine offsets max(index-256,0) .. index+256 step 8 are scored with fresh FFTs of the wanted
+ * sync frames; in/out: index, raw_quality are replaced by the best offset (strict '>' on
+ * |q - local_mean|, earlier offset wins ties), local_mean is kept.
+ */
+int awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
+                     double water_delta, awm_search_score *scores, size_t n_scores);
+
+/* ---- block decode: FFTAnalyzer::fft_range (src/wmcommon.cc:123-141) + mix_decode
+ * (src/wmget.cc:67-108) + randomize_bit_order(decode) for blocks starting at indices[i]
+ * (sample-frames of the padded signal).  raw_bits_out: [n_blocks][n_coded_bits] floats;
+ * valid_out[i] = 0 when the block would read past the end (fft_range returns empty).
+ */
+int awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size_t n_blocks,
+                       float *raw_bits_out, int *valid_out);
+
+/* ---- Viterbi: normalize_soft_bits (src/wmget.cc:40-65) + conv_decode_soft (src/convcode.cc:128-213)
+ * for n_jobs independent code words.  raw_bits: [n_jobs][n_coded] (n_coded = rate * (msg+15),
+ * rate 6 for A/B, 12 for AB); block_types[j] in AWM_BLOCK_*; hard != 0 => --hard.
+ * bits_out: [n_jobs][n_coded / rate - 15] bytes (0/1), error_out[j] = metric / n_coded.
+ */
+int awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_coded, const int *block_types,
+                 int hard, uint8_t *bits_out, float *error_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWM_B200_H */
