@@ -25,6 +25,7 @@ SEARCH_SCORE = np.dtype([("index", "<u8"), ("raw_quality", "<f8"), ("local_mean"
 
 EXPORTS = [
     "awm_create", "awm_destroy", "awm_last_error", "awm_launch_count", "awm_stream", "awm_synchronize",
+    "awm_profile_enable", "awm_profile_report",
     "awm_fft_r2c", "awm_fft_c2r", "awm_set_embed_tables", "awm_set_sync_tables", "awm_set_mix_tables",
     "awm_pcm_bind", "awm_embed", "awm_sync_approx", "awm_sync_refine", "awm_decode_blocks", "awm_viterbi",
 ]
@@ -92,6 +93,15 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.awm_synchronize(self.h))
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.awm_profile_enable(self.h, ctypes.c_int(1 if on else 0)))
+
+    def profile_report(self) -> dict:
+        import json
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._ck(self.lib.awm_profile_report(self.h, buf, ctypes.c_size_t(len(buf))))
+        return json.loads(buf.value.decode())
 
     # ---- FFTProcessor
     def fft_r2c(self, x: np.ndarray) -> np.ndarray:

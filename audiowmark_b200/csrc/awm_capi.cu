@@ -70,6 +70,9 @@ struct awm_ctx
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
+  bool profiling = false;
+  struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
 
   DevBuf tw, win, synth;             // constant tables
   DevBuf frame_mod; int embed_fpb = 0;
@@ -102,7 +105,31 @@ fail (awm_ctx *ctx, const char *fmt, ...)
 }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail (ctx, "%s: %s", #call, cudaGetErrorString (e_)); } while (0)
-#define LAUNCH_CHECK(name) do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail (ctx, "launch %s: %s", name, cudaGetErrorString (e_)); } while (0)
+#define LAUNCH_CHECK(name) do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail (ctx, "launch %s: %s", name, cudaGetErrorString (e_)); prof_end (ctx, name); } while (0)
+/* PROF (ctx) goes right before a kernel launch, LAUNCH_CHECK right after it */
+#define PROF(ctx) prof_begin (ctx)
+
+void
+prof_begin (awm_ctx *ctx)
+{
+  if (!ctx->profiling)
+    return;
+  awm_ctx::ProfRec r;
+  r.name = nullptr;
+  cudaEventCreate (&r.e0);
+  cudaEventCreate (&r.e1);
+  cudaEventRecord (r.e0, ctx->stream);
+  ctx->prof.push_back (r);
+}
+
+void
+prof_end (awm_ctx *ctx, const char *name)
+{
+  if (!ctx->profiling || ctx->prof.empty() || ctx->prof.back().name)
+    return;
+  ctx->prof.back().name = name;
+  cudaEventRecord (ctx->prof.back().e1, ctx->stream);
+}
 
 bool
 is_device_ptr (const void *p)
@@ -264,6 +291,57 @@ awm_synchronize (awm_ctx *ctx)
   return 0;
 }
 
+int
+awm_profile_enable (awm_ctx *ctx, int on)
+{
+  ctx->profiling = on != 0;
+  return 0;
+}
+
+int
+awm_profile_report (awm_ctx *ctx, char *json_out, size_t json_cap)
+{
+  CK (cudaSetDevice (ctx->device));
+  CK (cudaStreamSynchronize (ctx->stream));
+  struct Acc { std::string name; int n; double ms; };
+  std::vector<Acc> acc;
+  for (auto& r : ctx->prof)
+    {
+      float ms = 0;
+      if (r.name && cudaEventElapsedTime (&ms, r.e0, r.e1) == cudaSuccess)
+        {
+          bool found = false;
+          for (auto& a : acc)
+            if (a.name == r.name)
+              {
+                a.n++;
+                a.ms += ms;
+                found = true;
+              }
+          if (!found)
+            acc.push_back ({ r.name, 1, ms });
+        }
+      cudaEventDestroy (r.e0);
+      cudaEventDestroy (r.e1);
+    }
+  ctx->prof.clear();
+  std::string js = "{";
+  for (size_t i = 0; i < acc.size(); i++)
+    {
+      char buf[256];
+      snprintf (buf, sizeof (buf), "%s\"%s\": {\"launches\": %d, \"ms\": %.6f}", i ? ", " : "", acc[i].name.c_str(), acc[i].n, acc[i].ms);
+      js += buf;
+    }
+  js += "}";
+  if (json_out && json_cap)
+    {
+      if (js.size() + 1 > json_cap)
+        return fail (ctx, "awm_profile_report: buffer too small");
+      memcpy (json_out, js.c_str(), js.size() + 1);
+    }
+  return 0;
+}
+
 /* ---------------------------------------------------------------- FFTProcessor */
 
 static int
@@ -294,11 +372,13 @@ fft_batch (awm_ctx *ctx, const float *in, float *out, size_t count, int n, bool 
   if (inverse)
     {
       if (set_smem (ctx, k_fft_c2r, smem)) return 1;
+      PROF (ctx);
       k_fft_c2r<<<grid, kFftWarps * 32, smem, ctx->stream>>> (d_in, d_out, (long long) count, ctx->tw.as<float2>());
     }
   else
     {
       if (set_smem (ctx, k_fft_r2c, smem)) return 1;
+      PROF (ctx);
       k_fft_r2c<<<grid, kFftWarps * 32, smem, ctx->stream>>> (d_in, d_out, (long long) count, ctx->tw.as<float2>());
     }
   LAUNCH_CHECK ("k_fft");
@@ -472,17 +552,20 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
   A.limiter_block = limiter_block;
   A.peaks = ctx->peaks.as<unsigned>();
   A.snr = snr_power ? ctx->snr.as<double>() : nullptr;
+  A.snr_frames = limiter_block > 0 ? n_proc : n_real;   // frames the reference loop emits (src/wmadd.cc:539-546)
   A.tw = ctx->tw.as<float2>();
   A.win = ctx->win.as<float>();
   A.synth = ctx->synth.as<float>();
   const size_t smem = fft_smem_bytes (kEmbedWarps) + 3 * kFrame * sizeof (float) + 2 * size_t (kEmbedWarps) * kEdge * sizeof (float2);
   if (set_smem (ctx, k_embed, smem)) return 1;
   const unsigned grid = unsigned ((n_proc + kEmbedTile - 1) / kEmbedTile);
+  PROF (ctx);
   k_embed<<<grid, kEmbedWarps * 32, smem, ctx->stream>>> (A);
   LAUNCH_CHECK ("k_embed");
   if (limiter_block > 0)
     {
       const unsigned g2 = unsigned ((n_frames + 255) / 256);
+      PROF (ctx);
       k_limiter<<<g2, 256, 0, ctx->stream>>> (d_out, (long long) n_frames, channels, limiter_block, limiter_ceiling,
                                               ctx->peaks.as<unsigned>(), n_blocks);
       LAUNCH_CHECK ("k_limiter");
@@ -529,6 +612,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     const size_t smem = fft_smem_bytes (kStftWarps) + kBands * (kStftWarps + 1) * sizeof (float);
     if (set_smem (ctx, k_stft_db, smem)) return 1;
     dim3 grid (unsigned ((n_out + kStftWarps - 1) / kStftWarps), 4);
+    PROF (ctx);
     k_stft_db<<<grid, kStftWarps * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
                                                             ctx->dbT.as<float>(), ctx->have.as<unsigned char>(),
                                                             (long long) wav_first, (long long) wav_last,
@@ -542,6 +626,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     if (mode == AWM_MODE_CLIP)
       {
         if (set_smem (ctx, k_sync_approx<true>, smem)) return 1;
+        PROF (ctx);
         k_sync_approx<true><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_starts),
                                                                         t.ent.as<awm_sync_entry>(), t.n_ent, t.off.as<int>(), t.n_bits,
                                                                         norm_div, ctx->q.as<double>());
@@ -549,6 +634,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     else
       {
         if (set_smem (ctx, k_sync_approx<false>, smem)) return 1;
+        PROF (ctx);
         k_sync_approx<false><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_starts),
                                                                          t.ent.as<awm_sync_entry>(), t.n_ent, t.off.as<int>(), t.n_bits,
                                                                          norm_div, ctx->q.as<double>());
@@ -557,6 +643,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   }
   {
     const long long n = n_starts * 4;
+    PROF (ctx);
     k_local_mean<<<unsigned ((n + 255) / 256), 256, 0, ctx->stream>>> (ctx->q.as<double>(), n, ctx->scores.as<awm_search_score>());
     LAUNCH_CHECK ("k_local_mean");
   }
@@ -614,11 +701,13 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
       CK (cudaMemcpyAsync (ctx->cand_start.p, h_start.data(), nc * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
       CK (cudaMemcpyAsync (ctx->cand_noff.p, h_noff.data(), nc * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
       const long long jobs = (long long) nc * t.n_ent * kOffsets;
+      PROF (ctx);
       k_refine_fft<<<unsigned ((jobs + kRefineWarps - 1) / kRefineWarps), kRefineWarps * 32, smem, ctx->stream>>> (
         ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
         t.ent.as<awm_sync_entry>(), t.n_ent, total, (long long) wav_first, (long long) wav_last,
         ctx->S.as<float>(), ctx->Hv.as<unsigned char>(), ctx->tw.as<float2>(), ctx->win.as<float>());
       LAUNCH_CHECK ("k_refine_fft");
+      PROF (ctx);
       k_refine_sum<<<unsigned (nc), kOffPad + 24, 0, ctx->stream>>> (
         ctx->S.as<float>(), ctx->Hv.as<unsigned char>(), ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
         t.n_ent, t.off.as<int>(), t.n_bits, total, (long long) ctx->pcm_frames, norm_div, ctx->rq.as<double>(), ctx->rvalid.as<unsigned char>());
@@ -691,11 +780,13 @@ awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size_t n
       CK (cudaMemcpyAsync (ctx->blk_start.p, starts.data() + b0, nb * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
       const int pairs = (C + 1) / 2;
       const long long jobs = (long long) nb * k.fpb * pairs;
+      PROF (ctx);
       k_decode_fft<<<unsigned ((jobs + kDecodeWarps - 1) / kDecodeWarps), kDecodeWarps * 32, smem, ctx->stream>>> (
         ctx->pcm, (long long) ctx->pcm_frames, C, ctx->blk_start.as<long long>(), int (nb), k.fpb, ctx->D.as<float>(),
         ctx->tw.as<float2>(), ctx->win.as<float>());
       LAUNCH_CHECK ("k_decode_fft");
       dim3 grid (unsigned ((k.n_coded + 127) / 128), unsigned (nb));
+      PROF (ctx);
       k_mix_decode<<<grid, 128, 0, ctx->stream>>> (ctx->D.as<float>(), int (nb), C, k.fpb, k.mix.as<awm_mix_entry>(), k.frames_per_bit,
                                                    k.n_coded, k.order.as<uint16_t>(), ctx->raw.as<float>());
       LAUNCH_CHECK ("k_mix_decode");
@@ -745,6 +836,7 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_coded, co
       CK (ctx->vit_err.reserve (nj * sizeof (float)));
       CK (cudaMemcpyAsync (ctx->vit_raw.p, raw_bits + j0 * n_coded, nj * n_coded * sizeof (float), cudaMemcpyDefault, ctx->stream));
       CK (cudaMemcpyAsync (ctx->vit_types.p, block_types + j0, nj * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+      PROF (ctx);
       k_viterbi<<<unsigned (nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), n_coded, ctx->vit_types.as<int>(), hard,
                                                                   ctx->vit_delta.as<float>(), ctx->vit_dec.as<uint32_t>(),
                                                                   ctx->vit_bits.as<unsigned char>(), ctx->vit_err.as<float>());

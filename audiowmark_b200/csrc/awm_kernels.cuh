@@ -668,6 +668,7 @@ struct EmbedArgs
   int limiter_block;           // 0 = no peak tracking
   unsigned *peaks;             // [n_blocks] float bits, atomicMax
   double *snr;                 // [2] or null
+  long long snr_frames;        // frames that count for --snr (the reference loop stops earlier without limiter)
   const float2 *tw;
   const float *win;
   const float *synth;          // [3072] synthesis window
@@ -810,7 +811,7 @@ k_embed (EmbedArgs A)
                     }
                 }
               const float ya = __fadd_rn (wa, oa), yb = __fadd_rn (wb, ob);
-              if (A.snr)
+              if (A.snr && m < A.snr_frames)
                 {
                   snr_d += double (wa) * double (wa) + (chB >= 0 ? double (wb) * double (wb) : 0.0);
                   snr_s += double (oa) * double (oa) + (chB >= 0 ? double (ob) * double (ob) : 0.0);

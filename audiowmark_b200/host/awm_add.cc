@@ -1,0 +1,180 @@
+// awm_add.cc -- `audiowmark add`: add_stream_watermark / add_watermark (reference src/wmadd.cc:448-657).
+// The reference pulls 1024-frame blocks through WatermarkGen / WatermarkSynth / Limiter on one CPU
+// thread; here the whole stream is handed to awm_embed, which reproduces the same stream semantics
+// (frame numbering from 2*fpb - 250, zero padding of the tail, limiter on the zero-extended signal).
+#include "awm_wm.hh"
+#include "awm_engine.hh"
+#include "awm_tables.hh"
+#include "awm_util.hh"
+
+#include <math.h>
+
+using std::string;
+using std::vector;
+
+/* number of WatermarkGen::run calls the reference loop makes (src/wmadd.cc:520-589): zero frames are fed
+ * after EOF until every input frame has been written; synth delays one frame (src/wmadd.cc:240-249) and the
+ * limiter keeps one block of look-ahead (src/limiter.cc:53-58).  Only needed for the "Data Blocks" line. */
+static size_t
+gen_runs (size_t n_frames, bool limiter_on, size_t limiter_block)
+{
+  const size_t N = Params::frame_size;
+  if (n_frames == 0)
+    return 0;
+  if (!limiter_on)
+    return 1 + (n_frames + N - 1) / N;
+  const size_t need = ((n_frames + limiter_block - 1) / limiter_block + 1) * limiter_block;
+  return 1 + (need + N - 1) / N;
+}
+
+static void
+info_format (const string& label, const RawFormat& format)
+{
+  const char *e = format.encoding() == Encoding::SIGNED ? "signed" : format.encoding() == Encoding::UNSIGNED ? "unsigned" : "float";
+  info ("%-13s %d Hz, %d Channels, %d Bit (%s %s-endian)\n", (label + ":").c_str(), format.sample_rate(), format.n_channels(),
+        format.bit_depth(), e, format.endian() == RawFormat::LITTLE ? "little" : "big");
+}
+
+int
+add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,
+                      const string& bits, AddStats *stats)
+{
+  const vector<int> bitvec = parse_payload (bits);
+  if (bitvec.empty())
+    return 1;
+  if (sample_rate != Params::mark_sample_rate)
+    {
+      error ("audiowmark: input sample rate %d: only %d Hz is supported (resampling is not available in this build)\n",
+             sample_rate, Params::mark_sample_rate);
+      return 1;
+    }
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx || !Engine::set_embed_tables (key, bitvec))
+    return 1;
+  const int limiter_block = Params::test_no_limiter ? 0 : int (sample_rate * int (Params::limiter_block_size_ms) / 1000);
+  double snr_power[2] = { 0, 0 };
+  if (awm_embed (ctx, in, out, n_frames, n_channels, 0, Params::frames_pad_start, Params::water_delta,
+                 limiter_block, Params::limiter_ceiling, (Params::snr || stats) ? snr_power : nullptr))
+    {
+      error ("audiowmark: embedding failed: %s\n", awm_last_error (ctx));
+      return 1;
+    }
+  if (stats)
+    {
+      const size_t fpb = frames_per_block(), f0 = 2 * fpb - Params::frames_pad_start;
+      const size_t runs = gen_runs (n_frames, !Params::test_no_limiter, sample_rate * int (Params::limiter_block_size_ms) / 1000);
+      const int blocks = int ((f0 + runs) / fpb - f0 / fpb);
+      stats->data_blocks = std::max (blocks - 1, 0);         // the first (partial B) block is padding
+      stats->snr_db = snr_power[0] > 0 ? 10 * log10 (snr_power[1] / snr_power[0]) : INFINITY;
+    }
+  return 0;
+}
+
+int
+add_stream_watermark (const Key& key, AudioInputStream *in_stream, AudioOutputStream *out_stream, const string& bits, size_t zero_frames)
+{
+  auto bitvec = parse_payload (bits);
+  if (bitvec.empty())
+    return 1;
+  if (zero_frames)
+    {
+      error ("audiowmark: stream offsets (HLS segment watermarking) are not supported in this build\n");
+      return 1;
+    }
+  if (in_stream->sample_rate() != out_stream->sample_rate())
+    {
+      error ("audiowmark: input sample rate (%d) and output sample rate (%d) don't match\n", in_stream->sample_rate(), out_stream->sample_rate());
+      return 1;
+    }
+  if (in_stream->n_channels() != out_stream->n_channels())
+    {
+      error ("audiowmark: input channels (%d) and output channels (%d) don't match\n", in_stream->n_channels(), out_stream->n_channels());
+      return 1;
+    }
+  info ("Message:      %s\n", bit_vec_to_str (bitvec).c_str());
+  info ("Strength:     %.6g\n\n", Params::water_delta * 1000);
+  if (in_stream->n_frames() == AudioInputStream::N_FRAMES_UNKNOWN)
+    info ("Time:         unknown\n");
+  else
+    {
+      const size_t orig_seconds = in_stream->n_frames() / in_stream->sample_rate();
+      info ("Time:         %zd:%02zd\n", orig_seconds / 60, orig_seconds % 60);
+    }
+  info ("Sample Rate:  %d\n", in_stream->sample_rate());
+  info ("Channels:     %d\n", in_stream->n_channels());
+
+  WavData wav;
+  Error err = wav.load (in_stream);
+  if (err)
+    {
+      error ("audiowmark: input stream read failed: %s\n", err.message());
+      return 1;
+    }
+  vector<float> out (wav.n_values());
+  AddStats stats;
+  if (add_watermark_buffer (key, wav.samples().data(), out.data(), wav.n_frames(), wav.n_channels(), wav.sample_rate(), bits, &stats))
+    return 1;
+  vector<float>().swap (wav.mutable_samples());
+  err = out_stream->write_frames (out);
+  if (err)
+    {
+      error ("audiowmark output write failed: %s\n", err.message());
+      return 1;
+    }
+  if (Params::snr)
+    info ("SNR:          %f dB\n", stats.snr_db);
+  info ("Data Blocks:  %d\n", stats.data_blocks);
+
+  const size_t total_output_frames = out.size() / std::max (in_stream->n_channels(), 1);
+  if (in_stream->n_frames() != AudioInputStream::N_FRAMES_UNKNOWN && total_output_frames != in_stream->n_frames())
+    {
+      auto msg = string_printf ("unexpected EOF; input frames (%zd) != output frames (%zd)", in_stream->n_frames(), total_output_frames);
+      if (Params::strict)
+        {
+          error ("audiowmark: error: %s\n", msg.c_str());
+          return 1;
+        }
+      warning ("audiowmark: warning: %s\n", msg.c_str());
+    }
+  err = out_stream->close();
+  if (err)
+    {
+      error ("audiowmark: closing output stream failed: %s\n", err.message());
+      return 1;
+    }
+  return 0;
+}
+
+int
+add_watermark (const Key& key, const string& infile, const string& outfile, const string& bits)
+{
+  Error err;
+  std::unique_ptr<AudioInputStream> in_stream = AudioInputStream::create (infile, err);
+  if (err)
+    {
+      error ("audiowmark: error opening %s: %s\n", infile.c_str(), err.message());
+      return 1;
+    }
+  /* output keeps the input's depth / encoding, but at least 16 bit signed */
+  int out_bit_depth = in_stream->bit_depth();
+  Encoding out_encoding = in_stream->encoding();
+  if (in_stream->bit_depth() < 16)
+    {
+      out_bit_depth = 16;
+      out_encoding = Encoding::SIGNED;
+    }
+  std::unique_ptr<AudioOutputStream> out_stream = AudioOutputStream::create (outfile, in_stream->n_channels(), in_stream->sample_rate(),
+                                                                           out_bit_depth, out_encoding, in_stream->n_frames(), err);
+  if (err)
+    {
+      error ("audiowmark: error writing to %s: %s\n", outfile.c_str(), err.message());
+      return 1;
+    }
+  info ("Input:        %s\n", Params::input_label.size() ? Params::input_label.c_str() : infile.c_str());
+  if (Params::input_format == Format::RAW)
+    info_format ("Raw Input", Params::raw_input_format);
+  info ("Output:       %s\n", Params::output_label.size() ? Params::output_label.c_str() : outfile.c_str());
+  if (Params::output_format == Format::RAW)
+    info_format ("Raw Output", Params::raw_output_format);
+  return add_stream_watermark (key, in_stream.get(), out_stream.get(), bits, 0);
+}

@@ -1,0 +1,708 @@
+// awm_get.cc -- `audiowmark get / cmp`: chunk loop, BlockDecoder, ClipDecoder, ResultSet
+// (reference src/wmget.cc:163-1013, src/wavchunkloader.cc:54-239).  FFTs, soft-bit extraction and the
+// Viterbi decoder run on the GPU through the C ABI; pairing / combining logic stays on the host.
+#include "awm_results.hh"
+#include "awm_engine.hh"
+#include "awm_tables.hh"
+#include "awm_util.hh"
+
+#include <algorithm>
+#include <map>
+#include <math.h>
+#include <string.h>
+
+using std::string;
+using std::vector;
+using std::max;
+using std::min;
+
+int
+frame_count (const WavData& wav_data)
+{
+  return wav_data.n_values() / wav_data.n_channels() / Params::frame_size;
+}
+
+/* ---------------------------------------------------------------- ResultSet */
+
+bool
+ResultSet::Pattern::approx_match (const Pattern& p) const
+{
+  const double time_delta = Params::frame_size / double (Params::mark_sample_rate);
+  const double speed_delta = 0.01;
+  return key == p.key && (fabs (time - p.time) < time_delta || type == Type::ALL) && bit_vec == p.bit_vec
+      && sync_score.block_type == p.sync_score.block_type && type == p.type && fabs (speed - p.speed) < speed_delta;
+}
+
+void
+ResultSet::add_pattern (const Key& key, double time, SyncFinder::Score sync_score, const vector<int>& bit_vec, float decode_error, Type pattern_type, double speed)
+{
+  Pattern p;
+  p.key = key;
+  p.time = time;
+  p.sync_score = sync_score;
+  p.bit_vec = bit_vec;
+  p.decode_error = decode_error;
+  p.type = pattern_type;
+  p.speed = speed;
+  patterns.push_back (p);
+}
+
+void
+ResultSet::apply_time_offset (double time_offset)
+{
+  for (auto& p : patterns)
+    p.time += time_offset;
+}
+
+void
+ResultSet::rate_patterns (const Key& key)
+{
+  /* rating = sum of sync qualities of all patterns with the same bits; "all" patterns count twice */
+  std::map<string, float> rating;
+  for (const auto& p : patterns)
+    if (p.key == key)
+      rating[bit_vec_to_str (p.bit_vec)] += p.sync_score.quality * ((p.type == Type::ALL) ? 2.f : 1.f);
+  for (auto& p : patterns)
+    if (p.key == key)
+      p.rating = rating[bit_vec_to_str (p.bit_vec)];
+}
+
+static int
+ab_rank (const ResultSet::Pattern& p)
+{
+  switch (p.sync_score.block_type)
+    {
+      case ConvBlockType::a:  return 0;
+      case ConvBlockType::b:  return 1;
+      case ConvBlockType::ab: return 2;
+    }
+  return 99;
+}
+
+void
+ResultSet::sort (const vector<Key>& key_list)
+{
+  for (const auto& key : key_list)
+    rate_patterns (key);
+  std::sort (patterns.begin(), patterns.end(), [] (const Pattern& p1, const Pattern& p2)
+    {
+      const int all1 = p1.type == Type::ALL, all2 = p2.type == Type::ALL;
+      if (p1.key.name() != p2.key.name())
+        return p1.key.name() < p2.key.name();
+      if (p1.rating != p2.rating)
+        return p1.rating > p2.rating;
+      if (all1 != all2)
+        return all1 < all2;
+      if (p1.time != p2.time)
+        return p1.time < p2.time;
+      if (ab_rank (p1) != ab_rank (p2))
+        return ab_rank (p1) < ab_rank (p2);
+      return bit_vec_to_str (p1.bit_vec) < bit_vec_to_str (p2.bit_vec);
+    });
+}
+
+void
+ResultSet::merge (ResultSet& other)
+{
+  vector<Pattern> to_merge = other.patterns;
+  std::stable_sort (to_merge.begin(), to_merge.end(), [] (const Pattern& p1, const Pattern& p2) { return p1.time < p2.time; });
+  for (const auto& p : to_merge)
+    {
+      bool is_new = true;
+      for (auto& mine : patterns)
+        if (mine.approx_match (p))
+          is_new = false;
+      if (is_new)
+        patterns.push_back (p);
+    }
+  if (debug_sync.empty())
+    debug_sync = other.debug_sync;
+}
+
+static string
+json_escape (const string& s)
+{
+  string result;
+  for (unsigned char ch : s)
+    {
+      if (ch == '"' || ch == '\\')
+        {
+          result += '\\';
+          result += ch;
+        }
+      else if (ch < 32)
+        result += string_printf ("\\u%04x", ch);
+      else
+        result += ch;
+    }
+  return result;
+}
+
+static string
+pattern_type_str (const ResultSet::Pattern& pattern, bool json)
+{
+  string btype;
+  switch (pattern.sync_score.block_type)
+    {
+      case ConvBlockType::a:  btype = "A";  break;
+      case ConvBlockType::b:  btype = "B";  break;
+      case ConvBlockType::ab: btype = "AB"; break;
+    }
+  if (json && pattern.type == ResultSet::Type::ALL)
+    btype = "ALL";
+  if (pattern.type == ResultSet::Type::CLIP)
+    btype = "CLIP-" + btype;
+  if (pattern.speed != 1)
+    btype += "-SPEED";
+  return btype;
+}
+
+void
+ResultSet::print_json (FILE *outfile, size_t time_length)
+{
+  fprintf (outfile, "{ \"length\": \"%ld:%02ld\",\n", long (time_length / 60), long (time_length % 60));
+  fprintf (outfile, "  \"matches\": [\n");
+  int nth = 0;
+  for (const auto& pattern : patterns)
+    {
+      if (nth++ != 0)
+        fprintf (outfile, ",\n");
+      const int seconds = pattern.time;
+      fprintf (outfile, "    { \"key\": \"%s\", \"pos\": \"%d:%02d\", \"bits\": \"%s\", \"quality\": %.5f, \"error\": %.6f, \"rating\": %.5f, \"type\": \"%s\", \"speed\": %.6f }",
+               json_escape (pattern.key.name()).c_str(), seconds / 60, seconds % 60, bit_vec_to_str (pattern.bit_vec).c_str(),
+               pattern.sync_score.quality, pattern.decode_error, pattern.rating, pattern_type_str (pattern, true).c_str(), pattern.speed);
+    }
+  fprintf (outfile, " ]\n}\n");
+}
+
+void
+ResultSet::print_json (size_t time_length, const string& json_file)
+{
+  FILE *outfile = fopen (json_file == "-" ? "/dev/stdout" : json_file.c_str(), "w");
+  if (!outfile)
+    {
+      perror (("audiowmark: failed to open \"" + json_file + "\":").c_str());
+      exit (127);
+    }
+  print_json (outfile, time_length);
+  fclose (outfile);
+}
+
+void
+ResultSet::print (FILE *out)
+{
+  string last_key_name;
+  bool print_speed = true;
+  for (const auto& pattern : patterns)
+    {
+      if (pattern.key.name() != last_key_name)
+        {
+          fprintf (out, "key %s\n", pattern.key.name().c_str());
+          last_key_name = pattern.key.name();
+          print_speed = true;
+        }
+      if (print_speed)
+        {
+          for (const auto& p : patterns)
+            if (p.key == pattern.key && p.speed != 1)
+              {
+                fprintf (out, "speed %.6f\n", p.speed);
+                break;
+              }
+          print_speed = false;
+        }
+      if (pattern.type == Type::ALL)
+        fprintf (out, "pattern   all %s %.3f %.3f%s\n", bit_vec_to_str (pattern.bit_vec).c_str(), pattern.sync_score.quality,
+                 pattern.decode_error, pattern.speed != 1 ? " SPEED" : "");
+      else
+        {
+          const int seconds = pattern.time;
+          fprintf (out, "pattern %2d:%02d %s %.3f %.3f %s\n", seconds / 60, seconds % 60, bit_vec_to_str (pattern.bit_vec).c_str(),
+                   pattern.sync_score.quality, pattern.decode_error, pattern_type_str (pattern, false).c_str());
+        }
+    }
+}
+
+int
+ResultSet::match_count (const vector<int>& orig_bits) const
+{
+  int n = 0;
+  for (const auto& p : patterns)
+    if (p.bit_vec == orig_bits)
+      n++;
+  return n;
+}
+
+int
+ResultSet::print_match_count (const vector<int>& orig_bits)
+{
+  const int n = match_count (orig_bits);
+  printf ("match_count %d %zd\n", n, patterns.size());
+  return n;
+}
+
+/* ---------------------------------------------------------------- GPU helpers */
+
+namespace {
+
+struct VitJob
+{
+  vector<float>     soft;        // raw (un-normalised) soft bits, normalisation happens on the GPU
+  ConvBlockType     block_type;
+  double            time;
+  SyncFinder::Score score;
+  ResultSet::Type   type;
+};
+
+/* code_decode_soft for a list of jobs: one awm_viterbi call per code rate */
+void
+run_viterbi_jobs (const Key& key, vector<VitJob>& jobs, ResultSet& result_set, double speed)
+{
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx)
+    return;
+  for (int pass = 0; pass < 2; pass++)
+    {
+      vector<size_t> sel;
+      for (size_t i = 0; i < jobs.size(); i++)
+        if ((jobs[i].block_type == ConvBlockType::ab) == (pass == 1))
+          sel.push_back (i);
+      if (sel.empty())
+        continue;
+      const size_t n_coded = jobs[sel[0]].soft.size();
+      const int n_msg = int (n_coded / (pass ? 12 : 6)) - AWM_VITERBI_ORDER;
+      vector<float> raw (sel.size() * n_coded);
+      vector<int> types (sel.size());
+      for (size_t j = 0; j < sel.size(); j++)
+        {
+          memcpy (&raw[j * n_coded], jobs[sel[j]].soft.data(), n_coded * sizeof (float));
+          types[j] = jobs[sel[j]].block_type == ConvBlockType::a ? AWM_BLOCK_A : jobs[sel[j]].block_type == ConvBlockType::b ? AWM_BLOCK_B : AWM_BLOCK_AB;
+        }
+      vector<uint8_t> bits (sel.size() * n_msg);
+      vector<float> err (sel.size());
+      if (awm_viterbi (ctx, raw.data(), sel.size(), int (n_coded), types.data(), Params::hard ? 1 : 0, bits.data(), err.data()))
+        {
+          error ("audiowmark: viterbi decoder failed: %s\n", awm_last_error (ctx));
+          continue;
+        }
+      for (size_t j = 0; j < sel.size(); j++)
+        {
+          const VitJob& job = jobs[sel[j]];
+          vector<int> bit_vec (bits.begin() + j * n_msg, bits.begin() + (j + 1) * n_msg);
+          result_set.add_pattern (key, job.time, job.score, bit_vec, err[j], job.type, speed);
+        }
+    }
+  jobs.clear();
+}
+
+/* fft_range + mix_decode + randomize_bit_order (decode) for several block start positions */
+bool
+decode_raw_bits (const Key& key, const vector<uint64_t>& indices, vector<vector<float>>& raw, vector<int>& valid)
+{
+  awm_ctx *ctx = Engine::ctx();
+  const int slot = ctx ? Engine::key_slot (key) : -1;
+  if (slot < 0)
+    return false;
+  const size_t n_coded = code_size (ConvBlockType::a, Params::payload_size);
+  vector<float> flat (indices.size() * n_coded);
+  valid.assign (indices.size(), 0);
+  if (awm_decode_blocks (ctx, slot, indices.data(), indices.size(), flat.data(), valid.data()))
+    {
+      error ("audiowmark: block decode failed: %s\n", awm_last_error (ctx));
+      return false;
+    }
+  raw.resize (indices.size());
+  for (size_t i = 0; i < indices.size(); i++)
+    raw[i].assign (flat.begin() + i * n_coded, flat.begin() + (i + 1) * n_coded);
+  return true;
+}
+
+/* ---------------------------------------------------------------- BlockDecoder (src/wmget.cc:492-735) */
+
+class BlockDecoder
+{
+  int debug_sync_frame_count = 0;
+  const double speed;
+  vector<SyncFinder::KeyResult> key_results;
+public:
+  explicit BlockDecoder (double speed) : speed (speed) {}
+
+  /* the PCM (n_frames x n_channels at sample_rate) is already bound to the GPU context */
+  void
+  run (const vector<Key>& key_list, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set)
+  {
+    SyncFinder sync_finder;
+    key_results = sync_finder.search (key_list, n_frames, n_channels, SyncFinder::Mode::BLOCK, 0, n_frames * n_channels);
+    const size_t count = mark_sync_frame_count() + mark_data_frame_count();
+    const size_t block_len = count * Params::frame_size;
+
+    for (const auto& key_result : key_results)
+      {
+        const Key& key = key_result.key;
+        struct PatternRawBits { size_t index; double quality; vector<float> raw_bit_vec; ConvBlockType block_type; };
+        vector<PatternRawBits> prv;
+        vector<VitJob> jobs;
+
+        vector<uint64_t> indices;
+        for (const auto& s : key_result.sync_scores)
+          indices.push_back (s.index);
+        vector<vector<float>> raw;
+        vector<int> valid;
+        if (!indices.empty() && !decode_raw_bits (key, indices, raw, valid))
+          continue;
+        for (size_t i = 0; i < indices.size(); i++)
+          if (valid[i])
+            {
+              const auto& sync_score = key_result.sync_scores[i];
+              prv.push_back ({ sync_score.index, sync_score.quality, raw[i], sync_score.block_type });
+              jobs.push_back ({ raw[i], sync_score.block_type, double (sync_score.index) / sample_rate, sync_score, ResultSet::Type::BLOCK });
+            }
+        /* AB: a B block with the closest earlier A block one block length before it (within half a frame) */
+        for (size_t i = 0; i < prv.size(); i++)
+          if (prv[i].block_type == ConvBlockType::b)
+            {
+              int best_j = -1, best_abs_dist = Params::frame_size / 2;
+              for (size_t j = 0; j < i; j++)
+                if (prv[j].block_type == ConvBlockType::a)
+                  {
+                    const int abs_dist = std::abs (int (prv[i].index - prv[j].index) - int (block_len));
+                    if (abs_dist < best_abs_dist)
+                      {
+                        best_j = j;
+                        best_abs_dist = abs_dist;
+                      }
+                  }
+              if (best_j >= 0)
+                {
+                  const auto& a = prv[best_j];
+                  const auto& b = prv[i];
+                  vector<float> ab_bits (a.raw_bit_vec.size() * 2);
+                  for (size_t k = 0; k < a.raw_bit_vec.size(); k++)
+                    {
+                      ab_bits[k * 2] = a.raw_bit_vec[k];
+                      ab_bits[k * 2 + 1] = b.raw_bit_vec[k];
+                    }
+                  SyncFinder::Score score_ab { b.index, (a.quality + b.quality) / 2, ConvBlockType::ab };
+                  jobs.push_back ({ ab_bits, ConvBlockType::ab, double (b.index) / sample_rate, score_ab, ResultSet::Type::BLOCK });
+                }
+            }
+        /* all: the chain of blocks at multiples of the block length with alternating types and the largest sync sum */
+        vector<size_t> best_all_blocks;
+        auto sync_sum = [&] (const vector<size_t>& blocks)
+          {
+            float sum = 0;
+            for (auto b : blocks)
+              sum += prv[b].quality;
+            return sum;
+          };
+        for (size_t i = 0; i < prv.size(); i++)
+          {
+            const size_t max_block_idx = lrint (prv.back().index / double (block_len) + 0.5);
+            vector<size_t> all_blocks { i };
+            size_t block_idx = 1;
+            while (block_idx <= max_block_idx)
+              {
+                const size_t expect_start = prv[all_blocks.back()].index + block_idx * block_len;
+                int best_j = -1, best_abs_dist = block_idx * Params::frame_size / 2;
+                auto expect_block_type = prv[all_blocks.back()].block_type;
+                if (block_idx & 1)
+                  expect_block_type = expect_block_type == ConvBlockType::a ? ConvBlockType::b : ConvBlockType::a;
+                for (size_t j = all_blocks.back(); j < prv.size(); j++)
+                  {
+                    const int abs_dist = std::abs (int (expect_start) - int (prv[j].index));
+                    if (abs_dist < best_abs_dist && prv[j].block_type == expect_block_type)
+                      {
+                        best_j = j;
+                        best_abs_dist = abs_dist;
+                      }
+                  }
+                if (best_j >= 0)
+                  {
+                    all_blocks.push_back (best_j);
+                    block_idx = 1;
+                  }
+                else
+                  block_idx++;
+              }
+            if (sync_sum (all_blocks) > sync_sum (best_all_blocks))
+              best_all_blocks = all_blocks;
+          }
+        if (best_all_blocks.size() > 1)
+          {
+            vector<float> raw_all (code_size (ConvBlockType::ab, Params::payload_size));
+            int norm[2] = { 0, 0 };
+            SyncFinder::Score score_all { 0, 0, ConvBlockType::a };
+            for (auto bi : best_all_blocks)
+              {
+                const auto& p = prv[bi];
+                score_all.quality += p.quality;
+                const int ab = p.block_type == ConvBlockType::b ? 1 : 0;
+                for (size_t k = 0; k < p.raw_bit_vec.size(); k++)
+                  raw_all[k * 2 + ab] += p.raw_bit_vec[k];
+                norm[ab]++;
+              }
+            for (size_t k = 0; k < raw_all.size(); k += 2)
+              {
+                raw_all[k]     /= max (norm[0], 1);
+                raw_all[k + 1] /= max (norm[1], 1);
+              }
+            score_all.quality /= norm[0] + norm[1];
+            jobs.push_back ({ raw_all, ConvBlockType::ab, 0.0, score_all, ResultSet::Type::ALL });
+          }
+        run_viterbi_jobs (key, jobs, result_set, speed);
+      }
+    debug_sync_frame_count = n_frames / Params::frame_size;
+  }
+  string
+  debug_sync()
+  {
+    if (key_results.size() != 1)
+      return "";
+    const auto& sync_scores = key_results[0].sync_scores;
+    const int expect0 = Params::frames_pad_start * Params::frame_size;
+    const int expect_step = (mark_sync_frame_count() + mark_data_frame_count()) * Params::frame_size;
+    const int expect_end = debug_sync_frame_count * Params::frame_size;
+    int sync_match = 0;
+    for (int expect_index = expect0; expect_index + expect_step < expect_end; expect_index += expect_step)
+      for (auto sync_score : sync_scores)
+        if (abs (int (sync_score.index + Params::test_cut) - expect_index) < int (Params::frame_size / 2))
+          {
+            sync_match++;
+            break;
+          }
+    return string_printf ("sync_match %d %zd\n", sync_match, sync_scores.size());
+  }
+};
+
+/* ---------------------------------------------------------------- ClipDecoder (src/wmget.cc:737-884) */
+
+class ClipDecoder
+{
+  const int frames_per_blk;
+  const double speed;
+
+  enum class Pos { START, END };
+  void
+  run_block (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set, Pos pos)
+  {
+    awm_ctx *ctx = Engine::ctx();
+    if (!ctx)
+      return;
+    const size_t n_values = n_frames * n_channels;
+    const size_t n = size_t (frames_per_blk + 5) * Params::frame_size * n_channels;      // values of one padded block
+    size_t first_sample, last_sample, pad_start = n, pad_end = n;
+    if (pos == Pos::START)
+      {
+        first_sample = 0;
+        last_sample = min (n, n_values);
+        if (last_sample < n)                    // available samples + padding must always be one long block
+          pad_start += n - last_sample;
+      }
+    else
+      {
+        if (n_values <= n)
+          return;
+        first_sample = n_values - n;
+        last_sample = n_values;
+      }
+    const double time_offset = double (first_sample) / sample_rate / n_channels;
+    /* scan_silence on the padded signal: [wav_first, wav_last) in value units */
+    size_t nz_first = first_sample, nz_last = last_sample;
+    while (nz_first < last_sample && samples[nz_first] == 0)
+      nz_first++;
+    while (nz_last > nz_first && samples[nz_last - 1] == 0)
+      nz_last--;
+    size_t wav_first, wav_last;
+    const size_t ext_values = pad_start + (last_sample - first_sample) + pad_end;
+    if (nz_first == last_sample)                // all zero
+      wav_first = wav_last = ext_values;
+    else
+      {
+        wav_first = pad_start + (nz_first - first_sample);
+        wav_last = pad_start + (nz_last - first_sample);
+      }
+    const size_t ext_frames = ext_values / n_channels;
+    if (awm_pcm_bind (ctx, samples + first_sample, (last_sample - first_sample) / n_channels, n_channels, pad_start / n_channels, pad_end / n_channels))
+      {
+        error ("audiowmark: %s\n", awm_last_error (ctx));
+        return;
+      }
+    SyncFinder sync_finder;
+    vector<SyncFinder::KeyResult> key_results = sync_finder.search (key_list, ext_frames, n_channels, SyncFinder::Mode::CLIP, wav_first, wav_last);
+    const size_t count = mark_sync_frame_count() + mark_data_frame_count();
+    for (const auto& key_result : key_results)
+      {
+        const Key& key = key_result.key;
+        vector<uint64_t> indices;
+        for (const auto& s : key_result.sync_scores)
+          {
+            indices.push_back (s.index);
+            indices.push_back (s.index + count * Params::frame_size);
+          }
+        vector<vector<float>> raw;
+        vector<int> valid;
+        if (indices.empty() || !decode_raw_bits (key, indices, raw, valid))
+          continue;
+        vector<VitJob> jobs;
+        for (size_t i = 0; i < key_result.sync_scores.size(); i++)
+          if (valid[2 * i] && valid[2 * i + 1])
+            {
+              const auto& sync_score = key_result.sync_scores[i];
+              const vector<float>& r1 = raw[2 * i], & r2 = raw[2 * i + 1];
+              vector<float> raw_bit_vec (r1.size() * 2);
+              for (size_t k = 0; k < r1.size(); k++)
+                {
+                  raw_bit_vec[2 * k]     = sync_score.block_type == ConvBlockType::a ? r1[k] : r2[k];
+                  raw_bit_vec[2 * k + 1] = sync_score.block_type == ConvBlockType::a ? r2[k] : r1[k];
+                }
+              SyncFinder::Score sync_score_nopad = sync_score;
+              sync_score_nopad.index = time_offset * sample_rate;
+              jobs.push_back ({ raw_bit_vec, ConvBlockType::ab, time_offset, sync_score_nopad, ResultSet::Type::CLIP });
+            }
+        run_viterbi_jobs (key, jobs, result_set, speed);
+      }
+  }
+public:
+  explicit ClipDecoder (double speed) : frames_per_blk (mark_sync_frame_count() + mark_data_frame_count()), speed (speed) {}
+  void
+  run (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set)
+  {
+    const int wav_frames = n_frames / Params::frame_size;
+    if (wav_frames < frames_per_blk * 3.1)       // clip decoder is only used for small inputs
+      {
+        run_block (key_list, samples, n_frames, n_channels, sample_rate, result_set, Pos::START);
+        run_block (key_list, samples, n_frames, n_channels, sample_rate, result_set, Pos::END);
+      }
+  }
+};
+
+/* decode (src/wmget.cc:886-939) for one chunk */
+int
+decode_chunk (ResultSet& result_set, const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
+              bool first_chunk)
+{
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx)
+    return 1;
+  if (Params::detect_speed || Params::detect_speed_patient || Params::try_speed > 0)
+    {
+      error ("audiowmark: speed detection / --try-speed is not supported in this build\n");
+      return 1;
+    }
+  if (awm_pcm_bind (ctx, samples, n_frames, n_channels, 0, 0))
+    {
+      error ("audiowmark: %s\n", awm_last_error (ctx));
+      return 1;
+    }
+  BlockDecoder block_decoder (1);
+  block_decoder.run (key_list, n_frames, n_channels, sample_rate, result_set);
+  if (first_chunk)
+    {
+      ClipDecoder clip_decoder (1);
+      clip_decoder.run (key_list, samples, n_frames, n_channels, sample_rate, result_set);
+    }
+  result_set.set_debug_sync (block_decoder.debug_sync());
+  return 0;
+}
+
+} // namespace
+
+/* chunk geometry of WavChunkLoader (src/wavchunkloader.cc:54-163): chunks of get_chunk_size minutes that
+ * overlap by two blocks * 1.3 */
+static void
+chunk_sizes (int sample_rate, size_t& max_frames, size_t& overlap_frames)
+{
+  max_frames = lrint (Params::get_chunk_size * 60 * sample_rate);
+  const double block_seconds = (mark_sync_frame_count() + mark_data_frame_count()) * Params::frame_size / double (Params::mark_sample_rate);
+  overlap_frames = lrint (2 * block_seconds * 1.3 * sample_rate);
+}
+
+int
+get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set)
+{
+  if (sample_rate != Params::mark_sample_rate)
+    {
+      error ("audiowmark: input sample rate %d: only %d Hz is supported (resampling is not available in this build)\n", sample_rate, Params::mark_sample_rate);
+      return 1;
+    }
+  size_t max_frames, overlap;
+  chunk_sizes (sample_rate, max_frames, overlap);
+  size_t start = 0, end = min (max_frames, n_frames);
+  double time_offset = 0;
+  bool first_chunk = true, eof = end < max_frames;
+  if (n_frames == 0)
+    return 0;
+  for (;;)
+    {
+      ResultSet chunk_result_set;
+      if (decode_chunk (chunk_result_set, key_list, samples + start * n_channels, end - start, n_channels, sample_rate, first_chunk))
+        return 1;
+      chunk_result_set.apply_time_offset (time_offset);
+      result_set.merge (chunk_result_set);
+      first_chunk = false;
+      if (eof)
+        break;
+      time_offset += double (end - start - overlap) / sample_rate;
+      start = end - overlap;
+      const size_t new_end = min (start + max_frames, n_frames);
+      eof = (new_end - start) < max_frames;
+      end = new_end;
+    }
+  result_set.sort (key_list);
+  return 0;
+}
+
+static int
+report (ResultSet& result_set, size_t time_length, const vector<int>& orig_bits)
+{
+  if (!Params::json_output.empty())
+    result_set.print_json (time_length, Params::json_output);
+  if (Params::json_output != "-")
+    result_set.print();
+  if (!orig_bits.empty())
+    {
+      const int match_count = result_set.print_match_count (orig_bits);
+      result_set.print_debug_sync();
+      if (Params::expect_matches >= 0)
+        {
+          printf ("expect_matches %d\n", Params::expect_matches);
+          if (match_count != Params::expect_matches)
+            return 1;
+        }
+      else if (!match_count)
+        return 1;
+    }
+  return 0;
+}
+
+int
+get_watermark (const vector<Key>& key_list, const string& infile, const string& orig_pattern)
+{
+  vector<int> orig_bitvec;
+  if (!orig_pattern.empty())
+    {
+      orig_bitvec = parse_payload (orig_pattern);
+      if (orig_bitvec.empty())
+        return 1;
+    }
+  /* the reference streams chunk by chunk to bound host memory; the device holds 180 GB, so the file is
+   * read once and the same chunk geometry is applied to the buffer */
+  WavData wav;
+  Error err = wav.load (infile);
+  if (err)
+    {
+      error ("audiowmark: error loading %s: %s\n", infile.c_str(), err.message());
+      return 1;
+    }
+  if (Params::test_truncate)
+    {
+      const size_t want = size_t (wav.sample_rate()) * wav.n_channels() * Params::test_truncate;
+      if (want < wav.n_values())
+        wav.mutable_samples().resize (want);
+    }
+  ResultSet result_set;
+  if (get_watermark_buffer (key_list, wav.samples().data(), wav.n_frames(), wav.n_channels(), wav.sample_rate(), result_set))
+    return 1;
+  const size_t time_length = lrint (wav.n_values() / double (wav.sample_rate() * wav.n_channels()));
+  return report (result_set, time_length, orig_bitvec);
+}

@@ -1,0 +1,197 @@
+// awm_hostapi.cc -- plain C entry points over the host-side C++ (tables, add, get) so that the parity
+// tests and bench.py can drive exactly what the CLI runs.  Table functions are pure host code (no GPU).
+#include "awm_results.hh"
+#include "awm_engine.hh"
+#include "awm_tables.hh"
+#include "awm_util.hh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static Key
+make_key (const unsigned char *key16, const char *name)
+{
+  Key k;
+  k.set_key (key16, name ? name : "");
+  return k;
+}
+
+extern "C" {
+
+void
+awmh_set_params (double water_delta, int frames_per_bit, int mix, int hard, double sync_threshold2, int n_best,
+                 double chunk_size_min, int test_no_limiter, int test_no_sync, int gpu_device, int quiet)
+{
+  Params::water_delta = water_delta;
+  Params::frames_per_bit = frames_per_bit;
+  Params::mix = mix != 0;
+  Params::hard = hard != 0;
+  Params::sync_threshold2 = sync_threshold2;
+  Params::get_n_best = n_best;
+  Params::get_chunk_size = chunk_size_min;
+  Params::test_no_limiter = test_no_limiter != 0;
+  Params::test_no_sync = test_no_sync != 0;
+  Params::gpu_device = gpu_device;
+  set_log_level (quiet ? Log::WARNING : Log::INFO);
+}
+
+int awmh_frames_per_block() { return int (frames_per_block()); }
+int awmh_n_coded_bits()     { return int (code_size (ConvBlockType::a, Params::payload_size)); }
+
+int
+awmh_random_u64 (const unsigned char *key16, uint64_t seed, int stream, uint64_t *out, int n)
+{
+  Random r (make_key (key16, ""), seed, Random::Stream (stream));
+  for (int i = 0; i < n; i++)
+    out[i] = r();
+  return 0;
+}
+
+int
+awmh_gen_noise (const unsigned char *key16, float *out, size_t n_values)
+{
+  Random r (make_key (key16, ""), 0, Random::Stream::data_up_down);
+  for (size_t i = 0; i < n_values; i++)
+    out[i] = r.random_double() * 2 - 1;
+  return 0;
+}
+
+int
+awmh_sync_table (const unsigned char *key16, int mode, awm_sync_entry *out, int max_entries, int *bit_offsets /* [sync_bits + 1] */)
+{
+  const SyncTable t = gen_sync_table (make_key (key16, ""), mode);
+  if (int (t.entries.size()) > max_entries)
+    return -1;
+  memcpy (out, t.entries.data(), t.entries.size() * sizeof (awm_sync_entry));
+  memcpy (bit_offsets, t.bit_offsets.data(), t.bit_offsets.size() * sizeof (int));
+  return int (t.entries.size());
+}
+
+int
+awmh_mix_table (const unsigned char *key16, awm_mix_entry *out, int max_entries, uint16_t *order, int max_order)
+{
+  const Key key = make_key (key16, "");
+  const std::vector<MixEntry> mix = gen_mix_entries (key);
+  const std::vector<unsigned> ord = bit_order (key, code_size (ConvBlockType::a, Params::payload_size));
+  if (int (mix.size()) > max_entries || int (ord.size()) > max_order)
+    return -1;
+  for (size_t i = 0; i < mix.size(); i++)
+    {
+      out[i].frame = mix[i].frame;
+      out[i].up = mix[i].up;
+      out[i].down = mix[i].down;
+    }
+  for (size_t i = 0; i < ord.size(); i++)
+    order[i] = ord[i];
+  return int (mix.size());
+}
+
+int
+awmh_frame_mod (const unsigned char *key16, const char *payload_hex, uint8_t *out, size_t out_size)
+{
+  const std::vector<int> bitvec = parse_payload (payload_hex);
+  if (bitvec.empty())
+    return -1;
+  const std::vector<uint8_t> fm = gen_frame_mod_ab (make_key (key16, ""), bitvec);
+  if (fm.size() > out_size)
+    return -1;
+  memcpy (out, fm.data(), fm.size());
+  return int (fm.size());
+}
+
+int
+awmh_conv_encode (int block_type, const uint8_t *bits, int n, uint8_t *out, int max_out)
+{
+  std::vector<int> in (bits, bits + n);
+  const std::vector<int> enc = conv_encode (ConvBlockType (block_type), in);
+  if (int (enc.size()) > max_out)
+    return -1;
+  for (size_t i = 0; i < enc.size(); i++)
+    out[i] = enc[i];
+  return int (enc.size());
+}
+
+/* add_stream_watermark on buffers (host or device pointers) */
+int
+awmh_add (const unsigned char *key16, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,
+          const char *payload_hex, int *data_blocks, double *snr_db)
+{
+  AddStats stats;
+  const int rc = add_watermark_buffer (make_key (key16, ""), in, out, n_frames, n_channels, sample_rate, payload_hex, (data_blocks || snr_db) ? &stats : nullptr);
+  if (data_blocks)
+    *data_blocks = stats.data_blocks;
+  if (snr_db)
+    *snr_db = stats.snr_db;
+  return rc;
+}
+
+/* get_watermark on a buffer (host pointer; a device pointer is accepted for inputs longer than 3.1 blocks,
+ * where the clip decoder is not used).  Writes the --json document into json_out. */
+int
+awmh_get (const unsigned char *keys16, const char *const *names, int n_keys, const float *pcm, size_t n_frames, int n_channels,
+          int sample_rate, char *json_out, size_t json_cap, int *n_patterns)
+{
+  std::vector<Key> key_list;
+  for (int k = 0; k < n_keys; k++)
+    key_list.push_back (make_key (keys16 + 16 * k, names ? names[k] : ""));
+  ResultSet result_set;
+  const int rc = get_watermark_buffer (key_list, pcm, n_frames, n_channels, sample_rate, result_set);
+  if (rc)
+    return rc;
+  if (n_patterns)
+    *n_patterns = int (result_set.all().size());
+  if (json_out && json_cap)
+    {
+      char *buf = nullptr;
+      size_t len = 0;
+      FILE *f = open_memstream (&buf, &len);
+      result_set.print_json (f, size_t (lrint (double (n_frames) / sample_rate)));
+      fclose (f);
+      if (len + 1 > json_cap)
+        {
+          free (buf);
+          return -2;
+        }
+      memcpy (json_out, buf, len + 1);
+      free (buf);
+    }
+  return 0;
+}
+
+uint64_t
+awmh_gpu_launches()
+{
+  awm_ctx *c = Engine::ctx();
+  return c ? awm_launch_count (c) : 0;
+}
+
+void *
+awmh_gpu_stream()
+{
+  awm_ctx *c = Engine::ctx();
+  return c ? awm_stream (c) : nullptr;
+}
+
+int
+awmh_profile_enable (int on)
+{
+  awm_ctx *c = Engine::ctx();
+  return c ? awm_profile_enable (c, on) : 1;
+}
+
+int
+awmh_profile_report (char *json_out, size_t cap)
+{
+  awm_ctx *c = Engine::ctx();
+  return c ? awm_profile_report (c, json_out, cap) : 1;
+}
+
+void
+awmh_shutdown()
+{
+  Engine::shutdown();
+}
+
+} // extern "C"

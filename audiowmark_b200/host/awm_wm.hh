@@ -1,0 +1,37 @@
+// awm_wm.hh -- entry points of the watermark drivers, same names / argument meaning as the reference
+// (src/wmcommon.hh:226-228, src/syncfinder.hh:71-121).
+#pragma once
+#include <string>
+#include <vector>
+#include "awm_params.hh"
+#include "awm_random.hh"
+#include "awm_code.hh"
+#include "awm_streams.hh"
+
+int add_stream_watermark (const Key& key, AudioInputStream *in_stream, AudioOutputStream *out_stream, const std::string& bits, size_t zero_frames);
+int add_watermark (const Key& key, const std::string& infile, const std::string& outfile, const std::string& bits);
+int get_watermark (const std::vector<Key>& key_list, const std::string& infile, const std::string& orig_pattern);
+
+/* buffer-level drivers used by the C host API (bench / tests): same computation without file I/O */
+struct AddStats { int data_blocks = 0; double snr_db = 0; };
+int add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,
+                          const std::string& bits, AddStats *stats);
+
+class ResultSet;
+int get_watermark_buffer (const std::vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
+                          ResultSet& result_set);
+
+int frame_count (const WavData& wav_data);
+
+class SyncFinder
+{
+public:
+  enum class Mode { BLOCK, CLIP };
+  struct Score { size_t index; double quality; ConvBlockType block_type; };
+  struct KeyResult { Key key; std::vector<Score> sync_scores; };
+  /* searches the PCM currently bound to the GPU context; n_frames/n_channels describe it
+   * (padded length for CLIP mode), wav_first/wav_last = non-silent value range */
+  std::vector<KeyResult> search (const std::vector<Key>& key_list, size_t n_frames, int n_channels, Mode mode,
+                                 size_t wav_first, size_t wav_last);
+  static double normalize_sync_quality (double raw_quality);
+};

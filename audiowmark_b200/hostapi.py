@@ -1,0 +1,167 @@
+"""ctypes binding of lib/libawm_host.so: the host-side C++ (key tables, `add`, `get`) behind plain C
+entry points (audiowmark_b200/host/awm_hostapi.cc).  This is the reference-facing call path the CLI
+uses; bench.py's e2e number and the end-to-end parity tests go through it."""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+
+import numpy as np
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
+CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
+
+EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown"]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run __graft_entry__.build()" % LIB_PATH)
+        capi.load()        # libawm_b200.so first (rpath $ORIGIN also finds it)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.awmh_gpu_launches.restype = ctypes.c_uint64
+        lib.awmh_gpu_stream.restype = ctypes.c_void_p
+        _lib = lib
+    return _lib
+
+
+def _ptr(x):
+    if x is None:
+        return ctypes.c_void_p(0)
+    if isinstance(x, (int, np.integer)):
+        return ctypes.c_void_p(int(x))
+    assert x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data_as(ctypes.c_void_p)
+
+
+def _key(key) -> bytes:
+    k = bytes(key) if key is not None else bytes(16)
+    assert len(k) == 16
+    return k
+
+
+def set_params(water_delta=0.01, frames_per_bit=2, mix=True, hard=False, sync_threshold2=0.35, n_best=8, chunk_size_min=30.0,
+               test_no_limiter=False, test_no_sync=False, gpu_device=0, quiet=True):
+    load().awmh_set_params(ctypes.c_double(water_delta), ctypes.c_int(frames_per_bit), ctypes.c_int(mix), ctypes.c_int(hard),
+                           ctypes.c_double(sync_threshold2), ctypes.c_int(n_best), ctypes.c_double(chunk_size_min),
+                           ctypes.c_int(test_no_limiter), ctypes.c_int(test_no_sync), ctypes.c_int(gpu_device), ctypes.c_int(quiet))
+
+
+def frames_per_block() -> int:
+    return load().awmh_frames_per_block()
+
+
+def n_coded_bits() -> int:
+    return load().awmh_n_coded_bits()
+
+
+def random_u64(key, seed: int, stream: int, n: int) -> np.ndarray:
+    out = np.zeros(n, np.uint64)
+    load().awmh_random_u64(_key(key), ctypes.c_uint64(seed), ctypes.c_int(stream), _ptr(out), ctypes.c_int(n))
+    return out
+
+
+def gen_noise(key, n_values: int) -> np.ndarray:
+    out = np.zeros(n_values, np.float32)
+    load().awmh_gen_noise(_key(key), _ptr(out), ctypes.c_size_t(n_values))
+    return out
+
+
+def sync_table(key, mode: int):
+    ent = np.zeros(4096, capi.SYNC_ENTRY)
+    off = np.zeros(7, np.int32)
+    n = load().awmh_sync_table(_key(key), ctypes.c_int(mode), _ptr(ent), ctypes.c_int(len(ent)), _ptr(off))
+    assert n > 0
+    return ent[:n].copy(), off
+
+
+def mix_table(key):
+    ent = np.zeros(200000, capi.MIX_ENTRY)
+    order = np.zeros(8192, np.uint16)
+    n = load().awmh_mix_table(_key(key), _ptr(ent), ctypes.c_int(len(ent)), _ptr(order), ctypes.c_int(len(order)))
+    assert n > 0
+    return ent[:n].copy(), order[:n_coded_bits()].copy()
+
+
+def frame_mod(key, payload_hex: str) -> np.ndarray:
+    fpb = frames_per_block()
+    out = np.zeros((2, fpb, 101), np.uint8)
+    n = load().awmh_frame_mod(_key(key), payload_hex.encode(), _ptr(out), ctypes.c_size_t(out.size))
+    assert n == out.size
+    return out
+
+
+def conv_encode(block_type: int, bits) -> np.ndarray:
+    b = np.ascontiguousarray(bits, np.uint8)
+    out = np.zeros((len(b) + 15) * 12, np.uint8)
+    n = load().awmh_conv_encode(ctypes.c_int(block_type), _ptr(b), ctypes.c_int(len(b)), _ptr(out), ctypes.c_int(len(out)))
+    return out[:n].copy()
+
+
+def add(pcm_in, payload_hex: str, key=None, pcm_out=None, n_frames=None, channels=None, sample_rate=44100, want_stats=False):
+    """add_stream_watermark on a buffer: numpy arrays (host) or device pointers (ints)."""
+    if isinstance(pcm_in, np.ndarray):
+        pcm_in = np.ascontiguousarray(pcm_in, np.float32)
+        n_frames, channels = pcm_in.shape
+        if pcm_out is None:
+            pcm_out = np.empty_like(pcm_in)
+    blocks, snr = ctypes.c_int(), ctypes.c_double()
+    rc = load().awmh_add(_key(key), _ptr(pcm_in), _ptr(pcm_out), ctypes.c_size_t(n_frames), ctypes.c_int(channels), ctypes.c_int(sample_rate),
+                         payload_hex.encode(), ctypes.byref(blocks) if want_stats else None, ctypes.byref(snr) if want_stats else None)
+    if rc:
+        raise RuntimeError("awmh_add failed (rc=%d); see stderr" % rc)
+    return (pcm_out, blocks.value, snr.value) if want_stats else pcm_out
+
+
+def get(pcm, keys=None, names=None, n_frames=None, channels=None, sample_rate=44100, parse=True):
+    """get_watermark on a buffer -> the --json document (dict) of the run."""
+    keys = keys or [bytes(16)]
+    names = names or [""] * len(keys)
+    if isinstance(pcm, np.ndarray):
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        n_frames, channels = pcm.shape
+    kb = b"".join(_key(k) for k in keys)
+    name_arr = (ctypes.c_char_p * len(keys))(*[n.encode() for n in names])
+    cap = 1 << 22
+    buf = ctypes.create_string_buffer(cap)
+    n_pat = ctypes.c_int()
+    rc = load().awmh_get(kb, name_arr, ctypes.c_int(len(keys)), _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
+                         ctypes.c_int(sample_rate), buf, ctypes.c_size_t(cap), ctypes.byref(n_pat))
+    if rc:
+        raise RuntimeError("awmh_get failed (rc=%d); see stderr" % rc)
+    text = buf.value.decode()
+    return json.loads(text) if parse else text
+
+
+def gpu_launches() -> int:
+    return int(load().awmh_gpu_launches())
+
+
+def gpu_stream() -> int:
+    return int(load().awmh_gpu_stream() or 0)
+
+
+def profile_enable(on=True):
+    if load().awmh_profile_enable(ctypes.c_int(1 if on else 0)):
+        raise RuntimeError("no GPU context")
+
+
+def profile_report() -> dict:
+    buf = ctypes.create_string_buffer(1 << 16)
+    if load().awmh_profile_report(buf, ctypes.c_size_t(len(buf))):
+        raise RuntimeError("awmh_profile_report failed")
+    return json.loads(buf.value.decode())
+
+
+def shutdown():
+    if _lib is not None:
+        _lib.awmh_shutdown()

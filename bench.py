@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the spectral watermark hot path (BASELINE.json).
+
+metric   audio frames/sec embed+detect, 44.1 kHz stereo (PCM sample-frames per second of
+         `add` + `get` wall time; decoded payload checked against the embedded one)
+workload BASELINE.json configs[1]: 1 h stereo 44.1 kHz per GPU (weak scaling: every rank owns
+         one hour of the N-hour stream; ranks exchange nothing but the final result gather)
+step     one `add` (embed + limiter) followed by one `get` (chunked sync search, block decode,
+         Viterbi, result merge) over the whole hour, through the host-side C++ drivers
+         (audiowmark_b200/host -> C ABI -> sm_100a kernels)
+
+value  : inputs resident in HBM (device pointers), timed with CUDA events on the context stream
+e2e    : the same call with pinned HOST buffers; H2D of the input for add, D2H of the marked audio,
+         H2D of the marked audio for get and D2H of the results are all inside the timed region
+roofline / kernels : per-kernel CUDA-event times of the timed steps (awm_profile_*)
+cpu_baseline       : the reference's own CPU implementation (oracle/_ref/audiowmark, unmodified
+                     sources, FFT = in-repo shim) on a bounded sample, rank 0 at N=1 only
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--minutes M]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+RATE = 44100
+PAYLOAD = "0123456789abcdef0011223344556677"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "audiowmark")
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+
+def run_reference(steps, warmup, minutes):
+    """The reference's own CPU `add` + `get` (unmodified sources in oracle/_ref) on a bounded sample."""
+    import numpy as np
+    import awm_oracle as O
+    if not os.path.exists(REF_BIN):
+        import build_oracle
+        build_oracle.build_reference()
+    if not os.path.exists(REF_BIN):
+        raise RuntimeError("oracle/_ref/audiowmark is missing (built by __graft_entry__.build() where /root/reference is mounted)")
+    seconds = minutes * 60.0
+    n = int(seconds * RATE)
+    tmp = tempfile.mkdtemp(prefix="awm_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    src, dst = os.path.join(tmp, "in.wav"), os.path.join(tmp, "wm.wav")
+    rng = np.random.default_rng(1)
+    x = (rng.random((n, 2), dtype=np.float32) - 0.5).astype(np.float32)
+    O.write_wav16(src, x)
+    del x
+    times = []
+    ok = True
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        subprocess.run([REF_BIN, "-q", "add", src, dst, PAYLOAD], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t1 = time.perf_counter()
+        p = subprocess.run([REF_BIN, "-q", "cmp", dst, PAYLOAD], capture_output=True, text=True)
+        t2 = time.perf_counter()
+        ok = ok and p.returncode == 0
+        if it >= warmup:
+            times.append((t1 - t0, t2 - t1))
+    for f in (src, dst):
+        try:
+            os.remove(f)
+        except OSError:
+            pass
+    os.rmdir(tmp)
+    t_add = sum(t[0] for t in times) / len(times)
+    t_get = sum(t[1] for t in times) / len(times)
+    return {"value": n / (t_add + t_get), "t_add_s": t_add, "t_get_s": t_get, "n_frames": n, "payload_ok": ok,
+            "cores": os.cpu_count(), "sample": "%g min stereo 44.1 kHz s16 WAV on tmpfs: `audiowmark add` (1 thread) + `audiowmark cmp` (all threads), wall time incl. file I/O" % minutes}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    minutes = args.minutes if args.minutes else 5.0
+    r = run_reference(args.steps, args.warmup, minutes)
+    line = {
+        "impl": "reference", "metric": "audio frames/sec embed+detect, 44.1 kHz stereo; decoded-bit match vs ref", "value": r["value"],
+        "unit": "PCM frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (r["t_add_s"] + r["t_get_s"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "payload_ok": r["payload_ok"],
+        "config": {"workload": "1 h stereo 44.1 kHz embed+detect (reference CPU path timed on a %g min sample of it)" % minutes,
+                   "sample_frames": r["n_frames"]},
+        "cpu_baseline": {"value": r["value"], "unit": "PCM frames/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "PCM frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+# algorithmic HBM bytes per launch of each kernel, per stereo PCM frame of its input
+def algo_bytes(kernel, n_frames, ch, prof):
+    per_frame = {
+        "k_embed": 8.0 * ch,                         # read 4C + write 4C
+        "k_limiter": 8.0 * ch,                       # read + write in place
+        "k_stft_db": 4.0 * ch + 4 * 81 * 4 / 1024.0,  # read the chunk once, write the four band-major dB matrices
+        "k_sync_approx": 4 * 81 * 4 / 1024.0 + 4 * 8 / 1024.0,   # read the dB matrices once, write one double per candidate
+        "k_local_mean": 4 * (8 + 24) / 1024.0,
+    }
+    return per_frame.get(kernel, 0.0) * n_frames
+
+
+def main_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from audiowmark_b200 import hostapi as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    minutes = args.minutes if args.minutes else 60.0
+    n = int(minutes * 60 * RATE)
+    ch = 2
+    H.set_params(gpu_device=local)
+    # synthetic input: uniform noise at -6 dBFS, generated on the device (value arm) and copied to pinned host memory (e2e arm)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    x_dev = (torch.rand((n, ch), device=dev, generator=g, dtype=torch.float32) - 0.5)
+    y_dev = torch.empty_like(x_dev)
+    x_host = torch.empty((n, ch), dtype=torch.float32, pin_memory=True)
+    y_host = torch.empty((n, ch), dtype=torch.float32, pin_memory=True)
+    x_host.copy_(x_dev)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(H.gpu_stream(), device=dev)
+    want_real = None
+
+    def step_resident():
+        H.add(x_dev.data_ptr(), PAYLOAD, None, y_dev.data_ptr(), n, ch)
+        return H.get(y_dev.data_ptr(), n_frames=n, channels=ch)
+
+    def step_e2e():
+        H.add(x_host.numpy(), PAYLOAD, None, y_host.numpy())
+        return H.get(y_host.numpy())
+
+    def check(doc):
+        real = [m for m in doc["matches"] if m["quality"] > 0.35]
+        return len(real) > 0 and all(m["bits"] == PAYLOAD for m in real), len(real)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile):
+        barrier()
+        if profile:
+            H.profile_enable(True)
+        l0 = H.gpu_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        doc = None
+        for _ in range(steps):
+            doc = fn()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        prof = H.profile_report() if profile else None
+        if profile:
+            H.profile_enable(False)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall, doc, H.gpu_launches() - l0, prof
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, wall, doc, launches, prof = timed(step_resident, args.steps, True)
+    clk = clocks.stop() if rank == 0 else None
+    ok, n_real = check(doc)
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    ms_e2e, wall_e2e, doc2, _, _ = timed(step_e2e, args.steps, False)
+    ok2, _ = check(doc2)
+
+    # final gather of the per-rank results (the only exchange of the sharded job): detections per rank
+    det = torch.tensor([n_real, int(ok), int(ok2)], device=dev, dtype=torch.int64)
+    if world > 1:
+        gathered = [torch.zeros_like(det) for _ in range(world)]
+        dist.all_gather(gathered, det)
+        det_all = torch.stack(gathered).cpu().tolist()
+    else:
+        det_all = [det.cpu().tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_frames = n * world
+    ms_step = ms / args.steps
+    value = total_frames / (ms_step / 1e3)
+    e2e_value = total_frames / (ms_e2e / args.steps / 1e3)
+    # per-kernel picture and the roofline of the dominant kernel
+    peaks = measured_peaks()
+    peak_gbs = (peaks or {}).get("hbm_gbs", 6650.0)
+    n_chunk_frames = n * 1.0747 if minutes >= 59 else n         # chunk overlap of `get`
+    kernels = {}
+    for name, r in (prof or {}).items():
+        per_launch_ms = r["ms"] / max(r["launches"], 1)
+        fr = n_chunk_frames if name in ("k_stft_db", "k_sync_approx", "k_local_mean") else n
+        ab_total = algo_bytes(name, fr, ch, prof) * args.steps
+        kernels[name] = {"launches": r["launches"], "ms_total": round(r["ms"], 4), "ms_per_launch": round(per_launch_ms, 5),
+                         "share_of_step": round(r["ms"] / ms, 4),
+                         "algo_GBps": round(ab_total / (r["ms"] / 1e3) / 1e9, 2) if ab_total else None}
+    dominant = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
+    roofline = None
+    if dominant:
+        a = kernels[dominant]["algo_GBps"] or 0.0
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": a, "peak": peak_gbs, "unit": "GB/s", "frac": round(a / peak_gbs, 5),
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                    "note": "algorithmic bytes per launch / CUDA-event launch time; see DESIGN.md section 5 for the per-kernel byte model"}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_reference(1, 0, 3.0)
+            cpu = {"value": r["value"], "unit": "PCM frames/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"],
+                   "t_add_s": round(r["t_add_s"], 3), "t_get_s": round(r["t_get_s"], 3), "payload_ok": r["payload_ok"]}
+        except Exception as e:          # the bench line must still print
+            cpu = {"value": None, "unit": "PCM frames/s", "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: %s" % e}
+    line = {
+        "metric": "audio frames/sec embed+detect, 44.1 kHz stereo; decoded-bit match vs ref",
+        "value": value, "unit": "PCM frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%g min stereo 44.1 kHz embed+detect per GPU (BASELINE.json configs[1]%s)" % (minutes, "" if minutes == 60 else ", shortened"),
+                   "pcm_frames_per_gpu": n, "channels": ch, "payload_bits": 128, "get_chunks": "30 min, 134.4 s overlap",
+                   "parallelism": "chunk/frame-block shard per GPU, final result gather only" if world > 1 else "1 GPU",
+                   "l2": "inputs (%.2f GB per pass) larger than L2" % (n * ch * 4 / 1e9)},
+        "analysis_frames_per_s": value / 1024.0,
+        "payload_ok": bool(all(d[1] for d in det_all)), "detections_per_rank": [d[0] for d in det_all],
+        "e2e": {"value": e2e_value, "unit": "PCM frames/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 2 * n * ch * 4, "d2h_bytes_per_step": n * ch * 4, "payload_ok": bool(all(d[2] for d in det_all)),
+                "api": "hostapi.add + hostapi.get (C++ add_watermark_buffer / get_watermark_buffer) on pinned host buffers"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "kernels": kernels,
+        "host_wall_ms_per_step": 1e3 * wall / args.steps,
+        "cpu_baseline": cpu,
+        "clocks": clk,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--minutes", type=float, default=0.0, help="audio length per GPU (default 60 = BASELINE configs[1]; reference arm: 5)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

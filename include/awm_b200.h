@@ -65,6 +65,10 @@ uint64_t    awm_launch_count (const awm_ctx *ctx);
 /* CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
 void       *awm_stream (awm_ctx *ctx);
 int         awm_synchronize (awm_ctx *ctx);
+/* measurement aid: when enabled every kernel launch is bracketed by CUDA events on the context stream;
+ * awm_profile_report synchronises, writes {"kernel": {"launches": n, "ms": total}, ...} as JSON and resets */
+int         awm_profile_enable (awm_ctx *ctx, int on);
+int         awm_profile_report (awm_ctx *ctx, char *json_out, size_t json_cap);
 
 /* ---- FFTProcessor (src/fft.hh:25-44, src/fft.cc:82-118) ------------------------------------
  * batched r2c / unnormalised c2r, n must be 1024.  in/out layouts as FFTW:

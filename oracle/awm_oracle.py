@@ -556,13 +556,15 @@ def embed(samples: np.ndarray, key: Key, bits: str, P: Params | None = None, rat
     wm[:F] = wm[:F] + wmf[2:F + 2] * w0
     wm = np.ascontiguousarray(wm.transpose(0, 2, 1)).reshape((F + 1) * N, nch)
     mixed = wm + ext                                                          # wmadd.cc:564-565
-    d = wm.astype(np.float64)          # the loop also sums the zero-padded tail (wmadd.cc:553-563)
+    bs = rate * P.limiter_block_size_ms // 1000
+    runs = embed_gen_runs(n, N, not P.test_no_limiter, bs)
+    # --snr sums every frame the loop emits (runs - 1 of them, wmadd.cc:553-563): the zero-padded tail of the last
+    # frame always, the spill frame F only when the limiter keeps the loop running
+    d = wm[:min(runs - 1, F + 1) * N].astype(np.float64)
     o = samples.astype(np.float64)
     snr = 10 * math.log10((o * o).sum() / max((d * d).sum(), 1e-300))
     out = mixed if P.test_no_limiter else limiter(mixed, rate, P)
     # data block counter (wmadd.cc:311-313,345-350): number of WatermarkGen::run calls made by the loop
-    bs = rate * P.limiter_block_size_ms // 1000
-    runs = embed_gen_runs(n, N, not P.test_no_limiter, bs)
     f0 = 2 * fpb - P.frames_pad_start
     m_data_blocks = (f0 + runs) // fpb - f0 // fpb
     return EmbedResult(out[:n].copy(), max(m_data_blocks - 1, 0), snr, wm[:n].copy() if keep_wm else None)
@@ -925,6 +927,23 @@ class ResultSet:                                     # wmget.cc:163-474
                 sec = int(p.time)
                 out.append("pattern %2d:%02d %s %.3f %.3f %s" % (sec // 60, sec % 60, bit_vec_to_str(p.bit_vec), p.sync_score.quality, p.decode_error, p.block_str()))
         return out
+
+    def json_doc(self, time_length: int) -> dict:
+        """print_json (wmget.cc:339-382): numbers are kept as the strings the reference prints."""
+        m = []
+        for p in self.patterns:
+            btype = {A: "A", B: "B", AB: "AB"}[p.sync_score.block_type]
+            if p.type == TYPE_ALL:
+                btype = "ALL"
+            if p.type == TYPE_CLIP:
+                btype = "CLIP-" + btype
+            if p.speed != 1:
+                btype += "-SPEED"
+            sec = int(p.time)
+            m.append({"key": p.key.name, "pos": "%d:%02d" % (sec // 60, sec % 60), "bits": bit_vec_to_str(p.bit_vec),
+                      "quality": "%.5f" % p.sync_score.quality, "error": "%.6f" % p.decode_error, "rating": "%.5f" % p.rating,
+                      "type": btype, "speed": "%.6f" % p.speed})
+        return {"length": "%d:%02d" % (time_length // 60, time_length % 60), "matches": m}
 
     def match_count(self, orig_bits):
         return sum(1 for p in self.patterns if p.bit_vec == orig_bits)

@@ -1,0 +1,92 @@
+"""CPU: pins the oracle against the reference's own outputs.
+
+tests/golden/golden.json was produced by tests/golden/make_golden.py with the unmodified reference
+sources (oracle/_ref).  The oracle has to reproduce them exactly: PCM hashes bit-for-bit, pattern
+lists with every printed digit.  These are the "golden vectors" of the path -- the reference tree
+itself ships none."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import awm_oracle as O
+import awm_testlib as T
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+P = O.Params()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def q16(x):
+    return O.int16_to_float(O.quantize_sndfile16(x))
+
+
+def fmt_ref_json(doc):
+    out = []
+    for m in doc["matches"]:
+        out.append({"key": m["key"], "pos": m["pos"], "bits": m["bits"], "quality": "%.5f" % m["quality"], "error": "%.6f" % m["error"],
+                    "rating": "%.5f" % m["rating"], "type": m["type"], "speed": "%.6f" % m["speed"]})
+    return {"length": doc["length"], "matches": out}
+
+
+def test_keyed_noise_generator_matches_reference():
+    n16 = O.quantize_sndfile16(O.gen_noise(20))
+    assert [int(v) for v in n16.reshape(-1)[:32]] == G["gen_noise_20s"]["head"]
+    assert sha(n16) == G["gen_noise_20s"]["sha256"]
+    assert sha(O.quantize_sndfile16(O.gen_noise(2, key=O.Key.test_key(7)))) == G["gen_noise_2s_testkey7"]["sha256"]
+
+
+CASES = {
+    "clip10_mono": lambda: (q16(T.noise(10.0, 1, seed=1234)), O.Key()),
+    "block115": lambda: (q16(T.noise(115.0, 2, seed=1234)), O.Key()),
+    "block115_nolimiter": lambda: (q16(T.noise(115.0, 2, seed=1234)), O.Key()),
+    "block115_testkey3": lambda: (q16(T.noise(115.0, 2, seed=1234)), O.Key.test_key(3)),
+    "limiter30": lambda: (q16(T.noise(30.7, 2, seed=99, amp=1.0)), O.Key()),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_embed_bit_exact_vs_reference(name):
+    g = G[name]
+    x, key = CASES[name]()
+    assert sha(O.quantize_sndfile16(x)) == g["input_sha256"]
+    Pc = O.Params(test_no_limiter="--test-no-limiter" in g["add_args"])
+    r = O.embed(x, key, g["payload"], Pc)
+    out16 = O.quantize_sndfile16(r.samples)
+    assert [int(v) for v in out16.reshape(-1)[:64]] == g["output_head"]
+    assert sha(out16) == g["output_sha256"]
+    assert ("Data Blocks:  %d\n" % r.data_blocks) in g["add_stderr"]
+    if "--snr" in g["add_args"]:
+        assert ("SNR:          %f dB\n" % r.snr_db) in g["add_stderr"]
+
+
+@pytest.mark.parametrize("name", ["clip10_mono", "block115_testkey3"])
+def test_get_exact_vs_reference(name):
+    g = G[name]
+    x, key = CASES[name]()
+    y = q16(O.embed(x, key, g["payload"], P).samples)
+    rs = O.get_watermark(y, [key], P)
+    assert rs.json_doc(int(np.rint(len(y) / 44100.0))) == fmt_ref_json(g["json"])
+    assert "\n".join(rs.lines()) + "\n" == g["get_stdout"]
+    want = O.parse_payload(g["payload"], P)
+    assert ("match_count %d %d\n" % (rs.match_count(want), len(rs.patterns))) in g["cmp_stdout"]
+
+
+def test_sync_after_cut_vs_reference():
+    """tests/sync-test.sh: 200 s reference noise, 882300 samples cut off -> 3 matches."""
+    g = G["noise200"]
+    x = q16(O.gen_noise(200))
+    y16 = O.quantize_sndfile16(O.embed(x, O.Key(), "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", P).samples)
+    assert sha(y16) == g["wm_sha256"]
+    y = O.int16_to_float(y16)[882300:]
+    rs = O.ResultSet()
+    O.block_decoder_run(O.Key(), y, rs, P)
+    rs.sort([O.Key()])
+    assert rs.json_doc(int(np.rint(len(y) / 44100.0))) == fmt_ref_json(g["cut_json"])
+    assert "match_count 3 9" in g["cut_cmp_stdout"]
+    assert rs.match_count(O.parse_payload("f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", P)) == 3
