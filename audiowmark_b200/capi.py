@@ -187,16 +187,16 @@ class Context:
         self._ck(self.lib.awm_decode_blocks(self.h, ctypes.c_int(key_slot), _ptr(idx), ctypes.c_size_t(len(idx)), _ptr(raw), _ptr(valid)))
         return raw, valid
 
-    def viterbi(self, raw_bits: np.ndarray, block_types, hard=False):
-        raw = np.ascontiguousarray(raw_bits, np.float32)
-        if raw.ndim == 1:
-            raw = raw[None]
+    def viterbi(self, jobs, block_types, n_msg_bits=128, hard=False):
+        """jobs: list of 1-D float arrays (or a 2-D array) of raw soft bits, one per code word (mixed A/B/AB allowed)."""
+        jobs = [np.ascontiguousarray(j, np.float32).reshape(-1) for j in jobs]
         bt = np.ascontiguousarray(block_types, np.int32).reshape(-1)
-        n_jobs, n_coded = raw.shape
-        rate = 12 if bt[0] == BLOCK_AB else 6
-        n_msg = n_coded // rate - 15
-        bits = np.zeros((n_jobs, n_msg), np.uint8)
-        err = np.zeros(n_jobs, np.float32)
-        self._ck(self.lib.awm_viterbi(self.h, _ptr(raw), ctypes.c_size_t(n_jobs), ctypes.c_int(n_coded), _ptr(bt), ctypes.c_int(1 if hard else 0),
+        assert len(jobs) == len(bt)
+        for j, t in zip(jobs, bt):
+            assert len(j) == (12 if t == BLOCK_AB else 6) * (n_msg_bits + 15)
+        raw = np.concatenate(jobs) if jobs else np.zeros(0, np.float32)
+        bits = np.zeros((len(jobs), n_msg_bits), np.uint8)
+        err = np.zeros(len(jobs), np.float32)
+        self._ck(self.lib.awm_viterbi(self.h, _ptr(raw), ctypes.c_size_t(len(jobs)), ctypes.c_int(n_msg_bits), _ptr(bt), ctypes.c_int(1 if hard else 0),
                                       _ptr(bits), _ptr(err)))
         return bits, err

@@ -6,6 +6,7 @@
 #include "awm_kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -49,7 +50,8 @@ struct DevBuf
 
 struct SyncTab
 {
-  DevBuf ent, off;
+  DevBuf ent, off, sorted, groups;
+  int n_groups = 0;
   int n_ent = 0, n_bits = 0, total_frames = 0;
   std::vector<awm_sync_entry> h_ent;
   std::vector<int> h_off;
@@ -83,9 +85,9 @@ struct awm_ctx
   DevBuf pcm_own;
 
   DevBuf dbT, have, q, scores;       // approx
-  DevBuf cand_start, cand_noff, S, Hv, rq, rvalid;   // refine
+  DevBuf cand_start, cand_noff, r_ud, r_cnt, rvalid;   // refine
   DevBuf blk_start, D, raw;          // decode
-  DevBuf vit_raw, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
+  DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
   DevBuf emb_in, emb_out, peaks, snr;
 };
 
@@ -246,7 +248,7 @@ awm_destroy (awm_ctx *ctx)
   cudaSetDevice (ctx->device);
   cudaStreamSynchronize (ctx->stream);
   DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores,
-                     &ctx->cand_start, &ctx->cand_noff, &ctx->S, &ctx->Hv, &ctx->rq, &ctx->rvalid, &ctx->blk_start, &ctx->D, &ctx->raw,
+                     &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
                      &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
                      &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr };
   for (DevBuf *b : bufs)
@@ -257,6 +259,8 @@ awm_destroy (awm_ctx *ctx)
         {
           s.ent.release();
           s.off.release();
+          s.sorted.release();
+          s.groups.release();
         }
       k.mix.release();
       k.order.release();
@@ -426,6 +430,43 @@ awm_set_sync_tables (awm_ctx *ctx, int key_slot, int mode, const awm_sync_entry 
   CK (cudaMemcpyAsync (t.ent.p, entries, sizeof (awm_sync_entry) * n_entries, cudaMemcpyHostToDevice, ctx->stream));
   CK (cudaMemcpyAsync (t.off.p, bit_offsets, sizeof (int) * (n_bits + 1), cudaMemcpyHostToDevice, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
+  if (n_bits > 6)
+    return fail (ctx, "awm_set_sync_tables: at most 6 sync bits are supported");
+  /* k_sync_approx walks all entries in ascending frame order (per-bit order is kept: frames are sorted inside a bit) */
+  std::vector<ApproxEntry> sorted (n_entries);
+  {
+    std::vector<int> idx (n_entries), bit_of (n_entries);
+    for (int b = 0; b < n_bits; b++)
+      for (int e = bit_offsets[b]; e < bit_offsets[b + 1]; e++)
+        bit_of[e] = b;
+    for (int i = 0; i < n_entries; i++)
+      idx[i] = i;
+    std::stable_sort (idx.begin(), idx.end(), [&] (int a, int b) { return entries[a].frame < entries[b].frame; });
+    for (int i = 0; i < n_entries; i++)
+      {
+        const awm_sync_entry& src = entries[idx[i]];
+        sorted[i].frame = src.frame;
+        sorted[i].bit = bit_of[idx[i]];
+        sorted[i].pad = 0;
+        memcpy (sorted[i].up, src.up, kUD);
+        memcpy (sorted[i].down, src.down, kUD);
+      }
+  }
+  std::vector<int> group_end;
+  for (int i = 0; i < n_entries; )
+    {
+      int j = i;
+      while (j < n_entries && j - i < 16 && sorted[j].frame - sorted[i].frame <= kApproxMaxSpan)
+        j++;
+      group_end.push_back (j);
+      i = j;
+    }
+  CK (t.sorted.reserve (sorted.size() * sizeof (ApproxEntry)));
+  CK (t.groups.reserve (group_end.size() * sizeof (int)));
+  CK (cudaMemcpyAsync (t.sorted.p, sorted.data(), sorted.size() * sizeof (ApproxEntry), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaMemcpyAsync (t.groups.p, group_end.data(), group_end.size() * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  t.n_groups = int (group_end.size());
   t.n_ent = n_entries;
   t.n_bits = n_bits;
   t.h_ent.assign (entries, entries + n_entries);
@@ -547,8 +588,8 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
   A.fpb = ctx->embed_fpb;
   A.frame_number0 = (long long) (first_frame_number % (2ull * A.fpb)) + 2LL * A.fpb - frames_pad_start;
   A.frame_mod = ctx->frame_mod.as<uint8_t>();
-  A.pow_up = float (-water_delta * 1);       // powf (mag, -Params::water_delta * data_bit_sign), src/wmadd.cc:79
-  A.pow_down = float (-water_delta * -1);
+  A.pow_up = 0.5f * float (-water_delta * 1);       // powf (mag, -Params::water_delta * data_bit_sign), src/wmadd.cc:79
+  A.pow_down = 0.5f * float (-water_delta * -1);
   A.limiter_block = limiter_block;
   A.peaks = ctx->peaks.as<unsigned>();
   A.snr = snr_power ? ctx->snr.as<double>() : nullptr;
@@ -611,7 +652,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   {
     const size_t smem = fft_smem_bytes (kStftWarps) + kBands * (kStftWarps + 1) * sizeof (float);
     if (set_smem (ctx, k_stft_db, smem)) return 1;
-    dim3 grid (unsigned ((n_out + kStftWarps - 1) / kStftWarps), 4);
+    const unsigned grid = 4u * unsigned ((n_out + kStftWarps - 1) / kStftWarps);
     PROF (ctx);
     k_stft_db<<<grid, kStftWarps * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
                                                             ctx->dbT.as<float>(), ctx->have.as<unsigned char>(),
@@ -621,23 +662,23 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   }
   const double norm_div = water_delta < 0.080 ? water_delta : 0.080;     // normalize_sync_quality, src/syncfinder.cc:90
   {
-    const size_t smem = sizeof (awm_sync_entry) * t.n_ent;
-    dim3 grid (unsigned ((n_starts + kApproxThreads - 1) / kApproxThreads), 4);
+    const size_t smem = kApproxSmem;
+    dim3 grid (unsigned ((n_starts + kApproxCands - 1) / kApproxCands), 4);
     if (mode == AWM_MODE_CLIP)
       {
         if (set_smem (ctx, k_sync_approx<true>, smem)) return 1;
         PROF (ctx);
-        k_sync_approx<true><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_starts),
-                                                                        t.ent.as<awm_sync_entry>(), t.n_ent, t.off.as<int>(), t.n_bits,
-                                                                        norm_div, ctx->q.as<double>());
+        k_sync_approx<true><<<grid, kApproxCands, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
+                                                                      t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
+                                                                      norm_div, ctx->q.as<double>());
       }
     else
       {
         if (set_smem (ctx, k_sync_approx<false>, smem)) return 1;
         PROF (ctx);
-        k_sync_approx<false><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_starts),
-                                                                         t.ent.as<awm_sync_entry>(), t.n_ent, t.off.as<int>(), t.n_bits,
-                                                                         norm_div, ctx->q.as<double>());
+        k_sync_approx<false><<<grid, kApproxCands, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
+                                                                       t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
+                                                                       norm_div, ctx->q.as<double>());
       }
     LAUNCH_CHECK ("k_sync_approx");
   }
@@ -670,69 +711,77 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   const int total = fpb * (mode == AWM_MODE_CLIP ? 2 : 1);
   const double norm_div = water_delta < 0.080 ? water_delta : 0.080;
 
-  // bound the scratch (S is n_cand * n_ent * 60 * 72 floats): process candidates in batches
-  const size_t per_cand = size_t (t.n_ent) * 60 * kOffPad * sizeof (float);
-  size_t batch = std::max<size_t> (1, (size_t (3) << 30) / per_cand);
-  batch = std::min (batch, n_scores);
-  CK (ctx->S.reserve (batch * per_cand));
-  CK (ctx->Hv.reserve (batch * t.n_ent * kOffPad));
-  CK (ctx->rq.reserve (batch * kOffPad * sizeof (double)));
-  CK (ctx->rvalid.reserve (batch * kOffPad));
-  CK (ctx->cand_start.reserve (batch * sizeof (long long)));
-  CK (ctx->cand_noff.reserve (batch * sizeof (int)));
-  const size_t smem = fft_smem_bytes (kRefineWarps) + kRefineWarps * 96 * sizeof (float);
-  if (set_smem (ctx, k_refine_fft, smem)) return 1;
-
-  std::vector<long long> h_start (batch);
-  std::vector<int> h_noff (batch);
-  std::vector<double> h_q (batch * kOffPad);
-  std::vector<unsigned char> h_valid (batch * kOffPad);
-  for (size_t c0 = 0; c0 < n_scores; c0 += batch)
+  const size_t nc = n_scores;
+  const int n_bits = t.n_bits;
+  CK (ctx->cand_start.reserve (nc * sizeof (long long)));
+  CK (ctx->cand_noff.reserve (nc * sizeof (int)));
+  CK (ctx->r_ud.reserve (nc * kOffsets * n_bits * 2 * sizeof (float)));
+  CK (ctx->r_cnt.reserve (nc * kOffsets * n_bits * sizeof (int)));
+  CK (ctx->rvalid.reserve (nc * kOffsets));
+  std::vector<long long> h_start (nc);
+  std::vector<int> h_noff (nc);
+  for (size_t c = 0; c < nc; c++)
     {
-      const size_t nc = std::min (batch, n_scores - c0);
-      for (size_t c = 0; c < nc; c++)
-        {
-          // int start = max (int (index) - sync_search_step, 0); end = index + sync_search_step; step sync_search_fine
-          const long long idx = (long long) scores[c0 + c].index;
-          const long long start = std::max<long long> (idx - 256, 0), end = idx + 256;
-          h_start[c] = start;
-          h_noff[c] = int ((end - start) / 8 + 1);
-        }
-      CK (cudaMemcpyAsync (ctx->cand_start.p, h_start.data(), nc * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
-      CK (cudaMemcpyAsync (ctx->cand_noff.p, h_noff.data(), nc * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
-      const long long jobs = (long long) nc * t.n_ent * kOffsets;
-      PROF (ctx);
-      k_refine_fft<<<unsigned ((jobs + kRefineWarps - 1) / kRefineWarps), kRefineWarps * 32, smem, ctx->stream>>> (
-        ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
-        t.ent.as<awm_sync_entry>(), t.n_ent, total, (long long) wav_first, (long long) wav_last,
-        ctx->S.as<float>(), ctx->Hv.as<unsigned char>(), ctx->tw.as<float2>(), ctx->win.as<float>());
-      LAUNCH_CHECK ("k_refine_fft");
-      PROF (ctx);
-      k_refine_sum<<<unsigned (nc), kOffPad + 24, 0, ctx->stream>>> (
-        ctx->S.as<float>(), ctx->Hv.as<unsigned char>(), ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
-        t.n_ent, t.off.as<int>(), t.n_bits, total, (long long) ctx->pcm_frames, norm_div, ctx->rq.as<double>(), ctx->rvalid.as<unsigned char>());
-      LAUNCH_CHECK ("k_refine_sum");
-      CK (cudaMemcpyAsync (h_q.data(), ctx->rq.p, nc * kOffPad * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
-      CK (cudaMemcpyAsync (h_valid.data(), ctx->rvalid.p, nc * kOffPad, cudaMemcpyDeviceToHost, ctx->stream));
-      CK (cudaStreamSynchronize (ctx->stream));
-      for (size_t c = 0; c < nc; c++)
-        {
-          awm_search_score& sc = scores[c0 + c];
-          double best_quality = sc.raw_quality;
-          uint64_t best_index = sc.index;
-          for (int o = 0; o < h_noff[c] && o < kOffsets; o++)
-            if (h_valid[c * kOffPad + o])
+      // int start = max (int (index) - sync_search_step, 0); end = index + sync_search_step; step sync_search_fine
+      const long long idx = (long long) scores[c].index;
+      const long long start = std::max<long long> (idx - 256, 0), end = idx + 256;
+      h_start[c] = start;
+      h_noff[c] = int (std::min<long long> ((end - start) / 8 + 1, kOffsets));
+    }
+  CK (cudaMemcpyAsync (ctx->cand_start.p, h_start.data(), nc * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaMemcpyAsync (ctx->cand_noff.p, h_noff.data(), nc * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+  const size_t smem = fft_smem_bytes (kRefineWarps) + kRefineWarps * 96 * sizeof (float);
+  if (set_smem (ctx, k_refine, smem)) return 1;
+  const long long jobs = (long long) nc * kOffsets * n_bits;
+  PROF (ctx);
+  k_refine<<<unsigned ((jobs + kRefineWarps - 1) / kRefineWarps), kRefineWarps * 32, smem, ctx->stream>>> (
+    ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
+    t.ent.as<awm_sync_entry>(), t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last,
+    ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>(), ctx->tw.as<float2>(), ctx->win.as<float>());
+  LAUNCH_CHECK ("k_refine");
+  std::vector<float> h_ud (nc * kOffsets * n_bits * 2);
+  std::vector<int> h_cnt (nc * kOffsets * n_bits);
+  std::vector<unsigned char> h_valid (nc * kOffsets);
+  CK (cudaMemcpyAsync (h_ud.data(), ctx->r_ud.p, h_ud.size() * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaMemcpyAsync (h_cnt.data(), ctx->r_cnt.p, h_cnt.size() * sizeof (int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaMemcpyAsync (h_valid.data(), ctx->rvalid.p, h_valid.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  for (size_t c = 0; c < nc; c++)
+    {
+      awm_search_score& sc = scores[c];
+      double best_quality = sc.raw_quality;
+      uint64_t best_index = sc.index;
+      for (int o = 0; o < h_noff[c]; o++)
+        if (h_valid[c * kOffsets + o])
+          {
+            // sync_decode epilogue (src/syncfinder.cc:94-114,144-152) from the per-bit float sums
+            double sync_quality = 0;
+            int bit_count = 0;
+            for (int bit = 0; bit < n_bits; bit++)
               {
-                const double q = h_q[c * kOffPad + o];
-                if (fabs (q - sc.local_mean) > fabs (best_quality - sc.local_mean))   // src/syncfinder.cc:436-440
-                  {
-                    best_quality = q;
-                    best_index = uint64_t (h_start[c] + 8LL * o);
-                  }
+                const size_t ob = (c * kOffsets + o) * n_bits + bit;
+                const float umag = h_ud[ob * 2], dmag = h_ud[ob * 2 + 1];
+                double raw_bit;
+                if (umag == 0 || dmag == 0)
+                  raw_bit = 0;
+                else if (umag < dmag)
+                  raw_bit = 1 - umag / dmag;
+                else
+                  raw_bit = dmag / umag - 1;
+                sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * h_cnt[ob];
+                bit_count += h_cnt[ob];
               }
-          sc.index = best_index;
-          sc.raw_quality = best_quality;
-        }
+            if (bit_count)
+              sync_quality /= bit_count;
+            const double q = sync_quality / norm_div / 2.9;
+            if (fabs (q - sc.local_mean) > fabs (best_quality - sc.local_mean))   // src/syncfinder.cc:436-440
+              {
+                best_quality = q;
+                best_index = uint64_t (h_start[c] + 8LL * o);
+              }
+          }
+      sc.index = best_index;
+      sc.raw_quality = best_quality;
     }
   return 0;
 }
@@ -802,46 +851,49 @@ awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size_t n
 /* ---------------------------------------------------------------- Viterbi */
 
 int
-awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_coded, const int *block_types,
+awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits, const int *block_types,
              int hard, uint8_t *bits_out, float *error_out)
 {
   if (n_jobs == 0)
     return 0;
-  if (!raw_bits || !block_types || !bits_out || !error_out || n_coded <= 0)
+  if (!raw_bits || !block_types || !bits_out || !error_out || n_msg_bits <= 0 || n_msg_bits > 4096)
     return fail (ctx, "awm_viterbi: bad arguments");
-  int n_msg = -1;
+  const int steps = n_msg_bits + AWM_VITERBI_ORDER;
+  std::vector<long long> off (n_jobs + 1, 0);
   for (size_t j = 0; j < n_jobs; j++)
     {
-      const int rate = block_types[j] == AWM_BLOCK_AB ? 12 : 6;
-      if (block_types[j] < 0 || block_types[j] > 2 || n_coded % rate || n_coded / rate <= AWM_VITERBI_ORDER)
-        return fail (ctx, "awm_viterbi: n_coded %d does not fit block type %d", n_coded, block_types[j]);
-      const int m = n_coded / rate - AWM_VITERBI_ORDER;
-      if (n_msg >= 0 && m != n_msg)
-        return fail (ctx, "awm_viterbi: all jobs of one call must have the same rate");
-      n_msg = m;
+      if (block_types[j] < 0 || block_types[j] > 2)
+        return fail (ctx, "awm_viterbi: bad block type %d", block_types[j]);
+      off[j + 1] = off[j] + (long long) steps * (block_types[j] == AWM_BLOCK_AB ? 12 : 6);
     }
   CK (cudaSetDevice (ctx->device));
-  const int steps = n_msg + AWM_VITERBI_ORDER;
-  const size_t max_jobs = 256;
-  const size_t smem = size_t (n_coded) * sizeof (float);
+  const size_t max_jobs = 512;
+  const size_t smem = size_t (steps) * 12 * sizeof (float);
   if (set_smem (ctx, k_viterbi, smem)) return 1;
   for (size_t j0 = 0; j0 < n_jobs; j0 += max_jobs)
     {
       const size_t nj = std::min (max_jobs, n_jobs - j0);
-      CK (ctx->vit_raw.reserve (nj * n_coded * sizeof (float)));
+      const long long base = off[j0], n_raw = off[j0 + nj] - base;
+      std::vector<long long> rel (nj);
+      for (size_t j = 0; j < nj; j++)
+        rel[j] = off[j0 + j] - base;
+      CK (ctx->vit_raw.reserve (n_raw * sizeof (float)));
+      CK (ctx->vit_off.reserve (nj * sizeof (long long)));
       CK (ctx->vit_types.reserve (nj * sizeof (int)));
       CK (ctx->vit_delta.reserve (nj * 2 * kVitStates * sizeof (float)));
       CK (ctx->vit_dec.reserve (nj * steps * kVitWords * sizeof (uint32_t)));
-      CK (ctx->vit_bits.reserve (nj * n_msg));
+      CK (ctx->vit_bits.reserve (nj * n_msg_bits));
       CK (ctx->vit_err.reserve (nj * sizeof (float)));
-      CK (cudaMemcpyAsync (ctx->vit_raw.p, raw_bits + j0 * n_coded, nj * n_coded * sizeof (float), cudaMemcpyDefault, ctx->stream));
+      CK (cudaMemcpyAsync (ctx->vit_raw.p, raw_bits + base, n_raw * sizeof (float), cudaMemcpyDefault, ctx->stream));
+      CK (cudaMemcpyAsync (ctx->vit_off.p, rel.data(), nj * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
       CK (cudaMemcpyAsync (ctx->vit_types.p, block_types + j0, nj * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
       PROF (ctx);
-      k_viterbi<<<unsigned (nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), n_coded, ctx->vit_types.as<int>(), hard,
+      k_viterbi<<<unsigned (nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), ctx->vit_off.as<long long>(), n_msg_bits, ctx->vit_types.as<int>(), hard,
+                                                                  steps,
                                                                   ctx->vit_delta.as<float>(), ctx->vit_dec.as<uint32_t>(),
                                                                   ctx->vit_bits.as<unsigned char>(), ctx->vit_err.as<float>());
       LAUNCH_CHECK ("k_viterbi");
-      CK (cudaMemcpyAsync (bits_out + j0 * n_msg, ctx->vit_bits.p, nj * n_msg, cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaMemcpyAsync (bits_out + j0 * n_msg_bits, ctx->vit_bits.p, nj * n_msg_bits, cudaMemcpyDeviceToHost, ctx->stream));
       CK (cudaMemcpyAsync (error_out + j0, ctx->vit_err.p, nj * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
       CK (cudaStreamSynchronize (ctx->stream));
     }

@@ -215,7 +215,7 @@ k_fft_c2r (const float *__restrict__ in, float *__restrict__ out, long long coun
 // SyncFinder::sync_fft / sync_fft_parallel for all four 256-sample shifts
 // (src/syncfinder.cc:560-657): db[shift][band][frame] (band-major so the per-candidate gathers of
 // k_sync_approx are coalesced over consecutive start frames) and have[shift][frame].
-// grid = (ceil(n_out/8), 4 shifts), 8 warps, warp = one frame.
+// grid = 4 * ceil(n_out/8) CTAs (shift = blockIdx.x & 3), 8 warps, warp = one frame.
 // =============================================================================================
 constexpr int kStftWarps = 8;
 
@@ -228,8 +228,9 @@ k_stft_db (const float *__restrict__ pcm, long long n_frames, int C, int n_out, 
   FftSmem s = fft_smem_setup (smem, g_tw, g_win, kStftWarps);
   float *tile = s.extra;                               // [81][kStftWarps + 1]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int shift_idx = blockIdx.y;
-  const int f = blockIdx.x * kStftWarps + w;
+  // the four shifts of a frame tile are neighbouring CTAs, so the tile's samples are fetched from HBM once (L2 serves the rest)
+  const int shift_idx = blockIdx.x & 3, tile_idx = blockIdx.x >> 2;
+  const int f = tile_idx * kStftWarps + w;
   const long long start = (long long) shift_idx * 256 + (long long) f * kFrame;
 
   bool ok = f < n_out;
@@ -249,7 +250,7 @@ k_stft_db (const float *__restrict__ pcm, long long n_frames, int C, int n_out, 
   for (int i = threadIdx.x; i < kBands * kStftWarps; i += blockDim.x)
     {
       const int band = i / kStftWarps, ww = i % kStftWarps;
-      const int ff = blockIdx.x * kStftWarps + ww;
+      const int ff = tile_idx * kStftWarps + ww;
       if (ff < n_out)
         dbT[((size_t) shift_idx * kBands + band) * ld + ff] = tile[band * (kStftWarps + 1) + ww];
     }
@@ -257,64 +258,110 @@ k_stft_db (const float *__restrict__ pcm, long long n_frames, int C, int n_out, 
 
 // =============================================================================================
 // SyncFinder::sync_decode for every start frame (src/syncfinder.cc:116-153, bit_quality :94-114,
-// normalize_sync_quality :80-91).  One thread = one candidate; float sums in reference order.
+// normalize_sync_quality :80-91).  One thread = one candidate start frame, float sums in the reference's
+// order (per sync bit: frames ascending, 30 up / 30 down bands each).
+//
+// A CTA owns kApproxCands consecutive start frames of one shift.  Candidate s reads db[band][s + frame(e)] for
+// each sync entry e, so while the entries are walked in ascending frame order the CTA's working set is a
+// sliding window of the band-major dB matrix: it is staged in a shared-memory ring (81 bands x kApproxRing
+// frames) that is topped up group by group, and every dB value is fetched from L2 once per CTA instead of
+// once per (candidate, entry) -- 30600 float adds per candidate then run at shared-memory speed.
+//   ent_sorted: all entries of all bits merged by ascending frame (per-bit order is preserved),
+//               64 bytes each: u16 frame, u8 bit, u8 pad, u8 up[30], u8 down[30]
+//   group_end : entries [group_end[g-1], group_end[g]) span at most kApproxRing - kApproxCands - 1 frames
 // out[s*4 + shift] so that the array is already sorted by index = s*1024 + shift*256.
 // =============================================================================================
-constexpr int kApproxThreads = 128;
+constexpr int kApproxCands = 256;          // candidates (= threads) per CTA
+constexpr int kApproxRing = 512;           // ring length in frames (power of two)
+constexpr int kApproxMaxSpan = kApproxRing - kApproxCands - 1;
+struct ApproxEntry { uint16_t frame; uint8_t bit, pad; uint8_t up[30], down[30]; };
+static_assert (sizeof (ApproxEntry) == 64, "ApproxEntry must be 64 bytes");
+constexpr size_t kApproxSmem = size_t (kBands) * kApproxRing * sizeof (float) + kApproxRing;
 
-template<bool CHECK_HAVE> __global__ void __launch_bounds__ (kApproxThreads)
-k_sync_approx (const float *__restrict__ dbT, const unsigned char *__restrict__ have, int ld, int n_starts,
-               const awm_sync_entry *__restrict__ g_ent, int n_ent, const int *__restrict__ g_bit_off, int n_bits,
+template<bool CHECK_HAVE> __global__ void __launch_bounds__ (kApproxCands, 1)
+k_sync_approx (const float *__restrict__ dbT, const unsigned char *__restrict__ have, int ld, int n_out, int n_starts,
+               const ApproxEntry *__restrict__ ent_sorted, const int *__restrict__ group_end, int n_groups, int n_bits,
                double norm_div, double *__restrict__ out)
 {
   extern __shared__ __align__ (16) unsigned char smem[];
-  awm_sync_entry *ent = reinterpret_cast<awm_sync_entry *> (smem);
-  {
-    const uint16_t *src = reinterpret_cast<const uint16_t *> (g_ent);
-    uint16_t *dst = reinterpret_cast<uint16_t *> (smem);
-    const int n16 = n_ent * int (sizeof (awm_sync_entry) / 2);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x)
-      dst[i] = src[i];
-  }
-  __syncthreads();
+  float *ring = reinterpret_cast<float *> (smem);                         // [band][kApproxRing]
+  unsigned char *hring = smem + size_t (kBands) * kApproxRing * sizeof (float);   // have flags, same slots
   const int shift_idx = blockIdx.y;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_starts)
-    return;
+  const int s0 = blockIdx.x * kApproxCands;
+  const int s = s0 + threadIdx.x;
   const float *db = dbT + (size_t) shift_idx * kBands * ld;
   const unsigned char *hv = have + (size_t) shift_idx * ld;
+
+  float u0 = 0, u1 = 0, u2 = 0, u3 = 0, u4 = 0, u5 = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0;
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+  int loaded = s0;                                                          // frames < loaded are (or were) in the ring
+  int e = 0;
+  for (int g = 0; g < n_groups; g++)
+    {
+      const int e_end = group_end[g];
+      const int fr_first = ent_sorted[e].frame, fr_last = ent_sorted[e_end - 1].frame;
+      const int need_lo = max (loaded, s0 + fr_first), need_hi = s0 + fr_last + kApproxCands;
+      __syncthreads();                                                      // previous group no longer reads the slots we overwrite
+      const int n_new = need_hi - need_lo;
+      for (int i = threadIdx.x; i < n_new * kBands; i += kApproxCands)
+        {
+          const int band = i / n_new, f = need_lo + i % n_new;
+          ring[band * kApproxRing + (f & (kApproxRing - 1))] = f < n_out ? __ldg (db + (size_t) band * ld + f) : 0.f;
+        }
+      if (CHECK_HAVE)
+        for (int i = threadIdx.x; i < n_new; i += kApproxCands)
+          {
+            const int f = need_lo + i;
+            hring[f & (kApproxRing - 1)] = f < n_out ? hv[f] : 0;
+          }
+      loaded = need_hi;
+      __syncthreads();
+      for (; e < e_end; e++)
+        {
+          const uint4 *e4 = reinterpret_cast<const uint4 *> (ent_sorted + e);
+          const uint4 w0 = __ldg (e4), w1 = __ldg (e4 + 1), w2 = __ldg (e4 + 2), w3 = __ldg (e4 + 3);
+          const unsigned words[16] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w };
+          const int frame = words[0] & 0xffff, bit = (words[0] >> 16) & 0xff;
+          const int slot = (s + frame) & (kApproxRing - 1);
+          if (CHECK_HAVE && !hring[slot])
+            continue;
+          const float *base = ring + slot;
+          float um = bit == 0 ? u0 : bit == 1 ? u1 : bit == 2 ? u2 : bit == 3 ? u3 : bit == 4 ? u4 : u5;
+          float dm = bit == 0 ? d0 : bit == 1 ? d1 : bit == 2 ? d2 : bit == 3 ? d3 : bit == 4 ? d4 : d5;
+#pragma unroll
+          for (int i = 0; i < kUD; i++)
+            {
+              const unsigned ub = (words[(4 + i) >> 2] >> (8 * ((4 + i) & 3))) & 0xffu;
+              const unsigned dbn = (words[(34 + i) >> 2] >> (8 * ((34 + i) & 3))) & 0xffu;
+              um += base[ub * kApproxRing];
+              dm += base[dbn * kApproxRing];
+            }
+          if (bit == 0) { u0 = um; d0 = dm; c0++; } else if (bit == 1) { u1 = um; d1 = dm; c1++; }
+          else if (bit == 2) { u2 = um; d2 = dm; c2++; } else if (bit == 3) { u3 = um; d3 = dm; c3++; }
+          else if (bit == 4) { u4 = um; d4 = dm; c4++; } else { u5 = um; d5 = dm; c5++; }
+        }
+    }
+  if (s >= n_starts)
+    return;
+  const float um[6] = { u0, u1, u2, u3, u4, u5 }, dm[6] = { d0, d1, d2, d3, d4, d5 };
+  const int cn[6] = { c0, c1, c2, c3, c4, c5 };
   double sync_quality = 0;
   int bit_count = 0;
-  for (int bit = 0; bit < n_bits; bit++)
-    {
-      float umag = 0, dmag = 0;
-      int frame_bit_count = 0;
-      const int e1 = g_bit_off[bit + 1];
-      for (int e = g_bit_off[bit]; e < e1; e++)
-        {
-          const int f = s + ent[e].frame;
-          if (!CHECK_HAVE || hv[f])
-            {
-              const float *col = db + f;
 #pragma unroll
-              for (int i = 0; i < kUD; i++)
-                {
-                  umag += col[(size_t) ent[e].up[i] * ld];
-                  dmag += col[(size_t) ent[e].down[i] * ld];
-                }
-              frame_bit_count++;
-            }
-        }
-      double raw_bit;
-      if (umag == 0 || dmag == 0)
-        raw_bit = 0;
-      else if (umag < dmag)
-        raw_bit = 1 - double (umag) / double (dmag);
-      else
-        raw_bit = double (dmag) / double (umag) - 1;
-      sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * frame_bit_count;
-      bit_count += frame_bit_count;
-    }
+  for (int bit = 0; bit < 6; bit++)
+    if (bit < n_bits)
+      {
+        const float umag = um[bit], dmag = dm[bit];
+        double raw_bit;
+        if (umag == 0 || dmag == 0)
+          raw_bit = 0;
+        else if (umag < dmag)
+          raw_bit = 1 - double (umag) / double (dmag);
+        else
+          raw_bit = double (dmag) / double (umag) - 1;
+        sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * cn[bit];
+        bit_count += cn[bit];
+      }
   if (bit_count)
     sync_quality /= bit_count;
   out[(size_t) s * 4 + shift_idx] = sync_quality / norm_div / 2.9;
@@ -347,113 +394,70 @@ k_local_mean (const double *__restrict__ q, long long n, awm_search_score *__res
 }
 
 // =============================================================================================
-// SyncFinder::search_refine (src/syncfinder.cc:393-458), stage 1: for candidate c, fine offset o
-// and wanted sync frame e one warp computes the channel-summed dB of the frame at sample
-// cand_start[c] + 8*o + frame(e)*1024 and stores the 30 up + 30 down values the sync pattern
-// reads, laid out [c][e][60][kOffPad] so that stage 2 (one thread per offset) is coalesced.
+// SyncFinder::search_refine (src/syncfinder.cc:393-458): for candidate c and fine offset o
+// (sample cand_start[c] + 8*o) sync_fft of the wanted sync frames + sync_decode (start frame 0).
+// One warp = one (candidate, offset, sync bit): it walks the bit's sync frames in ascending frame order,
+// one FFT each, and accumulates umag / dmag in the reference's order (lane 0: up bands, lane 1: down
+// bands, sequential float adds), so no spectra are ever written to memory.
+// out_ud[((c*65 + o)*n_bits + bit)*2 + {0,1}] = umag, dmag; out_cnt = frames used; out_valid[c*65 + o].
 // =============================================================================================
 constexpr int kOffsets = 65;
-constexpr int kOffPad = 72;
 constexpr int kRefineWarps = 8;
 
 __global__ void __launch_bounds__ (kRefineWarps * 32, 2)
-k_refine_fft (const float *__restrict__ pcm, long long n_frames, int C,
-              const long long *__restrict__ cand_start, const int *__restrict__ cand_noff, int n_cand,
-              const awm_sync_entry *__restrict__ g_ent, int n_ent, int total_frame_count,
-              long long wav_first, long long wav_last,
-              float *__restrict__ S, unsigned char *__restrict__ Hv, const float2 *g_tw, const float *g_win)
+k_refine (const float *__restrict__ pcm, long long n_frames, int C,
+          const long long *__restrict__ cand_start, const int *__restrict__ cand_noff, int n_cand,
+          const awm_sync_entry *__restrict__ g_ent, const int *__restrict__ g_bit_off, int n_bits, int total_frame_count,
+          long long wav_first, long long wav_last,
+          float *__restrict__ out_ud, int *__restrict__ out_cnt, unsigned char *__restrict__ out_valid,
+          const float2 *g_tw, const float *g_win)
 {
   extern __shared__ __align__ (16) unsigned char smem[];
   FftSmem s = fft_smem_setup (smem, g_tw, g_win, kRefineWarps);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float *sband = s.extra + w * 96;                      // [81] per warp
   const long long job = (long long) blockIdx.x * kRefineWarps + w;
-  const long long per_cand = (long long) n_ent * kOffsets;
-  if (job >= per_cand * n_cand)
+  if (job >= (long long) n_cand * kOffsets * n_bits)
     return;
-  const int c = int (job / per_cand);
-  const int e = int ((job % per_cand) / kOffsets);
-  const int o = int (job % kOffsets);
-  if (o >= cand_noff[c])
-    return;
+  const int c = int (job / (kOffsets * n_bits));
+  const int o = int ((job / n_bits) % kOffsets);
+  const int bit = int (job % n_bits);
   const long long fine = cand_start[c] + 8LL * o;
-  if (fine + (long long) total_frame_count * kFrame > n_frames)   // sync_fft: read past end -> no result for this offset
-    return;
-  const awm_sync_entry *en = g_ent + e;
-  const long long start = fine + (long long) en->frame * kFrame;
-  const long long f_first = start * C, f_last = (start + kFrame) * C;
-  const bool ok = !(f_last < wav_first || f_first > wav_last);
-  const size_t ce = (size_t) c * n_ent + e;
-  if (lane == 0)
-    Hv[ce * kOffPad + o] = ok ? 1 : 0;
-  if (!ok)
-    return;
-  float acc[4];
-  frame_db_sum (pcm, n_frames, C, start, s, lane, acc);
-  bands_to_array (acc, lane, sband, 1);
-  __syncwarp();
-  float *dst = S + ce * 60 * kOffPad + o;
-  if (lane < kUD)
-    {
-      dst[(size_t) lane * kOffPad] = sband[en->up[lane]];
-      dst[(size_t) (kUD + lane) * kOffPad] = sband[en->down[lane]];
-    }
-}
-
-// stage 2: one thread per (candidate, offset): sync_decode (start_frame 0) in reference order
-__global__ void
-k_refine_sum (const float *__restrict__ S, const unsigned char *__restrict__ Hv,
-              const long long *__restrict__ cand_start, const int *__restrict__ cand_noff, int n_cand,
-              int n_ent, const int *__restrict__ g_bit_off, int n_bits, int total_frame_count, long long n_frames,
-              double norm_div, double *__restrict__ q_out, unsigned char *__restrict__ q_valid)
-{
-  const int c = blockIdx.x, o = threadIdx.x;
-  if (o >= kOffPad)
-    return;
-  bool valid = o < cand_noff[c];
-  if (valid)
-    {
-      const long long fine = cand_start[c] + 8LL * o;
-      if (fine + (long long) total_frame_count * kFrame > n_frames)
-        valid = false;
-    }
-  q_valid[c * kOffPad + o] = valid ? 1 : 0;
+  // sync_fft: an offset whose window would read past the end yields no result at all
+  const bool valid = o < cand_noff[c] && fine + (long long) total_frame_count * kFrame <= n_frames;
+  if (bit == 0 && lane == 0)
+    out_valid[c * kOffsets + o] = valid ? 1 : 0;
   if (!valid)
     return;
-  double sync_quality = 0;
-  int bit_count = 0;
-  for (int bit = 0; bit < n_bits; bit++)
+  float mag = 0.f;                                      // lane 0: umag, lane 1: dmag
+  int cnt = 0;
+  const int e1 = g_bit_off[bit + 1];
+  for (int e = g_bit_off[bit]; e < e1; e++)
     {
-      float umag = 0, dmag = 0;
-      int frame_bit_count = 0;
-      for (int e = g_bit_off[bit]; e < g_bit_off[bit + 1]; e++)
+      const awm_sync_entry *en = g_ent + e;
+      const long long start = fine + (long long) en->frame * kFrame;
+      const long long f_first = start * C, f_last = (start + kFrame) * C;
+      if (f_last < wav_first || f_first > wav_last)     // frame in digital silence: not counted
+        continue;
+      float acc[4];
+      frame_db_sum (pcm, n_frames, C, start, s, lane, acc);
+      bands_to_array (acc, lane, sband, 1);
+      __syncwarp();
+      if (lane < 2)
         {
-          const size_t ce = (size_t) c * n_ent + e;
-          if (Hv[ce * kOffPad + o])
-            {
-              const float *src = S + ce * 60 * kOffPad + o;
+          const uint8_t *idx = lane == 0 ? en->up : en->down;
 #pragma unroll 6
-              for (int i = 0; i < kUD; i++)
-                {
-                  umag += src[(size_t) i * kOffPad];
-                  dmag += src[(size_t) (kUD + i) * kOffPad];
-                }
-              frame_bit_count++;
-            }
+          for (int i = 0; i < kUD; i++)
+            mag += sband[idx[i]];
         }
-      double raw_bit;
-      if (umag == 0 || dmag == 0)
-        raw_bit = 0;
-      else if (umag < dmag)
-        raw_bit = 1 - double (umag) / double (dmag);
-      else
-        raw_bit = double (dmag) / double (umag) - 1;
-      sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * frame_bit_count;
-      bit_count += frame_bit_count;
+      cnt++;
+      __syncwarp();
     }
-  if (bit_count)
-    sync_quality /= bit_count;
-  q_out[c * kOffPad + o] = sync_quality / norm_div / 2.9;
+  const size_t ob = ((size_t) c * kOffsets + o) * n_bits + bit;
+  if (lane < 2)
+    out_ud[ob * 2 + lane] = mag;
+  if (lane == 0)
+    out_cnt[ob] = cnt;
 }
 
 // =============================================================================================
@@ -533,31 +537,48 @@ k_mix_decode (const float *__restrict__ D, int n_blk, int C, int frames_per_bloc
 constexpr int kVitStates = 1 << AWM_VITERBI_ORDER;
 constexpr int kVitThreads = 512;      // CTA size; each thread owns two groups of 32 new states
 constexpr int kVitWords = kVitStates / 32;   // decision words per trellis step
-__constant__ unsigned c_ab_generators[12] = { 066561, 075211, 071545, 054435, 063635, 052475,
-                                              063543, 075307, 052547, 045627, 067657, 051757 };  // src/convcode.cc:42-46
 
-// one trellis step for the 32 new states owned by thread tid; returns the 32 decision bits
-template<int RATE> __device__ __forceinline__ uint32_t
-viterbi_step (const float *__restrict__ d_old, float *__restrict__ d_new, int gen_off,
-              const float *m0, const float *m1, int tid)
+// generator polynomials (src/convcode.cc:42-46) as compile-time constants: A = even, B = odd, AB = all
+__host__ __device__ constexpr unsigned ab_generator (int i)
 {
+  return i == 0 ? 066561u : i == 1 ? 075211u : i == 2 ? 071545u : i == 3 ? 054435u : i == 4 ? 063635u : i == 5 ? 052475u
+       : i == 6 ? 063543u : i == 7 ? 075307u : i == 8 ? 052547u : i == 9 ? 045627u : i == 10 ? 067657u : 051757u;
+}
+template<int TYPE> __host__ __device__ constexpr unsigned type_generator (int p) { return TYPE == AWM_BLOCK_AB ? ab_generator (p) : ab_generator (2 * p + TYPE); }
+__host__ __device__ constexpr bool cparity (unsigned v) { v ^= v >> 16; v ^= v >> 8; v ^= v >> 4; v ^= v >> 2; v ^= v >> 1; return v & 1u; }
+
+// One trellis step for the 32 new states ns = 32u + q of group u; returns the 32 decision bits.
+// The output bit p of state ns is parity (ns & g_p) = parity (32u & g_p) ^ parity (q & g_p): the first factor
+// is a per-group constant (hi, bit p), the second a compile-time constant, so which of (c-0)^2 / (c-1)^2 is
+// added needs no instruction at all inside the unrolled loops.
+template<int TYPE> __device__ __forceinline__ uint32_t
+viterbi_step (const float *__restrict__ d_old, float *__restrict__ d_new, unsigned hi, const float *m0, const float *m1, int u)
+{
+  constexpr int RATE = TYPE == AWM_BLOCK_AB ? 12 : 6;
+  float mA[RATE], mB[RATE];               // metric for output bit == hi-bit / != hi-bit
+#pragma unroll
+  for (int p = 0; p < RATE; p++)
+    {
+      const bool h = (hi >> p) & 1u;
+      mA[p] = h ? m1[p] : m0[p];
+      mB[p] = h ? m0[p] : m1[p];
+    }
   uint32_t word = 0;
 #pragma unroll
   for (int v = 0; v < 4; v++)                                // 8 new states <- 4 + 4 predecessors
     {
-      const float4 x = *reinterpret_cast<const float4 *> (d_old + 16 * tid + 4 * v);
-      const float4 y = *reinterpret_cast<const float4 *> (d_old + 16 * tid + 4 * v + (kVitStates >> 1));
+      const float4 x = *reinterpret_cast<const float4 *> (d_old + 16 * u + 4 * v);
+      const float4 y = *reinterpret_cast<const float4 *> (d_old + 16 * u + 4 * v + (kVitStates >> 1));
       const float a0[4] = { x.x, x.y, x.z, x.w }, a1[4] = { y.x, y.y, y.z, y.w };
       float outv[8];
 #pragma unroll
       for (int q = 0; q < 8; q++)
         {
-          const unsigned ns = 32u * tid + 8u * v + q;
           float d0 = a0[q >> 1], d1 = a1[q >> 1];
 #pragma unroll
           for (int p = 0; p < RATE; p++)
             {
-              const float m = (__popc (ns & c_ab_generators[(RATE == 12 ? p : 2 * p) + gen_off]) & 1) ? m1[p] : m0[p];
+              const float m = cparity (unsigned (8 * v + q) & type_generator<TYPE> (p)) ? mB[p] : mA[p];
               d0 = __fadd_rn (d0, m);
               d1 = __fadd_rn (d1, m);
             }
@@ -565,16 +586,50 @@ viterbi_step (const float *__restrict__ d_old, float *__restrict__ d_new, int ge
           outv[q] = take1 ? d1 : d0;
           word |= (take1 ? 1u : 0u) << (8 * v + q);
         }
-      float4 *on = reinterpret_cast<float4 *> (d_new + 32 * tid + 8 * v);
+      float4 *on = reinterpret_cast<float4 *> (d_new + 32 * u + 8 * v);
       on[0] = make_float4 (outv[0], outv[1], outv[2], outv[3]);
       on[1] = make_float4 (outv[4], outv[5], outv[6], outv[7]);
     }
   return word;
 }
 
+template<int TYPE> __device__ __forceinline__ void
+viterbi_run (float *d_old, float *d_new, uint32_t *dec, const float *coded, float *m0, float *m1, int steps, int tid)
+{
+  constexpr int RATE = TYPE == AWM_BLOCK_AB ? 12 : 6;
+  unsigned hi[kVitWords / kVitThreads];
+#pragma unroll
+  for (int g = 0; g < kVitWords / kVitThreads; g++)
+    {
+      const unsigned base = 32u * unsigned (tid + g * kVitThreads);
+      hi[g] = 0;
+#pragma unroll
+      for (int p = 0; p < RATE; p++)
+        hi[g] |= unsigned (__popc (base & type_generator<TYPE> (p)) & 1) << p;
+    }
+  for (int t = 0; t < steps; t++)
+    {
+      if (tid < RATE)
+        {
+          const float c = coded[t * RATE + tid];
+          m0[tid] = __fmul_rn (c, c);                       // (c - 0)^2
+          m1[tid] = __fmul_rn (c - 1.0f, c - 1.0f);         // (c - 1)^2
+        }
+      __syncthreads();
+#pragma unroll
+      for (int g = 0; g < kVitWords / kVitThreads; g++)
+        {
+          const int u = tid + g * kVitThreads;
+          dec[(size_t) t * kVitWords + u] = viterbi_step<TYPE> (d_old, d_new, hi[g], m0, m1, u);
+        }
+      __syncthreads();
+      float *tmp = d_old; d_old = d_new; d_new = tmp;
+    }
+}
+
 __global__ void __launch_bounds__ (kVitThreads)
-k_viterbi (const float *__restrict__ raw, int n_coded, const int *__restrict__ block_types, int hard,
-           float *__restrict__ delta_buf /* [job][2][32768] */, uint32_t *__restrict__ dec_buf /* [job][steps][kVitWords] */,
+k_viterbi (const float *__restrict__ raw, const long long *__restrict__ raw_off, int n_msg, const int *__restrict__ block_types, int hard,
+           int max_steps, float *__restrict__ delta_buf /* [job][2][32768] */, uint32_t *__restrict__ dec_buf /* [job][steps][kVitWords] */,
            unsigned char *__restrict__ bits_out, float *__restrict__ err_out)
 {
   extern __shared__ __align__ (16) unsigned char smem[];
@@ -584,10 +639,10 @@ k_viterbi (const float *__restrict__ raw, int n_coded, const int *__restrict__ b
   const int job = blockIdx.x, tid = threadIdx.x;
   const int btype = block_types[job];
   const int rate = (btype == AWM_BLOCK_AB) ? 12 : 6;
-  const int steps = n_coded / rate;
-  const int gen_off = (btype == AWM_BLOCK_B) ? 1 : 0;      // A: even generators, B: odd, AB: all (src/convcode.cc:77-98)
+  const int steps = n_msg + AWM_VITERBI_ORDER;
+  const int n_coded = steps * rate;
 
-  const float *rj = raw + (size_t) job * n_coded;
+  const float *rj = raw + raw_off[job];
   if (tid == 0)
     {
       double mean = 0;
@@ -600,37 +655,25 @@ k_viterbi (const float *__restrict__ raw, int n_coded, const int *__restrict__ b
     coded[i] = hard ? (rj[i] > 0 ? 1.0f : 0.0f) : float (0.5 * (double (rj[i]) / s_mean + 1));
 
   float *d_old = delta_buf + (size_t) job * 2 * kVitStates, *d_new = d_old + kVitStates;
-  uint32_t *dec = dec_buf + (size_t) job * steps * kVitWords;
+  uint32_t *dec = dec_buf + (size_t) job * max_steps * kVitWords;
   for (int i = tid; i < kVitStates; i += blockDim.x)
     d_old[i] = (i == 0) ? 0.f : INFINITY;
   __syncthreads();
 
-  for (int t = 0; t < steps; t++)
+  if (btype == AWM_BLOCK_A)
+    viterbi_run<AWM_BLOCK_A> (d_old, d_new, dec, coded, m0, m1, steps, tid);
+  else if (btype == AWM_BLOCK_B)
+    viterbi_run<AWM_BLOCK_B> (d_old, d_new, dec, coded, m0, m1, steps, tid);
+  else
+    viterbi_run<AWM_BLOCK_AB> (d_old, d_new, dec, coded, m0, m1, steps, tid);
+  if (steps & 1)
     {
-      if (tid < rate)
-        {
-          const float c = coded[t * rate + tid];
-          m0[tid] = __fmul_rn (c, c);                       // (c - 0)^2
-          m1[tid] = __fmul_rn (c - 1.0f, c - 1.0f);         // (c - 1)^2
-        }
-      __syncthreads();
-      for (int u = tid; u < kVitWords; u += kVitThreads)
-        {
-          uint32_t word;
-          if (rate == 6)
-            word = viterbi_step<6> (d_old, d_new, gen_off, m0, m1, u);
-          else
-            word = viterbi_step<12> (d_old, d_new, 0, m0, m1, u);
-          dec[(size_t) t * kVitWords + u] = word;
-        }
-      __syncthreads();
       float *tmp = d_old; d_old = d_new; d_new = tmp;
     }
   if (tid == 0)
     {
       err_out[job] = d_old[0] / float (n_coded);
       unsigned state = 0;
-      const int n_msg = steps - AWM_VITERBI_ORDER;
       for (int t = steps; t > 0; t--)
         {
           const uint32_t word = dec[(size_t) (t - 1) * kVitWords + (state >> 5)];
@@ -664,7 +707,7 @@ struct EmbedArgs
   long long frame_number0;     // table row counter of frame 0: first_frame_number + 2*fpb - pad_start
   int fpb;
   const uint8_t *frame_mod;    // [2][fpb][101]
-  float pow_up, pow_down;      // exponents -delta*(+1), -delta*(-1) as float
+  float pow_up, pow_down;      // HALF the exponents -delta*(+1), -delta*(-1): applied to log2 of the squared magnitude
   int limiter_block;           // 0 = no peak tracking
   unsigned *peaks;             // [n_blocks] float bits, atomicMax
   double *snr;                 // [2] or null
@@ -726,13 +769,14 @@ k_embed (EmbedArgs A)
                 const int mod = fm[k]; \
                 if (mod != 0) \
                   { \
-                    const float ex = (mod == 1) ? A.pow_up : A.pow_down; \
-                    const float ma = hypotf (ar, ai); \
-                    if (ma > 1e-7f) { const float f = powf (ma, ex) - 1.0f; dar = ar * f; dai = ai * f; } \
+                    /* mag^e - 1 = exp2 (e/2 * log2 (re^2 + im^2)) - 1; mag > 1e-7 <=> mag^2 > 1e-14 */ \
+                    const float ex2 = (mod == 1) ? A.pow_up : A.pow_down; \
+                    const float pa = ar * ar + ai * ai; \
+                    if (pa > 1e-14f) { const float f = exp2f (ex2 * log2f (pa)) - 1.0f; dar = ar * f; dai = ai * f; } \
                     if (chB >= 0) \
                       { \
-                        const float mb = hypotf (br, bi); \
-                        if (mb > 1e-7f) { const float f = powf (mb, ex) - 1.0f; dbr = br * f; dbi = bi * f; } \
+                        const float pb = br * br + bi * bi; \
+                        if (pb > 1e-14f) { const float f = exp2f (ex2 * log2f (pb)) - 1.0f; dbr = br * f; dbi = bi * f; } \
                       } \
                   } \
               } \

@@ -9,6 +9,10 @@ awm_ctx *g_ctx = nullptr;
 bool     g_failed = false;
 struct SlotInfo { std::vector<unsigned char> key; size_t payload_size; int frames_per_bit; bool mix; };
 std::vector<SlotInfo> g_slots;
+/* the FrameMod table currently on the device */
+std::vector<unsigned char> g_embed_key;
+std::vector<int>           g_embed_bits;
+int                        g_embed_fpb_mix = -1;
 }
 
 awm_ctx *
@@ -36,6 +40,8 @@ Engine::shutdown()
   g_ctx = nullptr;
   g_failed = false;
   g_slots.clear();
+  g_embed_key.clear();
+  g_embed_bits.clear();
 }
 
 std::string
@@ -97,11 +103,18 @@ Engine::set_embed_tables (const Key& key, const std::vector<int>& bitvec)
   awm_ctx *c = ctx();
   if (!c)
     return false;
+  const std::vector<unsigned char> kb (key.aes_key(), key.aes_key() + Key::SIZE);
+  const int sig = int (frames_per_block()) * 2 + (Params::mix ? 1 : 0);
+  if (kb == g_embed_key && bitvec == g_embed_bits && sig == g_embed_fpb_mix)
+    return true;                                  // same key + payload as the previous `add`: table is already uploaded
   const std::vector<uint8_t> fm = gen_frame_mod_ab (key, bitvec);
   if (awm_set_embed_tables (c, fm.data(), int (frames_per_block())))
     {
       error ("audiowmark: %s\n", awm_last_error (c));
       return false;
     }
+  g_embed_key = kb;
+  g_embed_bits = bitvec;
+  g_embed_fpb_mix = sig;
   return true;
 }

@@ -252,47 +252,44 @@ struct VitJob
   double            time;
   SyncFinder::Score score;
   ResultSet::Type   type;
+  Key               key;
+  int               chunk = 0;
+  double            speed = 1;
 };
 
-/* code_decode_soft for a list of jobs: one awm_viterbi call per code rate */
-void
-run_viterbi_jobs (const Key& key, vector<VitJob>& jobs, ResultSet& result_set, double speed)
+/* code_decode_soft for every pending code word of a `get` run (A, B and AB mixed, all chunks and keys) in ONE
+ * awm_viterbi launch; the decoded patterns go to the result set of the chunk they came from. */
+bool
+run_viterbi_jobs (vector<VitJob>& jobs, vector<ResultSet>& chunk_results)
 {
   awm_ctx *ctx = Engine::ctx();
   if (!ctx)
-    return;
-  for (int pass = 0; pass < 2; pass++)
+    return false;
+  if (jobs.empty())
+    return true;
+  const int n_msg = int (Params::payload_size);
+  vector<float> raw;
+  vector<int> types (jobs.size());
+  for (size_t j = 0; j < jobs.size(); j++)
     {
-      vector<size_t> sel;
-      for (size_t i = 0; i < jobs.size(); i++)
-        if ((jobs[i].block_type == ConvBlockType::ab) == (pass == 1))
-          sel.push_back (i);
-      if (sel.empty())
-        continue;
-      const size_t n_coded = jobs[sel[0]].soft.size();
-      const int n_msg = int (n_coded / (pass ? 12 : 6)) - AWM_VITERBI_ORDER;
-      vector<float> raw (sel.size() * n_coded);
-      vector<int> types (sel.size());
-      for (size_t j = 0; j < sel.size(); j++)
-        {
-          memcpy (&raw[j * n_coded], jobs[sel[j]].soft.data(), n_coded * sizeof (float));
-          types[j] = jobs[sel[j]].block_type == ConvBlockType::a ? AWM_BLOCK_A : jobs[sel[j]].block_type == ConvBlockType::b ? AWM_BLOCK_B : AWM_BLOCK_AB;
-        }
-      vector<uint8_t> bits (sel.size() * n_msg);
-      vector<float> err (sel.size());
-      if (awm_viterbi (ctx, raw.data(), sel.size(), int (n_coded), types.data(), Params::hard ? 1 : 0, bits.data(), err.data()))
-        {
-          error ("audiowmark: viterbi decoder failed: %s\n", awm_last_error (ctx));
-          continue;
-        }
-      for (size_t j = 0; j < sel.size(); j++)
-        {
-          const VitJob& job = jobs[sel[j]];
-          vector<int> bit_vec (bits.begin() + j * n_msg, bits.begin() + (j + 1) * n_msg);
-          result_set.add_pattern (key, job.time, job.score, bit_vec, err[j], job.type, speed);
-        }
+      raw.insert (raw.end(), jobs[j].soft.begin(), jobs[j].soft.end());
+      types[j] = jobs[j].block_type == ConvBlockType::a ? AWM_BLOCK_A : jobs[j].block_type == ConvBlockType::b ? AWM_BLOCK_B : AWM_BLOCK_AB;
+    }
+  vector<uint8_t> bits (jobs.size() * n_msg);
+  vector<float> err (jobs.size());
+  if (awm_viterbi (ctx, raw.data(), jobs.size(), n_msg, types.data(), Params::hard ? 1 : 0, bits.data(), err.data()))
+    {
+      error ("audiowmark: viterbi decoder failed: %s\n", awm_last_error (ctx));
+      return false;
+    }
+  for (size_t j = 0; j < jobs.size(); j++)
+    {
+      const VitJob& job = jobs[j];
+      vector<int> bit_vec (bits.begin() + j * n_msg, bits.begin() + (j + 1) * n_msg);
+      chunk_results[job.chunk].add_pattern (job.key, job.time, job.score, bit_vec, err[j], job.type, job.speed);
     }
   jobs.clear();
+  return true;
 }
 
 /* fft_range + mix_decode + randomize_bit_order (decode) for several block start positions */
@@ -329,7 +326,7 @@ public:
 
   /* the PCM (n_frames x n_channels at sample_rate) is already bound to the GPU context */
   void
-  run (const vector<Key>& key_list, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set)
+  run (const vector<Key>& key_list, size_t n_frames, int n_channels, int sample_rate, vector<VitJob>& pending, int chunk)
   {
     SyncFinder sync_finder;
     key_results = sync_finder.search (key_list, n_frames, n_channels, SyncFinder::Mode::BLOCK, 0, n_frames * n_channels);
@@ -341,7 +338,11 @@ public:
         const Key& key = key_result.key;
         struct PatternRawBits { size_t index; double quality; vector<float> raw_bit_vec; ConvBlockType block_type; };
         vector<PatternRawBits> prv;
-        vector<VitJob> jobs;
+        auto add_job = [&] (const vector<float>& soft, ConvBlockType bt, double time, SyncFinder::Score score, ResultSet::Type type)
+          {
+            VitJob job { soft, bt, time, score, type, key, chunk, speed };
+            pending.push_back (job);
+          };
 
         vector<uint64_t> indices;
         for (const auto& s : key_result.sync_scores)
@@ -355,7 +356,7 @@ public:
             {
               const auto& sync_score = key_result.sync_scores[i];
               prv.push_back ({ sync_score.index, sync_score.quality, raw[i], sync_score.block_type });
-              jobs.push_back ({ raw[i], sync_score.block_type, double (sync_score.index) / sample_rate, sync_score, ResultSet::Type::BLOCK });
+              add_job (raw[i], sync_score.block_type, double (sync_score.index) / sample_rate, sync_score, ResultSet::Type::BLOCK);
             }
         /* AB: a B block with the closest earlier A block one block length before it (within half a frame) */
         for (size_t i = 0; i < prv.size(); i++)
@@ -383,7 +384,7 @@ public:
                       ab_bits[k * 2 + 1] = b.raw_bit_vec[k];
                     }
                   SyncFinder::Score score_ab { b.index, (a.quality + b.quality) / 2, ConvBlockType::ab };
-                  jobs.push_back ({ ab_bits, ConvBlockType::ab, double (b.index) / sample_rate, score_ab, ResultSet::Type::BLOCK });
+                  add_job (ab_bits, ConvBlockType::ab, double (b.index) / sample_rate, score_ab, ResultSet::Type::BLOCK);
                 }
             }
         /* all: the chain of blocks at multiples of the block length with alternating types and the largest sync sum */
@@ -447,9 +448,8 @@ public:
                 raw_all[k + 1] /= max (norm[1], 1);
               }
             score_all.quality /= norm[0] + norm[1];
-            jobs.push_back ({ raw_all, ConvBlockType::ab, 0.0, score_all, ResultSet::Type::ALL });
+            add_job (raw_all, ConvBlockType::ab, 0.0, score_all, ResultSet::Type::ALL);
           }
-        run_viterbi_jobs (key, jobs, result_set, speed);
       }
     debug_sync_frame_count = n_frames / Params::frame_size;
   }
@@ -483,7 +483,7 @@ class ClipDecoder
 
   enum class Pos { START, END };
   void
-  run_block (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set, Pos pos)
+  run_block (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, vector<VitJob>& pending, int chunk, Pos pos)
   {
     awm_ctx *ctx = Engine::ctx();
     if (!ctx)
@@ -543,7 +543,6 @@ class ClipDecoder
         vector<int> valid;
         if (indices.empty() || !decode_raw_bits (key, indices, raw, valid))
           continue;
-        vector<VitJob> jobs;
         for (size_t i = 0; i < key_result.sync_scores.size(); i++)
           if (valid[2 * i] && valid[2 * i + 1])
             {
@@ -557,29 +556,28 @@ class ClipDecoder
                 }
               SyncFinder::Score sync_score_nopad = sync_score;
               sync_score_nopad.index = time_offset * sample_rate;
-              jobs.push_back ({ raw_bit_vec, ConvBlockType::ab, time_offset, sync_score_nopad, ResultSet::Type::CLIP });
+              pending.push_back (VitJob { raw_bit_vec, ConvBlockType::ab, time_offset, sync_score_nopad, ResultSet::Type::CLIP, key, chunk, speed });
             }
-        run_viterbi_jobs (key, jobs, result_set, speed);
       }
   }
 public:
   explicit ClipDecoder (double speed) : frames_per_blk (mark_sync_frame_count() + mark_data_frame_count()), speed (speed) {}
   void
-  run (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set)
+  run (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, vector<VitJob>& pending, int chunk)
   {
     const int wav_frames = n_frames / Params::frame_size;
     if (wav_frames < frames_per_blk * 3.1)       // clip decoder is only used for small inputs
       {
-        run_block (key_list, samples, n_frames, n_channels, sample_rate, result_set, Pos::START);
-        run_block (key_list, samples, n_frames, n_channels, sample_rate, result_set, Pos::END);
+        run_block (key_list, samples, n_frames, n_channels, sample_rate, pending, chunk, Pos::START);
+        run_block (key_list, samples, n_frames, n_channels, sample_rate, pending, chunk, Pos::END);
       }
   }
 };
 
-/* decode (src/wmget.cc:886-939) for one chunk */
+/* decode (src/wmget.cc:886-939) for one chunk: everything up to the soft bits; the Viterbi jobs are queued */
 int
-decode_chunk (ResultSet& result_set, const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
-              bool first_chunk)
+decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vector<Key>& key_list, const float *samples, size_t n_frames,
+              int n_channels, int sample_rate, bool first_chunk)
 {
   awm_ctx *ctx = Engine::ctx();
   if (!ctx)
@@ -595,13 +593,13 @@ decode_chunk (ResultSet& result_set, const vector<Key>& key_list, const float *s
       return 1;
     }
   BlockDecoder block_decoder (1);
-  block_decoder.run (key_list, n_frames, n_channels, sample_rate, result_set);
+  block_decoder.run (key_list, n_frames, n_channels, sample_rate, pending, chunk);
   if (first_chunk)
     {
       ClipDecoder clip_decoder (1);
-      clip_decoder.run (key_list, samples, n_frames, n_channels, sample_rate, result_set);
+      clip_decoder.run (key_list, samples, n_frames, n_channels, sample_rate, pending, chunk);
     }
-  result_set.set_debug_sync (block_decoder.debug_sync());
+  debug_sync = block_decoder.debug_sync();
   return 0;
 }
 
@@ -632,13 +630,17 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
   bool first_chunk = true, eof = end < max_frames;
   if (n_frames == 0)
     return 0;
+  /* pass 1: sync search + soft bits per chunk (GPU), Viterbi jobs of all chunks are collected */
+  vector<VitJob> pending;
+  vector<double> time_offsets;
+  vector<string> debug_syncs;
   for (;;)
     {
-      ResultSet chunk_result_set;
-      if (decode_chunk (chunk_result_set, key_list, samples + start * n_channels, end - start, n_channels, sample_rate, first_chunk))
+      string debug_sync;
+      if (decode_chunk (pending, int (time_offsets.size()), debug_sync, key_list, samples + start * n_channels, end - start, n_channels, sample_rate, first_chunk))
         return 1;
-      chunk_result_set.apply_time_offset (time_offset);
-      result_set.merge (chunk_result_set);
+      time_offsets.push_back (time_offset);
+      debug_syncs.push_back (debug_sync);
       first_chunk = false;
       if (eof)
         break;
@@ -647,6 +649,16 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
       const size_t new_end = min (start + max_frames, n_frames);
       eof = (new_end - start) < max_frames;
       end = new_end;
+    }
+  /* pass 2: one Viterbi launch, then the reference's per-chunk merge in chunk order */
+  vector<ResultSet> chunk_results (time_offsets.size());
+  if (!run_viterbi_jobs (pending, chunk_results))
+    return 1;
+  for (size_t c = 0; c < chunk_results.size(); c++)
+    {
+      chunk_results[c].set_debug_sync (debug_syncs[c]);
+      chunk_results[c].apply_time_offset (time_offsets[c]);
+      result_set.merge (chunk_results[c]);
     }
   result_set.sort (key_list);
   return 0;

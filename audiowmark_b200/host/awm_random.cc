@@ -55,33 +55,68 @@ AES128::AES128 (const unsigned char *key)
     }
 }
 
+namespace {
+/* T-table for SubBytes + MixColumns of one state column (generated from the S-box) */
+struct TTab
+{
+  uint32_t t[4][256];
+  TTab()
+  {
+    for (int x = 0; x < 256; x++)
+      {
+        const uint8_t s = g_sbox.s[x], s2 = xtime (s), s3 = s2 ^ s;
+        const uint32_t w = uint32_t (s2) | (uint32_t (s) << 8) | (uint32_t (s) << 16) | (uint32_t (s3) << 24);   // bytes (2s, s, s, 3s), little endian
+        for (int r = 0; r < 4; r++)
+          t[r][x] = (w << (8 * r)) | (w >> ((32 - 8 * r) & 31));
+      }
+  }
+};
+const TTab g_ttab;
+inline uint32_t load_le32 (const uint8_t *p) { uint32_t v; memcpy (&v, p, 4); return v; }
+}
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__ ((target ("aes,sse2"))) static void
+encrypt_block_aesni (const uint8_t *rk, const uint8_t in[16], uint8_t out[16])
+{
+  __m128i s = _mm_xor_si128 (_mm_loadu_si128 ((const __m128i *) in), _mm_loadu_si128 ((const __m128i *) rk));
+  for (int r = 1; r < 10; r++)
+    s = _mm_aesenc_si128 (s, _mm_loadu_si128 ((const __m128i *) (rk + 16 * r)));
+  s = _mm_aesenclast_si128 (s, _mm_loadu_si128 ((const __m128i *) (rk + 160)));
+  _mm_storeu_si128 ((__m128i *) out, s);
+}
+static const bool g_have_aesni = __builtin_cpu_supports ("aes") && !getenv ("AWM_NO_AESNI");   // env switch lets the tests cover the table path
+#else
+static const bool g_have_aesni = false;
+static void encrypt_block_aesni (const uint8_t *, const uint8_t *, uint8_t *) {}
+#endif
+
 void
 AES128::encrypt_block (const uint8_t in[16], uint8_t out[16]) const
 {
-  uint8_t st[16];
-  for (int i = 0; i < 16; i++)
-    st[i] = in[i] ^ m_rk[i];
-  for (int round = 1; round <= 10; round++)
+  if (g_have_aesni)
     {
-      uint8_t t[16];
-      /* SubBytes + ShiftRows: state is column major, byte (r, c) at st[4c + r] */
-      for (int c = 0; c < 4; c++)
-        for (int r = 0; r < 4; r++)
-          t[4 * c + r] = g_sbox.s[st[4 * ((c + r) & 3) + r]];
-      if (round < 10)
-        for (int c = 0; c < 4; c++)
-          {
-            const uint8_t a0 = t[4 * c], a1 = t[4 * c + 1], a2 = t[4 * c + 2], a3 = t[4 * c + 3];
-            const uint8_t all = a0 ^ a1 ^ a2 ^ a3;
-            t[4 * c]     = a0 ^ all ^ xtime (a0 ^ a1);
-            t[4 * c + 1] = a1 ^ all ^ xtime (a1 ^ a2);
-            t[4 * c + 2] = a2 ^ all ^ xtime (a2 ^ a3);
-            t[4 * c + 3] = a3 ^ all ^ xtime (a3 ^ a0);
-          }
-      for (int i = 0; i < 16; i++)
-        st[i] = t[i] ^ m_rk[16 * round + i];
+      encrypt_block_aesni (m_rk, in, out);
+      return;
     }
-  memcpy (out, st, 16);
+  /* column c of the state as a little-endian word: byte (r, c) in bits 8r..8r+7 */
+  uint32_t c0 = load_le32 (in) ^ load_le32 (m_rk), c1 = load_le32 (in + 4) ^ load_le32 (m_rk + 4);
+  uint32_t c2 = load_le32 (in + 8) ^ load_le32 (m_rk + 8), c3 = load_le32 (in + 12) ^ load_le32 (m_rk + 12);
+  const uint32_t (*T)[256] = g_ttab.t;
+  for (int round = 1; round < 10; round++)
+    {
+      const uint8_t *rk = m_rk + 16 * round;
+      const uint32_t n0 = T[0][c0 & 0xff] ^ T[1][(c1 >> 8) & 0xff] ^ T[2][(c2 >> 16) & 0xff] ^ T[3][c3 >> 24] ^ load_le32 (rk);
+      const uint32_t n1 = T[0][c1 & 0xff] ^ T[1][(c2 >> 8) & 0xff] ^ T[2][(c3 >> 16) & 0xff] ^ T[3][c0 >> 24] ^ load_le32 (rk + 4);
+      const uint32_t n2 = T[0][c2 & 0xff] ^ T[1][(c3 >> 8) & 0xff] ^ T[2][(c0 >> 16) & 0xff] ^ T[3][c1 >> 24] ^ load_le32 (rk + 8);
+      const uint32_t n3 = T[0][c3 & 0xff] ^ T[1][(c0 >> 8) & 0xff] ^ T[2][(c1 >> 16) & 0xff] ^ T[3][c2 >> 24] ^ load_le32 (rk + 12);
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    }
+  const uint32_t col[4] = { c0, c1, c2, c3 };
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++)
+      out[4 * c + r] = g_sbox.s[(col[(c + r) & 3] >> (8 * r)) & 0xff] ^ m_rk[160 + 4 * c + r];
 }
 
 /* ---------------------------------------------------------------- Random */

@@ -35,33 +35,6 @@ select_local_maxima (vector<SearchScore>& scores)
   scores.swap (selected);
 }
 
-/* subtracting the local mean biases the neighbourhood of a strong peak in the opposite direction:
- * drop peaks that have a 3x stronger peak of opposite sign within 23 search steps */
-void
-mask_avg_false_positives (vector<SearchScore>& scores)
-{
-  constexpr int    mask_distance = local_mean_distance + 3;
-  constexpr double mask_factor   = 3;
-  auto sign = [] (const SearchScore& s) { return (s.raw_quality - s.local_mean < 0) ? -1 : 1; };
-  vector<SearchScore> out;
-  for (int i = 0; i < int (scores.size()); i++)
-    {
-      bool mask = false;
-      for (int d = -mask_distance; d <= mask_distance && !mask; d++)
-        {
-          const int j = i + d;
-          if (j == i || j < 0 || j >= int (scores.size()))
-            continue;
-          const int distance = std::abs (int (scores[i].index) - int (scores[j].index)) / Params::sync_search_step;
-          if (distance <= mask_distance && abs_quality (scores[j]) > abs_quality (scores[i]) * mask_factor && sign (scores[j]) != sign (scores[i]))
-            mask = true;
-        }
-      if (!mask)
-        out.push_back (scores[i]);
-    }
-  scores.swap (out);
-}
-
 void
 select_threshold_and_n_best (vector<SearchScore>& scores, double threshold)
 {
@@ -73,6 +46,60 @@ select_threshold_and_n_best (vector<SearchScore>& scores, double threshold)
     scores.resize (i);                        // all matches above the threshold
   else if (int (scores.size()) > Params::get_n_best)
     scores.resize (Params::get_n_best);       // otherwise the n best
+}
+
+/* select_local_maxima + mask_avg_false_positives + select_threshold_and_n_best in one pass with the same result:
+ * only the few best peaks can survive the threshold / n-best rule, so the (expensive) false-positive mask is
+ * evaluated lazily in descending quality order instead of for every one of the ~n/3 local maxima of a chunk. */
+void
+select_candidates (vector<SearchScore>& scores, double threshold)
+{
+  select_local_maxima (scores);
+  const size_t n = scores.size();
+  constexpr int    mask_distance = local_mean_distance + 3;
+  constexpr double mask_factor   = 3;
+  vector<double> aq (n);
+  vector<uint32_t> order (n);
+  for (size_t i = 0; i < n; i++)
+    {
+      aq[i] = abs_quality (scores[i]);
+      order[i] = i;
+    }
+  auto sign = [&] (size_t i) { return (scores[i].raw_quality - scores[i].local_mean < 0) ? -1 : 1; };
+  auto masked = [&] (int i)
+    {
+      for (int d = -mask_distance; d <= mask_distance; d++)
+        {
+          const int j = i + d;
+          if (j == i || j < 0 || j >= int (n))
+            continue;
+          const int distance = std::abs (int (scores[i].index) - int (scores[j].index)) / Params::sync_search_step;
+          if (distance <= mask_distance && aq[j] > aq[i] * mask_factor && sign (j) != sign (i))
+            return true;
+        }
+      return false;
+    };
+  vector<SearchScore> out;
+  size_t sorted = 0, batch = 64;
+  bool done = n == 0;
+  while (!done)
+    {
+      const size_t end = std::min (n, sorted + batch);
+      std::partial_sort (order.begin() + sorted, order.begin() + end, order.end(), [&] (uint32_t a, uint32_t b) { return aq[a] > aq[b]; });
+      for (size_t k = sorted; k < end && !done; k++)
+        {
+          const uint32_t i = order[k];
+          if (aq[i] <= threshold && int (out.size()) >= Params::get_n_best)
+            done = true;                         // everything above the threshold is in, and at least n_best matches
+          else if (!masked (i))
+            out.push_back (scores[i]);
+        }
+      sorted = end;
+      batch *= 4;
+      if (sorted == n)
+        done = true;
+    }
+  scores.swap (out);
 }
 
 void
@@ -138,9 +165,7 @@ SyncFinder::search (const vector<Key>& key_list, size_t n_frames, int n_channels
         }
       if (ok)
         {
-          select_local_maxima (scores);
-          mask_avg_false_positives (scores);
-          select_threshold_and_n_best (scores, Params::sync_threshold2 * 0.75);
+          select_candidates (scores, Params::sync_threshold2 * 0.75);
           if (mode == Mode::CLIP)               // ClipDecoder: at most n_best matches, but at least 5
             select_truncate_n (scores, std::max (Params::get_n_best, 5));
           ok = awm_sync_refine (ctx, slot, amode, wav_first, wav_last, Params::water_delta, scores.data(), scores.size()) == 0;

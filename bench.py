@@ -55,7 +55,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -131,7 +131,7 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    minutes = args.minutes if args.minutes else 5.0
+    minutes = args.minutes if args.minutes else 10.0
     r = run_reference(args.steps, args.warmup, minutes)
     line = {
         "impl": "reference", "metric": "audio frames/sec embed+detect, 44.1 kHz stereo; decoded-bit match vs ref", "value": r["value"],
@@ -285,7 +285,7 @@ def main_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = run_reference(1, 0, 3.0)
+            r = run_reference(1, 0, 10.0)
             cpu = {"value": r["value"], "unit": "PCM frames/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"],
                    "t_add_s": round(r["t_add_s"], 3), "t_get_s": round(r["t_get_s"], 3), "payload_ok": r["payload_ok"]}
         except Exception as e:          # the bench line must still print
@@ -322,7 +322,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--minutes", type=float, default=0.0, help="audio length per GPU (default 60 = BASELINE configs[1]; reference arm: 5)")
+    ap.add_argument("--minutes", type=float, default=0.0, help="audio length per GPU (default 60 = BASELINE configs[1]; reference arm: 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -146,11 +146,12 @@ int awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size
                        float *raw_bits_out, int *valid_out);
 
 /* ---- Viterbi: normalize_soft_bits (src/wmget.cc:40-65) + conv_decode_soft (src/convcode.cc:128-213)
- * for n_jobs independent code words.  raw_bits: [n_jobs][n_coded] (n_coded = rate * (msg+15),
- * rate 6 for A/B, 12 for AB); block_types[j] in AWM_BLOCK_*; hard != 0 => --hard.
- * bits_out: [n_jobs][n_coded / rate - 15] bytes (0/1), error_out[j] = metric / n_coded.
+ * for n_jobs independent code words in one launch.  block_types[j] in AWM_BLOCK_*: A / B words carry
+ * 6 * (n_msg_bits + 15) soft bits, AB words 12 * (n_msg_bits + 15); raw_bits holds the jobs back to back
+ * (un-normalised soft bits as mix_decode delivers them); hard != 0 => --hard.
+ * bits_out: [n_jobs][n_msg_bits] bytes (0/1), error_out[j] = final path metric / coded bits.
  */
-int awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_coded, const int *block_types,
+int awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits, const int *block_types,
                  int hard, uint8_t *bits_out, float *error_out);
 
 #ifdef __cplusplus

@@ -147,7 +147,6 @@ def test_viterbi_vs_oracle(ctx):
         jobs = []
         for noise in (0.0, 0.6, 1.5, 4.0):
             jobs.append(((coded * 2 - 1) + noise * rng.standard_normal(len(coded))).astype(np.float32))
-        jobs = np.stack(jobs)
         bits, err = ctx.viterbi(jobs, [cbt] * len(jobs))
         hbits, herr = ctx.viterbi(jobs, [cbt] * len(jobs), hard=True)
         for j in range(len(jobs)):
