@@ -84,7 +84,7 @@ struct awm_ctx
   const float *pcm = nullptr; size_t pcm_frames = 0; int pcm_ch = 0;
   DevBuf pcm_own;
 
-  DevBuf dbT, have, q, scores;       // approx
+  DevBuf dbT, have, q, scores, a_ud, a_cnt;       // approx
   DevBuf cand_start, cand_noff, r_ud, r_cnt, rvalid;   // refine
   DevBuf blk_start, D, raw;          // decode
   DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
@@ -247,7 +247,7 @@ awm_destroy (awm_ctx *ctx)
     return;
   cudaSetDevice (ctx->device);
   cudaStreamSynchronize (ctx->stream);
-  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores,
+  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt,
                      &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
                      &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
                      &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr };
@@ -293,6 +293,25 @@ awm_synchronize (awm_ctx *ctx)
   CK (cudaSetDevice (ctx->device));
   CK (cudaStreamSynchronize (ctx->stream));
   return 0;
+}
+
+void *
+awm_host_alloc (size_t bytes)
+{
+  void *p = nullptr;
+  if (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return nullptr;
+    }
+  return p;
+}
+
+void
+awm_host_free (void *p)
+{
+  if (p)
+    cudaFreeHost (p);
 }
 
 int
@@ -648,6 +667,8 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   CK (ctx->dbT.reserve (size_t (4) * kBands * ld * sizeof (float)));
   CK (ctx->have.reserve (size_t (4) * ld));
   CK (ctx->q.reserve (size_t (n_starts) * 4 * sizeof (double)));
+  CK (ctx->a_ud.reserve (size_t (n_starts) * 4 * t.n_bits * 2 * sizeof (float)));
+  CK (ctx->a_cnt.reserve (size_t (n_starts) * 4 * t.n_bits * sizeof (int)));
   CK (ctx->scores.reserve (size_t (n_starts) * 4 * sizeof (awm_search_score)));
   {
     const size_t smem = fft_smem_bytes (kStftWarps) + kBands * (kStftWarps + 1) * sizeof (float);
@@ -668,19 +689,23 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
       {
         if (set_smem (ctx, k_sync_approx<true>, smem)) return 1;
         PROF (ctx);
-        k_sync_approx<true><<<grid, kApproxCands, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
-                                                                      t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
-                                                                      norm_div, ctx->q.as<double>());
+        k_sync_approx<true><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
+                                                                        t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
+                                                                        ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
       }
     else
       {
         if (set_smem (ctx, k_sync_approx<false>, smem)) return 1;
         PROF (ctx);
-        k_sync_approx<false><<<grid, kApproxCands, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
-                                                                       t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
-                                                                       norm_div, ctx->q.as<double>());
+        k_sync_approx<false><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
+                                                                         t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
+                                                                         ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
       }
     LAUNCH_CHECK ("k_sync_approx");
+    PROF (ctx);
+    k_sync_quality<<<unsigned ((n_starts * 4 + 255) / 256), 256, 0, ctx->stream>>> (ctx->a_ud.as<float>(), ctx->a_cnt.as<int>(), int (n_starts), t.n_bits,
+                                                                                norm_div, ctx->q.as<double>());
+    LAUNCH_CHECK ("k_sync_quality");
   }
   {
     const long long n = n_starts * 4;

@@ -88,7 +88,7 @@ fft32_dif (float (&re)[32], float (&im)[32])
   DifK<2, 0, 0>::run (re, im);
 }
 
-constexpr int kWarpFftSmemFloats = 2 * 32 * 33;     // re + im planes, row stride 33 (bank-conflict free)
+constexpr int kWarpFftSmemFloats = 2 * 32 * 33;     // 32 x 33 float2, row stride 33 (bank-conflict free)
 
 // 1024-point forward FFT of the warp's 32x32 register tile.
 //   in : re[j], im[j] = z[32*j + lane]
@@ -99,21 +99,21 @@ __device__ __forceinline__ void
 fft1024_warp (float (&re)[32], float (&im)[32], const float2 *tw, float *xbuf, int lane)
 {
   fft32_dif (re, im);
-  float *sre = xbuf, *sim = xbuf + 32 * 33;
+  float2 *xb = reinterpret_cast<float2 *> (xbuf);        // [32][33] complex, row stride 33: 64-bit accesses stay conflict free
 #pragma unroll
   for (int i = 0; i < 32; i++)
     {
       const int k1 = brev5 (i);
       const float2 w = tw[k1 * 32 + lane];
-      sre[k1 * 33 + lane] = re[i] * w.x - im[i] * w.y;
-      sim[k1 * 33 + lane] = re[i] * w.y + im[i] * w.x;
+      xb[k1 * 33 + lane] = make_float2 (re[i] * w.x - im[i] * w.y, re[i] * w.y + im[i] * w.x);
     }
   __syncwarp();
 #pragma unroll
   for (int t = 0; t < 32; t++)
     {
-      re[t] = sre[lane * 33 + t];
-      im[t] = sim[lane * 33 + t];
+      const float2 v = xb[lane * 33 + t];
+      re[t] = v.x;
+      im[t] = v.y;
     }
   __syncwarp();
   fft32_dif (re, im);

@@ -47,7 +47,20 @@ __device__ __forceinline__ void
 load_pair (const float *__restrict__ pcm, long long n_frames, int C, long long start, int chA, int chB,
            const float *win, float (&re)[32], float (&im)[32], int lane)
 {
-  if (C == 2 && chB == 1)
+  if (C == 2 && chB == 1 && start >= 0 && start + kFrame <= n_frames)
+    {
+      /* common case: whole stereo frame inside the buffer -> one base pointer, immediate offsets, no bounds tests */
+      const float2 *p = reinterpret_cast<const float2 *> (pcm) + start + lane;
+#pragma unroll
+      for (int j = 0; j < 32; j++)
+        {
+          const float2 v = __ldg (p + 32 * j);
+          const float w = win[32 * j + lane];
+          re[j] = v.x * w;
+          im[j] = v.y * w;
+        }
+    }
+  else if (C == 2 && chB == 1)
     {
       const float2 *p2 = reinterpret_cast<const float2 *> (pcm);
 #pragma unroll
@@ -268,66 +281,92 @@ k_stft_db (const float *__restrict__ pcm, long long n_frames, int C, int n_out, 
 // once per (candidate, entry) -- 30600 float adds per candidate then run at shared-memory speed.
 //   ent_sorted: all entries of all bits merged by ascending frame (per-bit order is preserved),
 //               64 bytes each: u16 frame, u8 bit, u8 pad, u8 up[30], u8 down[30]
-//   group_end : entries [group_end[g-1], group_end[g]) span at most kApproxRing - kApproxCands - 1 frames
+//   group_end : entries [group_end[g-1], group_end[g]) span at most kApproxMaxSpan frames
 // out[s*4 + shift] so that the array is already sorted by index = s*1024 + shift*256.
 // =============================================================================================
-constexpr int kApproxCands = 256;          // candidates (= threads) per CTA
+constexpr int kApproxCands = 256;          // candidates per CTA
+constexpr int kApproxSplit = 3;            // thread groups per candidate: group j sums sync bits 2j, 2j+1 (more warps to hide latency)
+constexpr int kApproxThreads = kApproxCands * kApproxSplit;
 constexpr int kApproxRing = 512;           // ring length in frames (power of two)
-constexpr int kApproxMaxSpan = kApproxRing - kApproxCands - 1;
+constexpr int kApproxMaxSpan = (kApproxRing - kApproxCands) / 2 - 1;   // two consecutive groups fit the ring: group g+1 is prefetched while g is summed
 struct ApproxEntry { uint16_t frame; uint8_t bit, pad; uint8_t up[30], down[30]; };
 static_assert (sizeof (ApproxEntry) == 64, "ApproxEntry must be 64 bytes");
 constexpr size_t kApproxSmem = size_t (kBands) * kApproxRing * sizeof (float) + kApproxRing;
 
-template<bool CHECK_HAVE> __global__ void __launch_bounds__ (kApproxCands, 1)
+template<bool CHECK_HAVE> __global__ void __launch_bounds__ (kApproxThreads, 1)
 k_sync_approx (const float *__restrict__ dbT, const unsigned char *__restrict__ have, int ld, int n_out, int n_starts,
                const ApproxEntry *__restrict__ ent_sorted, const int *__restrict__ group_end, int n_groups, int n_bits,
-               double norm_div, double *__restrict__ out)
+               float *__restrict__ out_ud /* [4][n_starts][n_bits][2] */, int *__restrict__ out_cnt /* [4][n_starts][n_bits] */)
 {
   extern __shared__ __align__ (16) unsigned char smem[];
   float *ring = reinterpret_cast<float *> (smem);                         // [band][kApproxRing]
   unsigned char *hring = smem + size_t (kBands) * kApproxRing * sizeof (float);   // have flags, same slots
   const int shift_idx = blockIdx.y;
   const int s0 = blockIdx.x * kApproxCands;
-  const int s = s0 + threadIdx.x;
+  const int cand = threadIdx.x % kApproxCands, part = threadIdx.x / kApproxCands;   // part is warp-uniform
+  const int s = s0 + cand;
   const float *db = dbT + (size_t) shift_idx * kBands * ld;
   const unsigned char *hv = have + (size_t) shift_idx * ld;
 
-  float u0 = 0, u1 = 0, u2 = 0, u3 = 0, u4 = 0, u5 = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0;
-  int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+  float u0 = 0, u1 = 0, d0 = 0, d1 = 0;                                   // sums of sync bits 2*part and 2*part + 1
+  int c0 = 0, c1 = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int loaded = s0;                                                          // frames < loaded are (or were) in the ring
+  // asynchronous top-up of the ring with the frames group g needs (cp.async: no registers, no stall until the wait)
+  auto prefetch = [&] (int g)
+    {
+      const int e_first = g ? group_end[g - 1] : 0;
+      const int fr_first = ent_sorted[e_first].frame, fr_last = ent_sorted[group_end[g] - 1].frame;
+      const int need_lo = max (loaded, s0 + fr_first), need_hi = s0 + fr_last + kApproxCands;
+      for (int band = warp; band < kBands; band += kApproxThreads / 32)
+        {
+          const float *src = db + (size_t) band * ld;
+          float *dst = ring + band * kApproxRing;
+          for (int f = need_lo + lane; f < need_hi; f += 32)
+            {
+              if (f < n_out)
+                {
+                  const unsigned sa = (unsigned) __cvta_generic_to_shared (dst + (f & (kApproxRing - 1)));
+                  asm volatile ("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(src + f) : "memory");
+                }
+              else
+                dst[f & (kApproxRing - 1)] = 0.f;
+            }
+        }
+      if (CHECK_HAVE)
+        for (int f = need_lo + threadIdx.x; f < need_hi; f += kApproxThreads)
+          hring[f & (kApproxRing - 1)] = f < n_out ? hv[f] : 0;
+      loaded = need_hi;
+    };
+  prefetch (0);
+  asm volatile ("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
   int e = 0;
   for (int g = 0; g < n_groups; g++)
     {
       const int e_end = group_end[g];
-      const int fr_first = ent_sorted[e].frame, fr_last = ent_sorted[e_end - 1].frame;
-      const int need_lo = max (loaded, s0 + fr_first), need_hi = s0 + fr_last + kApproxCands;
-      __syncthreads();                                                      // previous group no longer reads the slots we overwrite
-      const int n_new = need_hi - need_lo;
-      for (int i = threadIdx.x; i < n_new * kBands; i += kApproxCands)
+      // group g+1 may be fetched while g is summed if both fit the ring together (normally true: groups span <= kApproxMaxSpan)
+      bool early = false;
+      if (g + 1 < n_groups)
         {
-          const int band = i / n_new, f = need_lo + i % n_new;
-          ring[band * kApproxRing + (f & (kApproxRing - 1))] = f < n_out ? __ldg (db + (size_t) band * ld + f) : 0.f;
+          early = int (ent_sorted[group_end[g + 1] - 1].frame) - int (ent_sorted[e].frame) + kApproxCands < kApproxRing;
+          if (early)
+            prefetch (g + 1);
         }
-      if (CHECK_HAVE)
-        for (int i = threadIdx.x; i < n_new; i += kApproxCands)
-          {
-            const int f = need_lo + i;
-            hring[f & (kApproxRing - 1)] = f < n_out ? hv[f] : 0;
-          }
-      loaded = need_hi;
-      __syncthreads();
       for (; e < e_end; e++)
         {
           const uint4 *e4 = reinterpret_cast<const uint4 *> (ent_sorted + e);
           const uint4 w0 = __ldg (e4), w1 = __ldg (e4 + 1), w2 = __ldg (e4 + 2), w3 = __ldg (e4 + 3);
           const unsigned words[16] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w };
           const int frame = words[0] & 0xffff, bit = (words[0] >> 16) & 0xff;
+          if ((bit >> 1) != part)
+            continue;                                                       // another thread group owns this sync bit
           const int slot = (s + frame) & (kApproxRing - 1);
           if (CHECK_HAVE && !hring[slot])
             continue;
           const float *base = ring + slot;
-          float um = bit == 0 ? u0 : bit == 1 ? u1 : bit == 2 ? u2 : bit == 3 ? u3 : bit == 4 ? u4 : u5;
-          float dm = bit == 0 ? d0 : bit == 1 ? d1 : bit == 2 ? d2 : bit == 3 ? d3 : bit == 4 ? d4 : d5;
+          const bool odd = bit & 1;
+          float um = odd ? u1 : u0, dm = odd ? d1 : d0;
 #pragma unroll
           for (int i = 0; i < kUD; i++)
             {
@@ -336,35 +375,60 @@ k_sync_approx (const float *__restrict__ dbT, const unsigned char *__restrict__ 
               um += base[ub * kApproxRing];
               dm += base[dbn * kApproxRing];
             }
-          if (bit == 0) { u0 = um; d0 = dm; c0++; } else if (bit == 1) { u1 = um; d1 = dm; c1++; }
-          else if (bit == 2) { u2 = um; d2 = dm; c2++; } else if (bit == 3) { u3 = um; d3 = dm; c3++; }
-          else if (bit == 4) { u4 = um; d4 = dm; c4++; } else { u5 = um; d5 = dm; c5++; }
+          if (odd) { u1 = um; d1 = dm; c1++; } else { u0 = um; d0 = dm; c0++; }
         }
+      if (g + 1 < n_groups && !early)
+        {
+          __syncthreads();
+          prefetch (g + 1);
+        }
+      asm volatile ("cp.async.wait_all;" ::: "memory");
+      __syncthreads();                                                      // next group's frames are in; nobody reads this group's any more
     }
   if (s >= n_starts)
     return;
-  const float um[6] = { u0, u1, u2, u3, u4, u5 }, dm[6] = { d0, d1, d2, d3, d4, d5 };
-  const int cn[6] = { c0, c1, c2, c3, c4, c5 };
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+    {
+      const int bit = 2 * part + k;
+      if (bit < n_bits)
+        {
+          const size_t o = ((size_t) shift_idx * n_starts + s) * n_bits + bit;
+          out_ud[o * 2] = k ? u1 : u0;
+          out_ud[o * 2 + 1] = k ? d1 : d0;
+          out_cnt[o] = k ? c1 : c0;
+        }
+    }
+}
+
+// sync_decode epilogue (bit_quality, src/syncfinder.cc:94-114; normalisation :80-91) + local mean of
+// SyncFinder::search_approx (:234-254).  q[i] with i = s*4 + shift is the score list sorted by index.
+__global__ void
+k_sync_quality (const float *__restrict__ ud, const int *__restrict__ cnt, int n_starts, int n_bits, double norm_div, double *__restrict__ q)
+{
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4LL * n_starts)
+    return;
+  const int s = int (i >> 2), shift_idx = int (i & 3);
   double sync_quality = 0;
   int bit_count = 0;
-#pragma unroll
-  for (int bit = 0; bit < 6; bit++)
-    if (bit < n_bits)
-      {
-        const float umag = um[bit], dmag = dm[bit];
-        double raw_bit;
-        if (umag == 0 || dmag == 0)
-          raw_bit = 0;
-        else if (umag < dmag)
-          raw_bit = 1 - double (umag) / double (dmag);
-        else
-          raw_bit = double (dmag) / double (umag) - 1;
-        sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * cn[bit];
-        bit_count += cn[bit];
-      }
+  for (int bit = 0; bit < n_bits; bit++)
+    {
+      const size_t o = ((size_t) shift_idx * n_starts + s) * n_bits + bit;
+      const float umag = ud[o * 2], dmag = ud[o * 2 + 1];
+      double raw_bit;
+      if (umag == 0 || dmag == 0)
+        raw_bit = 0;
+      else if (umag < dmag)
+        raw_bit = 1 - double (umag) / double (dmag);
+      else
+        raw_bit = double (dmag) / double (umag) - 1;
+      sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * cnt[o];
+      bit_count += cnt[o];
+    }
   if (bit_count)
     sync_quality /= bit_count;
-  out[(size_t) s * 4 + shift_idx] = sync_quality / norm_div / 2.9;
+  q[i] = sync_quality / norm_div / 2.9;
 }
 
 // local mean of SyncFinder::search_approx (src/syncfinder.cc:234-254) + packing of the score list

@@ -10,6 +10,7 @@
 #include <map>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 using std::string;
 using std::vector;
@@ -592,8 +593,11 @@ decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vect
       error ("audiowmark: %s\n", awm_last_error (ctx));
       return 1;
     }
+  const double tb0 = get_time();
   BlockDecoder block_decoder (1);
   block_decoder.run (key_list, n_frames, n_channels, sample_rate, pending, chunk);
+  if (getenv ("AWM_TRACE"))
+    fprintf (stderr, "[trace] chunk %d: block decoder (sync + soft bits) %.3f ms\n", chunk, (get_time() - tb0) * 1e3);
   if (first_chunk)
     {
       ClipDecoder clip_decoder (1);
@@ -652,8 +656,12 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
     }
   /* pass 2: one Viterbi launch, then the reference's per-chunk merge in chunk order */
   vector<ResultSet> chunk_results (time_offsets.size());
+  const double tv0 = get_time();
+  const size_t n_jobs = pending.size();
   if (!run_viterbi_jobs (pending, chunk_results))
     return 1;
+  if (getenv ("AWM_TRACE"))
+    fprintf (stderr, "[trace] viterbi: %zu jobs %.3f ms\n", n_jobs, (get_time() - tv0) * 1e3);
   for (size_t c = 0; c < chunk_results.size(); c++)
     {
       chunk_results[c].set_debug_sync (debug_syncs[c]);

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 using std::vector;
 
@@ -17,22 +18,72 @@ typedef awm_search_score SearchScore;
 inline double abs_quality (const SearchScore& s) { return fabs (s.raw_quality - s.local_mean); }
 constexpr int local_mean_distance = 20;
 
+/* select_local_maxima (src/syncfinder.cc:258-281) + sync_mask_avg_false_positives (:292-332) +
+ * sync_select_threshold_and_n_best (:364-383) with the same result, restructured for a list of several
+ * hundred thousand scores: one streaming pass finds the local maxima ("skip the score after a maximum" rule
+ * included); only the few best peaks can survive the threshold / n-best rule, so the false-positive mask
+ * (a 47-neighbour test) is evaluated lazily in descending quality order instead of for every peak. */
 void
-select_local_maxima (vector<SearchScore>& scores)
+select_candidates (const SearchScore *sc, size_t n, double threshold, vector<SearchScore>& out)
 {
-  vector<SearchScore> selected;
-  for (size_t i = 0; i < scores.size(); i++)
+  out.clear();
+  if (!n)
+    return;
+  vector<double> aq (n);
+  for (size_t i = 0; i < n; i++)
+    aq[i] = fabs (sc[i].raw_quality - sc[i].local_mean);
+  vector<uint32_t> ppos;                          // positions of the local maxima, ascending
+  ppos.reserve (n / 3 + 16);
+  for (size_t i = 0; i < n; i++)
     {
-      const double q = abs_quality (scores[i]);
-      const double q_last = i > 0 ? abs_quality (scores[i - 1]) : 0;
-      const double q_next = i + 1 < scores.size() ? abs_quality (scores[i + 1]) : 0;
+      const double q = aq[i], q_last = i > 0 ? aq[i - 1] : 0, q_next = i + 1 < n ? aq[i + 1] : 0;
       if (q >= q_last && q >= q_next)
         {
-          selected.push_back (scores[i]);
-          i++;       // the next score cannot be a local maximum
+          ppos.push_back (i);
+          i++;                                    // the next score cannot be a local maximum
         }
     }
-  scores.swap (selected);
+  const size_t np = ppos.size();
+  constexpr int    mask_distance = local_mean_distance + 3;
+  constexpr double mask_factor   = 3;
+  auto paq = [&] (size_t k) { return aq[ppos[k]]; };
+  auto sign = [&] (size_t k) { const SearchScore& s = sc[ppos[k]]; return (s.raw_quality - s.local_mean < 0) ? -1 : 1; };
+  auto masked = [&] (int i)
+    {
+      /* a peak is dropped if a 3x stronger peak of opposite sign lies within 23 search steps (and 23 peaks) */
+      for (int d = -mask_distance; d <= mask_distance; d++)
+        {
+          const int j = i + d;
+          if (j == i || j < 0 || j >= int (np))
+            continue;
+          const int distance = std::abs (int (sc[ppos[i]].index) - int (sc[ppos[j]].index)) / Params::sync_search_step;
+          if (distance <= mask_distance && paq (j) > paq (i) * mask_factor && sign (j) != sign (i))
+            return true;
+        }
+      return false;
+    };
+  vector<uint32_t> order (np);
+  for (size_t k = 0; k < np; k++)
+    order[k] = k;
+  size_t sorted = 0, batch = 64;
+  bool done = np == 0;
+  while (!done)
+    {
+      const size_t end = std::min (np, sorted + batch);
+      std::partial_sort (order.begin() + sorted, order.begin() + end, order.end(), [&] (uint32_t a, uint32_t b) { return paq (a) > paq (b); });
+      for (size_t k = sorted; k < end && !done; k++)
+        {
+          const uint32_t i = order[k];
+          if (paq (i) <= threshold && int (out.size()) >= Params::get_n_best)
+            done = true;                         // everything above the threshold is in, and at least n_best matches
+          else if (!masked (i))
+            out.push_back (sc[ppos[i]]);
+        }
+      sorted = end;
+      batch *= 4;
+      if (sorted == np)
+        done = true;
+    }
 }
 
 void
@@ -46,60 +97,6 @@ select_threshold_and_n_best (vector<SearchScore>& scores, double threshold)
     scores.resize (i);                        // all matches above the threshold
   else if (int (scores.size()) > Params::get_n_best)
     scores.resize (Params::get_n_best);       // otherwise the n best
-}
-
-/* select_local_maxima + mask_avg_false_positives + select_threshold_and_n_best in one pass with the same result:
- * only the few best peaks can survive the threshold / n-best rule, so the (expensive) false-positive mask is
- * evaluated lazily in descending quality order instead of for every one of the ~n/3 local maxima of a chunk. */
-void
-select_candidates (vector<SearchScore>& scores, double threshold)
-{
-  select_local_maxima (scores);
-  const size_t n = scores.size();
-  constexpr int    mask_distance = local_mean_distance + 3;
-  constexpr double mask_factor   = 3;
-  vector<double> aq (n);
-  vector<uint32_t> order (n);
-  for (size_t i = 0; i < n; i++)
-    {
-      aq[i] = abs_quality (scores[i]);
-      order[i] = i;
-    }
-  auto sign = [&] (size_t i) { return (scores[i].raw_quality - scores[i].local_mean < 0) ? -1 : 1; };
-  auto masked = [&] (int i)
-    {
-      for (int d = -mask_distance; d <= mask_distance; d++)
-        {
-          const int j = i + d;
-          if (j == i || j < 0 || j >= int (n))
-            continue;
-          const int distance = std::abs (int (scores[i].index) - int (scores[j].index)) / Params::sync_search_step;
-          if (distance <= mask_distance && aq[j] > aq[i] * mask_factor && sign (j) != sign (i))
-            return true;
-        }
-      return false;
-    };
-  vector<SearchScore> out;
-  size_t sorted = 0, batch = 64;
-  bool done = n == 0;
-  while (!done)
-    {
-      const size_t end = std::min (n, sorted + batch);
-      std::partial_sort (order.begin() + sorted, order.begin() + end, order.end(), [&] (uint32_t a, uint32_t b) { return aq[a] > aq[b]; });
-      for (size_t k = sorted; k < end && !done; k++)
-        {
-          const uint32_t i = order[k];
-          if (aq[i] <= threshold && int (out.size()) >= Params::get_n_best)
-            done = true;                         // everything above the threshold is in, and at least n_best matches
-          else if (!masked (i))
-            out.push_back (scores[i]);
-        }
-      sorted = end;
-      batch *= 4;
-      if (sorted == n)
-        done = true;
-    }
-  scores.swap (out);
 }
 
 void
@@ -152,24 +149,45 @@ SyncFinder::search (const vector<Key>& key_list, size_t n_frames, int n_channels
       key_result.key = key;
       const int slot = ctx ? Engine::key_slot (key) : -1;
       vector<SearchScore> scores;
+      static SearchScore *all = nullptr;       // page-locked staging buffer for the full score list of a chunk
+      static size_t all_cap = 0;
       bool ok = slot >= 0;
+      size_t n_all = 0;
+      const bool trace = getenv ("AWM_TRACE") != nullptr;
+      const double t0 = get_time();
+      double t1 = t0, t2 = t0, t3 = t0;
       if (ok)
         {
           size_t n_scores = 0;
           ok = awm_sync_approx (ctx, slot, amode, wav_first, wav_last, Params::water_delta, nullptr, 0, &n_scores) == 0;
-          if (ok && n_scores)
+          if (ok && n_scores > all_cap)
             {
-              scores.resize (n_scores);
-              ok = awm_sync_approx (ctx, slot, amode, wav_first, wav_last, Params::water_delta, scores.data(), scores.size(), &n_scores) == 0;
+              awm_host_free (all);
+              all_cap = n_scores + n_scores / 4;
+              all = static_cast<SearchScore *> (awm_host_alloc (all_cap * sizeof (SearchScore)));
+              if (!all)
+                {
+                  all_cap = 0;
+                  ok = false;
+                }
             }
+          if (ok && n_scores)
+            ok = awm_sync_approx (ctx, slot, amode, wav_first, wav_last, Params::water_delta, all, all_cap, &n_scores) == 0;
+          n_all = ok ? n_scores : 0;
         }
+      t1 = get_time();
       if (ok)
         {
-          select_candidates (scores, Params::sync_threshold2 * 0.75);
+          select_candidates (all, n_all, Params::sync_threshold2 * 0.75, scores);
           if (mode == Mode::CLIP)               // ClipDecoder: at most n_best matches, but at least 5
             select_truncate_n (scores, std::max (Params::get_n_best, 5));
+          t2 = get_time();
           ok = awm_sync_refine (ctx, slot, amode, wav_first, wav_last, Params::water_delta, scores.data(), scores.size()) == 0;
         }
+      t3 = get_time();
+      if (trace)
+        fprintf (stderr, "[trace] sync search: approx %.3f ms, select %.3f ms, refine %.3f ms (%zu candidates)\n",
+                 (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, scores.size());
       if (!ok)
         {
           error ("audiowmark: sync search failed: %s\n", Engine::last_error().c_str());

@@ -67,6 +67,9 @@ void       *awm_stream (awm_ctx *ctx);
 int         awm_synchronize (awm_ctx *ctx);
 /* measurement aid: when enabled every kernel launch is bracketed by CUDA events on the context stream;
  * awm_profile_report synchronises, writes {"kernel": {"launches": n, "ms": total}, ...} as JSON and resets */
+/* page-locked host memory for buffers that cross PCIe (PCM, score lists); plain malloc'ed memory works too, only slower */
+void       *awm_host_alloc (size_t bytes);
+void        awm_host_free (void *p);
 int         awm_profile_enable (awm_ctx *ctx, int on);
 int         awm_profile_report (awm_ctx *ctx, char *json_out, size_t json_cap);
 
