@@ -27,7 +27,7 @@ EXPORTS = [
     "awm_create", "awm_destroy", "awm_last_error", "awm_launch_count", "awm_stream", "awm_synchronize",
     "awm_profile_enable", "awm_profile_report", "awm_host_alloc", "awm_host_free",
     "awm_fft_r2c", "awm_fft_c2r", "awm_set_embed_tables", "awm_set_sync_tables", "awm_set_mix_tables",
-    "awm_pcm_bind", "awm_embed", "awm_sync_approx", "awm_sync_refine", "awm_decode_blocks", "awm_viterbi",
+    "awm_pcm_bind", "awm_embed", "awm_sync_approx", "awm_sync_peaks", "awm_sync_refine", "awm_decode_blocks", "awm_viterbi",
 ]
 
 _lib = None
@@ -170,6 +170,13 @@ class Context:
             self._ck(self.lib.awm_sync_approx(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), ctypes.c_uint64(wav_first), ctypes.c_uint64(wav_last),
                                               ctypes.c_double(water_delta), _ptr(out), ctypes.c_size_t(n.value), ctypes.byref(n)))
         return out
+
+    def sync_peaks(self, min_abs_quality: float, max_peaks: int = 65536):
+        """local maxima above a floor of the LAST sync_approx call; returns (peaks sorted by index, number found)."""
+        out = np.zeros(max_peaks, SEARCH_SCORE)
+        n = ctypes.c_size_t()
+        self._ck(self.lib.awm_sync_peaks(self.h, ctypes.c_double(min_abs_quality), _ptr(out), ctypes.c_size_t(max_peaks), ctypes.byref(n)))
+        return out[:min(n.value, max_peaks)].copy(), n.value
 
     def sync_refine(self, scores: np.ndarray, key_slot=0, mode=MODE_BLOCK, wav_first=0, wav_last=None, water_delta=0.01) -> np.ndarray:
         if wav_last is None:

@@ -84,7 +84,8 @@ struct awm_ctx
   const float *pcm = nullptr; size_t pcm_frames = 0; int pcm_ch = 0;
   DevBuf pcm_own;
 
-  DevBuf dbT, have, q, scores, a_ud, a_cnt;       // approx
+  DevBuf dbT, have, q, scores, a_ud, a_cnt, peaks_out, peaks_cnt;       // approx
+  size_t n_scores_dev = 0;
   DevBuf cand_start, cand_noff, r_ud, r_cnt, rvalid;   // refine
   DevBuf blk_start, D, raw;          // decode
   DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
@@ -247,7 +248,7 @@ awm_destroy (awm_ctx *ctx)
     return;
   cudaSetDevice (ctx->device);
   cudaStreamSynchronize (ctx->stream);
-  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt,
+  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt,
                      &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
                      &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
                      &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr };
@@ -659,9 +660,10 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   const long long n_out = fc > 0 ? fc - 1 : 0;                           // sync_fft_parallel: frame_count - 1 frames per shift
   const long long n_starts = fc - total - 1 > 0 ? fc - total - 1 : 0;    // (start + total) * n_bands < fft_db.size()
   *n_scores = size_t (n_starts) * 4;
-  if (!scores_out || n_starts == 0)
+  ctx->n_scores_dev = 0;
+  if (n_starts == 0)
     return 0;
-  if (max_scores < size_t (n_starts) * 4)
+  if (scores_out && max_scores < size_t (n_starts) * 4)
     return fail (ctx, "awm_sync_approx: scores_out too small (%zu < %lld)", max_scores, n_starts * 4);
   const int ld = int ((n_out + 31) / 32 * 32);
   CK (ctx->dbT.reserve (size_t (4) * kBands * ld * sizeof (float)));
@@ -713,8 +715,44 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     k_local_mean<<<unsigned ((n + 255) / 256), 256, 0, ctx->stream>>> (ctx->q.as<double>(), n, ctx->scores.as<awm_search_score>());
     LAUNCH_CHECK ("k_local_mean");
   }
-  CK (cudaMemcpyAsync (scores_out, ctx->scores.p, size_t (n_starts) * 4 * sizeof (awm_search_score), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->n_scores_dev = size_t (n_starts) * 4;
+  if (scores_out)
+    {
+      CK (cudaMemcpyAsync (scores_out, ctx->scores.p, size_t (n_starts) * 4 * sizeof (awm_search_score), cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaStreamSynchronize (ctx->stream));
+    }
+  return 0;
+}
+
+int
+awm_sync_peaks (awm_ctx *ctx, double min_abs_quality, awm_search_score *out, size_t max, size_t *n)
+{
+  if (!n || (max && !out))
+    return fail (ctx, "awm_sync_peaks: bad arguments");
+  *n = 0;
+  if (!ctx->n_scores_dev)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  CK (ctx->peaks_out.reserve (std::max<size_t> (max, 1) * sizeof (awm_search_score)));
+  CK (ctx->peaks_cnt.reserve (sizeof (unsigned long long)));
+  CK (cudaMemsetAsync (ctx->peaks_cnt.p, 0, sizeof (unsigned long long), ctx->stream));
+  const long long ns = (long long) ctx->n_scores_dev;
+  PROF (ctx);
+  k_peaks<<<unsigned ((ns + 255) / 256), 256, 0, ctx->stream>>> (ctx->scores.as<awm_search_score>(), ns, min_abs_quality,
+                                                                ctx->peaks_out.as<awm_search_score>(), (unsigned long long) max,
+                                                                ctx->peaks_cnt.as<unsigned long long>());
+  LAUNCH_CHECK ("k_peaks");
+  unsigned long long cnt = 0;
+  CK (cudaMemcpyAsync (&cnt, ctx->peaks_cnt.p, sizeof (cnt), cudaMemcpyDeviceToHost, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
+  *n = size_t (cnt);
+  const size_t got = std::min<size_t> (cnt, max);
+  if (got)
+    {
+      CK (cudaMemcpyAsync (out, ctx->peaks_out.p, got * sizeof (awm_search_score), cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaStreamSynchronize (ctx->stream));
+      std::sort (out, out + got, [] (const awm_search_score& a, const awm_search_score& b) { return a.index < b.index; });
+    }
   return 0;
 }
 

@@ -457,6 +457,29 @@ k_local_mean (const double *__restrict__ q, long long n, awm_search_score *__res
   scores[i].local_mean = avg;
 }
 
+// local maxima of |raw - local_mean| above a floor, appended in arbitrary order (the host sorts the short list);
+// q >= q_last && q >= q_next with 0 beyond the ends (src/syncfinder.cc:258-281; its "skip the next score" rule only
+// matters for exactly equal neighbours and is applied by the host).
+__global__ void
+k_peaks (const awm_search_score *__restrict__ scores, long long n, double floor_q, awm_search_score *__restrict__ out,
+         unsigned long long max_out, unsigned long long *__restrict__ counter)
+{
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const double q = fabs (scores[i].raw_quality - scores[i].local_mean);
+  if (!(q > floor_q))
+    return;
+  const double q_last = i > 0 ? fabs (scores[i - 1].raw_quality - scores[i - 1].local_mean) : 0;
+  const double q_next = i + 1 < n ? fabs (scores[i + 1].raw_quality - scores[i + 1].local_mean) : 0;
+  if (q >= q_last && q >= q_next)
+    {
+      const unsigned long long pos = atomicAdd (counter, 1ull);
+      if (pos < max_out)
+        out[pos] = scores[i];
+    }
+}
+
 // =============================================================================================
 // SyncFinder::search_refine (src/syncfinder.cc:393-458): for candidate c and fine offset o
 // (sample cand_start[c] + 8*o) sync_fft of the wanted sync frames + sync_decode (start frame 0).
@@ -466,7 +489,7 @@ k_local_mean (const double *__restrict__ q, long long n, awm_search_score *__res
 // out_ud[((c*65 + o)*n_bits + bit)*2 + {0,1}] = umag, dmag; out_cnt = frames used; out_valid[c*65 + o].
 // =============================================================================================
 constexpr int kOffsets = 65;
-constexpr int kRefineWarps = 8;
+constexpr int kRefineWarps = 10;      // 2 CTAs/SM = 20 warps: shared memory (transpose buffers) and 102 registers/thread both fit
 
 __global__ void __launch_bounds__ (kRefineWarps * 32, 2)
 k_refine (const float *__restrict__ pcm, long long n_frames, int C,
@@ -528,7 +551,7 @@ k_refine (const float *__restrict__ pcm, long long n_frames, int C,
 // block decode, stage 1: FFTAnalyzer::fft_range (src/wmcommon.cc:123-141) reduced to what
 // mix_decode reads: per (block, frame, channel) the dB of bins 20..100 -> D[blk][frame*C+ch][81].
 // =============================================================================================
-constexpr int kDecodeWarps = 8;
+constexpr int kDecodeWarps = 10;
 
 __global__ void __launch_bounds__ (kDecodeWarps * 32, 2)
 k_decode_fft (const float *__restrict__ pcm, long long n_frames, int C, const long long *__restrict__ blk_start,

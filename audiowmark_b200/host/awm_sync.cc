@@ -86,6 +86,78 @@ select_candidates (const SearchScore *sc, size_t n, double threshold, vector<Sea
     }
 }
 
+/* Same selection as select_candidates, but the local maxima come from the GPU (awm_sync_peaks) and only those above a
+ * floor are transferred.  Exactness: a peak can only be masked by a 3x stronger one, which is above the floor as
+ * well; peaks within 23 search steps of each other are always within 23 list positions; and if at least n_best
+ * unmasked peaks lie above the floor, every peak the reference would select does too.  The floor is lowered until
+ * that holds (or it reaches zero, i.e. all peaks). */
+bool
+select_candidates_gpu (awm_ctx *ctx, double threshold, vector<SearchScore>& out)
+{
+  constexpr int    mask_distance = local_mean_distance + 3;
+  constexpr double mask_factor   = 3;
+  static SearchScore *peaks = nullptr;
+  static const size_t max_peaks = 1 << 17;
+  if (!peaks)
+    peaks = static_cast<SearchScore *> (awm_host_alloc (max_peaks * sizeof (SearchScore)));
+  if (!peaks)
+    return false;
+  const double floors[] = { threshold, threshold * 0.6, threshold * 0.35, threshold * 0.15, 0.0, -1.0 };
+  for (double floor_q : floors)
+    {
+      size_t n = 0;
+      if (awm_sync_peaks (ctx, floor_q, peaks, max_peaks, &n))
+        return false;
+      if (n > max_peaks)
+        return false;                             // caller falls back to the full score list
+      /* "skip the score after a maximum": of directly adjacent scores that are both maxima (equal quality) the one
+       * right after a selected maximum is not looked at */
+      vector<SearchScore> pk;
+      pk.reserve (n);
+      bool prev_taken = false;
+      uint64_t prev_index = ~uint64_t (0);
+      for (size_t i = 0; i < n; i++)
+        {
+          const bool adjacent = peaks[i].index == prev_index + Params::sync_search_step;
+          const bool take = !(adjacent && prev_taken);
+          if (take)
+            pk.push_back (peaks[i]);
+          prev_taken = take;
+          prev_index = peaks[i].index;
+        }
+      const size_t np = pk.size();
+      vector<uint32_t> order (np);
+      for (size_t k = 0; k < np; k++)
+        order[k] = k;
+      std::sort (order.begin(), order.end(), [&] (uint32_t a, uint32_t b) { return abs_quality (pk[a]) > abs_quality (pk[b]); });
+      auto sign = [&] (size_t k) { return (pk[k].raw_quality - pk[k].local_mean < 0) ? -1 : 1; };
+      out.clear();
+      bool complete = false;
+      for (size_t k = 0; k < np && !complete; k++)
+        {
+          const int i = order[k];
+          const double q = abs_quality (pk[i]);
+          if (q <= threshold && int (out.size()) >= Params::get_n_best)
+            {
+              complete = true;                    // everything above the threshold is in, and at least n_best matches
+              break;
+            }
+          bool mask = false;
+          for (int j = i - 1; j >= 0 && !mask && int (pk[i].index - pk[j].index) / Params::sync_search_step <= mask_distance; j--)
+            mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
+          for (int j = i + 1; j < int (np) && !mask && int (pk[j].index - pk[i].index) / Params::sync_search_step <= mask_distance; j++)
+            mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
+          if (!mask)
+            out.push_back (pk[i]);
+        }
+      /* final if the scan stopped by itself, if n_best unmasked peaks lie above this floor (nothing below it can
+       * displace them), or if this floor already delivered every peak there is */
+      if (complete || int (out.size()) >= Params::get_n_best || floor_q < 0)
+        return true;
+    }
+  return true;
+}
+
 void
 select_threshold_and_n_best (vector<SearchScore>& scores, double threshold)
 {
@@ -153,6 +225,7 @@ SyncFinder::search (const vector<Key>& key_list, size_t n_frames, int n_channels
       static size_t all_cap = 0;
       bool ok = slot >= 0;
       size_t n_all = 0;
+      bool gpu_selected = false;
       const bool trace = getenv ("AWM_TRACE") != nullptr;
       const double t0 = get_time();
       double t1 = t0, t2 = t0, t3 = t0;
@@ -160,6 +233,10 @@ SyncFinder::search (const vector<Key>& key_list, size_t n_frames, int n_channels
         {
           size_t n_scores = 0;
           ok = awm_sync_approx (ctx, slot, amode, wav_first, wav_last, Params::water_delta, nullptr, 0, &n_scores) == 0;
+          /* the scores stay on the device; normally only the peaks that matter come back */
+          gpu_selected = ok && n_scores && !getenv ("AWM_HOST_SELECT") && select_candidates_gpu (ctx, Params::sync_threshold2 * 0.75, scores);
+          if (gpu_selected)
+            n_scores = 0;                         // nothing else to fetch
           if (ok && n_scores > all_cap)
             {
               awm_host_free (all);
@@ -178,7 +255,8 @@ SyncFinder::search (const vector<Key>& key_list, size_t n_frames, int n_channels
       t1 = get_time();
       if (ok)
         {
-          select_candidates (all, n_all, Params::sync_threshold2 * 0.75, scores);
+          if (!gpu_selected)
+            select_candidates (all, n_all, Params::sync_threshold2 * 0.75, scores);
           if (mode == Mode::CLIP)               // ClipDecoder: at most n_best matches, but at least 5
             select_truncate_n (scores, std::max (Params::get_n_best, 5));
           t2 = get_time();

@@ -127,10 +127,18 @@ int awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int c
  * *n_scores entries sorted by index.  wav_first/wav_last: non-silent value range
  * [first,last) as scan_silence computes it (:155-169) in interleaved-value units of the padded
  * signal; pass 0 / n_values for BLOCK mode.
- * Passing scores_out = NULL only returns the count.
+ * Passing scores_out = NULL runs the search, keeps the scores on the device (for awm_sync_peaks) and returns the count.
  */
 int awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
                      double water_delta, awm_search_score *scores_out, size_t max_scores, size_t *n_scores);
+
+/* awm_sync_peaks = sync_select_local_maxima (src/syncfinder.cc:258-281) on the score list of the last
+ * awm_sync_approx call (kept on the device), restricted to peaks with |raw_quality - local_mean| > min_abs_quality:
+ * only those can pass the threshold / n-best selection that follows, so the host never has to look at the
+ * several hundred thousand scores of a 30 minute chunk.  out: sorted by index; *n = number found (may exceed max,
+ * then only max entries were written and the caller should raise min_abs_quality or use awm_sync_approx's full list).
+ */
+int awm_sync_peaks (awm_ctx *ctx, double min_abs_quality, awm_search_score *out, size_t max, size_t *n);
 
 /* awm_sync_refine = SyncFinder::search_refine (src/syncfinder.cc:393-458): for each candidate the
  * fine offsets max(index-256,0) .. index+256 step 8 are scored with fresh FFTs of the wanted
