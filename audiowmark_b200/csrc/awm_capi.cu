@@ -590,7 +590,7 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
   long long n_blocks = 0;
   if (limiter_block > 0)
     {
-      n_blocks = (n_proc * kFrame + limiter_block - 1) / limiter_block + 1;
+      n_blocks = (n_proc * kFrame + limiter_block - 1) / limiter_block + 2;   // + partial first block of a mid-stream shard
       CK (ctx->peaks.reserve (n_blocks * sizeof (unsigned)));
       CK (cudaMemsetAsync (ctx->peaks.p, 0, n_blocks * sizeof (unsigned), ctx->stream));
     }
@@ -606,11 +606,13 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
   A.C = channels;
   A.n_proc = n_proc;
   A.fpb = ctx->embed_fpb;
-  A.frame_number0 = (long long) (first_frame_number % (2ull * A.fpb)) + 2LL * A.fpb - frames_pad_start;
+  A.frame_number0 = (long long) (first_frame_number % (2ull * A.fpb)) + 2LL * A.fpb - frames_pad_start;   // WatermarkGen starts at 2*fpb - pad (src/wmadd.cc:295)
   A.frame_mod = ctx->frame_mod.as<uint8_t>();
   A.pow_up = 0.5f * float (-water_delta * 1);       // powf (mag, -Params::water_delta * data_bit_sign), src/wmadd.cc:79
   A.pow_down = 0.5f * float (-water_delta * -1);
   A.limiter_block = limiter_block;
+  A.stream_pos0 = (long long) first_frame_number * kFrame;
+  A.blk0 = limiter_block > 0 ? A.stream_pos0 / limiter_block : 0;
   A.peaks = ctx->peaks.as<unsigned>();
   A.snr = snr_power ? ctx->snr.as<double>() : nullptr;
   A.snr_frames = limiter_block > 0 ? n_proc : n_real;   // frames the reference loop emits (src/wmadd.cc:539-546)
@@ -628,7 +630,7 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
       const unsigned g2 = unsigned ((n_frames + 255) / 256);
       PROF (ctx);
       k_limiter<<<g2, 256, 0, ctx->stream>>> (d_out, (long long) n_frames, channels, limiter_block, limiter_ceiling,
-                                              ctx->peaks.as<unsigned>(), n_blocks);
+                                              ctx->peaks.as<unsigned>(), n_blocks, (long long) first_frame_number * kFrame, first_frame_number == 0);
       LAUNCH_CHECK ("k_limiter");
     }
   if (!out_dev)

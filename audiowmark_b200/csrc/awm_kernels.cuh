@@ -796,6 +796,8 @@ struct EmbedArgs
   const uint8_t *frame_mod;    // [2][fpb][101]
   float pow_up, pow_down;      // HALF the exponents -delta*(+1), -delta*(-1): applied to log2 of the squared magnitude
   int limiter_block;           // 0 = no peak tracking
+  long long stream_pos0;       // stream position of sample 0 of this buffer (first_frame_number * 1024): limiter blocks are stream-global
+  long long blk0;              // stream_pos0 / limiter_block: peaks[] is indexed relative to it
   unsigned *peaks;             // [n_blocks] float bits, atomicMax
   double *snr;                 // [2] or null
   long long snr_frames;        // frames that count for --snr (the reference loop stops earlier without limiter)
@@ -825,8 +827,10 @@ k_embed (EmbedArgs A)
   long long blk_lo = 0, boundary = 0;
   if (A.limiter_block > 0 && emits)
     {
-      blk_lo = (m * kFrame) / A.limiter_block;
-      boundary = (blk_lo + 1) * A.limiter_block - m * kFrame;          // x >= boundary belongs to the next block
+      const long long gpos = A.stream_pos0 + m * kFrame;
+      blk_lo = gpos / A.limiter_block;
+      boundary = (blk_lo + 1) * A.limiter_block - gpos;                // x >= boundary belongs to the next block
+      blk_lo -= A.blk0;
     }
 
   for (int chA = 0; chA < C; chA += 2)
@@ -1000,16 +1004,19 @@ k_embed (EmbedArgs A)
 // ceiling / max (bm[b-1], bm[b]) and ceiling / max (bm[b], bm[b+1]); bm[b] = max (ceiling, peak[b]).
 __global__ void
 k_limiter (float *__restrict__ x, long long n_frames, int C, int block, float ceiling,
-           const unsigned *__restrict__ peaks, long long n_blocks)
+           const unsigned *__restrict__ peaks, long long n_blocks, long long stream_pos0, int first_is_stream_start)
 {
   const long long pos = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= n_frames)
     return;
-  const long long b = pos / block;
-  const int i = int (pos - b * block);
+  const long long gpos = stream_pos0 + pos;
+  const long long b = gpos / block - stream_pos0 / block;           // index into peaks[]
+  const int i = int (gpos % block);
   const float cur = fmaxf (ceiling, __uint_as_float (peaks[b]));
+  // block -1 of the stream counts as "ceiling"; for a shard that starts mid-stream the caller's halo makes peaks[b-1] valid
   const float last = b > 0 ? fmaxf (ceiling, __uint_as_float (peaks[b - 1])) : ceiling;
   const float next = b + 1 < n_blocks ? fmaxf (ceiling, __uint_as_float (peaks[b + 1])) : ceiling;
+  (void) first_is_stream_start;
   const float scale_start = __fdiv_rn (ceiling, fmaxf (last, cur));
   const float scale_end = __fdiv_rn (ceiling, fmaxf (cur, next));
   if (scale_start == 1.0f && scale_end == 1.0f)

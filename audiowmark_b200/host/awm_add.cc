@@ -37,7 +37,7 @@ info_format (const string& label, const RawFormat& format)
 
 int
 add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,
-                      const string& bits, AddStats *stats)
+                      const string& bits, AddStats *stats, uint64_t first_frame_number)
 {
   const vector<int> bitvec = parse_payload (bits);
   if (bitvec.empty())
@@ -53,7 +53,7 @@ add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_fram
     return 1;
   const int limiter_block = Params::test_no_limiter ? 0 : int (sample_rate * int (Params::limiter_block_size_ms) / 1000);
   double snr_power[2] = { 0, 0 };
-  if (awm_embed (ctx, in, out, n_frames, n_channels, 0, Params::frames_pad_start, Params::water_delta,
+  if (awm_embed (ctx, in, out, n_frames, n_channels, first_frame_number, Params::frames_pad_start, Params::water_delta,
                  limiter_block, Params::limiter_ceiling, (Params::snr || stats) ? snr_power : nullptr))
     {
       error ("audiowmark: embedding failed: %s\n", awm_last_error (ctx));

@@ -611,8 +611,8 @@ decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vect
 
 /* chunk geometry of WavChunkLoader (src/wavchunkloader.cc:54-163): chunks of get_chunk_size minutes that
  * overlap by two blocks * 1.3 */
-static void
-chunk_sizes (int sample_rate, size_t& max_frames, size_t& overlap_frames)
+void
+chunk_geometry (int sample_rate, size_t& max_frames, size_t& overlap_frames)
 {
   max_frames = lrint (Params::get_chunk_size * 60 * sample_rate);
   const double block_seconds = (mark_sync_frame_count() + mark_data_frame_count()) * Params::frame_size / double (Params::mark_sample_rate);
@@ -628,7 +628,7 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
       return 1;
     }
   size_t max_frames, overlap;
-  chunk_sizes (sample_rate, max_frames, overlap);
+  chunk_geometry (sample_rate, max_frames, overlap);
   size_t start = 0, end = min (max_frames, n_frames);
   double time_offset = 0;
   bool first_chunk = true, eof = end < max_frames;
@@ -669,6 +669,27 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
       result_set.merge (chunk_results[c]);
     }
   result_set.sort (key_list);
+  return 0;
+}
+
+int
+get_watermark_chunk (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
+                     bool first_chunk, ResultSet& chunk_result)
+{
+  if (sample_rate != Params::mark_sample_rate)
+    {
+      error ("audiowmark: input sample rate %d: only %d Hz is supported\n", sample_rate, Params::mark_sample_rate);
+      return 1;
+    }
+  vector<VitJob> pending;
+  string debug_sync;
+  if (decode_chunk (pending, 0, debug_sync, key_list, samples, n_frames, n_channels, sample_rate, first_chunk))
+    return 1;
+  vector<ResultSet> one (1);
+  if (!run_viterbi_jobs (pending, one))
+    return 1;
+  one[0].set_debug_sync (debug_sync);
+  chunk_result.merge (one[0]);
   return 0;
 }
 

@@ -116,10 +116,11 @@ awmh_conv_encode (int block_type, const uint8_t *bits, int n, uint8_t *out, int 
 /* add_stream_watermark on buffers (host or device pointers) */
 int
 awmh_add (const unsigned char *key16, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,
-          const char *payload_hex, int *data_blocks, double *snr_db)
+          const char *payload_hex, int *data_blocks, double *snr_db, uint64_t first_frame_number)
 {
   AddStats stats;
-  const int rc = add_watermark_buffer (make_key (key16, ""), in, out, n_frames, n_channels, sample_rate, payload_hex, (data_blocks || snr_db) ? &stats : nullptr);
+  const int rc = add_watermark_buffer (make_key (key16, ""), in, out, n_frames, n_channels, sample_rate, payload_hex,
+                                       (data_blocks || snr_db) ? &stats : nullptr, first_frame_number);
   if (data_blocks)
     *data_blocks = stats.data_blocks;
   if (snr_db)
@@ -158,6 +159,123 @@ awmh_get (const unsigned char *keys16, const char *const *names, int n_keys, con
       free (buf);
     }
   return 0;
+}
+
+/* ---- sharded `get`: chunk results as flat records ------------------------------------------------
+ * record (little endian, packed): i32 key_index, f64 time, f64 quality, u64 sync_index, f32 decode_error,
+ * u8 block_type, u8 type, f64 speed, u16 n_bits, n_bits bytes (0/1)
+ */
+static void
+put (std::vector<unsigned char>& b, const void *p, size_t n)
+{
+  const unsigned char *c = static_cast<const unsigned char *> (p);
+  b.insert (b.end(), c, c + n);
+}
+
+static std::vector<unsigned char>
+serialize (const ResultSet& rs, const std::vector<Key>& key_list)
+{
+  std::vector<unsigned char> b;
+  for (const auto& p : rs.all())
+    {
+      int32_t ki = 0;
+      for (size_t k = 0; k < key_list.size(); k++)
+        if (key_list[k] == p.key)
+          ki = k;
+      const double time = p.time, quality = p.sync_score.quality, speed = p.speed;
+      const uint64_t idx = p.sync_score.index;
+      const float err = p.decode_error;
+      const uint8_t bt = uint8_t (p.sync_score.block_type), ty = uint8_t (p.type);
+      const uint16_t nb = p.bit_vec.size();
+      put (b, &ki, 4); put (b, &time, 8); put (b, &quality, 8); put (b, &idx, 8); put (b, &err, 4);
+      put (b, &bt, 1); put (b, &ty, 1); put (b, &speed, 8); put (b, &nb, 2);
+      for (int bit : p.bit_vec)
+        b.push_back (bit ? 1 : 0);
+    }
+  return b;
+}
+
+static bool
+deserialize (const unsigned char *b, size_t len, const std::vector<Key>& key_list, ResultSet& rs)
+{
+  size_t pos = 0;
+  auto get = [&] (void *p, size_t n) { if (pos + n > len) return false; memcpy (p, b + pos, n); pos += n; return true; };
+  while (pos < len)
+    {
+      int32_t ki; double time, quality, speed; uint64_t idx; float err; uint8_t bt, ty; uint16_t nb;
+      if (!get (&ki, 4) || !get (&time, 8) || !get (&quality, 8) || !get (&idx, 8) || !get (&err, 4) || !get (&bt, 1) || !get (&ty, 1)
+          || !get (&speed, 8) || !get (&nb, 2) || pos + nb > len || ki < 0 || size_t (ki) >= key_list.size() || bt > 2 || ty > 2)
+        return false;
+      std::vector<int> bits (b + pos, b + pos + nb);
+      pos += nb;
+      rs.add_pattern (key_list[ki], time, SyncFinder::Score { size_t (idx), quality, ConvBlockType (bt) }, bits, err, ResultSet::Type (ty), speed);
+    }
+  return true;
+}
+
+static std::vector<Key>
+make_key_list (const unsigned char *keys16, const char *const *names, int n_keys)
+{
+  std::vector<Key> key_list;
+  for (int k = 0; k < n_keys; k++)
+    key_list.push_back (make_key (keys16 + 16 * k, names ? names[k] : ""));
+  return key_list;
+}
+
+/* decode ONE chunk of the reference's chunk geometry (pcm = the chunk's samples); records -> blob_out */
+int
+awmh_get_chunk (const unsigned char *keys16, const char *const *names, int n_keys, const float *pcm, size_t n_frames, int n_channels,
+                int sample_rate, int first_chunk, unsigned char *blob_out, size_t blob_cap, size_t *blob_len)
+{
+  const std::vector<Key> key_list = make_key_list (keys16, names, n_keys);
+  ResultSet rs;
+  const int rc = get_watermark_chunk (key_list, pcm, n_frames, n_channels, sample_rate, first_chunk != 0, rs);
+  if (rc)
+    return rc;
+  const std::vector<unsigned char> b = serialize (rs, key_list);
+  *blob_len = b.size();
+  if (b.size() > blob_cap)
+    return -2;
+  if (!b.empty())
+    memcpy (blob_out, b.data(), b.size());
+  return 0;
+}
+
+/* ResultSet::merge in chunk order + sort + --json document (src/wmget.cc:289-316,252-287,340-382) from chunk blobs */
+int
+awmh_merge_chunks (const unsigned char *keys16, const char *const *names, int n_keys, const unsigned char *const *blobs, const size_t *blob_lens,
+                   const double *time_offsets, int n_chunks, double total_seconds, char *json_out, size_t json_cap)
+{
+  const std::vector<Key> key_list = make_key_list (keys16, names, n_keys);
+  ResultSet result_set;
+  for (int c = 0; c < n_chunks; c++)
+    {
+      ResultSet chunk;
+      if (!deserialize (blobs[c], blob_lens[c], key_list, chunk))
+        return -3;
+      chunk.apply_time_offset (time_offsets[c]);
+      result_set.merge (chunk);
+    }
+  result_set.sort (key_list);
+  char *buf = nullptr;
+  size_t len = 0;
+  FILE *f = open_memstream (&buf, &len);
+  result_set.print_json (f, size_t (lrint (total_seconds)));
+  fclose (f);
+  const bool fits = len + 1 <= json_cap;
+  if (fits)
+    memcpy (json_out, buf, len + 1);
+  free (buf);
+  return fits ? 0 : -2;
+}
+
+void
+awmh_chunk_geometry (int sample_rate, uint64_t *max_frames, uint64_t *overlap_frames)
+{
+  size_t m, o;
+  chunk_geometry (sample_rate, m, o);
+  *max_frames = m;
+  *overlap_frames = o;
 }
 
 uint64_t

@@ -15,11 +15,17 @@ int get_watermark (const std::vector<Key>& key_list, const std::string& infile, 
 /* buffer-level drivers used by the C host API (bench / tests): same computation without file I/O */
 struct AddStats { int data_blocks = 0; double snr_db = 0; };
 int add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,
-                          const std::string& bits, AddStats *stats);
+                          const std::string& bits, AddStats *stats, uint64_t first_frame_number = 0);
 
 class ResultSet;
 int get_watermark_buffer (const std::vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
                           ResultSet& result_set);
+
+/* chunk-level pieces of get_watermark_buffer for sharded runs (one process per GPU): a rank decodes some of the
+ * reference's chunks (WavChunkLoader geometry) and the chunk result sets are merged in chunk order afterwards */
+int get_watermark_chunk (const std::vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
+                         bool first_chunk, ResultSet& chunk_result);
+void chunk_geometry (int sample_rate, size_t& max_frames, size_t& overlap_frames);
 
 int frame_count (const WavData& wav_data);
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown"]
 
 _lib = None
 
@@ -107,7 +107,7 @@ def conv_encode(block_type: int, bits) -> np.ndarray:
     return out[:n].copy()
 
 
-def add(pcm_in, payload_hex: str, key=None, pcm_out=None, n_frames=None, channels=None, sample_rate=44100, want_stats=False):
+def add(pcm_in, payload_hex: str, key=None, pcm_out=None, n_frames=None, channels=None, sample_rate=44100, want_stats=False, first_frame_number=0):
     """add_stream_watermark on a buffer: numpy arrays (host) or device pointers (ints)."""
     if isinstance(pcm_in, np.ndarray):
         pcm_in = np.ascontiguousarray(pcm_in, np.float32)
@@ -116,7 +116,8 @@ def add(pcm_in, payload_hex: str, key=None, pcm_out=None, n_frames=None, channel
             pcm_out = np.empty_like(pcm_in)
     blocks, snr = ctypes.c_int(), ctypes.c_double()
     rc = load().awmh_add(_key(key), _ptr(pcm_in), _ptr(pcm_out), ctypes.c_size_t(n_frames), ctypes.c_int(channels), ctypes.c_int(sample_rate),
-                         payload_hex.encode(), ctypes.byref(blocks) if want_stats else None, ctypes.byref(snr) if want_stats else None)
+                         payload_hex.encode(), ctypes.byref(blocks) if want_stats else None, ctypes.byref(snr) if want_stats else None,
+                         ctypes.c_uint64(first_frame_number))
     if rc:
         raise RuntimeError("awmh_add failed (rc=%d); see stderr" % rc)
     return (pcm_out, blocks.value, snr.value) if want_stats else pcm_out
@@ -140,6 +141,52 @@ def get(pcm, keys=None, names=None, n_frames=None, channels=None, sample_rate=44
         raise RuntimeError("awmh_get failed (rc=%d); see stderr" % rc)
     text = buf.value.decode()
     return json.loads(text) if parse else text
+
+
+def chunk_geometry(sample_rate=44100):
+    """(max_frames, overlap_frames) of the reference's WavChunkLoader for the current --chunk-size."""
+    m, o = ctypes.c_uint64(), ctypes.c_uint64()
+    load().awmh_chunk_geometry(ctypes.c_int(sample_rate), ctypes.byref(m), ctypes.byref(o))
+    return m.value, o.value
+
+
+def get_chunk(pcm, first_chunk: bool, keys=None, names=None, n_frames=None, channels=None, sample_rate=44100) -> bytes:
+    """decode one chunk; returns the chunk's pattern records (bytes) for merge_chunks."""
+    keys = keys or [bytes(16)]
+    names = names or [""] * len(keys)
+    if isinstance(pcm, np.ndarray):
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        n_frames, channels = pcm.shape
+    kb = b"".join(_key(k) for k in keys)
+    name_arr = (ctypes.c_char_p * len(keys))(*[n.encode() for n in names])
+    cap = 1 << 20
+    buf = (ctypes.c_ubyte * cap)()
+    blen = ctypes.c_size_t()
+    rc = load().awmh_get_chunk(kb, name_arr, ctypes.c_int(len(keys)), _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
+                               ctypes.c_int(sample_rate), ctypes.c_int(1 if first_chunk else 0), buf, ctypes.c_size_t(cap), ctypes.byref(blen))
+    if rc:
+        raise RuntimeError("awmh_get_chunk failed (rc=%d); see stderr" % rc)
+    return bytes(buf[:blen.value])
+
+
+def merge_chunks(blobs, time_offsets, total_seconds: float, keys=None, names=None) -> dict:
+    """ResultSet::merge in chunk order + sort -> the --json document."""
+    keys = keys or [bytes(16)]
+    names = names or [""] * len(keys)
+    kb = b"".join(_key(k) for k in keys)
+    name_arr = (ctypes.c_char_p * len(keys))(*[n.encode() for n in names])
+    n = len(blobs)
+    bufs = [(ctypes.c_ubyte * max(len(b), 1)).from_buffer_copy(b if b else b"\0") for b in blobs]
+    ptrs = (ctypes.POINTER(ctypes.c_ubyte) * n)(*[ctypes.cast(b, ctypes.POINTER(ctypes.c_ubyte)) for b in bufs])
+    lens = (ctypes.c_size_t * n)(*[len(b) for b in blobs])
+    offs = (ctypes.c_double * n)(*time_offsets)
+    cap = 1 << 22
+    out = ctypes.create_string_buffer(cap)
+    rc = load().awmh_merge_chunks(kb, name_arr, ctypes.c_int(len(keys)), ptrs, lens, offs, ctypes.c_int(n), ctypes.c_double(total_seconds),
+                                  out, ctypes.c_size_t(cap))
+    if rc:
+        raise RuntimeError("awmh_merge_chunks failed (rc=%d)" % rc)
+    return json.loads(out.value.decode())
 
 
 def gpu_launches() -> int:

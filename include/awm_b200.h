@@ -111,7 +111,9 @@ int awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels,
  * (src/wmadd.cc:215-250) + mix + Limiter::process (src/limiter.cc:45-124), for a whole buffer
  * at 44.1 kHz.  in/out: [n_frames][channels]; first_frame_number = index of the first 1024-frame
  * of this buffer in the stream (0 unless the caller shards; WatermarkGen starts its table row
- * at 2*frames_per_block - frames_pad_start, src/wmadd.cc:295).  limiter_block = sample_rate *
+ * at 2*frames_per_block - frames_pad_start, src/wmadd.cc:295; limiter blocks are counted from the stream start
+ * as well, so a shard that brings a halo of one frame + two limiter blocks on each side reproduces the
+ * unsharded result exactly in its interior).  limiter_block = sample_rate *
  * 1000 / 1000 frames (src/limiter.cc:33-37); limiter_block = 0 disables the limiter
  * (--test-no-limiter).  snr_power (optional, 2 doubles) receives sum(delta^2), sum(orig^2)
  * as --snr accumulates them (src/wmadd.cc:553-563).

@@ -1,0 +1,40 @@
+"""GPU: sharded runs reproduce the single-process result exactly (simulated ranks on one GPU; the collective itself is
+covered on CPU with gloo in test_sharding_cpu.py)."""
+import numpy as np
+import pytest
+
+import awm_testlib as T
+from audiowmark_b200 import hostapi as H, sharding as S
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sharded_embed_is_bit_identical():
+    x = T.noise(130.0, 2, seed=21, amp=1.0)                 # full-scale noise: the limiter works on every block
+    H.set_params()
+    full = H.add(x, T.PAYLOAD)
+    n = x.shape[0]
+    for cuts in ([0, n // 2, n], [0, 1234567, 2999999, n], [0, 44100 * 50, 44100 * 51, n]):
+        for lo, hi in zip(cuts, cuts[1:]):
+            e0, e1, ffn = S.embed_range(lo, hi, n, 44100)
+            part = H.add(x[e0:e1], T.PAYLOAD, first_frame_number=ffn)
+            assert np.array_equal(part[lo - e0:hi - e0], full[lo:hi]), (lo, hi, e0, e1)
+
+
+def test_chunk_sharded_get_equals_single_process():
+    x = T.noise(700.0, 2, seed=22)
+    H.set_params(chunk_size_min=4.0)
+    y = H.add(x, T.PAYLOAD)
+    doc = H.get(y)
+    mx, ov = H.chunk_geometry(44100)
+    plan = S.chunk_plan(y.shape[0], mx, ov)
+    assert len(plan) >= 3
+    for world in (1, 2, 3):
+        per_rank = []
+        for r in range(world):
+            lo, hi = S.assign_chunks(len(plan), world)[r]
+            per_rank.append([(c, H.get_chunk(y[plan[c][0]:plan[c][0] + plan[c][1]], first_chunk=(c == 0))) for c in range(lo, hi)])
+        blobs = dict(b for rk in per_rank for b in S.unpack_blobs(S.pack_blobs(rk)))
+        got = H.merge_chunks([blobs[c] for c in range(len(plan))], [p[2] for p in plan], y.shape[0] / 44100.0)
+        assert got == doc
+    H.set_params()

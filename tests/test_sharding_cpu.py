@@ -1,0 +1,125 @@
+"""CPU: the multi-GPU host logic -- chunk plan, shard ranges, result gather over gloo (world size 2) and the C++ merge of
+chunk records against the oracle's ResultSet."""
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import awm_oracle as O
+from audiowmark_b200 import hostapi as H, sharding as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = O.Params()
+
+
+def test_chunk_plan_matches_reference_geometry():
+    H.set_params()
+    mx, ov = H.chunk_geometry(44100)
+    assert (mx, ov) == (79380000, 5926502)                      # 30 min; lrint(2 * 51.6876 s * 1.3 * 44100)
+    for n in (0, 1000, mx - 1, mx, mx + 1, 158760000, 8 * 158760000):
+        want = O.chunk_ranges(n, P)
+        got = S.chunk_plan(n, mx, ov)
+        assert [(a, b) for a, b, _ in got] == [(a, b) for a, b, _ in want]
+        assert np.allclose([t for _, _, t in got], [t for _, _, t in want], rtol=0, atol=1e-9)
+    assert len(S.chunk_plan(158760000, mx, ov)) == 3           # 1 h: 1800 s, 1800 s, 268.8 s
+    assert len(S.chunk_plan(8 * 158760000, mx, ov)) == 18       # 8 h
+
+
+def test_assignment_and_embed_ranges_cover_the_stream():
+    H.set_params()
+    mx, ov = H.chunk_geometry(44100)
+    n = 4 * 158760000
+    for world in (1, 2, 3, 4, 8):
+        plan = S.chunk_plan(n, mx, ov)
+        parts = S.assign_chunks(len(plan), world)
+        assert parts[0][0] == 0 and parts[-1][1] == len(plan) and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1
+        for r in range(world):
+            _, (lo_c, hi_c), rng = S.rank_ranges(n, r, world, mx, ov)
+            if rng is None:
+                continue
+            lo, hi = rng
+            e0, e1, ffn = S.embed_range(lo, hi, n, 44100)
+            assert e0 % 1024 == 0 and ffn * 1024 == e0 and e0 <= lo and e1 >= hi and 0 <= e0 and e1 <= n
+            if lo > 0:       # one complete limiter block + one frame before the first owned block
+                assert e0 + 1024 <= (lo // 44100 - 1) * 44100
+            if hi < n:
+                assert e1 - 1024 >= ((hi - 1) // 44100 + 2) * 44100
+
+
+def _records(patterns, key_index=0):
+    out = b""
+    for (time, quality, idx, err, bt, ty, speed, bits) in patterns:
+        out += struct.pack("<iddQfBBdH", key_index, time, quality, idx, err, bt, ty, speed, len(bits)) + bytes(bits)
+    return out
+
+
+def test_merge_chunks_matches_oracle_resultset():
+    """C++ merge/sort/print of chunk records == the oracle's ResultSet (src/wmget.cc:252-316)."""
+    rng = np.random.default_rng(0)
+    key = O.Key()
+    payload = O.parse_payload("0123456789abcdef0011223344556677", P)
+    other = [int(b) for b in rng.integers(0, 2, 128)]
+    chunks, offs = [], [0.0, 1665.6122, 3331.2244]
+    want = O.ResultSet()
+    for c, toff in enumerate(offs):
+        pats, crs = [], O.ResultSet()
+        for k in range(6):
+            t = 5.8 + 51.688 * k
+            bits = payload if k % 3 else other
+            bt = k & 1
+            q = float(rng.uniform(0.3, 1.4))
+            err = float(np.float32(rng.uniform(0.05, 0.4)))
+            pats.append((t, q, int(t * 44100), err, bt, 0, 1.0, bits))
+            crs.add_pattern(key, t, O.Score(int(t * 44100), q, bt), bits, err, O.TYPE_BLOCK)
+        pats.append((0.0, 1.1, 0, 0.1, 0, 2, 1.0, payload))                       # "all"
+        crs.add_pattern(key, 0.0, O.Score(0, 1.1, O.A), payload, np.float32(0.1), O.TYPE_ALL)
+        # a duplicate of the previous chunk's overlap region: same block seen again with the shifted time
+        if c > 0:
+            t_dup = (5.8 + 51.688 * 5) + offs[c - 1] - toff
+            pats.append((t_dup, 0.9, 1, 0.2, 1, 0, 1.0, payload))
+            crs.add_pattern(key, t_dup, O.Score(1, 0.9, O.B), payload, np.float32(0.2), O.TYPE_BLOCK)
+        chunks.append(_records(pats))
+        crs.apply_time_offset(toff)
+        want.merge(crs)
+    want.sort([key])
+    doc = H.merge_chunks(chunks, offs, 3600.0)
+    wdoc = want.json_doc(3600)
+    assert doc["length"] == wdoc["length"] and len(doc["matches"]) == len(wdoc["matches"])
+    for g, w in zip(doc["matches"], wdoc["matches"]):
+        assert (g["pos"], g["bits"], g["type"]) == (w["pos"], w["bits"], w["type"])
+        assert "%.5f" % g["quality"] == w["quality"] and "%.6f" % g["error"] == w["error"] and "%.5f" % g["rating"] == w["rating"]
+
+
+WORKER = r"""
+import os, sys
+sys.path[:0] = [%(root)r]
+import torch, torch.distributed as dist
+from audiowmark_b200 import sharding as S
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank = dist.get_rank()
+plan = S.chunk_plan(2 * 158760000, 79380000, 5926502)
+lo, hi = S.assign_chunks(len(plan), dist.get_world_size())[rank]
+blobs = [(c, bytes([c]) * (100 * (c + 1) + rank)) for c in range(lo, hi)]
+allb = S.gather_blobs(blobs)
+flat = sorted((c, len(b), b[:1]) for per_rank in allb for c, b in per_rank)
+assert [c for c, _, _ in flat] == list(range(len(plan))), flat
+assert all(b == bytes([c]) for c, _, b in flat)
+if rank == 0:
+    print("GATHER_OK", len(flat))
+dist.destroy_process_group()
+"""
+
+
+def test_result_gather_over_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK 5" in outs[0][0]
