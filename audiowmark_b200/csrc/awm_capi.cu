@@ -70,6 +70,7 @@ struct awm_ctx
 {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of the pipelined host paths
   std::string err;
   uint64_t launches = 0;
   bool profiling = false;
@@ -83,6 +84,9 @@ struct awm_ctx
   // bound PCM
   const float *pcm = nullptr; size_t pcm_frames = 0; int pcm_ch = 0;
   DevBuf pcm_own;
+  struct Prefetch { DevBuf buf; const float *src = nullptr; size_t n_frames = 0; int ch = 0; cudaEvent_t done = nullptr; bool valid = false; };
+  Prefetch pref[2];
+  int pref_next = 0;
 
   DevBuf dbT, have, q, scores, a_ud, a_cnt, peaks_out, peaks_cnt;       // approx
   size_t n_scores_dev = 0;
@@ -254,6 +258,12 @@ awm_destroy (awm_ctx *ctx)
                      &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr };
   for (DevBuf *b : bufs)
     b->release();
+  for (auto& pf : ctx->pref)
+    {
+      pf.buf.release();
+      if (pf.done)
+        cudaEventDestroy (pf.done);
+    }
   for (KeyTab& k : ctx->keys)
     {
       for (SyncTab& s : k.sync)
@@ -266,6 +276,10 @@ awm_destroy (awm_ctx *ctx)
       k.mix.release();
       k.order.release();
     }
+  if (ctx->s_in)
+    cudaStreamDestroy (ctx->s_in);
+  if (ctx->s_out)
+    cudaStreamDestroy (ctx->s_out);
   cudaStreamDestroy (ctx->stream);
   delete ctx;
 }
@@ -531,7 +545,18 @@ awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, siz
     return fail (ctx, "awm_pcm_bind: bad arguments");
   CK (cudaSetDevice (ctx->device));
   const bool dev = pcm && is_device_ptr (pcm);
-  if (dev && pad_start == 0 && pad_end == 0)
+  awm_ctx::Prefetch *hit = nullptr;
+  if (!dev && pad_start == 0 && pad_end == 0)
+    for (auto& pf : ctx->pref)
+      if (pf.valid && pf.src == pcm && pf.n_frames == n_frames && pf.ch == channels)
+        hit = &pf;
+  if (hit)
+    {
+      CK (cudaStreamWaitEvent (ctx->stream, hit->done, 0));   // the prefetched copy becomes the bound PCM
+      ctx->pcm = hit->buf.as<float>();
+      hit->valid = false;
+    }
+  else if (dev && pad_start == 0 && pad_end == 0)
     {
       ctx->pcm = pcm;
     }
@@ -551,6 +576,41 @@ awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, siz
     }
   ctx->pcm_frames = pad_start + n_frames + pad_end;
   ctx->pcm_ch = channels;
+  return 0;
+}
+
+int
+awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels)
+{
+  if (!pcm || !n_frames || channels <= 0)
+    return fail (ctx, "awm_pcm_prefetch: bad arguments");
+  CK (cudaSetDevice (ctx->device));
+  if (is_device_ptr (pcm))
+    return 0;                                     // nothing to do: device memory is bound in place
+  if (!ctx->s_in)
+    {
+      CK (cudaStreamCreateWithFlags (&ctx->s_in, cudaStreamNonBlocking));
+      CK (cudaStreamCreateWithFlags (&ctx->s_out, cudaStreamNonBlocking));
+    }
+  awm_ctx::Prefetch& pf = ctx->pref[ctx->pref_next];
+  /* the slot's previous contents may still be the bound PCM of kernels in flight: order the copy behind them */
+  cudaEvent_t busy;
+  CK (cudaEventCreateWithFlags (&busy, cudaEventDisableTiming));
+  CK (cudaEventRecord (busy, ctx->stream));
+  CK (cudaStreamWaitEvent (ctx->s_in, busy, 0));
+  CK (cudaEventDestroy (busy));
+  if (ctx->pcm == pf.buf.p)
+    ctx->pcm_ch = 0;                              // the bound PCM is about to be overwritten: force a new bind
+  CK (pf.buf.reserve (n_frames * channels * sizeof (float)));
+  if (!pf.done)
+    CK (cudaEventCreateWithFlags (&pf.done, cudaEventDisableTiming));
+  CK (cudaMemcpyAsync (pf.buf.p, pcm, n_frames * channels * sizeof (float), cudaMemcpyHostToDevice, ctx->s_in));
+  CK (cudaEventRecord (pf.done, ctx->s_in));
+  pf.src = pcm;
+  pf.n_frames = n_frames;
+  pf.ch = channels;
+  pf.valid = true;
+  ctx->pref_next ^= 1;
   return 0;
 }
 
@@ -577,7 +637,6 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
   if (!in_dev)
     {
       CK (ctx->emb_in.reserve (n_val * sizeof (float)));
-      CK (cudaMemcpyAsync (ctx->emb_in.p, in, n_val * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
       d_in = ctx->emb_in.as<float>();
     }
   if (!out_dev)
@@ -621,19 +680,92 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
   A.synth = ctx->synth.as<float>();
   const size_t smem = fft_smem_bytes (kEmbedWarps) + 3 * kFrame * sizeof (float) + 2 * size_t (kEmbedWarps) * kEdge * sizeof (float2);
   if (set_smem (ctx, k_embed, smem)) return 1;
-  const unsigned grid = unsigned ((n_proc + kEmbedTile - 1) / kEmbedTile);
-  PROF (ctx);
-  k_embed<<<grid, kEmbedWarps * 32, smem, ctx->stream>>> (A);
-  LAUNCH_CHECK ("k_embed");
-  if (limiter_block > 0)
+
+  /* The buffer is processed in pieces of kPiece frames so that, for host buffers, the H2D copy of piece p+1, the
+   * kernels of piece p and the D2H copy of piece p-1 overlap (three streams, events in between).  The arithmetic is
+   * the same as for one launch: a piece only restricts which frames a launch emits, halo frames are read from the
+   * (already copied) neighbour pieces, the limiter of a piece runs once the block peaks after it are final. */
+  const long long kPiece = 12288;                            // 1024-frames per piece (12.6 M sample-frames, 100 MB stereo)
+  const bool pipelined = !in_dev && !out_dev && n_proc > 2 * kPiece;
+  const int n_pieces = pipelined ? int ((n_proc + kPiece - 1) / kPiece) : 1;
+  auto piece_frames = [&] (int p, long long& fb, long long& fe) { fb = pipelined ? p * kPiece : 0; fe = pipelined ? std::min<long long> (fb + kPiece, n_proc) : n_proc; };
+  auto piece_samples = [&] (int p, long long& s0, long long& s1) { long long fb, fe; piece_frames (p, fb, fe); s0 = std::min<long long> (fb * kFrame, n_frames); s1 = std::min<long long> (fe * kFrame, n_frames); };
+  std::vector<cudaEvent_t> ev_in (n_pieces), ev_out (n_pieces);
+  if (pipelined)
     {
-      const unsigned g2 = unsigned ((n_frames + 255) / 256);
-      PROF (ctx);
-      k_limiter<<<g2, 256, 0, ctx->stream>>> (d_out, (long long) n_frames, channels, limiter_block, limiter_ceiling,
-                                              ctx->peaks.as<unsigned>(), n_blocks, (long long) first_frame_number * kFrame, first_frame_number == 0);
-      LAUNCH_CHECK ("k_limiter");
+      if (!ctx->s_in)
+        {
+          CK (cudaStreamCreateWithFlags (&ctx->s_in, cudaStreamNonBlocking));
+          CK (cudaStreamCreateWithFlags (&ctx->s_out, cudaStreamNonBlocking));
+        }
+      for (int p = 0; p < n_pieces; p++)
+        {
+          CK (cudaEventCreateWithFlags (&ev_in[p], cudaEventDisableTiming));
+          CK (cudaEventCreateWithFlags (&ev_out[p], cudaEventDisableTiming));
+        }
+      cudaEvent_t ev_start;
+      CK (cudaEventCreateWithFlags (&ev_start, cudaEventDisableTiming));
+      CK (cudaEventRecord (ev_start, ctx->stream));          // copies must not overtake earlier work on the context stream
+      CK (cudaStreamWaitEvent (ctx->s_in, ev_start, 0));
+      CK (cudaEventDestroy (ev_start));
+      for (int p = 0; p < n_pieces; p++)
+        {
+          long long s0, s1;
+          piece_samples (p, s0, s1);
+          if (s1 > s0)
+            CK (cudaMemcpyAsync (ctx->emb_in.as<float>() + s0 * channels, in + s0 * channels, size_t (s1 - s0) * channels * sizeof (float),
+                                 cudaMemcpyHostToDevice, ctx->s_in));
+          CK (cudaEventRecord (ev_in[p], ctx->s_in));
+        }
     }
-  if (!out_dev)
+  else if (!in_dev)
+    CK (cudaMemcpyAsync (ctx->emb_in.p, in, n_val * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
+
+  auto launch_limiter = [&] (int p) -> int
+    {
+      long long s0, s1;
+      piece_samples (p, s0, s1);
+      if (limiter_block > 0 && s1 > s0)
+        {
+          PROF (ctx);
+          k_limiter<<<unsigned ((s1 - s0 + 255) / 256), 256, 0, ctx->stream>>> (d_out, s0, s1, channels, limiter_block, limiter_ceiling,
+                                                                           ctx->peaks.as<unsigned>(), n_blocks, (long long) first_frame_number * kFrame);
+          LAUNCH_CHECK ("k_limiter");
+        }
+      if (pipelined)
+        {
+          CK (cudaEventRecord (ev_out[p], ctx->stream));
+          CK (cudaStreamWaitEvent (ctx->s_out, ev_out[p], 0));
+          if (s1 > s0)
+            CK (cudaMemcpyAsync (out + s0 * channels, d_out + s0 * channels, size_t (s1 - s0) * channels * sizeof (float),
+                                 cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+      return 0;
+    };
+  for (int p = 0; p < n_pieces; p++)
+    {
+      if (pipelined)
+        CK (cudaStreamWaitEvent (ctx->stream, ev_in[std::min (p + 1, n_pieces - 1)], 0));   // halo frame of the next piece
+      piece_frames (p, A.frame_begin, A.frame_end);
+      const unsigned grid = unsigned ((A.frame_end - A.frame_begin + kEmbedTile - 1) / kEmbedTile);
+      PROF (ctx);
+      k_embed<<<grid, kEmbedWarps * 32, smem, ctx->stream>>> (A);
+      LAUNCH_CHECK ("k_embed");
+      if (p > 0 && launch_limiter (p - 1))                     // peaks of the blocks after piece p-1 are final now
+        return 1;
+    }
+  if (launch_limiter (n_pieces - 1))
+    return 1;
+  if (pipelined)
+    {
+      CK (cudaStreamSynchronize (ctx->s_out));
+      for (int p = 0; p < n_pieces; p++)
+        {
+          cudaEventDestroy (ev_in[p]);
+          cudaEventDestroy (ev_out[p]);
+        }
+    }
+  else if (!out_dev)
     CK (cudaMemcpyAsync (out, d_out, n_val * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
   if (snr_power)
     CK (cudaMemcpyAsync (snr_power, ctx->snr.p, 2 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -791,6 +791,7 @@ struct EmbedArgs
   long long n_frames;          // valid input sample-frames
   int C;
   long long n_proc;            // 1024-frames to process = ceil(n/1024) + 1 (tail spill)
+  long long frame_begin, frame_end;   // this launch emits frames [frame_begin, frame_end) (pipelined host<->device copies launch pieces)
   long long frame_number0;     // table row counter of frame 0: first_frame_number + 2*fpb - pad_start
   int fpb;
   const uint8_t *frame_mod;    // [2][fpb][101]
@@ -817,10 +818,10 @@ k_embed (EmbedArgs A)
   for (int i = threadIdx.x; i < 3 * kFrame; i += blockDim.x)
     synth[i] = A.synth[i];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long m = (long long) blockIdx.x * kEmbedTile - 1 + w;      // frame handled by this warp
+  const long long m = A.frame_begin + (long long) blockIdx.x * kEmbedTile - 1 + w;      // frame handled by this warp
   const long long n_real = (A.n_frames + kFrame - 1) / kFrame;          // frames that contain input
   const bool exists = m >= 0 && m < n_real;
-  const bool emits = w >= 1 && w <= kEmbedTile && m >= 0 && m < A.n_proc;
+  const bool emits = w >= 1 && w <= kEmbedTile && m >= A.frame_begin && m < A.frame_end && m < A.n_proc;
   const int C = A.C;
   float pk0 = 0.f, pk1 = 0.f;
   double snr_d = 0, snr_s = 0;
@@ -1003,11 +1004,11 @@ k_embed (EmbedArgs A)
 // Limiter::process_block (src/limiter.cc:99-124): gain ramps linearly over each block between
 // ceiling / max (bm[b-1], bm[b]) and ceiling / max (bm[b], bm[b+1]); bm[b] = max (ceiling, peak[b]).
 __global__ void
-k_limiter (float *__restrict__ x, long long n_frames, int C, int block, float ceiling,
-           const unsigned *__restrict__ peaks, long long n_blocks, long long stream_pos0, int first_is_stream_start)
+k_limiter (float *__restrict__ x, long long pos_begin, long long pos_end, int C, int block, float ceiling,
+           const unsigned *__restrict__ peaks, long long n_blocks, long long stream_pos0)
 {
-  const long long pos = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= n_frames)
+  const long long pos = pos_begin + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= pos_end)
     return;
   const long long gpos = stream_pos0 + pos;
   const long long b = gpos / block - stream_pos0 / block;           // index into peaks[]
@@ -1016,7 +1017,6 @@ k_limiter (float *__restrict__ x, long long n_frames, int C, int block, float ce
   // block -1 of the stream counts as "ceiling"; for a shard that starts mid-stream the caller's halo makes peaks[b-1] valid
   const float last = b > 0 ? fmaxf (ceiling, __uint_as_float (peaks[b - 1])) : ceiling;
   const float next = b + 1 < n_blocks ? fmaxf (ceiling, __uint_as_float (peaks[b + 1])) : ceiling;
-  (void) first_is_stream_start;
   const float scale_start = __fdiv_rn (ceiling, fmaxf (last, cur));
   const float scale_end = __fdiv_rn (ceiling, fmaxf (cur, next));
   if (scale_start == 1.0f && scale_end == 1.0f)

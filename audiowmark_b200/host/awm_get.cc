@@ -638,9 +638,19 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
   vector<VitJob> pending;
   vector<double> time_offsets;
   vector<string> debug_syncs;
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx)
+    return 1;
+  /* host buffers: the next chunk travels over PCIe while the current one is searched */
+  awm_pcm_prefetch (ctx, samples, end - start, n_channels);
   for (;;)
     {
       string debug_sync;
+      if (!eof)
+        {
+          const size_t nstart = end - overlap, nend = min (nstart + max_frames, n_frames);
+          awm_pcm_prefetch (ctx, samples + nstart * n_channels, nend - nstart, n_channels);
+        }
       if (decode_chunk (pending, int (time_offsets.size()), debug_sync, key_list, samples + start * n_channels, end - start, n_channels, sample_rate, first_chunk))
         return 1;
       time_offsets.push_back (time_offset);

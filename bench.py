@@ -176,30 +176,72 @@ def main_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
+    from audiowmark_b200 import sharding as S
     minutes = args.minutes if args.minutes else 60.0
-    n = int(minutes * 60 * RATE)
+    n = int(minutes * 60 * RATE)          # PCM frames per GPU (weak scaling: the stream is world * n frames long)
     ch = 2
     H.set_params(gpu_device=local)
-    # synthetic input: uniform noise at -6 dBFS, generated on the device (value arm) and copied to pinned host memory (e2e arm)
+    n_total = n * world
+    mx, ov = H.chunk_geometry(RATE)
+    plan, (lo_c, hi_c), own = S.rank_ranges(n_total, rank, world, mx, ov, RATE)
+    if world == 1:
+        e0, e1, ffn = 0, n, 0
+    else:
+        e0, e1, ffn = S.embed_range(own[0], own[1], n_total, RATE) if own else (0, 0, 0)
+    n_loc = e1 - e0                       # frames this rank embeds (its chunks + halo)
+
+    # synthetic input: uniform noise at -6 dBFS, a pure function of the stream position (blocks of 2^22 frames seeded by
+    # block number) so that the ranges of neighbouring ranks agree where they overlap
+    BLK = 1 << 22
+    x_dev = torch.empty((max(n_loc, 1), ch), device=dev, dtype=torch.float32)
     g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    x_dev = (torch.rand((n, ch), device=dev, generator=g, dtype=torch.float32) - 0.5)
+    for b in range(e0 // BLK, (max(e1, 1) - 1) // BLK + 1):
+        g.manual_seed(1234 + b)
+        blk = torch.rand((BLK, ch), device=dev, generator=g, dtype=torch.float32) - 0.5
+        lo, hi = max(e0, b * BLK), min(e1, (b + 1) * BLK)
+        if hi > lo:
+            x_dev[lo - e0:hi - e0] = blk[lo - b * BLK:hi - b * BLK]
+    del blk
     y_dev = torch.empty_like(x_dev)
-    x_host = torch.empty((n, ch), dtype=torch.float32, pin_memory=True)
-    y_host = torch.empty((n, ch), dtype=torch.float32, pin_memory=True)
+    x_host = torch.empty((max(n_loc, 1), ch), dtype=torch.float32, pin_memory=True)
+    y_host = torch.empty((max(n_loc, 1), ch), dtype=torch.float32, pin_memory=True)
     x_host.copy_(x_dev)
     torch.cuda.synchronize()
 
     stream = torch.cuda.ExternalStream(H.gpu_stream(), device=dev)
-    want_real = None
 
-    def step_resident():
-        H.add(x_dev.data_ptr(), PAYLOAD, None, y_dev.data_ptr(), n, ch)
-        return H.get(y_dev.data_ptr(), n_frames=n, channels=ch)
+    def merged(blobs):
+        """final gather of the chunk results (the job's only collective) + the reference's merge, on every rank"""
+        allb = S.gather_blobs(blobs, device=dev)
+        by_chunk = dict(b for per_rank in allb for b in per_rank)
+        return H.merge_chunks([by_chunk[c] for c in range(len(plan))], [p[2] for p in plan], n_total / float(RATE))
 
-    def step_e2e():
-        H.add(x_host.numpy(), PAYLOAD, None, y_host.numpy())
-        return H.get(y_host.numpy())
+    if world == 1:
+        def step_resident():
+            H.add(x_dev.data_ptr(), PAYLOAD, None, y_dev.data_ptr(), n, ch)
+            return H.get(y_dev.data_ptr(), n_frames=n, channels=ch)
+
+        def step_e2e():
+            H.add(x_host.numpy(), PAYLOAD, None, y_host.numpy())
+            return H.get(y_host.numpy())
+    else:
+        def sharded(xp, yp, host):
+            if n_loc:
+                H.add(xp, PAYLOAD, None, yp, n_loc, ch, first_frame_number=ffn)
+            blobs = []
+            for c in range(lo_c, hi_c):
+                off = plan[c][0] - e0
+                if host:
+                    blobs.append((c, H.get_chunk(y_host.numpy()[off:off + plan[c][1]], first_chunk=(c == 0))))
+                else:
+                    blobs.append((c, H.get_chunk(y_dev.data_ptr() + off * ch * 4, first_chunk=(c == 0), n_frames=plan[c][1], channels=ch)))
+            return merged(blobs)
+
+        def step_resident():
+            return sharded(x_dev.data_ptr(), y_dev.data_ptr(), False)
+
+        def step_e2e():
+            return sharded(x_host.numpy()[:max(n_loc, 1)], y_host.numpy()[:max(n_loc, 1)], True)
 
     def check(doc):
         real = [m for m in doc["matches"] if m["quality"] > 0.35]
@@ -246,7 +288,6 @@ def main_gpu(args):
     ms_e2e, wall_e2e, doc2, _, _ = timed(step_e2e, args.steps, False)
     ok2, _ = check(doc2)
 
-    # final gather of the per-rank results (the only exchange of the sharded job): detections per rank
     det = torch.tensor([n_real, int(ok), int(ok2)], device=dev, dtype=torch.int64)
     if world > 1:
         gathered = [torch.zeros_like(det) for _ in range(world)]
@@ -259,7 +300,7 @@ def main_gpu(args):
             dist.destroy_process_group()
         return
 
-    total_frames = n * world
+    total_frames = n_total
     ms_step = ms / args.steps
     value = total_frames / (ms_step / 1e3)
     e2e_value = total_frames / (ms_e2e / args.steps / 1e3)
@@ -297,12 +338,12 @@ def main_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%g min stereo 44.1 kHz embed+detect per GPU (BASELINE.json configs[1]%s)" % (minutes, "" if minutes == 60 else ", shortened"),
                    "pcm_frames_per_gpu": n, "channels": ch, "payload_bits": 128, "get_chunks": "30 min, 134.4 s overlap",
-                   "parallelism": "chunk/frame-block shard per GPU, final result gather only" if world > 1 else "1 GPU",
+                   "parallelism": ("one %d h stream: `get` sharded by 30-min chunks (%d chunks), `add` by frame blocks with halo; final result gather only" % (world, len(plan))) if world > 1 else "1 GPU",
                    "l2": "inputs (%.2f GB per pass) larger than L2" % (n * ch * 4 / 1e9)},
         "analysis_frames_per_s": value / 1024.0,
-        "payload_ok": bool(all(d[1] for d in det_all)), "detections_per_rank": [d[0] for d in det_all],
+        "payload_ok": bool(all(d[1] for d in det_all)), "detections": det_all[0][0],
         "e2e": {"value": e2e_value, "unit": "PCM frames/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": 2 * n * ch * 4, "d2h_bytes_per_step": n * ch * 4, "payload_ok": bool(all(d[2] for d in det_all)),
+                "h2d_bytes_per_step": 2 * n_loc * ch * 4, "d2h_bytes_per_step": n_loc * ch * 4, "payload_ok": bool(all(d[2] for d in det_all)),
                 "api": "hostapi.add + hostapi.get (C++ add_watermark_buffer / get_watermark_buffer) on pinned host buffers"},
         "gpu_launches": launches,
         "roofline": roofline,

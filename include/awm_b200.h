@@ -105,6 +105,10 @@ int awm_set_mix_tables (awm_ctx *ctx, int key_slot, const awm_mix_entry *entries
  * (ClipDecoder::run_block zero padding, src/wmget.cc:823-866) without the caller materialising them.
  */
 int awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end);
+/* optional: start copying a HOST buffer that will be bound next (the following chunk of a long file) on a separate
+ * stream while the kernels of the current chunk run; a later awm_pcm_bind with the same pointer / size / channels and
+ * no padding picks the copy up instead of transferring again.  Two prefetches may be outstanding. */
+int awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels);
 
 /* ---- embed: add_stream_watermark main loop (src/wmadd.cc:520-589) = FFTAnalyzer::run_fft
  * (src/wmcommon.cc:91-121) + apply_frame_mod (src/wmadd.cc:61-84) + WatermarkSynth::run

@@ -38,3 +38,24 @@ def test_chunk_sharded_get_equals_single_process():
         got = H.merge_chunks([blobs[c] for c in range(len(plan))], [p[2] for p in plan], y.shape[0] / 44100.0)
         assert got == doc
     H.set_params()
+
+
+def test_pipelined_host_paths_equal_device_paths():
+    """awm_embed splits long HOST buffers into pieces to overlap H2D / kernels / D2H, and `get` prefetches the next chunk:
+    both must give exactly what the one-shot device-pointer path gives."""
+    torch = pytest.importorskip("torch")
+    x = T.noise(600.0, 2, seed=23, amp=1.0)                 # 10 min: three pieces of 12288 frames, limiter active
+    H.set_params(chunk_size_min=4.0)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    H.add(xd.data_ptr(), T.PAYLOAD, None, yd.data_ptr(), x.shape[0], 2)
+    want = yd.cpu().numpy()
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.empty_like(xp).pin_memory()
+    H.add(xp.numpy(), T.PAYLOAD, None, yp.numpy())
+    assert np.array_equal(yp.numpy(), want)
+    assert np.array_equal(H.add(x, T.PAYLOAD), want)        # pageable host memory
+    doc_dev = H.get(yd.data_ptr(), n_frames=x.shape[0], channels=2)
+    assert H.get(yp.numpy()) == doc_dev
+    assert H.get(want) == doc_dev
+    H.set_params()
