@@ -292,6 +292,15 @@ awmh_gpu_stream()
   return c ? awm_stream (c) : nullptr;
 }
 
+/* device-pointer calls are stream ordered and return without waiting: synchronise before touching the results from
+ * another stream / the host */
+int
+awmh_synchronize()
+{
+  awm_ctx *c = Engine::ctx();
+  return c ? awm_synchronize (c) : 1;
+}
+
 int
 awmh_profile_enable (int on)
 {

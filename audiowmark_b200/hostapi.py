@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown"]
 
 _lib = None
 
@@ -195,6 +195,12 @@ def gpu_launches() -> int:
 
 def gpu_stream() -> int:
     return int(load().awmh_gpu_stream() or 0)
+
+
+def synchronize():
+    """wait for the context stream (calls with DEVICE pointers are asynchronous)."""
+    if load().awmh_synchronize():
+        raise RuntimeError("no GPU context")
 
 
 def profile_enable(on=True):

@@ -48,7 +48,9 @@ def test_pipelined_host_paths_equal_device_paths():
     H.set_params(chunk_size_min=4.0)
     xd = torch.from_numpy(x).cuda()
     yd = torch.empty_like(xd)
+    torch.cuda.synchronize()                                # the context has its own (non-blocking) stream
     H.add(xd.data_ptr(), T.PAYLOAD, None, yd.data_ptr(), x.shape[0], 2)
+    H.synchronize()                                         # device-pointer calls are asynchronous
     want = yd.cpu().numpy()
     xp = torch.from_numpy(x).pin_memory()
     yp = torch.empty_like(xp).pin_memory()

@@ -78,6 +78,7 @@ def test_embed_device_pointers_match_host_path(ctx):
     host = ctx.embed(x)
     xin = torch.from_numpy(x).cuda()
     xout = torch.empty_like(xin)
+    torch.cuda.synchronize()
     ctx.embed(xin.data_ptr(), xout.data_ptr(), n_frames=x.shape[0], channels=2)
     ctx.synchronize()
     assert np.array_equal(xout.cpu().numpy(), host)
