@@ -72,10 +72,21 @@ class Context:
             raise AwmError("awm_create failed (rc=%d): no usable CUDA device; this package has no CPU fallback" % rc)
         self.h = h
 
+    @classmethod
+    def from_handle(cls, handle):
+        """non-owning view of an existing awm_ctx* (the host library's engine context)"""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.h = ctypes.c_void_p(handle)
+        self._borrowed = True
+        if not handle:
+            raise AwmError("no GPU context (a CUDA device is required, there is no CPU fallback)")
+        return self
+
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and not getattr(self, "_borrowed", False):
             self.lib.awm_destroy(self.h)
-            self.h = None
+        self.h = None
 
     __del__ = close
 
@@ -170,6 +181,15 @@ class Context:
             self._ck(self.lib.awm_sync_approx(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), ctypes.c_uint64(wav_first), ctypes.c_uint64(wav_last),
                                               ctypes.c_double(water_delta), _ptr(out), ctypes.c_size_t(n.value), ctypes.byref(n)))
         return out
+
+    def sync_approx_run(self, key_slot=0, mode=MODE_BLOCK, wav_first=0, wav_last=None, water_delta=0.01) -> int:
+        """run the search, keep the scores on the device (for sync_peaks); returns the number of scores"""
+        if wav_last is None:
+            wav_last = 0xFFFFFFFFFFFFFFF
+        n = ctypes.c_size_t()
+        self._ck(self.lib.awm_sync_approx(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), ctypes.c_uint64(wav_first), ctypes.c_uint64(wav_last),
+                                          ctypes.c_double(water_delta), None, ctypes.c_size_t(0), ctypes.byref(n)))
+        return n.value
 
     def sync_peaks(self, min_abs_quality: float, max_peaks: int = 65536):
         """local maxima above a floor of the LAST sync_approx call; returns (peaks sorted by index, number found)."""

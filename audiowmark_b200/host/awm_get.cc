@@ -315,47 +315,24 @@ decode_raw_bits (const Key& key, const vector<uint64_t>& indices, vector<vector<
   return true;
 }
 
-/* ---------------------------------------------------------------- BlockDecoder (src/wmget.cc:492-735) */
-
-class BlockDecoder
+/* BlockDecoder::run after the soft bits are known (src/wmget.cc:539-701): one job per decoded block, AB pairs, the "all" pattern */
+void
+build_block_jobs (const Key& key, const vector<SyncFinder::Score>& sync_scores, const vector<vector<float>>& raw, const vector<int>& valid,
+                  int sample_rate, int chunk, double speed, vector<VitJob>& pending)
 {
-  int debug_sync_frame_count = 0;
-  const double speed;
-  vector<SyncFinder::KeyResult> key_results;
-public:
-  explicit BlockDecoder (double speed) : speed (speed) {}
-
-  /* the PCM (n_frames x n_channels at sample_rate) is already bound to the GPU context */
-  void
-  run (const vector<Key>& key_list, size_t n_frames, int n_channels, int sample_rate, vector<VitJob>& pending, int chunk)
-  {
-    SyncFinder sync_finder;
-    key_results = sync_finder.search (key_list, n_frames, n_channels, SyncFinder::Mode::BLOCK, 0, n_frames * n_channels);
-    const size_t count = mark_sync_frame_count() + mark_data_frame_count();
-    const size_t block_len = count * Params::frame_size;
-
-    for (const auto& key_result : key_results)
-      {
-        const Key& key = key_result.key;
-        struct PatternRawBits { size_t index; double quality; vector<float> raw_bit_vec; ConvBlockType block_type; };
-        vector<PatternRawBits> prv;
-        auto add_job = [&] (const vector<float>& soft, ConvBlockType bt, double time, SyncFinder::Score score, ResultSet::Type type)
-          {
-            VitJob job { soft, bt, time, score, type, key, chunk, speed };
-            pending.push_back (job);
-          };
-
-        vector<uint64_t> indices;
-        for (const auto& s : key_result.sync_scores)
-          indices.push_back (s.index);
-        vector<vector<float>> raw;
-        vector<int> valid;
-        if (!indices.empty() && !decode_raw_bits (key, indices, raw, valid))
-          continue;
-        for (size_t i = 0; i < indices.size(); i++)
+  const size_t count = mark_sync_frame_count() + mark_data_frame_count();
+  const size_t block_len = count * Params::frame_size;
+  struct PatternRawBits { size_t index; double quality; vector<float> raw_bit_vec; ConvBlockType block_type; };
+  vector<PatternRawBits> prv;
+  auto add_job = [&] (const vector<float>& soft, ConvBlockType bt, double time, SyncFinder::Score score, ResultSet::Type type)
+    {
+      VitJob job { soft, bt, time, score, type, key, chunk, speed };
+      pending.push_back (job);
+    };
+        for (size_t i = 0; i < sync_scores.size(); i++)
           if (valid[i])
             {
-              const auto& sync_score = key_result.sync_scores[i];
+              const auto& sync_score = sync_scores[i];
               prv.push_back ({ sync_score.index, sync_score.quality, raw[i], sync_score.block_type });
               add_job (raw[i], sync_score.block_type, double (sync_score.index) / sample_rate, sync_score, ResultSet::Type::BLOCK);
             }
@@ -451,6 +428,35 @@ public:
             score_all.quality /= norm[0] + norm[1];
             add_job (raw_all, ConvBlockType::ab, 0.0, score_all, ResultSet::Type::ALL);
           }
+}
+
+/* ---------------------------------------------------------------- BlockDecoder (src/wmget.cc:492-735) */
+
+class BlockDecoder
+{
+  int debug_sync_frame_count = 0;
+  const double speed;
+  vector<SyncFinder::KeyResult> key_results;
+public:
+  explicit BlockDecoder (double speed) : speed (speed) {}
+
+  /* the PCM (n_frames x n_channels at sample_rate) is already bound to the GPU context */
+  void
+  run (const vector<Key>& key_list, size_t n_frames, int n_channels, int sample_rate, vector<VitJob>& pending, int chunk)
+  {
+    SyncFinder sync_finder;
+    key_results = sync_finder.search (key_list, n_frames, n_channels, SyncFinder::Mode::BLOCK, 0, n_frames * n_channels);
+    for (const auto& key_result : key_results)
+      {
+        const Key& key = key_result.key;
+        vector<uint64_t> indices;
+        for (const auto& s : key_result.sync_scores)
+          indices.push_back (s.index);
+        vector<vector<float>> raw;
+        vector<int> valid;
+        if (!indices.empty() && !decode_raw_bits (key, indices, raw, valid))
+          continue;
+        build_block_jobs (key, key_result.sync_scores, raw, valid, sample_rate, chunk, speed, pending);
       }
     debug_sync_frame_count = n_frames / Params::frame_size;
   }
@@ -608,6 +614,29 @@ decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vect
 }
 
 } // namespace
+
+/* BlockDecoder job list of one chunk as flat records (for the multi-GPU driver):
+ * u8 code_type (AWM_BLOCK_*), u8 pattern_type (ResultSet::Type), u8 score_block_type, u8 pad, f64 time, u64 index, f64 quality, u32 n_soft, f32 soft[] */
+std::vector<unsigned char>
+block_jobs_blob (const Key& key, const vector<SyncFinder::Score>& sync_scores, const vector<vector<float>>& raw, const vector<int>& valid, int sample_rate, int *n_jobs)
+{
+  vector<VitJob> jobs;
+  build_block_jobs (key, sync_scores, raw, valid, sample_rate, 0, 1, jobs);
+  std::vector<unsigned char> b;
+  auto put = [&] (const void *p, size_t n) { const unsigned char *c = static_cast<const unsigned char *> (p); b.insert (b.end(), c, c + n); };
+  for (const auto& j : jobs)
+    {
+      const uint8_t hdr[4] = { uint8_t (j.block_type == ConvBlockType::a ? AWM_BLOCK_A : j.block_type == ConvBlockType::b ? AWM_BLOCK_B : AWM_BLOCK_AB),
+                               uint8_t (j.type), uint8_t (j.score.block_type), 0 };
+      const double time = j.time, quality = j.score.quality;
+      const uint64_t index = j.score.index;
+      const uint32_t n_soft = j.soft.size();
+      put (hdr, 4); put (&time, 8); put (&index, 8); put (&quality, 8); put (&n_soft, 4);
+      put (j.soft.data(), n_soft * sizeof (float));
+    }
+  *n_jobs = int (jobs.size());
+  return b;
+}
 
 /* chunk geometry of WavChunkLoader (src/wavchunkloader.cc:54-163): chunks of get_chunk_size minutes that
  * overlap by two blocks * 1.3 */

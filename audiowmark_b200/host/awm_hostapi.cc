@@ -5,6 +5,7 @@
 #include "awm_tables.hh"
 #include "awm_util.hh"
 
+#include <algorithm>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -17,6 +18,9 @@ make_key (const unsigned char *key16, const char *name)
   k.set_key (key16, name ? name : "");
   return k;
 }
+
+std::vector<unsigned char> block_jobs_blob (const Key& key, const std::vector<SyncFinder::Score>& sync_scores, const std::vector<std::vector<float>>& raw,
+                                            const std::vector<int>& valid, int sample_rate, int *n_jobs);
 
 extern "C" {
 
@@ -276,6 +280,81 @@ awmh_chunk_geometry (int sample_rate, uint64_t *max_frames, uint64_t *overlap_fr
   chunk_geometry (sample_rate, m, o);
   *max_frames = m;
   *overlap_frames = o;
+}
+
+/* ---- stage-level access for the frame-balanced multi-GPU driver (audiowmark_b200/sharding.py) ---------------- */
+
+void *
+awmh_ctx()
+{
+  return Engine::ctx();
+}
+
+int
+awmh_key_slot (const unsigned char *key16)
+{
+  return Engine::key_slot (make_key (key16, ""));
+}
+
+/* candidates of one chunk from its (gathered) peak list, complete above floor_q; *complete = 0 -> ask again with a lower floor */
+int
+awmh_stage_select (const awm_search_score *peaks, size_t n, double floor_q, int clip_mode, awm_search_score *out, size_t max_out, size_t *n_out, int *complete)
+{
+  std::vector<awm_search_score> sel;
+  *complete = select_candidates_from_peaks (peaks, n, floor_q, Params::sync_threshold2 * 0.75, sel) ? 1 : 0;
+  if (clip_mode)
+    {
+      std::sort (sel.begin(), sel.end(), [] (const awm_search_score& a, const awm_search_score& b) { return fabs (a.raw_quality - a.local_mean) > fabs (b.raw_quality - b.local_mean); });
+      const size_t n_max = std::max (Params::get_n_best, 5);
+      if (sel.size() > n_max)
+        sel.resize (n_max);
+    }
+  *n_out = sel.size();
+  if (sel.size() > max_out)
+    return -2;
+  if (!sel.empty())
+    memcpy (out, sel.data(), sel.size() * sizeof (awm_search_score));
+  return 0;
+}
+
+/* threshold2 / n-best selection of a chunk's refined scores -> (index, quality, block type) sorted by index */
+int
+awmh_stage_final (const awm_search_score *refined, size_t n, uint64_t *index_out, double *quality_out, int *btype_out, size_t *n_out)
+{
+  std::vector<awm_search_score> v (refined, refined + n);
+  std::vector<SyncFinder::Score> out;
+  select_final_scores (v, out);
+  *n_out = out.size();
+  for (size_t i = 0; i < out.size(); i++)
+    {
+      index_out[i] = out[i].index;
+      quality_out[i] = out[i].quality;
+      btype_out[i] = int (out[i].block_type);
+    }
+  return 0;
+}
+
+/* Viterbi job list (single blocks, AB pairs, "all") of one chunk from its final scores and their soft bits */
+int
+awmh_stage_jobs (const unsigned char *key16, const uint64_t *index, const double *quality, const int *btype, size_t n, const float *raw, const int *valid,
+                 int sample_rate, unsigned char *blob, size_t cap, size_t *len, int *n_jobs)
+{
+  const size_t n_coded = code_size (ConvBlockType::a, Params::payload_size);
+  std::vector<SyncFinder::Score> scores (n);
+  std::vector<std::vector<float>> rawv (n);
+  std::vector<int> validv (valid, valid + n);
+  for (size_t i = 0; i < n; i++)
+    {
+      scores[i] = SyncFinder::Score { size_t (index[i]), quality[i], ConvBlockType (btype[i]) };
+      rawv[i].assign (raw + i * n_coded, raw + (i + 1) * n_coded);
+    }
+  const std::vector<unsigned char> b = block_jobs_blob (make_key (key16, ""), scores, rawv, validv, sample_rate, n_jobs);
+  *len = b.size();
+  if (b.size() > cap)
+    return -2;
+  if (!b.empty())
+    memcpy (blob, b.data(), b.size());
+  return 0;
 }
 
 uint64_t

@@ -86,16 +86,68 @@ select_candidates (const SearchScore *sc, size_t n, double threshold, vector<Sea
     }
 }
 
-/* Same selection as select_candidates, but the local maxima come from the GPU (awm_sync_peaks) and only those above a
- * floor are transferred.  Exactness: a peak can only be masked by a 3x stronger one, which is above the floor as
- * well; peaks within 23 search steps of each other are always within 23 list positions; and if at least n_best
- * unmasked peaks lie above the floor, every peak the reference would select does too.  The floor is lowered until
- * that holds (or it reaches zero, i.e. all peaks). */
+} // namespace
+
+/* Candidate selection on a list of local maxima (sorted by index) that is complete above `floor_q`
+ * (= sync_select_local_maxima + sync_mask_avg_false_positives + sync_select_threshold_and_n_best, src/syncfinder.cc:258-383).
+ * Exactness: a peak can only be masked by a 3x stronger one, which is above the floor as well; peaks within 23 search
+ * steps of each other are always within 23 list positions; and if the scan stops before it would need a peak at or below
+ * the floor, every peak the reference would select has been seen.  Returns false if the list was not sufficient
+ * (the caller lowers the floor and asks again). */
 bool
-select_candidates_gpu (awm_ctx *ctx, double threshold, vector<SearchScore>& out)
+select_candidates_from_peaks (const awm_search_score *peaks, size_t n, double floor_q, double threshold, vector<awm_search_score>& out)
 {
   constexpr int    mask_distance = local_mean_distance + 3;
   constexpr double mask_factor   = 3;
+  /* "skip the score after a maximum": of directly adjacent scores that are both maxima (equal quality) the one
+   * right after a selected maximum is not looked at */
+  vector<SearchScore> pk;
+  pk.reserve (n);
+  bool prev_taken = false;
+  uint64_t prev_index = ~uint64_t (0);
+  for (size_t i = 0; i < n; i++)
+    {
+      const bool adjacent = peaks[i].index == prev_index + Params::sync_search_step;
+      const bool take = !(adjacent && prev_taken);
+      if (take)
+        pk.push_back (peaks[i]);
+      prev_taken = take;
+      prev_index = peaks[i].index;
+    }
+  const size_t np = pk.size();
+  vector<uint32_t> order (np);
+  for (size_t k = 0; k < np; k++)
+    order[k] = k;
+  std::sort (order.begin(), order.end(), [&] (uint32_t a, uint32_t b) { return abs_quality (pk[a]) > abs_quality (pk[b]); });
+  auto sign = [&] (size_t k) { return (pk[k].raw_quality - pk[k].local_mean < 0) ? -1 : 1; };
+  out.clear();
+  for (size_t k = 0; k < np; k++)
+    {
+      const int i = order[k];
+      const double q = abs_quality (pk[i]);
+      if (q <= threshold && int (out.size()) >= Params::get_n_best)
+        return true;                            // everything above the threshold is in, and at least n_best matches
+      if (q <= floor_q)
+        return false;                           // peaks at or below the floor may be missing from the list
+      bool mask = false;
+      for (int j = i - 1; j >= 0 && !mask && int (pk[i].index - pk[j].index) / Params::sync_search_step <= mask_distance; j--)
+        mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
+      for (int j = i + 1; j < int (np) && !mask && int (pk[j].index - pk[i].index) / Params::sync_search_step <= mask_distance; j++)
+        mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
+      if (!mask)
+        out.push_back (pk[i]);
+    }
+  /* list exhausted: final if it held every peak there is, or if n_best unmasked peaks lie above the floor */
+  return floor_q < 0 || int (out.size()) >= Params::get_n_best;
+}
+
+namespace {
+
+/* the local maxima come from the GPU (awm_sync_peaks); only those above a floor are transferred, the floor is lowered
+ * until the selection is complete */
+bool
+select_candidates_gpu (awm_ctx *ctx, double threshold, vector<SearchScore>& out)
+{
   static SearchScore *peaks = nullptr;
   static const size_t max_peaks = 1 << 17;
   if (!peaks)
@@ -110,49 +162,7 @@ select_candidates_gpu (awm_ctx *ctx, double threshold, vector<SearchScore>& out)
         return false;
       if (n > max_peaks)
         return false;                             // caller falls back to the full score list
-      /* "skip the score after a maximum": of directly adjacent scores that are both maxima (equal quality) the one
-       * right after a selected maximum is not looked at */
-      vector<SearchScore> pk;
-      pk.reserve (n);
-      bool prev_taken = false;
-      uint64_t prev_index = ~uint64_t (0);
-      for (size_t i = 0; i < n; i++)
-        {
-          const bool adjacent = peaks[i].index == prev_index + Params::sync_search_step;
-          const bool take = !(adjacent && prev_taken);
-          if (take)
-            pk.push_back (peaks[i]);
-          prev_taken = take;
-          prev_index = peaks[i].index;
-        }
-      const size_t np = pk.size();
-      vector<uint32_t> order (np);
-      for (size_t k = 0; k < np; k++)
-        order[k] = k;
-      std::sort (order.begin(), order.end(), [&] (uint32_t a, uint32_t b) { return abs_quality (pk[a]) > abs_quality (pk[b]); });
-      auto sign = [&] (size_t k) { return (pk[k].raw_quality - pk[k].local_mean < 0) ? -1 : 1; };
-      out.clear();
-      bool complete = false;
-      for (size_t k = 0; k < np && !complete; k++)
-        {
-          const int i = order[k];
-          const double q = abs_quality (pk[i]);
-          if (q <= threshold && int (out.size()) >= Params::get_n_best)
-            {
-              complete = true;                    // everything above the threshold is in, and at least n_best matches
-              break;
-            }
-          bool mask = false;
-          for (int j = i - 1; j >= 0 && !mask && int (pk[i].index - pk[j].index) / Params::sync_search_step <= mask_distance; j--)
-            mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
-          for (int j = i + 1; j < int (np) && !mask && int (pk[j].index - pk[i].index) / Params::sync_search_step <= mask_distance; j++)
-            mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
-          if (!mask)
-            out.push_back (pk[i]);
-        }
-      /* final if the scan stopped by itself, if n_best unmasked peaks lie above this floor (nothing below it can
-       * displace them), or if this floor already delivered every peak there is */
-      if (complete || int (out.size()) >= Params::get_n_best || floor_q < 0)
+      if (select_candidates_from_peaks (peaks, n, floor_q, threshold, out))
         return true;
     }
   return true;
@@ -180,6 +190,21 @@ select_truncate_n (vector<SearchScore>& scores, size_t n)
 }
 
 } // namespace
+
+/* threshold2 / n-best selection of the refined scores + conversion to Score (src/syncfinder.cc:533-555) */
+void
+select_final_scores (vector<awm_search_score>& scores, vector<SyncFinder::Score>& out)
+{
+  std::sort (scores.begin(), scores.end(), [] (const SearchScore& a, const SearchScore& b) { return a.index < b.index; });
+  select_threshold_and_n_best (scores, Params::sync_threshold2);
+  std::sort (scores.begin(), scores.end(), [] (const SearchScore& a, const SearchScore& b) { return a.index < b.index; });
+  out.clear();
+  for (const auto& s : scores)
+    {
+      const double q = s.raw_quality - s.local_mean;
+      out.push_back (SyncFinder::Score { size_t (s.index), fabs (q), q > 0 ? ConvBlockType::a : ConvBlockType::b });
+    }
+}
 
 double
 SyncFinder::normalize_sync_quality (double raw_quality)
@@ -272,14 +297,7 @@ SyncFinder::search (const vector<Key>& key_list, size_t n_frames, int n_channels
           key_results.push_back (key_result);
           continue;
         }
-      std::sort (scores.begin(), scores.end(), [] (const SearchScore& a, const SearchScore& b) { return a.index < b.index; });
-      select_threshold_and_n_best (scores, Params::sync_threshold2);
-      std::sort (scores.begin(), scores.end(), [] (const SearchScore& a, const SearchScore& b) { return a.index < b.index; });
-      for (const auto& s : scores)
-        {
-          const double q = s.raw_quality - s.local_mean;
-          key_result.sync_scores.push_back (Score { size_t (s.index), fabs (q), q > 0 ? ConvBlockType::a : ConvBlockType::b });
-        }
+      select_final_scores (scores, key_result.sync_scores);
       key_results.push_back (key_result);
     }
   return key_results;

@@ -7,6 +7,7 @@
 #include "awm_random.hh"
 #include "awm_code.hh"
 #include "awm_streams.hh"
+#include "../../include/awm_b200.h"
 
 int add_stream_watermark (const Key& key, AudioInputStream *in_stream, AudioOutputStream *out_stream, const std::string& bits, size_t zero_frames);
 int add_watermark (const Key& key, const std::string& infile, const std::string& outfile, const std::string& bits);
@@ -41,3 +42,9 @@ public:
                                  size_t wav_first, size_t wav_last);
   static double normalize_sync_quality (double raw_quality);
 };
+
+/* stage functions of SyncFinder::search / BlockDecoder::run, used by get_watermark_buffer and by the frame-balanced
+ * multi-GPU driver (audiowmark_b200/sharding.py), which runs the GPU stages on slices of a chunk on different ranks */
+bool select_candidates_from_peaks (const awm_search_score *peaks, size_t n, double floor_q, double threshold, std::vector<awm_search_score>& out);
+void select_final_scores (std::vector<awm_search_score>& scores, std::vector<SyncFinder::Score>& out);
+

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown"]
 
 _lib = None
 
@@ -30,6 +30,7 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
         lib.awmh_gpu_launches.restype = ctypes.c_uint64
         lib.awmh_gpu_stream.restype = ctypes.c_void_p
+        lib.awmh_ctx.restype = ctypes.c_void_p
         _lib = lib
     return _lib
 
@@ -49,8 +50,16 @@ def _key(key) -> bytes:
     return k
 
 
+_PARAMS = {"sync_threshold2": 0.35, "n_best": 8, "water_delta": 0.01}
+
+
+def get_param(name):
+    return _PARAMS[name]
+
+
 def set_params(water_delta=0.01, frames_per_bit=2, mix=True, hard=False, sync_threshold2=0.35, n_best=8, chunk_size_min=30.0,
                test_no_limiter=False, test_no_sync=False, gpu_device=0, quiet=True):
+    _PARAMS.update(sync_threshold2=sync_threshold2, n_best=n_best, water_delta=water_delta)
     load().awmh_set_params(ctypes.c_double(water_delta), ctypes.c_int(frames_per_bit), ctypes.c_int(mix), ctypes.c_int(hard),
                            ctypes.c_double(sync_threshold2), ctypes.c_int(n_best), ctypes.c_double(chunk_size_min),
                            ctypes.c_int(test_no_limiter), ctypes.c_int(test_no_sync), ctypes.c_int(gpu_device), ctypes.c_int(quiet))
@@ -187,6 +196,64 @@ def merge_chunks(blobs, time_offsets, total_seconds: float, keys=None, names=Non
     if rc:
         raise RuntimeError("awmh_merge_chunks failed (rc=%d)" % rc)
     return json.loads(out.value.decode())
+
+
+def engine_ctx() -> int:
+    """awm_ctx* of the host library's GPU context (creates it; raises without a CUDA device)"""
+    h = load().awmh_ctx()
+    if not h:
+        raise RuntimeError("no GPU context: a CUDA device is required, there is no CPU fallback")
+    return int(h)
+
+
+def key_slot(key=None) -> int:
+    s = load().awmh_key_slot(_key(key))
+    if s < 0:
+        raise RuntimeError("key table upload failed")
+    return s
+
+
+def stage_select(peaks: np.ndarray, floor_q: float, clip_mode=False):
+    pk = np.ascontiguousarray(peaks, capi.SEARCH_SCORE)
+    out = np.zeros(max(len(pk), 1), capi.SEARCH_SCORE)
+    n, complete = ctypes.c_size_t(), ctypes.c_int()
+    rc = load().awmh_stage_select(_ptr(pk), ctypes.c_size_t(len(pk)), ctypes.c_double(floor_q), ctypes.c_int(1 if clip_mode else 0),
+                                  _ptr(out), ctypes.c_size_t(len(out)), ctypes.byref(n), ctypes.byref(complete))
+    if rc:
+        raise RuntimeError("awmh_stage_select failed (%d)" % rc)
+    return out[:n.value].copy(), bool(complete.value)
+
+
+def stage_final(refined: np.ndarray):
+    r = np.ascontiguousarray(refined, capi.SEARCH_SCORE)
+    idx, q, bt = np.zeros(len(r), np.uint64), np.zeros(len(r), np.float64), np.zeros(len(r), np.int32)
+    n = ctypes.c_size_t()
+    load().awmh_stage_final(_ptr(r), ctypes.c_size_t(len(r)), _ptr(idx), _ptr(q), _ptr(bt), ctypes.byref(n))
+    return idx[:n.value].copy(), q[:n.value].copy(), bt[:n.value].copy()
+
+
+def stage_jobs(key, index, quality, btype, raw, valid, sample_rate=44100):
+    """Viterbi jobs of one chunk: list of (code_type, pattern_type, score_btype, time, index, quality, soft float32[])"""
+    import struct
+    idx, q, bt = (np.ascontiguousarray(index, np.uint64), np.ascontiguousarray(quality, np.float64), np.ascontiguousarray(btype, np.int32))
+    raw = np.ascontiguousarray(raw, np.float32)
+    valid = np.ascontiguousarray(valid, np.int32)
+    cap = 64 + (len(idx) * 3 + 2) * (36 + raw.shape[1] * 8) if len(idx) else 64
+    buf = (ctypes.c_ubyte * cap)()
+    blen, nj = ctypes.c_size_t(), ctypes.c_int()
+    rc = load().awmh_stage_jobs(_key(key), _ptr(idx), _ptr(q), _ptr(bt), ctypes.c_size_t(len(idx)), _ptr(raw), _ptr(valid), ctypes.c_int(sample_rate),
+                                buf, ctypes.c_size_t(cap), ctypes.byref(blen), ctypes.byref(nj))
+    if rc:
+        raise RuntimeError("awmh_stage_jobs failed (%d)" % rc)
+    data = bytes(buf[:blen.value])
+    out, pos = [], 0
+    for _ in range(nj.value):
+        ct, pt, sbt, _pad, time, index_, quality_, n_soft = struct.unpack_from("<BBBBdQdI", data, pos)
+        pos += 32
+        soft = np.frombuffer(data, np.float32, n_soft, pos).copy()
+        pos += 4 * n_soft
+        out.append((ct, pt, sbt, time, index_, quality_, soft))
+    return out
 
 
 def gpu_launches() -> int:

@@ -112,3 +112,253 @@ def gather_blobs(blobs, device=None):
     bufs = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(bufs, buf)
     return [unpack_blobs(bytes(b[:int(s.item())].cpu().numpy().tobytes())) for b, s in zip(bufs, sizes)]
+
+
+# =====================================================================================================================
+# Frame-balanced `get` across ranks.
+#
+# Chunk sharding above is exact but coarse (30-minute units).  Here every rank owns an equal span of stream POSITIONS;
+# for each chunk that overlaps its span it runs the GPU stages on the slice of the chunk's start frames it owns (with a
+# 6-frame margin for the local mean and a 2227-frame tail the sync pattern reaches into), and the per-chunk decisions
+# (candidate selection, threshold / n-best, AB / "all" combination, merge) are taken on the gathered lists by every rank
+# identically.  Results are identical to the single-process run; four small gathers (peaks, refined scores, soft bits,
+# decoded words) are the only communication.
+# =====================================================================================================================
+
+import ctypes
+
+import numpy as np
+
+T_BLOCK = 2226                 # frames per block (payload 128 bit): sync pattern length in BLOCK mode
+MARGIN = 6                     # start frames of margin on each side of a slice (local mean uses +-20 scores = +-5 frames)
+
+
+def owner_span(n_total: int, world: int) -> int:
+    per = -(-n_total // world)
+    return -(-per // FRAME) * FRAME
+
+
+class Slice:
+    __slots__ = ("chunk", "sa", "sb", "a", "b", "lo", "hi")
+
+    def __init__(self, chunk, sa, sb, a, b, lo, hi):
+        self.chunk, self.sa, self.sb, self.a, self.b, self.lo, self.hi = chunk, sa, sb, a, b, lo, hi
+
+
+def rank_slices(plan, rank: int, world: int, n_total: int):
+    """slices (chunk, owned start frames [sa,sb), searched [a,b), stream PCM range [lo,hi)) of one rank"""
+    span = owner_span(n_total, world)
+    out = []
+    for c, (cs, cn, _) in enumerate(plan):
+        n_starts = max(cn // FRAME - T_BLOCK - 1, 0)
+        if n_starts == 0:
+            continue
+        # start frame s sits at stream position cs + s*1024; owner = position // span (last rank takes the remainder)
+        def first_s(pos):                       # smallest s with cs + s*1024 >= pos
+            return max(0, -(-(pos - cs) // FRAME))
+        sa = min(first_s(rank * span), n_starts)
+        sb = n_starts if rank == world - 1 else min(first_s((rank + 1) * span), n_starts)
+        if sb <= sa:
+            continue
+        a, b = max(sa - MARGIN, 0), min(sb + MARGIN, n_starts)
+        hi = cs + cn if b == n_starts else cs + (b + T_BLOCK + 1) * FRAME     # the last slice keeps the chunk's partial tail frame
+        out.append(Slice(c, sa, sb, a, b, cs + a * FRAME, hi))
+    return out
+
+
+def _pack(arrs) -> bytes:
+    import pickle
+    return pickle.dumps(arrs, protocol=4)
+
+
+def _unpack(b: bytes):
+    import pickle
+    return pickle.loads(b)
+
+
+def allgather_bytes(payload: bytes, device=None):
+    """bytes from every rank (tensor collectives: works on NCCL and gloo)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [payload]
+    world = dist.get_world_size()
+    dev = device if device is not None else torch.device("cpu")
+    size = torch.tensor([len(payload)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    cap = max(int(max(int(s.item()) for s in sizes)), 1)
+    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    if payload:
+        buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    return [bytes(b[:int(s.item())].cpu().numpy().tobytes()) for b, s in zip(bufs, sizes)]
+
+
+class BalancedGet:
+    """One rank of the frame-balanced `get`.  `pcm` is this rank's part of the (marked) stream: a numpy array [n, ch] or a
+    device pointer, starting at stream frame `pcm_start`.  Stages alternate with gathers (see run())."""
+
+    def __init__(self, rank, world, n_total, pcm, pcm_start, pcm_frames, channels, key=None, sample_rate=44100):
+        from . import capi, hostapi as H
+        self.H, self.capi = H, capi
+        self.rank, self.world, self.n_total = rank, world, n_total
+        self.pcm, self.pcm_start, self.pcm_frames, self.ch, self.rate = pcm, pcm_start, pcm_frames, channels, sample_rate
+        self.key = bytes(key) if key is not None else bytes(16)
+        mx, ov = H.chunk_geometry(sample_rate)
+        self.plan = chunk_plan(n_total, mx, ov, sample_rate)
+        self.slices = rank_slices(self.plan, rank, world, n_total)
+        self.ctx = capi.Context.from_handle(H.engine_ctx())
+        self.slot = H.key_slot(self.key)
+        self.thr1 = H.get_param("sync_threshold2") * 0.75
+        self.n_coded = H.n_coded_bits()
+
+    # -- helpers
+    def _bind(self, sl: Slice):
+        off = sl.lo - self.pcm_start
+        n = sl.hi - sl.lo
+        assert off >= 0 and off + n <= self.pcm_frames, (off, n, self.pcm_frames)
+        if isinstance(self.pcm, np.ndarray):
+            self.ctx.pcm_bind(self.pcm[off:off + n])
+        else:
+            self.ctx.pcm_bind(int(self.pcm) + off * self.ch * 4, n, self.ch)
+
+    def _slice_of(self, chunk, start_frame):
+        for sl in self.slices:
+            if sl.chunk == chunk and sl.a <= start_frame < max(sl.b, sl.sb + 1):
+                if sl.sa <= start_frame < sl.sb or (start_frame >= sl.sb and sl.b == sl.sb) or (start_frame < sl.sa and sl.a == sl.sa):
+                    return sl
+        return None
+
+    def owner_of(self, chunk, index):
+        """rank that owns chunk-relative sample index `index` (by the start frame it falls into)"""
+        cs, cn, _ = self.plan[chunk]
+        n_starts = max(cn // FRAME - T_BLOCK - 1, 0)
+        s = min(max(index // FRAME, 0), max(n_starts - 1, 0))
+        span = owner_span(self.n_total, self.world)
+        return min((cs + s * FRAME) // span, self.world - 1)
+
+    def _my_slice(self, chunk):
+        for sl in self.slices:
+            if sl.chunk == chunk:
+                return sl
+        return None
+
+    # -- stage 1: approximate search on my slices -> peaks above an (adaptive) floor, in chunk coordinates
+    def stage_peaks(self, floors=None) -> bytes:
+        out = []
+        for sl in self.slices:
+            self._bind(sl)
+            self.ctx.sync_approx_run(self.slot, self.capi.MODE_BLOCK)
+            seq = [self.thr1, self.thr1 * 0.6, self.thr1 * 0.35, self.thr1 * 0.15, -1.0]
+            if floors and sl.chunk in floors:
+                seq = [floors[sl.chunk]]
+            for f in seq:
+                pk, n = self.ctx.sync_peaks(f, 1 << 17)
+                if n > len(pk):
+                    raise RuntimeError("too many peaks above floor %g" % f)
+                own = pk[(pk["index"] >= (sl.sa - sl.a) * FRAME) & (pk["index"] < (sl.sb - sl.a) * FRAME)].copy()
+                if len(own) >= 64 or f < 0:
+                    break
+            own["index"] += sl.a * FRAME
+            out.append((sl.chunk, f, own))
+        return _pack(out)
+
+    # -- stage 2: candidate selection per chunk from everybody's peaks (identical on every rank)
+    def stage_select(self, payloads):
+        per_chunk = {}
+        for p in payloads:
+            for chunk, floor_q, pk in _unpack(p):
+                per_chunk.setdefault(chunk, []).append((floor_q, pk))
+        self.cands, retry = {}, {}
+        for chunk, lst in per_chunk.items():
+            floor_q = max(f for f, _ in lst)
+            pk = np.concatenate([a for _, a in lst]) if lst else np.zeros(0, self.capi.SEARCH_SCORE)
+            pk = np.sort(pk, order="index")
+            sel, complete = self.H.stage_select(pk, floor_q)
+            if not complete and floor_q >= 0:
+                retry[chunk] = -1.0
+            self.cands[chunk] = sel
+        return retry            # chunks whose peak lists were too short (rare): ask for all peaks and select again
+
+    # -- stage 3: refine the candidates I own
+    def stage_refine(self) -> bytes:
+        out = []
+        for chunk, sel in self.cands.items():
+            mine = [i for i in range(len(sel)) if self.owner_of(chunk, int(sel["index"][i])) == self.rank]
+            sl = self._my_slice(chunk)
+            if not mine or sl is None:
+                continue
+            self._bind(sl)
+            part = sel[mine].copy()
+            part["index"] -= sl.a * FRAME
+            ref = self.ctx.sync_refine(part, self.slot, self.capi.MODE_BLOCK)
+            ref["index"] += sl.a * FRAME
+            out.append((chunk, np.array(mine, np.int64), ref))
+        return _pack(out)
+
+    # -- stage 4: threshold2 / n-best per chunk
+    def stage_final(self, payloads):
+        refined = {c: sel.copy() for c, sel in self.cands.items()}
+        for p in payloads:
+            for chunk, pos, ref in _unpack(p):
+                refined[chunk][pos] = ref
+        self.final = {c: self.H.stage_final(r) for c, r in refined.items()}       # (index, quality, btype) arrays
+
+    # -- stage 5: soft bits of the final scores I own
+    def stage_decode(self) -> bytes:
+        out = []
+        for chunk, (idx, q, bt) in self.final.items():
+            mine = [i for i in range(len(idx)) if self.owner_of(chunk, int(idx[i])) == self.rank]
+            sl = self._my_slice(chunk)
+            if not mine or sl is None:
+                continue
+            self._bind(sl)
+            rel = idx[mine].astype(np.int64) - sl.a * FRAME
+            # fft_range validity is decided against the CHUNK length: the slice either reaches the chunk end or is long enough
+            raw, valid = self.ctx.decode_blocks(np.maximum(rel, 0).astype(np.uint64), self.n_coded, self.slot)
+            out.append((chunk, np.array(mine, np.int64), raw, valid))
+        return _pack(out)
+
+    # -- stage 6: Viterbi jobs of all chunks, my share decoded
+    def stage_viterbi(self, payloads) -> bytes:
+        raws = {c: (np.zeros((len(v[0]), self.n_coded), np.float32), np.zeros(len(v[0]), np.int32)) for c, v in self.final.items()}
+        for p in payloads:
+            for chunk, pos, raw, valid in _unpack(p):
+                raws[chunk][0][pos] = raw
+                raws[chunk][1][pos] = valid
+        self.jobs = []                       # (chunk, code_type, pattern_type, score_btype, time, index, quality, soft)
+        for chunk in sorted(self.final):
+            idx, q, bt = self.final[chunk]
+            for j in self.H.stage_jobs(self.key, idx, q, bt, raws[chunk][0], raws[chunk][1], self.rate):
+                self.jobs.append((chunk,) + j)
+        mine = list(range(self.rank, len(self.jobs), self.world))
+        if not mine:
+            return _pack((mine, None, None))
+        bits, err = self.ctx.viterbi([self.jobs[i][7] for i in mine], [self.jobs[i][1] for i in mine])
+        return _pack((mine, bits, err))
+
+    # -- stage 7: records -> the reference's merge
+    def stage_merge(self, payloads) -> dict:
+        import struct as st
+        bits_all, err_all = {}, {}
+        for p in payloads:
+            mine, bits, err = _unpack(p)
+            for k, i in enumerate(mine):
+                bits_all[i], err_all[i] = bits[k], err[k]
+        blobs = [b"" for _ in self.plan]
+        for i, (chunk, code_type, ptype, sbt, time, index, quality, soft) in enumerate(self.jobs):
+            b = bits_all[i]
+            blobs[chunk] += st.pack("<iddQfBBdH", 0, time, quality, index, float(err_all[i]), sbt, ptype, 1.0, len(b)) + bytes(bytearray(b))
+        return self.H.merge_chunks(blobs, [p[2] for p in self.plan], self.n_total / float(self.rate), [self.key], [""])
+
+    def run(self, allgather) -> dict:
+        pay = allgather(self.stage_peaks())
+        retry = self.stage_select(pay)
+        if retry:
+            pay = allgather(self.stage_peaks(retry))
+            self.stage_select(pay)
+        self.stage_final(allgather(self.stage_refine()))
+        pay = allgather(self.stage_decode())
+        return self.stage_merge(allgather(self.stage_viterbi(pay)))

@@ -61,3 +61,34 @@ def test_pipelined_host_paths_equal_device_paths():
     assert H.get(yp.numpy()) == doc_dev
     assert H.get(want) == doc_dev
     H.set_params()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_frame_balanced_get_equals_single_process(world):
+    """every rank searches an equal share of the start frames of every chunk; per-chunk decisions are taken on the
+    gathered lists -- the merged result must be the single-process one, digit for digit."""
+    x = T.noise(700.0, 2, seed=22)
+    H.set_params(chunk_size_min=4.0)
+    y = H.add(x, T.PAYLOAD)
+    doc = H.get(y)
+    n = y.shape[0]
+    ranks = []
+    for r in range(world):
+        mx, ov = H.chunk_geometry(44100)
+        sl = S.rank_slices(S.chunk_plan(n, mx, ov), r, world, n)
+        lo, hi = min(s.lo for s in sl), max(s.hi for s in sl)
+        ranks.append(S.BalancedGet(r, world, n, y[lo:hi], lo, hi - lo, 2))
+    # lock-step simulation of the collectives
+    pay = [rk.stage_peaks() for rk in ranks]
+    retry = [rk.stage_select(pay) for rk in ranks]
+    assert all(rt == retry[0] for rt in retry)
+    if retry[0]:
+        pay = [rk.stage_peaks(retry[0]) for rk in ranks]
+        [rk.stage_select(pay) for rk in ranks]
+    pay = [rk.stage_refine() for rk in ranks]
+    [rk.stage_final(pay) for rk in ranks]
+    pay = [rk.stage_decode() for rk in ranks]
+    pay = [rk.stage_viterbi(pay) for rk in ranks]
+    docs = [rk.stage_merge(pay) for rk in ranks]
+    assert all(d == doc for d in docs)
+    H.set_params()
