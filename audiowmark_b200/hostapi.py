@@ -169,13 +169,13 @@ def get_chunk(pcm, first_chunk: bool, keys=None, names=None, n_frames=None, chan
     kb = b"".join(_key(k) for k in keys)
     name_arr = (ctypes.c_char_p * len(keys))(*[n.encode() for n in names])
     cap = 1 << 20
-    buf = (ctypes.c_ubyte * cap)()
+    buf = ctypes.create_string_buffer(cap)
     blen = ctypes.c_size_t()
     rc = load().awmh_get_chunk(kb, name_arr, ctypes.c_int(len(keys)), _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
                                ctypes.c_int(sample_rate), ctypes.c_int(1 if first_chunk else 0), buf, ctypes.c_size_t(cap), ctypes.byref(blen))
     if rc:
         raise RuntimeError("awmh_get_chunk failed (rc=%d); see stderr" % rc)
-    return bytes(buf[:blen.value])
+    return ctypes.string_at(buf, blen.value)
 
 
 def merge_chunks(blobs, time_offsets, total_seconds: float, keys=None, names=None) -> dict:
@@ -239,13 +239,13 @@ def stage_jobs(key, index, quality, btype, raw, valid, sample_rate=44100):
     raw = np.ascontiguousarray(raw, np.float32)
     valid = np.ascontiguousarray(valid, np.int32)
     cap = 64 + (len(idx) * 3 + 2) * (36 + raw.shape[1] * 8) if len(idx) else 64
-    buf = (ctypes.c_ubyte * cap)()
+    buf = ctypes.create_string_buffer(cap)
     blen, nj = ctypes.c_size_t(), ctypes.c_int()
     rc = load().awmh_stage_jobs(_key(key), _ptr(idx), _ptr(q), _ptr(bt), ctypes.c_size_t(len(idx)), _ptr(raw), _ptr(valid), ctypes.c_int(sample_rate),
                                 buf, ctypes.c_size_t(cap), ctypes.byref(blen), ctypes.byref(nj))
     if rc:
         raise RuntimeError("awmh_stage_jobs failed (%d)" % rc)
-    data = bytes(buf[:blen.value])
+    data = ctypes.string_at(buf, blen.value)
     out, pos = [], 0
     for _ in range(nj.value):
         ct, pt, sbt, _pad, time, index_, quality_, n_soft = struct.unpack_from("<BBBBdQdI", data, pos)

@@ -255,7 +255,7 @@ class BalancedGet:
             if floors and sl.chunk in floors:
                 seq = [floors[sl.chunk]]
             for f in seq:
-                pk, n = self.ctx.sync_peaks(f, 1 << 17)
+                pk, n = self.ctx.sync_peaks(f, 1 << 15 if f >= 0 else 1 << 17)
                 if n > len(pk):
                     raise RuntimeError("too many peaks above floor %g" % f)
                 own = pk[(pk["index"] >= (sl.sa - sl.a) * FRAME) & (pk["index"] < (sl.sb - sl.a) * FRAME)].copy()

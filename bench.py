@@ -183,11 +183,15 @@ def main_gpu(args):
     H.set_params(gpu_device=local)
     n_total = n * world
     mx, ov = H.chunk_geometry(RATE)
-    plan, (lo_c, hi_c), own = S.rank_ranges(n_total, rank, world, mx, ov, RATE)
+    plan = S.chunk_plan(n_total, mx, ov, RATE)
     if world == 1:
         e0, e1, ffn = 0, n, 0
     else:
-        e0, e1, ffn = S.embed_range(own[0], own[1], n_total, RATE) if own else (0, 0, 0)
+        # frame-balanced shard: this rank searches an equal share of the start frames of every chunk (S.rank_slices) and
+        # embeds exactly the PCM those slices read (+ the halo that makes its interior identical to the unsharded `add`)
+        sl = S.rank_slices(plan, rank, world, n_total)
+        own = (min(s.lo for s in sl), max(s.hi for s in sl))
+        e0, e1, ffn = S.embed_range(own[0], own[1], n_total, RATE)
     n_loc = e1 - e0                       # frames this rank embeds (its chunks + halo)
 
     # synthetic input: uniform noise at -6 dBFS, a pure function of the stream position (blocks of 2^22 frames seeded by
@@ -210,12 +214,6 @@ def main_gpu(args):
 
     stream = torch.cuda.ExternalStream(H.gpu_stream(), device=dev)
 
-    def merged(blobs):
-        """final gather of the chunk results (the job's only collective) + the reference's merge, on every rank"""
-        allb = S.gather_blobs(blobs, device=dev)
-        by_chunk = dict(b for per_rank in allb for b in per_rank)
-        return H.merge_chunks([by_chunk[c] for c in range(len(plan))], [p[2] for p in plan], n_total / float(RATE))
-
     if world == 1:
         def step_resident():
             H.add(x_dev.data_ptr(), PAYLOAD, None, y_dev.data_ptr(), n, ch)
@@ -225,23 +223,16 @@ def main_gpu(args):
             H.add(x_host.numpy(), PAYLOAD, None, y_host.numpy())
             return H.get(y_host.numpy())
     else:
-        def sharded(xp, yp, host):
-            if n_loc:
-                H.add(xp, PAYLOAD, None, yp, n_loc, ch, first_frame_number=ffn)
-            blobs = []
-            for c in range(lo_c, hi_c):
-                off = plan[c][0] - e0
-                if host:
-                    blobs.append((c, H.get_chunk(y_host.numpy()[off:off + plan[c][1]], first_chunk=(c == 0))))
-                else:
-                    blobs.append((c, H.get_chunk(y_dev.data_ptr() + off * ch * 4, first_chunk=(c == 0), n_frames=plan[c][1], channels=ch)))
-            return merged(blobs)
+        def sharded(xp, ypcm):
+            H.add(xp, PAYLOAD, None, ypcm if not isinstance(ypcm, int) else ypcm, n_loc, ch, first_frame_number=ffn)
+            job = S.BalancedGet(rank, world, n_total, ypcm, e0, n_loc, ch)
+            return job.run(lambda payload: S.allgather_bytes(payload, device=dev))
 
         def step_resident():
-            return sharded(x_dev.data_ptr(), y_dev.data_ptr(), False)
+            return sharded(x_dev.data_ptr(), y_dev.data_ptr())
 
         def step_e2e():
-            return sharded(x_host.numpy()[:max(n_loc, 1)], y_host.numpy()[:max(n_loc, 1)], True)
+            return sharded(x_host.numpy(), y_host.numpy())
 
     def check(doc):
         real = [m for m in doc["matches"] if m["quality"] > 0.35]
@@ -338,7 +329,7 @@ def main_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%g min stereo 44.1 kHz embed+detect per GPU (BASELINE.json configs[1]%s)" % (minutes, "" if minutes == 60 else ", shortened"),
                    "pcm_frames_per_gpu": n, "channels": ch, "payload_bits": 128, "get_chunks": "30 min, 134.4 s overlap",
-                   "parallelism": ("one %d h stream: `get` sharded by 30-min chunks (%d chunks), `add` by frame blocks with halo; final result gather only" % (world, len(plan))) if world > 1 else "1 GPU",
+                   "parallelism": ("one %d h stream (%d chunks): every rank owns an equal span of positions -- `add` by frame blocks with halo, `get` by start-frame slices of each chunk; 4 small result gathers, no PCM exchanged" % (world, len(plan))) if world > 1 else "1 GPU",
                    "l2": "inputs (%.2f GB per pass) larger than L2" % (n * ch * 4 / 1e9)},
         "analysis_frames_per_s": value / 1024.0,
         "payload_ok": bool(all(d[1] for d in det_all)), "detections": det_all[0][0],
