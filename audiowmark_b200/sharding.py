@@ -176,24 +176,44 @@ def _unpack(b: bytes):
     return pickle.loads(b)
 
 
-def allgather_bytes(payload: bytes, device=None):
-    """bytes from every rank (tensor collectives: works on NCCL and gloo)."""
+_AG = {}
+
+
+def allgather_bytes(payload: bytes, device=None, cap: int = 1 << 19):
+    """bytes from every rank with ONE tensor collective (works on NCCL and gloo): every rank contributes a fixed-size
+    slot [u64 length | payload | padding]; persistent device / pinned buffers.  Payloads larger than the slot fall back
+    to a second, exactly sized exchange."""
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return [payload]
     world = dist.get_world_size()
     dev = device if device is not None else torch.device("cpu")
-    size = torch.tensor([len(payload)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(size) for _ in range(world)]
-    dist.all_gather(sizes, size)
-    cap = max(int(max(int(s.item()) for s in sizes)), 1)
-    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
-    if payload:
-        buf[:len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    key = (str(dev), world, cap)
+    if key not in _AG:
+        pin = dev.type == "cuda"
+        _AG[key] = (torch.zeros(cap, dtype=torch.uint8, device=dev), torch.zeros(world * cap, dtype=torch.uint8, device=dev),
+                    torch.zeros(cap, dtype=torch.uint8, pin_memory=pin), torch.zeros(world * cap, dtype=torch.uint8, pin_memory=pin))
+    send, recv, hsend, hrecv = _AG[key]
+    n = len(payload)
+    fits = n + 8 <= cap
+    hsend[:8] = torch.frombuffer(bytearray(struct.pack("<Q", n)), dtype=torch.uint8)
+    if fits and n:
+        hsend[8:8 + n] = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    send.copy_(hsend, non_blocking=True)
+    dist.all_gather_into_tensor(recv, send)
+    hrecv.copy_(recv)
+    raw = hrecv.numpy()
+    sizes = [struct.unpack_from("<Q", raw, r * cap)[0] for r in range(world)]
+    if all(sz + 8 <= cap for sz in sizes):
+        return [raw[r * cap + 8:r * cap + 8 + sizes[r]].tobytes() for r in range(world)]
+    big = max(sizes)                                    # rare: someone had more than a slot's worth
+    buf = torch.zeros(big, dtype=torch.uint8, device=dev)
+    if n:
+        buf[:n] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
     bufs = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(bufs, buf)
-    return [bytes(b[:int(s.item())].cpu().numpy().tobytes()) for b, s in zip(bufs, sizes)]
+    return [bytes(b[:sz].cpu().numpy().tobytes()) for b, sz in zip(bufs, sizes)]
 
 
 class BalancedGet:

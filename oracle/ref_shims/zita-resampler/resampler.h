@@ -1,6 +1,5 @@
-/* Stand-in for zita-resampler's Resampler (library absent, out of scope):
- * setup() always fails so the reference reports "resampling not available"
- * (call sites src/resample.cc:80-92,233-245). */
+/* Stand-in for zita-resampler's fixed-ratio Resampler: setup() always fails, which makes the reference fall back
+ * to VResampler (src/resample.cc:80-92,233-245) -- one in-repo algorithm serves both. */
 #ifndef AWM_REF_SHIM_ZITA_RESAMPLER_H
 #define AWM_REF_SHIM_ZITA_RESAMPLER_H
 class Resampler

@@ -1,14 +1,9 @@
-/* Stand-in for zita-resampler's VResampler (see resampler.h). */
+/* Stand-in for zita-resampler's VResampler: interface of the library (absent here), algorithm of
+ * ../awm_vresampler.hh (in-repo, NOT zita's coefficients -> parity downstream of a resampler is unpinned). */
 #ifndef AWM_REF_SHIM_ZITA_VRESAMPLER_H
 #define AWM_REF_SHIM_ZITA_VRESAMPLER_H
-class VResampler
+#include "../awm_vresampler.hh"
+class VResampler : public AwmVResampler
 {
-public:
-  unsigned int inp_count = 0, out_count = 0;
-  float       *inp_data = nullptr, *out_data = nullptr;
-  int  setup (double, unsigned int, unsigned int) { return 1; }
-  int  nchan() const { return 1; }
-  int  inpsize() const { return 2; }
-  int  process() { return 1; }
 };
 #endif

@@ -106,6 +106,11 @@ lo, hi = S.assign_chunks(len(plan), dist.get_world_size())[rank]
 blobs = [(c, bytes([c]) * (100 * (c + 1) + rank)) for c in range(lo, hi)]
 allb = S.gather_blobs(blobs)
 flat = sorted((c, len(b), b[:1]) for per_rank in allb for c, b in per_rank)
+# single-collective byte gather (frame-balanced get): small and oversized payloads
+for size in (0, 10, (1 << 12) + rank):
+    got = S.allgather_bytes(bytes([rank + 1]) * size, cap=1 << 12)
+    assert [len(g) for g in got] == [size if size < (1 << 12) else (1 << 12) + r for r in range(dist.get_world_size())], [len(g) for g in got]
+    assert all(g == bytes([r + 1]) * len(g) for r, g in enumerate(got))
 assert [c for c, _, _ in flat] == list(range(len(plan))), flat
 assert all(b == bytes([c]) for c, _, b in flat)
 if rank == 0:
