@@ -4,9 +4,12 @@
 // through context-owned device memory; device pointers are used in place.  There is no CPU
 // fallback: every entry point launches the sm_100a kernels of awm_kernels.cuh or fails.
 #include "awm_kernels.cuh"
+#include "awm_speed.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <map>
+#include <thread>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -94,6 +97,12 @@ struct awm_ctx
   DevBuf blk_start, D, raw;          // decode
   DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
   DevBuf emb_in, emb_out, peaks, snr;
+
+  // resampler / speed scan
+  struct CoefTab { DevBuf buf; int h = 0; };
+  std::map<std::pair<double, int>, CoefTab> coef_cache;          // (ratio, hlen) -> filter table
+  DevBuf rs_in, rs_out, rs_jobs;
+  DevBuf win512, sp_clip, sp_sub, sp_mags, sp_mag_jobs, sp_cmp_jobs, sp_best;
 };
 
 namespace {
@@ -255,9 +264,12 @@ awm_destroy (awm_ctx *ctx)
   DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt,
                      &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
                      &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
-                     &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr };
+                     &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr, &ctx->rs_in, &ctx->rs_out, &ctx->rs_jobs,
+                     &ctx->win512, &ctx->sp_clip, &ctx->sp_sub, &ctx->sp_mags, &ctx->sp_mag_jobs, &ctx->sp_cmp_jobs, &ctx->sp_best };
   for (DevBuf *b : bufs)
     b->release();
+  for (auto& ct : ctx->coef_cache)
+    ct.second.buf.release();
   for (auto& pf : ctx->pref)
     {
       pf.buf.release();
@@ -1098,3 +1110,273 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits,
 }
 
 } // extern "C"
+
+/* ---------------------------------------------------------------- resampler */
+
+namespace {
+
+double
+rs_sinc (double x)
+{
+  x = fabs (x);
+  if (x < 1e-9)
+    return 1;
+  x *= M_PI;
+  return sin (x) / x;
+}
+
+double
+rs_window (double x)        /* three-term cosine window on [-1, 1] */
+{
+  x = fabs (x);
+  if (x >= 1)
+    return 0;
+  x *= M_PI;
+  return 0.384 + 0.5 * cos (x) + 0.116 * cos (2 * x);
+}
+
+/* filter table for one conversion ratio: g(d) = fc sinc (fc d) w (d / h), fc = min (1, ratio), h = ceil (hlen / fc) input
+ * frames to each side; row p holds the 2h taps for a fractional position of p / 256.  Built on the host in double (a
+ * few ms, cached per ratio) so that every implementation that evaluates the same formula has the same float table. */
+int
+coef_table (awm_ctx *ctx, double ratio, int hlen, const float **coef, int *h_out)
+{
+  if (!(ratio > 1.0 / 64 && ratio < 64) || hlen < 8 || hlen > 96)
+    return fail (ctx, "resampler: ratio %g / hlen %d not supported", ratio, hlen);
+  auto key = std::make_pair (ratio, hlen);
+  auto it = ctx->coef_cache.find (key);
+  if (it == ctx->coef_cache.end())
+    {
+      if (ctx->coef_cache.size() >= 1024)          /* data dependent ratios accumulate in long running hosts */
+        {
+          CK (cudaStreamSynchronize (ctx->stream));
+          for (auto& ct : ctx->coef_cache)
+            ct.second.buf.release();
+          ctx->coef_cache.clear();
+        }
+      const double fc = ratio < 1 ? ratio : 1;
+      const int h = int (ceil (hlen / fc));
+      const int taps = 2 * h, rows = kResamplePhases + 1;
+      std::vector<float> tab (size_t (rows) * taps);
+      auto fill = [&] (int p0, int p1)
+        {
+          for (int p = p0; p < p1; p++)
+            for (int j = 0; j < taps; j++)
+              {
+                const double d = (j - (h - 1)) - double (p) / kResamplePhases;
+                tab[size_t (p) * taps + j] = float (fc * rs_sinc (fc * d) * rs_window (d / h));
+              }
+        };
+      const int n_thr = 8;
+      std::vector<std::thread> thr;
+      for (int t = 0; t < n_thr; t++)
+        thr.emplace_back (fill, rows * t / n_thr, rows * (t + 1) / n_thr);
+      for (auto& t : thr)
+        t.join();
+      awm_ctx::CoefTab& ct = ctx->coef_cache[key];
+      ct.h = h;
+      CK (ct.buf.reserve (tab.size() * sizeof (float)));
+      CK (cudaMemcpy (ct.buf.p, tab.data(), tab.size() * sizeof (float), cudaMemcpyHostToDevice));
+      it = ctx->coef_cache.find (key);
+    }
+  *coef = it->second.buf.as<float>();
+  *h_out = it->second.h;
+  return 0;
+}
+
+int
+launch_resample (awm_ctx *ctx, const std::vector<ResampleJob>& jobs, int channels)
+{
+  if (jobs.empty())
+    return 0;
+  long long max_out = 0;
+  for (const auto& j : jobs)
+    max_out = std::max (max_out, j.n_out);
+  if (max_out == 0)
+    return 0;
+  CK (ctx->rs_jobs.reserve (jobs.size() * sizeof (ResampleJob)));
+  CK (cudaMemcpyAsync (ctx->rs_jobs.p, jobs.data(), jobs.size() * sizeof (ResampleJob), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));             /* jobs is a caller-owned host vector */
+  const dim3 grid (unsigned (std::min<long long> ((max_out + 255) / 256, 1 << 20)), unsigned (jobs.size()));
+  PROF (ctx);
+  if (channels == 2)
+    k_resample<2><<<grid, 256, 0, ctx->stream>>> (ctx->rs_jobs.as<ResampleJob>(), channels);
+  else if (channels == 1)
+    k_resample<1><<<grid, 256, 0, ctx->stream>>> (ctx->rs_jobs.as<ResampleJob>(), channels);
+  else
+    k_resample<0><<<grid, 256, 0, ctx->stream>>> (ctx->rs_jobs.as<ResampleJob>(), channels);
+  LAUNCH_CHECK ("k_resample");
+  return 0;
+}
+
+} // namespace
+
+int
+awm_resample (awm_ctx *ctx, const float *in, size_t n_in, int channels, double ratio, int hlen, float *out, size_t n_out)
+{
+  if (channels <= 0 || (n_in && !in) || (n_out && !out))
+    return fail (ctx, "awm_resample: bad arguments");
+  if (n_out == 0)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  const float *coef;
+  int h;
+  if (coef_table (ctx, ratio, hlen, &coef, &h))
+    return 1;
+  const bool in_dev = n_in == 0 || is_device_ptr (in), out_dev = is_device_ptr (out);
+  ResampleJob J;
+  J.in = in;
+  J.out = out;
+  if (!in_dev)
+    {
+      CK (ctx->rs_in.reserve (n_in * channels * sizeof (float)));
+      CK (cudaMemcpyAsync (ctx->rs_in.p, in, n_in * channels * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
+      J.in = ctx->rs_in.as<float>();
+    }
+  if (!out_dev)
+    {
+      CK (ctx->rs_out.reserve (n_out * channels * sizeof (float)));
+      J.out = ctx->rs_out.as<float>();
+    }
+  J.n_in = (long long) n_in;
+  J.n_out = (long long) n_out;
+  J.step = 1.0 / ratio;
+  J.h = h;
+  J.coef = coef;
+  if (launch_resample (ctx, { J }, channels))
+    return 1;
+  if (!out_dev)
+    {
+      CK (cudaMemcpyAsync (out, J.out, n_out * channels * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaStreamSynchronize (ctx->stream));
+    }
+  return 0;
+}
+
+/* ---------------------------------------------------------------- speed scan */
+
+int
+awm_speed_scan (awm_ctx *ctx, int key_slot, const float *clip, size_t clip_frames, int channels, int sample_rate,
+                double seconds, const double *centers, int n_centers, const double *relative_speeds, int n_relative,
+                double water_delta, double *quality_out)
+{
+  if (key_slot < 0 || key_slot >= AWM_MAX_KEYS || channels <= 0 || !clip || !centers || !relative_speeds || !quality_out || n_centers < 0 || n_relative < 0)
+    return fail (ctx, "awm_speed_scan: bad arguments");
+  SyncTab& t = ctx->keys[key_slot].sync[AWM_MODE_BLOCK];
+  const int fpb = ctx->keys[key_slot].fpb;
+  if (!t.n_ent || !fpb)
+    return fail (ctx, "awm_speed_scan: tables for key slot %d not set", key_slot);
+  if (t.n_ent > kCmpMaxEntries)
+    return fail (ctx, "awm_speed_scan: %d sync entries exceed the kernel limit %d", t.n_ent, kCmpMaxEntries);
+  const size_t n_jobs = size_t (n_centers) * n_relative;
+  for (size_t i = 0; i < n_jobs; i++)
+    quality_out[i] = 0;
+  if (!n_jobs)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  if (!ctx->win512.p)
+    {
+      /* FFTAnalyzer::gen_normalized_window (sub_frame_size), src/wmcommon.cc:68-89 */
+      std::vector<float> win (kSpeedFrame);
+      double weight = 0;
+      for (int i = 0; i < kSpeedFrame; i++)
+        {
+          const double w = window_cos ((i - kSpeedFrame / 2.0) / (kSpeedFrame / 2.0));
+          win[i] = w;
+          weight += w;
+        }
+      for (int i = 0; i < kSpeedFrame; i++)
+        win[i] *= 2.0 / weight;
+      CK (ctx->win512.reserve (win.size() * sizeof (float)));
+      CK (cudaMemcpy (ctx->win512.p, win.data(), win.size() * sizeof (float), cudaMemcpyHostToDevice));
+    }
+  const float *d_clip = clip;
+  if (!is_device_ptr (clip))
+    {
+      CK (ctx->sp_clip.reserve (clip_frames * channels * sizeof (float)));
+      CK (cudaMemcpyAsync (ctx->sp_clip.p, clip, clip_frames * channels * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
+      d_clip = ctx->sp_clip.as<float>();
+    }
+  /* geometry per centre: resample_ratio_truncate (in_data, center / 2, ..., seconds / center), src/wmspeed.cc:206 + src/resample.cc:100-125 */
+  std::vector<ResampleJob> rj (n_centers);
+  std::vector<MagJob> mj (n_centers);
+  std::vector<CmpJob> cj (n_jobs);
+  size_t sub_total = 0, mag_total = 0;
+  int max_rows = 0;
+  for (int c = 0; c < n_centers; c++)
+    {
+      const double ratio = centers[c] / 2;
+      const float *coef;
+      int h;
+      if (coef_table (ctx, ratio, 16, &coef, &h))
+        return 1;
+      const double max_in_seconds = seconds / centers[c];
+      size_t in_trunc = clip_frames;
+      if (max_in_seconds > 0)
+        in_trunc = std::min<size_t> (in_trunc, size_t (lrint (sample_rate * max_in_seconds)));
+      const long long n_sub = lrint (double (in_trunc) * ratio);
+      const int rows = n_sub > kSpeedFrame ? int ((n_sub - kSpeedFrame + kSpeedHop - 1) / kSpeedHop) : 0;
+      rj[c].in = d_clip;
+      rj[c].n_in = (long long) in_trunc;
+      rj[c].n_out = n_sub;
+      rj[c].step = 1.0 / ratio;
+      rj[c].h = h;
+      rj[c].coef = coef;
+      mj[c].n_sub = n_sub;
+      mj[c].rows = rows;
+      sub_total += size_t (n_sub) * channels;
+      mag_total += size_t (rows) * t.n_ent;
+      max_rows = std::max (max_rows, rows);
+    }
+  CK (ctx->sp_sub.reserve (std::max<size_t> (sub_total, 1) * sizeof (float)));
+  CK (ctx->sp_mags.reserve (std::max<size_t> (mag_total, 1) * sizeof (float2)));
+  {
+    size_t so = 0, mo = 0;
+    for (int c = 0; c < n_centers; c++)
+      {
+        rj[c].out = ctx->sp_sub.as<float>() + so;
+        mj[c].sub = rj[c].out;
+        mj[c].mags = ctx->sp_mags.as<float2>() + mo;
+        so += size_t (rj[c].n_out) * channels;
+        mo += size_t (mj[c].rows) * t.n_ent;
+        for (int r = 0; r < n_relative; r++)
+          {
+            CmpJob& J = cj[size_t (c) * n_relative + r];
+            const double rs = relative_speeds[size_t (c) * n_relative + r];
+            J.mags = mj[c].mags;
+            J.rows = mj[c].rows;
+            J.inv = 1 / rs;                              /* relative_speed_inv, src/wmspeed.cc:274 */
+            J.off_scale = (1 << 16) / rs;                /* src/wmspeed.cc:341 */
+          }
+      }
+  }
+  if (launch_resample (ctx, rj, channels))
+    return 1;
+  CK (ctx->sp_mag_jobs.reserve (mj.size() * sizeof (MagJob)));
+  CK (ctx->sp_cmp_jobs.reserve (cj.size() * sizeof (CmpJob)));
+  CK (ctx->sp_best.reserve (n_jobs * sizeof (unsigned long long)));
+  CK (cudaMemcpyAsync (ctx->sp_mag_jobs.p, mj.data(), mj.size() * sizeof (MagJob), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaMemcpyAsync (ctx->sp_cmp_jobs.p, cj.data(), cj.size() * sizeof (CmpJob), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaMemsetAsync (ctx->sp_best.p, 0, n_jobs * sizeof (unsigned long long), ctx->stream));
+  if (max_rows > 0)
+    {
+      if (set_smem (ctx, k_speed_mags, kMagSmemBytes)) return 1;
+      const dim3 grid (unsigned ((max_rows + kMagRows - 1) / kMagRows), unsigned (n_centers));
+      PROF (ctx);
+      k_speed_mags<<<grid, kMagWarps * 32, kMagSmemBytes, ctx->stream>>> (ctx->sp_mag_jobs.as<MagJob>(), channels, t.ent.as<awm_sync_entry>(), t.n_ent,
+                                                                          ctx->tw.as<float2>(), ctx->win512.as<float>());
+      LAUNCH_CHECK ("k_speed_mags");
+      /* SpeedSync::compare: offsets -pad_start .. -1, pad_start = one block + one frame in search steps (src/wmspeed.cc:331) */
+      const int pad_start = fpb * 4 + 4;
+      const double norm_div = water_delta < 0.080 ? water_delta : 0.080;
+      const dim3 cgrid (unsigned ((pad_start + 255) / 256), unsigned (n_jobs));
+      PROF (ctx);
+      k_speed_compare<<<cgrid, 256, 0, ctx->stream>>> (ctx->sp_cmp_jobs.as<CmpJob>(), t.ent.as<awm_sync_entry>(), t.off.as<int>(), t.n_bits, t.n_ent,
+                                                       fpb, pad_start, norm_div, ctx->sp_best.as<unsigned long long>());
+      LAUNCH_CHECK ("k_speed_compare");
+    }
+  static_assert (sizeof (double) == sizeof (unsigned long long), "quality bits");
+  CK (cudaMemcpyAsync (quality_out, ctx->sp_best.p, n_jobs * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  return 0;
+}

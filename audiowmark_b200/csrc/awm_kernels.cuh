@@ -420,9 +420,9 @@ k_sync_quality (const float *__restrict__ ud, const int *__restrict__ cnt, int n
       if (umag == 0 || dmag == 0)
         raw_bit = 0;
       else if (umag < dmag)
-        raw_bit = 1 - double (umag) / double (dmag);
+        raw_bit = __fsub_rn (1.0f, __fdiv_rn (umag, dmag));      // float arithmetic as in src/syncfinder.cc:107
       else
-        raw_bit = double (dmag) / double (umag) - 1;
+        raw_bit = __fsub_rn (__fdiv_rn (dmag, umag), 1.0f);
       sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * cnt[o];
       bit_count += cnt[o];
     }

@@ -171,6 +171,27 @@ int awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size
 int awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits, const int *block_types,
                  int hard, uint8_t *bits_out, float *error_out);
 
+/* ---- resampler: process_resampler / resample / resample_ratio_truncate (src/resample.cc:27-131) -------------
+ * The reference delegates to zita-resampler (third party, not part of its tree); this library defines the filter itself:
+ *   out[n] = sum_i in[i] g (i - n / ratio),   g (d) = fc sinc (fc d) w (d / h),   fc = min (1, ratio),   h = ceil (hlen / fc),
+ *   w = 0.384 + 0.5 cos (pi x) + 0.116 cos (2 pi x) on [-1, 1];  256 phases, linear interpolation between phase rows,
+ *   float accumulation in tap order; in is zero outside [0, n_in), outputs whose taps would pass h frames beyond the
+ *   input are 0 (where a streaming resampler fed h - 1 frames of pre-roll and h of post-roll stops).
+ * in/out: interleaved, host or device.  hlen = 16 everywhere in the reference.
+ */
+int awm_resample (awm_ctx *ctx, const float *in, size_t n_in, int channels, double ratio, int hlen, float *out, size_t n_out);
+
+/* ---- speed detection scan: SpeedSync::prepare_mags + SpeedSync::compare (src/wmspeed.cc:203-375) ------------------
+ * clip = the audio SpeedSearch::get_jobs cut out (get_speed_clip, :33-52).  For every centre speed the clip is
+ * truncated to seconds / centre, resampled by centre / 2, turned into the MagMatrix (512-point spectra, hop 128), and
+ * scored for n_relative relative speeds (relative_speeds[c * n_relative + r] = pow (step, p) * speed / centre, :173).
+ * quality_out[c * n_relative + r] = Score::quality of that compare() call (0 if no offset had data).
+ * Uses the BLOCK mode sync table of key_slot (awm_set_sync_tables) and frames_per_block of awm_set_mix_tables.
+ */
+int awm_speed_scan (awm_ctx *ctx, int key_slot, const float *clip, size_t clip_frames, int channels, int sample_rate,
+                    double seconds, const double *centers, int n_centers, const double *relative_speeds, int n_relative,
+                    double water_delta, double *quality_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -916,11 +916,18 @@ class ResultSet:                                     # wmget.cc:163-474
                                           p.sync_score.block_type, bit_vec_to_str(p.bit_vec)))
 
     def lines(self):                                 # print() wmget.cc:384-441
-        out, last_key = [], ""
+        out, last_key, print_speed = [], "", True
         for p in self.patterns:
             if p.key.name != last_key:
                 out.append("key %s" % p.key.name)
                 last_key = p.key.name
+                print_speed = True                   # one speed per key (wmget.cc:391-406)
+            if print_speed:
+                for q in self.patterns:
+                    if q.key == p.key and q.speed != 1:
+                        out.append("speed %.6f" % q.speed)
+                        break
+                print_speed = False
             if p.type == TYPE_ALL:
                 out.append("pattern   all %s %.3f %.3f%s" % (bit_vec_to_str(p.bit_vec), p.sync_score.quality, p.decode_error, " SPEED" if p.speed != 1 else ""))
             else:
@@ -957,7 +964,7 @@ class RawBits:
     block_type: int
 
 
-def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=44100, trace: dict | None = None):
+def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=44100, trace: dict | None = None, speed=1.0):
     """BlockDecoder::run (wmget.cc:502-706) for one key."""
     sf = SyncFinder(P)
     stages = {} if trace is not None else None
@@ -973,7 +980,7 @@ def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=
             continue
         prv.append(RawBits(sc.index, sc.quality, raw, sc.block_type))
         bits, err = conv_decode_soft(sc.block_type, normalize_soft_bits(raw, P))
-        result_set.add_pattern(key, sc.index / rate, sc, bits, err, TYPE_BLOCK)
+        result_set.add_pattern(key, sc.index / rate, sc, bits, err, TYPE_BLOCK, speed)
     if trace is not None:
         trace["raw_bits"] = prv
     # AB (:554-604)
@@ -990,7 +997,7 @@ def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=
                 ab = np.empty(len(a.raw) * 2, dtype=np.float32)
                 ab[0::2], ab[1::2] = a.raw, b.raw
                 bits, err = conv_decode_soft(AB, normalize_soft_bits(ab, P))
-                result_set.add_pattern(key, b.index / rate, Score(b.index, (a.quality + b.quality) / 2, AB), bits, err, TYPE_BLOCK)
+                result_set.add_pattern(key, b.index / rate, Score(b.index, (a.quality + b.quality) / 2, AB), bits, err, TYPE_BLOCK, speed)
     # all (:606-701)
     best_all = []
 
@@ -1034,7 +1041,7 @@ def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=
         raw_all[1::2] = raw_all[1::2] / np.float32(max(norm[1], 1))
         q /= norm[0] + norm[1]
         bits, err = conv_decode_soft(AB, normalize_soft_bits(raw_all, P))
-        result_set.add_pattern(key, 0.0, Score(0, q, A), bits, err, TYPE_ALL)
+        result_set.add_pattern(key, 0.0, Score(0, q, A), bits, err, TYPE_ALL, speed)
     return sync_scores
 
 
@@ -1042,7 +1049,7 @@ def round_half_even(x):
     return np.rint(x)     # lrint with the default rounding mode
 
 
-def clip_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=44100):
+def clip_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=44100, speed=1.0):
     """ClipDecoder::run (wmget.cc:764-884) for one key."""
     fpb = frames_per_block(P)
     n, nch = samples.shape
@@ -1076,7 +1083,7 @@ def clip_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=4
             else:
                 raw[0::2], raw[1::2] = r2, r1
             bits, err = conv_decode_soft(AB, normalize_soft_bits(raw, P))
-            result_set.add_pattern(key, time_offset, Score(int(time_offset * rate), sc.quality, sc.block_type), bits, err, TYPE_CLIP)
+            result_set.add_pattern(key, time_offset, Score(int(time_offset * rate), sc.quality, sc.block_type), bits, err, TYPE_CLIP, speed)
 
 
 def chunk_ranges(n_frames: int, P: Params, rate=44100):
@@ -1103,15 +1110,243 @@ def chunk_ranges(n_frames: int, P: Params, rate=44100):
     return out
 
 
-def get_watermark(samples, key_list, P: Params | None = None, rate=44100) -> ResultSet:
-    """get_watermark / decode (wmget.cc:886-939,971-1013) without speed detection."""
+# --------------------------------------------------------------------------- resampler
+
+def resample_ratio(samples: np.ndarray, ratio: float, n_out: int | None = None, hlen: int = 16) -> np.ndarray:
+    """resample_ratio / resample (resample.cc:52-131): out has lrint(n * ratio) frames (or n_out)."""
+    samples = np.ascontiguousarray(samples, dtype=np.float32)
+    n, nch = samples.shape
+    if n_out is None:
+        n_out = int(np.rint(n * ratio))
+    out = np.zeros((n_out, nch), np.float32)
+    rc = lib().orc_resample(_p(samples), ctypes.c_int64(n), ctypes.c_int(nch), ctypes.c_double(ratio), ctypes.c_int(hlen),
+                            _p(out), ctypes.c_int64(n_out))
+    assert rc == 0, "resampler setup failed for ratio %r" % ratio
+    return out
+
+
+def resample(samples: np.ndarray, old_rate: int, new_rate: int) -> np.ndarray:      # resample.cc:52-95
+    return resample_ratio(samples, float(new_rate) / old_rate)
+
+
+def stream_out_count(n_in: int, ratio: float, hlen: int = 16) -> int:
+    """frames a streaming resampler (BufferedResamplerImpl: write_frames ... write_trailing_frames, resample.cc:133-215)
+    delivers for n_in input frames: every output whose taps fit into pre-roll + input + post-roll."""
+    fc = min(1.0, ratio)
+    h = int(math.ceil(hlen / fc))
+    step = 1.0 / ratio
+    n = max(int(n_in * ratio) - 2, 0)
+    while math.floor((h - 1) + float(n) * step) <= n_in + h - 2:
+        n += 1
+    return n
+
+
+def resample_stream(samples: np.ndarray, old_rate: int, new_rate: int) -> np.ndarray:
+    """what WavChunkLoader (wavchunkloader.cc:66-73,196-221) hands on for an input that is not at the watermark rate"""
+    ratio = float(new_rate) / old_rate
+    return resample_ratio(samples, ratio, stream_out_count(samples.shape[0], ratio))
+
+
+def resample_ratio_truncate(samples, rate, ratio, max_in_seconds):                   # resample.cc:97-125
+    n = samples.shape[0]
+    if max_in_seconds > 0:
+        n = min(n, int(np.rint(rate * max_in_seconds)))
+    return resample_ratio(samples[:n], ratio)
+
+
+# --------------------------------------------------------------------------- speed detection (wmspeed.cc)
+
+@dataclass
+class SpeedScanParams:                               # wmspeed.cc:54-60
+    seconds: float
+    step: float
+    n_steps: int
+    n_center_steps: int = 0
+
+
+def get_speed_clip(location, samples, rate, clip_seconds):          # wmspeed.cc:33-52
+    n = samples.shape[0]
+    end_sec = float(n) / rate
+    start_sec = location * (end_sec - clip_seconds)
+    if start_sec < 0:
+        start_sec = 0
+    start_point = int(start_sec * rate)
+    end_point = min(int(start_point + clip_seconds * rate), n)
+    return samples[start_point:end_point]
+
+
+def get_clip_locations(key: Key, samples, n):                        # wmspeed.cc:533-552
+    rng = Random(key, 0, STREAM_SPEED_CLIP)
+    flat = samples.reshape(-1)
+    idx, pos, size = [], 0, flat.shape[0]
+    while pos < size:
+        idx.append(pos)
+        pos += rng() % 1000
+    xs = np.ascontiguousarray(flat[np.array(idx, np.int64)], dtype=np.float32)
+    import hashlib
+    seed = struct.unpack(">Q", hashlib.sha1(xs.tobytes()).digest()[:8])[0]     # Random::seed_from_hash, random.cc:184-190
+    rng.seed(seed, STREAM_SPEED_CLIP)
+    return [rng.random_double() for _ in range(n)]
+
+
+def get_best_clip_location(key: Key, samples, rate, seconds, candidates):       # wmspeed.cc:554-575
+    clip_location, best_energy = 0.0, 0.0
+    for location in get_clip_locations(key, samples, candidates):
+        wd = get_speed_clip(location, samples, rate, seconds).reshape(-1)
+        sq = (wd * wd).astype(np.float64)            # float product, double running sum
+        energy = float(np.cumsum(sq)[-1]) if sq.size else 0.0
+        if energy > best_energy:
+            best_energy, clip_location = energy, location
+    return clip_location
+
+
+def speed_sync_entries(key: Key, P: Params):
+    """SpeedSync constructor (wmspeed.cc:144-161): BLOCK sync entries of all bits, sorted by frame."""
+    sb = get_sync_bits(key, BLOCK, P)
+    n = len(sb.frame)
+    bit = np.zeros(n, np.int32)
+    for b in range(P.sync_bits):
+        bit[sb.off[b]:sb.off[b + 1]] = b
+    order = np.argsort(sb.frame, kind="stable")
+    up = sb.up.reshape(n, -1)[order]
+    down = sb.down.reshape(n, -1)[order]
+    return (np.ascontiguousarray(sb.frame[order], np.int32), np.ascontiguousarray(bit[order], np.int32),
+            np.ascontiguousarray(up, np.int32), np.ascontiguousarray(down, np.int32))
+
+
+def speed_prepare_mags(clip, rate, center, seconds, entries):                   # SpeedSync::prepare_mags, wmspeed.cc:203-268
+    frame, bit, up, down = entries
+    sub = resample_ratio_truncate(clip, rate, center / 2, seconds / center)
+    L = lib()
+    L.orc_speed_rows.restype = ctypes.c_int64
+    rows = int(L.orc_speed_rows(ctypes.c_int64(sub.shape[0])))
+    mags = np.zeros((len(frame), rows, 2), np.float32)
+    window = gen_normalized_window(512)
+    L.orc_speed_mags(_p(sub), ctypes.c_int64(sub.shape[0]), ctypes.c_int(sub.shape[1]), _p(window), ctypes.c_int(len(frame)),
+                     ctypes.c_int(up.shape[1]), _p(up), _p(down), _p(mags))
+    return mags
+
+
+def speed_compare(mags, entries, relative_speeds, P: Params):                   # SpeedSync::compare, wmspeed.cc:328-375
+    frame, bit, up, down = entries
+    rel = np.ascontiguousarray(relative_speeds, np.float64)
+    out = np.zeros(len(rel), np.float64)
+    lib().orc_speed_compare(_p(mags), ctypes.c_int64(mags.shape[1]), ctypes.c_int(len(frame)), _p(frame), _p(bit), ctypes.c_int(P.sync_bits),
+                            ctypes.c_int(frames_per_block(P)), _p(rel), ctypes.c_int(len(rel)), ctypes.c_double(P.water_delta), _p(out))
+    return out
+
+
+def speed_search(key: Key, samples, rate, clip_location, scan: SpeedScanParams, speeds, P: Params, trace=None):
+    """SpeedSearch::get_jobs + the job execution of run_search (wmspeed.cc:459-484, 688-722): list of (speed, quality)."""
+    clip = get_speed_clip(clip_location, samples, rate, scan.seconds * 1.3)
+    entries = speed_sync_entries(key, P)
+    scores = []
+    for speed in speeds:
+        for c in range(-scan.n_center_steps, scan.n_center_steps + 1):
+            center = speed * math.pow(scan.step, c * (scan.n_steps * 2 + 1))
+            mags = speed_prepare_mags(clip, rate, center, scan.seconds, entries)
+            rel = [math.pow(scan.step, p) * center / center for p in range(-scan.n_steps, scan.n_steps + 1)]
+            q = speed_compare(mags, entries, rel, P)
+            scores += [(r * center, float(qq)) for r, qq in zip(rel, q)]
+            if trace is not None:
+                trace.append((center, rel, [float(x) for x in q]))
+    return scores
+
+
+def select_n_best_scores(scores, n):                                            # wmspeed.cc:487-530
+    scores = sorted(scores, key=lambda s: s[0])
+
+    def get_quality(pos):
+        return scores[pos][1] if 0 <= pos < len(scores) else 0.0
+    lmax, x = [], 0
+    while x < len(scores):
+        q1, q2, q3 = get_quality(x - 1), get_quality(x), get_quality(x + 1)
+        if q1 <= q2 and q2 >= q3:
+            lmax.append(scores[x])
+            x += 1
+        x += 1
+    lmax.sort(key=lambda s: -s[1])
+    return lmax[:n]
+
+
+def score_smooth_find_best(scores, step, distance):                             # wmspeed.cc:385-419
+    scores = sorted(scores, key=lambda s: s[0])
+    sp = np.array([s[0] for s in scores], np.float64)
+    qu = np.array([s[1] for s in scores], np.float64)
+    L = lib()
+    L.orc_score_smooth_find_best.restype = ctypes.c_double
+    return float(L.orc_score_smooth_find_best(_p(sp), _p(qu), ctypes.c_int(len(sp)), ctypes.c_double(step), ctypes.c_double(distance)))
+
+
+@dataclass
+class DetectSpeedInfo:
+    speed: float = 0.0
+    quality: float = 0.0
+    accepted: bool = False
+    line: str = ""
+    clip_location: float = 0.0
+    stages: dict = field(default_factory=dict)
+
+
+def detect_speed(key: Key, samples, P: Params, rate=44100, patient=False, test_speed=-1.0) -> DetectSpeedInfo | None:
+    """detect_speed (wmspeed.cc:622-781) for one key; None for inputs shorter than 0.25 s."""
+    samples = np.ascontiguousarray(samples, dtype=np.float32)
+    if float(samples.shape[0]) / rate < 0.25:
+        return None
+    scan1 = SpeedScanParams(50, 1.00035, 11, 28) if patient else SpeedScanParams(25, 1.0007, 5, 28)
+    scan2 = SpeedScanParams(50, 1.000175, 1) if patient else SpeedScanParams(50, 1.00035, 1)
+    scan3 = SpeedScanParams(50, 1.00005, 40)
+    n_best = 15 if patient else 5
+    info = DetectSpeedInfo()
+    info.clip_location = get_best_clip_location(key, samples, rate, scan1.seconds, 5)
+    s1 = speed_search(key, samples, rate, info.clip_location, scan1, [1.0], P)
+    best = select_n_best_scores(s1, n_best)
+    s2 = speed_search(key, samples, rate, info.clip_location, scan2, [b[0] for b in best], P)
+    best1 = select_n_best_scores(s2, 1)
+    s3 = speed_search(key, samples, rate, info.clip_location, scan3, [best1[0][0]], P)
+    info.stages = {"scan1": s1, "scan2": s2, "scan3": s3}
+    info.speed = score_smooth_find_best(s3, 1 - scan3.step, 20)
+    info.quality = max([0.0] + [q for _, q in s3])
+    delta = -1.0
+    if test_speed > 0:
+        delta = 100 * abs(info.speed - test_speed) / test_speed
+    info.line = "detect_speed %f %f %.4f" % (info.speed, info.quality, delta)
+    info.accepted = info.quality > 0.4 and (info.speed < 0.9999 or info.speed > 1.0001)
+    return info
+
+
+def get_watermark(samples, key_list, P: Params | None = None, rate=44100, detect=False, patient=False, try_speed=-1.0,
+                  test_speed=-1.0, speed_lines: list | None = None) -> ResultSet:
+    """get_watermark / decode (wmget.cc:886-939,971-1013); detect / patient / try_speed = --detect-speed,
+    --detect-speed-patient, --try-speed."""
     P = P or Params()
     samples = np.ascontiguousarray(samples, dtype=np.float32)
+    if rate != P.mark_sample_rate:
+        samples = resample_stream(samples, rate, P.mark_sample_rate)
+        rate = P.mark_sample_rate
     rs = ResultSet()
     first = True
     for start, cnt, toff in chunk_ranges(samples.shape[0], P, rate):
         chunk = samples[start:start + cnt]
         crs = ResultSet()
+        if detect or patient or try_speed > 0:
+            speed_results = []
+            if detect or patient:
+                for key in key_list:
+                    info = detect_speed(key, chunk, P, rate, patient, test_speed)
+                    if info is not None:
+                        if speed_lines is not None:
+                            speed_lines.append(info.line)
+                        if info.accepted:
+                            speed_results.append((key, info.speed))
+            else:
+                speed_results = [(key, try_speed) for key in key_list]
+            for key, speed in speed_results:
+                stretched = resample_ratio(chunk, speed)
+                srate = int(P.mark_sample_rate * speed)
+                block_decoder_run(key, stretched, crs, P, srate, speed=speed)
+                if first:
+                    clip_decoder_run(key, stretched, crs, P, srate, speed=speed)
         for key in key_list:
             block_decoder_run(key, chunk, crs, P, rate)
         if first:

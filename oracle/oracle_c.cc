@@ -361,3 +361,214 @@ void orc_powf (const float *a, const float *b, float *out, int64_t n) { for (int
 void orc_hypotf (const float *a, const float *b, float *out, int64_t n) { for (int64_t i = 0; i < n; i++) out[i] = hypotf (a[i], b[i]); }
 
 } // extern "C"
+
+/* ------------------------------------------------------------------------------------------------ resampler
+ * process_resampler (src/resample.cc:27-50) driving the in-repo VResampler stand-in (ref_shims/awm_vresampler.hh --
+ * zita-resampler itself is third party and absent, see that header): k/2 - 1 frames of zero pre-roll, the input,
+ * k/2 frames of zero post-roll; outputs that cannot be produced stay 0 like the zero-initialised vector of the caller.
+ */
+#include "ref_shims/awm_vresampler.hh"
+extern "C" {
+
+int
+orc_resample (const float *in, int64_t n_in, int n_channels, double ratio, int hlen, float *out, int64_t n_out)
+{
+  AwmVResampler r;
+  if (r.setup (ratio, n_channels, hlen) != 0)
+    return 1;
+  memset (out, 0, sizeof (float) * n_out * n_channels);
+  r.out_count = n_out;
+  r.out_data = out;
+  r.inp_count = r.inpsize() / 2 - 1;
+  r.inp_data = nullptr;
+  r.process();
+  r.inp_count = n_in;
+  r.inp_data = const_cast<float *> (in);
+  r.process();
+  r.inp_count = r.inpsize() / 2;
+  r.inp_data = nullptr;
+  r.process();
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ speed detection
+ * SpeedSync::prepare_mags (src/wmspeed.cc:203-268) on the already resampled half-rate clip.
+ *   sub: [n_sub][n_channels]; window: gen_normalized_window (512); entries sorted by frame (SpeedSync ctor :156-160),
+ *   up/down: [n_ent][n_ud] band indices (bin - min_band).  mags: [n_ent][rows][2] (column major like MagMatrix :75-79).
+ * returns the number of rows.
+ */
+int64_t
+orc_speed_rows (int64_t n_sub)
+{
+  int64_t rows = 0;
+  for (int64_t ppos = 0; ppos + 512 < n_sub; ppos += 128)
+    rows++;
+  return rows;
+}
+
+void
+orc_speed_mags (const float *sub, int64_t n_sub, int n_channels, const float *window, int n_ent, int n_ud,
+                const int *up, const int *down, float *mags)
+{
+  const int sub_frame_size = 512, sub_sync_search_step = 128, min_band = 20, max_band = 100;
+  const int64_t rows = orc_speed_rows (n_sub);
+  Plans& p = plans_for (sub_frame_size);
+#pragma omp parallel for schedule(static)
+  for (int64_t row = 0; row < rows; row++)
+    {
+      const int64_t pos = row * sub_sync_search_step;
+      float in[512 + 2], out[512 + 2];
+      float fft_out_db[max_band - min_band + 1];
+      for (int i = 0; i <= max_band - min_band; i++)
+        fft_out_db[i] = 0;
+      for (int ch = 0; ch < n_channels; ch++)
+        {
+          for (int i = 0; i < sub_frame_size; i++)
+            in[i] = sub[ch + (pos + i) * n_channels] * window[i];
+          fftwf_execute_dft_r2c (p.fwd, in, (fftwf_complex *) out);
+          for (int i = min_band; i <= max_band; i++)
+            fft_out_db[i - min_band] += db_from_complex (out[i * 2], out[i * 2 + 1], -96);
+        }
+      for (int col = 0; col < n_ent; col++)
+        {
+          float umag = 0, dmag = 0;
+          for (int i = 0; i < n_ud; i++)
+            {
+              umag += fft_out_db[up[col * n_ud + i]];
+              dmag += fft_out_db[down[col * n_ud + i]];
+            }
+          mags[(int64_t (col) * rows + row) * 2] = umag;
+          mags[(int64_t (col) * rows + row) * 2 + 1] = dmag;
+        }
+    }
+}
+
+namespace {
+struct OrcBitValue { float umag = 0, dmag = 0; int count = 0; };
+struct OrcCmpState { int offset = 0; OrcBitValue bit_values[8]; };
+
+/* SpeedSync::compare_bits<BLOCK> (src/wmspeed.cc:270-326) */
+void
+orc_compare_bits (int BLOCK, std::vector<OrcCmpState>& cmp_states, double relative_speed, const float *mags, int64_t rows,
+                  int n_ent, const int *frame, const int *bit, int frames_per_block)
+{
+  const int steps_per_frame = 4, OFFSET_SHIFT = 16;
+  const double relative_speed_inv = 1 / relative_speed;
+  size_t begin = cmp_states.size(), end = cmp_states.size();
+  for (int mi = 0; mi < n_ent; mi++)
+    {
+      const int frame_offset = ((BLOCK * frames_per_block + frame[mi]) * steps_per_frame * relative_speed_inv + 0.5) * (1 << OFFSET_SHIFT);
+      while (begin > 0)
+        {
+          const int index = cmp_states[begin - 1].offset + frame_offset;
+          if (index < 0)
+            break;
+          begin--;
+        }
+      while (end > 0)
+        {
+          const int index = (cmp_states[end - 1].offset + frame_offset) >> OFFSET_SHIFT;
+          if (index < rows)
+            break;
+          end--;
+        }
+      for (size_t it = begin; it < end; it++)
+        {
+          const int index = (cmp_states[it].offset + frame_offset) >> OFFSET_SHIFT;
+          OrcBitValue& bv = cmp_states[it].bit_values[bit[mi]];
+          const float mu = mags[(int64_t (mi) * rows + index) * 2], md = mags[(int64_t (mi) * rows + index) * 2 + 1];
+          if (BLOCK & 1)
+            {
+              bv.umag += md;
+              bv.dmag += mu;
+            }
+          else
+            {
+              bv.umag += mu;
+              bv.dmag += md;
+            }
+          bv.count++;
+        }
+    }
+}
+}
+
+/* SpeedSync::compare (src/wmspeed.cc:328-375) for n_rel relative speeds on one MagMatrix; quality_out[r] = best_score.quality */
+void
+orc_speed_compare (const float *mags, int64_t rows, int n_ent, const int *frame, const int *bit, int n_sync_bits, int frames_per_block,
+                   const double *relative_speeds, int n_rel, double water_delta, double *quality_out)
+{
+#pragma omp parallel for schedule(dynamic)
+  for (int r = 0; r < n_rel; r++)
+    {
+      const double relative_speed = relative_speeds[r];
+      const int steps_per_frame = 4;
+      const int pad_start = frames_per_block * steps_per_frame + steps_per_frame;
+      std::vector<OrcCmpState> cmp_states;
+      for (int offset = -pad_start; offset < 0; offset++)
+        {
+          OrcCmpState cs;
+          cs.offset = offset * ((1 << 16) / relative_speed);
+          cmp_states.push_back (cs);
+        }
+      orc_compare_bits (0, cmp_states, relative_speed, mags, rows, n_ent, frame, bit, frames_per_block);
+      orc_compare_bits (1, cmp_states, relative_speed, mags, rows, n_ent, frame, bit, frames_per_block);
+      orc_compare_bits (2, cmp_states, relative_speed, mags, rows, n_ent, frame, bit, frames_per_block);
+      double best_quality = 0;
+      for (const auto& cs : cmp_states)
+        {
+          double sync_quality = 0;
+          int bit_count = 0;
+          for (int b = 0; b < n_sync_bits; b++)
+            {
+              const OrcBitValue& bv = cs.bit_values[b];
+              /* SyncFinder::bit_quality (src/syncfinder.cc:94-114) */
+              double raw_bit;
+              if (bv.umag == 0 || bv.dmag == 0)
+                raw_bit = 0;
+              else if (bv.umag < bv.dmag)
+                raw_bit = 1 - bv.umag / bv.dmag;
+              else
+                raw_bit = bv.dmag / bv.umag - 1;
+              sync_quality += ((b & 1) ? raw_bit : -raw_bit) * bv.count;
+              bit_count += bv.count;
+            }
+          if (bit_count)
+            {
+              sync_quality /= bit_count;
+              const double wd = water_delta < 0.080 ? water_delta : 0.080;
+              sync_quality = fabs (sync_quality / wd / 2.9);
+              if (sync_quality > best_quality)
+                best_quality = sync_quality;
+            }
+        }
+      quality_out[r] = best_quality;
+    }
+}
+
+/* score_smooth_find_best (src/wmspeed.cc:385-419); scores sorted by speed by the caller */
+double
+orc_score_smooth_find_best (const double *speeds, const double *qualities, int n, double step, double distance)
+{
+  double best_speed = 0, best_quality = 0;
+  for (double speed = speeds[0]; speed < speeds[n - 1]; speed += 0.000001)
+    {
+      double quality_sum = 0, quality_div = 0;
+      for (int i = 0; i < n; i++)
+        {
+          const double x = (speeds[i] - speed) / (step * distance);
+          const double w = fabs (x) > 1 ? 0 : 0.5 * cos (x * M_PI) + 0.5;
+          quality_sum += qualities[i] * w;
+          quality_div += w;
+        }
+      quality_sum /= quality_div;
+      if (quality_sum > best_quality)
+        {
+          best_speed = speed;
+          best_quality = quality_sum;
+        }
+    }
+  return best_speed;
+}
+
+} // extern "C"

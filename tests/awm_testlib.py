@@ -54,3 +54,29 @@ def noise(seconds, channels=2, seed=1234, amp=0.5):
 def rms(x):
     x = np.asarray(x, np.float64)
     return float(np.sqrt(np.mean(x * x))) if x.size else 0.0
+
+
+_SPEED_CACHE = {}
+
+
+def watermarked_noise(seconds, payload="f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0"):
+    """reference test signal: keyed noise (test-gen-noise), watermarked by the oracle, on the 16 bit grid"""
+    k = ("wm", seconds, payload)
+    if k not in _SPEED_CACHE:
+        x = O.int16_to_float(O.quantize_sndfile16(O.gen_noise(seconds)))
+        _SPEED_CACHE[k] = O.int16_to_float(O.quantize_sndfile16(O.embed(x, O.Key(), payload, O.Params()).samples))
+    return _SPEED_CACHE[k]
+
+
+def cli_float(v):
+    """the reference CLI parses every floating point argument with strtof (src/audiowmark.cc:188-199)"""
+    return float(np.float32(v))
+
+
+def speed_changed(seconds, speed):
+    """tests/detect-speed-test.sh input: test-change-speed = resample_ratio (1 / speed), saved as 16 bit"""
+    k = ("sp", seconds, speed)
+    if k not in _SPEED_CACHE:
+        y = watermarked_noise(seconds)
+        _SPEED_CACHE[k] = O.int16_to_float(O.quantize_sndfile16(O.resample_ratio(y, 1 / cli_float(speed))))
+    return _SPEED_CACHE[k]

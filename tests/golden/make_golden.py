@@ -91,6 +91,25 @@ def main():
         c1 = run("cmp", cut, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", "--test-cut", 882300, "--json", js)
         G["noise200"] = {"wm_sha256": sha(pcm16(wm)), "cmp_stdout": c0.stdout,
                          "cut_cmp_stdout": c1.stdout, "cut_json": json.load(open(js))}
+        # ---- speed detection (tests/detect-speed-test.sh): 30 s reference noise, watermarked, speed changed.
+        # NOTE: everything behind a resampler runs on oracle/ref_shims/awm_vresampler.hh (zita-resampler is absent).
+        run("test-gen-noise", nz, 30, 44100)
+        wm30 = os.path.join(tmp, "wm30.wav")
+        sp30 = os.path.join(tmp, "sp30.wav")
+        run("add", nz, wm30, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0")
+        G["speed30"] = {"wm_sha256": sha(pcm16(wm30)), "cases": []}
+        for speed, opt in ((0.9764, "--detect-speed"), (1.0, "--detect-speed"), (1.01, "--detect-speed"), (1.01, "--detect-speed-patient")):
+            run("test-change-speed", wm30, sp30, speed)
+            c = run("cmp", sp30, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", opt, "--test-speed", speed, "--json", js)
+            G["speed30"]["cases"].append({"speed": speed, "opt": opt, "input_sha256": sha(pcm16(sp30)), "n_frames": int(pcm16(sp30).shape[0]),
+                                          "cmp_stdout": c.stdout, "json": json.load(open(js))})
+        t = run("cmp", sp30, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", "--try-speed", 1.01, "--json", js)
+        G["speed30"]["try_speed_1.01"] = {"cmp_stdout": t.stdout, "json": json.load(open(js))}
+        # ---- sample rate (tests/sample-rate-test.sh, shortened): 44.1 kHz watermark resampled to 48 kHz, get resamples back
+        r48 = os.path.join(tmp, "r48.wav")
+        run("test-resample", wm, r48, 48000)
+        c48 = run("cmp", r48, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", "--json", js)
+        G["rate48000"] = {"input_sha256": sha(pcm16(r48)), "n_frames": int(pcm16(r48).shape[0]), "cmp_stdout": c48.stdout, "json": json.load(open(js))}
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     json.dump(G, open(out, "w"), indent=1, sort_keys=True)
     print("wrote", out, os.path.getsize(out), "bytes")

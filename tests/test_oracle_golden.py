@@ -90,3 +90,59 @@ def test_sync_after_cut_vs_reference():
     assert rs.json_doc(int(np.rint(len(y) / 44100.0))) == fmt_ref_json(g["cut_json"])
     assert "match_count 3 9" in g["cut_cmp_stdout"]
     assert rs.match_count(O.parse_payload("f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", P)) == 3
+
+
+# ---- speed detection / resampler.  zita-resampler is not part of the reference tree: reference and oracle share the
+# in-repo resampler (oracle/ref_shims/awm_vresampler.hh); everything else on this path is reference code.
+
+def test_speed_changed_input_matches_reference():
+    g = G["speed30"]
+    assert sha(O.quantize_sndfile16(T.watermarked_noise(30))) == g["wm_sha256"]
+    for c in g["cases"]:
+        y = T.speed_changed(30, c["speed"])
+        assert y.shape[0] == c["n_frames"]
+        assert sha(O.quantize_sndfile16(y)) == c["input_sha256"], c["speed"]
+
+
+@pytest.mark.parametrize("idx", [0, 2])
+def test_detect_speed_exact_vs_reference(idx):
+    """tests/detect-speed-test.sh: speed 0.9764 / 1.01, --detect-speed"""
+    c = G["speed30"]["cases"][idx]
+    assert c["opt"] == "--detect-speed"
+    y = T.speed_changed(30, c["speed"])
+    lines = []
+    rs = O.get_watermark(y, [O.Key()], P, detect=True, test_speed=T.cli_float(c["speed"]), speed_lines=lines)
+    out = "\n".join(lines + rs.lines()) + "\n"
+    want = O.parse_payload("f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", P)
+    out += "match_count %d %d\n" % (rs.match_count(want), len(rs.patterns))
+    assert out == c["cmp_stdout"][:len(out)]
+    assert rs.json_doc(int(np.rint(len(y) / 44100.0))) == fmt_ref_json(c["json"])
+
+
+def test_detect_speed_lines_other_modes_vs_reference():
+    """speed 1.0 (detected, not applied) and --detect-speed-patient at 1.01: the detect_speed line"""
+    for idx in (1, 3):
+        c = G["speed30"]["cases"][idx]
+        info = O.detect_speed(O.Key(), T.speed_changed(30, c["speed"]), P, patient=c["opt"].endswith("patient"), test_speed=T.cli_float(c["speed"]))
+        assert info.line + "\n" == c["cmp_stdout"].split("\n")[0] + "\n"
+        assert info.accepted == ("speed " in c["cmp_stdout"].replace("detect_speed", ""))
+
+
+def test_try_speed_vs_reference():
+    g = G["speed30"]["try_speed_1.01"]
+    y = T.speed_changed(30, 1.01)
+    rs = O.get_watermark(y, [O.Key()], P, try_speed=T.cli_float(1.01))
+    assert rs.json_doc(int(np.rint(len(y) / 44100.0))) == fmt_ref_json(g["json"])
+
+
+def test_get_48000_vs_reference():
+    """tests/sample-rate-test.sh (second half): the 44.1 kHz watermark resampled to 48 kHz decodes with 5 matches"""
+    g = G["rate48000"]
+    y = T.watermarked_noise(200)
+    assert sha(O.quantize_sndfile16(y)) == G["noise200"]["wm_sha256"]
+    z = O.int16_to_float(O.quantize_sndfile16(O.resample(y, 44100, 48000)))
+    assert z.shape[0] == g["n_frames"] and sha(O.quantize_sndfile16(z)) == g["input_sha256"]
+    rs = O.get_watermark(z, [O.Key()], P, rate=48000)
+    n44 = O.stream_out_count(z.shape[0], 44100 / 48000.0)
+    assert rs.json_doc(int(np.rint(n44 / 44100.0))) == fmt_ref_json(g["json"])
+    assert "match_count 5 10" in g["cmp_stdout"]
