@@ -28,6 +28,7 @@ EXPORTS = [
     "awm_profile_enable", "awm_profile_report", "awm_host_alloc", "awm_host_free",
     "awm_fft_r2c", "awm_fft_c2r", "awm_set_embed_tables", "awm_set_sync_tables", "awm_set_mix_tables",
     "awm_pcm_bind", "awm_pcm_prefetch", "awm_embed", "awm_sync_approx", "awm_sync_peaks", "awm_sync_refine", "awm_decode_blocks", "awm_viterbi",
+    "awm_resample", "awm_pcm_push_resampled", "awm_pcm_pop", "awm_copy_to_host", "awm_is_device_pointer", "awm_speed_scan",
 ]
 
 _lib = None
@@ -227,3 +228,35 @@ class Context:
         self._ck(self.lib.awm_viterbi(self.h, _ptr(raw), ctypes.c_size_t(len(jobs)), ctypes.c_int(n_msg_bits), _ptr(bt), ctypes.c_int(1 if hard else 0),
                                       _ptr(bits), _ptr(err)))
         return bits, err
+
+    def resample(self, pcm, ratio: float, n_out: int | None = None, hlen: int = 16, n_frames=None, channels=None, out=None):
+        """awm_resample: numpy [n, ch] -> numpy [n_out, ch] (n_out defaults to lrint(n * ratio)); device pointers with sizes given"""
+        if isinstance(pcm, np.ndarray):
+            pcm = np.ascontiguousarray(pcm, np.float32)
+            n_frames, channels = pcm.shape
+        if n_out is None:
+            n_out = int(np.rint(n_frames * ratio))
+        res = np.zeros((n_out, channels), np.float32) if out is None else out
+        self._ck(self.lib.awm_resample(self.h, _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels), ctypes.c_double(ratio), ctypes.c_int(hlen),
+                                       _ptr(res), ctypes.c_size_t(n_out)))
+        return res
+
+    def pcm_push_resampled(self, ratio: float, n_out: int, hlen: int = 16):
+        self._ck(self.lib.awm_pcm_push_resampled(self.h, ctypes.c_double(ratio), ctypes.c_int(hlen), ctypes.c_size_t(n_out)))
+
+    def pcm_pop(self):
+        self._ck(self.lib.awm_pcm_pop(self.h))
+
+    def speed_scan(self, clip, seconds: float, centers, relative_speeds, key_slot=0, sample_rate=44100, water_delta=0.01,
+                   n_frames=None, channels=None) -> np.ndarray:
+        """awm_speed_scan: relative_speeds [n_centers][n_rel] -> quality [n_centers][n_rel]"""
+        if isinstance(clip, np.ndarray):
+            clip = np.ascontiguousarray(clip, np.float32)
+            n_frames, channels = clip.shape
+        centers = np.ascontiguousarray(centers, np.float64).reshape(-1)
+        rel = np.ascontiguousarray(relative_speeds, np.float64).reshape(len(centers), -1)
+        out = np.zeros(rel.shape, np.float64)
+        self._ck(self.lib.awm_speed_scan(self.h, ctypes.c_int(key_slot), _ptr(clip), ctypes.c_size_t(n_frames), ctypes.c_int(channels), ctypes.c_int(sample_rate),
+                                         ctypes.c_double(seconds), _ptr(centers), ctypes.c_int(len(centers)), _ptr(rel), ctypes.c_int(rel.shape[1]),
+                                         ctypes.c_double(water_delta), _ptr(out)))
+        return out

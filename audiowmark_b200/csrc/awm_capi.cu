@@ -101,7 +101,8 @@ struct awm_ctx
   // resampler / speed scan
   struct CoefTab { DevBuf buf; int h = 0; };
   std::map<std::pair<double, int>, CoefTab> coef_cache;          // (ratio, hlen) -> filter table
-  DevBuf rs_in, rs_out, rs_jobs;
+  DevBuf rs_in, rs_out, rs_jobs, pcm_rs;
+  const float *saved_pcm = nullptr; size_t saved_frames = 0; int saved_ch = 0; bool pushed = false;
   DevBuf win512, sp_clip, sp_sub, sp_mags, sp_mag_jobs, sp_cmp_jobs, sp_best;
 };
 
@@ -264,7 +265,7 @@ awm_destroy (awm_ctx *ctx)
   DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt,
                      &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
                      &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
-                     &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr, &ctx->rs_in, &ctx->rs_out, &ctx->rs_jobs,
+                     &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr, &ctx->rs_in, &ctx->rs_out, &ctx->rs_jobs, &ctx->pcm_rs,
                      &ctx->win512, &ctx->sp_clip, &ctx->sp_sub, &ctx->sp_mags, &ctx->sp_mag_jobs, &ctx->sp_cmp_jobs, &ctx->sp_best };
   for (DevBuf *b : bufs)
     b->release();
@@ -556,6 +557,7 @@ awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, siz
   if (channels <= 0 || (!pcm && n_frames))
     return fail (ctx, "awm_pcm_bind: bad arguments");
   CK (cudaSetDevice (ctx->device));
+  ctx->pushed = false;                           // a new bind replaces whatever awm_pcm_push_resampled saved
   const bool dev = pcm && is_device_ptr (pcm);
   awm_ctx::Prefetch *hit = nullptr;
   if (!dev && pad_start == 0 && pad_end == 0)
@@ -1250,6 +1252,65 @@ awm_resample (awm_ctx *ctx, const float *in, size_t n_in, int channels, double r
       CK (cudaMemcpyAsync (out, J.out, n_out * channels * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
       CK (cudaStreamSynchronize (ctx->stream));
     }
+  return 0;
+}
+
+int
+awm_pcm_push_resampled (awm_ctx *ctx, double ratio, int hlen, size_t n_out)
+{
+  if (!ctx->pcm_ch)
+    return fail (ctx, "awm_pcm_push_resampled: no PCM bound");
+  if (ctx->pushed)
+    return fail (ctx, "awm_pcm_push_resampled: a resampled binding is already active");
+  CK (cudaSetDevice (ctx->device));
+  const float *coef;
+  int h;
+  if (coef_table (ctx, ratio, hlen, &coef, &h))
+    return 1;
+  CK (ctx->pcm_rs.reserve (std::max<size_t> (n_out, 1) * ctx->pcm_ch * sizeof (float)));
+  ResampleJob J;
+  J.in = ctx->pcm;
+  J.out = ctx->pcm_rs.as<float>();
+  J.n_in = (long long) ctx->pcm_frames;
+  J.n_out = (long long) n_out;
+  J.step = 1.0 / ratio;
+  J.h = h;
+  J.coef = coef;
+  if (launch_resample (ctx, { J }, ctx->pcm_ch))
+    return 1;
+  ctx->saved_pcm = ctx->pcm;
+  ctx->saved_frames = ctx->pcm_frames;
+  ctx->saved_ch = ctx->pcm_ch;
+  ctx->pushed = true;
+  ctx->pcm = J.out;
+  ctx->pcm_frames = n_out;
+  return 0;
+}
+
+int
+awm_pcm_pop (awm_ctx *ctx)
+{
+  if (!ctx->pushed)
+    return fail (ctx, "awm_pcm_pop: nothing to restore");
+  ctx->pcm = ctx->saved_pcm;
+  ctx->pcm_frames = ctx->saved_frames;
+  ctx->pcm_ch = ctx->saved_ch;
+  ctx->pushed = false;
+  return 0;
+}
+
+int
+awm_is_device_pointer (const void *p)
+{
+  return p && is_device_ptr (p) ? 1 : 0;
+}
+
+int
+awm_copy_to_host (awm_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+  CK (cudaSetDevice (ctx->device));
+  CK (cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
   return 0;
 }
 

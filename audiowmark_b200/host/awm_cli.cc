@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "awm_wm.hh"
+#include "awm_speed.hh"
 #include "awm_engine.hh"
 #include "awm_tables.hh"
 #include "awm_util.hh"
@@ -82,7 +83,7 @@ atof_or_die (const char *s)
 {
   char *end;
   errno = 0;
-  const double d = strtod (s, &end);
+  const float d = strtof (s, &end);          /* single precision like the reference (src/audiowmark.cc:188-199) */
   if (errno || *end || !*s)
     {
       error ("audiowmark: error during string->float conversion: %s\n", s);
@@ -332,11 +333,29 @@ parse_get_options (ArgParser& ap)
     Params::hard = true;
   if (ap.parse_opt ("--test-no-sync"))
     Params::test_no_sync = true;
-  if (ap.parse_opt ("--detect-speed") || ap.parse_opt ("--detect-speed-patient") || ap.parse_opt ("--try-speed", f))
+  int speed_options = 0;
+  if (ap.parse_opt ("--detect-speed"))
     {
-      error ("audiowmark: speed detection is not available in this build\n");
+      Params::detect_speed = true;
+      speed_options++;
+    }
+  if (ap.parse_opt ("--detect-speed-patient"))
+    {
+      Params::detect_speed_patient = true;
+      speed_options++;
+    }
+  if (ap.parse_opt ("--try-speed", f))
+    {
+      Params::try_speed = f;
+      speed_options++;
+    }
+  if (speed_options > 1)
+    {
+      error ("audiowmark: can only use one option: --detect-speed or --detect-speed-patient or --try-speed\n");
       exit (1);
     }
+  if (ap.parse_opt ("--test-speed", f))
+    Params::test_speed = f;
   if (ap.parse_opt ("--input-format", s) || ap.parse_opt ("--format", s))
     Params::input_format = parse_format (s);
   if (ap.parse_opt ("--raw-input-endian", s) || ap.parse_opt ("--raw-endian", s))   Params::raw_input_format.set_endian (parse_endian (s));
@@ -427,6 +446,44 @@ test_gen_noise (const Key& key, const string& out_file, double seconds, int rate
   for (size_t i = 0; i < n; i++)
     noise.push_back (rng.random_double() * 2 - 1);
   return save_or_complain (WavData (noise, channels, rate, bits), out_file);
+}
+
+static int
+test_speed (const Key& key, int seed)              /* src/audiowmark.cc:389-397 */
+{
+  Random rng (key, seed, Random::Stream::data_up_down);
+  const double low = 0.85, high = 1.15;
+  printf ("%.6f\n", low + (rng() / double (UINT64_MAX)) * (high - low));
+  return 0;
+}
+
+static int
+test_change_speed (const string& in_file, const string& out_file, double speed)      /* src/audiowmark.cc:419-438 */
+{
+  WavData in_data;
+  if (load_or_complain (in_data, in_file))
+    return 1;
+  vector<float> out;
+  if (!resample_ratio (in_data.samples().data(), in_data.n_frames(), in_data.n_channels(), 1 / speed, out))
+    return 1;
+  return save_or_complain (WavData (out, in_data.n_channels(), in_data.sample_rate(), in_data.bit_depth()), out_file);
+}
+
+static int
+test_resample (const string& in_file, const string& out_file, int new_rate)           /* src/audiowmark.cc:440-458 */
+{
+  WavData in_data;
+  if (load_or_complain (in_data, in_file))
+    return 1;
+  if (new_rate == in_data.sample_rate())
+    {
+      error ("audiowmark: test-resample: input already has sample rate %d\n", new_rate);
+      return 1;
+    }
+  vector<float> out;
+  if (!resample_ratio (in_data.samples().data(), in_data.n_frames(), in_data.n_channels(), double (new_rate) / in_data.sample_rate(), out))
+    return 1;
+  return save_or_complain (WavData (out, in_data.n_channels(), new_rate, in_data.bit_depth()), out_file);
 }
 
 static int
@@ -669,9 +726,28 @@ main (int argc, char **argv)
       args = parse_positional (ap, { "input_wav", "property" });
       rc = test_info (args[0], args[1]);
     }
-  else if (ap.parse_cmd ("hls-add") || ap.parse_cmd ("hls-prepare") || ap.parse_cmd ("test-change-speed") || ap.parse_cmd ("test-resample") || ap.parse_cmd ("test-speed"))
+  else if (ap.parse_cmd ("test-speed"))
     {
-      error ("audiowmark: command '%s' is not available in this build (HLS / resampling are out of scope)\n", ap.command().c_str());
+      parse_shared_options (ap);
+      Key key = parse_key (ap);
+      args = parse_positional (ap, { "seed" });
+      rc = test_speed (key, atoi_or_die (args[0].c_str()));
+    }
+  else if (ap.parse_cmd ("test-change-speed"))
+    {
+      parse_shared_options (ap);
+      args = parse_positional (ap, { "input_wav", "output_wav", "speed" });
+      rc = test_change_speed (args[0], args[1], atof_or_die (args[2].c_str()));
+    }
+  else if (ap.parse_cmd ("test-resample"))
+    {
+      parse_shared_options (ap);
+      args = parse_positional (ap, { "input_wav", "output_wav", "new_rate" });
+      rc = test_resample (args[0], args[1], atoi_or_die (args[2].c_str()));
+    }
+  else if (ap.parse_cmd ("hls-add") || ap.parse_cmd ("hls-prepare"))
+    {
+      error ("audiowmark: command '%s' is not available in this build (HLS is out of scope)\n", ap.command().c_str());
       rc = 1;
     }
   else if (!ap.remaining_args().empty())

@@ -118,3 +118,9 @@ Engine::set_embed_tables (const Key& key, const std::vector<int>& bitvec)
   g_embed_fpb_mix = sig;
   return true;
 }
+
+bool
+Engine::is_device_pointer (const void *p)
+{
+  return p && awm_is_device_pointer (p) != 0;
+}

@@ -17,4 +17,5 @@ public:
   static int      key_slot (const Key& key);   // uploads sync (BLOCK + CLIP) and mix tables on first use; -1 on error
   static bool     set_embed_tables (const Key& key, const std::vector<int>& bitvec);
   static std::string last_error();
+  static bool     is_device_pointer (const void *p);   // true if p is CUDA device (or managed) memory
 };

@@ -2,6 +2,7 @@
 // (reference src/wmget.cc:163-1013, src/wavchunkloader.cc:54-239).  FFTs, soft-bit extraction and the
 // Viterbi decoder run on the GPU through the C ABI; pairing / combining logic stays on the host.
 #include "awm_results.hh"
+#include "awm_speed.hh"
 #include "awm_engine.hh"
 #include "awm_tables.hh"
 #include "awm_util.hh"
@@ -584,20 +585,67 @@ public:
 /* decode (src/wmget.cc:886-939) for one chunk: everything up to the soft bits; the Viterbi jobs are queued */
 int
 decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vector<Key>& key_list, const float *samples, size_t n_frames,
-              int n_channels, int sample_rate, bool first_chunk)
+              int n_channels, int sample_rate, bool first_chunk, bool print_speed_results = false)
 {
   awm_ctx *ctx = Engine::ctx();
   if (!ctx)
     return 1;
-  if (Params::detect_speed || Params::detect_speed_patient || Params::try_speed > 0)
-    {
-      error ("audiowmark: speed detection / --try-speed is not supported in this build\n");
-      return 1;
-    }
   if (awm_pcm_bind (ctx, samples, n_frames, n_channels, 0, 0))
     {
       error ("audiowmark: %s\n", awm_last_error (ctx));
       return 1;
+    }
+  /* The strategy for integrating speed detection into decoding (src/wmget.cc:888-928):
+   *  - the watermark is always decoded on the original data
+   *  - if the detected speed is somewhat different from 1.0, stretched data is decoded as well
+   *  - all normal and speed results are reported (the detected speed may be wrong on short clips) */
+  if (Params::detect_speed || Params::detect_speed_patient || Params::try_speed > 0)
+    {
+      vector<DetectSpeedResult> speed_results;
+      if (Params::detect_speed || Params::detect_speed_patient)
+        speed_results = detect_speed (key_list, samples, n_frames, n_channels, sample_rate, print_speed_results);
+      else
+        for (const auto& key : key_list)
+          speed_results.push_back ({ key, Params::try_speed });
+      bool rebind = false;
+      for (const auto& speed_result : speed_results)
+        {
+          /* resample_ratio (wav_data, speed, mark_sample_rate * speed): the stretched chunk stays on the device */
+          const size_t speed_frames = lrint (double (n_frames) * speed_result.speed);
+          const int speed_rate = Params::mark_sample_rate * speed_result.speed;
+          if (rebind && awm_pcm_bind (ctx, samples, n_frames, n_channels, 0, 0))
+            return 1;
+          rebind = false;
+          if (awm_pcm_push_resampled (ctx, speed_result.speed, 16, speed_frames))
+            {
+              error ("audiowmark: %s\n", awm_last_error (ctx));
+              return 1;
+            }
+          BlockDecoder speed_block_decoder (speed_result.speed);
+          speed_block_decoder.run ({ speed_result.key }, speed_frames, n_channels, speed_rate, pending, chunk);
+          awm_pcm_pop (ctx);
+          if (first_chunk && int (speed_frames / Params::frame_size) < (mark_sync_frame_count() + mark_data_frame_count()) * 3.1)
+            {
+              /* the clip decoder cuts and pads on the host: short inputs only, so the extra copy is small */
+              vector<float> stretched;
+              const float *host_samples = samples;
+              vector<float> host_copy;
+              if (Engine::is_device_pointer (samples))
+                {
+                  host_copy.resize (n_frames * n_channels);
+                  if (awm_copy_to_host (ctx, host_copy.data(), samples, host_copy.size() * sizeof (float)))
+                    return 1;
+                  host_samples = host_copy.data();
+                }
+              if (!resample_ratio (host_samples, n_frames, n_channels, speed_result.speed, stretched))
+                return 1;
+              ClipDecoder speed_clip_decoder (speed_result.speed);
+              speed_clip_decoder.run ({ speed_result.key }, stretched.data(), speed_frames, n_channels, speed_rate, pending, chunk);
+              rebind = true;
+            }
+        }
+      if (rebind && awm_pcm_bind (ctx, samples, n_frames, n_channels, 0, 0))
+        return 1;
     }
   const double tb0 = get_time();
   BlockDecoder block_decoder (1);
@@ -649,13 +697,30 @@ chunk_geometry (int sample_rate, size_t& max_frames, size_t& overlap_frames)
 }
 
 int
-get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set)
+get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set,
+                      bool print_speed_results, size_t *mark_rate_frames)
 {
+  vector<float> resampled;
   if (sample_rate != Params::mark_sample_rate)
     {
-      error ("audiowmark: input sample rate %d: only %d Hz is supported (resampling is not available in this build)\n", sample_rate, Params::mark_sample_rate);
-      return 1;
+      /* WavChunkLoader resamples the input to the watermark rate while it reads (src/wavchunkloader.cc:66-73, 196-221) */
+      const double ratio = double (Params::mark_sample_rate) / sample_rate;
+      awm_ctx *rctx = Engine::ctx();
+      if (!rctx)
+        return 1;
+      const size_t n_out = resample_stream_frames (n_frames, ratio);
+      resampled.assign (n_out * n_channels, 0.f);
+      if (awm_resample (rctx, samples, n_frames, n_channels, ratio, 16, resampled.data(), n_out))
+        {
+          error ("audiowmark: %s\n", awm_last_error (rctx));
+          return 1;
+        }
+      samples = resampled.data();
+      n_frames = n_out;
+      sample_rate = Params::mark_sample_rate;
     }
+  if (mark_rate_frames)
+    *mark_rate_frames = n_frames;
   size_t max_frames, overlap;
   chunk_geometry (sample_rate, max_frames, overlap);
   size_t start = 0, end = min (max_frames, n_frames);
@@ -680,7 +745,7 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
           const size_t nstart = end - overlap, nend = min (nstart + max_frames, n_frames);
           awm_pcm_prefetch (ctx, samples + nstart * n_channels, nend - nstart, n_channels);
         }
-      if (decode_chunk (pending, int (time_offsets.size()), debug_sync, key_list, samples + start * n_channels, end - start, n_channels, sample_rate, first_chunk))
+      if (decode_chunk (pending, int (time_offsets.size()), debug_sync, key_list, samples + start * n_channels, end - start, n_channels, sample_rate, first_chunk, print_speed_results))
         return 1;
       time_offsets.push_back (time_offset);
       debug_syncs.push_back (debug_sync);
@@ -781,8 +846,9 @@ get_watermark (const vector<Key>& key_list, const string& infile, const string& 
         wav.mutable_samples().resize (want);
     }
   ResultSet result_set;
-  if (get_watermark_buffer (key_list, wav.samples().data(), wav.n_frames(), wav.n_channels(), wav.sample_rate(), result_set))
+  size_t mark_rate_frames = 0;
+  if (get_watermark_buffer (key_list, wav.samples().data(), wav.n_frames(), wav.n_channels(), wav.sample_rate(), result_set, !orig_bitvec.empty(), &mark_rate_frames))
     return 1;
-  const size_t time_length = lrint (wav.n_values() / double (wav.sample_rate() * wav.n_channels()));
+  const size_t time_length = lrint (mark_rate_frames / double (Params::mark_sample_rate));
   return report (result_set, time_length, orig_bitvec);
 }

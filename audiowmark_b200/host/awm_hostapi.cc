@@ -1,6 +1,7 @@
 // awm_hostapi.cc -- plain C entry points over the host-side C++ (tables, add, get) so that the parity
 // tests and bench.py can drive exactly what the CLI runs.  Table functions are pure host code (no GPU).
 #include "awm_results.hh"
+#include "awm_speed.hh"
 #include "awm_engine.hh"
 #include "awm_tables.hh"
 #include "awm_util.hh"
@@ -40,6 +41,52 @@ awmh_set_params (double water_delta, int frames_per_bit, int mix, int hard, doub
   Params::gpu_device = gpu_device;
   set_log_level (quiet ? Log::WARNING : Log::INFO);
 }
+
+/* --detect-speed / --detect-speed-patient / --try-speed / --test-speed of `audiowmark get` (src/audiowmark.cc:831-854) */
+void
+awmh_set_speed_params (int detect_speed, int detect_speed_patient, double try_speed, double test_speed)
+{
+  Params::detect_speed = detect_speed != 0;
+  Params::detect_speed_patient = detect_speed_patient != 0;
+  Params::try_speed = try_speed;
+  Params::test_speed = test_speed;
+}
+
+/* detect_speed (src/wmspeed.cc:622-781) for one key on one chunk: best speed / quality as the reference would print
+ * them, *accepted = 1 if the speed would be used for a second decode */
+int
+awmh_detect_speed (const unsigned char *key16, const float *pcm, size_t n_frames, int n_channels, int sample_rate,
+                   double *speed, double *quality, int *accepted)
+{
+  DetectSpeedInfo info;
+  const std::vector<DetectSpeedResult> r = detect_speed ({ make_key (key16, "") }, pcm, n_frames, n_channels, sample_rate, false, &info);
+  if (!info.valid)
+    return 1;
+  if (speed)
+    *speed = info.speed;
+  if (quality)
+    *quality = info.quality;
+  if (accepted)
+    *accepted = r.empty() ? 0 : 1;
+  return 0;
+}
+
+/* resample_ratio (src/resample.cc:127-131) / the streaming frame count of BufferedResamplerImpl */
+int
+awmh_resample (const float *in, size_t n_in, int n_channels, double ratio, float *out, size_t n_out)
+{
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx)
+    return 1;
+  if (awm_resample (ctx, in, n_in, n_channels, ratio, 16, out, n_out))
+    {
+      error ("audiowmark: %s\n", awm_last_error (ctx));
+      return 1;
+    }
+  return 0;
+}
+
+uint64_t awmh_resample_stream_frames (uint64_t n_in, double ratio) { return resample_stream_frames (n_in, ratio); }
 
 int awmh_frames_per_block() { return int (frames_per_block()); }
 int awmh_n_coded_bits()     { return int (code_size (ConvBlockType::a, Params::payload_size)); }
@@ -142,7 +189,8 @@ awmh_get (const unsigned char *keys16, const char *const *names, int n_keys, con
   for (int k = 0; k < n_keys; k++)
     key_list.push_back (make_key (keys16 + 16 * k, names ? names[k] : ""));
   ResultSet result_set;
-  const int rc = get_watermark_buffer (key_list, pcm, n_frames, n_channels, sample_rate, result_set);
+  size_t mark_rate_frames = n_frames;
+  const int rc = get_watermark_buffer (key_list, pcm, n_frames, n_channels, sample_rate, result_set, false, &mark_rate_frames);
   if (rc)
     return rc;
   if (n_patterns)
@@ -152,7 +200,7 @@ awmh_get (const unsigned char *keys16, const char *const *names, int n_keys, con
       char *buf = nullptr;
       size_t len = 0;
       FILE *f = open_memstream (&buf, &len);
-      result_set.print_json (f, size_t (lrint (double (n_frames) / sample_rate)));
+      result_set.print_json (f, size_t (lrint (double (mark_rate_frames) / Params::mark_sample_rate)));
       fclose (f);
       if (len + 1 > json_cap)
         {

@@ -20,7 +20,7 @@ int add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_
 
 class ResultSet;
 int get_watermark_buffer (const std::vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
-                          ResultSet& result_set);
+                          ResultSet& result_set, bool print_speed_results = false, size_t *mark_rate_frames = nullptr);
 
 /* chunk-level pieces of get_watermark_buffer for sharded runs (one process per GPU): a rank decodes some of the
  * reference's chunks (WavChunkLoader geometry) and the chunk result sets are merged in chunk order afterwards */

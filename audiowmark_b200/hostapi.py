@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames"]
 
 _lib = None
 
@@ -150,6 +150,47 @@ def get(pcm, keys=None, names=None, n_frames=None, channels=None, sample_rate=44
         raise RuntimeError("awmh_get failed (rc=%d); see stderr" % rc)
     text = buf.value.decode()
     return json.loads(text) if parse else text
+
+
+def set_speed_params(detect_speed=False, detect_speed_patient=False, try_speed=-1.0, test_speed=-1.0):
+    """--detect-speed / --detect-speed-patient / --try-speed / --test-speed of `audiowmark get`"""
+    load().awmh_set_speed_params(ctypes.c_int(int(detect_speed)), ctypes.c_int(int(detect_speed_patient)), ctypes.c_double(try_speed),
+                                 ctypes.c_double(test_speed))
+
+
+def detect_speed(pcm, key=None, n_frames=None, channels=None, sample_rate=44100):
+    """detect_speed for one key on one chunk -> (speed, quality, accepted)"""
+    if isinstance(pcm, np.ndarray):
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        n_frames, channels = pcm.shape
+    sp, q, acc = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    rc = load().awmh_detect_speed(_key(key or bytes(16)), _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels), ctypes.c_int(sample_rate),
+                                  ctypes.byref(sp), ctypes.byref(q), ctypes.byref(acc))
+    if rc:
+        raise RuntimeError("awmh_detect_speed failed (rc=%d); see stderr" % rc)
+    return sp.value, q.value, bool(acc.value)
+
+
+def resample(pcm, ratio, n_out=None, out=None, n_frames=None, channels=None):
+    """resample_ratio: numpy in -> numpy out, or device pointers with n_frames / channels / n_out given"""
+    if isinstance(pcm, np.ndarray):
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        n_frames, channels = pcm.shape
+    if n_out is None:
+        n_out = int(np.rint(n_frames * ratio))
+    res = out
+    if out is None:
+        res = np.zeros((n_out, channels), np.float32)
+    rc = load().awmh_resample(_ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels), ctypes.c_double(ratio), _ptr(res), ctypes.c_size_t(n_out))
+    if rc:
+        raise RuntimeError("awmh_resample failed (rc=%d); see stderr" % rc)
+    return res
+
+
+def resample_stream_frames(n_in, ratio):
+    L = load()
+    L.awmh_resample_stream_frames.restype = ctypes.c_uint64
+    return int(L.awmh_resample_stream_frames(ctypes.c_uint64(n_in), ctypes.c_double(ratio)))
 
 
 def chunk_geometry(sample_rate=44100):

@@ -181,6 +181,17 @@ int awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_b
  */
 int awm_resample (awm_ctx *ctx, const float *in, size_t n_in, int channels, double ratio, int hlen, float *out, size_t n_out);
 
+/* resample_ratio (wav_data, speed, ...) of decode() (src/wmget.cc:916) without leaving the device: the bound PCM is
+ * resampled by `ratio` into a context-owned buffer of n_out frames, which becomes the bound PCM; awm_pcm_pop restores
+ * the previous binding (the original chunk is not copied again).  One level only; awm_pcm_bind drops a pushed binding. */
+int awm_pcm_push_resampled (awm_ctx *ctx, double ratio, int hlen, size_t n_out);
+int awm_pcm_pop (awm_ctx *ctx);
+/* stream ordered copy device (or host) -> host for callers that keep their PCM in device memory but need a few values on
+ * the host (clip selection of detect_speed hashes a sparse subset of the samples, src/wmspeed.cc:533-552) */
+int awm_copy_to_host (awm_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* 1 if p points to CUDA device / managed memory (such pointers are used in place by the PCM entry points), else 0 */
+int awm_is_device_pointer (const void *p);
+
 /* ---- speed detection scan: SpeedSync::prepare_mags + SpeedSync::compare (src/wmspeed.cc:203-375) ------------------
  * clip = the audio SpeedSearch::get_jobs cut out (get_speed_clip, :33-52).  For every centre speed the clip is
  * truncated to seconds / centre, resampled by centre / 2, turned into the MagMatrix (512-point spectra, hop 128), and
