@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <map>
 #include <thread>
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -689,6 +690,7 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
   A.peaks = ctx->peaks.as<unsigned>();
   A.snr = snr_power ? ctx->snr.as<double>() : nullptr;
   A.snr_frames = limiter_block > 0 ? n_proc : n_real;   // frames the reference loop emits (src/wmadd.cc:539-546)
+  A.delta_only = 0;
   A.tw = ctx->tw.as<float2>();
   A.win = ctx->win.as<float>();
   A.synth = ctx->synth.as<float>();
@@ -1241,6 +1243,7 @@ awm_resample (awm_ctx *ctx, const float *in, size_t n_in, int channels, double r
       J.out = ctx->rs_out.as<float>();
     }
   J.n_in = (long long) n_in;
+  J.n_stop = J.n_in;
   J.n_out = (long long) n_out;
   J.step = 1.0 / ratio;
   J.h = h;
@@ -1272,6 +1275,7 @@ awm_pcm_push_resampled (awm_ctx *ctx, double ratio, int hlen, size_t n_out)
   J.in = ctx->pcm;
   J.out = ctx->pcm_rs.as<float>();
   J.n_in = (long long) ctx->pcm_frames;
+  J.n_stop = J.n_in;
   J.n_out = (long long) n_out;
   J.step = 1.0 / ratio;
   J.h = h;
@@ -1311,6 +1315,127 @@ awm_copy_to_host (awm_ctx *ctx, void *dst, const void *src, size_t bytes)
   CK (cudaSetDevice (ctx->device));
   CK (cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDefault, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
+  return 0;
+}
+
+/* ---------------------------------------------------------------- embed at other sample rates */
+
+int
+awm_embed_resampled (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels, int sample_rate, int mark_sample_rate,
+                     size_t n_emit, int frames_pad_start, double water_delta, int limiter_block, float limiter_ceiling, double *snr_power)
+{
+  if (!ctx->embed_fpb)
+    return fail (ctx, "awm_embed_resampled: awm_set_embed_tables has not been called");
+  if (channels <= 0 || sample_rate <= 0 || mark_sample_rate <= 0 || sample_rate == mark_sample_rate || n_emit < n_frames || (n_frames && (!in || !out)))
+    return fail (ctx, "awm_embed_resampled: bad arguments");
+  if (snr_power)
+    snr_power[0] = snr_power[1] = 0;
+  if (n_frames == 0)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  const double r_in = double (mark_sample_rate) / sample_rate, r_out = double (sample_rate) / mark_sample_rate;
+  const float *coef_in, *coef_out;
+  int h_in, h_out;
+  if (coef_table (ctx, r_in, 16, &coef_in, &h_in) || coef_table (ctx, r_out, 16, &coef_out, &h_out))
+    return 1;
+  /* watermark frames needed for the emitted output: highest tap of output n_emit - 1 */
+  const double step_out = 1.0 / r_out;
+  const long long top = (long long) floor (double (n_emit - 1) * step_out) + h_out;
+  const long long n_blocks44 = top / kFrame + 1;
+  const long long n44 = n_blocks44 * kFrame;
+  const size_t n_val = n_frames * channels;
+  const bool in_dev = is_device_ptr (in), out_dev = is_device_ptr (out);
+  const float *d_in = in;
+  float *d_out = out;
+  if (!in_dev)
+    {
+      CK (ctx->emb_in.reserve (n_val * sizeof (float)));
+      CK (cudaMemcpyAsync (ctx->emb_in.p, in, n_val * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
+      d_in = ctx->emb_in.as<float>();
+    }
+  if (!out_dev)
+    {
+      CK (ctx->emb_out.reserve (n_val * sizeof (float)));
+      d_out = ctx->emb_out.as<float>();
+    }
+  CK (ctx->rs_in.reserve (size_t (n44) * channels * sizeof (float)));       /* x44: input at the watermark rate */
+  CK (ctx->rs_out.reserve (size_t (n44) * channels * sizeof (float)));      /* wm44: watermark signal at the watermark rate */
+  CK (ctx->pcm_rs.reserve (n_emit * channels * sizeof (float)));            /* watermark at the input rate */
+  ctx->pushed = false;
+  ctx->pcm_ch = ctx->pcm == ctx->pcm_rs.p ? 0 : ctx->pcm_ch;                 /* a pushed binding lived in pcm_rs */
+  /* 1. in_resampler (src/wmadd.cc:392-393): the loop keeps feeding zero frames, so the input is zero extended */
+  ResampleJob J;
+  J.in = d_in; J.out = ctx->rs_in.as<float>(); J.n_in = (long long) n_frames; J.n_stop = LLONG_MAX / 4; J.n_out = n44;
+  J.step = 1.0 / r_in; J.h = h_in; J.coef = coef_in;
+  if (launch_resample (ctx, { J }, channels))
+    return 1;
+  /* 2. WatermarkGen::run on every 1024-frame of it (src/wmadd.cc:394-399) */
+  {
+    EmbedArgs A;
+    A.in = ctx->rs_in.as<float>();
+    A.out = ctx->rs_out.as<float>();
+    A.n_frames = n44;
+    A.C = channels;
+    A.n_proc = n_blocks44 + 1;
+    A.frame_begin = 0;
+    A.frame_end = A.n_proc;
+    A.fpb = ctx->embed_fpb;
+    A.frame_number0 = 2LL * A.fpb - frames_pad_start;
+    A.frame_mod = ctx->frame_mod.as<uint8_t>();
+    A.pow_up = 0.5f * float (-water_delta * 1);
+    A.pow_down = 0.5f * float (-water_delta * -1);
+    A.limiter_block = 0;
+    A.stream_pos0 = 0;
+    A.blk0 = 0;
+    A.peaks = nullptr;
+    A.snr = nullptr;
+    A.snr_frames = 0;
+    A.delta_only = 1;
+    A.tw = ctx->tw.as<float2>();
+    A.win = ctx->win.as<float>();
+    A.synth = ctx->synth.as<float>();
+    const size_t smem = fft_smem_bytes (kEmbedWarps) + 3 * kFrame * sizeof (float) + 2 * size_t (kEmbedWarps) * kEdge * sizeof (float2);
+    if (set_smem (ctx, k_embed, smem)) return 1;
+    const unsigned grid = unsigned ((A.n_proc + kEmbedTile - 1) / kEmbedTile);
+    PROF (ctx);
+    k_embed<<<grid, kEmbedWarps * 32, smem, ctx->stream>>> (A);
+    LAUNCH_CHECK ("k_embed");
+  }
+  /* 3. out_resampler (src/wmadd.cc:401-406) */
+  J.in = ctx->rs_out.as<float>(); J.out = ctx->pcm_rs.as<float>(); J.n_in = n44; J.n_stop = LLONG_MAX / 4; J.n_out = (long long) n_emit;
+  J.step = step_out; J.h = h_out; J.coef = coef_out;
+  if (launch_resample (ctx, { J }, channels))
+    return 1;
+  /* 4. mix + limiter at the input rate (src/wmadd.cc:553-569) */
+  long long n_lim_blocks = 0;
+  if (limiter_block > 0)
+    {
+      n_lim_blocks = (long long) ((n_emit + limiter_block - 1) / limiter_block) + 1;
+      CK (ctx->peaks.reserve (n_lim_blocks * sizeof (unsigned)));
+      CK (cudaMemsetAsync (ctx->peaks.p, 0, n_lim_blocks * sizeof (unsigned), ctx->stream));
+    }
+  if (snr_power)
+    {
+      CK (ctx->snr.reserve (2 * sizeof (double)));
+      CK (cudaMemsetAsync (ctx->snr.p, 0, 2 * sizeof (double), ctx->stream));
+    }
+  PROF (ctx);
+  k_mix_peaks<<<unsigned ((n_emit + 255) / 256), 256, 0, ctx->stream>>> (d_in, (long long) n_frames, ctx->pcm_rs.as<float>(), (long long) n_emit, channels, d_out,
+                                                                         limiter_block, limiter_ceiling, ctx->peaks.as<unsigned>(), snr_power ? ctx->snr.as<double>() : nullptr);
+  LAUNCH_CHECK ("k_mix_peaks");
+  if (limiter_block > 0)
+    {
+      PROF (ctx);
+      k_limiter<<<unsigned ((n_frames + 255) / 256), 256, 0, ctx->stream>>> (d_out, 0, (long long) n_frames, channels, limiter_block, limiter_ceiling,
+                                                                            ctx->peaks.as<unsigned>(), n_lim_blocks, 0);
+      LAUNCH_CHECK ("k_limiter");
+    }
+  if (!out_dev)
+    CK (cudaMemcpyAsync (out, d_out, n_val * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (snr_power)
+    CK (cudaMemcpyAsync (snr_power, ctx->snr.p, 2 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!out_dev || snr_power)
+    CK (cudaStreamSynchronize (ctx->stream));
   return 0;
 }
 
@@ -1379,6 +1504,7 @@ awm_speed_scan (awm_ctx *ctx, int key_slot, const float *clip, size_t clip_frame
       const int rows = n_sub > kSpeedFrame ? int ((n_sub - kSpeedFrame + kSpeedHop - 1) / kSpeedHop) : 0;
       rj[c].in = d_clip;
       rj[c].n_in = (long long) in_trunc;
+      rj[c].n_stop = rj[c].n_in;
       rj[c].n_out = n_sub;
       rj[c].step = 1.0 / ratio;
       rj[c].h = h;

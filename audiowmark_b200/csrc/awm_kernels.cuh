@@ -802,6 +802,7 @@ struct EmbedArgs
   unsigned *peaks;             // [n_blocks] float bits, atomicMax
   double *snr;                 // [2] or null
   long long snr_frames;        // frames that count for --snr (the reference loop stops earlier without limiter)
+  int delta_only;              // 1: write the watermark signal alone (WatermarkGen::run output), not input + watermark
   const float2 *tw;
   const float *win;
   const float *synth;          // [3072] synthesis window
@@ -946,7 +947,7 @@ k_embed (EmbedArgs A)
                         ob = __ldg (A.in + pos * C + chB);
                     }
                 }
-              const float ya = __fadd_rn (wa, oa), yb = __fadd_rn (wb, ob);
+              const float ya = A.delta_only ? wa : __fadd_rn (wa, oa), yb = A.delta_only ? wb : __fadd_rn (wb, ob);
               if (A.snr && m < A.snr_frames)
                 {
                   snr_d += double (wa) * double (wa) + (chB >= 0 ? double (wb) * double (wb) : 0.0);

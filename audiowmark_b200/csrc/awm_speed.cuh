@@ -21,6 +21,8 @@ struct ResampleJob
   const float *in;          // [n_in][C]
   float       *out;         // [n_out][C]
   long long    n_in, n_out;
+  long long    n_stop;      // outputs whose centre lies at or beyond n_stop are 0 (where a stream with h frames of post-roll
+                            // ends): n_in for resample(), "never" when the input is followed by more zeros
   double       step;        // input frames per output frame = 1 / ratio
   int          h;           // half filter length in input frames; 2h taps
   const float *coef;        // [kResamplePhases + 1][2h]
@@ -42,7 +44,7 @@ k_resample (const ResampleJob *__restrict__ jobs, int c_dyn)
       const double fl = floor (t);
       const long long c = (long long) fl;
       float *o = J.out + n * CH;
-      if (c > J.n_in + h - 2)                    // taps would run past the post-roll: a streaming resampler stops here
+      if (c > J.n_stop + h - 2)                  // taps would run past the post-roll: a streaming resampler stops here
         {
           for (int ch = 0; ch < CH; ch++)
             o[ch] = 0.0f;
@@ -81,6 +83,47 @@ k_resample (const ResampleJob *__restrict__ jobs, int c_dyn)
                 }
               o[ch] = s;
             }
+        }
+    }
+}
+
+// out[i] = orig[i] + wm[i] for the frames the add loop emits (src/wmadd.cc:548-566 with a WatermarkResampler): orig is zero
+// beyond n_in; per limiter block the peak of |out| (only peaks above the ceiling matter, Limiter::block_max starts at the
+// ceiling) and the --snr sums.  Values are stored for i < n_in only, the limiter rescales them in place afterwards.
+__global__ void __launch_bounds__ (256)
+k_mix_peaks (const float *__restrict__ orig, long long n_in, const float *__restrict__ wm, long long n_emit, int C, float *__restrict__ out,
+             int limiter_block, float ceiling, unsigned *__restrict__ peaks, double *__restrict__ snr)
+{
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  double sd = 0, ss = 0;
+  if (i < n_emit)
+    {
+      float mx = 0.f;
+      for (int c = 0; c < C; c++)
+        {
+          const float o = i < n_in ? __ldg (orig + i * C + c) : 0.f;
+          const float w = __ldg (wm + i * C + c);
+          const float y = __fadd_rn (w, o);
+          if (i < n_in)
+            out[i * C + c] = y;
+          mx = fmaxf (mx, fabsf (y));
+          sd += double (w) * double (w);
+          ss += double (o) * double (o);
+        }
+      if (limiter_block > 0 && mx > ceiling)
+        atomicMax (peaks + i / limiter_block, __float_as_uint (mx));
+    }
+  if (snr)
+    {
+      for (int d = 16; d > 0; d >>= 1)
+        {
+          sd += __shfl_xor_sync (0xffffffffu, sd, d);
+          ss += __shfl_xor_sync (0xffffffffu, ss, d);
+        }
+      if ((threadIdx.x & 31) == 0 && (sd != 0 || ss != 0))
+        {
+          atomicAdd (snr, sd);
+          atomicAdd (snr + 1, ss);
         }
     }
 }

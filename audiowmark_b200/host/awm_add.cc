@@ -3,6 +3,7 @@
 // thread; here the whole stream is handed to awm_embed, which reproduces the same stream semantics
 // (frame numbering from 2*fpb - 250, zero padding of the tail, limiter on the zero-extended signal).
 #include "awm_wm.hh"
+#include "awm_speed.hh"
 #include "awm_engine.hh"
 #include "awm_tables.hh"
 #include "awm_util.hh"
@@ -27,6 +28,35 @@ gen_runs (size_t n_frames, bool limiter_on, size_t limiter_block)
   return 1 + (need + N - 1) / N;
 }
 
+/* Frame counts of the add loop when the input is not at the watermark rate (src/wmadd.cc:520-589 with a
+ * WatermarkResampler, :353-430).  Every iteration pushes one 1024-frame block (zero frames after EOF) into the input
+ * resampler; whole 1024-frames at the watermark rate go through WatermarkGen::run and the output resampler; whatever
+ * that has delivered is mixed, counted for --snr and handed to the limiter, which holds back until two complete blocks
+ * are buffered (src/limiter.cc:53-58).  The loop stops at the first short read with everything written.
+ *   n_emit: frames that went through the mixer;  gen_runs: WatermarkGen::run calls */
+void
+resampled_add_plan (size_t n_frames, int sample_rate, bool limiter_on, size_t limiter_block, size_t& n_emit, size_t& gen_runs_out)
+{
+  const size_t N = Params::frame_size;
+  const double r_in = double (Params::mark_sample_rate) / sample_rate, r_out = double (sample_rate) / Params::mark_sample_rate;
+  size_t total_in = 0, total_out = 0;
+  n_emit = gen_runs_out = 0;
+  for (size_t iteration = 1;; iteration++)
+    {
+      const size_t real = std::min (N, n_frames - total_in);
+      total_in += real;
+      if (real < N && total_in == total_out)
+        break;
+      const size_t at_mark_rate = resample_stream_available (N * iteration, r_in);
+      gen_runs_out = at_mark_rate / N;
+      n_emit = gen_runs_out ? resample_stream_available (gen_runs_out * N, r_out) : 0;
+      size_t released = n_emit;
+      if (limiter_on)
+        released = n_emit / limiter_block >= 2 ? (n_emit / limiter_block - 1) * limiter_block : 0;
+      total_out = std::min (released, total_in);
+    }
+}
+
 static void
 info_format (const string& label, const RawFormat& format)
 {
@@ -42,17 +72,35 @@ add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_fram
   const vector<int> bitvec = parse_payload (bits);
   if (bitvec.empty())
     return 1;
-  if (sample_rate != Params::mark_sample_rate)
-    {
-      error ("audiowmark: input sample rate %d: only %d Hz is supported (resampling is not available in this build)\n",
-             sample_rate, Params::mark_sample_rate);
-      return 1;
-    }
   awm_ctx *ctx = Engine::ctx();
   if (!ctx || !Engine::set_embed_tables (key, bitvec))
     return 1;
   const int limiter_block = Params::test_no_limiter ? 0 : int (sample_rate * int (Params::limiter_block_size_ms) / 1000);
   double snr_power[2] = { 0, 0 };
+  if (sample_rate != Params::mark_sample_rate)
+    {
+      if (first_frame_number)
+        {
+          error ("audiowmark: sharded embedding is only available at %d Hz\n", Params::mark_sample_rate);
+          return 1;
+        }
+      size_t n_emit = 0, runs = 0;
+      resampled_add_plan (n_frames, sample_rate, !Params::test_no_limiter, sample_rate * int (Params::limiter_block_size_ms) / 1000, n_emit, runs);
+      if (awm_embed_resampled (ctx, in, out, n_frames, n_channels, sample_rate, Params::mark_sample_rate, std::max (n_emit, n_frames), Params::frames_pad_start,
+                               Params::water_delta, limiter_block, Params::limiter_ceiling, (Params::snr || stats) ? snr_power : nullptr))
+        {
+          error ("audiowmark: embedding failed: %s\n", awm_last_error (ctx));
+          return 1;
+        }
+      if (stats)
+        {
+          const size_t fpb = frames_per_block(), f0 = 2 * fpb - Params::frames_pad_start;
+          const int blocks = int ((f0 + runs) / fpb - f0 / fpb);
+          stats->data_blocks = std::max (blocks - 1, 0);
+          stats->snr_db = snr_power[0] > 0 ? 10 * log10 (snr_power[1] / snr_power[0]) : INFINITY;
+        }
+      return 0;
+    }
   if (awm_embed (ctx, in, out, n_frames, n_channels, first_frame_number, Params::frames_pad_start, Params::water_delta,
                  limiter_block, Params::limiter_ceiling, (Params::snr || stats) ? snr_power : nullptr))
     {

@@ -87,6 +87,16 @@ awmh_resample (const float *in, size_t n_in, int n_channels, double ratio, float
 }
 
 uint64_t awmh_resample_stream_frames (uint64_t n_in, double ratio) { return resample_stream_frames (n_in, ratio); }
+uint64_t awmh_resample_stream_available (uint64_t fed, double ratio) { return resample_stream_available (fed, ratio); }
+
+void
+awmh_resampled_add_plan (uint64_t n_frames, int sample_rate, uint64_t *n_emit, uint64_t *gen_runs)
+{
+  size_t e = 0, r = 0;
+  resampled_add_plan (n_frames, sample_rate, !Params::test_no_limiter, sample_rate * int (Params::limiter_block_size_ms) / 1000, e, r);
+  *n_emit = e;
+  *gen_runs = r;
+}
 
 int awmh_frames_per_block() { return int (frames_per_block()); }
 int awmh_n_coded_bits()     { return int (code_size (ConvBlockType::a, Params::payload_size)); }

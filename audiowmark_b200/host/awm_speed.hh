@@ -19,3 +19,5 @@ std::vector<DetectSpeedResult> detect_speed (const std::vector<Key>& key_list, c
 bool   resample_ratio (const float *in, size_t n_frames, int n_channels, double ratio, std::vector<float>& out);
 /* number of frames the streaming resampler of WavChunkLoader / WatermarkResampler delivers for n_in input frames */
 size_t resample_stream_frames (size_t n_in, double ratio);
+/* outputs available from a streaming resampler after `fed` frames were written (no trailing frames yet) */
+size_t resample_stream_available (size_t fed, double ratio);

@@ -18,6 +18,9 @@ struct AddStats { int data_blocks = 0; double snr_db = 0; };
 int add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,
                           const std::string& bits, AddStats *stats, uint64_t first_frame_number = 0);
 
+/* frame counts of the add loop for inputs that are not at the watermark rate (see awm_add.cc) */
+void resampled_add_plan (size_t n_frames, int sample_rate, bool limiter_on, size_t limiter_block, size_t& n_emit, size_t& gen_runs_out);
+
 class ResultSet;
 int get_watermark_buffer (const std::vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
                           ResultSet& result_set, bool print_speed_results = false, size_t *mark_rate_frames = nullptr);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan"]
 
 _lib = None
 
@@ -191,6 +191,19 @@ def resample_stream_frames(n_in, ratio):
     L = load()
     L.awmh_resample_stream_frames.restype = ctypes.c_uint64
     return int(L.awmh_resample_stream_frames(ctypes.c_uint64(n_in), ctypes.c_double(ratio)))
+
+
+def resample_stream_available(fed, ratio):
+    L = load()
+    L.awmh_resample_stream_available.restype = ctypes.c_uint64
+    return int(L.awmh_resample_stream_available(ctypes.c_uint64(fed), ctypes.c_double(ratio)))
+
+
+def resampled_add_plan(n_frames, sample_rate):
+    """(frames through the mixer, WatermarkGen::run calls) of `add` at a sample rate other than 44.1 kHz"""
+    e, r = ctypes.c_uint64(), ctypes.c_uint64()
+    load().awmh_resampled_add_plan(ctypes.c_uint64(n_frames), ctypes.c_int(sample_rate), ctypes.byref(e), ctypes.byref(r))
+    return e.value, r.value
 
 
 def chunk_geometry(sample_rate=44100):

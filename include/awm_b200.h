@@ -181,6 +181,16 @@ int awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_b
  */
 int awm_resample (awm_ctx *ctx, const float *in, size_t n_in, int channels, double ratio, int hlen, float *out, size_t n_out);
 
+/* ---- embed for inputs that are not at the watermark rate: WatermarkResampler::run (src/wmadd.cc:353-430) inside the
+ * add loop (:520-589).  The input is resampled to mark_sample_rate, the watermark signal alone is generated there
+ * (WatermarkGen::run), resampled back and added to the untouched input; the limiter runs at the input rate
+ * (limiter_block = sample_rate * ms / 1000).  n_emit >= n_frames = frames the reference loop pushes through the mixer
+ * before it stops (zero frames are fed after EOF until resamplers and limiter have delivered everything): they enter the
+ * --snr sums and the limiter's block peaks.  in/out: [n_frames][channels], host or device.
+ */
+int awm_embed_resampled (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels, int sample_rate, int mark_sample_rate,
+                         size_t n_emit, int frames_pad_start, double water_delta, int limiter_block, float limiter_ceiling, double *snr_power);
+
 /* resample_ratio (wav_data, speed, ...) of decode() (src/wmget.cc:916) without leaving the device: the bound PCM is
  * resampled by `ratio` into a context-owned buffer of n_out frames, which becomes the bound PCM; awm_pcm_pop restores
  * the previous binding (the original chunk is not copied again).  One level only; awm_pcm_bind drops a pushed binding. */

@@ -520,9 +520,10 @@ class EmbedResult:
 
 
 def embed(samples: np.ndarray, key: Key, bits: str, P: Params | None = None, rate: int = 44100, keep_wm: bool = False) -> EmbedResult:
-    """add_stream_watermark (wmadd.cc:448-618) at 44.1 kHz (no resampler), zero_frames = 0."""
+    """add_stream_watermark (wmadd.cc:448-618), zero_frames = 0; other rates than 44.1 kHz go through embed_resampled."""
     P = P or Params()
-    assert rate == P.mark_sample_rate, "oracle covers the 44.1 kHz path only (resampler is out of scope)"
+    if rate != P.mark_sample_rate:
+        return embed_resampled(samples, key, bits, P, rate, keep_wm)
     bitvec = parse_payload(bits, P)
     assert bitvec, "bad payload"
     samples = np.ascontiguousarray(samples, dtype=np.float32)
@@ -565,6 +566,38 @@ def embed(samples: np.ndarray, key: Key, bits: str, P: Params | None = None, rat
     snr = 10 * math.log10((o * o).sum() / max((d * d).sum(), 1e-300))
     out = mixed if P.test_no_limiter else limiter(mixed, rate, P)
     # data block counter (wmadd.cc:311-313,345-350): number of WatermarkGen::run calls made by the loop
+    f0 = 2 * fpb - P.frames_pad_start
+    m_data_blocks = (f0 + runs) // fpb - f0 // fpb
+    return EmbedResult(out[:n].copy(), max(m_data_blocks - 1, 0), snr, wm[:n].copy() if keep_wm else None)
+
+
+def embed_resampled(samples: np.ndarray, key: Key, bits: str, P: Params, rate: int, keep_wm: bool = False) -> EmbedResult:
+    """add_stream_watermark with WatermarkResampler (wmadd.cc:353-430, 520-589): the input is resampled to the watermark
+    rate, WatermarkGen produces the watermark signal there, it is resampled back and added to the untouched input; the
+    limiter runs at the input rate.  Whole-buffer restatement of the streaming loop: zero frames keep being fed after
+    EOF, so both resamplers see zero-extended signals."""
+    samples = np.ascontiguousarray(samples, dtype=np.float32)
+    n, nch = samples.shape
+    N = P.frame_size
+    n_emit, runs = resampled_add_plan(n, rate, P)
+    r_in, r_out = float(P.mark_sample_rate) / rate, float(rate) / P.mark_sample_rate
+    h_out = int(math.ceil(16 / min(1.0, r_out)))
+    top = int(math.floor((n_emit - 1) * (1.0 / r_out))) + h_out            # highest watermark-rate frame any emitted output touches
+    n44 = (top // N + 1) * N
+    xz = np.zeros((n + 4 * 64, nch), np.float32)                           # post-roll >> filter length: true zero extension
+    xz[:n] = samples
+    x44 = resample_ratio(xz, r_in, n_out=n44)
+    Pn = Params(**{**{k: getattr(P, k) for k in Params.__annotations__}, "test_no_limiter": True})
+    wm44 = embed(x44, key, bits, Pn, P.mark_sample_rate, keep_wm=True).wm  # WatermarkGen::run output of every frame
+    wm = resample_ratio(wm44, r_out, n_out=n_emit)
+    ext = np.zeros((n_emit, nch), np.float32)
+    ext[:n] = samples
+    mixed = wm + ext                                                        # wmadd.cc:564-565
+    d = wm.astype(np.float64)
+    o = samples.astype(np.float64)
+    snr = 10 * math.log10((o * o).sum() / max((d * d).sum(), 1e-300))       # wmadd.cc:553-563 over everything emitted
+    out = mixed if P.test_no_limiter else limiter(mixed, rate, P)
+    fpb = frames_per_block(P)
     f0 = 2 * fpb - P.frames_pad_start
     m_data_blocks = (f0 + runs) // fpb - f0 // fpb
     return EmbedResult(out[:n].copy(), max(m_data_blocks - 1, 0), snr, wm[:n].copy() if keep_wm else None)
@@ -1129,16 +1162,49 @@ def resample(samples: np.ndarray, old_rate: int, new_rate: int) -> np.ndarray:  
     return resample_ratio(samples, float(new_rate) / old_rate)
 
 
-def stream_out_count(n_in: int, ratio: float, hlen: int = 16) -> int:
-    """frames a streaming resampler (BufferedResamplerImpl: write_frames ... write_trailing_frames, resample.cc:133-215)
-    delivers for n_in input frames: every output whose taps fit into pre-roll + input + post-roll."""
+def stream_avail(fed: int, ratio: float, hlen: int = 16) -> int:
+    """outputs a streaming resampler (BufferedResamplerImpl::write_frames, resample.cc:168-196) has delivered once `fed`
+    frames (after the k/2 - 1 frames of pre-roll) have been written: every output whose 2h taps are buffered."""
     fc = min(1.0, ratio)
     h = int(math.ceil(hlen / fc))
     step = 1.0 / ratio
-    n = max(int(n_in * ratio) - 2, 0)
-    while math.floor((h - 1) + float(n) * step) <= n_in + h - 2:
+    if fed - 2 < h - 1:
+        return 0
+    n = max(int((fed - 1 - h) * ratio) - 2, 0)
+    while n > 0 and math.floor((h - 1) + float(n - 1) * step) > fed - 2:
+        n -= 1
+    while math.floor((h - 1) + float(n) * step) <= fed - 2:
         n += 1
     return n
+
+
+def stream_out_count(n_in: int, ratio: float, hlen: int = 16) -> int:
+    """... plus write_trailing_frames (k/2 zero frames, resample.cc:198-204): what WavChunkLoader gets for n_in input frames"""
+    h = int(math.ceil(hlen / min(1.0, ratio)))
+    return stream_avail(n_in + h, ratio, hlen)
+
+
+def resampled_add_plan(n: int, rate: int, P: Params):
+    """Frame counts of the add loop (wmadd.cc:520-589) when a WatermarkResampler is active: returns
+    (frames pushed through mixer / --snr sums / limiter, number of WatermarkGen::run calls)."""
+    N = P.frame_size
+    r_in, r_out = float(P.mark_sample_rate) / rate, float(rate) / P.mark_sample_rate
+    bs = rate * P.limiter_block_size_ms // 1000
+    total_in = total_out = 0
+    emitted = runs = 0
+    j = 0
+    while True:
+        real = min(N, n - total_in)
+        total_in += real
+        if real < N and total_in == total_out:
+            break
+        x44 = stream_avail(N * (j + 1), r_in)
+        runs = x44 // N
+        emitted = stream_avail(runs * N, r_out) if runs else 0
+        lim = emitted if P.test_no_limiter else max(emitted // bs - 1, 0) * bs
+        total_out = min(lim, total_in)
+        j += 1
+    return emitted, runs
 
 
 def resample_stream(samples: np.ndarray, old_rate: int, new_rate: int) -> np.ndarray:

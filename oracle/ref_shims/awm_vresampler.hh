@@ -93,7 +93,8 @@ public:
           }
         if (!out_count || !inp_count)
           break;
-        /* take input in blocks, drop history that is no longer needed */
+        /* take just the input the next output needs (a stream that is consumed frame by frame delivers every output as
+         * early as possible), drop history that is no longer needed */
         const long long need_from = (long long) floor (m_t) - m_h + 1;
         if (need_from > m_base + 4096)
           {
@@ -101,7 +102,10 @@ public:
             m_buf.erase (m_buf.begin(), m_buf.begin() + drop * m_nchan);
             m_base += drop;
           }
-        const unsigned int take = inp_count < 4096 ? inp_count : 4096;
+        const long long have = m_base + (long long) (m_buf.size() / m_nchan);
+        const long long missing = (long long) floor (m_t) + m_h + 1 - have;        /* frames up to tap c + h */
+        const unsigned int want = missing > 1 ? (unsigned int) (missing < 4096 ? missing : 4096) : 1;
+        const unsigned int take = inp_count < want ? inp_count : want;
         const size_t old = m_buf.size();
         m_buf.resize (old + size_t (take) * m_nchan);
         if (inp_data)

@@ -110,6 +110,17 @@ def main():
         run("test-resample", wm, r48, 48000)
         c48 = run("cmp", r48, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", "--json", js)
         G["rate48000"] = {"input_sha256": sha(pcm16(r48)), "n_frames": int(pcm16(r48).shape[0]), "cmp_stdout": c48.stdout, "json": json.load(open(js))}
+        # ---- sample rate (tests/sample-rate-test.sh, first half): 200 s reference noise at 32 kHz, add + cmp -> 5 matches;
+        # plus a short 48 kHz case without limiter and with --snr
+        def rate_case(name, seconds, rate, extra_add):
+            src, dst = os.path.join(tmp, name + ".wav"), os.path.join(tmp, name + "_wm.wav")
+            run("test-gen-noise", src, seconds, rate)
+            p = run("add", *extra_add, src, dst, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0")
+            c = run("cmp", dst, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", "--json", js, ok_codes=(0, 1))
+            return {"seconds": seconds, "rate": rate, "add_args": list(extra_add), "input_sha256": sha(pcm16(src)), "output_sha256": sha(pcm16(dst)),
+                    "add_stderr": p.stderr, "cmp_stdout": c.stdout, "json": json.load(open(js))}
+        G["rate32000_add"] = rate_case("r32", 200, 32000, ("--snr",))
+        G["rate48000_add_nolimiter"] = rate_case("r48nl", 11.3, 48000, ("--snr", "--test-no-limiter"))
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     json.dump(G, open(out, "w"), indent=1, sort_keys=True)
     print("wrote", out, os.path.getsize(out), "bytes")

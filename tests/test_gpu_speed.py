@@ -145,3 +145,25 @@ def test_speed_long_input_detect_and_decode():
     hits = [m for m in doc["matches"] if m["bits"] == "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0"]
     assert len(hits) == 5 and all(m["type"].endswith("SPEED") for m in hits)
     assert abs(hits[0]["speed"] - 1.010014) < 3e-6
+
+
+@pytest.mark.parametrize("name", ["rate32000_add", "rate48000_add_nolimiter"])
+def test_add_other_sample_rates_vs_reference(name):
+    """`add` through the WatermarkResampler path: GPU output against the oracle (== reference PCM, see the CPU test)"""
+    g = G[name]
+    x = O.int16_to_float(O.quantize_sndfile16(O.gen_noise(g["seconds"], g["rate"])))
+    no_lim = "--test-no-limiter" in g["add_args"]
+    H.set_params(test_no_limiter=no_lim)
+    try:
+        out, blocks, snr = H.add(x, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", want_stats=True, sample_rate=g["rate"])
+    finally:
+        H.set_params()
+    ref = O.embed(x, O.Key(), "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", O.Params(test_no_limiter=no_lim), g["rate"])
+    assert T.rms(out - ref.samples) < 1e-5
+    d = O.quantize_sndfile16(out).astype(np.int32) - O.quantize_sndfile16(ref.samples).astype(np.int32)
+    assert np.abs(d).max() <= 1 and np.count_nonzero(d) < 1e-3 * d.size
+    assert ("Data Blocks:  %d\n" % blocks) in g["add_stderr"]
+    assert abs(snr - ref.snr_db) < 1e-3
+    if name == "rate32000_add":
+        doc = H.get(O.int16_to_float(O.quantize_sndfile16(out)), sample_rate=g["rate"])
+        assert check_matches(doc, g["json"]) == 5

@@ -123,3 +123,21 @@ def test_raw_and_wav_pipe_streams(tmp_path):
     txt = open(key).read()
     assert txt.startswith("# watermarking key for audiowmark\n\nkey ") and 'name "a \\"b\\""' in txt
     assert oct(os.stat(key).st_mode & 0o777) == "0o600"
+
+
+def test_resampler_stream_counts_match_oracle():
+    """host-side frame bookkeeping of the resampled paths (pure integer / double arithmetic, no GPU): streaming
+    resampler availability, WavChunkLoader frame count, and the add loop's frame plan at other sample rates"""
+    import random
+    rnd = random.Random(5)
+    for ratio in (44100 / 48000.0, 48000 / 44100.0, 44100 / 32000.0, 32000 / 44100.0, 44100 / 96000.0, 96000 / 44100.0, 0.4873, 1.0 / 1.01, 2.0, 0.5):
+        for fed in [0, 1, 15, 16, 17, 31, 32, 33, 40, 100, 1024, 1025, 4096, 44100] + [rnd.randrange(1, 5_000_000) for _ in range(20)]:
+            assert H.resample_stream_available(fed, ratio) == O.stream_avail(fed, ratio), (fed, ratio)
+            assert H.resample_stream_frames(fed, ratio) == O.stream_out_count(fed, ratio), (fed, ratio)
+    for no_lim in (False, True):
+        H.set_params(test_no_limiter=no_lim)
+        P = O.Params(test_no_limiter=no_lim)
+        for rate in (8000, 22050, 32000, 33333, 48000, 88200, 96000):
+            for n in (0, 1, 1023, 1024, 1025, 5000, rate, rate + 1, 7 * rate - 1, 361417, 6_400_000):
+                assert H.resampled_add_plan(n, rate) == O.resampled_add_plan(n, rate, P), (rate, n, no_lim)
+    H.set_params()

@@ -146,3 +146,17 @@ def test_get_48000_vs_reference():
     n44 = O.stream_out_count(z.shape[0], 44100 / 48000.0)
     assert rs.json_doc(int(np.rint(n44 / 44100.0))) == fmt_ref_json(g["json"])
     assert "match_count 5 10" in g["cmp_stdout"]
+
+
+@pytest.mark.parametrize("name", ["rate32000_add", "rate48000_add_nolimiter"])
+def test_embed_other_sample_rates_bit_exact_vs_reference(name):
+    """tests/sample-rate-test.sh, first half (and a 48 kHz / --test-no-limiter variant): add at a rate that needs the
+    WatermarkResampler, output PCM, SNR and Data Blocks lines of the reference"""
+    g = G[name]
+    x = q16(O.gen_noise(g["seconds"], g["rate"]))
+    assert sha(O.quantize_sndfile16(x)) == g["input_sha256"]
+    Pc = O.Params(test_no_limiter="--test-no-limiter" in g["add_args"])
+    r = O.embed(x, O.Key(), "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", Pc, g["rate"])
+    assert sha(O.quantize_sndfile16(r.samples)) == g["output_sha256"]
+    assert ("Data Blocks:  %d\n" % r.data_blocks) in g["add_stderr"]
+    assert ("SNR:          %f dB\n" % r.snr_db) in g["add_stderr"]
