@@ -1168,7 +1168,7 @@ coef_table (awm_ctx *ctx, double ratio, int hlen, const float **coef, int *h_out
             for (int j = 0; j < taps; j++)
               {
                 const double d = (j - (h - 1)) - double (p) / kResamplePhases;
-                tab[size_t (p) * taps + j] = float (fc * rs_sinc (fc * d) * rs_window (d / h));
+                tab[size_t (j) * rows + p] = float (fc * rs_sinc (fc * d) * rs_window (d / h));     /* tap major, see ResampleJob */
               }
         };
       const int n_thr = 8;
@@ -1300,6 +1300,25 @@ awm_pcm_pop (awm_ctx *ctx)
   ctx->pcm_frames = ctx->saved_frames;
   ctx->pcm_ch = ctx->saved_ch;
   ctx->pushed = false;
+  return 0;
+}
+
+int
+awm_gather (awm_ctx *ctx, const float *src, const uint64_t *indices, size_t n, float *dst_host)
+{
+  if (!src || !indices || !dst_host)
+    return fail (ctx, "awm_gather: bad arguments");
+  if (!n)
+    return 0;
+  CK (cudaSetDevice (ctx->device));
+  CK (ctx->rs_jobs.reserve (n * sizeof (uint64_t)));
+  CK (ctx->rs_out.reserve (n * sizeof (float)));
+  CK (cudaMemcpyAsync (ctx->rs_jobs.p, indices, n * sizeof (uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  PROF (ctx);
+  k_gather<<<unsigned ((n + 255) / 256), 256, 0, ctx->stream>>> (src, ctx->rs_jobs.as<unsigned long long>(), (long long) n, ctx->rs_out.as<float>());
+  LAUNCH_CHECK ("k_gather");
+  CK (cudaMemcpyAsync (dst_host, ctx->rs_out.p, n * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
   return 0;
 }
 

@@ -25,7 +25,8 @@ struct ResampleJob
                             // ends): n_in for resample(), "never" when the input is followed by more zeros
   double       step;        // input frames per output frame = 1 / ratio
   int          h;           // half filter length in input frames; 2h taps
-  const float *coef;        // [kResamplePhases + 1][2h]
+  const float *coef;        // [2h][kResamplePhases + 1]: tap major, so that the lanes of a warp (same tap, different phase)
+                            // gather inside one 1 KB row instead of touching 32 different rows
 };
 
 // out[n] = sum_j x[c - 2h + 2 + j] * ((1-a) coef[p][j] + a coef[p+1][j]),  t = (h-1) + n step, c = floor t,
@@ -53,7 +54,8 @@ k_resample (const ResampleJob *__restrict__ jobs, int c_dyn)
       const double frac = __dmul_rn (__dsub_rn (t, fl), double (kResamplePhases));
       const int p = int (frac);
       const float a = float (__dsub_rn (frac, double (p))), b = __fsub_rn (1.0f, a);
-      const float *c0 = J.coef + (size_t) p * taps, *c1 = c0 + taps;
+      const float *c0 = J.coef + p, *c1 = c0 + 1;
+      constexpr int RS = kResamplePhases + 1;        // row stride of the tap-major table
       const long long i0 = c - 2LL * h + 2;
       if (C == 2)
         {
@@ -62,7 +64,7 @@ k_resample (const ResampleJob *__restrict__ jobs, int c_dyn)
           for (int j = 0; j < taps; j++)
             {
               const long long i = i0 + j;
-              const float w = __fadd_rn (__fmul_rn (b, __ldg (c0 + j)), __fmul_rn (a, __ldg (c1 + j)));
+              const float w = __fadd_rn (__fmul_rn (b, __ldg (c0 + j * RS)), __fmul_rn (a, __ldg (c1 + j * RS)));
               const float2 x = (i >= 0 && i < J.n_in) ? __ldg (x2 + i) : make_float2 (0.0f, 0.0f);
               s0 = __fadd_rn (s0, __fmul_rn (x.x, w));
               s1 = __fadd_rn (s1, __fmul_rn (x.y, w));
@@ -77,7 +79,7 @@ k_resample (const ResampleJob *__restrict__ jobs, int c_dyn)
               for (int j = 0; j < taps; j++)
                 {
                   const long long i = i0 + j;
-                  const float w = __fadd_rn (__fmul_rn (b, __ldg (c0 + j)), __fmul_rn (a, __ldg (c1 + j)));
+                  const float w = __fadd_rn (__fmul_rn (b, __ldg (c0 + j * RS)), __fmul_rn (a, __ldg (c1 + j * RS)));
                   const float x = (i >= 0 && i < J.n_in) ? __ldg (J.in + i * CH + ch) : 0.0f;
                   s = __fadd_rn (s, __fmul_rn (x, w));
                 }
@@ -85,6 +87,15 @@ k_resample (const ResampleJob *__restrict__ jobs, int c_dyn)
             }
         }
     }
+}
+
+// dst[k] = src[idx[k]]: the sparse sample subset get_clip_locations hashes (src/wmspeed.cc:538-543) when the PCM lives in device memory
+__global__ void
+k_gather (const float *__restrict__ src, const unsigned long long *__restrict__ idx, long long n, float *__restrict__ dst)
+{
+  const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n)
+    dst[k] = __ldg (src + idx[k]);
 }
 
 // out[i] = orig[i] + wm[i] for the frames the add loop emits (src/wmadd.cc:548-566 with a WatermarkResampler): orig is zero

@@ -106,13 +106,15 @@ struct SpeedScanParams        /* src/wmspeed.cc:54-60 */
 
 struct Score { double speed = 0; double quality = 0; };
 
-/* PCM of one chunk; samples is a host pointer */
+/* PCM of one chunk; samples is a host pointer, or a device pointer when on_device is set (then the few values the
+ * host needs are fetched with awm_gather / awm_copy_to_host, the chunk itself never crosses PCIe) */
 struct Pcm
 {
   const float *samples;
   size_t       n_frames;
   int          n_channels;
   int          sample_rate;
+  bool         on_device;
 };
 
 /* get_speed_clip (src/wmspeed.cc:33-52): [start, end) in frames */
@@ -134,8 +136,18 @@ get_clip_locations (const Key& key, const Pcm& in, int n)      /* src/wmspeed.cc
   /* to improve performance, not all samples are hashed but just a few */
   const size_t n_values = in.n_frames * in.n_channels;
   vector<float> xsamples;
-  for (size_t p = 0; p < n_values; p += rng() % 1000)
-    xsamples.push_back (in.samples[p]);
+  if (in.on_device)
+    {
+      vector<uint64_t> positions;
+      for (size_t p = 0; p < n_values; p += rng() % 1000)
+        positions.push_back (p);
+      xsamples.resize (positions.size());
+      if (awm_gather (Engine::ctx(), in.samples, positions.data(), positions.size(), xsamples.data()))
+        error ("audiowmark: %s\n", awm_last_error (Engine::ctx()));
+    }
+  else
+    for (size_t p = 0; p < n_values; p += rng() % 1000)
+      xsamples.push_back (in.samples[p]);
   rng.seed (seed_from_hash (xsamples), Random::Stream::speed_clip);
   vector<double> result;
   for (int c = 0; c < n; c++)
@@ -151,10 +163,19 @@ get_best_clip_location (const Key& key, const Pcm& in, double seconds, int candi
     {
       size_t s, e;
       speed_clip_range (location, in, seconds, s, e);
-      double energy = 0;
-      for (size_t i = s * in.n_channels; i < e * in.n_channels; i++)
+      const float *clip = in.samples + s * in.n_channels;
+      vector<float> clip_copy;
+      if (in.on_device)
         {
-          const float v = in.samples[i];
+          clip_copy.resize ((e - s) * in.n_channels);
+          if (awm_copy_to_host (Engine::ctx(), clip_copy.data(), clip, clip_copy.size() * sizeof (float)))
+            error ("audiowmark: %s\n", awm_last_error (Engine::ctx()));
+          clip = clip_copy.data();
+        }
+      double energy = 0;
+      for (size_t i = 0; i < (e - s) * in.n_channels; i++)
+        {
+          const float v = clip[i];
           energy += v * v;
         }
       if (energy > best_energy)
@@ -283,24 +304,10 @@ detect_speed (const vector<Key>& key_list, const float *samples, size_t n_frames
   const size_t n_best = patient ? 15 : 5;
   const int clip_candidates = 5;
 
-  /* a caller may keep its PCM in device memory: the clip selection needs it on the host */
   awm_ctx *ctx = Engine::ctx();
   if (!ctx)
     return results;
-  float *host_copy = nullptr;
-  const size_t n_values = n_frames * n_channels;
-  if (Engine::is_device_pointer (samples))
-    {
-      host_copy = static_cast<float *> (awm_host_alloc (n_values * sizeof (float)));
-      if (!host_copy || awm_copy_to_host (ctx, host_copy, samples, n_values * sizeof (float)))
-        {
-          error ("audiowmark: detect_speed: cannot copy PCM to the host\n");
-          awm_host_free (host_copy);
-          return results;
-        }
-      samples = host_copy;
-    }
-  const Pcm in { samples, n_frames, n_channels, sample_rate };
+  const Pcm in { samples, n_frames, n_channels, sample_rate, Engine::is_device_pointer (samples) };
   for (const auto& key : key_list)
     {
       const double clip_location = get_best_clip_location (key, in, scan1.seconds, clip_candidates);
@@ -343,7 +350,6 @@ detect_speed (const vector<Key>& key_list, const float *samples, size_t n_frames
             results.push_back ({ key, best_speed });
         }
     }
-  awm_host_free (host_copy);
   return results;
 }
 
