@@ -2,7 +2,7 @@
 // Same argv grammar, messages and exit codes as the reference CLI (src/audiowmark.cc:47-88,540-1079)
 // for: add, get, cmp, gen-key and the test helpers the reference's tests/*.sh use (test-gen-noise,
 // cut-start, test-snr, test-info, test-clip, test-subtract, gentest).  Not available here: hls-*,
-// --detect-speed*, --try-speed, --short, --linear (get), non-44.1 kHz input, MP3/FLAC input.
+// MP3/FLAC and other libsndfile formats.
 #include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
@@ -225,8 +225,13 @@ parse_shared_options (ArgParser& ap)
   int i;
   if (ap.parse_opt ("--short", i))
     {
-      error ("audiowmark: unsupported short payload size %d (short payload mode is not available in this build)\n", i);
-      exit (1);
+      Params::payload_size = i;
+      if (!short_code_init (Params::payload_size))
+        {
+          error ("audiowmark: unsupported short payload size %zd\n", Params::payload_size);
+          exit (1);
+        }
+      Params::payload_short = true;
     }
   ap.parse_opt ("--frames-per-bit", Params::frames_per_bit);
   if (ap.parse_opt ("--linear"))

@@ -12,6 +12,9 @@ std::vector<int> conv_encode (ConvBlockType block_type, const std::vector<int>& 
 /* code_* dispatch between the plain convolutional code and the (deprecated) short payload mode */
 size_t           code_size (ConvBlockType block_type, size_t msg_size);
 std::vector<int> code_encode (ConvBlockType block_type, const std::vector<int>& in_bits);
-/* --short <bits> needs the block-code generator matrices of src/shortcode.cc:28-83 (tabulated data,
- * not restated here): reports 0 = unsupported */
+/* --short <bits> (12, 16 or 20): selects the block code, returns its length n (0 = unsupported size) */
 size_t           short_code_init (size_t k);
+std::vector<int> short_encode_blk (const std::vector<int>& in_bits);
+std::vector<int> short_decode_blk (const std::vector<int>& coded_bits);   /* empty: no code word matches */
+/* message bits of the convolutional code: the payload, or the block code word in short mode */
+size_t           code_message_bits();

@@ -63,11 +63,6 @@ Engine::key_slot (const Key& key)
   if (g_slots.size() >= AWM_MAX_KEYS)
     g_slots.clear();                               // recycle: tables are cheap to rebuild
   const int slot = int (g_slots.size());
-  if (!Params::mix)
-    {
-      error ("audiowmark: --linear is not supported by the GPU decoder\n");
-      return -1;
-    }
   for (int mode : { AWM_MODE_BLOCK, AWM_MODE_CLIP })
     {
       const SyncTable t = gen_sync_table (key, mode);

@@ -269,7 +269,7 @@ run_viterbi_jobs (vector<VitJob>& jobs, vector<ResultSet>& chunk_results)
     return false;
   if (jobs.empty())
     return true;
-  const int n_msg = int (Params::payload_size);
+  const int n_msg = int (code_message_bits());        /* the block code word in short payload mode */
   vector<float> raw;
   vector<int> types (jobs.size());
   for (size_t j = 0; j < jobs.size(); j++)
@@ -288,6 +288,12 @@ run_viterbi_jobs (vector<VitJob>& jobs, vector<ResultSet>& chunk_results)
     {
       const VitJob& job = jobs[j];
       vector<int> bit_vec (bits.begin() + j * n_msg, bits.begin() + (j + 1) * n_msg);
+      if (Params::payload_short)
+        {
+          bit_vec = short_decode_blk (bit_vec);        /* code_decode_soft, src/shortcode.cc:129-133 */
+          if (bit_vec.empty())
+            continue;
+        }
       chunk_results[job.chunk].add_pattern (job.key, job.time, job.score, bit_vec, err[j], job.type, job.speed);
     }
   jobs.clear();

@@ -42,6 +42,24 @@ awmh_set_params (double water_delta, int frames_per_bit, int mix, int hard, doub
   set_log_level (quiet ? Log::WARNING : Log::INFO);
 }
 
+/* --short <bits> (src/audiowmark.cc:665-674); bits = 0 returns to the 128 bit payload.  returns the block code length or -1 */
+int
+awmh_set_short_payload (int bits)
+{
+  if (bits == 0)
+    {
+      Params::payload_short = false;
+      Params::payload_size = 128;
+      return 0;
+    }
+  const size_t n = short_code_init (bits);
+  if (!n)
+    return -1;
+  Params::payload_size = bits;
+  Params::payload_short = true;
+  return int (n);
+}
+
 /* --detect-speed / --detect-speed-patient / --try-speed / --test-speed of `audiowmark get` (src/audiowmark.cc:831-854) */
 void
 awmh_set_speed_params (int detect_speed, int detect_speed_patient, double try_speed, double test_speed)

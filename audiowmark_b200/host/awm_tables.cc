@@ -56,8 +56,12 @@ gen_mix_entries (const Key& key)
       for (size_t i = 0; i < up.size(); i++)
         entries.push_back ({ bit_pos_gen.data_frame (f), up[i], down[i] });
     }
-  Random random (key, 0, Random::Stream::mix);
-  random.shuffle (entries);
+  /* --linear (src/wmget.cc:110-152): the same (frame, up, down) triples in generation order, no mixing */
+  if (Params::mix)
+    {
+      Random random (key, 0, Random::Stream::mix);
+      random.shuffle (entries);
+    }
   return entries;
 }
 

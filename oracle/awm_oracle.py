@@ -257,6 +257,8 @@ def bit_vec_to_str(v) -> str:                        # utils.cc:113-133
 
 def parse_payload(bits: str, P: Params) -> list:     # wmcommon.cc:210-238
     v = bit_str_to_vec(bits)
+    if P.payload_short and len(v) != P.payload_size:
+        return []
     if not v or len(v) > P.payload_size:
         return []
     if len(v) < P.payload_size:
@@ -304,8 +306,69 @@ def conv_decode_soft(block_type: int, coded: np.ndarray):    # convcode.cc:128-2
 
 # --------------------------------------------------------------------------- key-derived tables
 
+SHORT_CODES = {      # shortcode.cc:26-83: best known linear codes [n, k] over GF(2); row i as a bit mask, bit j = column j
+    12: (56, [0xfeb8b646cb1001, 0x05d0daf7f1b002, 0x68aec1274e8804, 0x73c692698c2808, 0xda51f4b6048810, 0x57617a230f1020, 0xb9eda54a308040, 0x3f9dfcd0163080, 0xd4b8e8ef2d2900, 0x6b339794612200, 0x8acc5794991c00, 0x9ff7fc1fffc000]),
+    16: (61, [0x0498284fd74f0001, 0x0930509fae9e0002, 0x1260a13f5d3c0004, 0x139f97d14b610008, 0x1061fa0d67db0010, 0x179d21b53eaf0020, 0x186496c58c470040, 0x0797f824e9970080, 0x0f2ff049d32e0100, 0x1e5fe093a65c0200, 0x0be11488bda10400, 0x17c229117b420800, 0x18da878d079d1000, 0x06ebdab5fe232000, 0x0dd7b56bfc464000, 0x1baf6ad7f88c8000]),
+    20: (65, [0x1dcfaff02fec40001, 0x1fb826f058a840002, 0x1b5734f0b62040004, 0x128910f16b3040008, 0x013558f2d11040010, 0x1ab9a385b11e00020, 0x1448828b599e00040, 0x09aac096889e00080, 0x0e9a2fdd3ed040100, 0x05e74dda6e9e00200, 0x16013544f2d040400, 0x08251299e2d440800, 0x08993753d69601000, 0x0cfdc15782c442000, 0x012891cf16b204000, 0x1f9e8d6e028848000, 0x1b1a62cc026450000, 0x1213bc8803b860000, 0x18d31360133a80000, 0x109de2401dd300000]),
+}
+
+
+def short_encode_blk(in_bits, k):                    # shortcode.cc:136-157
+    n, rows = SHORT_CODES[k]
+    w = 0
+    for bit in range(k):
+        if in_bits[bit]:
+            w ^= rows[bit]
+    return [(w >> j) & 1 for j in range(n)]
+
+
+def short_decode_blk(coded_bits, k):                 # shortcode.cc:171-213 (first message whose code word matches; [] if none)
+    n, rows = SHORT_CODES[k]
+    r = 0
+    for j, b in enumerate(coded_bits):
+        r |= (int(b) & 1) << j
+    table = _short_codebook(k)
+    c = table.get(r)
+    return [] if c is None else [(c >> bit) & 1 for bit in range(k)]
+
+
+_SHORT_BOOK = {}
+
+
+def _short_codebook(k):
+    if k not in _SHORT_BOOK:
+        n, rows = SHORT_CODES[k]
+        book = {0: 0}
+        words = [0]
+        for bit in range(k):                          # gray-free doubling: words of messages < 2^(bit+1)
+            words = words + [w ^ rows[bit] for w in words]
+        for c, w in enumerate(words):
+            book.setdefault(w, c)                    # ascending message order: first match wins
+        _SHORT_BOOK[k] = book
+    return _SHORT_BOOK[k]
+
+
+def code_message_bits(P: Params) -> int:
+    return SHORT_CODES[P.payload_size][0] if P.payload_short else P.payload_size
+
+
+def code_size(block_type: int, P: Params) -> int:    # shortcode.cc:123-127
+    return conv_code_size(block_type, code_message_bits(P))
+
+
+def code_encode(block_type: int, in_bits: list, P: Params) -> list:      # shortcode.cc:117-121
+    return conv_encode(block_type, short_encode_blk(in_bits, P.payload_size) if P.payload_short else in_bits)
+
+
+def code_decode_soft(block_type: int, coded, P: Params):                 # shortcode.cc:129-133
+    bits, err = conv_decode_soft(block_type, coded)
+    if P.payload_short:
+        bits = short_decode_blk(bits, P.payload_size)
+    return bits, err
+
+
 def mark_data_frame_count(P: Params) -> int:         # wmcommon.cc:167-171
-    return conv_code_size(A, P.payload_size) * P.frames_per_bit
+    return code_size(A, P) * P.frames_per_bit
 
 
 def mark_sync_frame_count(P: Params) -> int:         # wmcommon.cc:173-177
@@ -371,7 +434,7 @@ KEEP, UP, DOWN = 0, 1, 2
 def init_frame_mod(key: Key, ab: int, bitvec: list, P: Params) -> np.ndarray:
     """wmadd.cc:49-59,86-162 -> uint8 [frames_per_block][max_band+1]."""
     fm = np.zeros((frames_per_block(P), P.max_band + 1), dtype=np.uint8)
-    fec = randomize_bit_order(key, conv_encode(B if ab else A, bitvec), True)
+    fec = randomize_bit_order(key, code_encode(B if ab else A, bitvec, P), True)
     # mark_sync (wmadd.cc:129-146)
     udg, bpg = UpDownGen(key, STREAM_SYNC_UP_DOWN, P), BitPosGen(key, P)
     for f in range(mark_sync_frame_count(P)):
@@ -921,6 +984,8 @@ class ResultSet:                                     # wmget.cc:163-474
         self.debug_sync = ""
 
     def add_pattern(self, key, time, sync_score, bit_vec, decode_error, ptype, speed=1.0):
+        if not len(bit_vec):                         # short payload: no code word matched (wmget.cc:549,594,698,814)
+            return
         self.patterns.append(Pattern(key, time, list(bit_vec), np.float32(decode_error), sync_score, ptype, speed))
 
     def apply_time_offset(self, off):
@@ -1012,7 +1077,7 @@ def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=
         if raw is None:
             continue
         prv.append(RawBits(sc.index, sc.quality, raw, sc.block_type))
-        bits, err = conv_decode_soft(sc.block_type, normalize_soft_bits(raw, P))
+        bits, err = code_decode_soft(sc.block_type, normalize_soft_bits(raw, P), P)
         result_set.add_pattern(key, sc.index / rate, sc, bits, err, TYPE_BLOCK, speed)
     if trace is not None:
         trace["raw_bits"] = prv
@@ -1029,7 +1094,7 @@ def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=
                 a, b = prv[best_j], prv[i]
                 ab = np.empty(len(a.raw) * 2, dtype=np.float32)
                 ab[0::2], ab[1::2] = a.raw, b.raw
-                bits, err = conv_decode_soft(AB, normalize_soft_bits(ab, P))
+                bits, err = code_decode_soft(AB, normalize_soft_bits(ab, P), P)
                 result_set.add_pattern(key, b.index / rate, Score(b.index, (a.quality + b.quality) / 2, AB), bits, err, TYPE_BLOCK, speed)
     # all (:606-701)
     best_all = []
@@ -1061,7 +1126,7 @@ def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=
         if sync_sum(all_blocks) > sync_sum(best_all):
             best_all = all_blocks
     if len(best_all) > 1:
-        raw_all = np.zeros(conv_code_size(AB, P.payload_size), dtype=np.float32)
+        raw_all = np.zeros(code_size(AB, P), dtype=np.float32)
         norm = [0, 0]
         q = 0.0
         for bi in best_all:
@@ -1073,7 +1138,7 @@ def block_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=
         raw_all[0::2] = raw_all[0::2] / np.float32(max(norm[0], 1))
         raw_all[1::2] = raw_all[1::2] / np.float32(max(norm[1], 1))
         q /= norm[0] + norm[1]
-        bits, err = conv_decode_soft(AB, normalize_soft_bits(raw_all, P))
+        bits, err = code_decode_soft(AB, normalize_soft_bits(raw_all, P), P)
         result_set.add_pattern(key, 0.0, Score(0, q, A), bits, err, TYPE_ALL, speed)
     return sync_scores
 
@@ -1115,7 +1180,7 @@ def clip_decoder_run(key: Key, samples, result_set: ResultSet, P: Params, rate=4
                 raw[0::2], raw[1::2] = r1, r2
             else:
                 raw[0::2], raw[1::2] = r2, r1
-            bits, err = conv_decode_soft(AB, normalize_soft_bits(raw, P))
+            bits, err = code_decode_soft(AB, normalize_soft_bits(raw, P), P)
             result_set.add_pattern(key, time_offset, Score(int(time_offset * rate), sc.quality, sc.block_type), bits, err, TYPE_CLIP, speed)
 
 

@@ -121,6 +121,19 @@ def main():
                     "add_stderr": p.stderr, "cmp_stdout": c.stdout, "json": json.load(open(js))}
         G["rate32000_add"] = rate_case("r32", 200, 32000, ("--snr",))
         G["rate48000_add_nolimiter"] = rate_case("r48nl", 11.3, 48000, ("--snr", "--test-no-limiter"))
+        # ---- short payload (tests/short-payload-test.sh, 120 s instead of 200 s) and --linear
+        def opt_case(name, payload, opts):
+            src, dst = os.path.join(tmp, name + ".wav"), os.path.join(tmp, name + "_wm.wav")
+            run("test-gen-noise", src, 120, 44100)
+            p = run("add", *opts, src, dst, payload)
+            g = run("get", *opts, "--json", js, dst)
+            c = run("cmp", *opts, dst, payload, ok_codes=(0, 1))
+            return {"opts": list(opts), "payload": payload, "output_sha256": sha(pcm16(dst)), "add_stderr": p.stderr, "get_stdout": g.stdout,
+                    "cmp_stdout": c.stdout, "cmp_rc": c.returncode, "json": json.load(open(js))}
+        G["short12"] = opt_case("s12", "abc", ("--short", 12))
+        G["short16"] = opt_case("s16", "abcd", ("--short", 16))
+        G["short20"] = opt_case("s20", "abcde", ("--short", 20))
+        G["linear120"] = opt_case("lin", T.PAYLOAD, ("--linear",))
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     json.dump(G, open(out, "w"), indent=1, sort_keys=True)
     print("wrote", out, os.path.getsize(out), "bytes")

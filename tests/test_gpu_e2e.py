@@ -134,3 +134,31 @@ def test_cli_round_trip(tmp_path):
     # json on stdout
     p = subprocess.run([cli, "get", "--json", "-", wm], capture_output=True, text=True)
     assert json.loads(p.stdout)["matches"][0]["bits"] == msg
+
+
+@pytest.mark.parametrize("name", ["short12", "short16", "short20", "linear120"])
+def test_short_payload_and_linear_vs_reference(name):
+    """--short 12/16/20 (tests/short-payload-test.sh) and --linear: GPU add within 1e-5 RMS of the oracle (== reference PCM,
+    CPU test), GPU get reproduces the reference's pattern list"""
+    g = G[name]
+    opts = g["opts"]
+    Pc = O.Params()
+    short = int(opts[opts.index("--short") + 1]) if "--short" in opts else 0
+    if short:
+        Pc.payload_short, Pc.payload_size = True, short
+    if "--linear" in opts:
+        Pc.mix = False
+    x = q16(O.gen_noise(120))
+    H.set_params(mix="--linear" not in opts)
+    H.set_short_payload(short)
+    try:
+        out = H.add(x, g["payload"])
+        ref = O.embed(x, O.Key(), g["payload"], Pc)
+        assert T.rms(out - ref.samples) < 1e-5
+        y = q16(ref.samples)
+        doc = H.get(y)
+    finally:
+        H.set_short_payload(0)
+        H.set_params()
+    n_real = check_matches(doc, g["json"])
+    assert n_real >= 3 and all(m["bits"] == g["payload"] for m in doc["matches"][:n_real])

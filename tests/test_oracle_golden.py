@@ -160,3 +160,28 @@ def test_embed_other_sample_rates_bit_exact_vs_reference(name):
     assert sha(O.quantize_sndfile16(r.samples)) == g["output_sha256"]
     assert ("Data Blocks:  %d\n" % r.data_blocks) in g["add_stderr"]
     assert ("SNR:          %f dB\n" % r.snr_db) in g["add_stderr"]
+
+
+def _opt_params(opts):
+    Pc = O.Params()
+    if "--linear" in opts:
+        Pc.mix = False
+    if "--short" in opts:
+        Pc.payload_short, Pc.payload_size = True, int(opts[opts.index("--short") + 1])
+    return Pc
+
+
+@pytest.mark.parametrize("name", ["short12", "short20", "linear120"])
+def test_short_payload_and_linear_exact_vs_reference(name):
+    """tests/short-payload-test.sh (block code [56,12] / [65,20] in front of the convolutional code) and --linear"""
+    g = G[name]
+    Pc = _opt_params(g["opts"])
+    x = q16(O.gen_noise(120))
+    r = O.embed(x, O.Key(), g["payload"], Pc)
+    y16 = O.quantize_sndfile16(r.samples)
+    assert sha(y16) == g["output_sha256"]
+    assert ("Data Blocks:  %d\n" % r.data_blocks) in g["add_stderr"]
+    rs = O.get_watermark(O.int16_to_float(y16), [O.Key()], Pc)
+    assert "\n".join(rs.lines()) + "\n" == g["get_stdout"]
+    assert rs.json_doc(120) == fmt_ref_json(g["json"])
+    assert g["cmp_rc"] == 0
