@@ -28,7 +28,7 @@ EXPORTS = [
     "awm_profile_enable", "awm_profile_report", "awm_host_alloc", "awm_host_free",
     "awm_fft_r2c", "awm_fft_c2r", "awm_set_embed_tables", "awm_set_sync_tables", "awm_set_mix_tables",
     "awm_pcm_bind", "awm_pcm_prefetch", "awm_embed", "awm_sync_approx", "awm_sync_peaks", "awm_sync_refine", "awm_decode_blocks", "awm_viterbi",
-    "awm_resample", "awm_pcm_push_resampled", "awm_pcm_pop", "awm_copy_to_host", "awm_is_device_pointer", "awm_speed_scan", "awm_embed_resampled", "awm_gather",
+    "awm_resample", "awm_pcm_push_resampled", "awm_pcm_pop", "awm_copy_to_host", "awm_is_device_pointer", "awm_speed_scan", "awm_embed_resampled", "awm_gather", "awm_pcm_bind_s16", "awm_pcm_prefetch_s16", "awm_pcm_device", "awm_embed_s16",
 ]
 
 _lib = None
@@ -148,6 +148,14 @@ class Context:
 
     # ---- PCM
     def pcm_bind(self, pcm, n_frames: int | None = None, channels: int | None = None, pad_start: int = 0, pad_end: int = 0):
+        if isinstance(pcm, np.ndarray) and pcm.dtype == np.int16:        # 16 bit PCM: converted on the device
+            pcm = np.ascontiguousarray(pcm)
+            n_frames, channels = pcm.shape
+            self._keep = pcm
+            self._ck(self.lib.awm_pcm_bind_s16(self.h, _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
+                                               ctypes.c_size_t(pad_start), ctypes.c_size_t(pad_end)))
+            self.synchronize()
+            return
         if isinstance(pcm, np.ndarray):
             pcm = np.ascontiguousarray(pcm, np.float32)
             n_frames, channels = pcm.shape

@@ -87,8 +87,8 @@ struct awm_ctx
 
   // bound PCM
   const float *pcm = nullptr; size_t pcm_frames = 0; int pcm_ch = 0;
-  DevBuf pcm_own;
-  struct Prefetch { DevBuf buf; const float *src = nullptr; size_t n_frames = 0; int ch = 0; cudaEvent_t done = nullptr; bool valid = false; };
+  DevBuf pcm_own, pcm16_own;
+  struct Prefetch { DevBuf buf, buf16; bool s16 = false; const void *src = nullptr; size_t n_frames = 0; int ch = 0; cudaEvent_t done = nullptr; bool valid = false; };
   Prefetch pref[2];
   int pref_next = 0;
 
@@ -97,7 +97,7 @@ struct awm_ctx
   DevBuf cand_start, cand_noff, r_ud, r_cnt, rvalid;   // refine
   DevBuf blk_start, D, raw;          // decode
   DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
-  DevBuf emb_in, emb_out, peaks, snr;
+  DevBuf emb_in, emb_out, emb_in16, emb_out16, peaks, snr;
 
   // resampler / speed scan
   struct CoefTab { DevBuf buf; int h = 0; };
@@ -263,10 +263,10 @@ awm_destroy (awm_ctx *ctx)
     return;
   cudaSetDevice (ctx->device);
   cudaStreamSynchronize (ctx->stream);
-  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt,
+  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->pcm16_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt,
                      &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
                      &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
-                     &ctx->emb_in, &ctx->emb_out, &ctx->peaks, &ctx->snr, &ctx->rs_in, &ctx->rs_out, &ctx->rs_jobs, &ctx->pcm_rs,
+                     &ctx->emb_in, &ctx->emb_out, &ctx->emb_in16, &ctx->emb_out16, &ctx->peaks, &ctx->snr, &ctx->rs_in, &ctx->rs_out, &ctx->rs_jobs, &ctx->pcm_rs,
                      &ctx->win512, &ctx->sp_clip, &ctx->sp_sub, &ctx->sp_mags, &ctx->sp_mag_jobs, &ctx->sp_cmp_jobs, &ctx->sp_best };
   for (DevBuf *b : bufs)
     b->release();
@@ -275,6 +275,7 @@ awm_destroy (awm_ctx *ctx)
   for (auto& pf : ctx->pref)
     {
       pf.buf.release();
+      pf.buf16.release();
       if (pf.done)
         cudaEventDestroy (pf.done);
     }
@@ -552,18 +553,22 @@ awm_set_mix_tables (awm_ctx *ctx, int key_slot, const awm_mix_entry *entries, in
 
 /* ---------------------------------------------------------------- PCM */
 
+namespace {
+
+/* awm_pcm_bind / awm_pcm_bind_s16 */
 int
-awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end)
+pcm_bind_any (awm_ctx *ctx, const void *pcm_v, bool s16, size_t n_frames, int channels, size_t pad_start, size_t pad_end)
 {
-  if (channels <= 0 || (!pcm && n_frames))
+  if (channels <= 0 || (!pcm_v && n_frames))
     return fail (ctx, "awm_pcm_bind: bad arguments");
   CK (cudaSetDevice (ctx->device));
   ctx->pushed = false;                           // a new bind replaces whatever awm_pcm_push_resampled saved
-  const bool dev = pcm && is_device_ptr (pcm);
+  const float *pcm = s16 ? nullptr : static_cast<const float *> (pcm_v);
+  const bool dev = pcm_v && is_device_ptr (pcm_v);
   awm_ctx::Prefetch *hit = nullptr;
   if (!dev && pad_start == 0 && pad_end == 0)
     for (auto& pf : ctx->pref)
-      if (pf.valid && pf.src == pcm && pf.n_frames == n_frames && pf.ch == channels)
+      if (pf.valid && pf.src == pcm_v && pf.n_frames == n_frames && pf.ch == channels && pf.s16 == s16)
         hit = &pf;
   if (hit)
     {
@@ -571,7 +576,7 @@ awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, siz
       ctx->pcm = hit->buf.as<float>();
       hit->valid = false;
     }
-  else if (dev && pad_start == 0 && pad_end == 0)
+  else if (dev && !s16 && pad_start == 0 && pad_end == 0)
     {
       ctx->pcm = pcm;
     }
@@ -582,9 +587,23 @@ awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, siz
       float *d = ctx->pcm_own.as<float>();
       if (pad_start)
         CK (cudaMemsetAsync (d, 0, pad_start * channels * sizeof (float), ctx->stream));
-      if (n_frames)
+      if (n_frames && !s16)
         CK (cudaMemcpyAsync (d + pad_start * channels, pcm, n_frames * channels * sizeof (float),
                              dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+      if (n_frames && s16)
+        {
+          const int16_t *src16 = static_cast<const int16_t *> (pcm_v);
+          const long long n_val = (long long) (n_frames * channels);
+          if (!dev)
+            {
+              CK (ctx->pcm16_own.reserve (n_val * sizeof (int16_t)));
+              CK (cudaMemcpyAsync (ctx->pcm16_own.p, src16, n_val * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->stream));
+              src16 = ctx->pcm16_own.as<int16_t>();
+            }
+          PROF (ctx);
+          k_s16_to_f32<<<unsigned (((n_val + 1) / 2 + 255) / 256), 256, 0, ctx->stream>>> (src16, d + pad_start * channels, n_val);
+          LAUNCH_CHECK ("k_s16_to_f32");
+        }
       if (pad_end)
         CK (cudaMemsetAsync (d + (pad_start + n_frames) * channels, 0, pad_end * channels * sizeof (float), ctx->stream));
       ctx->pcm = d;
@@ -595,7 +614,7 @@ awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, siz
 }
 
 int
-awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels)
+pcm_prefetch_any (awm_ctx *ctx, const void *pcm, bool s16, size_t n_frames, int channels)
 {
   if (!pcm || !n_frames || channels <= 0)
     return fail (ctx, "awm_pcm_prefetch: bad arguments");
@@ -616,29 +635,67 @@ awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels)
   CK (cudaEventDestroy (busy));
   if (ctx->pcm == pf.buf.p)
     ctx->pcm_ch = 0;                              // the bound PCM is about to be overwritten: force a new bind
-  CK (pf.buf.reserve (n_frames * channels * sizeof (float)));
+  const size_t n_val = n_frames * channels;
+  CK (pf.buf.reserve (n_val * sizeof (float)));
   if (!pf.done)
     CK (cudaEventCreateWithFlags (&pf.done, cudaEventDisableTiming));
-  CK (cudaMemcpyAsync (pf.buf.p, pcm, n_frames * channels * sizeof (float), cudaMemcpyHostToDevice, ctx->s_in));
+  if (s16)
+    {
+      CK (pf.buf16.reserve (n_val * sizeof (int16_t)));
+      CK (cudaMemcpyAsync (pf.buf16.p, pcm, n_val * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->s_in));
+      k_s16_to_f32<<<unsigned (((n_val + 1) / 2 + 255) / 256), 256, 0, ctx->s_in>>> (pf.buf16.as<int16_t>(), pf.buf.as<float>(), (long long) n_val);
+      LAUNCH_CHECK ("k_s16_to_f32");
+    }
+  else
+    CK (cudaMemcpyAsync (pf.buf.p, pcm, n_val * sizeof (float), cudaMemcpyHostToDevice, ctx->s_in));
   CK (cudaEventRecord (pf.done, ctx->s_in));
   pf.src = pcm;
   pf.n_frames = n_frames;
   pf.ch = channels;
+  pf.s16 = s16;
   pf.valid = true;
   ctx->pref_next ^= 1;
   return 0;
 }
 
+} // namespace
+
+int awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end) { return pcm_bind_any (ctx, pcm, false, n_frames, channels, pad_start, pad_end); }
+int awm_pcm_bind_s16 (awm_ctx *ctx, const int16_t *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end) { return pcm_bind_any (ctx, pcm, true, n_frames, channels, pad_start, pad_end); }
+int awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels) { return pcm_prefetch_any (ctx, pcm, false, n_frames, channels); }
+int awm_pcm_prefetch_s16 (awm_ctx *ctx, const int16_t *pcm, size_t n_frames, int channels) { return pcm_prefetch_any (ctx, pcm, true, n_frames, channels); }
+
+/* the device copy of the bound PCM (float, [frames][channels]): lets a caller that bound 16 bit or host audio run device-pointer
+ * entry points (awm_speed_scan, awm_gather) on it without another transfer */
+const float *
+awm_pcm_device (awm_ctx *ctx, size_t *n_frames, int *channels)
+{
+  if (!ctx || !ctx->pcm_ch)
+    return nullptr;
+  if (n_frames)
+    *n_frames = ctx->pcm_frames;
+  if (channels)
+    *channels = ctx->pcm_ch;
+  return ctx->pcm;
+}
+
 /* ---------------------------------------------------------------- embed */
 
+namespace {
+
+/* awm_embed / awm_embed_s16: `s16` selects 16 bit PCM buffers (in16 / out16) that are converted on the device */
 int
-awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels,
+embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frames, int channels,
            uint64_t first_frame_number, int frames_pad_start, double water_delta,
            int limiter_block, float limiter_ceiling, double *snr_power)
 {
+  const float *in = s16 ? nullptr : static_cast<const float *> (in_v);
+  float *out = s16 ? nullptr : static_cast<float *> (out_v);
+  const int16_t *in16 = s16 ? static_cast<const int16_t *> (in_v) : nullptr;
+  int16_t *out16 = s16 ? static_cast<int16_t *> (out_v) : nullptr;
   if (!ctx->embed_fpb)
     return fail (ctx, "awm_embed: awm_set_embed_tables has not been called");
-  if (channels <= 0 || (n_frames && (!in || !out)))
+  if (channels <= 0 || (n_frames && (!in_v || !out_v)))
     return fail (ctx, "awm_embed: bad arguments");
   if (snr_power)
     snr_power[0] = snr_power[1] = 0;
@@ -646,7 +703,9 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
     return 0;
   CK (cudaSetDevice (ctx->device));
   const size_t n_val = n_frames * channels;
-  const bool in_dev = is_device_ptr (in), out_dev = is_device_ptr (out);
+  /* 16 bit buffers always go through the float staging buffers; a device resident 16 bit buffer is converted in place of a copy */
+  const bool in16_dev = s16 && is_device_ptr (in16), out16_dev = s16 && is_device_ptr (out16);
+  const bool in_dev = !s16 && is_device_ptr (in), out_dev = !s16 && is_device_ptr (out);
   const float *d_in = in;
   float *d_out = out;
   if (!in_dev)
@@ -659,6 +718,38 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
       CK (ctx->emb_out.reserve (n_val * sizeof (float)));
       d_out = ctx->emb_out.as<float>();
     }
+  const int16_t *d_in16 = in16;
+  int16_t *d_out16 = out16;
+  if (s16 && !in16_dev)
+    {
+      CK (ctx->emb_in16.reserve (n_val * sizeof (int16_t)));
+      d_in16 = ctx->emb_in16.as<int16_t>();
+    }
+  if (s16 && !out16_dev)
+    {
+      CK (ctx->emb_out16.reserve (n_val * sizeof (int16_t)));
+      d_out16 = ctx->emb_out16.as<int16_t>();
+    }
+  auto to_float = [&] (long long v0, long long v1, cudaStream_t st) -> int     /* values [v0, v1) of the 16 bit input -> emb_in */
+    {
+      if (v1 <= v0)
+        return 0;
+      if (st == ctx->stream)          /* the profile events live on the context stream */
+        PROF (ctx);
+      k_s16_to_f32<<<unsigned (((v1 - v0 + 1) / 2 + 255) / 256), 256, 0, st>>> (d_in16 + v0, ctx->emb_in.as<float>() + v0, v1 - v0);
+      LAUNCH_CHECK ("k_s16_to_f32");
+      return 0;
+    };
+  auto to_s16 = [&] (long long v0, long long v1, cudaStream_t st) -> int
+    {
+      if (v1 <= v0)
+        return 0;
+      if (st == ctx->stream)
+        PROF (ctx);
+      k_f32_to_s16<<<unsigned (((v1 - v0 + 1) / 2 + 255) / 256), 256, 0, st>>> (d_out + v0, d_out16 + v0, v1 - v0);
+      LAUNCH_CHECK ("k_f32_to_s16");
+      return 0;
+    };
   const long long n_real = (long long) ((n_frames + kFrame - 1) / kFrame);
   const long long n_proc = n_real + 1;
   long long n_blocks = 0;
@@ -702,7 +793,7 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
    * the same as for one launch: a piece only restricts which frames a launch emits, halo frames are read from the
    * (already copied) neighbour pieces, the limiter of a piece runs once the block peaks after it are final. */
   const long long kPiece = 12288;                            // 1024-frames per piece (12.6 M sample-frames, 100 MB stereo)
-  const bool pipelined = !in_dev && !out_dev && n_proc > 2 * kPiece;
+  const bool pipelined = !in_dev && !out_dev && !in16_dev && !out16_dev && n_proc > 2 * kPiece;
   const int n_pieces = pipelined ? int ((n_proc + kPiece - 1) / kPiece) : 1;
   auto piece_frames = [&] (int p, long long& fb, long long& fe) { fb = pipelined ? p * kPiece : 0; fe = pipelined ? std::min<long long> (fb + kPiece, n_proc) : n_proc; };
   auto piece_samples = [&] (int p, long long& s0, long long& s1) { long long fb, fe; piece_frames (p, fb, fe); s0 = std::min<long long> (fb * kFrame, n_frames); s1 = std::min<long long> (fe * kFrame, n_frames); };
@@ -728,11 +819,25 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
         {
           long long s0, s1;
           piece_samples (p, s0, s1);
-          if (s1 > s0)
+          if (s1 > s0 && !s16)
             CK (cudaMemcpyAsync (ctx->emb_in.as<float>() + s0 * channels, in + s0 * channels, size_t (s1 - s0) * channels * sizeof (float),
                                  cudaMemcpyHostToDevice, ctx->s_in));
+          if (s1 > s0 && s16)
+            {
+              CK (cudaMemcpyAsync (ctx->emb_in16.as<int16_t>() + s0 * channels, in16 + s0 * channels, size_t (s1 - s0) * channels * sizeof (int16_t),
+                                   cudaMemcpyHostToDevice, ctx->s_in));
+              if (to_float (s0 * channels, s1 * channels, ctx->s_in))
+                return 1;
+            }
           CK (cudaEventRecord (ev_in[p], ctx->s_in));
         }
+    }
+  else if (s16)
+    {
+      if (!in16_dev)
+        CK (cudaMemcpyAsync (ctx->emb_in16.p, in16, n_val * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->stream));
+      if (to_float (0, (long long) n_val, ctx->stream))
+        return 1;
     }
   else if (!in_dev)
     CK (cudaMemcpyAsync (ctx->emb_in.p, in, n_val * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
@@ -752,9 +857,16 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
         {
           CK (cudaEventRecord (ev_out[p], ctx->stream));
           CK (cudaStreamWaitEvent (ctx->s_out, ev_out[p], 0));
-          if (s1 > s0)
+          if (s1 > s0 && !s16)
             CK (cudaMemcpyAsync (out + s0 * channels, d_out + s0 * channels, size_t (s1 - s0) * channels * sizeof (float),
                                  cudaMemcpyDeviceToHost, ctx->s_out));
+          if (s1 > s0 && s16)
+            {
+              if (to_s16 (s0 * channels, s1 * channels, ctx->s_out))
+                return 1;
+              CK (cudaMemcpyAsync (out16 + s0 * channels, d_out16 + s0 * channels, size_t (s1 - s0) * channels * sizeof (int16_t),
+                                   cudaMemcpyDeviceToHost, ctx->s_out));
+            }
         }
       return 0;
     };
@@ -781,13 +893,38 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
           cudaEventDestroy (ev_out[p]);
         }
     }
+  else if (s16)
+    {
+      if (to_s16 (0, (long long) n_val, ctx->stream))
+        return 1;
+      if (!out16_dev)
+        CK (cudaMemcpyAsync (out16, d_out16, n_val * sizeof (int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
   else if (!out_dev)
     CK (cudaMemcpyAsync (out, d_out, n_val * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
   if (snr_power)
     CK (cudaMemcpyAsync (snr_power, ctx->snr.p, 2 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (!out_dev || snr_power)
+  if ((s16 ? !out16_dev : !out_dev) || snr_power)
     CK (cudaStreamSynchronize (ctx->stream));
   return 0;
+}
+
+} // namespace
+
+int
+awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels,
+           uint64_t first_frame_number, int frames_pad_start, double water_delta,
+           int limiter_block, float limiter_ceiling, double *snr_power)
+{
+  return embed_any (ctx, in, out, false, n_frames, channels, first_frame_number, frames_pad_start, water_delta, limiter_block, limiter_ceiling, snr_power);
+}
+
+int
+awm_embed_s16 (awm_ctx *ctx, const int16_t *in, int16_t *out, size_t n_frames, int channels,
+               uint64_t first_frame_number, int frames_pad_start, double water_delta,
+               int limiter_block, float limiter_ceiling, double *snr_power)
+{
+  return embed_any (ctx, in, out, true, n_frames, channels, first_frame_number, frames_pad_start, water_delta, limiter_block, limiter_ceiling, snr_power);
 }
 
 /* ---------------------------------------------------------------- sync search */

@@ -89,6 +89,53 @@ k_resample (const ResampleJob *__restrict__ jobs, int c_dyn)
     }
 }
 
+// 16 bit PCM <-> float exactly as the reference converts around its float pipeline: reading through libsndfile's int
+// API and scaling by 2^-31 (src/sfinputstream.cc:189-210: a 16 bit sample arrives left justified), writing with
+// float_to_int_clip<32> (src/rawconverter.hh:34-50) and keeping the 16 most significant bits (src/sfoutputstream.cc:148-155).
+// Converting on the device halves the PCIe traffic of 16 bit audio.
+__global__ void
+k_s16_to_f32 (const int16_t *__restrict__ in, float *__restrict__ out, long long n)
+{
+  const long long i = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n)
+    {
+      const short2 v = *reinterpret_cast<const short2 *> (in + i);
+      *reinterpret_cast<float2 *> (out + i) = make_float2 (float (int (v.x) << 16) * (1.0f / 2147483648.0f), float (int (v.y) << 16) * (1.0f / 2147483648.0f));
+    }
+  else if (i < n)
+    out[i] = float (int (in[i]) << 16) * (1.0f / 2147483648.0f);
+}
+
+__device__ __forceinline__ int16_t
+f32_to_s16 (float f)
+{
+  const float snorm = __fmul_rn (f, 2147483648.0f);
+  int v;
+  if (snorm >= 2147483648.0f)            // max_value = float (2^31 - 1) = 2^31
+    v = 0x7fffffff;
+  else if (snorm <= -2147483648.0f)
+    v = int (0x80000000u);
+  else
+    v = int (snorm);                     // truncation toward zero
+  return int16_t (v >> 16);
+}
+
+__global__ void
+k_f32_to_s16 (const float *__restrict__ in, int16_t *__restrict__ out, long long n)
+{
+  const long long i = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n)
+    {
+      const float2 v = *reinterpret_cast<const float2 *> (in + i);
+      short2 o;
+      o.x = f32_to_s16 (v.x);
+      o.y = f32_to_s16 (v.y);
+      *reinterpret_cast<short2 *> (out + i) = o;
+    }
+  else if (i < n)
+    out[i] = f32_to_s16 (in[i]);
+}
+
 // dst[k] = src[idx[k]]: the sparse sample subset get_clip_locations hashes (src/wmspeed.cc:538-543) when the PCM lives in device memory
 __global__ void
 k_gather (const float *__restrict__ src, const unsigned long long *__restrict__ idx, long long n, float *__restrict__ dst)

@@ -118,6 +118,42 @@ add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_fram
   return 0;
 }
 
+/* `add` between two 16 bit PCM buffers in host memory (44.1 kHz): the int <-> float conversions of SFInputStream / SFOutputStream
+ * run on the device (awm_embed_s16), only 2 + 2 bytes per sample cross PCIe */
+int
+add_watermark_buffer_s16 (const Key& key, const int16_t *in, int16_t *out, size_t n_frames, int n_channels, int sample_rate,
+                          const string& bits, AddStats *stats, uint64_t first_frame_number)
+{
+  const vector<int> bitvec = parse_payload (bits);
+  if (bitvec.empty())
+    return 1;
+  if (sample_rate != Params::mark_sample_rate)
+    {
+      error ("audiowmark: 16 bit buffers are only accepted at %d Hz (use the float entry point for other rates)\n", Params::mark_sample_rate);
+      return 1;
+    }
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx || !Engine::set_embed_tables (key, bitvec))
+    return 1;
+  const int limiter_block = Params::test_no_limiter ? 0 : int (sample_rate * int (Params::limiter_block_size_ms) / 1000);
+  double snr_power[2] = { 0, 0 };
+  if (awm_embed_s16 (ctx, in, out, n_frames, n_channels, first_frame_number, Params::frames_pad_start, Params::water_delta,
+                     limiter_block, Params::limiter_ceiling, (Params::snr || stats) ? snr_power : nullptr))
+    {
+      error ("audiowmark: embedding failed: %s\n", awm_last_error (ctx));
+      return 1;
+    }
+  if (stats)
+    {
+      const size_t fpb = frames_per_block(), f0 = 2 * fpb - Params::frames_pad_start;
+      const size_t runs = gen_runs (n_frames, !Params::test_no_limiter, sample_rate * int (Params::limiter_block_size_ms) / 1000);
+      const int blocks = int ((f0 + runs) / fpb - f0 / fpb);
+      stats->data_blocks = std::max (blocks - 1, 0);
+      stats->snr_db = snr_power[0] > 0 ? 10 * log10 (snr_power[1] / snr_power[0]) : INFINITY;
+    }
+  return 0;
+}
+
 int
 add_stream_watermark (const Key& key, AudioInputStream *in_stream, AudioOutputStream *out_stream, const string& bits, size_t zero_frames)
 {

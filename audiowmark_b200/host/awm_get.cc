@@ -576,6 +576,7 @@ class ClipDecoder
   }
 public:
   explicit ClipDecoder (double speed) : frames_per_blk (mark_sync_frame_count() + mark_data_frame_count()), speed (speed) {}
+  bool wanted (size_t n_frames) const { return int (n_frames / Params::frame_size) < frames_per_blk * 3.1; }   /* clip decoder is only used for small inputs */
   void
   run (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, vector<VitJob>& pending, int chunk)
   {
@@ -588,19 +589,64 @@ public:
   }
 };
 
+/* the audio of a chunk: float samples (host or device memory) or 16 bit PCM in host memory, which is converted on the device
+ * (awm_pcm_bind_s16) so that only half the bytes cross PCIe */
+struct PcmRef
+{
+  const float   *f32 = nullptr;
+  const int16_t *s16 = nullptr;
+  PcmRef advanced (size_t values) const { PcmRef r; r.f32 = f32 ? f32 + values : nullptr; r.s16 = s16 ? s16 + values : nullptr; return r; }
+  int bind (awm_ctx *ctx, size_t n_frames, int n_channels) const
+  {
+    return s16 ? awm_pcm_bind_s16 (ctx, s16, n_frames, n_channels, 0, 0) : awm_pcm_bind (ctx, f32, n_frames, n_channels, 0, 0);
+  }
+  int prefetch (awm_ctx *ctx, size_t n_frames, int n_channels) const
+  {
+    return s16 ? awm_pcm_prefetch_s16 (ctx, s16, n_frames, n_channels) : awm_pcm_prefetch (ctx, f32, n_frames, n_channels);
+  }
+  /* float samples in host memory (what the clip decoder cuts and pads): only needed for short inputs */
+  const float *host_floats (awm_ctx *ctx, size_t n_values, vector<float>& storage) const
+  {
+    if (s16)
+      {
+        storage.resize (n_values);
+        const float norm = 1.0 / 0x80000000LL;                 /* src/sfinputstream.cc:207-209 */
+        for (size_t i = 0; i < n_values; i++)
+          storage[i] = (int (s16[i]) << 16) * norm;
+        return storage.data();
+      }
+    if (Engine::is_device_pointer (f32))
+      {
+        storage.resize (n_values);
+        if (awm_copy_to_host (ctx, storage.data(), f32, n_values * sizeof (float)))
+          return nullptr;
+        return storage.data();
+      }
+    return f32;
+  }
+};
+
 /* decode (src/wmget.cc:886-939) for one chunk: everything up to the soft bits; the Viterbi jobs are queued */
 int
-decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vector<Key>& key_list, const float *samples, size_t n_frames,
+decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vector<Key>& key_list, const PcmRef& pcm, size_t n_frames,
               int n_channels, int sample_rate, bool first_chunk, bool print_speed_results = false)
 {
   awm_ctx *ctx = Engine::ctx();
   if (!ctx)
     return 1;
-  if (awm_pcm_bind (ctx, samples, n_frames, n_channels, 0, 0))
+  if (pcm.bind (ctx, n_frames, n_channels))
     {
       error ("audiowmark: %s\n", awm_last_error (ctx));
       return 1;
     }
+  vector<float> host_storage;
+  const float *host_samples = nullptr;          /* fetched lazily: only the clip decoder needs it */
+  auto need_host = [&] () -> const float *
+    {
+      if (!host_samples)
+        host_samples = pcm.host_floats (ctx, n_frames * n_channels, host_storage);
+      return host_samples;
+    };
   /* The strategy for integrating speed detection into decoding (src/wmget.cc:888-928):
    *  - the watermark is always decoded on the original data
    *  - if the detected speed is somewhat different from 1.0, stretched data is decoded as well
@@ -609,7 +655,11 @@ decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vect
     {
       vector<DetectSpeedResult> speed_results;
       if (Params::detect_speed || Params::detect_speed_patient)
-        speed_results = detect_speed (key_list, samples, n_frames, n_channels, sample_rate, print_speed_results);
+        {
+          /* 16 bit input: the float copy that was just bound on the device serves the speed scan as well */
+          const float *speed_samples = pcm.s16 ? awm_pcm_device (ctx, nullptr, nullptr) : pcm.f32;
+          speed_results = detect_speed (key_list, speed_samples, n_frames, n_channels, sample_rate, print_speed_results);
+        }
       else
         for (const auto& key : key_list)
           speed_results.push_back ({ key, Params::try_speed });
@@ -619,7 +669,7 @@ decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vect
           /* resample_ratio (wav_data, speed, mark_sample_rate * speed): the stretched chunk stays on the device */
           const size_t speed_frames = lrint (double (n_frames) * speed_result.speed);
           const int speed_rate = Params::mark_sample_rate * speed_result.speed;
-          if (rebind && awm_pcm_bind (ctx, samples, n_frames, n_channels, 0, 0))
+          if (rebind && pcm.bind (ctx, n_frames, n_channels))
             return 1;
           rebind = false;
           if (awm_pcm_push_resampled (ctx, speed_result.speed, 16, speed_frames))
@@ -634,23 +684,14 @@ decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vect
             {
               /* the clip decoder cuts and pads on the host: short inputs only, so the extra copy is small */
               vector<float> stretched;
-              const float *host_samples = samples;
-              vector<float> host_copy;
-              if (Engine::is_device_pointer (samples))
-                {
-                  host_copy.resize (n_frames * n_channels);
-                  if (awm_copy_to_host (ctx, host_copy.data(), samples, host_copy.size() * sizeof (float)))
-                    return 1;
-                  host_samples = host_copy.data();
-                }
-              if (!resample_ratio (host_samples, n_frames, n_channels, speed_result.speed, stretched))
+              if (!need_host() || !resample_ratio (need_host(), n_frames, n_channels, speed_result.speed, stretched))
                 return 1;
               ClipDecoder speed_clip_decoder (speed_result.speed);
               speed_clip_decoder.run ({ speed_result.key }, stretched.data(), speed_frames, n_channels, speed_rate, pending, chunk);
               rebind = true;
             }
         }
-      if (rebind && awm_pcm_bind (ctx, samples, n_frames, n_channels, 0, 0))
+      if (rebind && pcm.bind (ctx, n_frames, n_channels))
         return 1;
     }
   const double tb0 = get_time();
@@ -661,7 +702,12 @@ decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vect
   if (first_chunk)
     {
       ClipDecoder clip_decoder (1);
-      clip_decoder.run (key_list, samples, n_frames, n_channels, sample_rate, pending, chunk);
+      if (clip_decoder.wanted (n_frames))
+        {
+          if (!need_host())
+            return 1;
+          clip_decoder.run (key_list, need_host(), n_frames, n_channels, sample_rate, pending, chunk);
+        }
     }
   debug_sync = block_decoder.debug_sync();
   return 0;
@@ -706,7 +752,31 @@ int
 get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set,
                       bool print_speed_results, size_t *mark_rate_frames)
 {
-  vector<float> resampled;
+  return get_watermark_pcm (key_list, samples, nullptr, n_frames, n_channels, sample_rate, result_set, print_speed_results, mark_rate_frames);
+}
+
+int
+get_watermark_buffer_s16 (const vector<Key>& key_list, const int16_t *samples, size_t n_frames, int n_channels, int sample_rate, ResultSet& result_set,
+                          bool print_speed_results, size_t *mark_rate_frames)
+{
+  return get_watermark_pcm (key_list, nullptr, samples, n_frames, n_channels, sample_rate, result_set, print_speed_results, mark_rate_frames);
+}
+
+int
+get_watermark_pcm (const vector<Key>& key_list, const float *samples, const int16_t *samples16, size_t n_frames, int n_channels, int sample_rate,
+                   ResultSet& result_set, bool print_speed_results, size_t *mark_rate_frames)
+{
+  vector<float> resampled, converted;
+  if (samples16 && sample_rate != Params::mark_sample_rate)
+    {
+      /* rare combination: convert on the host, then take the float path through the resampler */
+      converted.resize (n_frames * n_channels);
+      const float norm = 1.0 / 0x80000000LL;
+      for (size_t i = 0; i < converted.size(); i++)
+        converted[i] = (int (samples16[i]) << 16) * norm;
+      samples = converted.data();
+      samples16 = nullptr;
+    }
   if (sample_rate != Params::mark_sample_rate)
     {
       /* WavChunkLoader resamples the input to the watermark rate while it reads (src/wavchunkloader.cc:66-73, 196-221) */
@@ -722,6 +792,7 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
           return 1;
         }
       samples = resampled.data();
+      samples16 = nullptr;
       n_frames = n_out;
       sample_rate = Params::mark_sample_rate;
     }
@@ -742,16 +813,19 @@ get_watermark_buffer (const vector<Key>& key_list, const float *samples, size_t 
   if (!ctx)
     return 1;
   /* host buffers: the next chunk travels over PCIe while the current one is searched */
-  awm_pcm_prefetch (ctx, samples, end - start, n_channels);
+  PcmRef pcm;
+  pcm.f32 = samples16 ? nullptr : samples;
+  pcm.s16 = samples16;
+  pcm.prefetch (ctx, end - start, n_channels);
   for (;;)
     {
       string debug_sync;
       if (!eof)
         {
           const size_t nstart = end - overlap, nend = min (nstart + max_frames, n_frames);
-          awm_pcm_prefetch (ctx, samples + nstart * n_channels, nend - nstart, n_channels);
+          pcm.advanced (nstart * n_channels).prefetch (ctx, nend - nstart, n_channels);
         }
-      if (decode_chunk (pending, int (time_offsets.size()), debug_sync, key_list, samples + start * n_channels, end - start, n_channels, sample_rate, first_chunk, print_speed_results))
+      if (decode_chunk (pending, int (time_offsets.size()), debug_sync, key_list, pcm.advanced (start * n_channels), end - start, n_channels, sample_rate, first_chunk, print_speed_results))
         return 1;
       time_offsets.push_back (time_offset);
       debug_syncs.push_back (debug_sync);
@@ -793,7 +867,9 @@ get_watermark_chunk (const vector<Key>& key_list, const float *samples, size_t n
     }
   vector<VitJob> pending;
   string debug_sync;
-  if (decode_chunk (pending, 0, debug_sync, key_list, samples, n_frames, n_channels, sample_rate, first_chunk))
+  PcmRef pcm;
+  pcm.f32 = samples;
+  if (decode_chunk (pending, 0, debug_sync, key_list, pcm, n_frames, n_channels, sample_rate, first_chunk))
     return 1;
   vector<ResultSet> one (1);
   if (!run_viterbi_jobs (pending, one))

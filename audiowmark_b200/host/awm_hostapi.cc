@@ -207,6 +207,38 @@ awmh_add (const unsigned char *key16, const float *in, float *out, size_t n_fram
   return rc;
 }
 
+/* add / get between 16 bit PCM host buffers (the contents of a 16 bit WAV file): conversions run on the device */
+int
+awmh_add_s16 (const unsigned char *key16, const int16_t *in, int16_t *out, size_t n_frames, int n_channels, int sample_rate,
+              const char *payload_hex, int *data_blocks, double *snr_db, uint64_t first_frame_number)
+{
+  AddStats stats;
+  const int rc = add_watermark_buffer_s16 (make_key (key16, ""), in, out, n_frames, n_channels, sample_rate, payload_hex, (data_blocks || snr_db) ? &stats : nullptr,
+                                           first_frame_number);
+  if (data_blocks)
+    *data_blocks = stats.data_blocks;
+  if (snr_db)
+    *snr_db = stats.snr_db;
+  return rc;
+}
+
+static int result_json (ResultSet& result_set, size_t mark_rate_frames, char *json_out, size_t json_cap, int *n_patterns);
+
+int
+awmh_get_s16 (const unsigned char *keys16, const char *const *names, int n_keys, const int16_t *pcm, size_t n_frames, int n_channels,
+              int sample_rate, char *json_out, size_t json_cap, int *n_patterns)
+{
+  std::vector<Key> key_list;
+  for (int k = 0; k < n_keys; k++)
+    key_list.push_back (make_key (keys16 + 16 * k, names ? names[k] : ""));
+  ResultSet result_set;
+  size_t mark_rate_frames = n_frames;
+  const int rc = get_watermark_buffer_s16 (key_list, pcm, n_frames, n_channels, sample_rate, result_set, false, &mark_rate_frames);
+  if (rc)
+    return rc;
+  return result_json (result_set, mark_rate_frames, json_out, json_cap, n_patterns);
+}
+
 /* get_watermark on a buffer (host pointer; a device pointer is accepted for inputs longer than 3.1 blocks,
  * where the clip decoder is not used).  Writes the --json document into json_out. */
 int
@@ -221,6 +253,12 @@ awmh_get (const unsigned char *keys16, const char *const *names, int n_keys, con
   const int rc = get_watermark_buffer (key_list, pcm, n_frames, n_channels, sample_rate, result_set, false, &mark_rate_frames);
   if (rc)
     return rc;
+  return result_json (result_set, mark_rate_frames, json_out, json_cap, n_patterns);
+}
+
+static int
+result_json (ResultSet& result_set, size_t mark_rate_frames, char *json_out, size_t json_cap, int *n_patterns)
+{
   if (n_patterns)
     *n_patterns = int (result_set.all().size());
   if (json_out && json_cap)

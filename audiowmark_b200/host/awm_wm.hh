@@ -25,6 +25,14 @@ class ResultSet;
 int get_watermark_buffer (const std::vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,
                           ResultSet& result_set, bool print_speed_results = false, size_t *mark_rate_frames = nullptr);
 
+/* 16 bit PCM in host memory (what a 16 bit WAV file holds): converted on the device, identical results at half the PCIe traffic */
+int get_watermark_buffer_s16 (const std::vector<Key>& key_list, const int16_t *samples, size_t n_frames, int n_channels, int sample_rate,
+                              ResultSet& result_set, bool print_speed_results = false, size_t *mark_rate_frames = nullptr);
+int get_watermark_pcm (const std::vector<Key>& key_list, const float *samples, const int16_t *samples16, size_t n_frames, int n_channels, int sample_rate,
+                       ResultSet& result_set, bool print_speed_results, size_t *mark_rate_frames);
+int add_watermark_buffer_s16 (const Key& key, const int16_t *in, int16_t *out, size_t n_frames, int n_channels, int sample_rate,
+                              const std::string& bits, AddStats *stats, uint64_t first_frame_number = 0);
+
 /* chunk-level pieces of get_watermark_buffer for sharded runs (one process per GPU): a rank decodes some of the
  * reference's chunks (WavChunkLoader geometry) and the chunk result sets are merged in chunk order afterwards */
 int get_watermark_chunk (const std::vector<Key>& key_list, const float *samples, size_t n_frames, int n_channels, int sample_rate,

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16"]
 
 _lib = None
 
@@ -210,6 +210,40 @@ def resampled_add_plan(n_frames, sample_rate):
     e, r = ctypes.c_uint64(), ctypes.c_uint64()
     load().awmh_resampled_add_plan(ctypes.c_uint64(n_frames), ctypes.c_int(sample_rate), ctypes.byref(e), ctypes.byref(r))
     return e.value, r.value
+
+
+def add_s16(pcm_in, payload_hex: str, key=None, pcm_out=None, sample_rate=44100, want_stats=False, first_frame_number=0):
+    """`add` between 16 bit PCM host buffers (int16 numpy [n, ch]): the int <-> float conversions run on the device"""
+    pcm_in = np.ascontiguousarray(pcm_in, np.int16)
+    n_frames, channels = pcm_in.shape
+    if pcm_out is None:
+        pcm_out = np.empty_like(pcm_in)
+    blocks, snr = ctypes.c_int(), ctypes.c_double()
+    rc = load().awmh_add_s16(_key(key), _ptr(pcm_in), _ptr(pcm_out), ctypes.c_size_t(n_frames), ctypes.c_int(channels), ctypes.c_int(sample_rate),
+                             payload_hex.encode(), ctypes.byref(blocks) if want_stats else None, ctypes.byref(snr) if want_stats else None,
+                             ctypes.c_uint64(first_frame_number))
+    if rc:
+        raise RuntimeError("awmh_add_s16 failed (rc=%d); see stderr" % rc)
+    return (pcm_out, blocks.value, snr.value) if want_stats else pcm_out
+
+
+def get_s16(pcm, keys=None, names=None, sample_rate=44100, parse=True):
+    """`get` on a 16 bit PCM host buffer (int16 numpy [n, ch]) -> the --json document"""
+    keys = keys or [bytes(16)]
+    names = names or [""] * len(keys)
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    n_frames, channels = pcm.shape
+    kb = b"".join(_key(k) for k in keys)
+    name_arr = (ctypes.c_char_p * len(keys))(*[n.encode() for n in names])
+    cap = 1 << 22
+    buf = ctypes.create_string_buffer(cap)
+    n_pat = ctypes.c_int()
+    rc = load().awmh_get_s16(kb, name_arr, ctypes.c_int(len(keys)), _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
+                             ctypes.c_int(sample_rate), buf, ctypes.c_size_t(cap), ctypes.byref(n_pat))
+    if rc:
+        raise RuntimeError("awmh_get_s16 failed (rc=%d); see stderr" % rc)
+    text = buf.value.decode()
+    return json.loads(text) if parse else text
 
 
 def chunk_geometry(sample_rate=44100):

@@ -10,8 +10,10 @@ step     one `add` (embed + limiter) followed by one `get` (chunked sync search,
          (audiowmark_b200/host -> C ABI -> sm_100a kernels)
 
 value  : inputs resident in HBM (device pointers), timed with CUDA events on the context stream
-e2e    : the same call with pinned HOST buffers; H2D of the input for add, D2H of the marked audio,
-         H2D of the marked audio for get and D2H of the results are all inside the timed region
+e2e    : the same call with pinned HOST buffers holding 16 bit PCM (the sample format of the reference arm's WAV
+         files; converted on the device with the reference's rules): H2D of the input for add, D2H of the marked
+         audio, H2D of the marked audio for get and D2H of the results are all inside the timed region
+e2e_f32: the same with fp32 host buffers (twice the PCIe bytes)
 roofline / kernels : per-kernel CUDA-event times of the timed steps (awm_profile_*)
 cpu_baseline       : the reference's own CPU implementation (oracle/_ref/audiowmark, unmodified
                      sources, FFT = in-repo shim) on a bounded sample, rank 0 at N=1 only
@@ -210,6 +212,10 @@ def main_gpu(args):
     x_host = torch.empty((max(n_loc, 1), ch), dtype=torch.float32, pin_memory=True)
     y_host = torch.empty((max(n_loc, 1), ch), dtype=torch.float32, pin_memory=True)
     x_host.copy_(x_dev)
+    # the same audio as 16 bit PCM (what a WAV file of the reference arm holds): floor (x * 32768), cf. src/sfoutputstream.cc:148-155
+    x16_host = torch.empty((max(n_loc, 1), ch), dtype=torch.int16, pin_memory=True)
+    y16_host = torch.empty((max(n_loc, 1), ch), dtype=torch.int16, pin_memory=True)
+    x16_host.copy_(torch.floor(x_dev * 32768.0).clamp_(-32768, 32767).to(torch.int16))
     torch.cuda.synchronize()
 
     stream = torch.cuda.ExternalStream(H.gpu_stream(), device=dev)
@@ -222,6 +228,10 @@ def main_gpu(args):
         def step_e2e():
             H.add(x_host.numpy(), PAYLOAD, None, y_host.numpy())
             return H.get(y_host.numpy())
+
+        def step_e2e_s16():
+            H.add_s16(x16_host.numpy(), PAYLOAD, None, y16_host.numpy())
+            return H.get_s16(y16_host.numpy())
     else:
         def sharded(xp, ypcm):
             H.add(xp, PAYLOAD, None, ypcm if not isinstance(ypcm, int) else ypcm, n_loc, ch, first_frame_number=ffn)
@@ -233,6 +243,11 @@ def main_gpu(args):
 
         def step_e2e():
             return sharded(x_host.numpy(), y_host.numpy())
+
+        def step_e2e_s16():
+            H.add_s16(x16_host.numpy(), PAYLOAD, None, y16_host.numpy(), first_frame_number=ffn)
+            job = S.BalancedGet(rank, world, n_total, y16_host.numpy(), e0, n_loc, ch)
+            return job.run(lambda payload: S.allgather_bytes(payload, device=dev))
 
     def check(doc):
         real = [m for m in doc["matches"] if m["quality"] > 0.35]
@@ -278,6 +293,11 @@ def main_gpu(args):
         step_e2e()
     ms_e2e, wall_e2e, doc2, _, _ = timed(step_e2e, args.steps, False)
     ok2, _ = check(doc2)
+    for _ in range(min(args.warmup, 1)):
+        step_e2e_s16()
+    ms_e2e16, _, doc3, _, _ = timed(step_e2e_s16, args.steps, False)
+    ok3, _ = check(doc3)
+    ok2 = ok2 and ok3
 
     det = torch.tensor([n_real, int(ok), int(ok2)], device=dev, dtype=torch.int64)
     if world > 1:
@@ -295,6 +315,7 @@ def main_gpu(args):
     ms_step = ms / args.steps
     value = total_frames / (ms_step / 1e3)
     e2e_value = total_frames / (ms_e2e / args.steps / 1e3)
+    e2e16_value = total_frames / (ms_e2e16 / args.steps / 1e3)
     # per-kernel picture and the roofline of the dominant kernel
     peaks = measured_peaks()
     peak_gbs = (peaks or {}).get("hbm_gbs", 6650.0)
@@ -333,9 +354,16 @@ def main_gpu(args):
                    "l2": "inputs (%.2f GB per pass) larger than L2" % (n * ch * 4 / 1e9)},
         "analysis_frames_per_s": value / 1024.0,
         "payload_ok": bool(all(d[1] for d in det_all)), "detections": det_all[0][0],
-        "e2e": {"value": e2e_value, "unit": "PCM frames/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": 2 * n_loc * ch * 4, "d2h_bytes_per_step": n_loc * ch * 4, "payload_ok": bool(all(d[2] for d in det_all)),
-                "api": "hostapi.add + hostapi.get (C++ add_watermark_buffer / get_watermark_buffer) on pinned host buffers"},
+        # headline e2e: 16 bit PCM host buffers in and out -- what the WAV files of the reference arm hold; the int <-> float conversions of
+        # SFInputStream / SFOutputStream run on the device (bit identical to converting on the host, tests/test_gpu_e2e.py)
+        "e2e": {"value": e2e16_value, "unit": "PCM frames/s", "ms_per_step": ms_e2e16 / args.steps,
+                "h2d_bytes_per_step": 2 * n_loc * ch * 2, "d2h_bytes_per_step": n_loc * ch * 2, "payload_ok": bool(all(d[2] for d in det_all)),
+                "pcm": "s16 pinned host buffers (input, marked output, input of get)",
+                "api": "hostapi.add_s16 + hostapi.get_s16 (C++ add_watermark_buffer_s16 / get_watermark_buffer_s16 -> awm_embed_s16, awm_pcm_prefetch_s16 ...)"},
+        # the same with fp32 host buffers (what AudioInputStream::read_frames hands over inside the reference): twice the PCIe bytes
+        "e2e_f32": {"value": e2e_value, "unit": "PCM frames/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 2 * n_loc * ch * 4, "d2h_bytes_per_step": n_loc * ch * 4,
+                    "api": "hostapi.add + hostapi.get (C++ add_watermark_buffer / get_watermark_buffer) on pinned fp32 host buffers"},
         "gpu_launches": launches,
         "roofline": roofline,
         "kernels": kernels,

@@ -110,6 +110,15 @@ int awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels,
  * no padding picks the copy up instead of transferring again.  Two prefetches may be outstanding. */
 int awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels);
 
+/* 16 bit PCM variants: the buffers hold interleaved int16 (what a 16 bit WAV file holds); conversion to / from the float
+ * pipeline happens on the device with the reference's rules -- reading: sample * 2^-15 (src/sfinputstream.cc:189-210),
+ * writing: float_to_int_clip<32> (src/rawconverter.hh:34-50), 16 most significant bits kept (src/sfoutputstream.cc:148-155) --
+ * so results are identical to converting on the host, at half the PCIe traffic. */
+int awm_pcm_bind_s16 (awm_ctx *ctx, const int16_t *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end);
+int awm_pcm_prefetch_s16 (awm_ctx *ctx, const int16_t *pcm, size_t n_frames, int channels);
+/* device copy (float) of the bound PCM incl. padding; NULL if nothing is bound */
+const float *awm_pcm_device (awm_ctx *ctx, size_t *n_frames, int *channels);
+
 /* ---- embed: add_stream_watermark main loop (src/wmadd.cc:520-589) = FFTAnalyzer::run_fft
  * (src/wmcommon.cc:91-121) + apply_frame_mod (src/wmadd.cc:61-84) + WatermarkSynth::run
  * (src/wmadd.cc:215-250) + mix + Limiter::process (src/limiter.cc:45-124), for a whole buffer
@@ -125,6 +134,10 @@ int awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int chann
 int awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels,
                uint64_t first_frame_number, int frames_pad_start, double water_delta,
                int limiter_block, float limiter_ceiling, double *snr_power);
+/* the same for 16 bit PCM in and out (see awm_pcm_bind_s16): what `audiowmark add in16.wav out16.wav` computes between the files */
+int awm_embed_s16 (awm_ctx *ctx, const int16_t *in, int16_t *out, size_t n_frames, int channels,
+                   uint64_t first_frame_number, int frames_pad_start, double water_delta,
+                   int limiter_block, float limiter_ceiling, double *snr_power);
 
 /* ---- sync search on the bound PCM --------------------------------------------------------
  * awm_sync_approx = SyncFinder::search_approx (src/syncfinder.cc:171-256): for the four

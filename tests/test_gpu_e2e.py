@@ -162,3 +162,31 @@ def test_short_payload_and_linear_vs_reference(name):
         H.set_params()
     n_real = check_matches(doc, g["json"])
     assert n_real >= 3 and all(m["bits"] == g["payload"] for m in doc["matches"][:n_real])
+
+
+def test_s16_entry_points_equal_host_side_conversion():
+    """16 bit PCM buffers converted on the device (awm_embed_s16 / awm_pcm_bind_s16): bit identical to converting on the host
+    with the reference's rules (src/sfinputstream.cc:189-210, src/rawconverter.hh:34-50 + src/sfoutputstream.cc:148-155) around
+    the float entry points, for add (incl. clipping at full scale), get (block and clip decoder) and get --detect-speed"""
+    H.set_params()
+    for seconds, ch, seed, amp in ((130.0, 2, 5, 0.5), (30.7, 2, 99, 1.0), (12.0, 1, 3, 0.5)):
+        x16 = O.quantize_sndfile16(T.noise(seconds, ch, seed=seed, amp=amp))
+        xf = O.int16_to_float(x16)
+        want = O.quantize_sndfile16(H.add(xf, T.PAYLOAD))
+        got, blocks, snr = H.add_s16(x16, T.PAYLOAD, want_stats=True)
+        assert got.dtype == np.int16 and np.array_equal(got, want)
+        doc_f = H.get(O.int16_to_float(got))
+        doc_s = H.get_s16(got)
+        assert doc_s == doc_f and len(doc_s["matches"]) >= 1
+    # pipelined path (> 2 * 12288 frames of 1024): 10 minutes
+    x16 = O.quantize_sndfile16(T.noise(600.0, 2, seed=8))
+    want = O.quantize_sndfile16(H.add(O.int16_to_float(x16), T.PAYLOAD))
+    got = H.add_s16(x16, T.PAYLOAD)
+    assert np.array_equal(got, want)
+    assert H.get_s16(got) == H.get(O.int16_to_float(got))
+    H.set_speed_params(detect_speed=True)
+    try:
+        y16 = O.quantize_sndfile16(T.speed_changed(30, 1.01))
+        assert H.get_s16(y16) == H.get(O.int16_to_float(y16))
+    finally:
+        H.set_speed_params()
