@@ -78,7 +78,7 @@ struct awm_ctx
   std::string err;
   uint64_t launches = 0;
   bool profiling = false;
-  struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+  struct ProfRec { const char *name; cudaEvent_t e0, e1; double bytes; };
   std::vector<ProfRec> prof;
 
   DevBuf tw, win, synth;             // constant tables
@@ -134,6 +134,7 @@ prof_begin (awm_ctx *ctx)
     return;
   awm_ctx::ProfRec r;
   r.name = nullptr;
+  r.bytes = 0;
   cudaEventCreate (&r.e0);
   cudaEventCreate (&r.e1);
   cudaEventRecord (r.e0, ctx->stream);
@@ -147,6 +148,15 @@ prof_end (awm_ctx *ctx, const char *name)
     return;
   ctx->prof.back().name = name;
   cudaEventRecord (ctx->prof.back().e1, ctx->stream);
+}
+
+/* measurement aid: algorithmic bytes of the launch that was just recorded (the compulsory traffic of the work it was given;
+ * only kernels whose volume depends on run-time counts report it here, the others are sized by the caller from the input) */
+void
+prof_bytes (awm_ctx *ctx, double bytes)
+{
+  if (ctx->profiling && !ctx->prof.empty())
+    ctx->prof.back().bytes = bytes;
 }
 
 bool
@@ -356,7 +366,7 @@ awm_profile_report (awm_ctx *ctx, char *json_out, size_t json_cap)
 {
   CK (cudaSetDevice (ctx->device));
   CK (cudaStreamSynchronize (ctx->stream));
-  struct Acc { std::string name; int n; double ms; };
+  struct Acc { std::string name; int n; double ms; double bytes; };
   std::vector<Acc> acc;
   for (auto& r : ctx->prof)
     {
@@ -369,10 +379,11 @@ awm_profile_report (awm_ctx *ctx, char *json_out, size_t json_cap)
               {
                 a.n++;
                 a.ms += ms;
+                a.bytes += r.bytes;
                 found = true;
               }
           if (!found)
-            acc.push_back ({ r.name, 1, ms });
+            acc.push_back ({ r.name, 1, ms, r.bytes });
         }
       cudaEventDestroy (r.e0);
       cudaEventDestroy (r.e1);
@@ -382,7 +393,7 @@ awm_profile_report (awm_ctx *ctx, char *json_out, size_t json_cap)
   for (size_t i = 0; i < acc.size(); i++)
     {
       char buf[256];
-      snprintf (buf, sizeof (buf), "%s\"%s\": {\"launches\": %d, \"ms\": %.6f}", i ? ", " : "", acc[i].name.c_str(), acc[i].n, acc[i].ms);
+      snprintf (buf, sizeof (buf), "%s\"%s\": {\"launches\": %d, \"ms\": %.6f, \"algo_bytes\": %.0f}", i ? ", " : "", acc[i].name.c_str(), acc[i].n, acc[i].ms, acc[i].bytes);
       js += buf;
     }
   js += "}";
@@ -1089,6 +1100,9 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     t.ent.as<awm_sync_entry>(), t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last,
     ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>(), ctx->tw.as<float2>(), ctx->win.as<float>());
   LAUNCH_CHECK ("k_refine");
+  /* compulsory traffic: every candidate's window of sync frames (one block, two in CLIP mode, + the +-256 samples of the
+   * offsets) is read once -- the 65 offsets x 6 bits re-read it from L2 */
+  prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
   std::vector<float> h_ud (nc * kOffsets * n_bits * 2);
   std::vector<int> h_cnt (nc * kOffsets * n_bits);
   std::vector<unsigned char> h_valid (nc * kOffsets);
@@ -1184,6 +1198,7 @@ awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size_t n
         ctx->pcm, (long long) ctx->pcm_frames, C, ctx->blk_start.as<long long>(), int (nb), k.fpb, ctx->D.as<float>(),
         ctx->tw.as<float2>(), ctx->win.as<float>());
       LAUNCH_CHECK ("k_decode_fft");
+      prof_bytes (ctx, double (nb) * k.fpb * (double (kFrame) * C * sizeof (float) + double (C) * kBands * sizeof (float)));   /* block PCM in, band dB out */
       dim3 grid (unsigned ((k.n_coded + 127) / 128), unsigned (nb));
       PROF (ctx);
       k_mix_decode<<<grid, 128, 0, ctx->stream>>> (ctx->D.as<float>(), int (nb), C, k.fpb, k.mix.as<awm_mix_entry>(), k.frames_per_bit,
