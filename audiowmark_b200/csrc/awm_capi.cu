@@ -5,6 +5,7 @@
 // fallback: every entry point launches the sm_100a kernels of awm_kernels.cuh or fails.
 #include "awm_kernels.cuh"
 #include "awm_speed.cuh"
+#include "awm_refine_slide.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -94,7 +95,7 @@ struct awm_ctx
 
   DevBuf dbT, have, q, scores, a_ud, a_cnt, peaks_out, peaks_cnt;       // approx
   size_t n_scores_dev = 0;
-  DevBuf cand_start, cand_noff, r_ud, r_cnt, rvalid;   // refine
+  DevBuf cand_start, cand_noff, r_ud, r_cnt, rvalid, r_ent_ud, r_ent_flag, tw1024;   // refine
   DevBuf blk_start, D, raw;          // decode
   DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
   DevBuf emb_in, emb_out, emb_in16, emb_out16, peaks, snr;
@@ -274,7 +275,7 @@ awm_destroy (awm_ctx *ctx)
   cudaSetDevice (ctx->device);
   cudaStreamSynchronize (ctx->stream);
   DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->pcm16_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt,
-                     &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
+                     &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->r_ent_ud, &ctx->r_ent_flag, &ctx->tw1024, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
                      &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
                      &ctx->emb_in, &ctx->emb_out, &ctx->emb_in16, &ctx->emb_out16, &ctx->peaks, &ctx->snr, &ctx->rs_in, &ctx->rs_out, &ctx->rs_jobs, &ctx->pcm_rs,
                      &ctx->win512, &ctx->sp_clip, &ctx->sp_sub, &ctx->sp_mags, &ctx->sp_mag_jobs, &ctx->sp_cmp_jobs, &ctx->sp_best };
@@ -1091,6 +1092,54 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     }
   CK (cudaMemcpyAsync (ctx->cand_start.p, h_start.data(), nc * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
   CK (cudaMemcpyAsync (ctx->cand_noff.p, h_noff.data(), nc * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+  /* default: sliding DFT over the 65 offsets (awm_refine_slide.cuh); AWM_REFINE=fft selects the kernel that transforms every
+   * frame of every offset afresh (also used for more than two channels) */
+  static const bool force_fft = [] { const char *e = getenv ("AWM_REFINE"); return e && !strcmp (e, "fft"); } ();
+  if (ctx->pcm_ch <= 2 && !force_fft)
+    {
+      if (!ctx->tw1024.p)
+        {
+          std::vector<float2> tw (1024);
+          for (int p = 0; p < 1024; p++)
+            {
+              const double a = -2.0 * M_PI * double (p) / 1024.0;
+              tw[p] = make_float2 (float (cos (a)), float (sin (a)));
+            }
+          CK (ctx->tw1024.reserve (tw.size() * sizeof (float2)));
+          CK (cudaMemcpy (ctx->tw1024.p, tw.data(), tw.size() * sizeof (float2), cudaMemcpyHostToDevice));
+        }
+      const size_t n_pairs = size_t (nc) * kOffsets * t.n_ent;
+      CK (ctx->r_ent_ud.reserve (n_pairs * sizeof (float2)));
+      CK (ctx->r_ent_flag.reserve (n_pairs));
+      const size_t smem = fft_smem_bytes (kSlideWarps);
+      const long long jobs = (long long) nc * t.n_ent;
+      const unsigned grid = unsigned ((jobs + kSlideWarps - 1) / kSlideWarps);
+      PROF (ctx);
+      if (ctx->pcm_ch == 2)
+        {
+          if (set_smem (ctx, k_refine_slide<2>, smem)) return 1;
+          k_refine_slide<2><<<grid, kSlideWarps * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
+            t.ent.as<awm_sync_entry>(), t.n_ent, total, (long long) wav_first, (long long) wav_last, ctx->r_ent_ud.as<float2>(), ctx->r_ent_flag.as<unsigned char>(),
+            ctx->tw.as<float2>(), ctx->tw1024.as<float2>());
+        }
+      else
+        {
+          if (set_smem (ctx, k_refine_slide<1>, smem)) return 1;
+          k_refine_slide<1><<<grid, kSlideWarps * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
+            t.ent.as<awm_sync_entry>(), t.n_ent, total, (long long) wav_first, (long long) wav_last, ctx->r_ent_ud.as<float2>(), ctx->r_ent_flag.as<unsigned char>(),
+            ctx->tw.as<float2>(), ctx->tw1024.as<float2>());
+        }
+      LAUNCH_CHECK ("k_refine_slide");
+      prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
+      const long long n_red = (long long) nc * kOffsets * n_bits;
+      PROF (ctx);
+      k_refine_reduce<<<unsigned ((n_red + 127) / 128), 128, 0, ctx->stream>>> (ctx->r_ent_ud.as<float2>(), ctx->r_ent_flag.as<unsigned char>(), int (nc), t.n_ent,
+        t.off.as<int>(), n_bits, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), (long long) ctx->pcm_frames, total,
+        ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>());
+      LAUNCH_CHECK ("k_refine_reduce");
+    }
+  else
+    {
   const size_t smem = fft_smem_bytes (kRefineWarps) + kRefineWarps * 96 * sizeof (float);
   if (set_smem (ctx, k_refine, smem)) return 1;
   const long long jobs = (long long) nc * kOffsets * n_bits;
@@ -1103,6 +1152,7 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   /* compulsory traffic: every candidate's window of sync frames (one block, two in CLIP mode, + the +-256 samples of the
    * offsets) is read once -- the 65 offsets x 6 bits re-read it from L2 */
   prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
+    }
   std::vector<float> h_ud (nc * kOffsets * n_bits * 2);
   std::vector<int> h_cnt (nc * kOffsets * n_bits);
   std::vector<unsigned char> h_valid (nc * kOffsets);

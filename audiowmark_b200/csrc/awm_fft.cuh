@@ -146,4 +146,11 @@ db_from_complex (float re, float im, float min_db)
   return abs2 > 0.0f ? log2f (abs2) * 3.01029995663981f : min_db;
 }
 
+// the same from the squared magnitude
+__device__ __forceinline__ float
+db_from_complex_abs2 (float abs2)
+{
+  return abs2 > 0.0f ? log2f (abs2) * 3.01029995663981f : -96.0f;
+}
+
 } // namespace awm
