@@ -6,6 +6,7 @@
 #include "awm_kernels.cuh"
 #include "awm_speed.cuh"
 #include "awm_refine_slide.cuh"
+#include "awm_approx_mags.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -93,7 +94,7 @@ struct awm_ctx
   Prefetch pref[2];
   int pref_next = 0;
 
-  DevBuf dbT, have, q, scores, a_ud, a_cnt, peaks_out, peaks_cnt;       // approx
+  DevBuf dbT, have, q, scores, a_ud, a_cnt, peaks_out, peaks_cnt, a_mags;       // approx
   size_t n_scores_dev = 0;
   DevBuf cand_start, cand_noff, r_ud, r_cnt, rvalid, r_ent_ud, r_ent_flag, tw1024;   // refine
   DevBuf blk_start, D, raw;          // decode
@@ -274,7 +275,7 @@ awm_destroy (awm_ctx *ctx)
     return;
   cudaSetDevice (ctx->device);
   cudaStreamSynchronize (ctx->stream);
-  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->pcm16_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt,
+  DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->pcm16_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt, &ctx->a_mags,
                      &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->r_ent_ud, &ctx->r_ent_flag, &ctx->tw1024, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
                      &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
                      &ctx->emb_in, &ctx->emb_out, &ctx->emb_in16, &ctx->emb_out16, &ctx->peaks, &ctx->snr, &ctx->rs_in, &ctx->rs_out, &ctx->rs_jobs, &ctx->pcm_rs,
@@ -964,13 +965,45 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     return 0;
   if (scores_out && max_scores < size_t (n_starts) * 4)
     return fail (ctx, "awm_sync_approx: scores_out too small (%zu < %lld)", max_scores, n_starts * 4);
-  const int ld = int ((n_out + 31) / 32 * 32);
-  CK (ctx->dbT.reserve (size_t (4) * kBands * ld * sizeof (float)));
+  const int ld = int ((n_out + 63) / 64 * 64);
   CK (ctx->have.reserve (size_t (4) * ld));
   CK (ctx->q.reserve (size_t (n_starts) * 4 * sizeof (double)));
   CK (ctx->a_ud.reserve (size_t (n_starts) * 4 * t.n_bits * 2 * sizeof (float)));
   CK (ctx->a_cnt.reserve (size_t (n_starts) * 4 * t.n_bits * sizeof (int)));
   CK (ctx->scores.reserve (size_t (n_starts) * 4 * sizeof (awm_search_score)));
+  const double norm_div = water_delta < 0.080 ? water_delta : 0.080;     // normalize_sync_quality, src/syncfinder.cc:90
+  /* default: per-frame entry sums + one streaming gather (awm_approx_mags.cuh); AWM_APPROX=ring selects the kernel that walks
+   * the dB matrix per start frame in the reference's exact summation order */
+  static const bool force_ring = [] { const char *e = getenv ("AWM_APPROX"); return e && !strcmp (e, "ring"); } ();
+  if (!force_ring && t.n_ent <= kGatherMaxEntries)
+    {
+      CK (ctx->a_mags.reserve (size_t (4) * t.n_ent * ld * sizeof (float2)));
+      {
+        const size_t smem = kMagSmem2;
+        if (set_smem (ctx, k_stft_mags, smem)) return 1;
+        const unsigned grid = 4u * unsigned ((n_out + kMagTile - 1) / kMagTile);
+        PROF (ctx);
+        k_stft_mags<<<grid, kMagWarps2 * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
+                                                                  t.ent.as<awm_sync_entry>(), t.n_ent, ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(),
+                                                                  (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>());
+        LAUNCH_CHECK ("k_stft_mags");
+        prof_bytes (ctx, double (ctx->pcm_frames) * ctx->pcm_ch * sizeof (float) + double (4) * t.n_ent * n_out * sizeof (float2));   /* PCM in, entry sums out */
+      }
+      dim3 grid (unsigned ((n_starts + 255) / 256), 4);
+      PROF (ctx);
+      if (mode == AWM_MODE_CLIP)
+        k_sync_gather<true><<<grid, 256, 0, ctx->stream>>> (ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(), ld, int (n_starts), t.ent.as<awm_sync_entry>(), t.n_ent,
+                                                            t.off.as<int>(), t.n_bits, ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
+      else
+        k_sync_gather<false><<<grid, 256, 0, ctx->stream>>> (ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(), ld, int (n_starts), t.ent.as<awm_sync_entry>(), t.n_ent,
+                                                             t.off.as<int>(), t.n_bits, ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
+      LAUNCH_CHECK ("k_sync_gather");
+      /* every (start frame, entry) pair reads its float2 once; the per-bit sums are written once */
+      prof_bytes (ctx, double (4) * n_starts * t.n_ent * sizeof (float2) + double (4) * n_starts * t.n_bits * 12.0);
+    }
+  else
+    {
+  CK (ctx->dbT.reserve (size_t (4) * kBands * ld * sizeof (float)));
   {
     const size_t smem = fft_smem_bytes (kStftWarps) + kBands * (kStftWarps + 1) * sizeof (float);
     if (set_smem (ctx, k_stft_db, smem)) return 1;
@@ -982,7 +1015,6 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
                                                             ctx->tw.as<float2>(), ctx->win.as<float>());
     LAUNCH_CHECK ("k_stft_db");
   }
-  const double norm_div = water_delta < 0.080 ? water_delta : 0.080;     // normalize_sync_quality, src/syncfinder.cc:90
   {
     const size_t smem = kApproxSmem;
     dim3 grid (unsigned ((n_starts + kApproxCands - 1) / kApproxCands), 4);
@@ -1003,6 +1035,9 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
                                                                          ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
       }
     LAUNCH_CHECK ("k_sync_approx");
+  }
+    }
+  {
     PROF (ctx);
     k_sync_quality<<<unsigned ((n_starts * 4 + 255) / 256), 256, 0, ctx->stream>>> (ctx->a_ud.as<float>(), ctx->a_cnt.as<int>(), int (n_starts), t.n_bits,
                                                                                 norm_div, ctx->q.as<double>());
