@@ -17,13 +17,13 @@
 namespace awm {
 
 constexpr int kMagWarps2 = 16;              // warps per CTA
-constexpr int kMagTile = 64;                // frames per CTA: four transforms per warp
+constexpr int kMagTile = 128;               // frames per CTA: eight transforms per warp
 constexpr int kMagEntChunk = 512;           // sync entries staged in shared memory at a time
 constexpr size_t kMagSmem2 = fft_smem_bytes (kMagWarps2) + size_t (kBands) * kMagTile * sizeof (float) + size_t (kMagEntChunk) * 64;
 
-// Phase 2 mapping: lane = two neighbouring frames of the tile, warp = one sync entry at a time.  All lanes read the same band row
-// (float2 at consecutive addresses: conflict free), the band list of the entry is a broadcast read -- the per-entry sums then cost
-// one LDS.64 + two FADD per band and two frames, in list order.
+// Phase 2 mapping: lane = four neighbouring frames of the tile, warp = one sync entry at a time.  All lanes read the same band row
+// (float4 at consecutive addresses: conflict free), the band list of the entry is a broadcast read -- the per-entry sums then cost
+// one LDS.128 + four FADD per band and four frames, in list order.
 __global__ void __launch_bounds__ (kMagWarps2 * 32, 1)
 k_stft_mags (const float *__restrict__ pcm, long long n_frames, int C, int n_out, int ld,
              const awm_sync_entry *__restrict__ ent, int n_ent,
@@ -32,7 +32,7 @@ k_stft_mags (const float *__restrict__ pcm, long long n_frames, int C, int n_out
 {
   extern __shared__ __align__ (16) unsigned char smem[];
   FftSmem s = fft_smem_setup (smem, g_tw, g_win, kMagWarps2);
-  float *tile = s.extra;                               // [81][64]
+  float *tile = s.extra;                               // [81][128]
   uint32_t *ent_sm = reinterpret_cast<uint32_t *> (tile + kBands * kMagTile);      // [chunk][16 words]: 30 up bytes + 2 pad, 30 down bytes + 2 pad
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int shift_idx = blockIdx.x & 3, tile_idx = blockIdx.x >> 2;
@@ -80,18 +80,19 @@ k_stft_mags (const float *__restrict__ pcm, long long n_frames, int C, int n_out
           const uint4 u0 = ew[0], u1 = ew[1], d0 = ew[2], d1 = ew[3];
           const uint32_t uw[8] = { u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w };
           const uint32_t dw[8] = { d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w };
-          const float2 *t2 = reinterpret_cast<const float2 *> (tile) + lane;
-          float ua = 0.f, ub = 0.f, da = 0.f, db = 0.f;
+          const float4 *t4 = reinterpret_cast<const float4 *> (tile) + lane;
+          float4 ua = make_float4 (0.f, 0.f, 0.f, 0.f), da = ua;
 #pragma unroll
           for (int i = 0; i < kUD; i++)
             {
               const int bu = (uw[i >> 2] >> (8 * (i & 3))) & 0xff, bd = (dw[i >> 2] >> (8 * (i & 3))) & 0xff;
-              const float2 vu = t2[bu * (kMagTile / 2)], vd = t2[bd * (kMagTile / 2)];
-              ua += vu.x; ub += vu.y;
-              da += vd.x; db += vd.y;
+              const float4 vu = t4[bu * (kMagTile / 4)], vd = t4[bd * (kMagTile / 4)];
+              ua.x += vu.x; ua.y += vu.y; ua.z += vu.z; ua.w += vu.w;
+              da.x += vd.x; da.y += vd.y; da.z += vd.z; da.w += vd.w;
             }
-          float4 *o = reinterpret_cast<float4 *> (mags + ((size_t) shift_idx * n_ent + e0 + e) * ld + f0) + lane;     // ld, f0 multiples of 64
-          *o = make_float4 (ua, da, ub, db);
+          float4 *o = reinterpret_cast<float4 *> (mags + ((size_t) shift_idx * n_ent + e0 + e) * ld + f0) + 2 * lane;     // ld, f0 multiples of 128
+          o[0] = make_float4 (ua.x, da.x, ua.y, da.y);
+          o[1] = make_float4 (ua.z, da.z, ua.w, da.w);
         }
     }
 }

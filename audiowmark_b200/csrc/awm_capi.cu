@@ -862,7 +862,7 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
       if (limiter_block > 0 && s1 > s0)
         {
           PROF (ctx);
-          k_limiter<<<unsigned ((s1 - s0 + 255) / 256), 256, 0, ctx->stream>>> (d_out, s0, s1, channels, limiter_block, limiter_ceiling,
+          k_limiter<<<unsigned ((s1 - s0 + 256 * kLimiterIter - 1) / (256 * kLimiterIter)), 256, 0, ctx->stream>>> (d_out, s0, s1, channels, limiter_block, limiter_ceiling,
                                                                            ctx->peaks.as<unsigned>(), n_blocks, (long long) first_frame_number * kFrame);
           LAUNCH_CHECK ("k_limiter");
         }
@@ -965,7 +965,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     return 0;
   if (scores_out && max_scores < size_t (n_starts) * 4)
     return fail (ctx, "awm_sync_approx: scores_out too small (%zu < %lld)", max_scores, n_starts * 4);
-  const int ld = int ((n_out + 63) / 64 * 64);
+  const int ld = int ((n_out + 127) / 128 * 128);
   CK (ctx->have.reserve (size_t (4) * ld));
   CK (ctx->q.reserve (size_t (n_starts) * 4 * sizeof (double)));
   CK (ctx->a_ud.reserve (size_t (n_starts) * 4 * t.n_bits * 2 * sizeof (float)));
@@ -1682,7 +1682,7 @@ awm_embed_resampled (awm_ctx *ctx, const float *in, float *out, size_t n_frames,
   if (limiter_block > 0)
     {
       PROF (ctx);
-      k_limiter<<<unsigned ((n_frames + 255) / 256), 256, 0, ctx->stream>>> (d_out, 0, (long long) n_frames, channels, limiter_block, limiter_ceiling,
+      k_limiter<<<unsigned ((n_frames + 256 * kLimiterIter - 1) / (256 * kLimiterIter)), 256, 0, ctx->stream>>> (d_out, 0, (long long) n_frames, channels, limiter_block, limiter_ceiling,
                                                                             ctx->peaks.as<unsigned>(), n_lim_blocks, 0);
       LAUNCH_CHECK ("k_limiter");
     }

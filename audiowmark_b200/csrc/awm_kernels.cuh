@@ -1004,28 +1004,48 @@ k_embed (EmbedArgs A)
 
 // Limiter::process_block (src/limiter.cc:99-124): gain ramps linearly over each block between
 // ceiling / max (bm[b-1], bm[b]) and ceiling / max (bm[b], bm[b+1]); bm[b] = max (ceiling, peak[b]).
+constexpr int kLimiterIter = 16;        // sample-frames per thread: a CTA covers 4096 consecutive positions
+
 __global__ void
 k_limiter (float *__restrict__ x, long long pos_begin, long long pos_end, int C, int block, float ceiling,
            const unsigned *__restrict__ peaks, long long n_blocks, long long stream_pos0)
 {
-  const long long pos = pos_begin + (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= pos_end)
+  const long long cta_first = pos_begin + (long long) blockIdx.x * blockDim.x * kLimiterIter;
+  if (cta_first >= pos_end)
     return;
-  const long long gpos = stream_pos0 + pos;
-  const long long b = gpos / block - stream_pos0 / block;           // index into peaks[]
-  const int i = int (gpos % block);
-  const float cur = fmaxf (ceiling, __uint_as_float (peaks[b]));
-  // block -1 of the stream counts as "ceiling"; for a shard that starts mid-stream the caller's halo makes peaks[b-1] valid
-  const float last = b > 0 ? fmaxf (ceiling, __uint_as_float (peaks[b - 1])) : ceiling;
-  const float next = b + 1 < n_blocks ? fmaxf (ceiling, __uint_as_float (peaks[b + 1])) : ceiling;
-  const float scale_start = __fdiv_rn (ceiling, fmaxf (last, cur));
-  const float scale_end = __fdiv_rn (ceiling, fmaxf (cur, next));
-  if (scale_start == 1.0f && scale_end == 1.0f)
-    return;                                                 // x * 1.0f == x
-  const float scale_step = __fdiv_rn (__fsub_rn (scale_end, scale_start), float (block));
-  const float scale = __fadd_rn (scale_start, __fmul_rn (float (i), scale_step));
-  for (int c = 0; c < C; c++)
-    x[pos * C + c] = __fmul_rn (x[pos * C + c], scale);
+  // most audio never reaches the ceiling: if no limiter block that touches this CTA's range (or its neighbours, which steer the
+  // gain ramp) has a peak above it, every scale factor is exactly 1.0 and x * 1.0f == x -- nothing to read or write
+  {
+    const long long cta_last = (cta_first + (long long) blockDim.x * kLimiterIter < pos_end ? cta_first + (long long) blockDim.x * kLimiterIter : pos_end) - 1;
+    const long long b_lo = (stream_pos0 + cta_first) / block - stream_pos0 / block - 1, b_hi = (stream_pos0 + cta_last) / block - stream_pos0 / block + 1;
+    bool engaged = false;
+    for (long long b = b_lo < 0 ? 0 : b_lo; b <= b_hi && b < n_blocks; b++)
+      if (__uint_as_float (peaks[b]) > ceiling)
+        engaged = true;
+    if (!engaged)
+      return;
+  }
+  for (int it = 0; it < kLimiterIter; it++)
+    {
+      const long long pos = cta_first + (long long) it * blockDim.x + threadIdx.x;
+      if (pos >= pos_end)
+        return;
+      const long long gpos = stream_pos0 + pos;
+      const long long b = gpos / block - stream_pos0 / block;           // index into peaks[]
+      const int i = int (gpos % block);
+      const float cur = fmaxf (ceiling, __uint_as_float (peaks[b]));
+      // block -1 of the stream counts as "ceiling"; for a shard that starts mid-stream the caller's halo makes peaks[b-1] valid
+      const float last = b > 0 ? fmaxf (ceiling, __uint_as_float (peaks[b - 1])) : ceiling;
+      const float next = b + 1 < n_blocks ? fmaxf (ceiling, __uint_as_float (peaks[b + 1])) : ceiling;
+      const float scale_start = __fdiv_rn (ceiling, fmaxf (last, cur));
+      const float scale_end = __fdiv_rn (ceiling, fmaxf (cur, next));
+      if (scale_start == 1.0f && scale_end == 1.0f)
+        continue;                                               // x * 1.0f == x
+      const float scale_step = __fdiv_rn (__fsub_rn (scale_end, scale_start), float (block));
+      const float scale = __fadd_rn (scale_start, __fmul_rn (float (i), scale_step));
+      for (int c = 0; c < C; c++)
+        x[pos * C + c] = __fmul_rn (x[pos * C + c], scale);
+    }
 }
 
 } // namespace awm
