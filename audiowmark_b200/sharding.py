@@ -8,6 +8,7 @@ collective is the final gather of the chunk results (a few hundred bytes per det
 """
 from __future__ import annotations
 
+import os
 import struct
 
 FRAME = 1024
@@ -225,6 +226,17 @@ class BalancedGet:
         self.H, self.capi = H, capi
         self.rank, self.world, self.n_total = rank, world, n_total
         self.pcm, self.pcm_start, self.pcm_frames, self.ch, self.rate = pcm, pcm_start, pcm_frames, channels, sample_rate
+        if isinstance(pcm, np.ndarray):
+            # host audio (float32 or 16 bit PCM): one upload for all stages -- every stage binds slices of the same device copy
+            import torch
+            d = torch.from_numpy(np.ascontiguousarray(pcm)).to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+            if d.dtype == torch.int16:
+                d = d.to(torch.float32) * (1.0 / 32768.0)     # exact; the reference's int -> float rule (src/sfinputstream.cc:189-210)
+            elif d.dtype != torch.float32:
+                d = d.to(torch.float32)
+            torch.cuda.current_stream().synchronize()
+            self._device_copy = d
+            self.pcm = d.data_ptr()
         self.key = bytes(key) if key is not None else bytes(16)
         mx, ov = H.chunk_geometry(sample_rate)
         self.plan = chunk_plan(n_total, mx, ov, sample_rate)
@@ -374,6 +386,8 @@ class BalancedGet:
         return self.H.merge_chunks(blobs, [p[2] for p in self.plan], self.n_total / float(self.rate), [self.key], [""])
 
     def run(self, allgather) -> dict:
+        if os.environ.get("AWM_TRACE"):
+            return self._run_traced(allgather)
         pay = allgather(self.stage_peaks())
         retry = self.stage_select(pay)
         if retry:
@@ -382,3 +396,32 @@ class BalancedGet:
         self.stage_final(allgather(self.stage_refine()))
         pay = allgather(self.stage_decode())
         return self.stage_merge(allgather(self.stage_viterbi(pay)))
+
+    def _run_traced(self, allgather) -> dict:
+        """run() with wall-clock stage times on stderr (development aid)"""
+        import sys
+        import time
+        t = [time.perf_counter()]
+        names = []
+
+        def mark(name):
+            t.append(time.perf_counter())
+            names.append(name)
+        p = self.stage_peaks(); mark("peaks")
+        pay = allgather(p); mark("gather1")
+        retry = self.stage_select(pay); mark("select")
+        if retry:
+            pay = allgather(self.stage_peaks(retry))
+            self.stage_select(pay); mark("retry")
+        r = self.stage_refine(); mark("refine")
+        pay = allgather(r); mark("gather2")
+        self.stage_final(pay); mark("final")
+        d = self.stage_decode(); mark("decode")
+        pay = allgather(d); mark("gather3")
+        v = self.stage_viterbi(pay); mark("viterbi")
+        pay = allgather(v); mark("gather4")
+        doc = self.stage_merge(pay); mark("merge")
+        if self.rank == 0:
+            print("[trace] balanced get: " + " ".join("%s %.2f" % (n, (b - a) * 1e3) for n, a, b in zip(names, t, t[1:])) + " total %.2f ms" % ((t[-1] - t[0]) * 1e3),
+                  file=sys.stderr, flush=True)
+        return doc

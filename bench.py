@@ -174,6 +174,7 @@ def main_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -300,7 +301,7 @@ def main_gpu(args):
     ms_e2e16, _, doc3, _, _ = timed(step_e2e_s16, args.steps, False)
     ok3, _ = check(doc3)
     ok2 = ok2 and ok3
-    if rank == 0 and len(clocks.rows) < 8:          # very short runs: keep the load up until a few samples exist
+    if world == 1 and len(clocks.rows) < 8:         # very short runs: keep the load up until a few samples exist (single process only: the sharded step is collective)
         t_end = time.time() + 1.0
         while time.time() < t_end and len(clocks.rows) < 8:
             step_resident()
@@ -384,7 +385,7 @@ def main_gpu(args):
         "cpu_baseline": cpu,
         "clocks": clk,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
