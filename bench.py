@@ -342,12 +342,20 @@ def main_gpu(args):
     roofline = None
     if dominant:
         a = kernels[dominant]["algo_GBps"] or 0.0
-        # ncu (profiles/r1_ncu_full_v3_*): issue slots busy -- the ceiling these kernels actually run into
-        issue_busy = {"k_refine": 73.5, "k_sync_approx": 70.3, "k_stft_db": 66.9, "k_embed": 42.7, "k_viterbi": 34.4}
-        dram_traffic = {"k_refine": 66.4e6, "k_sync_approx": 33.6e6, "k_embed": 384e6, "k_stft_db": 239.7e6}     # bytes per launch of the 10 min capture
+        # ncu --set full on the 10 min workload (profiles/r1_ncu_full_v4_all_kernels_10min.md): what each kernel actually runs into
+        limiter = {"k_stft_mags": "shared-memory bandwidth of the per-entry band sums (143.5 M LSU wavefronts per 10 min launch, short-scoreboard stalls) on top of the FFT's fp32 issue (49 % issue slots busy)",
+                   "k_refine_slide": "fp32 issue rate (62 % issue slots busy); the PCM window is re-read from L2",
+                   "k_sync_gather": "HBM: one streaming pass over the entry-sum matrix",
+                   "k_embed": "latency: 16 warps / SM (128 registers, 165 KB shared memory), 43 % issue slots busy",
+                   "k_viterbi": "serial dependency of 143 trellis steps, one CTA per code word"}
+        dram_traffic = {"k_stft_mags": 577.6e6, "k_refine_slide": 64.5e6, "k_sync_gather": 394.8e6, "k_embed": 387.4e6}      # dram read + write, bytes per launch
+        gather = kernels.get("k_sync_gather", {}).get("algo_GBps")
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": a, "peak": peak_gbs, "unit": "GB/s", "frac": round(a / peak_gbs, 5),
-                    "traffic": dram_traffic.get(dominant), "traffic_note": "dram__bytes_read+write per launch, ncu --set full on the 10 min workload (profiles/)",
-                    "actual_limiter": "fp32 issue rate: %.1f %% issue slots busy (ncu); the kernel re-reads its window from L2, HBM is idle by design" % issue_busy[dominant] if dominant in issue_busy else None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                    "traffic": dram_traffic.get(dominant),
+                    "traffic_note": "dram__bytes_read+write per launch of the 10 min ncu capture (a 30 min chunk launch moves 3x as much)",
+                    "actual_limiter": limiter.get(dominant),
+                    "hbm_bound_kernel": {"kernel": "k_sync_gather", "achieved": gather, "frac": round((gather or 0.0) / peak_gbs, 4)},
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                     "note": "algorithmic bytes per launch / CUDA-event launch time; see DESIGN.md section 5 for the per-kernel byte model"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
