@@ -160,9 +160,11 @@ class Context:
             pcm = np.ascontiguousarray(pcm, np.float32)
             n_frames, channels = pcm.shape
             self._keep = pcm
+        host = isinstance(pcm, np.ndarray)
         self._ck(self.lib.awm_pcm_bind(self.h, _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
                                        ctypes.c_size_t(pad_start), ctypes.c_size_t(pad_end)))
-        self.synchronize()
+        if host or pad_start or pad_end:        # the asynchronous copy reads the caller's array; a device pointer is bound in place
+            self.synchronize()
 
     # ---- embed
     def embed(self, pcm_in, pcm_out=None, n_frames=None, channels=None, first_frame_number=0, frames_pad_start=250,
@@ -202,7 +204,7 @@ class Context:
 
     def sync_peaks(self, min_abs_quality: float, max_peaks: int = 65536):
         """local maxima above a floor of the LAST sync_approx call; returns (peaks sorted by index, number found)."""
-        out = np.zeros(max_peaks, SEARCH_SCORE)
+        out = np.empty(max_peaks, SEARCH_SCORE)
         n = ctypes.c_size_t()
         self._ck(self.lib.awm_sync_peaks(self.h, ctypes.c_double(min_abs_quality), _ptr(out), ctypes.c_size_t(max_peaks), ctypes.byref(n)))
         return out[:min(n.value, max_peaks)].copy(), n.value

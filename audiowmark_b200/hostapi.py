@@ -35,6 +35,18 @@ def load():
     return _lib
 
 
+_BUFS = {}
+
+
+def _outbuf(tag: str, cap: int):
+    """persistent ctypes output buffer (create_string_buffer zero-fills: megabytes per call add up in the per-step path)"""
+    b = _BUFS.get(tag)
+    if b is None or len(b) < cap:
+        b = ctypes.create_string_buffer(cap)
+        _BUFS[tag] = b
+    return b
+
+
 def _ptr(x):
     if x is None:
         return ctypes.c_void_p(0)
@@ -142,7 +154,7 @@ def get(pcm, keys=None, names=None, n_frames=None, channels=None, sample_rate=44
     kb = b"".join(_key(k) for k in keys)
     name_arr = (ctypes.c_char_p * len(keys))(*[n.encode() for n in names])
     cap = 1 << 22
-    buf = ctypes.create_string_buffer(cap)
+    buf = _outbuf("get", cap)
     n_pat = ctypes.c_int()
     rc = load().awmh_get(kb, name_arr, ctypes.c_int(len(keys)), _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
                          ctypes.c_int(sample_rate), buf, ctypes.c_size_t(cap), ctypes.byref(n_pat))
@@ -236,7 +248,7 @@ def get_s16(pcm, keys=None, names=None, sample_rate=44100, parse=True):
     kb = b"".join(_key(k) for k in keys)
     name_arr = (ctypes.c_char_p * len(keys))(*[n.encode() for n in names])
     cap = 1 << 22
-    buf = ctypes.create_string_buffer(cap)
+    buf = _outbuf("get", cap)
     n_pat = ctypes.c_int()
     rc = load().awmh_get_s16(kb, name_arr, ctypes.c_int(len(keys)), _ptr(pcm), ctypes.c_size_t(n_frames), ctypes.c_int(channels),
                              ctypes.c_int(sample_rate), buf, ctypes.c_size_t(cap), ctypes.byref(n_pat))
@@ -284,7 +296,7 @@ def merge_chunks(blobs, time_offsets, total_seconds: float, keys=None, names=Non
     lens = (ctypes.c_size_t * n)(*[len(b) for b in blobs])
     offs = (ctypes.c_double * n)(*time_offsets)
     cap = 1 << 22
-    out = ctypes.create_string_buffer(cap)
+    out = _outbuf("merge", cap)
     rc = load().awmh_merge_chunks(kb, name_arr, ctypes.c_int(len(keys)), ptrs, lens, offs, ctypes.c_int(n), ctypes.c_double(total_seconds),
                                   out, ctypes.c_size_t(cap))
     if rc:
@@ -333,7 +345,7 @@ def stage_jobs(key, index, quality, btype, raw, valid, sample_rate=44100):
     raw = np.ascontiguousarray(raw, np.float32)
     valid = np.ascontiguousarray(valid, np.int32)
     cap = 64 + (len(idx) * 3 + 2) * (36 + raw.shape[1] * 8) if len(idx) else 64
-    buf = ctypes.create_string_buffer(cap)
+    buf = _outbuf("jobs", cap)
     blen, nj = ctypes.c_size_t(), ctypes.c_int()
     rc = load().awmh_stage_jobs(_key(key), _ptr(idx), _ptr(q), _ptr(bt), ctypes.c_size_t(len(idx)), _ptr(raw), _ptr(valid), ctypes.c_int(sample_rate),
                                 buf, ctypes.c_size_t(cap), ctypes.byref(blen), ctypes.byref(nj))

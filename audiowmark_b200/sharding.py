@@ -307,7 +307,7 @@ class BalancedGet:
         for chunk, lst in per_chunk.items():
             floor_q = max(f for f, _ in lst)
             pk = np.concatenate([a for _, a in lst]) if lst else np.zeros(0, self.capi.SEARCH_SCORE)
-            pk = np.sort(pk, order="index")
+            pk = pk[np.argsort(pk["index"], kind="stable")]
             sel, complete = self.H.stage_select(pk, floor_q)
             if not complete and floor_q >= 0:
                 retry[chunk] = -1.0
