@@ -314,11 +314,24 @@ class BalancedGet:
             self.cands[chunk] = sel
         return retry            # chunks whose peak lists were too short (rare): ask for all peaks and select again
 
+    def owners(self, chunk, indices) -> np.ndarray:
+        """owner_of for an array of chunk-relative sample indices"""
+        cs, cn, _ = self.plan[chunk]
+        n_starts = max(cn // FRAME - T_BLOCK - 1, 0)
+        s = np.clip(np.asarray(indices, np.int64) // FRAME, 0, max(n_starts - 1, 0))
+        span = owner_span(self.n_total, self.world)
+        return np.minimum((cs + s * FRAME) // span, self.world - 1)
+
+    def viterbi_rank(self, chunk) -> int:
+        """all code words of a chunk are decoded (and packed for the merge) by one rank, so that no rank builds the job list of
+        every chunk of the stream"""
+        return chunk % self.world
+
     # -- stage 3: refine the candidates I own
     def stage_refine(self) -> bytes:
         out = []
         for chunk, sel in self.cands.items():
-            mine = [i for i in range(len(sel)) if self.owner_of(chunk, int(sel["index"][i])) == self.rank]
+            mine = np.nonzero(self.owners(chunk, sel["index"]) == self.rank)[0].tolist() if len(sel) else []
             sl = self._my_slice(chunk)
             if not mine or sl is None:
                 continue
@@ -342,7 +355,7 @@ class BalancedGet:
     def stage_decode(self) -> bytes:
         out = []
         for chunk, (idx, q, bt) in self.final.items():
-            mine = [i for i in range(len(idx)) if self.owner_of(chunk, int(idx[i])) == self.rank]
+            mine = np.nonzero(self.owners(chunk, idx) == self.rank)[0].tolist() if len(idx) else []
             sl = self._my_slice(chunk)
             if not mine or sl is None:
                 continue
@@ -353,36 +366,37 @@ class BalancedGet:
             out.append((chunk, np.array(mine, np.int64), raw, valid))
         return _pack(out)
 
-    # -- stage 6: Viterbi jobs of all chunks, my share decoded
+    # -- stage 6: Viterbi: the code words of chunk c are built, decoded and packed by rank viterbi_rank (c)
     def stage_viterbi(self, payloads) -> bytes:
-        raws = {c: (np.zeros((len(v[0]), self.n_coded), np.float32), np.zeros(len(v[0]), np.int32)) for c, v in self.final.items()}
+        import struct as st
+        my_chunks = [c for c in sorted(self.final) if self.viterbi_rank(c) == self.rank]
+        raws = {c: (np.zeros((len(self.final[c][0]), self.n_coded), np.float32), np.zeros(len(self.final[c][0]), np.int32)) for c in my_chunks}
         for p in payloads:
             for chunk, pos, raw, valid in _unpack(p):
-                raws[chunk][0][pos] = raw
-                raws[chunk][1][pos] = valid
-        self.jobs = []                       # (chunk, code_type, pattern_type, score_btype, time, index, quality, soft)
-        for chunk in sorted(self.final):
+                if chunk in raws:
+                    raws[chunk][0][pos] = raw
+                    raws[chunk][1][pos] = valid
+        jobs = []                            # (chunk, code_type, pattern_type, score_btype, time, index, quality, soft)
+        for chunk in my_chunks:
             idx, q, bt = self.final[chunk]
             for j in self.H.stage_jobs(self.key, idx, q, bt, raws[chunk][0], raws[chunk][1], self.rate):
-                self.jobs.append((chunk,) + j)
-        mine = list(range(self.rank, len(self.jobs), self.world))
-        if not mine:
-            return _pack((mine, None, None))
-        bits, err = self.ctx.viterbi([self.jobs[i][7] for i in mine], [self.jobs[i][1] for i in mine])
-        return _pack((mine, bits, err))
+                jobs.append((chunk,) + j)
+        blobs = {c: b"" for c in my_chunks}
+        if jobs:
+            bits, err = self.ctx.viterbi([j[7] for j in jobs], [j[1] for j in jobs])
+            parts = {c: [] for c in my_chunks}
+            for i, (chunk, code_type, ptype, sbt, time, index, quality, soft) in enumerate(jobs):
+                b = bits[i]
+                parts[chunk].append(st.pack("<iddQfBBdH", 0, time, quality, index, float(err[i]), sbt, ptype, 1.0, len(b)) + b.tobytes())
+            blobs = {c: b"".join(v) for c, v in parts.items()}
+        return _pack(blobs)
 
-    # -- stage 7: records -> the reference's merge
+    # -- stage 7: records -> the reference's merge (any rank can do it; run() leaves it to rank 0)
     def stage_merge(self, payloads) -> dict:
-        import struct as st
-        bits_all, err_all = {}, {}
-        for p in payloads:
-            mine, bits, err = _unpack(p)
-            for k, i in enumerate(mine):
-                bits_all[i], err_all[i] = bits[k], err[k]
         blobs = [b"" for _ in self.plan]
-        for i, (chunk, code_type, ptype, sbt, time, index, quality, soft) in enumerate(self.jobs):
-            b = bits_all[i]
-            blobs[chunk] += st.pack("<iddQfBBdH", 0, time, quality, index, float(err_all[i]), sbt, ptype, 1.0, len(b)) + bytes(bytearray(b))
+        for p in payloads:
+            for chunk, blob in _unpack(p).items():
+                blobs[chunk] = blob
         return self.H.merge_chunks(blobs, [p[2] for p in self.plan], self.n_total / float(self.rate), [self.key], [""])
 
     def run(self, allgather) -> dict:
@@ -395,7 +409,8 @@ class BalancedGet:
             self.stage_select(pay)
         self.stage_final(allgather(self.stage_refine()))
         pay = allgather(self.stage_decode())
-        return self.stage_merge(allgather(self.stage_viterbi(pay)))
+        pay = allgather(self.stage_viterbi(pay))
+        return self.stage_merge(pay) if self.rank == 0 else None       # the merged result lives on rank 0
 
     def _run_traced(self, allgather) -> dict:
         """run() with wall-clock stage times on stderr (development aid)"""
@@ -420,7 +435,7 @@ class BalancedGet:
         pay = allgather(d); mark("gather3")
         v = self.stage_viterbi(pay); mark("viterbi")
         pay = allgather(v); mark("gather4")
-        doc = self.stage_merge(pay); mark("merge")
+        doc = self.stage_merge(pay) if self.rank == 0 else None; mark("merge")
         if self.rank == 0:
             print("[trace] balanced get: " + " ".join("%s %.2f" % (n, (b - a) * 1e3) for n, a, b in zip(names, t, t[1:])) + " total %.2f ms" % ((t[-1] - t[0]) * 1e3),
                   file=sys.stderr, flush=True)

@@ -261,6 +261,8 @@ def main_gpu(args):
             return job.run(lambda payload: S.allgather_bytes(payload, device=dev))
 
     def check(doc):
+        if doc is None:                       # sharded run: the merged result lives on rank 0
+            return True, 0
         real = [m for m in doc["matches"] if m["quality"] > 0.35]
         return len(real) > 0 and all(m["bits"] == PAYLOAD for m in real), len(real)
 
