@@ -167,3 +167,39 @@ def test_add_other_sample_rates_vs_reference(name):
     if name == "rate32000_add":
         doc = H.get(O.int16_to_float(O.quantize_sndfile16(out)), sample_rate=g["rate"])
         assert check_matches(doc, g["json"]) == 5
+
+
+def test_cli_reference_shell_tests(tmp_path):
+    """the reference's tests/detect-speed-test.sh, sample-rate-test.sh and short-payload-test.sh run against bin/audiowmark
+    (same argv grammar, same pass criteria: `cmp` exits 0 iff the message was found; --expect-matches where the scripts use it)"""
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "audiowmark_b200", "bin", "audiowmark")
+    msg = "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0"
+    a, b, c = (str(tmp_path / n) for n in ("in.wav", "out.wav", "spd.wav"))
+    # detect-speed-test.sh
+    subprocess.check_call([cli, "test-gen-noise", a, "30", "44100"])
+    subprocess.check_call([cli, "add", "-q", a, b, msg])
+    for speed in ("0.9764", "1.01"):
+        subprocess.check_call([cli, "test-change-speed", b, c, speed])
+        for opt in ("--detect-speed", "--detect-speed-patient"):
+            p = subprocess.run([cli, "cmp", c, msg, opt, "--test-speed", speed], capture_output=True, text=True)
+            assert p.returncode == 0, p.stdout + p.stderr
+            line = p.stdout.split("\n")[0].split()
+            assert line[0] == "detect_speed" and float(line[3]) < 0.01          # relative error in percent
+            assert "\nspeed " in p.stdout and "-SPEED" in p.stdout
+        # without speed detection the message is not found at this speed
+        assert subprocess.run([cli, "cmp", c, msg], capture_output=True).returncode == 1
+    # sample-rate-test.sh
+    subprocess.check_call([cli, "test-gen-noise", a, "200", "32000"])
+    subprocess.check_call([cli, "add", "-q", a, b, msg])
+    assert subprocess.run([cli, "cmp", "--expect-matches", "5", b, msg], capture_output=True).returncode == 0
+    subprocess.check_call([cli, "test-resample", b, c, "48000"])
+    assert subprocess.run([cli, "cmp", "--expect-matches", "5", c, msg], capture_output=True).returncode == 0
+    # short-payload-test.sh
+    subprocess.check_call([cli, "test-gen-noise", a, "200", "44100"])
+    for bits, m in (("12", "abc"), ("16", "abcd"), ("20", "abcde")):
+        subprocess.check_call([cli, "add", "-q", "--short", bits, a, b, m])
+        assert subprocess.run([cli, "cmp", "--short", bits, b, m], capture_output=True).returncode == 0
+    # --linear round trip
+    subprocess.check_call([cli, "add", "-q", "--linear", a, b, msg])
+    assert subprocess.run([cli, "cmp", "--linear", b, msg], capture_output=True).returncode == 0
