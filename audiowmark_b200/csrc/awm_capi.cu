@@ -1130,7 +1130,8 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   /* default: sliding DFT over the 65 offsets (awm_refine_slide.cuh); AWM_REFINE=fft selects the kernel that transforms every
    * frame of every offset afresh (also used for more than two channels) */
   static const bool force_fft = [] { const char *e = getenv ("AWM_REFINE"); return e && !strcmp (e, "fft"); } ();
-  if (ctx->pcm_ch <= 2 && !force_fft)
+  const bool used_slide = ctx->pcm_ch <= 2 && !force_fft;
+  if (used_slide)
     {
       if (!ctx->tw1024.p)
         {
@@ -1195,6 +1196,112 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   CK (cudaMemcpyAsync (h_cnt.data(), ctx->r_cnt.p, h_cnt.size() * sizeof (int), cudaMemcpyDeviceToHost, ctx->stream));
   CK (cudaMemcpyAsync (h_valid.data(), ctx->rvalid.p, h_valid.size(), cudaMemcpyDeviceToHost, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
+  // sync_decode epilogue (src/syncfinder.cc:94-114,144-152) from the per-bit float sums
+  auto quality_of = [&] (const float *ud, const int *cnt, size_t base) -> double
+    {
+      double sync_quality = 0;
+      int bit_count = 0;
+      for (int bit = 0; bit < n_bits; bit++)
+        {
+          const size_t ob = base * n_bits + bit;
+          const float umag = ud[ob * 2], dmag = ud[ob * 2 + 1];
+          double raw_bit;
+          if (umag == 0 || dmag == 0)
+            raw_bit = 0;
+          else if (umag < dmag)
+            raw_bit = 1 - umag / dmag;
+          else
+            raw_bit = dmag / umag - 1;
+          sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * cnt[ob];
+          bit_count += cnt[ob];
+        }
+      if (bit_count)
+        sync_quality /= bit_count;
+      return sync_quality / norm_div / 2.9;
+    };
+  if (used_slide)
+    {
+      /* The sliding DFT ranks the 65 offsets; the best kVerify of each candidate are then scored again by k_refine (fresh FFTs, the
+       * reference's summation order: k_refine_exact_fft / _sum compute what k_refine computes), and the reference's rule picks among those exact values.  The quality peak is flat to ~1e-4
+       * relative, so rounding alone could otherwise move the arg-max by one 8-sample step; this keeps index and quality those of the
+       * exact kernel at ~6 % of its cost. */
+      constexpr int kVerify = 4;
+      std::vector<long long> p_start;
+      std::vector<int> p_noff, p_cand, p_off;
+      for (size_t c = 0; c < nc; c++)
+        {
+          std::vector<std::pair<double, int>> ranked;          // (-|q - local_mean|, offset): ascending sort = best first, lower offset first
+          for (int o = 0; o < h_noff[c]; o++)
+            if (h_valid[c * kOffsets + o])
+              ranked.push_back ({ -fabs (quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o) - scores[c].local_mean), o });
+          std::sort (ranked.begin(), ranked.end());
+          if (ranked.size() > size_t (kVerify))
+            ranked.resize (kVerify);
+          std::sort (ranked.begin(), ranked.end(), [] (const std::pair<double, int>& x, const std::pair<double, int>& y) { return x.second < y.second; });
+          for (const auto& r : ranked)
+            {
+              p_start.push_back (h_start[c] + 8LL * r.second);
+              p_noff.push_back (1);
+              p_cand.push_back (int (c));
+              p_off.push_back (r.second);
+            }
+        }
+      const size_t np = p_start.size();
+      std::vector<float> e_ud (np * n_bits * 2);
+      std::vector<int> e_cnt (np * n_bits);
+      std::vector<unsigned char> e_valid (np);
+      if (np)
+        {
+          CK (ctx->cand_start.reserve (np * sizeof (long long)));
+          CK (ctx->r_ent_ud.reserve (np * t.n_ent * 2 * kUD * sizeof (float)));
+          CK (ctx->r_ud.reserve (np * n_bits * 2 * sizeof (float)));
+          CK (ctx->r_cnt.reserve (np * n_bits * sizeof (int)));
+          CK (ctx->rvalid.reserve (np));
+          CK (cudaMemcpyAsync (ctx->cand_start.p, p_start.data(), np * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+          const size_t smem = fft_smem_bytes (kExactWarps) + kExactWarps * 96 * sizeof (float);
+          if (set_smem (ctx, k_refine_exact_fft, smem)) return 1;
+          const long long jobs = (long long) np * t.n_ent;
+          PROF (ctx);
+          k_refine_exact_fft<<<unsigned ((jobs + kExactWarps - 1) / kExactWarps), kExactWarps * 32, smem, ctx->stream>>> (
+            ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), int (np), t.ent.as<awm_sync_entry>(), t.n_ent,
+            ctx->r_ent_ud.as<float>(), ctx->tw.as<float2>(), ctx->win.as<float>());
+          LAUNCH_CHECK ("k_refine_exact_fft");
+          prof_bytes (ctx, double (np) * double (total) * kFrame * ctx->pcm_ch * sizeof (float));
+          PROF (ctx);
+          k_refine_exact_sum<<<unsigned ((np * n_bits * 2 + 63) / 64), 64, 0, ctx->stream>>> (
+            ctx->r_ent_ud.as<float>(), ctx->cand_start.as<long long>(), int (np), (long long) ctx->pcm_frames, ctx->pcm_ch, t.ent.as<awm_sync_entry>(), t.n_ent,
+            t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last, ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>());
+          LAUNCH_CHECK ("k_refine_exact_sum");
+          CK (cudaMemcpyAsync (e_ud.data(), ctx->r_ud.p, e_ud.size() * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+          CK (cudaMemcpyAsync (e_cnt.data(), ctx->r_cnt.p, e_cnt.size() * sizeof (int), cudaMemcpyDeviceToHost, ctx->stream));
+          CK (cudaMemcpyAsync (e_valid.data(), ctx->rvalid.p, e_valid.size(), cudaMemcpyDeviceToHost, ctx->stream));
+          CK (cudaStreamSynchronize (ctx->stream));
+        }
+      std::vector<double> best_quality (nc);
+      std::vector<uint64_t> best_index (nc);
+      for (size_t c = 0; c < nc; c++)
+        {
+          best_quality[c] = scores[c].raw_quality;
+          best_index[c] = scores[c].index;
+        }
+      for (size_t p = 0; p < np; p++)               // per candidate in ascending offset order
+        if (e_valid[p])
+          {
+            const size_t c = size_t (p_cand[p]);
+            const double q = quality_of (e_ud.data(), e_cnt.data(), p);
+            if (fabs (q - scores[c].local_mean) > fabs (best_quality[c] - scores[c].local_mean))   // src/syncfinder.cc:436-440
+              {
+                best_quality[c] = q;
+                best_index[c] = uint64_t (h_start[c] + 8LL * p_off[p]);
+              }
+          }
+      for (size_t c = 0; c < nc; c++)
+        {
+          scores[c].index = best_index[c];
+          scores[c].raw_quality = best_quality[c];
+        }
+      return 0;
+    }
   for (size_t c = 0; c < nc; c++)
     {
       awm_search_score& sc = scores[c];
@@ -1203,26 +1310,7 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
       for (int o = 0; o < h_noff[c]; o++)
         if (h_valid[c * kOffsets + o])
           {
-            // sync_decode epilogue (src/syncfinder.cc:94-114,144-152) from the per-bit float sums
-            double sync_quality = 0;
-            int bit_count = 0;
-            for (int bit = 0; bit < n_bits; bit++)
-              {
-                const size_t ob = (c * kOffsets + o) * n_bits + bit;
-                const float umag = h_ud[ob * 2], dmag = h_ud[ob * 2 + 1];
-                double raw_bit;
-                if (umag == 0 || dmag == 0)
-                  raw_bit = 0;
-                else if (umag < dmag)
-                  raw_bit = 1 - umag / dmag;
-                else
-                  raw_bit = dmag / umag - 1;
-                sync_quality += ((bit & 1) ? raw_bit : -raw_bit) * h_cnt[ob];
-                bit_count += h_cnt[ob];
-              }
-            if (bit_count)
-              sync_quality /= bit_count;
-            const double q = sync_quality / norm_div / 2.9;
+            const double q = quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o);
             if (fabs (q - sc.local_mean) > fabs (best_quality - sc.local_mean))   // src/syncfinder.cc:436-440
               {
                 best_quality = q;

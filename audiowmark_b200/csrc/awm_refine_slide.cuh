@@ -252,3 +252,84 @@ k_refine_reduce (const float2 *__restrict__ ent_ud, const unsigned char *__restr
 }
 
 } // namespace awm
+
+namespace awm {
+
+// ---- exact re-scoring of a few (candidate, offset) pairs picked by the sliding pass -------------------------------------------
+// k_refine computes the same thing with one warp per (pair, sync bit) walking 85 frames one after the other; for a handful of
+// pairs that is a long serial chain on a nearly empty GPU.  Here the transforms run in parallel (warp = one pair x one sync frame,
+// time-domain window and arithmetic of frame_db_sum, i.e. of the reference's sync_fft) and only the additions stay serial:
+// k_refine_exact_sum adds the stored band values of a bit in the reference's order (frames ascending, 30 up / 30 down bands each).
+constexpr int kExactWarps = 8;
+
+__global__ void __launch_bounds__ (kExactWarps * 32, 2)
+k_refine_exact_fft (const float *__restrict__ pcm, long long n_frames, int C, const long long *__restrict__ pair_start, int n_pairs,
+                    const awm_sync_entry *__restrict__ g_ent, int n_ent, float *__restrict__ vals /* [pair][entry][60] */,
+                    const float2 *g_tw, const float *g_win)
+{
+  extern __shared__ __align__ (16) unsigned char smem[];
+  FftSmem s = fft_smem_setup (smem, g_tw, g_win, kExactWarps);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *sband = s.extra + w * 96;
+  const long long job = (long long) blockIdx.x * kExactWarps + w;
+  if (job >= (long long) n_pairs * n_ent)
+    return;
+  const int p = int (job / n_ent), e = int (job % n_ent);
+  const awm_sync_entry *en = g_ent + e;
+  const long long start = pair_start[p] + (long long) en->frame * kFrame;
+  float acc[4];
+  frame_db_sum (pcm, n_frames, C, start, s, lane, acc);
+  bands_to_array (acc, lane, sband, 1);
+  __syncwarp();
+  float *o = vals + ((size_t) p * n_ent + e) * (2 * kUD);
+  if (lane < kUD)
+    {
+      o[lane] = sband[en->up[lane]];
+      o[kUD + lane] = sband[en->down[lane]];
+    }
+}
+
+__global__ void
+k_refine_exact_sum (const float *__restrict__ vals, const long long *__restrict__ pair_start, int n_pairs, long long n_frames, int C,
+                    const awm_sync_entry *__restrict__ g_ent, int n_ent, const int *__restrict__ g_bit_off, int n_bits, int total_frame_count,
+                    long long wav_first, long long wav_last, float *__restrict__ out_ud /* [pair][n_bits][2] */, int *__restrict__ out_cnt,
+                    unsigned char *__restrict__ out_valid)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs * n_bits * 2)
+    return;
+  const int p = i / (n_bits * 2), bit = (i / 2) % n_bits, which = i & 1;       // which: 0 = up bands, 1 = down bands
+  const long long fine = pair_start[p];
+  const bool valid = fine + (long long) total_frame_count * kFrame <= n_frames;
+  if (bit == 0 && which == 0)
+    out_valid[p] = valid ? 1 : 0;
+  if (!valid)
+    return;
+  float mag = 0.f;
+  int cnt = 0;
+  for (int e = g_bit_off[bit]; e < g_bit_off[bit + 1]; e++)
+    {
+      const long long start = fine + (long long) g_ent[e].frame * kFrame;
+      const long long f_first = start * C, f_last = (start + kFrame) * C;
+      if (f_last < wav_first || f_first > wav_last)     // frame in digital silence: not counted
+        continue;
+      // all 30 values of the frame in flight first (15 x 8 bytes, 8-byte aligned), then the serial additions
+      const float2 *v2 = reinterpret_cast<const float2 *> (vals + ((size_t) p * n_ent + e) * (2 * kUD) + which * kUD);
+      float2 r[kUD / 2];
+#pragma unroll
+      for (int k = 0; k < kUD / 2; k++)
+        r[k] = __ldg (v2 + k);
+#pragma unroll
+      for (int k = 0; k < kUD / 2; k++)
+        {
+          mag = __fadd_rn (mag, r[k].x);
+          mag = __fadd_rn (mag, r[k].y);
+        }
+      cnt++;
+    }
+  out_ud[((size_t) p * n_bits + bit) * 2 + which] = mag;
+  if (which == 0)
+    out_cnt[(size_t) p * n_bits + bit] = cnt;
+}
+
+} // namespace awm

@@ -219,3 +219,4 @@ def test_cli_reference_order_kernels_give_the_same_answer(tmp_path):
     exact = subprocess.run([cli, "get", b], capture_output=True, text=True, check=True, env=env).stdout
     real = lambda out: [l for l in out.split("\n") if "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0" in l]
     assert len(real(fast)) == 5 and real(fast) == real(exact)
+    assert "\n".join(real(fast)) + "\n" == "\n".join(G["noise200"]["cmp_stdout"].split("\n")[:5]) + "\n"      # and they are the reference's lines
