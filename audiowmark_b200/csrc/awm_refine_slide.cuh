@@ -307,25 +307,37 @@ k_refine_exact_sum (const float *__restrict__ vals, const long long *__restrict_
     return;
   float mag = 0.f;
   int cnt = 0;
-  for (int e = g_bit_off[bit]; e < g_bit_off[bit + 1]; e++)
+  const int e0 = g_bit_off[bit], e1 = g_bit_off[bit + 1];
+  // the values of frame e + 1 are fetched (15 x 8 bytes, 8-byte aligned) while those of frame e are added one after the other
+  float2 cur[kUD / 2], nxt[kUD / 2];
+  auto fetch = [&] (int e, float2 (&r)[kUD / 2])
     {
-      const long long start = fine + (long long) g_ent[e].frame * kFrame;
-      const long long f_first = start * C, f_last = (start + kFrame) * C;
-      if (f_last < wav_first || f_first > wav_last)     // frame in digital silence: not counted
-        continue;
-      // all 30 values of the frame in flight first (15 x 8 bytes, 8-byte aligned), then the serial additions
       const float2 *v2 = reinterpret_cast<const float2 *> (vals + ((size_t) p * n_ent + e) * (2 * kUD) + which * kUD);
-      float2 r[kUD / 2];
 #pragma unroll
       for (int k = 0; k < kUD / 2; k++)
         r[k] = __ldg (v2 + k);
+    };
+  if (e0 < e1)
+    fetch (e0, cur);
+  for (int e = e0; e < e1; e++)
+    {
+      if (e + 1 < e1)
+        fetch (e + 1, nxt);
+      const long long start = fine + (long long) g_ent[e].frame * kFrame;
+      const long long f_first = start * C, f_last = (start + kFrame) * C;
+      if (!(f_last < wav_first || f_first > wav_last))     // frames in digital silence are not counted
+        {
+#pragma unroll
+          for (int k = 0; k < kUD / 2; k++)
+            {
+              mag = __fadd_rn (mag, cur[k].x);
+              mag = __fadd_rn (mag, cur[k].y);
+            }
+          cnt++;
+        }
 #pragma unroll
       for (int k = 0; k < kUD / 2; k++)
-        {
-          mag = __fadd_rn (mag, r[k].x);
-          mag = __fadd_rn (mag, r[k].y);
-        }
-      cnt++;
+        cur[k] = nxt[k];
     }
   out_ud[((size_t) p * n_bits + bit) * 2 + which] = mag;
   if (which == 0)
