@@ -192,6 +192,34 @@ awmh_conv_encode (int block_type, const uint8_t *bits, int n, uint8_t *out, int 
   return int (enc.size());
 }
 
+/* short payload block code (src/shortcode.cc:136-213) under the current --short setting: encode k -> n bits, decode n -> k bits
+ * (returns 0 when no code word matches) */
+int
+awmh_short_encode (const uint8_t *bits, int k, uint8_t *out, int max_out)
+{
+  if (!Params::payload_short || size_t (k) != Params::payload_size)
+    return -1;
+  const std::vector<int> enc = short_encode_blk (std::vector<int> (bits, bits + k));
+  if (int (enc.size()) > max_out)
+    return -1;
+  for (size_t i = 0; i < enc.size(); i++)
+    out[i] = enc[i];
+  return int (enc.size());
+}
+
+int
+awmh_short_decode (const uint8_t *coded, int n, uint8_t *out, int max_out)
+{
+  if (!Params::payload_short || size_t (n) != code_message_bits())
+    return -1;
+  const std::vector<int> dec = short_decode_blk (std::vector<int> (coded, coded + n));
+  if (int (dec.size()) > max_out)
+    return -1;
+  for (size_t i = 0; i < dec.size(); i++)
+    out[i] = dec[i];
+  return int (dec.size());
+}
+
 /* add_stream_watermark on buffers (host or device pointers) */
 int
 awmh_add (const unsigned char *key16, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16", "awmh_short_encode", "awmh_short_decode"]
 
 _lib = None
 
@@ -125,6 +125,26 @@ def conv_encode(block_type: int, bits) -> np.ndarray:
     b = np.ascontiguousarray(bits, np.uint8)
     out = np.zeros((len(b) + 15) * 12, np.uint8)
     n = load().awmh_conv_encode(ctypes.c_int(block_type), _ptr(b), ctypes.c_int(len(b)), _ptr(out), ctypes.c_int(len(out)))
+    return out[:n].copy()
+
+
+def short_encode(bits) -> np.ndarray:
+    """block code of the current --short mode: k message bits -> n code bits"""
+    b = np.ascontiguousarray(bits, np.uint8)
+    out = np.zeros(128, np.uint8)
+    n = load().awmh_short_encode(_ptr(b), ctypes.c_int(len(b)), _ptr(out), ctypes.c_int(len(out)))
+    if n < 0:
+        raise ValueError("short payload mode is off or the message length does not match")
+    return out[:n].copy()
+
+
+def short_decode(coded) -> np.ndarray:
+    """n code bits -> k message bits; empty if no code word matches"""
+    c = np.ascontiguousarray(coded, np.uint8)
+    out = np.zeros(32, np.uint8)
+    n = load().awmh_short_decode(_ptr(c), ctypes.c_int(len(c)), _ptr(out), ctypes.c_int(len(out)))
+    if n < 0:
+        raise ValueError("short payload mode is off or the code length does not match")
     return out[:n].copy()
 
 

@@ -141,3 +141,40 @@ def test_resampler_stream_counts_match_oracle():
             for n in (0, 1, 1023, 1024, 1025, 5000, rate, rate + 1, 7 * rate - 1, 361417, 6_400_000):
                 assert H.resampled_add_plan(n, rate) == O.resampled_add_plan(n, rate, P), (rate, n, no_lim)
     H.set_params()
+
+
+def test_short_payload_and_linear_tables_byte_exact():
+    """--short 12/16/20 (block code in front of the convolutional code: different block length, sync positions and
+    frame-mod tables) and --linear (un-mixed data frames): host tables against the oracle, block code round trip"""
+    key = KEYS[0]
+    rng = np.random.default_rng(11)
+    try:
+        for k, n, payload in ((12, 56, "abc"), (16, 61, "abcd"), (20, 65, "abcde")):
+            H.set_params()
+            H.set_short_payload(k)
+            Pk = O.Params(payload_short=True, payload_size=k)
+            assert H.frames_per_block() == O.frames_per_block(Pk) == 510 + 2 * 6 * (n + 15)
+            assert H.n_coded_bits() == O.code_size(O.A, Pk)
+            for _ in range(20):
+                msg = rng.integers(0, 2, k)
+                enc = H.short_encode(msg)
+                assert list(enc) == O.short_encode_blk([int(b) for b in msg], k) and len(enc) == n
+                assert list(H.short_decode(enc)) == [int(b) for b in msg]
+                bad = enc.copy()
+                bad[rng.integers(0, n)] ^= 1                       # minimum distance >= 20: a single bit error is no code word
+                assert len(H.short_decode(bad)) == 0 and O.short_decode_blk([int(b) for b in bad], k) == []
+            ent, off = H.sync_table(key.aes_key, capi.MODE_BLOCK)
+            went, woff = T.sync_entries(key, capi.MODE_BLOCK, Pk)
+            assert ent.tobytes() == went.tobytes() and np.array_equal(off, woff)
+            assert H.frame_mod(key.aes_key, payload).tobytes() == T.frame_mod_ab(key, payload, Pk).tobytes()
+        H.set_short_payload(0)
+        H.set_params(mix=False)
+        Pl = O.Params(mix=False)
+        assert H.frame_mod(key.aes_key, T.PAYLOAD).tobytes() == T.frame_mod_ab(key, T.PAYLOAD, Pl).tobytes()
+        mix, order = H.mix_table(key.aes_key)                       # --linear: the same triples, not shuffled
+        udg, bpg = O.UpDownGen(key, O.STREAM_DATA_UP_DOWN, Pl), O.BitPosGen(key, Pl)
+        want = [(bpg.data_frame(f), u, d) for f in range(O.mark_data_frame_count(Pl)) for u, d in zip(*udg.get(f))]
+        assert [(int(m["frame"]), int(m["up"]), int(m["down"])) for m in mix] == [(int(a), int(b), int(c)) for a, b, c in want]
+    finally:
+        H.set_short_payload(0)
+        H.set_params()
