@@ -1003,39 +1003,39 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     }
   else
     {
-  CK (ctx->dbT.reserve (size_t (4) * kBands * ld * sizeof (float)));
-  {
-    const size_t smem = fft_smem_bytes (kStftWarps) + kBands * (kStftWarps + 1) * sizeof (float);
-    if (set_smem (ctx, k_stft_db, smem)) return 1;
-    const unsigned grid = 4u * unsigned ((n_out + kStftWarps - 1) / kStftWarps);
-    PROF (ctx);
-    k_stft_db<<<grid, kStftWarps * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
-                                                            ctx->dbT.as<float>(), ctx->have.as<unsigned char>(),
-                                                            (long long) wav_first, (long long) wav_last,
-                                                            ctx->tw.as<float2>(), ctx->win.as<float>());
-    LAUNCH_CHECK ("k_stft_db");
-  }
-  {
-    const size_t smem = kApproxSmem;
-    dim3 grid (unsigned ((n_starts + kApproxCands - 1) / kApproxCands), 4);
-    if (mode == AWM_MODE_CLIP)
+      CK (ctx->dbT.reserve (size_t (4) * kBands * ld * sizeof (float)));
       {
-        if (set_smem (ctx, k_sync_approx<true>, smem)) return 1;
+        const size_t smem = fft_smem_bytes (kStftWarps) + kBands * (kStftWarps + 1) * sizeof (float);
+        if (set_smem (ctx, k_stft_db, smem)) return 1;
+        const unsigned grid = 4u * unsigned ((n_out + kStftWarps - 1) / kStftWarps);
         PROF (ctx);
-        k_sync_approx<true><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
-                                                                        t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
-                                                                        ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
+        k_stft_db<<<grid, kStftWarps * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
+                                                                ctx->dbT.as<float>(), ctx->have.as<unsigned char>(),
+                                                                (long long) wav_first, (long long) wav_last,
+                                                                ctx->tw.as<float2>(), ctx->win.as<float>());
+        LAUNCH_CHECK ("k_stft_db");
       }
-    else
       {
-        if (set_smem (ctx, k_sync_approx<false>, smem)) return 1;
-        PROF (ctx);
-        k_sync_approx<false><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
-                                                                         t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
-                                                                         ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
+        const size_t smem = kApproxSmem;
+        dim3 grid (unsigned ((n_starts + kApproxCands - 1) / kApproxCands), 4);
+        if (mode == AWM_MODE_CLIP)
+          {
+            if (set_smem (ctx, k_sync_approx<true>, smem)) return 1;
+            PROF (ctx);
+            k_sync_approx<true><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
+                                                                            t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
+                                                                            ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
+          }
+        else
+          {
+            if (set_smem (ctx, k_sync_approx<false>, smem)) return 1;
+            PROF (ctx);
+            k_sync_approx<false><<<grid, kApproxThreads, smem, ctx->stream>>> (ctx->dbT.as<float>(), ctx->have.as<unsigned char>(), ld, int (n_out), int (n_starts),
+                                                                             t.sorted.as<ApproxEntry>(), t.groups.as<int>(), t.n_groups, t.n_bits,
+                                                                             ctx->a_ud.as<float>(), ctx->a_cnt.as<int>());
+          }
+        LAUNCH_CHECK ("k_sync_approx");
       }
-    LAUNCH_CHECK ("k_sync_approx");
-  }
     }
   {
     PROF (ctx);
@@ -1176,18 +1176,18 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
     }
   else
     {
-  const size_t smem = fft_smem_bytes (kRefineWarps) + kRefineWarps * 96 * sizeof (float);
-  if (set_smem (ctx, k_refine, smem)) return 1;
-  const long long jobs = (long long) nc * kOffsets * n_bits;
-  PROF (ctx);
-  k_refine<<<unsigned ((jobs + kRefineWarps - 1) / kRefineWarps), kRefineWarps * 32, smem, ctx->stream>>> (
-    ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
-    t.ent.as<awm_sync_entry>(), t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last,
-    ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>(), ctx->tw.as<float2>(), ctx->win.as<float>());
-  LAUNCH_CHECK ("k_refine");
-  /* compulsory traffic: every candidate's window of sync frames (one block, two in CLIP mode, + the +-256 samples of the
-   * offsets) is read once -- the 65 offsets x 6 bits re-read it from L2 */
-  prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
+      const size_t smem = fft_smem_bytes (kRefineWarps) + kRefineWarps * 96 * sizeof (float);
+      if (set_smem (ctx, k_refine, smem)) return 1;
+      const long long jobs = (long long) nc * kOffsets * n_bits;
+      PROF (ctx);
+      k_refine<<<unsigned ((jobs + kRefineWarps - 1) / kRefineWarps), kRefineWarps * 32, smem, ctx->stream>>> (
+        ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), ctx->cand_noff.as<int>(), int (nc),
+        t.ent.as<awm_sync_entry>(), t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last,
+        ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>(), ctx->tw.as<float2>(), ctx->win.as<float>());
+      LAUNCH_CHECK ("k_refine");
+      /* compulsory traffic: every candidate's window of sync frames (one block, two in CLIP mode, + the +-256 samples of the
+       * offsets) is read once -- the 65 offsets x 6 bits re-read it from L2 */
+      prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
     }
   std::vector<float> h_ud (nc * kOffsets * n_bits * 2);
   std::vector<int> h_cnt (nc * kOffsets * n_bits);
