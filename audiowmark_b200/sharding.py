@@ -167,6 +167,16 @@ def rank_slices(plan, rank: int, world: int, n_total: int):
     return out
 
 
+def index_owners(plan, n_total: int, world: int, chunk: int, indices) -> np.ndarray:
+    """rank that owns each chunk-relative sample index (by the start frame it falls into): the rank whose slice of `chunk`
+    contains that start frame in [sa, sb) (rank_slices uses the same position rule)"""
+    cs, cn, _ = plan[chunk]
+    n_starts = max(cn // FRAME - T_BLOCK - 1, 0)
+    s = np.clip(np.asarray(indices, np.int64) // FRAME, 0, max(n_starts - 1, 0))
+    span = owner_span(n_total, world)
+    return np.minimum((cs + s * FRAME) // span, world - 1)
+
+
 def _pack(arrs) -> bytes:
     import pickle
     return pickle.dumps(arrs, protocol=4)
@@ -316,11 +326,7 @@ class BalancedGet:
 
     def owners(self, chunk, indices) -> np.ndarray:
         """owner_of for an array of chunk-relative sample indices"""
-        cs, cn, _ = self.plan[chunk]
-        n_starts = max(cn // FRAME - T_BLOCK - 1, 0)
-        s = np.clip(np.asarray(indices, np.int64) // FRAME, 0, max(n_starts - 1, 0))
-        span = owner_span(self.n_total, self.world)
-        return np.minimum((cs + s * FRAME) // span, self.world - 1)
+        return index_owners(self.plan, self.n_total, self.world, chunk, indices)
 
     def viterbi_rank(self, chunk) -> int:
         """all code words of a chunk are decoded (and packed for the merge) by one rank, so that no rank builds the job list of

@@ -128,3 +128,35 @@ def test_result_gather_over_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK 5" in outs[0][0]
+
+
+def test_every_start_frame_has_exactly_one_owner_up_to_8_ranks():
+    """frame-balanced get: the position rule that deals candidates / blocks to ranks (index_owners) and the slices the ranks
+    search (rank_slices) must agree for every world size the bench runs (1, 2, 4, 8) and for ragged stream lengths"""
+    rng = np.random.default_rng(5)
+    for hours, world in ((1, 1), (2, 2), (4, 4), (8, 8), (1.37, 3), (0.2, 8), (8, 5)):
+        n_total = int(hours * 3600 * 44100)
+        mx = int(round(30.0 * 60 * 44100))
+        ov = int(round(2 * (2226 * 1024 / 44100.0) * 1.3 * 44100))
+        plan = S.chunk_plan(n_total, mx, ov)
+        slices = [S.rank_slices(plan, r, world, n_total) for r in range(world)]
+        for c, (cs, cn, _) in enumerate(plan):
+            n_starts = max(cn // S.FRAME - S.T_BLOCK - 1, 0)
+            if n_starts == 0:
+                assert not any(sl.chunk == c for per in slices for sl in per)
+                continue
+            # the owned ranges [sa, sb) of all ranks tile [0, n_starts) without gaps or overlaps
+            owned = sorted((sl.sa, sl.sb, r) for r, per in enumerate(slices) for sl in per if sl.chunk == c)
+            assert owned[0][0] == 0 and owned[-1][1] == n_starts
+            assert all(a[1] == b[0] for a, b in zip(owned, owned[1:]))
+            # ... and index_owners sends every index to the rank whose range holds its start frame
+            idx = np.concatenate([rng.integers(0, cn, 200), np.array([0, cn - 1, (n_starts - 1) * S.FRAME, n_starts * S.FRAME + 5])])
+            own = S.index_owners(plan, n_total, world, c, idx)
+            s = np.clip(idx // S.FRAME, 0, n_starts - 1)
+            for si, r in zip(s, own):
+                assert any(a <= si < b and rr == r for a, b, rr in owned), (hours, world, c, int(si), int(r))
+            # every slice carries the PCM its searched range [a, b) needs: b + one block + one frame, inside the chunk
+            for per in slices:
+                for sl in per:
+                    if sl.chunk == c:
+                        assert sl.lo == cs + sl.a * S.FRAME and sl.hi <= cs + cn and sl.hi >= min(cs + (sl.b + S.T_BLOCK + 1) * S.FRAME, cs + cn)
