@@ -178,3 +178,18 @@ def test_short_payload_and_linear_tables_byte_exact():
     finally:
         H.set_short_payload(0)
         H.set_params()
+
+
+def test_cli_option_handling_of_speed_and_short_modes(tmp_path):
+    """argv handling that needs no GPU (src/audiowmark.cc:389-397, 665-674, 831-854): option conflicts, unsupported sizes, test-speed"""
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "audiowmark_b200", "bin", "audiowmark")
+    p = subprocess.run([cli, "get", "--detect-speed", "--try-speed", "1.01", "x.wav"], capture_output=True, text=True)
+    assert p.returncode == 1 and "can only use one option: --detect-speed or --detect-speed-patient or --try-speed" in p.stderr
+    p = subprocess.run([cli, "add", "--short", "13", "a.wav", "b.wav", "abc"], capture_output=True, text=True)
+    assert p.returncode == 1 and "unsupported short payload size 13" in p.stderr
+    # test-speed: one keyed PRNG draw mapped to [0.85, 1.15] (tests/detect-speed-test.sh's companion command)
+    for seed in (0, 1, 42):
+        out = subprocess.check_output([cli, "test-speed", "--test-key", "7", str(seed)], text=True)
+        r = O.Random(O.Key.test_key(7), seed, O.STREAM_DATA_UP_DOWN)
+        assert out == "%.6f\n" % (0.85 + (r() / float(2 ** 64 - 1)) * (1.15 - 0.85))
