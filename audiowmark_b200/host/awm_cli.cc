@@ -390,8 +390,7 @@ parse_get_options (ArgParser& ap)
         }
       Params::get_n_best = i;
     }
-  if (ap.parse_opt ("--strength", f))
-    Params::water_delta = f / 1000;
+  /* --strength is an `add` option only: `get` normalises sync qualities with the default strength (src/audiowmark.cc:806-809) */
 }
 
 static vector<string>

@@ -134,6 +134,15 @@ def main():
         G["short16"] = opt_case("s16", "abcd", ("--short", 16))
         G["short20"] = opt_case("s20", "abcde", ("--short", 20))
         G["linear120"] = opt_case("lin", T.PAYLOAD, ("--linear",))
+        # --strength (add only) / --frames-per-bit / --hard (get only)
+        def opt_case2(name, payload, add_opts, get_opts):
+            src, dst = os.path.join(tmp, name + ".wav"), os.path.join(tmp, name + "_wm.wav")
+            run("test-gen-noise", src, 130, 44100)
+            p = run("add", *add_opts, src, dst, payload)
+            g = run("get", *get_opts, "--json", js, dst)
+            return {"add_opts": list(add_opts), "get_opts": list(get_opts), "payload": payload, "output_sha256": sha(pcm16(dst)),
+                    "add_stderr": p.stderr, "get_stdout": g.stdout, "json": json.load(open(js))}
+        G["strength15_fpb3_hard"] = opt_case2("fpb3", T.PAYLOAD, ("--strength", 15, "--frames-per-bit", 3), ("--frames-per-bit", 3, "--hard"))
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     json.dump(G, open(out, "w"), indent=1, sort_keys=True)
     print("wrote", out, os.path.getsize(out), "bytes")

@@ -188,6 +188,8 @@ def test_cli_option_handling_of_speed_and_short_modes(tmp_path):
     assert p.returncode == 1 and "can only use one option: --detect-speed or --detect-speed-patient or --try-speed" in p.stderr
     p = subprocess.run([cli, "add", "--short", "13", "a.wav", "b.wav", "abc"], capture_output=True, text=True)
     assert p.returncode == 1 and "unsupported short payload size 13" in p.stderr
+    p = subprocess.run([cli, "get", "--strength", "15", "x.wav"], capture_output=True, text=True)      # add-only option in the reference
+    assert p.returncode == 1 and "unsupported option '--strength' for command 'get'" in p.stderr
     # test-speed: one keyed PRNG draw mapped to [0.85, 1.15] (tests/detect-speed-test.sh's companion command)
     for seed in (0, 1, 42):
         out = subprocess.check_output([cli, "test-speed", "--test-key", "7", str(seed)], text=True)

@@ -186,3 +186,17 @@ def test_short_payload_and_linear_exact_vs_reference(name):
     assert "\n".join(rs.lines()) + "\n" == g["get_stdout"]
     assert rs.json_doc(120) == fmt_ref_json(g["json"])
     assert g["cmp_rc"] == 0
+
+
+def test_strength_frames_per_bit_hard_exact_vs_reference():
+    """--strength 15 --frames-per-bit 3 on add (block length 3084 frames), --frames-per-bit 3 --hard on get"""
+    g = G["strength15_fpb3_hard"]
+    x = q16(O.gen_noise(130))
+    Pa = O.Params(water_delta=float(np.float32(15.0)) / 1000, frames_per_bit=3)      # the CLI parses 15 as float, then / 1000
+    r = O.embed(x, O.Key(), g["payload"], Pa)
+    y16 = O.quantize_sndfile16(r.samples)
+    assert sha(y16) == g["output_sha256"]
+    assert ("Data Blocks:  %d\n" % r.data_blocks) in g["add_stderr"]
+    rs = O.get_watermark(O.int16_to_float(y16), [O.Key()], O.Params(frames_per_bit=3, hard=True))
+    assert "\n".join(rs.lines()) + "\n" == g["get_stdout"]
+    assert rs.json_doc(130) == fmt_ref_json(g["json"])
