@@ -50,10 +50,13 @@ print_usage()
   printf ("  --gpu-device <n>        CUDA device to run on                [0]\n");
   printf ("\n");
   printf ("Options for get / cmp:\n");
+  printf ("  --detect-speed          detect and correct replay speed difference\n");
+  printf ("  --detect-speed-patient  slower, more accurate speed detection\n");
   printf ("  --json <file>           write JSON results into file\n");
   printf ("\n");
   printf ("Options for add / get / cmp:\n");
   printf ("  --key <file>            load watermarking key from file\n");
+  printf ("  --short <bits>          enable short payload mode\n");
   printf ("  --strength <s>          set watermark strength              [%.6g]\n", Params::water_delta * 1000);
   printf ("\n");
   printf ("  --input-format raw      use raw stream as input\n");
