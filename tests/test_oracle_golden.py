@@ -80,8 +80,7 @@ def test_get_exact_vs_reference(name):
 def test_sync_after_cut_vs_reference():
     """tests/sync-test.sh: 200 s reference noise, 882300 samples cut off -> 3 matches."""
     g = G["noise200"]
-    x = q16(O.gen_noise(200))
-    y16 = O.quantize_sndfile16(O.embed(x, O.Key(), "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", P).samples)
+    y16 = O.quantize_sndfile16(T.watermarked_noise(200))        # shared with test_get_48000_vs_reference (cached)
     assert sha(y16) == g["wm_sha256"]
     y = O.int16_to_float(y16)[882300:]
     rs = O.ResultSet()
