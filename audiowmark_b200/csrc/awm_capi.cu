@@ -1266,7 +1266,8 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
             ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), int (np), t.ent.as<awm_sync_entry>(), t.n_ent,
             ctx->r_ent_ud.as<float>(), ctx->tw.as<float2>(), ctx->win.as<float>());
           LAUNCH_CHECK ("k_refine_exact_fft");
-          prof_bytes (ctx, double (np) * double (total) * kFrame * ctx->pcm_ch * sizeof (float));
+          /* the re-scored offsets of a candidate lie within 512 samples of each other: its window is compulsory traffic once */
+          prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
           PROF (ctx);
           k_refine_exact_sum<<<unsigned ((np * n_bits * 2 + 63) / 64), 64, 0, ctx->stream>>> (
             ctx->r_ent_ud.as<float>(), ctx->cand_start.as<long long>(), int (np), (long long) ctx->pcm_frames, ctx->pcm_ch, t.ent.as<awm_sync_entry>(), t.n_ent,
