@@ -143,6 +143,17 @@ def main():
             return {"add_opts": list(add_opts), "get_opts": list(get_opts), "payload": payload, "output_sha256": sha(pcm16(dst)),
                     "add_stderr": p.stderr, "get_stdout": g.stdout, "json": json.load(open(js))}
         G["strength15_fpb3_hard"] = opt_case2("fpb3", T.PAYLOAD, ("--strength", 15, "--frames-per-bit", 3), ("--frames-per-bit", 3, "--hard"))
+        # ---- two keys (tests/key-test.sh): 30 s noise watermarked twice with named keys from key files; get with both keys
+        k1, k2 = os.path.join(tmp, "k1.key"), os.path.join(tmp, "k2.key")
+        open(k1, "w").write('# watermarking key for audiowmark\n\nkey 000102030405060708090a0b0c0d0e0f\nname "alpha"\n')
+        open(k2, "w").write('key 101112131415161718191a1b1c1d1e1f\nname "beta"\n')
+        o1, o2 = os.path.join(tmp, "ko1.wav"), os.path.join(tmp, "ko2.wav")
+        run("test-gen-noise", nz, 30, 44100)
+        run("add", "--key", k1, nz, o1, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0")
+        run("add", "--key", k2, o1, o2, "0123456789abcdef0123456789abcdef")
+        g2 = run("get", "--key", k1, "--key", k2, "--json", js, o2)
+        G["two_keys30"] = {"keys": {"alpha": "000102030405060708090a0b0c0d0e0f", "beta": "101112131415161718191a1b1c1d1e1f"},
+                           "output_sha256": sha(pcm16(o2)), "get_stdout": g2.stdout, "json": json.load(open(js))}
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     json.dump(G, open(out, "w"), indent=1, sort_keys=True)
     print("wrote", out, os.path.getsize(out), "bytes")

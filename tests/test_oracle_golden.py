@@ -199,3 +199,17 @@ def test_strength_frames_per_bit_hard_exact_vs_reference():
     rs = O.get_watermark(O.int16_to_float(y16), [O.Key()], O.Params(frames_per_bit=3, hard=True))
     assert "\n".join(rs.lines()) + "\n" == g["get_stdout"]
     assert rs.json_doc(130) == fmt_ref_json(g["json"])
+
+
+def test_two_named_keys_exact_vs_reference():
+    """tests/key-test.sh: a file watermarked twice with two keys (key files with names), `get --key k1 --key k2`"""
+    g = G["two_keys30"]
+    ka = O.Key(bytes.fromhex(g["keys"]["alpha"]), "alpha")
+    kb = O.Key(bytes.fromhex(g["keys"]["beta"]), "beta")
+    x = q16(O.gen_noise(30))
+    y1 = q16(O.embed(x, ka, "f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0f0", P).samples)
+    y2_16 = O.quantize_sndfile16(O.embed(y1, kb, "0123456789abcdef0123456789abcdef", P).samples)
+    assert sha(y2_16) == g["output_sha256"]
+    rs = O.get_watermark(O.int16_to_float(y2_16), [ka, kb], P)
+    assert "\n".join(rs.lines()) + "\n" == g["get_stdout"]
+    assert rs.json_doc(30) == fmt_ref_json(g["json"])
