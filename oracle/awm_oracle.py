@@ -920,13 +920,16 @@ def mix_decode(key: Key, spect, nch, P: Params) -> np.ndarray:      # wmget.cc:6
 
 def linear_decode(key: Key, spect, nch, P: Params) -> np.ndarray:   # wmget.cc:110-152
     fc = mark_data_frame_count(P)
-    udg, bpg = UpDownGen(key, STREAM_DATA_UP_DOWN, P), BitPosGen(key, P)
-    df, up, down = [], [], []
-    for f in range(fc):
-        df.append(bpg.data_frame(f))
-        u, d = udg.get(f)
-        up += u; down += d
-    df, up, down = (np.array(x, dtype=np.int32) for x in (df, up, down))
+    k = ("linear", key.aes_key, P.payload_size, P.frames_per_bit, P.payload_short)
+    if k not in _MIX_CACHE:                              # key tables are the same for every block: build them once
+        udg, bpg = UpDownGen(key, STREAM_DATA_UP_DOWN, P), BitPosGen(key, P)
+        df, up, down = [], [], []
+        for f in range(fc):
+            df.append(bpg.data_frame(f))
+            u, d = udg.get(f)
+            up += u; down += d
+        _MIX_CACHE[k] = tuple(np.array(x, dtype=np.int32) for x in (df, up, down))
+    df, up, down = _MIX_CACHE[k]
     out = np.zeros(fc // P.frames_per_bit, dtype=np.float32)
     lib().orc_linear_decode(_p(spect), ctypes.c_int64(spect.shape[0]), ctypes.c_int(P.frame_size), ctypes.c_int(nch),
                             _p(df), _p(up), _p(down), ctypes.c_int(fc), ctypes.c_int(P.bands_per_frame), ctypes.c_int(P.frames_per_bit), _p(out))

@@ -86,18 +86,23 @@ orc_analyze_frames (const float *samples, int n_channels, const int64_t *starts,
                     const float *window, int n, float *out)
 {
   Plans& p = plans_for (n);
-  std::vector<float> frame (n + 2);
-  for (int64_t j = 0; j < n_jobs; j++)
-    for (int ch = 0; ch < n_channels; ch++)
-      {
-        int64_t pos = starts[j] * n_channels + ch;
-        for (int x = 0; x < n; x++)
-          {
-            frame[x] = samples[pos] * window[x];
-            pos += n_channels;
-          }
-        fftwf_execute_dft_r2c (p.fwd, frame.data(), (fftwf_complex *) (out + (j * n_channels + ch) * (n + 2)));
-      }
+  /* independent jobs: spread over threads (execute keeps its scratch on the caller's stack), same arithmetic per job */
+#pragma omp parallel
+  {
+    std::vector<float> frame (n + 2);
+#pragma omp for schedule(static)
+    for (int64_t j = 0; j < n_jobs; j++)
+      for (int ch = 0; ch < n_channels; ch++)
+        {
+          int64_t pos = starts[j] * n_channels + ch;
+          for (int x = 0; x < n; x++)
+            {
+              frame[x] = samples[pos] * window[x];
+              pos += n_channels;
+            }
+          fftwf_execute_dft_r2c (p.fwd, frame.data(), (fftwf_complex *) (out + (j * n_channels + ch) * (n + 2)));
+        }
+  }
 }
 
 /* db_from_complex (src/wmcommon.hh:204-224) */
