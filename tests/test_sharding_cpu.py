@@ -160,3 +160,25 @@ def test_every_start_frame_has_exactly_one_owner_up_to_8_ranks():
                 for sl in per:
                     if sl.chunk == c:
                         assert sl.lo == cs + sl.a * S.FRAME and sl.hi <= cs + cn and sl.hi >= min(cs + (sl.b + S.T_BLOCK + 1) * S.FRAME, cs + cn)
+
+
+def test_balanced_merge_accepts_per_chunk_blobs_from_the_viterbi_owners():
+    """frame-balanced get, last stage: every chunk's records arrive packed by the rank that decoded them (chunk mod world);
+    the merge on rank 0 must equal merging the same records directly (host code only, no GPU context)"""
+    rng = np.random.default_rng(4)
+    n_total = 2 * 158760000
+    plan = S.chunk_plan(n_total, 79380000, 5926502)
+    payload = O.parse_payload("0123456789abcdef0011223344556677", P)
+    blobs = []
+    for c in range(len(plan)):
+        pats = [(5.8 + 51.688 * k, float(rng.uniform(0.4, 1.4)), int((5.8 + 51.688 * k) * 44100), float(np.float32(rng.uniform(0.05, 0.3))), k & 1, 0, 1.0, payload)
+                for k in range(4)]
+        blobs.append(_records(pats))
+    world = 2
+    payloads = [S._pack({c: blobs[c] for c in range(len(plan)) if c % world == r}) for r in range(world)]
+    job = object.__new__(S.BalancedGet)                       # host-side state only
+    job.plan, job.H, job.key, job.n_total, job.rate, job.rank, job.world = plan, H, bytes(16), n_total, 44100, 0, world
+    assert [job.viterbi_rank(c) for c in range(len(plan))] == [c % world for c in range(len(plan))]
+    got = job.stage_merge(payloads)
+    want = H.merge_chunks(blobs, [p[2] for p in plan], n_total / 44100.0)
+    assert got == want and len(got["matches"]) >= 4
