@@ -27,7 +27,7 @@ EXPORTS = [
     "awm_create", "awm_destroy", "awm_last_error", "awm_launch_count", "awm_stream", "awm_synchronize",
     "awm_profile_enable", "awm_profile_report", "awm_host_alloc", "awm_host_free",
     "awm_fft_r2c", "awm_fft_c2r", "awm_set_embed_tables", "awm_set_sync_tables", "awm_set_mix_tables",
-    "awm_pcm_bind", "awm_pcm_prefetch", "awm_embed", "awm_sync_approx", "awm_sync_peaks", "awm_sync_refine", "awm_decode_blocks", "awm_viterbi",
+    "awm_pcm_bind", "awm_pcm_prefetch", "awm_embed", "awm_sync_approx", "awm_sync_peaks", "awm_sync_refine", "awm_sync_refine_offsets", "awm_decode_blocks", "awm_viterbi",
     "awm_resample", "awm_pcm_push_resampled", "awm_pcm_pop", "awm_copy_to_host", "awm_is_device_pointer", "awm_speed_scan", "awm_embed_resampled", "awm_gather", "awm_pcm_bind_s16", "awm_pcm_prefetch_s16", "awm_pcm_device", "awm_embed_s16",
 ]
 
@@ -216,6 +216,17 @@ class Context:
         self._ck(self.lib.awm_sync_refine(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), ctypes.c_uint64(wav_first), ctypes.c_uint64(wav_last),
                                           ctypes.c_double(water_delta), _ptr(s), ctypes.c_size_t(len(s))))
         return s
+
+    def sync_refine_offsets(self, scores: np.ndarray, exact: bool, key_slot=0, mode=MODE_BLOCK, wav_first=0, wav_last=None, water_delta=0.01):
+        """per-offset qualities of search_refine's 65 fine offsets: sliding-DFT ranking (exact=False) or fresh transforms (exact=True)"""
+        if wav_last is None:
+            wav_last = 0xFFFFFFFFFFFFFFF
+        s = np.ascontiguousarray(scores, SEARCH_SCORE)
+        q = np.zeros((len(s), 65), np.float64)
+        valid = np.zeros((len(s), 65), np.uint8)
+        self._ck(self.lib.awm_sync_refine_offsets(self.h, ctypes.c_int(key_slot), ctypes.c_int(mode), ctypes.c_uint64(wav_first), ctypes.c_uint64(wav_last),
+                                                  ctypes.c_double(water_delta), _ptr(s), ctypes.c_size_t(len(s)), ctypes.c_int(1 if exact else 0), _ptr(q), _ptr(valid)))
+        return q, valid.astype(bool)
 
     # ---- decode
     def decode_blocks(self, indices, n_coded: int, key_slot=0):

@@ -1090,9 +1090,11 @@ awm_sync_peaks (awm_ctx *ctx, double min_abs_quality, awm_search_score *out, siz
   return 0;
 }
 
-int
-awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
-                 double water_delta, awm_search_score *scores, size_t n_scores)
+/* force: -1 = default kernel choice, 0 = sliding DFT, 1 = fresh FFT per offset.  With q_out the per-offset qualities of that
+ * kernel are written ([n_scores][65], invalid offsets flagged 0 in valid_out) and the scores are left alone. */
+static int
+refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
+             double water_delta, awm_search_score *scores, size_t n_scores, int force, double *q_out, unsigned char *valid_out)
 {
   if (key_slot < 0 || key_slot >= AWM_MAX_KEYS || mode < 0 || mode > 1 || (n_scores && !scores))
     return fail (ctx, "awm_sync_refine: bad arguments");
@@ -1130,7 +1132,7 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   /* default: sliding DFT over the 65 offsets (awm_refine_slide.cuh); AWM_REFINE=fft selects the kernel that transforms every
    * frame of every offset afresh (also used for more than two channels) */
   static const bool force_fft = [] { const char *e = getenv ("AWM_REFINE"); return e && !strcmp (e, "fft"); } ();
-  const bool used_slide = ctx->pcm_ch <= 2 && !force_fft;
+  const bool used_slide = force < 0 ? (ctx->pcm_ch <= 2 && !force_fft) : (force == 0 && ctx->pcm_ch <= 2);
   if (used_slide)
     {
       if (!ctx->tw1024.p)
@@ -1219,13 +1221,27 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
         sync_quality /= bit_count;
       return sync_quality / norm_div / 2.9;
     };
+  if (q_out)
+    {
+      for (size_t c = 0; c < nc; c++)
+        for (int o = 0; o < kOffsets; o++)
+          {
+            const bool v = o < h_noff[c] && h_valid[c * kOffsets + o];
+            valid_out[c * kOffsets + o] = v ? 1 : 0;
+            q_out[c * kOffsets + o] = v ? quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o) : 0.0;
+          }
+      return 0;
+    }
   if (used_slide)
     {
-      /* The sliding DFT ranks the 65 offsets; the best kVerify of each candidate are then scored again by k_refine (fresh FFTs, the
-       * reference's summation order: k_refine_exact_fft / _sum compute what k_refine computes), and the reference's rule picks among those exact values.  The quality peak is flat to ~1e-4
-       * relative, so rounding alone could otherwise move the arg-max by one 8-sample step; this keeps index and quality those of the
-       * exact kernel at ~6 % of its cost. */
-      constexpr int kVerify = 4;
+      /* The sliding DFT only RANKS the 65 offsets: every offset whose sliding score S lies within kVerifyMargin of the best sliding
+       * score is scored again with fresh FFTs in the reference's summation order (k_refine_exact_fft / _sum compute what k_refine
+       * computes), and the reference's rule picks among those exact values E.  If |S - E| <= d for all offsets, the exact arg-max o*
+       * satisfies S(o*) >= E(o*) - d >= E(o') - d >= S(o') - 2d for the sliding arg-max o', so with kVerifyMargin >= 2d the exact
+       * arg-max is always re-scored and index / quality are those of the exact kernel.  d is measured by
+       * tests/test_gpu_stages.py::test_refine_slide_error_bound (< kVerifyMargin / 2 on every golden candidate); neighbouring offsets
+       * of a real peak differ by ~3e-3, so usually one or two offsets are re-scored. */
+      constexpr double kVerifyMargin = 1e-3;
       std::vector<long long> p_start;
       std::vector<int> p_noff, p_cand, p_off;
       for (size_t c = 0; c < nc; c++)
@@ -1235,8 +1251,17 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
             if (h_valid[c * kOffsets + o])
               ranked.push_back ({ -fabs (quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o) - scores[c].local_mean), o });
           std::sort (ranked.begin(), ranked.end());
-          if (ranked.size() > size_t (kVerify))
-            ranked.resize (kVerify);
+          size_t keep = 0;
+          while (keep < ranked.size() && ranked[keep].first <= ranked[0].first + kVerifyMargin)
+            keep++;
+          ranked.resize (keep);
+          /* the offset of the approx index itself is always re-scored: in the reference the search starts from the approx quality,
+           * which there IS the exact value of that offset (same transforms, same order of additions); ours comes from the
+           * entry-sum formulation and differs by ~1e-5 relative, so the exact value takes its place below */
+          const int o_self = int (((long long) scores[c].index - h_start[c]) / 8);
+          if (o_self < h_noff[c] && h_valid[c * kOffsets + o_self]
+              && std::find_if (ranked.begin(), ranked.end(), [&] (const std::pair<double, int>& r) { return r.second == o_self; }) == ranked.end())
+            ranked.push_back ({ 0.0, o_self });
           std::sort (ranked.begin(), ranked.end(), [] (const std::pair<double, int>& x, const std::pair<double, int>& y) { return x.second < y.second; });
           for (const auto& r : ranked)
             {
@@ -1285,6 +1310,9 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
           best_quality[c] = scores[c].raw_quality;
           best_index[c] = scores[c].index;
         }
+      for (size_t p = 0; p < np; p++)               // starting value: the exact quality at the approx index
+        if (e_valid[p] && uint64_t (p_start[p]) == scores[p_cand[p]].index)
+          best_quality[p_cand[p]] = quality_of (e_ud.data(), e_cnt.data(), p);
       for (size_t p = 0; p < np; p++)               // per candidate in ascending offset order
         if (e_valid[p])
           {
@@ -1308,6 +1336,9 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
       awm_search_score& sc = scores[c];
       double best_quality = sc.raw_quality;
       uint64_t best_index = sc.index;
+      const int o_self = int (((long long) sc.index - h_start[c]) / 8);      // starting value: the exact quality at the approx index (see above)
+      if (o_self < h_noff[c] && h_valid[c * kOffsets + o_self])
+        best_quality = quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o_self);
       for (int o = 0; o < h_noff[c]; o++)
         if (h_valid[c * kOffsets + o])
           {
@@ -1322,6 +1353,23 @@ awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
       sc.raw_quality = best_quality;
     }
   return 0;
+}
+
+int
+awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
+                 double water_delta, awm_search_score *scores, size_t n_scores)
+{
+  return refine_impl (ctx, key_slot, mode, wav_first, wav_last, water_delta, scores, n_scores, -1, nullptr, nullptr);
+}
+
+int
+awm_sync_refine_offsets (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last, double water_delta,
+                         const awm_search_score *scores, size_t n_scores, int exact, double *quality_out, unsigned char *valid_out)
+{
+  if (!quality_out || !valid_out)
+    return fail (ctx, "awm_sync_refine_offsets: bad arguments");
+  return refine_impl (ctx, key_slot, mode, wav_first, wav_last, water_delta, const_cast<awm_search_score *> (scores), n_scores, exact ? 1 : 0,
+                      quality_out, valid_out);
 }
 
 /* ---------------------------------------------------------------- block decode */

@@ -738,6 +738,18 @@ k_viterbi (const float *__restrict__ raw, const long long *__restrict__ raw_off,
       s_mean = mean / n_coded;
     }
   __syncthreads();
+  /* digital silence: every raw soft bit is exactly 0, so mean == 0 and normalize_soft_bits (src/wmget.cc:56-61) yields 0/0 = NaN for
+   * every coded bit (raw values are finite sums of dB values, so NaN is all-or-nothing).  In conv_decode_soft (src/convcode.cc:164-190)
+   * the NaN path metrics of step 0 fail the "old_table[state].delta >= 0" reachability test of step 1: every later table keeps its
+   * initial StateEntry {0, -1, 0}, the traceback reads bit 0 / last_state 0 everywhere and error_out = -1 / n_coded. */
+  if (!hard && !(s_mean > 0))
+    {
+      for (int i = tid; i < n_msg; i += blockDim.x)
+        bits_out[(size_t) job * n_msg + i] = 0;
+      if (tid == 0)
+        err_out[job] = -1.0f / float (n_coded);
+      return;
+    }
   for (int i = tid; i < n_coded; i += blockDim.x)
     coded[i] = hard ? (rj[i] > 0 ? 1.0f : 0.0f) : float (0.5 * (double (rj[i]) / s_mean + 1));
 

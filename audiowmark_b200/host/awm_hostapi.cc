@@ -438,12 +438,46 @@ awmh_key_slot (const unsigned char *key16)
   return Engine::key_slot (make_key (key16, ""));
 }
 
+/* test aid: sync positions.  awmh_sync_trace (1) starts recording what every SyncFinder::search call returns, awmh_sync_trace_fetch
+ * copies the records out as rows of 5 doubles {search number, mode (0 BLOCK / 1 CLIP), searched frames, -1, -1} (one header row per
+ * search) and {search number, index, quality, block type (0 A / 1 B), 0} (one row per score) and clears the trace */
+int
+awmh_sync_trace (int on)
+{
+  SyncFinder::trace_enable (on != 0);
+  return 0;
+}
+
+int
+awmh_sync_trace_fetch (double *rows, size_t max_rows, size_t *n_rows)
+{
+  const auto trace = SyncFinder::trace_take();
+  size_t n = 0;
+  auto put = [&] (double a, double b, double c, double d, double e)
+    {
+      if (n < max_rows)
+        {
+          double *r = rows + 5 * n;
+          r[0] = a; r[1] = b; r[2] = c; r[3] = d; r[4] = e;
+        }
+      n++;
+    };
+  for (size_t i = 0; i < trace.size(); i++)
+    {
+      put (double (i), trace[i].mode == SyncFinder::Mode::CLIP ? 1 : 0, double (trace[i].n_frames), -1, -1);
+      for (const auto& sc : trace[i].scores)
+        put (double (i), double (sc.index), sc.quality, sc.block_type == ConvBlockType::a ? 0 : 1, 0);
+    }
+  *n_rows = n;
+  return n <= max_rows ? 0 : -2;
+}
+
 /* candidates of one chunk from its (gathered) peak list, complete above floor_q; *complete = 0 -> ask again with a lower floor */
 int
 awmh_stage_select (const awm_search_score *peaks, size_t n, double floor_q, int clip_mode, awm_search_score *out, size_t max_out, size_t *n_out, int *complete)
 {
   std::vector<awm_search_score> sel;
-  *complete = select_candidates_from_peaks (peaks, n, floor_q, Params::sync_threshold2 * 0.75, sel) ? 1 : 0;
+  *complete = select_candidates_from_peaks (peaks, n, floor_q, Params::sync_threshold2 * 0.75, sel) > 0 ? 1 : 0;
   if (clip_mode)
     {
       std::sort (sel.begin(), sel.end(), [] (const awm_search_score& a, const awm_search_score& b) { return fabs (a.raw_quality - a.local_mean) > fabs (b.raw_quality - b.local_mean); });

@@ -18,83 +18,75 @@ typedef awm_search_score SearchScore;
 inline double abs_quality (const SearchScore& s) { return fabs (s.raw_quality - s.local_mean); }
 constexpr int local_mean_distance = 20;
 
-/* select_local_maxima (src/syncfinder.cc:258-281) + sync_mask_avg_false_positives (:292-332) +
- * sync_select_threshold_and_n_best (:364-383) with the same result, restructured for a list of several
- * hundred thousand scores: one streaming pass finds the local maxima ("skip the score after a maximum" rule
- * included); only the few best peaks can survive the threshold / n-best rule, so the false-positive mask
- * (a 47-neighbour test) is evaluated lazily in descending quality order instead of for every peak. */
+/* The selection chain of SyncFinder::search in the reference's own order of operations (src/syncfinder.cc:258-281 local maxima,
+ * :292-332 false-positive mask, :364-383 threshold / n-best): build the list of maxima, filter it, sort the filtered list by
+ * descending |q - mean| with std::sort, cut.  std::sort is not stable, so which of several EQUAL scores survive a cut by count
+ * depends on the element sequence handed to it; feeding it the same sequence as the reference does (maxima in index order)
+ * reproduces the reference's choice (same libstdc++).  This matters for degenerate input only -- digital silence gives
+ * |q - mean| == 0 for every start frame -- and costs a few ms per chunk, so the lazy paths below are used whenever no tie
+ * straddles the cut. */
 void
-select_candidates (const SearchScore *sc, size_t n, double threshold, vector<SearchScore>& out)
+select_from_maxima_reference_order (const vector<SearchScore>& maxima, double threshold, vector<SearchScore>& out)
 {
+  constexpr int reach = local_mean_distance + 3;  // in list positions and in search steps
   out.clear();
-  if (!n)
-    return;
-  vector<double> aq (n);
-  for (size_t i = 0; i < n; i++)
-    aq[i] = fabs (sc[i].raw_quality - sc[i].local_mean);
-  vector<uint32_t> ppos;                          // positions of the local maxima, ascending
-  ppos.reserve (n / 3 + 16);
-  for (size_t i = 0; i < n; i++)
+  const int nm = int (maxima.size());
+  for (int i = 0; i < nm; i++)
     {
-      const double q = aq[i], q_last = i > 0 ? aq[i - 1] : 0, q_next = i + 1 < n ? aq[i + 1] : 0;
-      if (q >= q_last && q >= q_next)
+      const double qi = abs_quality (maxima[i]);
+      const bool neg_i = maxima[i].raw_quality - maxima[i].local_mean < 0;
+      bool drop = false;
+      for (int j = std::max (0, i - reach); j <= std::min (nm - 1, i + reach) && !drop; j++)
         {
-          ppos.push_back (i);
-          i++;                                    // the next score cannot be a local maximum
-        }
-    }
-  const size_t np = ppos.size();
-  constexpr int    mask_distance = local_mean_distance + 3;
-  constexpr double mask_factor   = 3;
-  auto paq = [&] (size_t k) { return aq[ppos[k]]; };
-  auto sign = [&] (size_t k) { const SearchScore& s = sc[ppos[k]]; return (s.raw_quality - s.local_mean < 0) ? -1 : 1; };
-  auto masked = [&] (int i)
-    {
-      /* a peak is dropped if a 3x stronger peak of opposite sign lies within 23 search steps (and 23 peaks) */
-      for (int d = -mask_distance; d <= mask_distance; d++)
-        {
-          const int j = i + d;
-          if (j == i || j < 0 || j >= int (np))
+          if (j == i)
             continue;
-          const int distance = std::abs (int (sc[ppos[i]].index) - int (sc[ppos[j]].index)) / Params::sync_search_step;
-          if (distance <= mask_distance && paq (j) > paq (i) * mask_factor && sign (j) != sign (i))
-            return true;
+          const int steps = std::abs (int (maxima[i].index) - int (maxima[j].index)) / Params::sync_search_step;
+          const bool neg_j = maxima[j].raw_quality - maxima[j].local_mean < 0;
+          drop = steps <= reach && neg_i != neg_j && abs_quality (maxima[j]) > qi * 3;
         }
-      return false;
-    };
-  vector<uint32_t> order (np);
-  for (size_t k = 0; k < np; k++)
-    order[k] = k;
-  size_t sorted = 0, batch = 64;
-  bool done = np == 0;
-  while (!done)
-    {
-      const size_t end = std::min (np, sorted + batch);
-      std::partial_sort (order.begin() + sorted, order.begin() + end, order.end(), [&] (uint32_t a, uint32_t b) { return paq (a) > paq (b); });
-      for (size_t k = sorted; k < end && !done; k++)
-        {
-          const uint32_t i = order[k];
-          if (paq (i) <= threshold && int (out.size()) >= Params::get_n_best)
-            done = true;                         // everything above the threshold is in, and at least n_best matches
-          else if (!masked (i))
-            out.push_back (sc[ppos[i]]);
-        }
-      sorted = end;
-      batch *= 4;
-      if (sorted == np)
-        done = true;
+      if (!drop)
+        out.push_back (maxima[i]);
     }
+  std::sort (out.begin(), out.end(), [] (const SearchScore& a, const SearchScore& b) { return abs_quality (a) > abs_quality (b); });
+  size_t above = 0;
+  while (above < out.size() && abs_quality (out[above]) > threshold)
+    above++;
+  if (int (above) >= Params::get_n_best)
+    out.resize (above);
+  else if (int (out.size()) > Params::get_n_best)
+    out.resize (Params::get_n_best);
+}
+
+/* the same from the complete score list of a chunk (sorted by index) */
+void
+select_candidates_reference_order (const SearchScore *sc, size_t n, double threshold, vector<SearchScore>& out)
+{
+  vector<SearchScore> maxima;
+  maxima.reserve (n / 2 + 1);
+  for (size_t i = 0; i < n; i++)
+    {
+      const double q = abs_quality (sc[i]);
+      const double before = i ? abs_quality (sc[i - 1]) : 0.0;
+      const double after = i + 1 < n ? abs_quality (sc[i + 1]) : 0.0;
+      if (q < before || q < after)
+        continue;
+      maxima.push_back (sc[i]);
+      i++;                                        // its right neighbour is never examined
+    }
+  select_from_maxima_reference_order (maxima, threshold, out);
 }
 
 } // namespace
 
 /* Candidate selection on a list of local maxima (sorted by index) that is complete above `floor_q`
  * (= sync_select_local_maxima + sync_mask_avg_false_positives + sync_select_threshold_and_n_best, src/syncfinder.cc:258-383).
- * Exactness: a peak can only be masked by a 3x stronger one, which is above the floor as well; peaks within 23 search
- * steps of each other are always within 23 list positions; and if the scan stops before it would need a peak at or below
- * the floor, every peak the reference would select has been seen.  Returns false if the list was not sufficient
- * (the caller lowers the floor and asks again). */
-bool
+ * Why looking at the strongest peaks only is enough: a peak can only be masked by a 3x stronger one, which is above the floor
+ * as well; peaks within 23 search steps of each other are always within 23 list positions; and if the scan stops before it
+ * would need a peak at or below the floor, every peak the reference would select has been seen.
+ * Returns 1: `out` is final.  0: the list was too short, ask again with a lower floor.  -1: peaks of EQUAL strength sit on both
+ * sides of the n-best cut, which of them the reference keeps is decided by std::sort on the full list of maxima -- ask for all
+ * maxima (floor < 0); with a complete list the reference's order of operations is followed literally. */
+int
 select_candidates_from_peaks (const awm_search_score *peaks, size_t n, double floor_q, double threshold, vector<awm_search_score>& out)
 {
   constexpr int    mask_distance = local_mean_distance + 3;
@@ -114,31 +106,51 @@ select_candidates_from_peaks (const awm_search_score *peaks, size_t n, double fl
       prev_taken = take;
       prev_index = peaks[i].index;
     }
+  if (floor_q < 0)
+    {
+      select_from_maxima_reference_order (pk, threshold, out);
+      return 1;
+    }
   const size_t np = pk.size();
   vector<uint32_t> order (np);
   for (size_t k = 0; k < np; k++)
     order[k] = k;
   std::sort (order.begin(), order.end(), [&] (uint32_t a, uint32_t b) { return abs_quality (pk[a]) > abs_quality (pk[b]); });
   auto sign = [&] (size_t k) { return (pk[k].raw_quality - pk[k].local_mean < 0) ? -1 : 1; };
+  auto masked = [&] (int i)
+    {
+      const double q = abs_quality (pk[i]);
+      bool mask = false;
+      for (int j = i - 1; j >= 0 && !mask && int (pk[i].index - pk[j].index) / Params::sync_search_step <= mask_distance; j--)
+        mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
+      for (int j = i + 1; j < int (np) && !mask && int (pk[j].index - pk[i].index) / Params::sync_search_step <= mask_distance; j++)
+        mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
+      return mask;
+    };
   out.clear();
   for (size_t k = 0; k < np; k++)
     {
       const int i = order[k];
       const double q = abs_quality (pk[i]);
       if (q <= threshold && int (out.size()) >= Params::get_n_best)
-        return true;                            // everything above the threshold is in, and at least n_best matches
+        {
+          /* cut.  By value if more than n_best peaks lie above the threshold; by count otherwise -- then the next peak that
+           * would have been taken must be strictly weaker than the last one kept */
+          if (int (out.size()) == Params::get_n_best && q == abs_quality (out.back()) && abs_quality (out.back()) <= threshold)
+            {
+              for (size_t kk = k; kk < np && abs_quality (pk[order[kk]]) == q; kk++)
+                if (!masked (order[kk]))
+                  return -1;
+            }
+          return 1;
+        }
       if (q <= floor_q)
-        return false;                           // peaks at or below the floor may be missing from the list
-      bool mask = false;
-      for (int j = i - 1; j >= 0 && !mask && int (pk[i].index - pk[j].index) / Params::sync_search_step <= mask_distance; j--)
-        mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
-      for (int j = i + 1; j < int (np) && !mask && int (pk[j].index - pk[i].index) / Params::sync_search_step <= mask_distance; j++)
-        mask = abs_quality (pk[j]) > q * mask_factor && sign (j) != sign (i);
-      if (!mask)
+        return 0;                               // peaks at or below the floor may be missing from the list
+      if (!masked (i))
         out.push_back (pk[i]);
     }
-  /* list exhausted: final if it held every peak there is, or if n_best unmasked peaks lie above the floor */
-  return floor_q < 0 || int (out.size()) >= Params::get_n_best;
+  /* list exhausted: it held only the peaks above the floor; final if n_best unmasked peaks lie above it */
+  return int (out.size()) >= Params::get_n_best ? 1 : 0;
 }
 
 namespace {
@@ -149,7 +161,7 @@ bool
 select_candidates_gpu (awm_ctx *ctx, double threshold, vector<SearchScore>& out)
 {
   static SearchScore *peaks = nullptr;
-  static const size_t max_peaks = 1 << 17;
+  static const size_t max_peaks = 1 << 18;    // a 30 minute chunk has at most 150 584 local maxima
   if (!peaks)
     peaks = static_cast<SearchScore *> (awm_host_alloc (max_peaks * sizeof (SearchScore)));
   if (!peaks)
@@ -162,10 +174,17 @@ select_candidates_gpu (awm_ctx *ctx, double threshold, vector<SearchScore>& out)
         return false;
       if (n > max_peaks)
         return false;                             // caller falls back to the full score list
-      if (select_candidates_from_peaks (peaks, n, floor_q, threshold, out))
+      const int r = select_candidates_from_peaks (peaks, n, floor_q, threshold, out);
+      if (r > 0)
         return true;
+      if (r < 0 && floor_q >= 0)                  // a tie on the cut: only the complete list of maxima decides it
+        {
+          if (awm_sync_peaks (ctx, -1.0, peaks, max_peaks, &n) || n > max_peaks)
+            return false;
+          return select_candidates_from_peaks (peaks, n, -1.0, threshold, out) > 0;
+        }
     }
-  return true;
+  return false;
 }
 
 void
@@ -204,6 +223,26 @@ select_final_scores (vector<awm_search_score>& scores, vector<SyncFinder::Score>
       const double q = s.raw_quality - s.local_mean;
       out.push_back (SyncFinder::Score { size_t (s.index), fabs (q), q > 0 ? ConvBlockType::a : ConvBlockType::b });
     }
+}
+
+namespace {
+bool sync_trace_on = false;
+vector<SyncFinder::TraceRecord> sync_trace;
+}
+
+void
+SyncFinder::trace_enable (bool on)
+{
+  sync_trace_on = on;
+  sync_trace.clear();
+}
+
+vector<SyncFinder::TraceRecord>
+SyncFinder::trace_take()
+{
+  vector<TraceRecord> t;
+  t.swap (sync_trace);
+  return t;
 }
 
 double
@@ -281,7 +320,7 @@ SyncFinder::search (const vector<Key>& key_list, size_t n_frames, int n_channels
       if (ok)
         {
           if (!gpu_selected)
-            select_candidates (all, n_all, Params::sync_threshold2 * 0.75, scores);
+            select_candidates_reference_order (all, n_all, Params::sync_threshold2 * 0.75, scores);
           if (mode == Mode::CLIP)               // ClipDecoder: at most n_best matches, but at least 5
             select_truncate_n (scores, std::max (Params::get_n_best, 5));
           t2 = get_time();
@@ -299,6 +338,13 @@ SyncFinder::search (const vector<Key>& key_list, size_t n_frames, int n_channels
         }
       select_final_scores (scores, key_result.sync_scores);
       key_results.push_back (key_result);
+    }
+  if (sync_trace_on)
+    {
+      TraceRecord rec { mode, n_frames, {} };
+      for (const auto& kr : key_results)
+        rec.scores.insert (rec.scores.end(), kr.sync_scores.begin(), kr.sync_scores.end());
+      sync_trace.push_back (rec);
     }
   return key_results;
 }

@@ -52,10 +52,16 @@ public:
   std::vector<KeyResult> search (const std::vector<Key>& key_list, size_t n_frames, int n_channels, Mode mode,
                                  size_t wav_first, size_t wav_last);
   static double normalize_sync_quality (double raw_quality);
+
+  /* test aid: when tracing is on every search() call appends what it returns (mode, length of the searched signal and per key
+   * the final scores), so that tests can compare sync positions exactly with the reference's SyncFinder::search */
+  struct TraceRecord { Mode mode; size_t n_frames; std::vector<Score> scores; };
+  static void trace_enable (bool on);
+  static std::vector<TraceRecord> trace_take();
 };
 
 /* stage functions of SyncFinder::search / BlockDecoder::run, used by get_watermark_buffer and by the frame-balanced
  * multi-GPU driver (audiowmark_b200/sharding.py), which runs the GPU stages on slices of a chunk on different ranks */
-bool select_candidates_from_peaks (const awm_search_score *peaks, size_t n, double floor_q, double threshold, std::vector<awm_search_score>& out);
+int  select_candidates_from_peaks (const awm_search_score *peaks, size_t n, double floor_q, double threshold, std::vector<awm_search_score>& out);
 void select_final_scores (std::vector<awm_search_score>& scores, std::vector<SyncFinder::Score>& out);
 

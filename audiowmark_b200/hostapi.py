@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16", "awmh_short_encode", "awmh_short_decode"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16", "awmh_short_encode", "awmh_short_decode", "awmh_sync_trace", "awmh_sync_trace_fetch"]
 
 _lib = None
 
@@ -182,6 +182,28 @@ def get(pcm, keys=None, names=None, n_frames=None, channels=None, sample_rate=44
         raise RuntimeError("awmh_get failed (rc=%d); see stderr" % rc)
     text = buf.value.decode()
     return json.loads(text) if parse else text
+
+
+def sync_trace(on=True):
+    """test aid: record what every SyncFinder::search call returns from now on (see sync_trace_fetch)"""
+    load().awmh_sync_trace(ctypes.c_int(1 if on else 0))
+
+
+def sync_trace_fetch():
+    """-> list of searches in call order: {"mode": "BLOCK"|"CLIP", "n_frames": int, "scores": [[index, quality, "A"|"B"], ...]}
+    (the format of oracle/ref_shims/sync_dump.cc's print-out as tests/golden/make_golden_large.py stores it)"""
+    cap = 1 << 16
+    rows = np.zeros((cap, 5), np.float64)
+    n = ctypes.c_size_t()
+    if load().awmh_sync_trace_fetch(_ptr(rows), ctypes.c_size_t(cap), ctypes.byref(n)):
+        raise RuntimeError("sync trace longer than %d rows" % cap)
+    out = []
+    for r in rows[:n.value]:
+        if r[3] < 0:
+            out.append({"mode": "CLIP" if r[1] else "BLOCK", "n_frames": int(r[2]), "scores": []})
+        else:
+            out[-1]["scores"].append([int(r[1]), float(r[2]), "B" if r[3] else "A"])
+    return out
 
 
 def set_short_payload(bits=0):

@@ -167,6 +167,14 @@ int awm_sync_peaks (awm_ctx *ctx, double min_abs_quality, awm_search_score *out,
 int awm_sync_refine (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last,
                      double water_delta, awm_search_score *scores, size_t n_scores);
 
+/* measurement aid for the parity tests: the sync_decode quality of each of the 65 fine offsets search_refine looks at
+ * (src/syncfinder.cc:428-434), as the sliding-DFT kernel ranks them (exact = 0) or from fresh transforms in the reference's
+ * summation order (exact = 1).  quality_out / valid_out: [n_scores][65]; offsets the reference gets no result for
+ * (sync_fft returns nothing past the end of the signal) have valid 0.  awm_sync_refine re-scores every offset whose sliding
+ * quality is within 1e-3 of the best exactly, so its result is that of the exact kernel as long as the two differ by < 5e-4. */
+int awm_sync_refine_offsets (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t wav_last, double water_delta,
+                             const awm_search_score *scores, size_t n_scores, int exact, double *quality_out, unsigned char *valid_out);
+
 /* ---- block decode: FFTAnalyzer::fft_range (src/wmcommon.cc:123-141) + mix_decode
  * (src/wmget.cc:67-108) + randomize_bit_order(decode) for blocks starting at indices[i]
  * (sample-frames of the padded signal).  raw_bits_out: [n_blocks][n_coded_bits] floats;

@@ -809,8 +809,17 @@ class SyncFinder:
             masked[i] |= cond
         return [s for s, mk in zip(scores, masked) if not mk]
 
+    @staticmethod
+    def std_sort_desc(scores):
+        """std::sort by descending abs_quality, unstable like the reference's (ties: see orc_std_sort_desc)"""
+        keys = np.array([s.abs_quality() for s in scores], dtype=np.float64)
+        perm = np.zeros(len(scores), dtype=np.int64)
+        if len(scores):
+            lib().orc_std_sort_desc(_p(keys), ctypes.c_int64(len(scores)), _p(perm))
+        return [scores[i] for i in perm]
+
     def select_threshold_and_n_best(self, scores, threshold):
-        scores = sorted(scores, key=lambda s: -s.abs_quality())
+        scores = self.std_sort_desc(scores)
         i = 0
         while i < len(scores) and scores[i].abs_quality() > threshold:
             i += 1
@@ -820,9 +829,8 @@ class SyncFinder:
             return scores[:self.P.get_n_best]
         return scores
 
-    @staticmethod
-    def select_truncate_n(scores, n):
-        return sorted(scores, key=lambda s: -s.abs_quality())[:n]
+    def select_truncate_n(self, scores, n):
+        return self.std_sort_desc(scores)[:n]
 
     # -- search_refine (syncfinder.cc:393-458)
     def search_refine(self, samples, mode, scores, sb: SyncBits, key: Key):

@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "_build", "liboracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "audiowmark")
+REF_SYNC_DUMP = os.path.join(HERE, "_ref", "sync_dump")      # SyncFinder::search print-out (ref_shims/sync_dump.cc)
 
 
 def _newer(target, sources):
@@ -34,7 +35,7 @@ def build_reference(ref="/root/reference", force=False):
     """Compile the unmodified reference sources (only possible where `ref` exists)."""
     if not os.path.isdir(os.path.join(ref, "src")):
         return REF_BIN if os.path.exists(REF_BIN) else None
-    if force or not os.path.exists(REF_BIN):
+    if force or not os.path.exists(REF_BIN) or not os.path.exists(REF_SYNC_DUMP):
         subprocess.check_call(["make", "-s", "-f", os.path.join("oracle", "Makefile.ref"), "-j8", "REF=" + ref], cwd=ROOT)
     return REF_BIN
 

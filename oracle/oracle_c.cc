@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 
 namespace {
 
@@ -358,6 +359,22 @@ orc_viterbi (const unsigned *generators, int rate, int order, const float *coded
       state = last_state[size_t (idx) * state_count + state];
     }
   return err;
+}
+
+/* std::sort as the reference's selectors call it (src/syncfinder.cc:366,388: descending |q - mean|, comparator on the value only).
+ * std::sort is not stable: with equal keys (digital silence: every quality is 0) the surviving elements depend on libstdc++'s
+ * introsort and on the input sequence, so the oracle asks the same library for the permutation.  perm[i] = input position of the
+ * element that ends up at output position i. */
+void
+orc_std_sort_desc (const double *key, int64_t n, int64_t *perm)
+{
+  struct Item { int64_t pos; double key; double pad; };     /* three words like SyncFinder::SearchScore (moves are by value either way) */
+  std::vector<Item> v (n);
+  for (int64_t i = 0; i < n; i++)
+    v[i] = Item { i, key[i], 0 };
+  std::sort (v.begin(), v.end(), [] (Item& a, Item& b) { return a.key > b.key; });
+  for (int64_t i = 0; i < n; i++)
+    perm[i] = v[i].pos;
 }
 
 /* glibc transcendental probes so tests can pin device math against the host libm */
