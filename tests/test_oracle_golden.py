@@ -213,3 +213,33 @@ def test_two_named_keys_exact_vs_reference():
     rs = O.get_watermark(O.int16_to_float(y2_16), [ka, kb], P)
     assert "\n".join(rs.lines()) + "\n" == g["get_stdout"]
     assert rs.json_doc(30) == fmt_ref_json(g["json"])
+
+
+def test_fft_shim_simd_bit_identical():
+    """oracle/ref_shims/fftw_shim.cc runs its two narrow passes with explicit AVX2 where the CPU has it (runtime dispatch); the
+    results must not depend on that: same IEEE operations per element, no FMA.  Checked through liboracle, which links the shim."""
+    import ctypes
+    L = O.lib()
+    rng = np.random.default_rng(3)
+    for n in (1024, 512, 64):
+        L.fftwf_plan_dft_r2c_1d.restype = ctypes.c_void_p
+        L.fftwf_plan_dft_c2r_1d.restype = ctypes.c_void_p
+        fwd = ctypes.c_void_p(L.fftwf_plan_dft_r2c_1d(ctypes.c_int(n), None, None, ctypes.c_uint(0)))
+        inv = ctypes.c_void_p(L.fftwf_plan_dft_c2r_1d(ctypes.c_int(n), None, None, ctypes.c_uint(0)))
+        for scale in (1.0, 1e-4):
+            x = ((rng.random(n + 2, dtype=np.float32) - 0.5) * scale).astype(np.float32)
+            res = []
+            for simd in (0, 1):
+                L.awm_shim_set_simd(ctypes.c_int(simd))
+                spec = np.zeros(n + 2, np.float32)
+                back = np.zeros(n + 2, np.float32)
+                L.fftwf_execute_dft_r2c(fwd, x.ctypes.data_as(ctypes.c_void_p), spec.ctypes.data_as(ctypes.c_void_p))
+                L.fftwf_execute_dft_c2r(inv, spec.copy().ctypes.data_as(ctypes.c_void_p), back.ctypes.data_as(ctypes.c_void_p))
+                res.append((spec.tobytes(), back.tobytes()))
+            assert res[0] == res[1]
+            ref = np.fft.rfft(x[:n].astype(np.float64))
+            got = np.frombuffer(res[1][0], np.float32).astype(np.float64)
+            assert np.abs(got[0::2] + 1j * got[1::2] - ref).max() < 2e-6 * np.abs(ref).max()
+        L.fftwf_destroy_plan(fwd)
+        L.fftwf_destroy_plan(inv)
+    L.awm_shim_set_simd(ctypes.c_int(1))
