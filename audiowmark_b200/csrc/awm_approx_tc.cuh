@@ -1,0 +1,226 @@
+// awm_approx_tc.cuh -- k_stft_mags_tc: SyncFinder::sync_fft for the four 256-sample shifts (src/syncfinder.cc:560-657) plus the
+// inner sums of sync_decode (:116-153) as ONE persistent, warp-specialised Blackwell kernel.
+//
+// What it computes is what k_stft_mags (awm_approx_mags.cuh) computes: for every frame f of a shift the channel-summed band dB
+// values dB[f][0..80], and from them, for every sync entry e (a sync frame with 30 "up" and 30 "down" bands),
+//     U_e(f) = sum_{u in up(e)} dB[f][u],   D_e(f) = sum_{d in down(e)} dB[f][d]      -> mags[shift][e][f] = (U, D)
+// The second step is the contraction  [128 frames x 96 bands] . [96 bands x 2 n_ent 0/1 columns].  On the fp32 pipes it costs
+// 30 600 shared-memory reads + adds per frame and bounded the old kernel (2/3 of its time, shared-memory bandwidth).  Here it runs
+// on the 5th generation tensor cores:
+//   * A operand = the dB tile, written by the FFT warps straight into the K-major operand layout (awm_tc.cuh) as TWO fp16 terms
+//     hi = fp16 (v), lo = fp16 (v - hi): |v| < 256, so hi + lo carries v to 2^-16 absolute -- the resolution fp32 itself has there;
+//     every product with a 0/1 mask element is exact, accumulation is fp32 in tensor memory
+//   * B operand = the 0/1 masks of 128 entries (256 columns: U and D of an entry side by side), prepared once per key on the host
+//     in operand layout and fetched chunk by chunk with the bulk-copy engine (TMA, cp.async.bulk -> mbarrier complete_tx)
+//   * D = 128 x 256 fp32 in TMEM, double buffered (2 x 256 of the 512 columns): tcgen05.mma of chunk g + 1 runs while the
+//     epilogue warps drain chunk g with tcgen05.ld and write coalesced float2 rows of `mags`
+// Warp roles (one CTA per SM, CTAs walk the (frame tile, shift) list with stride gridDim.x):
+//   warps 0 .. F-1     FFT: frame -> packed 1024-point FFT -> dB -> fp16 hi/lo into A[buf]        (a_empty -> a_full)
+//   warps F .. F+3     epilogue: TMEM -> registers -> global                                      (tmem_full -> tmem_empty)
+//   warp  F+4, lane 0  TMA + MMA issue: B chunk load, 2 x 6 tcgen05.mma, commits                  (a_full, b_full, tmem_empty -> ...)
+// All hand-offs are mbarriers; the FFT of tile i + 1 overlaps the MMAs and the epilogue of tile i.
+#pragma once
+#include "awm_kernels.cuh"
+#include "awm_tc.cuh"
+#include <cuda_fp16.h>
+
+namespace awm {
+
+constexpr int kTcTile = 128;                 // frames per tile = UMMA M
+constexpr int kTcK = 96;                     // 81 bands padded to a multiple of the UMMA K (16)
+constexpr int kTcChunkEnt = 128;             // sync entries per B chunk
+constexpr int kTcN = 2 * kTcChunkEnt;        // UMMA N: U and D column of every entry
+constexpr uint32_t kTcASplit = kTcTile * kTcK * 2;        // bytes of one fp16 term of the A tile (24 KB)
+constexpr uint32_t kTcABytes = 2 * kTcASplit;             // hi + lo
+constexpr uint32_t kTcBBytes = kTcN * kTcK * 2;           // one B chunk (48 KB)
+constexpr int kTcEpiWarps = 4;
+
+template<int FFT_WARPS, int A_BUFS> constexpr size_t
+tc_smem_bytes() { return fft_smem_bytes (FFT_WARPS) + size_t (A_BUFS) * kTcABytes + kTcBBytes + 128; }
+
+// host side: the 0/1 masks of all entries in operand layout, chunk after chunk ([ceil (n_ent / 128)][kTcBBytes])
+inline void
+tc_build_masks (const awm_sync_entry *ent, int n_ent, std::vector<unsigned char>& out)
+{
+  const int n_chunks = (n_ent + kTcChunkEnt - 1) / kTcChunkEnt;
+  out.assign (size_t (n_chunks) * kTcBBytes, 0);
+  const uint16_t one = 0x3c00;               // 1.0 in fp16
+  for (int e = 0; e < n_ent; e++)
+    {
+      unsigned char *chunk = out.data() + size_t (e / kTcChunkEnt) * kTcBBytes;
+      const int col = 2 * (e % kTcChunkEnt);
+      for (int i = 0; i < kUD; i++)
+        {
+          memcpy (chunk + tc::operand_offset (kTcN, col, ent[e].up[i]), &one, 2);
+          memcpy (chunk + tc::operand_offset (kTcN, col + 1, ent[e].down[i]), &one, 2);
+        }
+    }
+}
+
+template<int FFT_WARPS, int A_BUFS> __global__ void __launch_bounds__ ((FFT_WARPS + kTcEpiWarps + 1) * 32, 1)
+k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_out, int ld,
+                const unsigned char *__restrict__ masks /* [n_chunks][kTcBBytes] */, int n_ent, int n_chunks,
+                float2 *__restrict__ mags /* [4][n_ent][ld] */, unsigned char *__restrict__ have,
+                long long wav_first, long long wav_last, const float2 *g_tw, const float *g_win)
+{
+  using namespace tc;
+  extern __shared__ __align__ (16) unsigned char smem[];
+  FftSmem s = fft_smem_setup (smem, g_tw, g_win, FFT_WARPS);
+  unsigned char *abuf = reinterpret_cast<unsigned char *> (s.extra);
+  unsigned char *bbuf = abuf + size_t (A_BUFS) * kTcABytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *> (bbuf + kTcBBytes);
+  uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_free = bars + 5, *tmem_full = bars + 6, *tmem_empty = bars + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *> (bars + 10);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int kEpi0 = FFT_WARPS, kMmaWarp = FFT_WARPS + kTcEpiWarps;
+
+  if (threadIdx.x == 0)
+    {
+      for (int i = 0; i < 2; i++)
+        {
+          mbar_init (&a_full[i], FFT_WARPS);
+          mbar_init (&a_empty[i], 1);
+          mbar_init (&tmem_full[i], 1);
+          mbar_init (&tmem_empty[i], kTcEpiWarps);
+        }
+      mbar_init (b_full, 1);
+      mbar_init (b_free, 1);
+      fence_mbar_init();
+    }
+  if (w == kMmaWarp)
+    tmem_alloc (tmem_slot, 512);
+  // band columns 81 .. 95 of A are never written again and must be finite: clear everything once
+  for (uint32_t i = threadIdx.x; i < A_BUFS * kTcABytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *> (abuf)[i] = make_uint4 (0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int n_tiles = 4 * ((n_out + kTcTile - 1) / kTcTile);
+
+  if (w < FFT_WARPS)
+    {
+      // ===================================================================================== FFT warps
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++)
+        {
+          const int shift_idx = t & 3, f0 = (t >> 2) * kTcTile;
+          const int a = it % A_BUFS, use = it / A_BUFS;
+          mbar_wait (&a_empty[a], (use & 1) ^ 1);                 // the MMAs that read this buffer last time are done
+          unsigned char *A = abuf + size_t (a) * kTcABytes;
+          for (int r = w; r < kTcTile; r += FFT_WARPS)
+            {
+              const int f = f0 + r;
+              const long long start = (long long) shift_idx * 256 + (long long) f * kFrame;
+              bool ok = f < n_out;
+              if (ok)
+                {
+                  const long long f_first = start * C, f_last = (start + kFrame) * C;
+                  if (f_last < wav_first || f_first > wav_last)   // frame in leading / trailing digital silence
+                    ok = false;
+                }
+              float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+              if (ok)
+                frame_db_sum (pcm, n_frames, C, start, s, lane, acc);
+#pragma unroll
+              for (int k2 = 0; k2 < 4; k2++)
+                {
+                  const int band = lane + 32 * k2 - kMinBand;
+                  if (band >= 0 && band < kBands)
+                    {
+                      const __half hi = __float2half_rn (acc[k2]);
+                      const __half lo = __float2half_rn (acc[k2] - __half2float (hi));
+                      const uint32_t o = operand_offset (kTcTile, r, band);
+                      *reinterpret_cast<__half *> (A + o) = hi;
+                      *reinterpret_cast<__half *> (A + kTcASplit + o) = lo;
+                    }
+                }
+              if (lane == 0 && f < n_out)
+                have[(size_t) shift_idx * ld + f] = ok ? 1 : 0;
+            }
+          fence_proxy_async();                                    // st.shared above -> visible to tcgen05.mma (async proxy)
+          __syncwarp();
+          if (lane == 0)
+            mbar_arrive (&a_full[a]);
+        }
+    }
+  else if (w < kMmaWarp)
+    {
+      // ===================================================================================== epilogue warps
+      const int q = w - kEpi0;                                    // == w % 4 (FFT_WARPS is a multiple of 4): TMEM lanes 32 q .. 32 q + 31
+      int g = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        {
+          const int shift_idx = t & 3, f0 = (t >> 2) * kTcTile;
+          const int f = f0 + q * 32 + lane;                       // frame of this thread's TMEM lane; f < ld always (ld multiple of 128)
+          for (int c = 0; c < n_chunks; c++, g++)
+            {
+              const int tb = g & 1;
+              mbar_wait (&tmem_full[tb], (g >> 1) & 1);
+              tc_fence_after_sync();
+              const uint32_t taddr = tmem + (uint32_t (q * 32) << 16) + uint32_t (tb * kTcN);
+#pragma unroll 1
+              for (int c0 = 0; c0 < kTcN; c0 += 32)
+                {
+                  uint32_t r[32];
+                  tmem_ld_32x32 (taddr + c0, r);
+                  tmem_ld_wait();
+                  const int e0 = c * kTcChunkEnt + c0 / 2;
+#pragma unroll
+                  for (int p = 0; p < 16; p++)
+                    if (e0 + p < n_ent)                           // warp uniform
+                      mags[((size_t) shift_idx * n_ent + e0 + p) * ld + f] = make_float2 (__uint_as_float (r[2 * p]), __uint_as_float (r[2 * p + 1]));
+                }
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0)
+                mbar_arrive (&tmem_empty[tb]);
+            }
+        }
+    }
+  else if (lane == 0)
+    {
+      // ===================================================================================== TMA + MMA issue (one thread)
+      constexpr uint32_t idesc = idesc_f16_f32 (kTcTile, kTcN);
+      const uint32_t b_addr = smem_u32 (bbuf);
+      int it = 0, g = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++)
+        {
+          const int a = it % A_BUFS, use = it / A_BUFS;
+          const uint32_t a_addr = smem_u32 (abuf + size_t (a) * kTcABytes);
+          for (int c = 0; c < n_chunks; c++, g++)
+            {
+              if (g > 0)
+                mbar_wait (b_free, (g - 1) & 1);                  // the MMAs of the previous chunk have read the B buffer
+              mbar_arrive_expect_tx (b_full, kTcBBytes);
+              bulk_load (bbuf, masks + size_t (c) * kTcBBytes, kTcBBytes, b_full);
+              if (c == 0)
+                mbar_wait (&a_full[a], use & 1);                  // all FFT warps have delivered their rows of the tile
+              mbar_wait (b_full, g & 1);
+              const int tb = g & 1;
+              mbar_wait (&tmem_empty[tb], ((g >> 1) & 1) ^ 1);    // the epilogue has drained this accumulator
+              tc_fence_after_sync();
+#pragma unroll
+              for (int sp = 0; sp < 2; sp++)
+#pragma unroll
+                for (int j = 0; j < kTcK / 16; j++)
+                  mma_f16 (tmem + uint32_t (tb * kTcN),
+                           smem_desc_kmajor (a_addr + sp * kTcASplit + j * 2 * (kTcTile * 16), kTcTile * 16, 128),
+                           smem_desc_kmajor (b_addr + j * 2 * (kTcN * 16), kTcN * 16, 128), idesc, (sp | j) != 0);
+              mma_commit (b_free);
+              mma_commit (&tmem_full[tb]);
+            }
+          mma_commit (&a_empty[a]);
+        }
+    }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (w == kMmaWarp)
+    {
+      tc_fence_after_sync();
+      tmem_dealloc (tmem, 512);
+    }
+}
+
+} // namespace awm

@@ -7,6 +7,9 @@
 #include "awm_speed.cuh"
 #include "awm_refine_slide.cuh"
 #include "awm_approx_mags.cuh"
+#include <vector>
+#include <string.h>
+#include "awm_approx_tc.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -57,6 +60,8 @@ struct DevBuf
 struct SyncTab
 {
   DevBuf ent, off, sorted, groups;
+  DevBuf masks;                       // 0/1 band masks of the entries as tcgen05 B operand chunks (awm_approx_tc.cuh)
+  int n_chunks = 0;
   int n_groups = 0;
   int n_ent = 0, n_bits = 0, total_frames = 0;
   std::vector<awm_sync_entry> h_ent;
@@ -79,6 +84,7 @@ struct awm_ctx
   cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of the pipelined host paths
   std::string err;
   uint64_t launches = 0;
+  int n_sms = 0;
   bool profiling = false;
   struct ProfRec { const char *name; cudaEvent_t e0, e1; double bytes; };
   std::vector<ProfRec> prof;
@@ -528,6 +534,14 @@ awm_set_sync_tables (awm_ctx *ctx, int key_slot, int mode, const awm_sync_entry 
   CK (cudaMemcpyAsync (t.sorted.p, sorted.data(), sorted.size() * sizeof (ApproxEntry), cudaMemcpyHostToDevice, ctx->stream));
   CK (cudaMemcpyAsync (t.groups.p, group_end.data(), group_end.size() * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
+  {
+    std::vector<unsigned char> masks;
+    tc_build_masks (entries, n_entries, masks);
+    CK (t.masks.reserve (masks.size()));
+    CK (cudaMemcpyAsync (t.masks.p, masks.data(), masks.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK (cudaStreamSynchronize (ctx->stream));
+    t.n_chunks = int (masks.size() / kTcBBytes);
+  }
   t.n_groups = int (group_end.size());
   t.n_ent = n_entries;
   t.n_bits = n_bits;
@@ -978,6 +992,39 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   if (!force_ring && t.n_ent <= kGatherMaxEntries)
     {
       CK (ctx->a_mags.reserve (size_t (4) * t.n_ent * ld * sizeof (float2)));
+      /* entry sums on the tensor cores (k_stft_mags_tc); AWM_APPROX=simt keeps them on the fp32 pipes (k_stft_mags), AWM_TC=12x1
+       * selects the variant with twelve FFT warps and a single A buffer */
+      const char *env_approx = getenv ("AWM_APPROX"), *env_tc = getenv ("AWM_TC");       // read per call: tests compare the variants in one process
+      const bool force_simt = env_approx && !strcmp (env_approx, "simt");
+      const bool tc_12x1 = env_tc && !strcmp (env_tc, "12x1");
+      if (!force_simt)
+        {
+          if (!ctx->n_sms)
+            CK (cudaDeviceGetAttribute (&ctx->n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+          const int n_tiles = 4 * int ((n_out + kTcTile - 1) / kTcTile);
+          const unsigned grid = unsigned (std::min (n_tiles, ctx->n_sms));
+          if (tc_12x1)
+            {
+              const size_t smem = tc_smem_bytes<12, 1>();
+              if (set_smem (ctx, k_stft_mags_tc<12, 1>, smem)) return 1;
+              PROF (ctx);
+              k_stft_mags_tc<12, 1><<<grid, (12 + kTcEpiWarps + 1) * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
+                t.masks.as<unsigned char>(), t.n_ent, t.n_chunks, ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(),
+                (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>());
+            }
+          else
+            {
+              const size_t smem = tc_smem_bytes<8, 2>();
+              if (set_smem (ctx, k_stft_mags_tc<8, 2>, smem)) return 1;
+              PROF (ctx);
+              k_stft_mags_tc<8, 2><<<grid, (8 + kTcEpiWarps + 1) * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
+                t.masks.as<unsigned char>(), t.n_ent, t.n_chunks, ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(),
+                (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>());
+            }
+          LAUNCH_CHECK ("k_stft_mags_tc");
+          prof_bytes (ctx, double (ctx->pcm_frames) * ctx->pcm_ch * sizeof (float) + double (4) * t.n_ent * n_out * sizeof (float2));   /* PCM in, entry sums out */
+        }
+      else
       {
         const size_t smem = kMagSmem2;
         if (set_smem (ctx, k_stft_mags, smem)) return 1;

@@ -101,6 +101,25 @@ def test_sync_approx_vs_oracle(ctx, marked):
     assert best["index"] == 256000 and best["raw_quality"] > 1.0
 
 
+def test_tensor_core_entry_sums_match_fp32_pipes(ctx, marked, monkeypatch):
+    """k_stft_mags_tc (tcgen05.mma on fp16 hi/lo terms of the dB values, fp32 accumulation in TMEM, masks by TMA) against k_stft_mags
+    (the same sums on the fp32 pipes): the two differ only by the rounding of the additions -- far below the 2e-4 bar against the
+    oracle that test_sync_approx_vs_oracle holds the default path to.  Both tile variants of the kernel are run."""
+    _, y = marked
+    ctx.pcm_bind(y)
+    monkeypatch.setenv("AWM_APPROX", "simt")
+    simt = ctx.sync_approx(0, capi.MODE_BLOCK)
+    monkeypatch.delenv("AWM_APPROX")
+    for variant in ("8x2", "12x1"):
+        monkeypatch.setenv("AWM_TC", variant)
+        tc = ctx.sync_approx(0, capi.MODE_BLOCK)
+        assert np.array_equal(tc["index"], simt["index"])
+        d = np.abs(tc["raw_quality"] - simt["raw_quality"]).max()
+        assert d < 2e-5, (variant, d)
+        assert np.abs(tc["local_mean"] - simt["local_mean"]).max() < 2e-5
+    monkeypatch.delenv("AWM_TC")
+
+
 def test_sync_refine_vs_oracle(ctx, marked):
     _, y = marked
     ctx.pcm_bind(y)
