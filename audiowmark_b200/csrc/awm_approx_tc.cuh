@@ -15,7 +15,8 @@
 //   * D = 128 x 256 fp32 in TMEM, double buffered (2 x 256 of the 512 columns): tcgen05.mma of chunk g + 1 runs while the
 //     epilogue warps drain chunk g with tcgen05.ld and write coalesced float2 rows of `mags`
 // Warp roles (one CTA per SM, CTAs walk the (frame tile, shift) list with stride gridDim.x):
-//   warps 0 .. F-1     FFT: frame -> packed 1024-point FFT -> dB -> fp16 hi/lo into A[buf]        (a_empty -> a_full)
+//   warps 0 .. F-1     FFT: frame (PCM prefetched by TMA into the warp's transpose buffer) -> packed 1024-point FFT -> dB ->
+//                      fp16 hi/lo into A[buf]                                                     (a_empty -> a_full)
 //   warps F .. F+3     epilogue: TMEM -> registers -> global                                      (tmem_full -> tmem_empty)
 //   warp  F+4, lane 0  TMA + MMA issue: B chunk load, 2 x 6 tcgen05.mma, commits                  (a_full, b_full, tmem_empty -> ...)
 // All hand-offs are mbarriers; the FFT of tile i + 1 overlaps the MMAs and the epilogue of tile i.
@@ -36,7 +37,7 @@ constexpr uint32_t kTcBBytes = kTcN * kTcK * 2;           // one B chunk (48 KB)
 constexpr int kTcEpiWarps = 4;
 
 template<int FFT_WARPS, int A_BUFS> constexpr size_t
-tc_smem_bytes() { return fft_smem_bytes (FFT_WARPS) + size_t (A_BUFS) * kTcABytes + kTcBBytes + 128; }
+tc_smem_bytes() { return fft_smem_bytes (FFT_WARPS) + size_t (A_BUFS) * kTcABytes + kTcBBytes + 256; }
 
 // host side: the 0/1 masks of all entries in operand layout, chunk after chunk ([ceil (n_ent / 128)][kTcBBytes])
 inline void
@@ -61,7 +62,7 @@ template<int FFT_WARPS, int A_BUFS> __global__ void __launch_bounds__ ((FFT_WARP
 k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_out, int ld,
                 const unsigned char *__restrict__ masks /* [n_chunks][kTcBBytes] */, int n_ent, int n_chunks,
                 float2 *__restrict__ mags /* [4][n_ent][ld] */, unsigned char *__restrict__ have,
-                long long wav_first, long long wav_last, const float2 *g_tw, const float *g_win)
+                long long wav_first, long long wav_last, const float2 *g_tw, const float *g_win, int tma_ok /* stereo, pcm 16-byte aligned */)
 {
   using namespace tc;
   extern __shared__ __align__ (16) unsigned char smem[];
@@ -70,7 +71,8 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
   unsigned char *bbuf = abuf + size_t (A_BUFS) * kTcABytes;
   uint64_t *bars = reinterpret_cast<uint64_t *> (bbuf + kTcBBytes);
   uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_free = bars + 5, *tmem_full = bars + 6, *tmem_empty = bars + 8;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *> (bars + 10);
+  uint64_t *pcm_bars = bars + 10;                                  // one per FFT warp: its next frame has landed in its transpose buffer
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *> (pcm_bars + FFT_WARPS);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   constexpr int kEpi0 = FFT_WARPS, kMmaWarp = FFT_WARPS + kTcEpiWarps;
 
@@ -85,6 +87,8 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
         }
       mbar_init (b_full, 1);
       mbar_init (b_free, 1);
+      for (int i = 0; i < FFT_WARPS; i++)
+        mbar_init (&pcm_bars[i], 1);
       fence_mbar_init();
     }
   if (w == kMmaWarp)
@@ -102,27 +106,93 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
   if (w < FFT_WARPS)
     {
       // ===================================================================================== FFT warps
-      int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++)
+      // The PCM of a frame reaches the warp through the bulk-copy engine: while the second butterfly pass of frame i runs, the
+      // 8 KB of frame i + 1 (1024 stereo sample-frames, contiguous and 16-byte aligned in the interleaved stream) land in the
+      // warp's transpose buffer, which is idle from that point on; the next iteration finds them in shared memory (mbarrier
+      // complete_tx) instead of waiting ~1 us for 32 global loads per lane.  Frames the copy cannot serve -- mono / multichannel
+      // audio, the ragged end of the stream, an unaligned caller buffer -- take the global-load path of frame_db_sum.
+      uint64_t *pcm_bar = pcm_bars + w;
+      uint32_t pcm_phase = 0;
+      struct Frame { int t, r; };
+      auto frame_start = [&] (Frame fr) { return (long long) (fr.t & 3) * 256 + (long long) ((fr.t >> 2) * kTcTile + fr.r) * kFrame; };
+      auto exists = [&] (Frame fr) { return fr.t < n_tiles; };
+      auto wanted = [&] (Frame fr)          // sync_fft computes this frame: inside the output range and not in leading / trailing digital silence
         {
-          const int shift_idx = t & 3, f0 = (t >> 2) * kTcTile;
+          const long long start = frame_start (fr);
+          const long long f_first = start * C, f_last = (start + kFrame) * C;
+          return (fr.t >> 2) * kTcTile + fr.r < n_out && !(f_last < wav_first || f_first > wav_last);
+        };
+      auto by_tma = [&] (Frame fr) { return tma_ok && exists (fr) && wanted (fr) && frame_start (fr) + kFrame <= n_frames; };
+      auto next_of = [&] (Frame fr)
+        {
+          fr.r += FFT_WARPS;
+          if (fr.r >= kTcTile)
+            {
+              fr.r = w;
+              fr.t += gridDim.x;
+            }
+          return fr;
+        };
+      auto prefetch = [&] (Frame fr)        // caller: after __syncwarp, every lane is done with the transpose buffer
+        {
+          if (lane == 0)
+            {
+              fence_proxy_async();          // the lanes' generic-proxy accesses to xbuf are ordered before the engine's writes
+              mbar_arrive_expect_tx (pcm_bar, kFrame * 2 * sizeof (float));
+              bulk_load (s.xbuf, pcm + frame_start (fr) * 2, kFrame * 2 * sizeof (float), pcm_bar);
+            }
+        };
+      Frame cur { int (blockIdx.x), w };
+      if (by_tma (cur))
+        prefetch (cur);
+      int it = 0;
+      for (; exists (cur); it++)
+        {
+          const int shift_idx = cur.t & 3, f0 = (cur.t >> 2) * kTcTile;
           const int a = it % A_BUFS, use = it / A_BUFS;
           mbar_wait (&a_empty[a], (use & 1) ^ 1);                 // the MMAs that read this buffer last time are done
           unsigned char *A = abuf + size_t (a) * kTcABytes;
-          for (int r = w; r < kTcTile; r += FFT_WARPS)
+          const int t_now = cur.t;
+          for (; cur.t == t_now; )
             {
-              const int f = f0 + r;
-              const long long start = (long long) shift_idx * 256 + (long long) f * kFrame;
-              bool ok = f < n_out;
-              if (ok)
-                {
-                  const long long f_first = start * C, f_last = (start + kFrame) * C;
-                  if (f_last < wav_first || f_first > wav_last)   // frame in leading / trailing digital silence
-                    ok = false;
-                }
+              const int r = cur.r, f = f0 + r;
+              const Frame nxt = next_of (cur);
+              const bool ok = wanted (cur), nxt_tma = by_tma (nxt);
               float acc[4] = { 0.f, 0.f, 0.f, 0.f };
-              if (ok)
-                frame_db_sum (pcm, n_frames, C, start, s, lane, acc);
+              if (by_tma (cur))
+                {
+                  float re[32], im[32];
+                  mbar_wait (pcm_bar, pcm_phase);
+                  pcm_phase ^= 1;
+                  const float2 *xp = reinterpret_cast<const float2 *> (s.xbuf) + lane;
+#pragma unroll
+                  for (int j = 0; j < 32; j++)
+                    {
+                      const float2 v = xp[32 * j];
+                      const float wn = s.win[32 * j + lane];
+                      re[j] = v.x * wn;
+                      im[j] = v.y * wn;
+                    }
+                  __syncwarp();                                   // all lanes hold their samples before the transposes reuse the buffer
+                  fft1024_warp (re, im, s.tw, s.xbuf, lane, [&] { if (nxt_tma) prefetch (nxt); });
+                  float ar, ai, br, bi;
+                  unpack_pair<0> (re, im, lane, ar, ai, br, bi);
+                  acc[0] = db_from_complex (ar, ai, -96.f) + db_from_complex (br, bi, -96.f);
+                  unpack_pair<1> (re, im, lane, ar, ai, br, bi);
+                  acc[1] = db_from_complex (ar, ai, -96.f) + db_from_complex (br, bi, -96.f);
+                  unpack_pair<2> (re, im, lane, ar, ai, br, bi);
+                  acc[2] = db_from_complex (ar, ai, -96.f) + db_from_complex (br, bi, -96.f);
+                  unpack_pair<3> (re, im, lane, ar, ai, br, bi);
+                  acc[3] = db_from_complex (ar, ai, -96.f) + db_from_complex (br, bi, -96.f);
+                }
+              else
+                {
+                  if (ok)
+                    frame_db_sum (pcm, n_frames, C, frame_start (cur), s, lane, acc);
+                  __syncwarp();
+                  if (nxt_tma)
+                    prefetch (nxt);
+                }
 #pragma unroll
               for (int k2 = 0; k2 < 4; k2++)
                 {
@@ -138,6 +208,7 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
                 }
               if (lane == 0 && f < n_out)
                 have[(size_t) shift_idx * ld + f] = ok ? 1 : 0;
+              cur = nxt;
             }
           fence_proxy_async();                                    // st.shared above -> visible to tcgen05.mma (async proxy)
           __syncwarp();
@@ -157,7 +228,7 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
           for (int c = 0; c < n_chunks; c++, g++)
             {
               const int tb = g & 1;
-              mbar_wait (&tmem_full[tb], (g >> 1) & 1);
+              mbar_wait_relaxed (&tmem_full[tb], (g >> 1) & 1);
               tc_fence_after_sync();
               const uint32_t taddr = tmem + (uint32_t (q * 32) << 16) + uint32_t (tb * kTcN);
 #pragma unroll 1
@@ -192,14 +263,14 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
           for (int c = 0; c < n_chunks; c++, g++)
             {
               if (g > 0)
-                mbar_wait (b_free, (g - 1) & 1);                  // the MMAs of the previous chunk have read the B buffer
+                mbar_wait_relaxed (b_free, (g - 1) & 1, 64);                  // the MMAs of the previous chunk have read the B buffer
               mbar_arrive_expect_tx (b_full, kTcBBytes);
               bulk_load (bbuf, masks + size_t (c) * kTcBBytes, kTcBBytes, b_full);
               if (c == 0)
-                mbar_wait (&a_full[a], use & 1);                  // all FFT warps have delivered their rows of the tile
-              mbar_wait (b_full, g & 1);
+                mbar_wait_relaxed (&a_full[a], use & 1);                // all FFT warps have delivered their rows of the tile
+              mbar_wait_relaxed (b_full, g & 1, 64);
               const int tb = g & 1;
-              mbar_wait (&tmem_empty[tb], ((g >> 1) & 1) ^ 1);    // the epilogue has drained this accumulator
+              mbar_wait_relaxed (&tmem_empty[tb], ((g >> 1) & 1) ^ 1, 64);    // the epilogue has drained this accumulator
               tc_fence_after_sync();
 #pragma unroll
               for (int sp = 0; sp < 2; sp++)

@@ -1003,6 +1003,8 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
             CK (cudaDeviceGetAttribute (&ctx->n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
           const int n_tiles = 4 * int ((n_out + kTcTile - 1) / kTcTile);
           const unsigned grid = unsigned (std::min (n_tiles, ctx->n_sms));
+          const char *env_tma = getenv ("AWM_TC_PCM");                      // AWM_TC_PCM=ldg: frames by global loads instead of bulk copies
+          const int tma_ok = ctx->pcm_ch == 2 && (reinterpret_cast<uintptr_t> (ctx->pcm) & 15) == 0 && !(env_tma && !strcmp (env_tma, "ldg"));
           if (tc_12x1)
             {
               const size_t smem = tc_smem_bytes<12, 1>();
@@ -1010,7 +1012,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
               PROF (ctx);
               k_stft_mags_tc<12, 1><<<grid, (12 + kTcEpiWarps + 1) * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
                 t.masks.as<unsigned char>(), t.n_ent, t.n_chunks, ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(),
-                (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>());
+                (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>(), tma_ok);
             }
           else
             {
@@ -1019,7 +1021,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
               PROF (ctx);
               k_stft_mags_tc<8, 2><<<grid, (8 + kTcEpiWarps + 1) * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
                 t.masks.as<unsigned char>(), t.n_ent, t.n_chunks, ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(),
-                (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>());
+                (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>(), tma_ok);
             }
           LAUNCH_CHECK ("k_stft_mags_tc");
           prof_bytes (ctx, double (ctx->pcm_frames) * ctx->pcm_ch * sizeof (float) + double (4) * t.n_ent * n_out * sizeof (float2));   /* PCM in, entry sums out */

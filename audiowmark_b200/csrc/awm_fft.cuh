@@ -95,8 +95,10 @@ constexpr int kWarpFftSmemFloats = 2 * 32 * 33;     // 32 x 33 float2, row strid
 //   out: re[i], im[i] = Z[lane + 32*brev5(i)]
 //   tw : shared copy of exp(-2 pi i k1 t / 1024) at [k1*32 + t]
 //   xbuf: this warp's transpose buffer (kWarpFftSmemFloats floats)
-__device__ __forceinline__ void
-fft1024_warp (float (&re)[32], float (&im)[32], const float2 *tw, float *xbuf, int lane)
+// `after_transpose` runs once the warp has read everything back from its transpose buffer, i.e. from the moment xbuf is free
+// again: k_stft_mags_tc starts the bulk copy of the warp's next frame into it there, under the second pass of butterflies.
+template<class Hook> __device__ __forceinline__ void
+fft1024_warp (float (&re)[32], float (&im)[32], const float2 *tw, float *xbuf, int lane, Hook after_transpose)
 {
   fft32_dif (re, im);
   float2 *xb = reinterpret_cast<float2 *> (xbuf);        // [32][33] complex, row stride 33: 64-bit accesses stay conflict free
@@ -116,7 +118,14 @@ fft1024_warp (float (&re)[32], float (&im)[32], const float2 *tw, float *xbuf, i
       im[t] = v.y;
     }
   __syncwarp();
+  after_transpose();
   fft32_dif (re, im);
+}
+
+__device__ __forceinline__ void
+fft1024_warp (float (&re)[32], float (&im)[32], const float2 *tw, float *xbuf, int lane)
+{
+  fft1024_warp (re, im, tw, xbuf, lane, [] {});
 }
 
 // Split the packed spectrum Z = FFT (a + i b) into the spectra of the two real inputs for

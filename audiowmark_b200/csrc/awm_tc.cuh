@@ -42,6 +42,21 @@ __device__ __forceinline__ void mbar_wait (uint64_t *bar, uint32_t parity)
     }
   while (!done);
 }
+// the same for warps whose wake-up latency does not matter (they wait for work that takes microseconds): a failed poll is
+// followed by nanosleep, so the waiting warp leaves the issue slots of its scheduler to the warps that compute
+__device__ __forceinline__ void mbar_wait_relaxed (uint64_t *bar, uint32_t parity, uint32_t sleep_ns = 256)
+{
+  const uint32_t addr = smem_u32 (bar);
+  for (;;)
+    {
+      uint32_t done;
+      asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+      if (done)
+        break;
+      asm volatile ("nanosleep.u32 %0;" :: "r"(sleep_ns));
+    }
+}
 // make generic-proxy writes to shared memory (st.shared) visible to the async proxy (tcgen05.mma / bulk copies read through it)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
 
