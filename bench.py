@@ -16,7 +16,9 @@ e2e    : the same call with pinned HOST buffers holding 16 bit PCM (the sample f
 e2e_f32: the same with fp32 host buffers (twice the PCIe bytes)
 roofline / kernels : per-kernel CUDA-event times of the timed steps (awm_profile_*)
 cpu_baseline       : the reference's own CPU implementation (oracle/_ref/audiowmark, unmodified
-                     sources, FFT = in-repo shim) on a bounded sample, rank 0 at N=1 only
+                     sources, FFT = in-repo shim with AVX2 passes) on the same 60 min workload, rank 0 at N=1 only
+add / get          : the two halves of a step timed separately (north_star's target is on `get`)
+cli_e2e            : `bin/audiowmark add` + `cmp` as processes on a tmpfs WAV: process start, CUDA context creation, file I/O included
 
 python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--minutes M]
 """
@@ -126,23 +128,81 @@ def run_reference(steps, warmup, minutes):
     t_add = sum(t[0] for t in times) / len(times)
     t_get = sum(t[1] for t in times) / len(times)
     return {"value": n / (t_add + t_get), "t_add_s": t_add, "t_get_s": t_get, "n_frames": n, "payload_ok": ok,
-            "cores": os.cpu_count(), "sample": "%g min stereo 44.1 kHz s16 WAV on tmpfs: `audiowmark add` (1 thread) + `audiowmark cmp` (all threads), wall time incl. file I/O" % minutes}
+            "add_value": n / t_add, "get_value": n / t_get, "fft": fft_shim_vs_pocketfft(),
+            "cores": os.cpu_count(), "sample": "%g min stereo 44.1 kHz s16 WAV on tmpfs: `audiowmark add` (1 thread) + `audiowmark cmp` (all threads), wall time incl. process start and file I/O" % minutes}
+
+
+def fft_shim_vs_pocketfft():
+    """The reference build's FFT is the in-repo shim (FFTW is not installed).  To quantify how far that is from a tuned library:
+    microseconds per 1024-point real transform, one thread, shim vs scipy's pocketfft (C++, SIMD)."""
+    try:
+        import ctypes
+        import numpy as np
+        import scipy.fft
+        import awm_oracle as O
+        L = O.lib()
+        L.orc_fft_r2c_us.restype = ctypes.c_double
+        L.orc_fft_r2c_us(ctypes.c_int(2000))
+        t_shim = L.orc_fft_r2c_us(ctypes.c_int(100000))
+        xs = (np.random.default_rng(0).random((4096, 1024), dtype=np.float32) - 0.5).astype(np.float32)
+        scipy.fft.rfft(xs, axis=1)
+        t0 = time.perf_counter()
+        for rep in range(5):
+            scipy.fft.rfft(xs, axis=1)
+        t_pf = (time.perf_counter() - t0) / (5 * len(xs)) * 1e6
+        return {"shim_us_per_r2c_1024": round(t_shim, 3), "pocketfft_us_per_r2c_1024": round(t_pf, 3)}
+    except Exception as e:
+        return {"error": str(e)}
+
+
+def run_cli_e2e(minutes):
+    """`audiowmark add` + `audiowmark cmp` of THIS repo as separate processes on a tmpfs WAV: what a user of the CLI sees, with process
+    start, CUDA context creation, WAV parsing and file I/O inside the time (the reference arm pays the same minus CUDA)."""
+    import numpy as np
+    import awm_oracle as O
+    from audiowmark_b200 import hostapi as H
+    n = int(minutes * 60 * RATE)
+    tmp = tempfile.mkdtemp(prefix="awm_cli_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    src, dst = os.path.join(tmp, "in.wav"), os.path.join(tmp, "wm.wav")
+    try:
+        rng = np.random.default_rng(1)
+        O.write_wav16(src, (rng.random((n, 2), dtype=np.float32) - 0.5).astype(np.float32))
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            subprocess.run([H.CLI_PATH, "-q", "add", src, dst, PAYLOAD], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            t1 = time.perf_counter()
+            p = subprocess.run([H.CLI_PATH, "-q", "cmp", dst, PAYLOAD], capture_output=True, text=True)
+            t2 = time.perf_counter()
+            if best is None or t2 - t0 < best[0] + best[1]:
+                best = (t1 - t0, t2 - t1, p.returncode == 0)
+        return {"value": n / (best[0] + best[1]), "unit": "PCM frames/s", "t_add_s": round(best[0], 3), "t_get_s": round(best[1], 3), "payload_ok": best[2],
+                "what": "bin/audiowmark add + cmp, %g min stereo s16 WAV on tmpfs, best of 2, incl. process start, CUDA context creation and file I/O" % minutes}
+    finally:
+        for f in (src, dst):
+            try:
+                os.remove(f)
+            except OSError:
+                pass
+        os.rmdir(tmp)
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    minutes = args.minutes if args.minutes else 10.0
+    minutes = args.minutes if args.minutes else 60.0
     r = run_reference(args.steps, args.warmup, minutes)
     line = {
         "impl": "reference", "metric": "audio frames/sec embed+detect, 44.1 kHz stereo; decoded-bit match vs ref", "value": r["value"],
         "unit": "PCM frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (r["t_add_s"] + r["t_get_s"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "payload_ok": r["payload_ok"],
-        "config": {"workload": "1 h stereo 44.1 kHz embed+detect (reference CPU path timed on a %g min sample of it)" % minutes,
-                   "sample_frames": r["n_frames"]},
-        "cpu_baseline": {"value": r["value"], "unit": "PCM frames/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+        "config": {"workload": "%g min stereo 44.1 kHz embed+detect per GPU (BASELINE.json configs[1]%s)" % (minutes, "" if minutes == 60 else ", shortened"),
+                   "pcm_frames_per_gpu": r["n_frames"], "channels": 2, "payload_bits": 128, "get_chunks": "30 min, 134.4 s overlap"},
+        "add": {"value": r["add_value"], "unit": "PCM frames/s", "s_per_step": r["t_add_s"], "threads": 1},
+        "get": {"value": r["get_value"], "unit": "PCM frames/s", "s_per_step": r["t_get_s"], "threads": r["cores"]},
+        "cpu_baseline": {"value": r["value"], "unit": "PCM frames/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"], "fft": r["fft"]},
         "e2e": {"value": r["value"], "unit": "PCM frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -150,18 +210,6 @@ def main_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-
-# algorithmic HBM bytes per launch of each kernel, per stereo PCM frame of its input
-def algo_bytes(kernel, n_frames, ch, prof):
-    per_frame = {
-        "k_embed": 8.0 * ch,                         # read 4C + write 4C
-        "k_limiter": 8.0 * ch,                       # read + write in place
-        "k_stft_db": 4.0 * ch + 4 * 81 * 4 / 1024.0,  # read the chunk once, write the four band-major dB matrices
-        "k_sync_approx": 4 * 81 * 4 / 1024.0 + 4 * 8 / 1024.0,   # read the dB matrices once, write one double per candidate
-        "k_local_mean": 4 * (8 + 24) / 1024.0,
-    }
-    return per_frame.get(kernel, 0.0) * n_frames
-
 
 def main_gpu(args):
     import numpy as np
@@ -313,6 +361,19 @@ def main_gpu(args):
     ms_e2e16, _, doc3, _, _ = timed(step_e2e_s16, args.steps, False)
     ok3, _ = check(doc3)
     ok2 = ok2 and ok3
+    # the two halves of a step on their own (north_star's >= 100x target is on `get`); single GPU only
+    halves = None
+    if world == 1:
+        def sync_after(fn):
+            def run():
+                fn()
+                H.synchronize()
+            return run
+        ms_add, _, _, _, _ = timed(sync_after(lambda: H.add(x_dev.data_ptr(), PAYLOAD, None, y_dev.data_ptr(), n, ch)), args.steps, False)
+        ms_get, _, _, _, _ = timed(lambda: H.get(y_dev.data_ptr(), n_frames=n, channels=ch), args.steps, False)
+        ms_add16, _, _, _, _ = timed(sync_after(lambda: H.add_s16(x16_host.numpy(), PAYLOAD, None, y16_host.numpy())), args.steps, False)
+        ms_get16, _, _, _, _ = timed(lambda: H.get_s16(y16_host.numpy()), args.steps, False)
+        halves = {"add_ms": ms_add / args.steps, "get_ms": ms_get / args.steps, "add_e2e_ms": ms_add16 / args.steps, "get_e2e_ms": ms_get16 / args.steps}
     if world == 1 and len(clocks.rows) < 8:         # very short runs: keep the load up until a few samples exist (single process only: the sharded step is collective)
         t_end = time.time() + 1.0
         while time.time() < t_end and len(clocks.rows) < 8:
@@ -338,45 +399,95 @@ def main_gpu(args):
     value = total_frames / (ms_step / 1e3)
     e2e_value = total_frames / (ms_e2e / args.steps / 1e3)
     e2e16_value = total_frames / (ms_e2e16 / args.steps / 1e3)
-    # per-kernel picture and the roofline of the dominant kernel
+    # per-kernel picture and the roofline of the dominant kernel.
+    # Algorithmic bytes follow SURVEY.md section 8(d): embed reads and writes every sample once (16 B per stereo PCM frame);
+    # detect reads every chunk sample once (8 B) and writes + reads the four 81-band dB matrices (2 * 4 * 81 * 4 B per 1024 frames
+    # = 2.53 B per frame): 10.53 B per frame of chunked input, 1.0747 x the stream length at 1 h.  Everything else a kernel moves
+    # (the entry-sum matrix this implementation puts between spectrogram and search, refine / decode windows) is NOT algorithmic;
+    # it shows up in `achieved_incl_intermediates` and in the measured DRAM traffic instead.
     peaks = measured_peaks()
     peak_gbs = (peaks or {}).get("hbm_gbs", 6650.0)
-    n_chunk_frames = n * 1.0747 if minutes >= 59 else n         # chunk overlap of `get`
+    overlap = 1.0747 if minutes >= 59 else 1.0                   # chunk overlap of `get`
+    n_chunk_frames = n * overlap
+    db_rw = 2 * 4 * 81 * 4 / 1024.0                              # 2.53 B / frame: dB matrices written once, read once
+    survey_bytes = {                                             # per step and GPU
+        "k_embed": 4.0 * ch * 2 * n,
+        "k_stft_mags_tc": (4.0 * ch + db_rw / 2) * n_chunk_frames,   # PCM once + the dB matrices once
+        "k_stft_mags": (4.0 * ch + db_rw / 2) * n_chunk_frames,
+        "k_sync_gather": (db_rw / 2) * n_chunk_frames,               # the dB matrices read back
+    }
+    builder_bytes = {                                            # what the kernels of this implementation have to move
+        "k_stft_mags_tc": (4.0 * ch + 4 * 510 * 8 / 1024.0) * n_chunk_frames,    # PCM once + entry sums (U, D) of 510 entries, 4 shifts
+        "k_stft_mags": (4.0 * ch + 4 * 510 * 8 / 1024.0) * n_chunk_frames,
+        "k_sync_gather": (4 * 510 * 8 / 1024.0) * n_chunk_frames,
+        "k_embed": 4.0 * ch * 2 * n,
+    }
+    # dram__bytes_read.sum + dram__bytes_write.sum per PCM frame of kernel input, ncu --set full on a 10 min launch (profiles/r2_ncu_*.md)
+    dram_per_frame = {"k_stft_mags_tc": (213.49e6 + 364.98e6) / 26.46e6, "k_embed": (213.32e6 + 170.57e6) / 26.46e6}
     kernels = {}
     for name, r in (prof or {}).items():
         per_launch_ms = r["ms"] / max(r["launches"], 1)
-        fr = n_chunk_frames if name in ("k_stft_db", "k_sync_approx", "k_local_mean") else n
-        ab_total = r.get("algo_bytes") or algo_bytes(name, fr, ch, prof) * args.steps     # run-time sized kernels report their own volume
+        sb = survey_bytes.get(name, 0.0) * args.steps
+        bb = (r.get("algo_bytes") or builder_bytes.get(name, 0.0) * args.steps)
+        if name == "k_limiter":
+            bb = 0.0                                             # CTAs whose blocks stay below the ceiling return at once: no meaningful byte count
         kernels[name] = {"launches": r["launches"], "ms_total": round(r["ms"], 4), "ms_per_launch": round(per_launch_ms, 5),
                          "share_of_step": round(r["ms"] / ms, 4),
-                         "algo_GBps": round(ab_total / (r["ms"] / 1e3) / 1e9, 2) if ab_total else None}
+                         "algo_GBps": round(sb / (r["ms"] / 1e3) / 1e9, 2) if sb else None,
+                         "moved_GBps": round(bb / (r["ms"] / 1e3) / 1e9, 2) if bb else None}
     dominant = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
     roofline = None
     if dominant:
-        a = kernels[dominant]["algo_GBps"] or 0.0
-        # ncu --set full on the 10 min workload (profiles/r1_ncu_full_v4_all_kernels_10min.md): what each kernel actually runs into
-        limiter = {"k_stft_mags": "shared-memory bandwidth of the per-entry band sums (143.5 M LSU wavefronts per 10 min launch, short-scoreboard stalls) on top of the FFT's fp32 issue (49 % issue slots busy)",
-                   "k_refine_slide": "fp32 issue rate (62 % issue slots busy); the PCM window is re-read from L2",
+        k = kernels[dominant]
+        a = k["algo_GBps"] or 0.0
+        limiter = {"k_stft_mags_tc": "fp32 issue rate of the FFT warps (8 of the 13 warps; ~1900 warp instructions per 1024-point stereo transform); the tensor-core contraction, the TMA copies and the epilogue stores run underneath",
+                   "k_refine_slide": "fp32 issue rate; the PCM window is re-read from L2",
                    "k_sync_gather": "HBM: one streaming pass over the entry-sum matrix",
-                   "k_embed": "latency: 16 warps / SM (128 registers, 165 KB shared memory), 43 % issue slots busy",
-                   "k_viterbi": "serial dependency of 143 trellis steps, one CTA per code word"}
-        dram_traffic = {"k_stft_mags": 577.6e6, "k_refine_slide": 64.5e6, "k_sync_gather": 394.8e6, "k_embed": 387.4e6}      # dram read + write, bytes per launch
-        gather = kernels.get("k_sync_gather", {}).get("algo_GBps")
+                   "k_embed": "fp32 issue rate / latency of two FFTs per frame",
+                   "k_viterbi": "serial dependency of 143 trellis steps"}
+        launches_per_step = k["launches"] / args.steps
+        traffic = dram_per_frame.get(dominant)
+        if traffic is not None:
+            traffic = traffic * (n_chunk_frames if dominant != "k_embed" else n) / launches_per_step
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": a, "peak": peak_gbs, "unit": "GB/s", "frac": round(a / peak_gbs, 5),
-                    "traffic": dram_traffic.get(dominant),
-                    "traffic_note": "dram__bytes_read+write per launch of the 10 min ncu capture (a 30 min chunk launch moves 3x as much)",
+                    "traffic": traffic,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (10 min launch), scaled to this kernel's average launch of the step",
+                    "achieved_incl_intermediates": k["moved_GBps"],
                     "actual_limiter": limiter.get(dominant),
-                    "hbm_bound_kernel": {"kernel": "k_sync_gather", "achieved": gather, "frac": round((gather or 0.0) / peak_gbs, 4)},
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                    "note": "algorithmic bytes per launch / CUDA-event launch time; see DESIGN.md section 5 for the per-kernel byte model"}
+                    "byte_model": "SURVEY.md 8(d): algorithmic bytes per launch / CUDA-event launch time",
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+        # the whole path against the same roofline: 16 B / frame for embed + 10.53 B / frame of chunked input for detect
+        path_bytes = 16.0 * n + 10.53 * n_chunk_frames
+        roofline["path"] = {"algorithmic_bytes_per_step": path_bytes, "achieved": round(path_bytes / (ms_step / 1e3) / 1e9, 2),
+                            "frac": round(path_bytes / (ms_step / 1e3) / 1e9 / peak_gbs, 5)}
+        if "k_embed" in kernels:
+            roofline["embed_kernel"] = {"achieved": kernels["k_embed"]["algo_GBps"], "frac": round((kernels["k_embed"]["algo_GBps"] or 0.0) / peak_gbs, 4)}
+        if "k_sync_gather" in kernels:
+            roofline["hbm_bound_kernel"] = {"kernel": "k_sync_gather", "moved_GBps": kernels["k_sync_gather"]["moved_GBps"],
+                                            "frac_of_peak_moved": round((kernels["k_sync_gather"]["moved_GBps"] or 0.0) / peak_gbs, 4)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = run_reference(1, 0, 10.0)
+            r = run_reference(1, 0, minutes)
             cpu = {"value": r["value"], "unit": "PCM frames/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"],
-                   "t_add_s": round(r["t_add_s"], 3), "t_get_s": round(r["t_get_s"], 3), "payload_ok": r["payload_ok"]}
+                   "t_add_s": round(r["t_add_s"], 3), "t_get_s": round(r["t_get_s"], 3), "add_value": r["add_value"], "get_value": r["get_value"],
+                   "payload_ok": r["payload_ok"], "fft": r["fft"]}
         except Exception as e:          # the bench line must still print
             cpu = {"value": None, "unit": "PCM frames/s", "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: %s" % e}
+    cli = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cli = run_cli_e2e(minutes)
+        except Exception as e:
+            cli = {"error": str(e)}
+    add_get = None
+    if halves:
+        add_get = {"add": {"value": n / (halves["add_ms"] / 1e3), "ms_per_step": halves["add_ms"], "e2e_value": n / (halves["add_e2e_ms"] / 1e3), "e2e_ms_per_step": halves["add_e2e_ms"]},
+                   "get": {"value": n / (halves["get_ms"] / 1e3), "ms_per_step": halves["get_ms"], "e2e_value": n / (halves["get_e2e_ms"] / 1e3), "e2e_ms_per_step": halves["get_e2e_ms"]},
+                   "unit": "PCM frames/s"}
+        if cpu and cpu.get("value"):
+            add_get["add"]["e2e_vs_cpu_reference"] = round(add_get["add"]["e2e_value"] / cpu["add_value"], 1)
+            add_get["get"]["e2e_vs_cpu_reference"] = round(add_get["get"]["e2e_value"] / cpu["get_value"], 1)
     line = {
         "metric": "audio frames/sec embed+detect, 44.1 kHz stereo; decoded-bit match vs ref",
         "value": value, "unit": "PCM frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -399,6 +510,8 @@ def main_gpu(args):
                     "h2d_bytes_per_step": 2 * n_loc * ch * 4, "d2h_bytes_per_step": n_loc * ch * 4,
                     "api": "hostapi.add + hostapi.get (C++ add_watermark_buffer / get_watermark_buffer) on pinned fp32 host buffers"},
         "gpu_launches": launches,
+        "add_get": add_get,
+        "cli_e2e": cli,
         "roofline": roofline,
         "kernels": kernels,
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
@@ -416,7 +529,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--minutes", type=float, default=0.0, help="audio length per GPU (default 60 = BASELINE configs[1]; reference arm: 10)")
+    ap.add_argument("--minutes", type=float, default=0.0, help="audio length per GPU (default 60 = BASELINE configs[1], both arms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

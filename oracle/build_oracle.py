@@ -26,7 +26,7 @@ def build_liboracle(force=False):
     if force or _newer(LIB, srcs + [os.path.join(HERE, "ref_shims", "fftw3.h"), os.path.join(HERE, "ref_shims", "awm_vresampler.hh")]):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         # plain x86-64 baseline, no fast-math: every float op rounds like the reference build
-        cmd = ["g++", "-O2", "-std=c++14", "-fopenmp", "-shared", "-fPIC", "-I", HERE, "-o", LIB] + srcs
+        cmd = ["g++", "-O3", "-std=c++14", "-fopenmp", "-shared", "-fPIC", "-I", HERE, "-o", LIB] + srcs
         subprocess.check_call(cmd)
     return LIB
 

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <vector>
 #include <algorithm>
 
@@ -375,6 +376,33 @@ orc_std_sort_desc (const double *key, int64_t n, int64_t *perm)
   std::sort (v.begin(), v.end(), [] (Item& a, Item& b) { return a.key > b.key; });
   for (int64_t i = 0; i < n; i++)
     perm[i] = v[i].pos;
+}
+
+/* microseconds per 1024-point r2c transform of the FFT shim, one thread (bench.py reports it next to pocketfft's, so that the
+ * distance between the reference build's FFT and a tuned library is on record) */
+double
+orc_fft_r2c_us (int reps)
+{
+  const int N = 1024;
+  float *in = (float *) fftwf_malloc (sizeof (float) * (N + 2));
+  fftwf_complex *out = (fftwf_complex *) fftwf_malloc (sizeof (float) * (N + 2));
+  for (int i = 0; i < N; i++)
+    in[i] = float ((i * 7919) % 1000) / 1000.f - 0.5f;
+  fftwf_plan p = fftwf_plan_dft_r2c_1d (N, in, out, 0);
+  struct timespec a, b;
+  volatile float sink = 0;
+  clock_gettime (CLOCK_MONOTONIC, &a);
+  for (int r = 0; r < reps; r++)
+    {
+      fftwf_execute_dft_r2c (p, in, out);
+      sink += out[5][0];
+      in[3] += 1e-9f;
+    }
+  clock_gettime (CLOCK_MONOTONIC, &b);
+  fftwf_destroy_plan (p);
+  fftwf_free (in);
+  fftwf_free (out);
+  return ((b.tv_sec - a.tv_sec) * 1e9 + (b.tv_nsec - a.tv_nsec)) / reps / 1e3;
 }
 
 /* glibc transcendental probes so tests can pin device math against the host libm */
