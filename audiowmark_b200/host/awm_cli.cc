@@ -1,17 +1,22 @@
 // awm_cli.cc -- the `audiowmark` command line of the B200 build.
-// Same argv grammar, messages and exit codes as the reference CLI (src/audiowmark.cc:47-88,540-1079)
-// for: add, get, cmp, gen-key and the test helpers the reference's tests/*.sh use (test-gen-noise,
-// cut-start, test-snr, test-info, test-clip, test-subtract, gentest).  Not available here: hls-*,
-// MP3/FLAC and other libsndfile formats.
-#include <fcntl.h>
-#include <math.h>
+//
+// Drop-in for the reference CLI (src/audiowmark.cc): same argv grammar, same messages, same exit codes for add, get, cmp, gen-key
+// and the helper commands the reference's tests/*.sh call.  The implementation is table driven:
+//   * kOptions  one row per option: spelling, arity, the commands that accept it and a small handler that stores the value
+//   * kCommands one row per command: the option groups it accepts, its key policy, the names of its positional arguments and the
+//               function that runs it
+// A command line is processed by ONE generic routine: options are taken out of the token list row by row (table order, so that
+// e.g. --format still overrides --input-format wherever it stands), every handler validates its own value, what is left must be
+// exactly the positional arguments.  Not available here: hls-*, MP3 / FLAC and other libsndfile formats.
+#include <errno.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <sys/stat.h>
-#include <unistd.h>
-#include <errno.h>
 
+#include <algorithm>
+#include <functional>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -20,756 +25,455 @@
 #include "awm_engine.hh"
 #include "awm_tables.hh"
 #include "awm_util.hh"
+#include "awm_cli_tools.hh"
 
 using std::string;
 using std::vector;
 
 #define AWM_VERSION "0.6.5-b200"
 
-static void
-print_usage()
-{
-  printf ("usage: audiowmark <command> [ <args>... ]\n");
-  printf ("\n");
-  printf ("Commands:\n");
-  printf ("  * create a watermarked wav file with a message\n");
-  printf ("    audiowmark add <input_wav> <watermarked_wav> <message_hex>\n");
-  printf ("\n");
-  printf ("  * retrieve message\n");
-  printf ("    audiowmark get <watermarked_wav>\n");
-  printf ("\n");
-  printf ("  * compare watermark message with expected message\n");
-  printf ("    audiowmark cmp <watermarked_wav> <message_hex>\n");
-  printf ("\n");
-  printf ("  * generate 128-bit watermarking key, to be used with --key option\n");
-  printf ("    audiowmark gen-key <key_file> [ --name <key_name> ]\n");
-  printf ("\n");
-  printf ("Global options:\n");
-  printf ("  -q, --quiet             disable information messages\n");
-  printf ("  --strict                treat (minor) problems as errors\n");
-  printf ("  --gpu-device <n>        CUDA device to run on                [0]\n");
-  printf ("\n");
-  printf ("Options for get / cmp:\n");
-  printf ("  --detect-speed          detect and correct replay speed difference\n");
-  printf ("  --detect-speed-patient  slower, more accurate speed detection\n");
-  printf ("  --json <file>           write JSON results into file\n");
-  printf ("\n");
-  printf ("Options for add / get / cmp:\n");
-  printf ("  --key <file>            load watermarking key from file\n");
-  printf ("  --short <bits>          enable short payload mode\n");
-  printf ("  --strength <s>          set watermark strength              [%.6g]\n", Params::water_delta * 1000);
-  printf ("\n");
-  printf ("  --input-format raw      use raw stream as input\n");
-  printf ("  --output-format raw     use raw stream as output\n");
-  printf ("  --format raw            use raw stream as input and output\n");
-  printf ("\n");
-  printf ("The options to set the raw stream parameters (such as --raw-rate\n");
-  printf ("or --raw-channels) follow the reference audiowmark README.\n");
-}
+namespace {
 
-static int
-atoi_or_die (const char *s)
+[[noreturn]] void
+die (const char *fmt, ...)
 {
-  char *end;
-  errno = 0;
-  const long l = strtol (s, &end, 10);
-  if (errno || *end || !*s)
-    {
-      error ("audiowmark: error during string->int conversion: %s\n", s);
-      exit (1);
-    }
-  return l;
-}
-
-static float
-atof_or_die (const char *s)
-{
-  char *end;
-  errno = 0;
-  const float d = strtof (s, &end);          /* single precision like the reference (src/audiowmark.cc:188-199) */
-  if (errno || *end || !*s)
-    {
-      error ("audiowmark: error during string->float conversion: %s\n", s);
-      exit (1);
-    }
-  return d;
-}
-
-static bool
-is_option (const string& arg)
-{
-  return arg.size() > 1 && arg[0] == '-';     // a single "-" means stdin / stdout
-}
-
-class ArgParser
-{
-  vector<string> m_args;
-  string         m_command;
-public:
-  ArgParser (int argc, char **argv) : m_args (argv + 1, argv + argc) {}
-  bool
-  parse_cmd (const string& cmd)
-  {
-    if (m_args.empty() || m_args[0] != cmd)
-      return false;
-    m_args.erase (m_args.begin());
-    m_command = cmd;
-    return true;
-  }
-  vector<string>
-  parse_multi_opt (const string& option)       // --option value  or  --option=value, any number of times
-  {
-    vector<string> values, rest;
-    for (size_t i = 0; i < m_args.size(); i++)
-      {
-        if (m_args[i] == option && i + 1 < m_args.size())
-          values.push_back (m_args[++i]);
-        else if (m_args[i].compare (0, option.size() + 1, option + "=") == 0)
-          values.push_back (m_args[i].substr (option.size() + 1));
-        else
-          rest.push_back (m_args[i]);
-      }
-    m_args = rest;
-    return values;
-  }
-  bool
-  parse_opt (const string& option, string& out)
-  {
-    const vector<string> v = parse_multi_opt (option);
-    if (v.empty())
-      return false;
-    out = v.back();
-    return true;
-  }
-  bool parse_opt (const string& option, int& out)   { string s; if (!parse_opt (option, s)) return false; out = atoi_or_die (s.c_str()); return true; }
-  bool parse_opt (const string& option, float& out) { string s; if (!parse_opt (option, s)) return false; out = atof_or_die (s.c_str()); return true; }
-  bool
-  parse_opt (const string& option)
-  {
-    for (auto it = m_args.begin(); it != m_args.end(); it++)
-      if (*it == option)
-        {
-          m_args.erase (it);
-          return true;
-        }
-    return false;
-  }
-  bool
-  parse_args (size_t expected, vector<string>& out)
-  {
-    if (m_args.size() != expected)
-      return false;
-    for (const auto& a : m_args)
-      if (is_option (a))
-        return false;
-    out = m_args;
-    return true;
-  }
-  const vector<string>& remaining_args() const { return m_args; }
-  const string&         command() const        { return m_command; }
-};
-
-static Format
-parse_format (const string& s)
-{
-  if (s == "raw") return Format::RAW;
-  if (s == "auto") return Format::AUTO;
-  if (s == "rf64") return Format::RF64;
-  if (s == "wav-pipe") return Format::WAV_PIPE;
-  error ("audiowmark: unsupported format '%s'\n", s.c_str());
+  va_list ap;
+  va_start (ap, fmt);
+  char buf[1024];
+  vsnprintf (buf, sizeof (buf), fmt, ap);
+  va_end (ap);
+  error ("%s", buf);
   exit (1);
 }
 
-static RawFormat::Endian
-parse_endian (const string& s)
+/* Numbers: what the reference accepts (src/audiowmark.cc:175-199) -- strtol with base 0 (so 0x10 and 010 work) / strtof, the
+ * whole token must be consumed, an empty token counts as 0, overflow is not diagnosed. */
+template<class T, class Convert> T
+number_or_die (const string& s, const char *type_name, Convert convert)
 {
-  if (s == "little") return RawFormat::LITTLE;
-  if (s == "big") return RawFormat::BIG;
-  error ("audiowmark: unsupported endianness '%s'\n", s.c_str());
-  exit (1);
+  char *end = nullptr;
+  const T v = T (convert (s.c_str(), &end));
+  if (end && *end)
+    die ("audiowmark: error during string->%s conversion: %s\n", type_name, s.c_str());
+  return v;
 }
 
-static void
-parse_encoding (const string& s, RawFormat& fmt)
+int   to_int (const string& s)   { return number_or_die<int> (s, "int", [] (const char *p, char **e) { return strtol (p, e, 0); }); }
+float to_float (const string& s) { return number_or_die<float> (s, "float", [] (const char *p, char **e) { return strtof (p, e); }); }
+
+bool looks_like_option (const string& t) { return t.size() > 1 && t[0] == '-'; }     // a lone "-" is stdin / stdout
+
+/* ------------------------------------------------------------------------------------------------ value vocabularies */
+
+template<class T> struct Word { const char *text; T value; };
+
+template<class T, size_t N> T
+lookup (const Word<T> (&words)[N], const string& s, const char *what)
 {
-  if (s == "signed") fmt.set_encoding (Encoding::SIGNED);
-  else if (s == "unsigned") fmt.set_encoding (Encoding::UNSIGNED);
-  else if (s == "float") fmt.set_encoding (Encoding::FLOAT);
-  else if (s == "double")
-    {
-      fmt.set_encoding (Encoding::FLOAT);
-      fmt.set_bit_depth (64);
-    }
-  else
-    {
-      error ("audiowmark: unsupported encoding '%s'\n", s.c_str());
-      exit (1);
-    }
-  if (s == "float")
-    fmt.set_bit_depth (32);
+  for (const auto& w : words)
+    if (s == w.text)
+      return w.value;
+  die ("audiowmark: unsupported %s '%s'\n", what, s.c_str());
 }
 
-static void
-update_raw_bits (RawFormat& fmt, int bits)
+const Word<Format> kFormats[] = { { "raw", Format::RAW }, { "auto", Format::AUTO }, { "rf64", Format::RF64 }, { "wav-pipe", Format::WAV_PIPE } };
+const Word<RawFormat::Endian> kEndians[] = { { "little", RawFormat::LITTLE }, { "big", RawFormat::BIG } };
+struct EncodingChoice { Encoding enc; int forced_bits; };      // float / double carry their width
+const Word<EncodingChoice> kEncodings[] = { { "signed", { Encoding::SIGNED, 0 } }, { "unsigned", { Encoding::UNSIGNED, 0 } },
+                                            { "float", { Encoding::FLOAT, 32 } }, { "double", { Encoding::FLOAT, 64 } } };
+
+enum Side { IN = 1, OUT = 2, BOTH = 3 };
+
+template<class F> void
+each_raw (int side, F f)
+{
+  if (side & IN)  f (Params::raw_input_format);
+  if (side & OUT) f (Params::raw_output_format);
+}
+
+void
+set_encoding (RawFormat& fmt, const string& s)
+{
+  const EncodingChoice c = lookup (kEncodings, s, "encoding");
+  fmt.set_encoding (c.enc);
+  if (c.forced_bits)
+    fmt.set_bit_depth (c.forced_bits);
+}
+
+void
+set_bits (RawFormat& fmt, int bits)
 {
   if (fmt.encoding() == Encoding::FLOAT)
-    return;                                   // float / double fix the width themselves
-  if (bits != 8 && bits != 16 && bits != 24 && bits != 32)
-    {
-      error ("audiowmark: unsupported bit depth %d (use 8, 16, 24 or 32)\n", bits);
-      exit (1);
-    }
-  fmt.set_bit_depth (bits);
+    die ("audiowmark: bit depth can not be changed for float / double encoding\n");
+  fmt.set_bit_depth (bits);                   // widths the raw converter has no code for are reported when the stream is opened
 }
 
-static void
-parse_shared_options (ArgParser& ap)
-{
-  int i;
-  if (ap.parse_opt ("--short", i))
-    {
-      Params::payload_size = i;
-      if (!short_code_init (Params::payload_size))
-        {
-          error ("audiowmark: unsupported short payload size %zd\n", Params::payload_size);
-          exit (1);
-        }
-      Params::payload_short = true;
-    }
-  ap.parse_opt ("--frames-per-bit", Params::frames_per_bit);
-  if (ap.parse_opt ("--linear"))
-    Params::mix = false;
-}
+/* ------------------------------------------------------------------------------------------------ option table */
 
-static vector<Key>
-parse_key_list (ArgParser& ap)
+enum Group : unsigned
 {
-  vector<Key> key_list;
-  for (const auto& f : ap.parse_multi_opt ("--key"))
+  G_SHARED = 1,      // payload / code options every watermark command takes
+  G_ADD    = 2,
+  G_GET    = 4,      // get and cmp
+  G_CMP    = 8,
+  G_KEYS   = 16,     // --key / --test-key
+  G_NAME   = 32,     // gen-key
+  G_BITS   = 64,     // test-gen-noise
+};
+
+enum Arity { FLAG, VALUE, REPEATED, CHECK };
+
+struct Session                     // what option handlers collect besides Params
+{
+  vector<Key> keys;
+  int         speed_option_count = 0;
+  string      key_name;
+  int         noise_bits = 16;
+};
+
+struct Option
+{
+  const char *name;                // spelling; for CHECK rows a comment
+  Arity       arity;
+  unsigned    groups;
+  std::function<void (const vector<string>&, Session&)> apply;     // FLAG: empty vector; VALUE: one element (the last given); REPEATED: all
+};
+
+void
+load_key_file (const vector<string>& files, Session& s)
+{
+  for (const auto& f : files)
     {
       Key key;
       key.load_key (f);
-      key_list.push_back (key);
+      s.keys.push_back (key);
     }
-  for (const auto& t : ap.parse_multi_opt ("--test-key"))
+}
+
+void
+add_test_keys (const vector<string>& seeds, Session& s)
+{
+  for (const auto& t : seeds)
     {
       Key key;
-      key.set_test_key (atoi_or_die (t.c_str()));
-      key_list.push_back (key);
+      key.set_test_key (to_int (t));
+      s.keys.push_back (key);
     }
-  if (key_list.empty())
-    key_list.push_back (Key());               // zero key
-  return key_list;
 }
 
-static Key
-parse_key (ArgParser& ap)
-{
-  auto key_list = parse_key_list (ap);
-  if (key_list.size() > 1)
-    {
-      error ("audiowmark %s: watermark key can at most be set once (--key / --test-key option)\n", ap.command().c_str());
-      exit (1);
-    }
-  return key_list[0];
-}
+#define V(expr) [] (const vector<string>& v, Session& s) { (void) v; (void) s; expr; }
 
-static void
-parse_add_options (ArgParser& ap)
-{
-  string s;
-  int i;
-  float f;
-  ap.parse_opt ("--set-input-label", Params::input_label);
-  ap.parse_opt ("--set-output-label", Params::output_label);
-  if (ap.parse_opt ("--snr"))
-    Params::snr = true;
-  if (ap.parse_opt ("--input-format", s))  Params::input_format = parse_format (s);
-  if (ap.parse_opt ("--output-format", s)) Params::output_format = parse_format (s);
-  if (ap.parse_opt ("--format", s))        Params::input_format = Params::output_format = parse_format (s);
-  if (ap.parse_opt ("--raw-input-endian", s))  Params::raw_input_format.set_endian (parse_endian (s));
-  if (ap.parse_opt ("--raw-output-endian", s)) Params::raw_output_format.set_endian (parse_endian (s));
-  if (ap.parse_opt ("--raw-endian", s))
-    {
-      Params::raw_input_format.set_endian (parse_endian (s));
-      Params::raw_output_format.set_endian (parse_endian (s));
-    }
-  if (ap.parse_opt ("--raw-input-encoding", s))  parse_encoding (s, Params::raw_input_format);
-  if (ap.parse_opt ("--raw-output-encoding", s)) parse_encoding (s, Params::raw_output_format);
-  if (ap.parse_opt ("--raw-encoding", s))
-    {
-      parse_encoding (s, Params::raw_input_format);
-      parse_encoding (s, Params::raw_output_format);
-    }
-  if (ap.parse_opt ("--raw-input-bits", i))  update_raw_bits (Params::raw_input_format, i);
-  if (ap.parse_opt ("--raw-output-bits", i)) update_raw_bits (Params::raw_output_format, i);
-  if (ap.parse_opt ("--raw-bits", i))
-    {
-      update_raw_bits (Params::raw_input_format, i);
-      update_raw_bits (Params::raw_output_format, i);
-    }
-  if (ap.parse_opt ("--raw-channels", i))
-    {
-      Params::raw_input_format.set_channels (i);
-      Params::raw_output_format.set_channels (i);
-    }
-  if (ap.parse_opt ("--raw-rate", i))
-    {
-      Params::raw_input_format.set_sample_rate (i);
-      Params::raw_output_format.set_sample_rate (i);
-    }
-  if (ap.parse_opt ("--test-no-limiter"))
-    Params::test_no_limiter = true;
-  if (Params::input_format == Format::RF64)
-    {
-      error ("audiowmark: using rf64 as input format has no effect\n");
-      exit (1);
-    }
-  if (ap.parse_opt ("--strength", f))
-    Params::water_delta = f / 1000;
-}
+const Option kOptions[] = {
+  /* ---- payload / code */
+  { "--short", VALUE, G_SHARED, V (
+      Params::payload_size = to_int (v[0]);
+      if (!short_code_init (Params::payload_size))
+        die ("audiowmark: unsupported short payload size %zd\n", Params::payload_size);
+      Params::payload_short = true) },
+  { "--frames-per-bit", VALUE, G_SHARED, V (Params::frames_per_bit = to_int (v[0])) },
+  { "--linear", FLAG, G_SHARED, V (Params::mix = false) },
 
-static void
-parse_get_options (ArgParser& ap)
+  /* ---- add */
+  { "--set-input-label", VALUE, G_ADD, V (Params::input_label = v[0]) },
+  { "--set-output-label", VALUE, G_ADD, V (Params::output_label = v[0]) },
+  { "--snr", FLAG, G_ADD, V (Params::snr = true) },
+  { "--input-format", VALUE, G_ADD, V (Params::input_format = lookup (kFormats, v[0], "format")) },
+  { "--output-format", VALUE, G_ADD, V (Params::output_format = lookup (kFormats, v[0], "format")) },
+  { "--format", VALUE, G_ADD, V (Params::input_format = Params::output_format = lookup (kFormats, v[0], "format")) },
+  { "--raw-input-endian", VALUE, G_ADD, V (Params::raw_input_format.set_endian (lookup (kEndians, v[0], "endianness"))) },
+  { "--raw-output-endian", VALUE, G_ADD, V (Params::raw_output_format.set_endian (lookup (kEndians, v[0], "endianness"))) },
+  { "--raw-endian", VALUE, G_ADD, V (const auto e = lookup (kEndians, v[0], "endianness"); each_raw (BOTH, [&] (RawFormat& f) { f.set_endian (e); })) },
+  { "--raw-input-encoding", VALUE, G_ADD, V (set_encoding (Params::raw_input_format, v[0])) },
+  { "--raw-output-encoding", VALUE, G_ADD, V (set_encoding (Params::raw_output_format, v[0])) },
+  { "--raw-encoding", VALUE, G_ADD, V (each_raw (BOTH, [&] (RawFormat& f) { set_encoding (f, v[0]); })) },
+  { "--raw-input-bits", VALUE, G_ADD, V (set_bits (Params::raw_input_format, to_int (v[0]))) },
+  { "--raw-output-bits", VALUE, G_ADD, V (set_bits (Params::raw_output_format, to_int (v[0]))) },
+  { "--raw-bits", VALUE, G_ADD, V (const int b = to_int (v[0]); each_raw (BOTH, [&] (RawFormat& f) { set_bits (f, b); })) },
+  { "--raw-channels", VALUE, G_ADD, V (const int c = to_int (v[0]); each_raw (BOTH, [&] (RawFormat& f) { f.set_channels (c); })) },
+  { "--raw-rate", VALUE, G_ADD, V (const int r = to_int (v[0]); each_raw (BOTH, [&] (RawFormat& f) { f.set_sample_rate (r); })) },
+  { "--test-no-limiter", FLAG, G_ADD, V (Params::test_no_limiter = true) },
+  { "rf64 is an output format", CHECK, G_ADD, V (
+      if (Params::input_format == Format::RF64)
+        die ("audiowmark: using rf64 as input format has no effect\n")) },
+  { "--strength", VALUE, G_ADD, V (Params::water_delta = to_float (v[0]) / 1000) },      // add only: get normalises with the default strength
+
+  /* ---- get / cmp */
+  { "--test-cut", VALUE, G_GET, V (Params::test_cut = to_int (v[0])) },
+  { "--test-truncate", VALUE, G_GET, V (Params::test_truncate = to_int (v[0])) },
+  { "--hard", FLAG, G_GET, V (Params::hard = true) },
+  { "--test-no-sync", FLAG, G_GET, V (Params::test_no_sync = true) },
+  { "--detect-speed", FLAG, G_GET, V (Params::detect_speed = true; s.speed_option_count++) },
+  { "--detect-speed-patient", FLAG, G_GET, V (Params::detect_speed_patient = true; s.speed_option_count++) },
+  { "--try-speed", VALUE, G_GET, V (Params::try_speed = to_float (v[0]); s.speed_option_count++) },
+  { "one speed option", CHECK, G_GET, V (
+      if (s.speed_option_count > 1)
+        die ("audiowmark: can only use one option: --detect-speed or --detect-speed-patient or --try-speed\n")) },
+  { "--test-speed", VALUE, G_GET, V (Params::test_speed = to_float (v[0])) },
+  { "--json", VALUE, G_GET, V (Params::json_output = v[0]) },
+  { "--chunk-size", VALUE, G_GET, V (
+      const float minutes = to_float (v[0]);
+      if (minutes < 10)
+        die ("audiowmark: --chunk-size needs to be at least 10 minutes\n");
+      Params::get_chunk_size = minutes) },
+  { "--sync-threshold", VALUE, G_GET, V (Params::sync_threshold2 = to_float (v[0])) },
+  { "--n-best", VALUE, G_GET, V (
+      const int n = to_int (v[0]);
+      if (n < 0)
+        die ("audiowmark: --n-best should not be a negative number\n");
+      Params::get_n_best = n) },
+  { "--expect-matches", VALUE, G_CMP, V (Params::expect_matches = to_int (v[0])) },
+
+  /* ---- keys, gen-key, test-gen-noise */
+  { "--key", REPEATED, G_KEYS, load_key_file },
+  { "--test-key", REPEATED, G_KEYS, add_test_keys },
+  { "--name", VALUE, G_NAME, V (s.key_name = v[0]) },
+  { "--bits", VALUE, G_BITS, V (s.noise_bits = to_int (v[0])) },
+};
+#undef V
+
+/* Takes the occurrences of one option out of `tokens`.  FLAG: the first occurrence only (a repeated flag is left over and reported
+ * as unsupported, like in the reference); VALUE / REPEATED: every "--opt value" and "--opt=value". */
+bool
+extract (vector<string>& tokens, const Option& opt, vector<string>& values)
 {
-  string s;
-  float f;
-  int i;
-  ap.parse_opt ("--test-cut", Params::test_cut);
-  ap.parse_opt ("--test-truncate", Params::test_truncate);
-  if (ap.parse_opt ("--hard"))
-    Params::hard = true;
-  if (ap.parse_opt ("--test-no-sync"))
-    Params::test_no_sync = true;
-  int speed_options = 0;
-  if (ap.parse_opt ("--detect-speed"))
+  const string name = opt.name, with_eq = name + "=";
+  vector<string> kept;
+  bool found = false;
+  for (size_t i = 0; i < tokens.size(); i++)
     {
-      Params::detect_speed = true;
-      speed_options++;
-    }
-  if (ap.parse_opt ("--detect-speed-patient"))
-    {
-      Params::detect_speed_patient = true;
-      speed_options++;
-    }
-  if (ap.parse_opt ("--try-speed", f))
-    {
-      Params::try_speed = f;
-      speed_options++;
-    }
-  if (speed_options > 1)
-    {
-      error ("audiowmark: can only use one option: --detect-speed or --detect-speed-patient or --try-speed\n");
-      exit (1);
-    }
-  if (ap.parse_opt ("--test-speed", f))
-    Params::test_speed = f;
-  if (ap.parse_opt ("--input-format", s) || ap.parse_opt ("--format", s))
-    Params::input_format = parse_format (s);
-  if (ap.parse_opt ("--raw-input-endian", s) || ap.parse_opt ("--raw-endian", s))   Params::raw_input_format.set_endian (parse_endian (s));
-  if (ap.parse_opt ("--raw-input-encoding", s) || ap.parse_opt ("--raw-encoding", s)) parse_encoding (s, Params::raw_input_format);
-  if (ap.parse_opt ("--raw-input-bits", i) || ap.parse_opt ("--raw-bits", i))       update_raw_bits (Params::raw_input_format, i);
-  if (ap.parse_opt ("--raw-channels", i)) Params::raw_input_format.set_channels (i);
-  if (ap.parse_opt ("--raw-rate", i))     Params::raw_input_format.set_sample_rate (i);
-  if (ap.parse_opt ("--json", s))
-    Params::json_output = s;
-  if (ap.parse_opt ("--chunk-size", f))
-    {
-      if (f < 10)
+      const string& t = tokens[i];
+      if (opt.arity == FLAG)
         {
-          error ("audiowmark: --chunk-size needs to be at least 10 minutes\n");
-          exit (1);
+          if (t == name && !found)
+            found = true;
+          else
+            kept.push_back (t);
         }
-      Params::get_chunk_size = f;
-    }
-  if (ap.parse_opt ("--sync-threshold", f))
-    Params::sync_threshold2 = f;
-  if (ap.parse_opt ("--n-best", i))
-    {
-      if (i < 0)
+      else if (t == name && i + 1 < tokens.size())
         {
-          error ("audiowmark: --n-best should not be a negative number\n");
-          exit (1);
+          values.push_back (tokens[++i]);
+          found = true;
         }
-      Params::get_n_best = i;
-    }
-  /* --strength is an `add` option only: `get` normalises sync qualities with the default strength (src/audiowmark.cc:806-809) */
-}
-
-static vector<string>
-parse_positional (ArgParser& ap, const vector<string>& names)
-{
-  vector<string> args;
-  if (ap.parse_args (names.size(), args))
-    return args;
-  for (const auto& arg : ap.remaining_args())
-    if (is_option (arg))
-      {
-        error ("audiowmark: unsupported option '%s' for command '%s' (use audiowmark -h)\n", arg.c_str(), ap.command().c_str());
-        exit (1);
-      }
-  error ("audiowmark: error parsing arguments for command '%s' (use audiowmark -h)\n\n", ap.command().c_str());
-  string msg = "usage: audiowmark " + ap.command() + " [options...]";
-  for (const auto& s : names)
-    msg += " <" + s + ">";
-  error ("%s\n", msg.c_str());
-  exit (1);
-}
-
-/* ---------------------------------------------------------------- test helpers (src/audiowmark.cc:201-481) */
-
-static int
-load_or_complain (WavData& wav, const string& file)
-{
-  Error err = wav.load (file);
-  if (err)
-    {
-      error ("audiowmark: error loading %s: %s\n", file.c_str(), err.message());
-      return 1;
-    }
-  return 0;
-}
-
-static int
-save_or_complain (const WavData& wav, const string& file)
-{
-  Error err = wav.save (file);
-  if (err)
-    {
-      error ("audiowmark: error saving %s: %s\n", file.c_str(), err.message());
-      return 1;
-    }
-  return 0;
-}
-
-static int
-test_gen_noise (const Key& key, const string& out_file, double seconds, int rate, int bits)
-{
-  const int channels = 2;
-  vector<float> noise;
-  Random rng (key, 0, Random::Stream::data_up_down);
-  const size_t n = size_t (rate * seconds) * channels;
-  noise.reserve (n);
-  for (size_t i = 0; i < n; i++)
-    noise.push_back (rng.random_double() * 2 - 1);
-  return save_or_complain (WavData (noise, channels, rate, bits), out_file);
-}
-
-static int
-test_speed (const Key& key, int seed)              /* src/audiowmark.cc:389-397 */
-{
-  Random rng (key, seed, Random::Stream::data_up_down);
-  const double low = 0.85, high = 1.15;
-  printf ("%.6f\n", low + (rng() / double (UINT64_MAX)) * (high - low));
-  return 0;
-}
-
-static int
-test_change_speed (const string& in_file, const string& out_file, double speed)      /* src/audiowmark.cc:419-438 */
-{
-  WavData in_data;
-  if (load_or_complain (in_data, in_file))
-    return 1;
-  vector<float> out;
-  if (!resample_ratio (in_data.samples().data(), in_data.n_frames(), in_data.n_channels(), 1 / speed, out))
-    return 1;
-  return save_or_complain (WavData (out, in_data.n_channels(), in_data.sample_rate(), in_data.bit_depth()), out_file);
-}
-
-static int
-test_resample (const string& in_file, const string& out_file, int new_rate)           /* src/audiowmark.cc:440-458 */
-{
-  WavData in_data;
-  if (load_or_complain (in_data, in_file))
-    return 1;
-  if (new_rate == in_data.sample_rate())
-    {
-      error ("audiowmark: test-resample: input already has sample rate %d\n", new_rate);
-      return 1;
-    }
-  vector<float> out;
-  if (!resample_ratio (in_data.samples().data(), in_data.n_frames(), in_data.n_channels(), double (new_rate) / in_data.sample_rate(), out))
-    return 1;
-  return save_or_complain (WavData (out, in_data.n_channels(), new_rate, in_data.bit_depth()), out_file);
-}
-
-static int
-cut_start (const string& infile, const string& outfile, const string& start_str)
-{
-  WavData wav;
-  if (load_or_complain (wav, infile))
-    return 1;
-  const size_t start = size_t (atoi_or_die (start_str.c_str())) * wav.n_channels();
-  const vector<float>& in = wav.samples();
-  vector<float> out (in.begin() + std::min (start, in.size()), in.end());
-  return save_or_complain (WavData (out, wav.n_channels(), wav.sample_rate(), wav.bit_depth()), outfile);
-}
-
-static int
-gentest (const string& infile, const string& outfile)
-{
-  printf ("generating test sample from '%s' to '%s'\n", infile.c_str(), outfile.c_str());
-  WavData wav;
-  if (load_or_complain (wav, infile))
-    return 1;
-  const size_t n = size_t (165) * wav.n_channels() * wav.sample_rate();      // 2:45, room for three blocks
-  if (wav.n_values() < n)
-    {
-      error ("audiowmark: input file %s too short\n", infile.c_str());
-      return 1;
-    }
-  vector<float> out (wav.samples().begin(), wav.samples().begin() + n);
-  return save_or_complain (WavData (out, wav.n_channels(), wav.sample_rate(), wav.bit_depth()), outfile);
-}
-
-static int
-test_subtract (const string& f1, const string& f2, const string& outfile)
-{
-  WavData a, b;
-  if (load_or_complain (a, f1) || load_or_complain (b, f2))
-    return 1;
-  if (a.n_values() != b.n_values())
-    {
-      const size_t delta = a.n_values() > b.n_values() ? a.n_values() - b.n_values() : b.n_values() - a.n_values();
-      warning ("audiowmark: size mismatch: %zd frames\n", delta / a.n_channels());
-      warning (" - %s frames: %zd\n", f1.c_str(), a.n_frames());
-      warning (" - %s frames: %zd\n", f2.c_str(), b.n_frames());
-    }
-  const size_t len = std::min (a.n_values(), b.n_values());
-  vector<float> out (len);
-  for (size_t i = 0; i < len; i++)
-    out[i] = a.samples()[i] - b.samples()[i];
-  return save_or_complain (WavData (out, a.n_channels(), a.sample_rate(), a.bit_depth()), outfile);
-}
-
-static int
-test_snr (const string& orig_file, const string& wm_file)
-{
-  WavData orig, wm;
-  if (load_or_complain (orig, orig_file) || load_or_complain (wm, wm_file))
-    return 1;
-  if (orig.n_values() != wm.n_values())
-    {
-      error ("audiowmark: test-snr: files differ in length\n");
-      return 1;
-    }
-  double delta_power = 0, signal_power = 0;
-  for (size_t i = 0; i < orig.n_values(); i++)
-    {
-      const double o = orig.samples()[i], d = orig.samples()[i] - wm.samples()[i];
-      delta_power += d * d;
-      signal_power += o * o;
-    }
-  printf ("%f\n", 10 * log10 (signal_power / delta_power));
-  return 0;
-}
-
-static int
-test_clip (const Key& key, const string& in_file, const string& out_file, int seed, int time_seconds)
-{
-  WavData in;
-  if (load_or_complain (in, in_file))
-    return 1;
-  Random rng (key, seed, Random::Stream::data_up_down);
-  size_t start_point, end_point;
-  for (;;)
-    {
-      const size_t values_per_block = frames_per_block() * Params::frame_size * in.n_channels();
-      start_point = 2 * values_per_block * rng.random_double();
-      start_point /= in.n_channels();
-      end_point = start_point + size_t (time_seconds) * in.sample_rate();
-      if (end_point < in.n_values() / in.n_channels())
-        break;
-    }
-  vector<float> out (in.samples().begin() + start_point * in.n_channels(), in.samples().begin() + end_point * in.n_channels());
-  return save_or_complain (WavData (out, in.n_channels(), in.sample_rate(), in.bit_depth()), out_file);
-}
-
-static int
-test_info (const string& in_file, const string& property)
-{
-  WavData in;
-  if (load_or_complain (in, in_file))
-    return 1;
-  if (property == "bit_depth")
-    {
-      printf ("%d\n", in.bit_depth());
-      return 0;
-    }
-  if (property == "frames")
-    {
-      printf ("%zd\n", in.n_frames());
-      return 0;
-    }
-  error ("audiowmark: unsupported property for test_info: %s\n", property.c_str());
-  return 1;
-}
-
-static int
-gen_key (const string& outfile, const string& key_name)
-{
-  string ename;
-  for (unsigned char ch : key_name)
-    {
-      if (ch == '"' || ch == '\\')
-        ename += '\\';
-      else if (ch < 32)
+      else if (t.compare (0, with_eq.size(), with_eq) == 0)
         {
-          error ("audiowmark: bad key name: %d is not allowed as character in key names\n", ch);
-          exit (1);
+          values.push_back (t.substr (with_eq.size()));
+          found = true;
         }
-      ename += ch;
+      else
+        kept.push_back (t);
     }
-  const int fd = open (outfile.c_str(), O_WRONLY | O_CREAT | O_TRUNC, S_IRUSR | S_IWUSR);
-  FILE *f = fd >= 0 ? fdopen (fd, "w") : nullptr;
-  if (!f)
-    {
-      if (fd >= 0)
-        close (fd);
-      error ("audiowmark: error opening file %s: %s\n", outfile.c_str(), strerror (errno));
-      return 1;
-    }
-  fprintf (f, "# watermarking key for audiowmark\n\nkey %s\n", Random::gen_key().c_str());
-  if (!key_name.empty())
-    fprintf (f, "name \"%s\"\n", ename.c_str());
-  fclose (f);
-  return 0;
+  tokens.swap (kept);
+  return found;
 }
+
+void
+apply_options (vector<string>& tokens, unsigned groups, Session& session)
+{
+  for (const Option& opt : kOptions)
+    {
+      if (!(opt.groups & groups))
+        continue;
+      if (opt.arity == CHECK)
+        {
+          opt.apply ({}, session);
+          continue;
+        }
+      vector<string> values;
+      if (!extract (tokens, opt, values))
+        continue;
+      if (opt.arity == VALUE)
+        values.erase (values.begin(), values.end() - 1);       // the last one wins
+      opt.apply (values, session);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ command table */
+
+enum KeyPolicy { NO_KEY, ONE_KEY, KEY_LIST };
+
+struct Invocation
+{
+  Session        session;
+  vector<string> args;             // positional arguments
+  const Key&     key() const { return session.keys[0]; }
+};
+
+struct Command
+{
+  const char *name;
+  unsigned    groups;
+  KeyPolicy   keys;
+  vector<const char *> positional;
+  int (*run) (Invocation&);
+};
+
+const Command kCommands[] = {
+  { "add", G_SHARED | G_ADD | G_KEYS, ONE_KEY, { "input_wav", "watermarked_wav", "message_hex" },
+    [] (Invocation& inv) { return add_watermark (inv.key(), inv.args[0], inv.args[1], inv.args[2]); } },
+  { "get", G_SHARED | G_GET | G_KEYS, KEY_LIST, { "watermarked_wav" },
+    [] (Invocation& inv) { return get_watermark (inv.session.keys, inv.args[0], ""); } },
+  { "cmp", G_SHARED | G_GET | G_CMP | G_KEYS, KEY_LIST, { "watermarked_wav", "message_hex" },
+    [] (Invocation& inv) { return get_watermark (inv.session.keys, inv.args[0], inv.args[1]); } },
+  { "gen-key", G_NAME, NO_KEY, { "key_file" },
+    [] (Invocation& inv) { return cli_tools::gen_key (inv.args[0], inv.session.key_name); } },
+  { "gentest", 0, NO_KEY, { "input_wav", "output_wav" },
+    [] (Invocation& inv) { return cli_tools::gentest (inv.args[0], inv.args[1]); } },
+  { "cut-start", 0, NO_KEY, { "input_wav", "output_wav", "cut_samples" },
+    [] (Invocation& inv) { return cli_tools::cut_start (inv.args[0], inv.args[1], size_t (to_int (inv.args[2]))); } },
+  { "test-subtract", 0, NO_KEY, { "input1_wav", "input2_wav", "output_wav" },
+    [] (Invocation& inv) { return cli_tools::subtract (inv.args[0], inv.args[1], inv.args[2]); } },
+  { "test-snr", 0, NO_KEY, { "orig_wav", "watermarked_wav" },
+    [] (Invocation& inv) { return cli_tools::snr (inv.args[0], inv.args[1]); } },
+  { "test-clip", G_SHARED | G_KEYS, ONE_KEY, { "input_wav", "output_wav", "seed", "seconds" },
+    [] (Invocation& inv) { return cli_tools::clip (inv.key(), inv.args[0], inv.args[1], to_int (inv.args[2]), to_int (inv.args[3])); } },
+  { "test-gen-noise", G_SHARED | G_BITS | G_KEYS, ONE_KEY, { "output_wav", "seconds", "sample_rate" },
+    [] (Invocation& inv) { return cli_tools::gen_noise (inv.key(), inv.args[0], to_float (inv.args[1]), to_int (inv.args[2]), inv.session.noise_bits); } },
+  { "test-info", G_SHARED, NO_KEY, { "input_wav", "property" },
+    [] (Invocation& inv) { return cli_tools::info (inv.args[0], inv.args[1]); } },
+  { "test-speed", G_SHARED | G_KEYS, ONE_KEY, { "seed" },
+    [] (Invocation& inv) { return cli_tools::speed (inv.key(), to_int (inv.args[0])); } },
+  { "test-change-speed", G_SHARED, NO_KEY, { "input_wav", "output_wav", "speed" },
+    [] (Invocation& inv) { return cli_tools::change_speed (inv.args[0], inv.args[1], to_float (inv.args[2])); } },
+  { "test-resample", G_SHARED, NO_KEY, { "input_wav", "output_wav", "new_rate" },
+    [] (Invocation& inv) { return cli_tools::resample (inv.args[0], inv.args[1], to_int (inv.args[2])); } },
+};
+
+int
+run_command (const Command& cmd, vector<string> tokens)
+{
+  Invocation inv;
+  apply_options (tokens, cmd.groups, inv.session);
+  if (cmd.keys != NO_KEY && inv.session.keys.empty())
+    inv.session.keys.push_back (Key());                      // the zero key
+  if (cmd.keys == ONE_KEY && inv.session.keys.size() > 1)
+    die ("audiowmark %s: watermark key can at most be set once (--key / --test-key option)\n", cmd.name);
+
+  bool clean = tokens.size() == cmd.positional.size();
+  for (const auto& t : tokens)
+    clean = clean && !looks_like_option (t);
+  if (!clean)
+    {
+      for (const auto& t : tokens)
+        if (looks_like_option (t))
+          die ("audiowmark: unsupported option '%s' for command '%s' (use audiowmark -h)\n", t.c_str(), cmd.name);
+      string usage = string ("usage: audiowmark ") + cmd.name + " [options...]";
+      for (const char *p : cmd.positional)
+        usage += string (" <") + p + ">";
+      die ("audiowmark: error parsing arguments for command '%s' (use audiowmark -h)\n\n%s\n", cmd.name, usage.c_str());
+    }
+  inv.args = tokens;
+  return cmd.run (inv);
+}
+
+void
+print_usage()
+{
+  static const char *const text[] = {
+    "usage: audiowmark <command> [ <args>... ]",
+    "",
+    "Commands:",
+    "  * create a watermarked wav file with a message",
+    "    audiowmark add <input_wav> <watermarked_wav> <message_hex>",
+    "",
+    "  * retrieve message",
+    "    audiowmark get <watermarked_wav>",
+    "",
+    "  * compare watermark message with expected message",
+    "    audiowmark cmp <watermarked_wav> <message_hex>",
+    "",
+    "  * generate 128-bit watermarking key, to be used with --key option",
+    "    audiowmark gen-key <key_file> [ --name <key_name> ]",
+    "",
+    "Global options:",
+    "  -q, --quiet             disable information messages",
+    "  --strict                treat (minor) problems as errors",
+    "  --gpu-device <n>        CUDA device to run on                [0]",
+    "",
+    "Options for get / cmp:",
+    "  --detect-speed          detect and correct replay speed difference",
+    "  --detect-speed-patient  slower, more accurate speed detection",
+    "  --json <file>           write JSON results into file",
+    "",
+    "Options for add / get / cmp:",
+    "  --key <file>            load watermarking key from file",
+    "  --short <bits>          enable short payload mode",
+  };
+  for (const char *line : text)
+    printf ("%s\n", line);
+  printf ("  --strength <s>          set watermark strength              [%.6g]\n", Params::water_delta * 1000);
+  static const char *const tail[] = {
+    "",
+    "  --input-format raw      use raw stream as input",
+    "  --output-format raw     use raw stream as output",
+    "  --format raw            use raw stream as input and output",
+    "",
+    "The options to set the raw stream parameters (such as --raw-rate",
+    "or --raw-channels) follow the reference audiowmark README.",
+  };
+  for (const char *line : tail)
+    printf ("%s\n", line);
+}
+
+/* a global flag may stand anywhere on the command line */
+bool
+take_flag (vector<string>& tokens, std::initializer_list<const char *> spellings)
+{
+  for (const char *sp : spellings)
+    for (auto it = tokens.begin(); it != tokens.end(); ++it)
+      if (*it == sp)
+        {
+          tokens.erase (it);
+          return true;
+        }
+  return false;
+}
+
+} // namespace
 
 int
 main (int argc, char **argv)
 {
-  ArgParser ap (argc, argv);
-  vector<string> args;
+  vector<string> tokens (argv + 1, argv + argc);
 
-  if (ap.parse_opt ("--help") || ap.parse_opt ("-h"))
+  if (take_flag (tokens, { "--help", "-h" }))
     {
       print_usage();
       return 0;
     }
-  if (ap.parse_opt ("--version") || ap.parse_opt ("-v"))
+  if (take_flag (tokens, { "--version", "-v" }))
     {
       printf ("audiowmark %s\n", AWM_VERSION);
       return 0;
     }
-  if (ap.parse_opt ("--quiet") || ap.parse_opt ("-q"))
+  if (take_flag (tokens, { "--quiet", "-q" }))
     set_log_level (Log::WARNING);
-  if (ap.parse_opt ("--strict"))
+  if (take_flag (tokens, { "--strict" }))
     Params::strict = true;
-  ap.parse_opt ("--gpu-device", Params::gpu_device);
+  {
+    const Option gpu_device { "--gpu-device", VALUE, 0, nullptr };
+    vector<string> values;
+    if (extract (tokens, gpu_device, values))
+      Params::gpu_device = to_int (values.back());
+  }
 
   int rc = 1;
-  if (ap.parse_cmd ("add"))
-    {
-      parse_shared_options (ap);
-      parse_add_options (ap);
-      Key key = parse_key (ap);
-      args = parse_positional (ap, { "input_wav", "watermarked_wav", "message_hex" });
-      rc = add_watermark (key, args[0], args[1], args[2]);
-    }
-  else if (ap.parse_cmd ("get"))
-    {
-      parse_shared_options (ap);
-      parse_get_options (ap);
-      vector<Key> key_list = parse_key_list (ap);
-      args = parse_positional (ap, { "watermarked_wav" });
-      rc = get_watermark (key_list, args[0], "");
-    }
-  else if (ap.parse_cmd ("cmp"))
-    {
-      parse_shared_options (ap);
-      parse_get_options (ap);
-      ap.parse_opt ("--expect-matches", Params::expect_matches);
-      vector<Key> key_list = parse_key_list (ap);
-      args = parse_positional (ap, { "watermarked_wav", "message_hex" });
-      rc = get_watermark (key_list, args[0], args[1]);
-    }
-  else if (ap.parse_cmd ("gen-key"))
-    {
-      string key_name;
-      ap.parse_opt ("--name", key_name);
-      args = parse_positional (ap, { "key_file" });
-      rc = gen_key (args[0], key_name);
-    }
-  else if (ap.parse_cmd ("gentest"))
-    {
-      args = parse_positional (ap, { "input_wav", "output_wav" });
-      rc = gentest (args[0], args[1]);
-    }
-  else if (ap.parse_cmd ("cut-start"))
-    {
-      args = parse_positional (ap, { "input_wav", "output_wav", "cut_samples" });
-      rc = cut_start (args[0], args[1], args[2]);
-    }
-  else if (ap.parse_cmd ("test-subtract"))
-    {
-      args = parse_positional (ap, { "input1_wav", "input2_wav", "output_wav" });
-      rc = test_subtract (args[0], args[1], args[2]);
-    }
-  else if (ap.parse_cmd ("test-snr"))
-    {
-      args = parse_positional (ap, { "orig_wav", "watermarked_wav" });
-      rc = test_snr (args[0], args[1]);
-    }
-  else if (ap.parse_cmd ("test-clip"))
-    {
-      parse_shared_options (ap);
-      Key key = parse_key (ap);
-      args = parse_positional (ap, { "input_wav", "output_wav", "seed", "seconds" });
-      rc = test_clip (key, args[0], args[1], atoi_or_die (args[2].c_str()), atoi_or_die (args[3].c_str()));
-    }
-  else if (ap.parse_cmd ("test-gen-noise"))
-    {
-      parse_shared_options (ap);
-      int bits = 16;
-      ap.parse_opt ("--bits", bits);
-      Key key = parse_key (ap);
-      args = parse_positional (ap, { "output_wav", "seconds", "sample_rate" });
-      rc = test_gen_noise (key, args[0], atof_or_die (args[1].c_str()), atoi_or_die (args[2].c_str()), bits);
-    }
-  else if (ap.parse_cmd ("test-info"))
-    {
-      parse_shared_options (ap);
-      args = parse_positional (ap, { "input_wav", "property" });
-      rc = test_info (args[0], args[1]);
-    }
-  else if (ap.parse_cmd ("test-speed"))
-    {
-      parse_shared_options (ap);
-      Key key = parse_key (ap);
-      args = parse_positional (ap, { "seed" });
-      rc = test_speed (key, atoi_or_die (args[0].c_str()));
-    }
-  else if (ap.parse_cmd ("test-change-speed"))
-    {
-      parse_shared_options (ap);
-      args = parse_positional (ap, { "input_wav", "output_wav", "speed" });
-      rc = test_change_speed (args[0], args[1], atof_or_die (args[2].c_str()));
-    }
-  else if (ap.parse_cmd ("test-resample"))
-    {
-      parse_shared_options (ap);
-      args = parse_positional (ap, { "input_wav", "output_wav", "new_rate" });
-      rc = test_resample (args[0], args[1], atoi_or_die (args[2].c_str()));
-    }
-  else if (ap.parse_cmd ("hls-add") || ap.parse_cmd ("hls-prepare"))
-    {
-      error ("audiowmark: command '%s' is not available in this build (HLS is out of scope)\n", ap.command().c_str());
-      rc = 1;
-    }
-  else if (!ap.remaining_args().empty())
-    {
-      const string s = ap.remaining_args().front();
-      if (is_option (s))
-        error ("audiowmark: unsupported global option '%s' (use audiowmark -h)\n", s.c_str());
-      else
-        error ("audiowmark: unsupported command '%s' (use audiowmark -h)\n", s.c_str());
-      rc = 1;
-    }
+  if (tokens.empty())
+    error ("audiowmark: error parsing commandline args (use audiowmark -h)\n");
   else
     {
-      error ("audiowmark: error parsing commandline args (use audiowmark -h)\n");
-      rc = 1;
+      const string word = tokens.front();
+      const Command *cmd = nullptr;
+      for (const Command& c : kCommands)
+        if (word == c.name)
+          cmd = &c;
+      if (cmd)
+        rc = run_command (*cmd, vector<string> (tokens.begin() + 1, tokens.end()));
+      else if (word == "hls-add" || word == "hls-prepare")
+        error ("audiowmark: command '%s' is not available in this build (HLS is out of scope)\n", word.c_str());
+      else if (looks_like_option (word))
+        error ("audiowmark: unsupported global option '%s' (use audiowmark -h)\n", word.c_str());
+      else
+        error ("audiowmark: unsupported command '%s' (use audiowmark -h)\n", word.c_str());
     }
   Engine::shutdown();
   return rc;

@@ -58,6 +58,18 @@ def test_argv_errors_are_the_reference_ones(tmp_path):
         ["add", "--format", "bogus", "n.wav", "o.wav", "00"], ["add", "--raw-rate", "x", "n.wav", "o.wav", "00"],
         ["add", "n.wav", "o.wav", "xyz"], ["add", "nofile.wav", "o.wav", "00"], ["get", "nofile.wav"], ["cmp", "nofile.wav", "00"],
         ["get", "--try-speed", "abc", "n.wav"], ["get", "--json"],
+        # the generic option scanner against the reference's hand-written sequences: repeated flags, "=" forms, last value wins,
+        # "--a || --b" pairs, options after positional arguments, checks that fire before later conversions
+        ["get", "--hard", "--hard", "n.wav"], ["get", "--n-best=-1", "n.wav"], ["add", "--format", "raw", "--format", "bogus", "a", "b", "00"],
+        ["add", "--strength"], ["-q", "foo"], ["--strict"], ["add", "a.wav", "--bogus", "b.wav", "00"],
+        ["get", "--input-format", "raw", "--format", "bogus", "n.wav"], ["get", "--raw-bits", "16", "n.wav"],
+        ["add", "--input-format", "rf64", "--strength", "abc", "n.wav", "o.wav", "00"], ["get", "--chunk-size", "5", "n.wav"],
+        ["cmp", "--expect-matches", "x", "n.wav", "00"], ["test-gen-noise", "--bits", "x", "o.wav", "1", "44100"],
+        ["get", "--detect-speed", "--try-speed", "1.1", "--test-speed", "abc", "n.wav"], ["add", "--raw-encoding", "double", "--raw-bits", "16", "n.wav", "o.wav", "00"], ["add", "--raw-rate", "0x", "n.wav", "o.wav", "00"],
+        ["add", "--raw-encoding", "float", "--raw-bits", "12", "--raw-endian", "middle", "n.wav", "o.wav", "00"],
+        ["add", "--short", "12", "n.wav", "o.wav", "abcd"], ["add", "--short=16", "--short", "13", "n.wav", "o.wav", "abcd"],
+        ["test-clip", "--test-key", "1", "--test-key", "2", "n.wav", "c.wav", "1", "1"], ["get", "--key"], ["get", "--key=nokey.key", "n.wav"],
+        ["cut-start", "n.wav", "o.wav", "abc"], ["test-speed", "x"],
     ]
     for args in cases:
         assert run(REF, tmp_path, args) == run(CLI, tmp_path, args), args
