@@ -10,6 +10,7 @@
 #include <vector>
 #include <string.h>
 #include "awm_approx_tc.cuh"
+#include "awm_embed_strip.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -814,6 +815,15 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
   A.synth = ctx->synth.as<float>();
   const size_t smem = fft_smem_bytes (kEmbedWarps) + 3 * kFrame * sizeof (float) + 2 * size_t (kEmbedWarps) * kEdge * sizeof (float2);
   if (set_smem (ctx, k_embed, smem)) return 1;
+  /* stereo audio in a 16-byte aligned buffer streams through k_embed_strip (awm_embed_strip.cuh); AWM_EMBED=tile keeps k_embed */
+  const char *env_embed = getenv ("AWM_EMBED");
+  const bool use_strip = channels == 2 && (reinterpret_cast<uintptr_t> (A.in) & 15) == 0 && !(env_embed && !strcmp (env_embed, "tile"));
+  if (use_strip)
+    {
+      if (!ctx->n_sms)
+        CK (cudaDeviceGetAttribute (&ctx->n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      if (set_smem (ctx, k_embed_strip, kStripSmem)) return 1;
+    }
 
   /* The buffer is processed in pieces of kPiece frames so that, for host buffers, the H2D copy of piece p+1, the
    * kernels of piece p and the D2H copy of piece p-1 overlap (three streams, events in between).  The arithmetic is
@@ -902,6 +912,20 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
       if (pipelined)
         CK (cudaStreamWaitEvent (ctx->stream, ev_in[std::min (p + 1, n_pieces - 1)], 0));   // halo frame of the next piece
       piece_frames (p, A.frame_begin, A.frame_end);
+      if (use_strip)
+        {
+          /* strips long enough to make the two halo frames cheap, short enough to give every SM's warps one */
+          const long long n_emit = A.frame_end - A.frame_begin;
+          const int strip_len = int (std::max<long long> (16, (n_emit + (long long) ctx->n_sms * kStripWarps - 1) / ((long long) ctx->n_sms * kStripWarps)));
+          const long long n_strips = (n_emit + strip_len - 1) / strip_len;
+          PROF (ctx);
+          k_embed_strip<<<unsigned ((n_strips + kStripWarps - 1) / kStripWarps), kStripWarps * 32, kStripSmem, ctx->stream>>> (A, strip_len);
+          LAUNCH_CHECK ("k_embed_strip");
+          prof_bytes (ctx, double (std::min<long long> (A.frame_end * kFrame, (long long) n_frames) - std::min<long long> (A.frame_begin * kFrame, (long long) n_frames)) * channels * 2 * sizeof (float));
+          if (p > 0 && launch_limiter (p - 1))
+            return 1;
+          continue;
+        }
       const unsigned grid = unsigned ((A.frame_end - A.frame_begin + kEmbedTile - 1) / kEmbedTile);
       PROF (ctx);
       k_embed<<<grid, kEmbedWarps * 32, smem, ctx->stream>>> (A);

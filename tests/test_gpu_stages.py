@@ -72,6 +72,19 @@ def test_embed_vs_oracle(ctx, limiter, seconds, channels):
         assert abs(snr - ref.snr_db) < 1e-3
 
 
+@pytest.mark.parametrize("seconds,limiter", [(20.0, True), (3.3, False), (0.01, True)])
+def test_embed_strip_kernel_equals_tile_kernel(ctx, monkeypatch, seconds, limiter):
+    """k_embed_strip (streaming, TMA-fed, neighbours' window tails carried in registers) and k_embed (CTA tiles with a halo frame on
+    each side) run the same arithmetic in the same order: identical bits, identical limiter peaks, for whole and ragged lengths"""
+    x = T.noise(seconds, 2, seed=21, amp=1.0 if limiter else 0.5)
+    monkeypatch.setenv("AWM_EMBED", "tile")
+    tile, tile_snr = ctx.embed(x, limiter_block=44100 if limiter else 0, want_snr=True)
+    monkeypatch.delenv("AWM_EMBED")
+    strip, strip_snr = ctx.embed(x, limiter_block=44100 if limiter else 0, want_snr=True)
+    assert np.array_equal(tile, strip)
+    assert np.allclose(tile_snr, strip_snr, rtol=1e-12)
+
+
 def test_embed_device_pointers_match_host_path(ctx):
     torch = pytest.importorskip("torch")
     x = T.noise(5.0, 2, seed=3)
