@@ -24,39 +24,6 @@ namespace awm {
 constexpr int kStripWarps = 8;
 constexpr size_t kStripSmem = fft_smem_bytes (kStripWarps) + 3 * kFrame * sizeof (float) + 64 + kStripWarps * sizeof (uint64_t);
 
-// delta spectrum of one K2 group (bins lane + 32 K2 of both channels) written into the (re <-> im swapped) input of the inverse
-// transform, mirrored half included -- the body k_embed uses as well
-template<int K2> __device__ __forceinline__ void
-embed_mod_group (const float (&re)[32], const float (&im)[32], float (&inr)[32], float (&ini)[32], const uint8_t *fm,
-                 float pow_up, float pow_down, int lane)
-{
-  float ar, ai, br, bi;
-  unpack_pair<K2> (re, im, lane, ar, ai, br, bi);
-  const int k = lane + 32 * K2;
-  float dar = 0.f, dai = 0.f, dbr = 0.f, dbi = 0.f;
-  if (k >= kMinBand && k <= kMaxBand)
-    {
-      const int mod = fm[k];
-      if (mod != 0)
-        {
-          /* mag^e - 1 = exp2 (e/2 * log2 (re^2 + im^2)) - 1; mag > 1e-7 <=> mag^2 > 1e-14 */
-          const float ex2 = (mod == 1) ? pow_up : pow_down;
-          const float pa = ar * ar + ai * ai;
-          if (pa > 1e-14f) { const float f = exp2f (ex2 * log2f (pa)) - 1.0f; dar = ar * f; dai = ai * f; }
-          const float pb = br * br + bi * bi;
-          if (pb > 1e-14f) { const float f = exp2f (ex2 * log2f (pb)) - 1.0f; dbr = br * f; dbi = bi * f; }
-        }
-    }
-  /* D[k] = dA + i dB ; D[N-k] = conj dA + i conj dB ; registers hold the re<->im swapped input */
-  inr[K2] = dai + dbr;
-  ini[K2] = dar - dbi;
-  const float mr = dar + dbi, mi = dbr - dai;
-  const int src = (32 - lane) & 31;
-  const float gr = __shfl_sync (0xffffffffu, mr, src), gi = __shfl_sync (0xffffffffu, mi, src);
-  if (lane == 0) { inr[(32 - K2) & 31] = (K2 == 0) ? inr[0] : gi; ini[(32 - K2) & 31] = (K2 == 0) ? ini[0] : gr; }
-  else           { inr[31 - K2] = gi; ini[31 - K2] = gr; }
-}
-
 __global__ void __launch_bounds__ (kStripWarps * 32, 1)
 k_embed_strip (EmbedArgs A, int strip_len)
 {
@@ -181,10 +148,10 @@ k_embed_strip (EmbedArgs A, int strip_len)
 #pragma unroll
           for (int j = 0; j < 32; j++)
             inr[j] = ini[j] = 0.f;
-          embed_mod_group<0> (re, im, inr, ini, fm, A.pow_up, A.pow_down, lane);
-          embed_mod_group<1> (re, im, inr, ini, fm, A.pow_up, A.pow_down, lane);
-          embed_mod_group<2> (re, im, inr, ini, fm, A.pow_up, A.pow_down, lane);
-          embed_mod_group<3> (re, im, inr, ini, fm, A.pow_up, A.pow_down, lane);
+          embed_mod_group<0> (re, im, inr, ini, fm, A.pow_up, A.pow_down, true, lane);
+          embed_mod_group<1> (re, im, inr, ini, fm, A.pow_up, A.pow_down, true, lane);
+          embed_mod_group<2> (re, im, inr, ini, fm, A.pow_up, A.pow_down, true, lane);
+          embed_mod_group<3> (re, im, inr, ini, fm, A.pow_up, A.pow_down, true, lane);
           fft1024_warp (inr, ini, s.tw, s.xbuf, lane, [&] { if (nxt_tma) prefetch (m + 1); });
           // inverse result: sample x = lane + 32*brev5(i): channel A = ini[i], channel B = inr[i]
 #pragma unroll

@@ -820,6 +820,53 @@ struct EmbedArgs
   const float *synth;          // [3072] synthesis window
 };
 
+// delta spectrum of one K2 group (bins lane + 32 K2 of both channels of the pair) written into the (re <-> im swapped) input of the
+// inverse transform, mirrored half included.  Shared by k_embed and k_embed_strip; every product and sum is spelled out with its
+// rounding (no FMA contraction left to the compiler), so the two kernels produce identical bits.
+template<int K2> __device__ __forceinline__ void
+embed_mod_group (const float (&re)[32], const float (&im)[32], float (&inr)[32], float (&ini)[32], const uint8_t *fm,
+                 float pow_up, float pow_down, bool have_b, int lane)
+{
+  float ar, ai, br, bi;
+  unpack_pair<K2> (re, im, lane, ar, ai, br, bi);
+  const int k = lane + 32 * K2;
+  float dar = 0.f, dai = 0.f, dbr = 0.f, dbi = 0.f;
+  if (k >= kMinBand && k <= kMaxBand)
+    {
+      const int mod = fm[k];
+      if (mod != 0)
+        {
+          /* mag^e - 1 = exp2 (e/2 * log2 (re^2 + im^2)) - 1; mag > 1e-7 <=> mag^2 > 1e-14 */
+          const float ex2 = (mod == 1) ? pow_up : pow_down;
+          const float pa = __fmaf_rn (ar, ar, __fmul_rn (ai, ai));
+          if (pa > 1e-14f)
+            {
+              const float f = __fsub_rn (exp2f (__fmul_rn (ex2, log2f (pa))), 1.0f);
+              dar = __fmul_rn (ar, f);
+              dai = __fmul_rn (ai, f);
+            }
+          if (have_b)
+            {
+              const float pb = __fmaf_rn (br, br, __fmul_rn (bi, bi));
+              if (pb > 1e-14f)
+                {
+                  const float f = __fsub_rn (exp2f (__fmul_rn (ex2, log2f (pb))), 1.0f);
+                  dbr = __fmul_rn (br, f);
+                  dbi = __fmul_rn (bi, f);
+                }
+            }
+        }
+    }
+  /* D[k] = dA + i dB ; D[N-k] = conj dA + i conj dB ; registers hold the re<->im swapped input */
+  inr[K2] = __fadd_rn (dai, dbr);
+  ini[K2] = __fsub_rn (dar, dbi);
+  const float mr = __fadd_rn (dar, dbi), mi = __fsub_rn (dbr, dai);
+  const int src = (32 - lane) & 31;
+  const float gr = __shfl_sync (0xffffffffu, mr, src), gi = __shfl_sync (0xffffffffu, mi, src);
+  if (lane == 0) { inr[(32 - K2) & 31] = (K2 == 0) ? inr[0] : gi; ini[(32 - K2) & 31] = (K2 == 0) ? ini[0] : gr; }
+  else           { inr[31 - K2] = gi; ini[31 - K2] = gr; }
+}
+
 __global__ void __launch_bounds__ (kEmbedWarps * 32, 1)
 k_embed (EmbedArgs A)
 {
@@ -863,39 +910,10 @@ k_embed (EmbedArgs A)
           for (int j = 0; j < 32; j++)
             inr[j] = ini[j] = 0.f;
           // own bins k = lane + 32*K2 at register K2, mirrored bins N-k arrive from lane (32-lane)&31
-#define AWM_MOD(K2) \
-          { \
-            float ar, ai, br, bi; \
-            unpack_pair<K2> (re, im, lane, ar, ai, br, bi); \
-            const int k = lane + 32 * K2; \
-            float dar = 0.f, dai = 0.f, dbr = 0.f, dbi = 0.f; \
-            if (k >= kMinBand && k <= kMaxBand) \
-              { \
-                const int mod = fm[k]; \
-                if (mod != 0) \
-                  { \
-                    /* mag^e - 1 = exp2 (e/2 * log2 (re^2 + im^2)) - 1; mag > 1e-7 <=> mag^2 > 1e-14 */ \
-                    const float ex2 = (mod == 1) ? A.pow_up : A.pow_down; \
-                    const float pa = ar * ar + ai * ai; \
-                    if (pa > 1e-14f) { const float f = exp2f (ex2 * log2f (pa)) - 1.0f; dar = ar * f; dai = ai * f; } \
-                    if (chB >= 0) \
-                      { \
-                        const float pb = br * br + bi * bi; \
-                        if (pb > 1e-14f) { const float f = exp2f (ex2 * log2f (pb)) - 1.0f; dbr = br * f; dbi = bi * f; } \
-                      } \
-                  } \
-              } \
-            /* D[k] = dA + i dB ; D[N-k] = conj dA + i conj dB ; registers hold the re<->im swapped input */ \
-            inr[K2] = dai + dbr; \
-            ini[K2] = dar - dbi; \
-            const float mr = dar + dbi, mi = dbr - dai; \
-            const int src = (32 - lane) & 31; \
-            const float gr = __shfl_sync (0xffffffffu, mr, src), gi = __shfl_sync (0xffffffffu, mi, src); \
-            if (lane == 0) { inr[(32 - K2) & 31] = (K2 == 0) ? inr[0] : gi; ini[(32 - K2) & 31] = (K2 == 0) ? ini[0] : gr; } \
-            else           { inr[31 - K2] = gi; ini[31 - K2] = gr; } \
-          }
-          AWM_MOD (0) AWM_MOD (1) AWM_MOD (2) AWM_MOD (3)
-#undef AWM_MOD
+          embed_mod_group<0> (re, im, inr, ini, fm, A.pow_up, A.pow_down, chB >= 0, lane);
+          embed_mod_group<1> (re, im, inr, ini, fm, A.pow_up, A.pow_down, chB >= 0, lane);
+          embed_mod_group<2> (re, im, inr, ini, fm, A.pow_up, A.pow_down, chB >= 0, lane);
+          embed_mod_group<3> (re, im, inr, ini, fm, A.pow_up, A.pow_down, chB >= 0, lane);
           fft1024_warp (inr, ini, s.tw, s.xbuf, lane);
           // inverse result: sample x = lane + 32*brev5(i): channel A = ini[i], channel B = inr[i]
 #pragma unroll
