@@ -7,9 +7,10 @@
 //     three frames, only its outer 103 samples on each side are non-zero) -- lives in fixed registers of fixed lanes (sample
 //     x = lane + 32 brev5 (i) sits in register i), so it is simply carried from one iteration to the next: no shared-memory
 //     exchange, no CTA barrier, and one halo frame per strip end instead of two per 14 frames (2 % recomputation instead of 14 %)
-//   * the PCM of frame m + 1 arrives by a bulk copy (TMA, cp.async.bulk + mbarrier) in the warp's FFT transpose buffer while the
-//     inverse transform of frame m runs its second butterfly pass; the warp keeps the raw samples in registers for the final
-//     "+ orig", so every input byte crosses HBM -> SM exactly once and no load ever stalls the butterflies
+//   * the PCM of a frame arrives by a bulk copy (TMA, cp.async.bulk + mbarrier) in a per-warp landing buffer in shared memory, issued
+//     as soon as the previous frame has been emitted; the forward transform reads it from there and so does the final "+ orig", so
+//     every input byte crosses HBM -> SM exactly once, no global load ever stalls the butterflies, and the raw samples cost no
+//     registers (twelve warps per SM instead of eight)
 //   * an iteration stores one contiguous 8 KB span: the last 104 samples of frame m - 1 (now that frame m's contribution is known)
 //     and the first 920 of frame m
 // Arithmetic and rounding order are those of k_embed (products and sums of the synthesis rounded separately, in the reference's
@@ -21,8 +22,9 @@
 
 namespace awm {
 
-constexpr int kStripWarps = 8;
-constexpr size_t kStripSmem = fft_smem_bytes (kStripWarps) + 3 * kFrame * sizeof (float) + 64 + kStripWarps * sizeof (uint64_t);
+constexpr int kStripWarps = 12;
+constexpr size_t kStripSmem = fft_smem_bytes (kStripWarps) + 3 * kFrame * sizeof (float) + size_t (kStripWarps) * kFrame * sizeof (float2)
+                              + 64 + kStripWarps * sizeof (uint64_t);
 
 __global__ void __launch_bounds__ (kStripWarps * 32, 1)
 k_embed_strip (EmbedArgs A, int strip_len)
@@ -31,7 +33,8 @@ k_embed_strip (EmbedArgs A, int strip_len)
   extern __shared__ __align__ (16) unsigned char smem[];
   FftSmem s = fft_smem_setup (smem, A.tw, A.win, kStripWarps);
   float *synth = s.extra;                                   // [3072]
-  uint64_t *bars = reinterpret_cast<uint64_t *> (synth + 3 * kFrame);
+  float2 *pcm_all = reinterpret_cast<float2 *> (synth + 3 * kFrame);       // [warps][1024]: landing buffers of the bulk copies
+  uint64_t *bars = reinterpret_cast<uint64_t *> (pcm_all + size_t (kStripWarps) * kFrame);
   for (int i = threadIdx.x; i < 3 * kFrame; i += blockDim.x)
     synth[i] = A.synth[i];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -42,6 +45,7 @@ k_embed_strip (EmbedArgs A, int strip_len)
   __syncthreads();
   uint64_t *bar = &bars[w];
   uint32_t phase = 0;
+  float2 *pcmbuf = pcm_all + size_t (w) * kFrame;
 
   const long long m_first = A.frame_begin + ((long long) blockIdx.x * kStripWarps + w) * strip_len;
   const long long m_last = m_first + strip_len < A.frame_end ? m_first + strip_len : A.frame_end;      // exclusive
@@ -52,13 +56,13 @@ k_embed_strip (EmbedArgs A, int strip_len)
   float2 *out2 = reinterpret_cast<float2 *> (A.out);
   auto exists = [&] (long long m) { return m >= 0 && m < n_real; };
   auto whole = [&] (long long m) { return m >= 0 && (m + 1) * kFrame <= A.n_frames; };      // the bulk copy needs all 1024 sample-frames
-  auto prefetch = [&] (long long m)             // caller: after __syncwarp, the transpose buffer is idle
+  auto prefetch = [&] (long long m)             // caller: after __syncwarp, no lane reads the landing buffer any more
     {
       if (lane == 0)
         {
           fence_proxy_async();
           mbar_arrive_expect_tx (bar, kFrame * sizeof (float2));
-          bulk_load (s.xbuf, in2 + m * kFrame, kFrame * sizeof (float2), bar);
+          bulk_load (pcmbuf, in2 + m * kFrame, kFrame * sizeof (float2), bar);
         }
     };
   // carried between iterations; the lane's head samples are registers brev5 (i) = 0..3 (the 4th only in lanes < 8: x < 104),
@@ -109,7 +113,6 @@ k_embed_strip (EmbedArgs A, int strip_len)
     prefetch (m_first - 1);
   for (long long m = m_first - 1; m <= m_last; m++)
     {
-      float2 orig[32];                            // raw input, orig[j] = sample 32 j + lane
       float re[32], im[32];
       const bool ex = exists (m), by_tma = ex && whole (m);
       const bool nxt_tma = m + 1 <= m_last && exists (m + 1) && whole (m + 1);
@@ -117,20 +120,17 @@ k_embed_strip (EmbedArgs A, int strip_len)
         {
           mbar_wait (bar, phase);
           phase ^= 1;
-          const float2 *xp = reinterpret_cast<const float2 *> (s.xbuf) + lane;
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            orig[j] = xp[32 * j];
-          __syncwarp();
         }
       else
         {
+          /* ragged last frame / beyond the input: the lanes fill the landing buffer themselves (zeros where there is no input) */
 #pragma unroll
           for (int j = 0; j < 32; j++)
             {
               const long long pos = m * kFrame + 32 * j + lane;
-              orig[j] = (ex && pos < A.n_frames) ? __ldg (in2 + pos) : make_float2 (0.f, 0.f);
+              pcmbuf[32 * j + lane] = (ex && pos < A.n_frames) ? __ldg (in2 + pos) : make_float2 (0.f, 0.f);
             }
+          __syncwarp();
         }
       if (ex)
         {
@@ -138,8 +138,9 @@ k_embed_strip (EmbedArgs A, int strip_len)
           for (int j = 0; j < 32; j++)
             {
               const float wn = s.win[32 * j + lane];
-              re[j] = orig[j].x * wn;
-              im[j] = orig[j].y * wn;
+              const float2 v = pcmbuf[32 * j + lane];
+              re[j] = v.x * wn;
+              im[j] = v.y * wn;
             }
           fft1024_warp (re, im, s.tw, s.xbuf, lane);
           const long long r = (A.frame_number0 + m) % (2LL * A.fpb);
@@ -152,7 +153,7 @@ k_embed_strip (EmbedArgs A, int strip_len)
           embed_mod_group<1> (re, im, inr, ini, fm, A.pow_up, A.pow_down, true, lane);
           embed_mod_group<2> (re, im, inr, ini, fm, A.pow_up, A.pow_down, true, lane);
           embed_mod_group<3> (re, im, inr, ini, fm, A.pow_up, A.pow_down, true, lane);
-          fft1024_warp (inr, ini, s.tw, s.xbuf, lane, [&] { if (nxt_tma) prefetch (m + 1); });
+          fft1024_warp (inr, ini, s.tw, s.xbuf, lane);
           // inverse result: sample x = lane + 32*brev5(i): channel A = ini[i], channel B = inr[i]
 #pragma unroll
           for (int i = 0; i < 32; i++)
@@ -166,9 +167,6 @@ k_embed_strip (EmbedArgs A, int strip_len)
 #pragma unroll
           for (int i = 0; i < 32; i++)
             re[i] = im[i] = 0.f;
-          __syncwarp();
-          if (nxt_tma)
-            prefetch (m + 1);
         }
       // ---- emit: the tail of frame m - 1 (x >= 920), then head and middle of frame m (x < 920)
       const bool emit_tail = m - 1 >= m_first && m - 1 < m_last && m - 1 < A.n_proc;
@@ -204,11 +202,11 @@ k_embed_strip (EmbedArgs A, int strip_len)
                 }
               // this frame's own tail: cur*w1 now, the next iteration adds next*w0
               tail_wm[q] = make_float2 (__fmul_rn (re[i], synth[kFrame + x]), __fmul_rn (im[i], synth[kFrame + x]));
-              tail_orig[q] = orig[b];
+              tail_orig[q] = pcmbuf[x];
               if (emit_body && !in_tail)           // x in [896, 920): middle of frame m
                 {
                   const float wa = tail_wm[q].x, wb = tail_wm[q].y;
-                  const float oa = orig[b].x, ob = orig[b].y;
+                  const float2 og = pcmbuf[x]; const float oa = og.x, ob = og.y;
                   const float ya = A.delta_only ? wa : __fadd_rn (wa, oa), yb = A.delta_only ? wb : __fadd_rn (wb, ob);
                   const long long pos = m * kFrame + x;
                   if (A.snr && m < A.snr_frames)
@@ -237,7 +235,7 @@ k_embed_strip (EmbedArgs A, int strip_len)
                 }
               if (emit_body)
                 {
-                  const float oa = orig[b].x, ob = orig[b].y;
+                  const float2 og = pcmbuf[x]; const float oa = og.x, ob = og.y;
                   const float ya = A.delta_only ? wa : __fadd_rn (wa, oa), yb = A.delta_only ? wb : __fadd_rn (wb, ob);
                   const long long pos = m * kFrame + x;
                   if (A.snr && m < A.snr_frames)
@@ -254,6 +252,9 @@ k_embed_strip (EmbedArgs A, int strip_len)
         }
       if (A.limiter_block > 0 && (emit_tail || emit_body))
         end_span (emit_body ? m * kFrame + kEdgeHi : m * kFrame);
+      __syncwarp();                                 // every lane has taken what it needs from the landing buffer
+      if (nxt_tma)
+        prefetch (m + 1);
     }
   if (A.limiter_block > 0)
     give (blk_cur, pk_cur);

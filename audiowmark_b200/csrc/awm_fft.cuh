@@ -54,9 +54,12 @@ twiddle32 (float tr, float ti, float& orr, float& oi)
   else if (IDX == 12) { const float r = 0.70710678118654752f; orr = (ti - tr) * r; oi = -(tr + ti) * r; }
   else
     {
+      /* one multiply + one fused multiply-add per component, spelled out: which of the two products gets fused is then the same
+       * in every kernel this is inlined into (left to the compiler it depends on the surrounding code, and two kernels that
+       * should agree bit for bit differ in the last digit) */
       const float c = w32_re (IDX), s = w32_im (IDX);
-      orr = tr * c - ti * s;
-      oi  = tr * s + ti * c;
+      orr = __fmaf_rn (tr, c, -__fmul_rn (ti, s));
+      oi  = __fmaf_rn (tr, s, __fmul_rn (ti, c));
     }
 }
 
@@ -107,7 +110,7 @@ fft1024_warp (float (&re)[32], float (&im)[32], const float2 *tw, float *xbuf, i
     {
       const int k1 = brev5 (i);
       const float2 w = tw[k1 * 32 + lane];
-      xb[k1 * 33 + lane] = make_float2 (re[i] * w.x - im[i] * w.y, re[i] * w.y + im[i] * w.x);
+      xb[k1 * 33 + lane] = make_float2 (__fmaf_rn (re[i], w.x, -__fmul_rn (im[i], w.y)), __fmaf_rn (re[i], w.y, __fmul_rn (im[i], w.x)));
     }
   __syncwarp();
 #pragma unroll
@@ -151,7 +154,7 @@ unpack_pair (const float (&re)[32], const float (&im)[32], int lane, float& ar, 
 __device__ __forceinline__ float
 db_from_complex (float re, float im, float min_db)
 {
-  const float abs2 = re * re + im * im;
+  const float abs2 = __fmaf_rn (re, re, __fmul_rn (im, im));
   return abs2 > 0.0f ? log2f (abs2) * 3.01029995663981f : min_db;
 }
 

@@ -2,6 +2,7 @@
 // (reference src/wmget.cc:163-1013, src/wavchunkloader.cc:54-239).  FFTs, soft-bit extraction and the
 // Viterbi decoder run on the GPU through the C ABI; pairing / combining logic stays on the host.
 #include "awm_results.hh"
+#include "awm_get_internal.hh"
 #include "awm_speed.hh"
 #include "awm_engine.hh"
 #include "awm_tables.hh"
@@ -245,57 +246,64 @@ ResultSet::print_match_count (const vector<int>& orig_bits)
 
 /* ---------------------------------------------------------------- GPU helpers */
 
-namespace {
+namespace get_detail {
 
-struct VitJob
-{
-  vector<float>     soft;        // raw (un-normalised) soft bits, normalisation happens on the GPU
-  ConvBlockType     block_type;
-  double            time;
-  SyncFinder::Score score;
-  ResultSet::Type   type;
-  Key               key;
-  int               chunk = 0;
-  double            speed = 1;
-};
-
-/* code_decode_soft for every pending code word of a `get` run (A, B and AB mixed, all chunks and keys) in ONE
- * awm_viterbi launch; the decoded patterns go to the result set of the chunk they came from. */
+/* code_decode_soft for a set of code words (A, B and AB mixed) in ONE awm_viterbi launch */
 bool
-run_viterbi_jobs (vector<VitJob>& jobs, vector<ResultSet>& chunk_results)
+viterbi_decode (const vector<const VitJob *>& jobs, vector<uint8_t>& bits, vector<float>& err)
 {
   awm_ctx *ctx = Engine::ctx();
   if (!ctx)
     return false;
+  const int n_msg = int (code_message_bits());        /* the block code word in short payload mode */
+  bits.assign (jobs.size() * n_msg, 0);
+  err.assign (jobs.size(), 0.f);
   if (jobs.empty())
     return true;
-  const int n_msg = int (code_message_bits());        /* the block code word in short payload mode */
   vector<float> raw;
   vector<int> types (jobs.size());
   for (size_t j = 0; j < jobs.size(); j++)
     {
-      raw.insert (raw.end(), jobs[j].soft.begin(), jobs[j].soft.end());
-      types[j] = jobs[j].block_type == ConvBlockType::a ? AWM_BLOCK_A : jobs[j].block_type == ConvBlockType::b ? AWM_BLOCK_B : AWM_BLOCK_AB;
+      raw.insert (raw.end(), jobs[j]->soft.begin(), jobs[j]->soft.end());
+      types[j] = jobs[j]->block_type == ConvBlockType::a ? AWM_BLOCK_A : jobs[j]->block_type == ConvBlockType::b ? AWM_BLOCK_B : AWM_BLOCK_AB;
     }
-  vector<uint8_t> bits (jobs.size() * n_msg);
-  vector<float> err (jobs.size());
   if (awm_viterbi (ctx, raw.data(), jobs.size(), n_msg, types.data(), Params::hard ? 1 : 0, bits.data(), err.data()))
     {
       error ("audiowmark: viterbi decoder failed: %s\n", awm_last_error (ctx));
       return false;
     }
-  for (size_t j = 0; j < jobs.size(); j++)
+  return true;
+}
+
+void
+add_decoded_pattern (const VitJob& job, const uint8_t *bits, float err, ResultSet& chunk_result)
+{
+  const int n_msg = int (code_message_bits());
+  vector<int> bit_vec (bits, bits + n_msg);
+  if (Params::payload_short)
     {
-      const VitJob& job = jobs[j];
-      vector<int> bit_vec (bits.begin() + j * n_msg, bits.begin() + (j + 1) * n_msg);
-      if (Params::payload_short)
-        {
-          bit_vec = short_decode_blk (bit_vec);        /* code_decode_soft, src/shortcode.cc:129-133 */
-          if (bit_vec.empty())
-            continue;
-        }
-      chunk_results[job.chunk].add_pattern (job.key, job.time, job.score, bit_vec, err[j], job.type, job.speed);
+      bit_vec = short_decode_blk (bit_vec);        /* code_decode_soft, src/shortcode.cc:129-133 */
+      if (bit_vec.empty())
+        return;
     }
+  chunk_result.add_pattern (job.key, job.time, job.score, bit_vec, err, job.type, job.speed);
+}
+
+/* every pending code word of a `get` run (all chunks and keys) in one launch; the decoded patterns go to the result set of the
+ * chunk they came from */
+bool
+run_viterbi_jobs (vector<VitJob>& jobs, vector<ResultSet>& chunk_results)
+{
+  vector<const VitJob *> list;
+  for (const auto& j : jobs)
+    list.push_back (&j);
+  vector<uint8_t> bits;
+  vector<float> err;
+  if (!viterbi_decode (list, bits, err))
+    return false;
+  const int n_msg = int (code_message_bits());
+  for (size_t j = 0; j < jobs.size(); j++)
+    add_decoded_pattern (jobs[j], bits.data() + j * n_msg, err[j], chunk_results[jobs[j].chunk]);
   jobs.clear();
   return true;
 }
@@ -322,119 +330,137 @@ decode_raw_bits (const Key& key, const vector<uint64_t>& indices, vector<vector<
   return true;
 }
 
-/* BlockDecoder::run after the soft bits are known (src/wmget.cc:539-701): one job per decoded block, AB pairs, the "all" pattern */
+/* What BlockDecoder::run does once the soft bits of the synchronised blocks are known (src/wmget.cc:539-701), as three separate
+ * steps over one list of decoded blocks (in sync-score order = ascending position):
+ *   single blocks   every valid block is a code word of its own type
+ *   AB pairs        a B block together with the A block that starts one block length before it
+ *   "all"           the longest-scoring chain of alternating blocks, soft bits averaged per type
+ * The selection rules (tolerances, strict comparisons, float accumulation of the chain score) are the reference's: they decide
+ * which patterns are printed. */
+struct DecodedBlock
+{
+  size_t               index;
+  double               quality;
+  ConvBlockType        type;
+  const vector<float> *soft;
+};
+
+ConvBlockType
+other_type (ConvBlockType t)
+{
+  return t == ConvBlockType::a ? ConvBlockType::b : ConvBlockType::a;
+}
+
+/* position in `blocks` of the block of type `want` nearest to sample `target`, among positions >= first and < last, nearer than
+ * `tolerance` samples (the earliest of equally near blocks); -1 if there is none */
+int
+nearest_block (const vector<DecodedBlock>& blocks, size_t first, size_t last, ConvBlockType want, int target, int tolerance)
+{
+  int found = -1, nearest = tolerance;
+  for (size_t j = first; j < last; j++)
+    {
+      const int dist = std::abs (target - int (blocks[j].index));
+      if (blocks[j].type == want && dist < nearest)
+        {
+          found = int (j);
+          nearest = dist;
+        }
+    }
+  return found;
+}
+
+/* chain of alternating blocks that starts at block `head`: after the last member, the block expected k block lengths later
+ * (type flips with odd k) is looked for with k = 1, 2, ... and a tolerance that grows with k; a hit restarts at k = 1 */
+vector<size_t>
+alternating_chain (const vector<DecodedBlock>& blocks, size_t head, size_t block_len)
+{
+  const size_t k_max = lrint (blocks.back().index / double (block_len) + 0.5);
+  vector<size_t> chain { head };
+  for (size_t k = 1; k <= k_max; )
+    {
+      const DecodedBlock& tail = blocks[chain.back()];
+      const int next = nearest_block (blocks, chain.back(), blocks.size(), (k & 1) ? other_type (tail.type) : tail.type,
+                                      int (tail.index + k * block_len), int (k * Params::frame_size / 2));
+      if (next >= 0)
+        {
+          chain.push_back (next);
+          k = 1;
+        }
+      else
+        k++;
+    }
+  return chain;
+}
+
+float
+chain_score (const vector<DecodedBlock>& blocks, const vector<size_t>& chain)
+{
+  float sum = 0;                                  /* single precision like the reference: it breaks near ties the same way */
+  for (size_t b : chain)
+    sum += blocks[b].quality;
+  return sum;
+}
+
 void
 build_block_jobs (const Key& key, const vector<SyncFinder::Score>& sync_scores, const vector<vector<float>>& raw, const vector<int>& valid,
                   int sample_rate, int chunk, double speed, vector<VitJob>& pending)
 {
-  const size_t count = mark_sync_frame_count() + mark_data_frame_count();
-  const size_t block_len = count * Params::frame_size;
-  struct PatternRawBits { size_t index; double quality; vector<float> raw_bit_vec; ConvBlockType block_type; };
-  vector<PatternRawBits> prv;
-  auto add_job = [&] (const vector<float>& soft, ConvBlockType bt, double time, SyncFinder::Score score, ResultSet::Type type)
+  const size_t block_len = (mark_sync_frame_count() + mark_data_frame_count()) * Params::frame_size;
+  auto queue = [&] (const vector<float>& soft, ConvBlockType code, double time, SyncFinder::Score score, ResultSet::Type type)
     {
-      VitJob job { soft, bt, time, score, type, key, chunk, speed };
-      pending.push_back (job);
+      pending.push_back (VitJob { soft, code, time, score, type, key, chunk, speed });
     };
-        for (size_t i = 0; i < sync_scores.size(); i++)
-          if (valid[i])
-            {
-              const auto& sync_score = sync_scores[i];
-              prv.push_back ({ sync_score.index, sync_score.quality, raw[i], sync_score.block_type });
-              add_job (raw[i], sync_score.block_type, double (sync_score.index) / sample_rate, sync_score, ResultSet::Type::BLOCK);
-            }
-        /* AB: a B block with the closest earlier A block one block length before it (within half a frame) */
-        for (size_t i = 0; i < prv.size(); i++)
-          if (prv[i].block_type == ConvBlockType::b)
-            {
-              int best_j = -1, best_abs_dist = Params::frame_size / 2;
-              for (size_t j = 0; j < i; j++)
-                if (prv[j].block_type == ConvBlockType::a)
-                  {
-                    const int abs_dist = std::abs (int (prv[i].index - prv[j].index) - int (block_len));
-                    if (abs_dist < best_abs_dist)
-                      {
-                        best_j = j;
-                        best_abs_dist = abs_dist;
-                      }
-                  }
-              if (best_j >= 0)
-                {
-                  const auto& a = prv[best_j];
-                  const auto& b = prv[i];
-                  vector<float> ab_bits (a.raw_bit_vec.size() * 2);
-                  for (size_t k = 0; k < a.raw_bit_vec.size(); k++)
-                    {
-                      ab_bits[k * 2] = a.raw_bit_vec[k];
-                      ab_bits[k * 2 + 1] = b.raw_bit_vec[k];
-                    }
-                  SyncFinder::Score score_ab { b.index, (a.quality + b.quality) / 2, ConvBlockType::ab };
-                  add_job (ab_bits, ConvBlockType::ab, double (b.index) / sample_rate, score_ab, ResultSet::Type::BLOCK);
-                }
-            }
-        /* all: the chain of blocks at multiples of the block length with alternating types and the largest sync sum */
-        vector<size_t> best_all_blocks;
-        auto sync_sum = [&] (const vector<size_t>& blocks)
-          {
-            float sum = 0;
-            for (auto b : blocks)
-              sum += prv[b].quality;
-            return sum;
-          };
-        for (size_t i = 0; i < prv.size(); i++)
-          {
-            const size_t max_block_idx = lrint (prv.back().index / double (block_len) + 0.5);
-            vector<size_t> all_blocks { i };
-            size_t block_idx = 1;
-            while (block_idx <= max_block_idx)
-              {
-                const size_t expect_start = prv[all_blocks.back()].index + block_idx * block_len;
-                int best_j = -1, best_abs_dist = block_idx * Params::frame_size / 2;
-                auto expect_block_type = prv[all_blocks.back()].block_type;
-                if (block_idx & 1)
-                  expect_block_type = expect_block_type == ConvBlockType::a ? ConvBlockType::b : ConvBlockType::a;
-                for (size_t j = all_blocks.back(); j < prv.size(); j++)
-                  {
-                    const int abs_dist = std::abs (int (expect_start) - int (prv[j].index));
-                    if (abs_dist < best_abs_dist && prv[j].block_type == expect_block_type)
-                      {
-                        best_j = j;
-                        best_abs_dist = abs_dist;
-                      }
-                  }
-                if (best_j >= 0)
-                  {
-                    all_blocks.push_back (best_j);
-                    block_idx = 1;
-                  }
-                else
-                  block_idx++;
-              }
-            if (sync_sum (all_blocks) > sync_sum (best_all_blocks))
-              best_all_blocks = all_blocks;
-          }
-        if (best_all_blocks.size() > 1)
-          {
-            vector<float> raw_all (code_size (ConvBlockType::ab, Params::payload_size));
-            int norm[2] = { 0, 0 };
-            SyncFinder::Score score_all { 0, 0, ConvBlockType::a };
-            for (auto bi : best_all_blocks)
-              {
-                const auto& p = prv[bi];
-                score_all.quality += p.quality;
-                const int ab = p.block_type == ConvBlockType::b ? 1 : 0;
-                for (size_t k = 0; k < p.raw_bit_vec.size(); k++)
-                  raw_all[k * 2 + ab] += p.raw_bit_vec[k];
-                norm[ab]++;
-              }
-            for (size_t k = 0; k < raw_all.size(); k += 2)
-              {
-                raw_all[k]     /= max (norm[0], 1);
-                raw_all[k + 1] /= max (norm[1], 1);
-              }
-            score_all.quality /= norm[0] + norm[1];
-            add_job (raw_all, ConvBlockType::ab, 0.0, score_all, ResultSet::Type::ALL);
-          }
+  vector<DecodedBlock> blocks;
+  for (size_t i = 0; i < sync_scores.size(); i++)
+    if (valid[i])
+      {
+        blocks.push_back ({ sync_scores[i].index, sync_scores[i].quality, sync_scores[i].block_type, &raw[i] });
+        queue (raw[i], sync_scores[i].block_type, double (sync_scores[i].index) / sample_rate, sync_scores[i], ResultSet::Type::BLOCK);
+      }
+  /* ---- AB pairs */
+  for (size_t i = 0; i < blocks.size(); i++)
+    {
+      if (blocks[i].type != ConvBlockType::b)
+        continue;
+      const int partner = nearest_block (blocks, 0, i, ConvBlockType::a, int (blocks[i].index) - int (block_len), Params::frame_size / 2);
+      if (partner < 0)
+        continue;
+      const vector<float>& sa = *blocks[partner].soft, &sb = *blocks[i].soft;
+      vector<float> interleaved (sa.size() * 2);
+      for (size_t k = 0; k < sa.size(); k++)
+        {
+          interleaved[2 * k] = sa[k];
+          interleaved[2 * k + 1] = sb[k];
+        }
+      queue (interleaved, ConvBlockType::ab, double (blocks[i].index) / sample_rate,
+             SyncFinder::Score { blocks[i].index, (blocks[partner].quality + blocks[i].quality) / 2, ConvBlockType::ab }, ResultSet::Type::BLOCK);
+    }
+  /* ---- "all": the chain with the largest quality sum (the first one among equals) */
+  vector<size_t> best;
+  for (size_t head = 0; head < blocks.size(); head++)
+    {
+      const vector<size_t> chain = alternating_chain (blocks, head, block_len);
+      if (chain_score (blocks, chain) > chain_score (blocks, best))
+        best = chain;
+    }
+  if (best.size() > 1)
+    {
+      vector<float> mean_soft (code_size (ConvBlockType::ab, Params::payload_size));
+      int members[2] = { 0, 0 };
+      double quality_sum = 0;
+      for (size_t b : best)
+        {
+          const int slot = blocks[b].type == ConvBlockType::b ? 1 : 0;
+          const vector<float>& soft = *blocks[b].soft;
+          for (size_t k = 0; k < soft.size(); k++)
+            mean_soft[2 * k + slot] += soft[k];
+          members[slot]++;
+          quality_sum += blocks[b].quality;
+        }
+      for (size_t k = 0; k < mean_soft.size(); k++)
+        mean_soft[k] /= max (members[k & 1], 1);
+      queue (mean_soft, ConvBlockType::ab, 0.0, SyncFinder::Score { 0, quality_sum / (members[0] + members[1]), ConvBlockType::a }, ResultSet::Type::ALL);
+    }
 }
 
 /* ---------------------------------------------------------------- BlockDecoder (src/wmget.cc:492-735) */
@@ -713,7 +739,9 @@ decode_chunk (vector<VitJob>& pending, int chunk, string& debug_sync, const vect
   return 0;
 }
 
-} // namespace
+} // namespace get_detail
+
+using namespace get_detail;
 
 /* BlockDecoder job list of one chunk as flat records (for the multi-GPU driver):
  * u8 code_type (AWM_BLOCK_*), u8 pattern_type (ResultSet::Type), u8 score_block_type, u8 pad, f64 time, u64 index, f64 quality, u32 n_soft, f32 soft[] */
