@@ -13,6 +13,7 @@
 #include "awm_embed_strip.cuh"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <map>
 #include <thread>
@@ -107,6 +108,13 @@ struct awm_ctx
   DevBuf blk_start, D, raw;          // decode
   DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
   DevBuf emb_in, emb_out, emb_in16, emb_out16, peaks, snr;
+
+  // multi-GPU exchange (awm_dist_*): NCCL communicator of the sharded run + staging buffers
+  void *nccl_comm = nullptr;
+  int dist_rank = 0, dist_world = 1;
+  DevBuf dist_send, dist_recv;
+  unsigned char *dist_hsend = nullptr, *dist_hhdr = nullptr;
+  size_t dist_hsend_cap = 0;
 
   // resampler / speed scan
   struct CoefTab { DevBuf buf; int h = 0; };
@@ -245,6 +253,8 @@ set_smem (awm_ctx *ctx, K kernel, size_t bytes)
 
 } // namespace
 
+void nccl_destroy (void *comm);       // defined with the awm_dist_* functions below
+
 extern "C" {
 
 int
@@ -289,6 +299,12 @@ awm_destroy (awm_ctx *ctx)
                      &ctx->win512, &ctx->sp_clip, &ctx->sp_sub, &ctx->sp_mags, &ctx->sp_mag_jobs, &ctx->sp_cmp_jobs, &ctx->sp_best };
   for (DevBuf *b : bufs)
     b->release();
+  ctx->dist_send.release();
+  ctx->dist_recv.release();
+  if (ctx->dist_hsend) cudaFreeHost (ctx->dist_hsend);
+  if (ctx->dist_hhdr) cudaFreeHost (ctx->dist_hhdr);
+  if (ctx->nccl_comm)
+    nccl_destroy (ctx->nccl_comm);
   for (auto& ct : ctx->coef_cache)
     ct.second.buf.release();
   for (auto& pf : ctx->pref)
@@ -303,6 +319,7 @@ awm_destroy (awm_ctx *ctx)
       for (SyncTab& s : k.sync)
         {
           s.ent.release();
+          s.masks.release();
           s.off.release();
           s.sorted.release();
           s.groups.release();
@@ -1443,6 +1460,166 @@ awm_sync_refine_offsets (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_firs
     return fail (ctx, "awm_sync_refine_offsets: bad arguments");
   return refine_impl (ctx, key_slot, mode, wav_first, wav_last, water_delta, const_cast<awm_search_score *> (scores), n_scores, exact ? 1 : 0,
                       quality_out, valid_out);
+}
+
+/* ---------------------------------------------------------------- multi-GPU exchange
+ * NCCL is loaded on first use (dlopen), so that single-GPU users of the library do not depend on it. */
+namespace {
+
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi
+{
+  void *lib = nullptr;
+  int (*GetUniqueId) (NcclUniqueId *) = nullptr;
+  int (*CommInitRank) (void **, int, NcclUniqueId, int) = nullptr;
+  int (*AllGather) (const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy) (void *) = nullptr;
+  const char *(*GetErrorString) (int) = nullptr;
+  std::string error;
+};
+
+NcclApi&
+nccl_api()
+{
+  static NcclApi api;
+  if (api.lib || !api.error.empty())
+    return api;
+  for (const char *name : { "libnccl.so.2", "libnccl.so" })
+    if ((api.lib = dlopen (name, RTLD_NOW | RTLD_GLOBAL)))
+      break;
+  if (!api.lib)
+    {
+      api.error = std::string ("cannot load libnccl.so.2: ") + dlerror();
+      return api;
+    }
+  auto sym = [&] (const char *n) { void *p = dlsym (api.lib, n); if (!p) api.error = std::string ("libnccl: missing symbol ") + n; return p; };
+  api.GetUniqueId = reinterpret_cast<decltype (api.GetUniqueId)> (sym ("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype (api.CommInitRank)> (sym ("ncclCommInitRank"));
+  api.AllGather = reinterpret_cast<decltype (api.AllGather)> (sym ("ncclAllGather"));
+  api.CommDestroy = reinterpret_cast<decltype (api.CommDestroy)> (sym ("ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<decltype (api.GetErrorString)> (sym ("ncclGetErrorString"));
+  return api;
+}
+
+} // namespace
+
+} // extern "C"
+
+void
+nccl_destroy (void *comm)
+{
+  NcclApi& n = nccl_api();
+  if (n.CommDestroy)
+    n.CommDestroy (comm);
+}
+
+extern "C" {
+
+int
+awm_dist_unique_id (unsigned char id_out[128])
+{
+  NcclApi& n = nccl_api();
+  if (!n.error.empty() || !id_out)
+    return 1;
+  NcclUniqueId id;
+  if (n.GetUniqueId (&id))
+    return 1;
+  memcpy (id_out, id.internal, 128);
+  return 0;
+}
+
+int
+awm_dist_init (awm_ctx *ctx, int rank, int world, const unsigned char id[128])
+{
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world)
+    return fail (ctx, "awm_dist_init: bad arguments");
+  NcclApi& n = nccl_api();
+  if (!n.error.empty())
+    return fail (ctx, "awm_dist_init: %s", n.error.c_str());
+  CK (cudaSetDevice (ctx->device));
+  if (ctx->nccl_comm)
+    {
+      n.CommDestroy (ctx->nccl_comm);
+      ctx->nccl_comm = nullptr;
+    }
+  NcclUniqueId uid;
+  memcpy (uid.internal, id, 128);
+  const int rc = n.CommInitRank (&ctx->nccl_comm, world, uid, rank);
+  if (rc)
+    return fail (ctx, "ncclCommInitRank: %s", n.GetErrorString (rc));
+  ctx->dist_rank = rank;
+  ctx->dist_world = world;
+  return 0;
+}
+
+int
+awm_dist_world (const awm_ctx *ctx, int *rank, int *world)
+{
+  if (!ctx)
+    return 1;
+  if (rank) *rank = ctx->dist_rank;
+  if (world) *world = ctx->nccl_comm ? ctx->dist_world : 1;
+  return 0;
+}
+
+int
+awm_dist_allgather (awm_ctx *ctx, const void *send, size_t send_bytes, size_t slot_bytes, void *recv, size_t *recv_bytes)
+{
+  if (!ctx || (send_bytes && !send) || !recv || !recv_bytes || slot_bytes < 16 || slot_bytes % 16)
+    return fail (ctx, "awm_dist_allgather: bad arguments");
+  const int world = ctx->nccl_comm ? ctx->dist_world : 1;
+  if (world == 1)
+    {
+      if (send_bytes + 8 > slot_bytes)
+        return fail (ctx, "awm_dist_allgather: payload of %zu bytes does not fit a slot of %zu", send_bytes, slot_bytes);
+      memcpy (recv, send, send_bytes);
+      recv_bytes[0] = send_bytes;
+      return 0;
+    }
+  NcclApi& n = nccl_api();
+  CK (cudaSetDevice (ctx->device));
+  CK (ctx->dist_send.reserve (slot_bytes));
+  CK (ctx->dist_recv.reserve (slot_bytes * world));
+  if (ctx->dist_hsend_cap < slot_bytes)
+    {
+      if (ctx->dist_hsend) cudaFreeHost (ctx->dist_hsend);
+      if (ctx->dist_hhdr) cudaFreeHost (ctx->dist_hhdr);
+      ctx->dist_hsend = ctx->dist_hhdr = nullptr;
+      ctx->dist_hsend_cap = 0;
+      CK (cudaMallocHost (reinterpret_cast<void **> (&ctx->dist_hsend), slot_bytes));
+      CK (cudaMallocHost (reinterpret_cast<void **> (&ctx->dist_hhdr), 8 * 1024));
+      ctx->dist_hsend_cap = slot_bytes;
+    }
+  /* slot = [u64 payload length | payload]; a payload that does not fit is announced by its length alone, every rank then sees
+   * the same lengths and reports the same failure (the caller repeats the exchange with a larger slot) */
+  const uint64_t len = send_bytes;
+  const bool fits = send_bytes + 8 <= slot_bytes;
+  memcpy (ctx->dist_hsend, &len, 8);
+  if (fits && send_bytes)
+    memcpy (ctx->dist_hsend + 8, send, send_bytes);
+  CK (cudaMemcpyAsync (ctx->dist_send.p, ctx->dist_hsend, fits ? 8 + send_bytes : 8, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = n.AllGather (ctx->dist_send.p, ctx->dist_recv.p, slot_bytes, 0 /* ncclChar */, ctx->nccl_comm, ctx->stream);
+  if (rc)
+    return fail (ctx, "ncclAllGather: %s", n.GetErrorString (rc));
+  ctx->launches++;
+  CK (cudaMemcpy2DAsync (ctx->dist_hhdr, 8, ctx->dist_recv.p, slot_bytes, 8, world, cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  bool all_fit = true;
+  for (int r = 0; r < world; r++)
+    {
+      uint64_t l;
+      memcpy (&l, ctx->dist_hhdr + 8 * r, 8);
+      recv_bytes[r] = size_t (l);
+      all_fit = all_fit && l + 8 <= slot_bytes;
+    }
+  if (!all_fit)
+    return 2;                                   /* recv_bytes holds the lengths: repeat with slot_bytes >= max + 8 */
+  for (int r = 0; r < world; r++)
+    if (recv_bytes[r])
+      CK (cudaMemcpyAsync (static_cast<unsigned char *> (recv) + size_t (r) * slot_bytes, ctx->dist_recv.as<unsigned char>() + size_t (r) * slot_bytes + 8,
+                           recv_bytes[r], cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaStreamSynchronize (ctx->stream));
+  return 0;
 }
 
 /* ---------------------------------------------------------------- block decode */

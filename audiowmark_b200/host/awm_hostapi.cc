@@ -1,6 +1,7 @@
 // awm_hostapi.cc -- plain C entry points over the host-side C++ (tables, add, get) so that the parity
 // tests and bench.py can drive exactly what the CLI runs.  Table functions are pure host code (no GPU).
 #include "awm_results.hh"
+#include "awm_balanced.hh"
 #include "awm_speed.hh"
 #include "awm_engine.hh"
 #include "awm_tables.hh"
@@ -422,6 +423,196 @@ awmh_chunk_geometry (int sample_rate, uint64_t *max_frames, uint64_t *overlap_fr
   chunk_geometry (sample_rate, m, o);
   *max_frames = m;
   *overlap_frames = o;
+}
+
+/* ---- sharded `get`: one long stream over several GPUs (awm_balanced.hh) --------------------------------------------------- */
+
+int
+awmh_dist_unique_id (unsigned char id_out[128])
+{
+  return awm_dist_unique_id (id_out);
+}
+
+/* join the NCCL communicator of the job (the id comes from rank 0's awmh_dist_unique_id, handed round by the launcher) */
+int
+awmh_dist_init (int rank, int world, const unsigned char id[128])
+{
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx)
+    return 1;
+  if (awm_dist_init (ctx, rank, world, id))
+    {
+      error ("audiowmark: %s\n", awm_last_error (ctx));
+      return 1;
+    }
+  return 0;
+}
+
+/* every rank calls this with its part of the stream ([pcm_start, pcm_start + pcm_frames) of n_total frames; float or 16 bit PCM,
+ * host or device memory); rank 0 receives the --json document (n_patterns >= 0), the other ranks n_patterns = -1 */
+int
+awmh_balanced_get (const unsigned char *key16, const void *pcm, int is_s16, uint64_t pcm_start, uint64_t pcm_frames, uint64_t n_total, int n_channels,
+                   int sample_rate, char *json_out, size_t json_cap, int *n_patterns)
+{
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx)
+    return 1;
+  int rank = 0, world = 1;
+  awm_dist_world (ctx, &rank, &world);
+  balanced::Get job (rank, world, n_total, is_s16 ? nullptr : static_cast<const float *> (pcm), is_s16 ? static_cast<const int16_t *> (pcm) : nullptr,
+                     pcm_start, pcm_frames, n_channels, sample_rate, make_key (key16, ""));
+  if (!job.ok())
+    return 1;
+  std::vector<unsigned char> recv;
+  std::vector<size_t> lens (world);
+  size_t slot = 256 * 1024;
+  auto exchange = [&] (const std::string& mine, std::vector<std::string>& all)
+    {
+      for (;;)
+        {
+          recv.resize (slot * world);
+          const int rc = awm_dist_allgather (ctx, mine.data(), mine.size(), slot, recv.data(), lens.data());
+          if (rc == 2)                               // somebody's payload did not fit: every rank saw the same lengths
+            {
+              slot = (*std::max_element (lens.begin(), lens.end()) + 8 + 4095) / 4096 * 4096;
+              continue;
+            }
+          if (rc)
+            {
+              error ("audiowmark: %s\n", awm_last_error (ctx));
+              return false;
+            }
+          break;
+        }
+      all.resize (world);
+      for (int r = 0; r < world; r++)
+        all[r].assign (reinterpret_cast<const char *> (recv.data()) + size_t (r) * slot, lens[r]);
+      return true;
+    };
+  ResultSet result_set;
+  if (!job.run (exchange, result_set))
+    return 1;
+  if (rank != 0)
+    {
+      if (n_patterns)
+        *n_patterns = -1;
+      return 0;
+    }
+  return result_json (result_set, n_total, json_out, json_cap, n_patterns);
+}
+
+/* the stages one by one, for tests that run several ranks in one process on one GPU (tests/test_gpu_sharding.py):
+ * stage 0 peaks, 1 select (-> retry list), 2 peaks again for the retry list in in[0], 3 refine + soft bits, 4 viterbi, 5 merge (-> JSON) */
+void *
+awmh_bg_create (const unsigned char *key16, int rank, int world, const float *pcm, uint64_t pcm_start, uint64_t pcm_frames, uint64_t n_total, int n_channels, int sample_rate)
+{
+  balanced::Get *g = new balanced::Get (rank, world, n_total, pcm, nullptr, pcm_start, pcm_frames, n_channels, sample_rate, make_key (key16, ""));
+  if (!g->ok())
+    {
+      delete g;
+      return nullptr;
+    }
+  return g;
+}
+
+void
+awmh_bg_destroy (void *h)
+{
+  delete static_cast<balanced::Get *> (h);
+}
+
+int
+awmh_bg_stage (void *h, int stage, const unsigned char *const *in, const size_t *in_len, int n_in, uint64_t n_total, unsigned char *out, size_t cap, size_t *out_len)
+{
+  balanced::Get *g = static_cast<balanced::Get *> (h);
+  std::vector<std::string> all;
+  for (int i = 0; i < n_in; i++)
+    all.emplace_back (reinterpret_cast<const char *> (in[i]), in_len[i]);
+  std::string res;
+  bool ok = false;
+  auto parse_floors = [] (const std::string& s)
+    {
+      std::map<int, double> m;
+      for (size_t pos = 0; pos + 12 <= s.size(); pos += 12)
+        {
+          int32_t c; double f;
+          memcpy (&c, s.data() + pos, 4); memcpy (&f, s.data() + pos + 4, 8);
+          m[c] = f;
+        }
+      return m;
+    };
+  switch (stage)
+    {
+    case 0: ok = g->stage_peaks ({}, res); break;
+    case 1:
+      {
+        std::map<int, double> retry;
+        ok = g->stage_select (all, retry);
+        for (const auto& kv : retry)
+          {
+            const int32_t c = kv.first; const double f = kv.second;
+            res.append (reinterpret_cast<const char *> (&c), 4);
+            res.append (reinterpret_cast<const char *> (&f), 8);
+          }
+        break;
+      }
+    case 2: ok = g->stage_peaks (parse_floors (all.empty() ? std::string() : all[0]), res); break;
+    case 3: ok = g->stage_refine_decode (res); break;
+    case 4: ok = g->stage_viterbi (all, res); break;
+    case 5:
+      {
+        ResultSet rs;
+        ok = g->stage_merge (all, rs);
+        if (ok)
+          {
+            char *buf = nullptr;
+            size_t len = 0;
+            FILE *f = open_memstream (&buf, &len);
+            rs.print_json (f, size_t (lrint (double (n_total) / Params::mark_sample_rate)));
+            fclose (f);
+            res.assign (buf, len);
+            free (buf);
+          }
+        break;
+      }
+    }
+  if (!ok)
+    return 1;
+  *out_len = res.size();
+  if (res.size() > cap)
+    return -2;
+  if (!res.empty())
+    memcpy (out, res.data(), res.size());
+  return 0;
+}
+
+/* the plan functions for CPU tests: chunk walk, slices of a rank, owner of an index */
+int
+awmh_bg_plan (uint64_t n_total, int sample_rate, int rank, int world, double *chunks /* [max][3] first, count, time offset */, int max_chunks, int *n_chunks,
+              int64_t *slices /* [max][7] chunk, sa, sb, a, b, lo, hi */, int max_slices, int *n_slices)
+{
+  const auto plan = balanced::chunk_plan (n_total, sample_rate);
+  *n_chunks = int (plan.size());
+  for (int c = 0; c < int (plan.size()) && c < max_chunks; c++)
+    {
+      chunks[3 * c] = double (plan[c].first);
+      chunks[3 * c + 1] = double (plan[c].count);
+      chunks[3 * c + 2] = plan[c].time_offset;
+    }
+  const auto sl = balanced::rank_slices (plan, rank, world, n_total);
+  *n_slices = int (sl.size());
+  for (int i = 0; i < int (sl.size()) && i < max_slices; i++)
+    {
+      const int64_t v[7] = { sl[i].chunk, sl[i].sa, sl[i].sb, sl[i].a, sl[i].b, int64_t (sl[i].lo), int64_t (sl[i].hi) };
+      memcpy (slices + 7 * i, v, sizeof (v));
+    }
+  return 0;
+}
+
+int
+awmh_bg_owner (uint64_t n_total, int sample_rate, int world, int chunk, uint64_t index)
+{
+  return balanced::owner_of (balanced::chunk_plan (n_total, sample_rate), n_total, world, chunk, index);
 }
 
 /* ---- stage-level access for the frame-balanced multi-GPU driver (audiowmark_b200/sharding.py) ---------------- */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16", "awmh_short_encode", "awmh_short_decode", "awmh_sync_trace", "awmh_sync_trace_fetch"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16", "awmh_short_encode", "awmh_short_decode", "awmh_sync_trace", "awmh_sync_trace_fetch", "awmh_dist_unique_id", "awmh_dist_init", "awmh_balanced_get", "awmh_bg_create", "awmh_bg_destroy", "awmh_bg_stage", "awmh_bg_plan", "awmh_bg_owner"]
 
 _lib = None
 
@@ -344,6 +344,101 @@ def merge_chunks(blobs, time_offsets, total_seconds: float, keys=None, names=Non
     if rc:
         raise RuntimeError("awmh_merge_chunks failed (rc=%d)" % rc)
     return json.loads(out.value.decode())
+
+
+# ---- sharded get: one long stream over several GPUs, one process per GPU (host/awm_balanced.hh) -----------------------------
+
+def dist_unique_id() -> bytes:
+    """NCCL unique id of a new job (rank 0 creates it, the launcher hands it to every rank)"""
+    buf = ctypes.create_string_buffer(128)
+    if load().awmh_dist_unique_id(buf):
+        raise RuntimeError("NCCL is not available")
+    return buf.raw
+
+
+def dist_init(rank: int, world: int, unique_id: bytes):
+    """join the job's NCCL communicator (exchanges of the sharded get run on the context stream)"""
+    if load().awmh_dist_init(ctypes.c_int(rank), ctypes.c_int(world), ctypes.c_char_p(unique_id)):
+        raise RuntimeError("awmh_dist_init failed; see stderr")
+
+
+def dist_init_from_torch():
+    """the usual launcher: torch.distributed is up (torchrun); rank 0's id is broadcast through it"""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(dist_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    dist_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+
+def balanced_get(pcm, pcm_start: int, n_total: int, key=None, n_frames=None, channels=None, sample_rate=44100):
+    """this rank's part of the stream (numpy float32 / int16 [n, ch], or a float32 device pointer) -> the --json document on rank 0,
+    None on the other ranks"""
+    is_s16 = 0
+    if isinstance(pcm, np.ndarray):
+        if pcm.dtype == np.int16:
+            pcm, is_s16 = np.ascontiguousarray(pcm), 1
+        else:
+            pcm = np.ascontiguousarray(pcm, np.float32)
+        n_frames, channels = pcm.shape
+    cap = 1 << 22
+    buf = _outbuf("get", cap)
+    n_pat = ctypes.c_int()
+    rc = load().awmh_balanced_get(_key(key), _ptr(pcm), ctypes.c_int(is_s16), ctypes.c_uint64(pcm_start), ctypes.c_uint64(n_frames), ctypes.c_uint64(n_total),
+                                  ctypes.c_int(channels), ctypes.c_int(sample_rate), buf, ctypes.c_size_t(cap), ctypes.byref(n_pat))
+    if rc:
+        raise RuntimeError("awmh_balanced_get failed (rc=%d); see stderr" % rc)
+    return json.loads(buf.value.decode()) if n_pat.value >= 0 else None
+
+
+class BalancedStages:
+    """one rank of the sharded get with the stages callable one by one (tests run several ranks in one process on one GPU)"""
+
+    def __init__(self, rank, world, n_total, pcm: np.ndarray, pcm_start, key=None, sample_rate=44100):
+        self.pcm = np.ascontiguousarray(pcm, np.float32)
+        self.n_total = n_total
+        L = load()
+        L.awmh_bg_create.restype = ctypes.c_void_p
+        self.h = L.awmh_bg_create(_key(key), ctypes.c_int(rank), ctypes.c_int(world), _ptr(self.pcm), ctypes.c_uint64(pcm_start), ctypes.c_uint64(self.pcm.shape[0]),
+                                  ctypes.c_uint64(n_total), ctypes.c_int(self.pcm.shape[1]), ctypes.c_int(sample_rate))
+        if not self.h:
+            raise RuntimeError("awmh_bg_create failed; see stderr")
+
+    def stage(self, number: int, payloads=()) -> bytes:
+        n = len(payloads)
+        arr = (ctypes.c_char_p * max(n, 1))(*[bytes(p) for p in payloads]) if n else None
+        lens = (ctypes.c_size_t * max(n, 1))(*[len(p) for p in payloads])
+        cap = 1 << 24
+        out = _outbuf("bg", cap)
+        out_len = ctypes.c_size_t()
+        rc = load().awmh_bg_stage(ctypes.c_void_p(self.h), ctypes.c_int(number), arr, lens, ctypes.c_int(n), ctypes.c_uint64(self.n_total), out, ctypes.c_size_t(cap),
+                                  ctypes.byref(out_len))
+        if rc:
+            raise RuntimeError("awmh_bg_stage %d failed (rc=%d)" % (number, rc))
+        return out.raw[:out_len.value]
+
+    def close(self):
+        if self.h:
+            load().awmh_bg_destroy(ctypes.c_void_p(self.h))
+            self.h = None
+
+
+def balanced_plan(n_total: int, rank: int, world: int, sample_rate=44100):
+    """-> (chunks [(first, count, time offset)], slices [(chunk, sa, sb, a, b, lo, hi)]) as the C++ driver computes them"""
+    chunks = np.zeros((64, 3), np.float64)
+    slices = np.zeros((64, 7), np.int64)
+    nc, ns = ctypes.c_int(), ctypes.c_int()
+    load().awmh_bg_plan(ctypes.c_uint64(n_total), ctypes.c_int(sample_rate), ctypes.c_int(rank), ctypes.c_int(world), _ptr(chunks), ctypes.c_int(64), ctypes.byref(nc),
+                        _ptr(slices), ctypes.c_int(64), ctypes.byref(ns))
+    return [(int(a), int(b), float(t)) for a, b, t in chunks[:nc.value]], [tuple(int(v) for v in row) for row in slices[:ns.value]]
+
+
+def balanced_owner(n_total: int, world: int, chunk: int, index: int, sample_rate=44100) -> int:
+    return load().awmh_bg_owner(ctypes.c_uint64(n_total), ctypes.c_int(sample_rate), ctypes.c_int(world), ctypes.c_int(chunk), ctypes.c_uint64(index))
 
 
 def engine_ctx() -> int:

@@ -211,6 +211,20 @@ def main_reference(args):
 
 # ----------------------------------------------------------------------------- GPU arm
 
+def bind_to_gpu_numa_node(gpu_index):
+    """8 ranks pulling their PCM through one socket's memory controllers was the end-to-end bottleneck of the 8 GPU run (GPUs 0-3 hang
+    off NUMA node 0, 4-7 off node 1): restrict this process to the CPUs NVML reports as local to its GPU, so that first-touch places the
+    pinned buffers there.  Best effort: returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return "cpu affinity set to the GPU's local CPUs (%d)" % len(os.sched_getaffinity(0))
+    except Exception as e:
+        return "not bound: %s" % e
+
+
 def main_gpu(args):
     import numpy as np
     import torch
@@ -231,17 +245,20 @@ def main_gpu(args):
             torch.cuda.set_device(local)
             dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
             torch.cuda.synchronize()
+            H.set_params(gpu_device=local)
+            H.dist_init_from_torch()          # NCCL communicator of the C++ sharded get (its exchanges run on the context stream)
         finally:
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)       # pinned buffers and the host threads of this rank on the GPU's own NUMA node
+    H.set_params(gpu_device=local)
 
     from audiowmark_b200 import sharding as S
     minutes = args.minutes if args.minutes else 60.0
     n = int(minutes * 60 * RATE)          # PCM frames per GPU (weak scaling: the stream is world * n frames long)
     ch = 2
-    H.set_params(gpu_device=local)
     n_total = n * world
     mx, ov = H.chunk_geometry(RATE)
     plan = S.chunk_plan(n_total, mx, ov, RATE)
@@ -292,21 +309,19 @@ def main_gpu(args):
             H.add_s16(x16_host.numpy(), PAYLOAD, None, y16_host.numpy())
             return H.get_s16(y16_host.numpy())
     else:
-        def sharded(xp, ypcm):
-            H.add(xp, PAYLOAD, None, ypcm if not isinstance(ypcm, int) else ypcm, n_loc, ch, first_frame_number=ffn)
-            job = S.BalancedGet(rank, world, n_total, ypcm, e0, n_loc, ch)
-            return job.run(lambda payload: S.allgather_bytes(payload, device=dev))
-
+        # one N-hour stream: `add` by frame blocks with halo (bit identical to the unsharded run), `get` by the C++ sharded driver
+        # (host/awm_balanced.cc): three ncclAllGather exchanges of small lists, no PCM crosses NVLink
         def step_resident():
-            return sharded(x_dev.data_ptr(), y_dev.data_ptr())
+            H.add(x_dev.data_ptr(), PAYLOAD, None, y_dev.data_ptr(), n_loc, ch, first_frame_number=ffn)
+            return H.balanced_get(y_dev.data_ptr(), e0, n_total, n_frames=n_loc, channels=ch)
 
         def step_e2e():
-            return sharded(x_host.numpy(), y_host.numpy())
+            H.add(x_host.numpy(), PAYLOAD, None, y_host.numpy(), first_frame_number=ffn)
+            return H.balanced_get(y_host.numpy(), e0, n_total)
 
         def step_e2e_s16():
             H.add_s16(x16_host.numpy(), PAYLOAD, None, y16_host.numpy(), first_frame_number=ffn)
-            job = S.BalancedGet(rank, world, n_total, y16_host.numpy(), e0, n_loc, ch)
-            return job.run(lambda payload: S.allgather_bytes(payload, device=dev))
+            return H.balanced_get(y16_host.numpy(), e0, n_total)
 
     def check(doc):
         if doc is None:                       # sharded run: the merged result lives on rank 0
@@ -382,6 +397,28 @@ def main_gpu(args):
     if clk is not None:
         clk["window"] = "warm-up + timed resident steps + e2e steps (nvidia-smi -lms 20)"
 
+    sharded_equals_single = None
+    if world > 1:
+        if rank == 0:
+            # the whole N-hour stream once more on this GPU alone (the input is a pure function of the position): the merged document
+            # of the sharded run has to be the single-GPU document, pattern for pattern
+            try:
+                xf = torch.empty((n_total, ch), device=dev, dtype=torch.float32)
+                for b in range(0, (n_total - 1) // BLK + 1):
+                    g.manual_seed(1234 + b)
+                    blk = torch.rand((BLK, ch), device=dev, generator=g, dtype=torch.float32) - 0.5
+                    hi = min(n_total, (b + 1) * BLK)
+                    xf[b * BLK:hi] = blk[:hi - b * BLK]
+                del blk
+                yf = torch.empty_like(xf)
+                torch.cuda.synchronize()
+                H.add(xf.data_ptr(), PAYLOAD, None, yf.data_ptr(), n_total, ch)
+                single = H.get(yf.data_ptr(), n_frames=n_total, channels=ch)
+                sharded_equals_single = bool(single == doc)
+                del xf, yf
+            except Exception as e:
+                sharded_equals_single = "check failed: %s" % e
+        barrier()
     det = torch.tensor([n_real, int(ok), int(ok2)], device=dev, dtype=torch.int64)
     if world > 1:
         gathered = [torch.zeros_like(det) for _ in range(world)]
@@ -495,10 +532,11 @@ def main_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%g min stereo 44.1 kHz embed+detect per GPU (BASELINE.json configs[1]%s)" % (minutes, "" if minutes == 60 else ", shortened"),
                    "pcm_frames_per_gpu": n, "channels": ch, "payload_bits": 128, "get_chunks": "30 min, 134.4 s overlap",
-                   "parallelism": ("one %d h stream (%d chunks): every rank owns an equal span of positions -- `add` by frame blocks with halo, `get` by start-frame slices of each chunk; 4 small result gathers, no PCM exchanged" % (world, len(plan))) if world > 1 else "1 GPU",
+                   "parallelism": ("one %d h stream (%d chunks): every rank owns an equal span of positions -- `add` by frame blocks with halo, `get` by start-frame slices of each chunk (C++ driver, 3 ncclAllGather exchanges of small lists, no PCM exchanged)" % (world, len(plan))) if world > 1 else "1 GPU",
                    "l2": "inputs (%.2f GB per pass) larger than L2" % (n * ch * 4 / 1e9)},
         "analysis_frames_per_s": value / 1024.0,
         "payload_ok": bool(all(d[1] for d in det_all)), "detections": det_all[0][0],
+        "sharded_equals_single_gpu": sharded_equals_single,
         # headline e2e: 16 bit PCM host buffers in and out -- what the WAV files of the reference arm hold; the int <-> float conversions of
         # SFInputStream / SFOutputStream run on the device (bit identical to converting on the host, tests/test_gpu_e2e.py)
         "e2e": {"value": e2e16_value, "unit": "PCM frames/s", "ms_per_step": ms_e2e16 / args.steps,
@@ -515,6 +553,7 @@ def main_gpu(args):
         "roofline": roofline,
         "kernels": kernels,
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
+        "numa": numa,
         "cpu_baseline": cpu,
         "clocks": clk,
     }

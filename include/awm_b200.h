@@ -236,6 +236,19 @@ int awm_speed_scan (awm_ctx *ctx, int key_slot, const float *clip, size_t clip_f
                     double seconds, const double *centers, int n_centers, const double *relative_speeds, int n_relative,
                     double water_delta, double *quality_out);
 
+/* ---- multi-GPU exchange for the sharded `get` (one process per GPU) ------------------------------------------------------
+ * The reference has no counterpart: its thread pool shares one address space.  Here the ranks of a job exchange the small
+ * per-chunk lists of the search (peaks, refined scores + soft bits, decoded words) with ncclAllGather on the context stream;
+ * no PCM ever crosses NVLink.  awm_dist_unique_id: rank 0 creates the NCCL id, the launcher hands it to every rank (bench.py
+ * broadcasts it with torch.distributed); awm_dist_init joins the communicator; awm_dist_allgather: every rank contributes
+ * send_bytes (<= slot_bytes - 8) and receives rank r's bytes at recv + r * slot_bytes, its length in recv_bytes[r].  Returns 2
+ * when some rank's payload did not fit (recv_bytes then holds all lengths: repeat with a larger slot; every rank sees the same).
+ * Without awm_dist_init the "world" is this process alone and the call degenerates to a copy. */
+int awm_dist_unique_id (unsigned char id_out[128]);
+int awm_dist_init (awm_ctx *ctx, int rank, int world, const unsigned char id[128]);
+int awm_dist_world (const awm_ctx *ctx, int *rank, int *world);
+int awm_dist_allgather (awm_ctx *ctx, const void *send, size_t send_bytes, size_t slot_bytes, void *recv, size_t *recv_bytes);
+
 #ifdef __cplusplus
 }
 #endif

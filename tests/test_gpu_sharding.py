@@ -1,5 +1,7 @@
 """GPU: sharded runs reproduce the single-process result exactly (simulated ranks on one GPU; the collective itself is
 covered on CPU with gloo in test_sharding_cpu.py)."""
+import json
+
 import numpy as np
 import pytest
 
@@ -66,7 +68,9 @@ def test_pipelined_host_paths_equal_device_paths():
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_frame_balanced_get_equals_single_process(world):
     """every rank searches an equal share of the start frames of every chunk; per-chunk decisions are taken on the
-    gathered lists -- the merged result must be the single-process one, digit for digit."""
+    gathered lists -- the merged result must be the single-process one, digit for digit.  The C++ driver
+    (host/awm_balanced.cc) runs here stage by stage, the exchanges are simulated in lock step (the product path uses
+    ncclAllGather; bench.py checks that one on real ranks)."""
     x = T.noise(700.0, 2, seed=22)
     H.set_params(chunk_size_min=4.0)
     y = H.add(x, T.PAYLOAD)
@@ -74,21 +78,35 @@ def test_frame_balanced_get_equals_single_process(world):
     n = y.shape[0]
     ranks = []
     for r in range(world):
-        mx, ov = H.chunk_geometry(44100)
-        sl = S.rank_slices(S.chunk_plan(n, mx, ov), r, world, n)
-        lo, hi = min(s.lo for s in sl), max(s.hi for s in sl)
-        ranks.append(S.BalancedGet(r, world, n, y[lo:hi], lo, hi - lo, 2))
-    # lock-step simulation of the collectives
-    pay = [rk.stage_peaks() for rk in ranks]
-    retry = [rk.stage_select(pay) for rk in ranks]
-    assert all(rt == retry[0] for rt in retry)
-    if retry[0]:
-        pay = [rk.stage_peaks(retry[0]) for rk in ranks]
-        [rk.stage_select(pay) for rk in ranks]
-    pay = [rk.stage_refine() for rk in ranks]
-    [rk.stage_final(pay) for rk in ranks]
-    pay = [rk.stage_decode() for rk in ranks]
-    pay = [rk.stage_viterbi(pay) for rk in ranks]
-    docs = [rk.stage_merge(pay) for rk in ranks]
-    assert all(d == doc for d in docs)
-    H.set_params()
+        _, slices = H.balanced_plan(n, r, world)
+        lo, hi = min(s[5] for s in slices), max(s[6] for s in slices)
+        ranks.append(H.BalancedStages(r, world, n, y[lo:hi], lo))
+    try:
+        pay = [rk.stage(0) for rk in ranks]                          # peaks
+        retry = [rk.stage(1, pay) for rk in ranks]                   # select
+        assert all(rt == retry[0] for rt in retry)
+        if retry[0]:
+            pay = [rk.stage(2, [retry[0]]) for rk in ranks]
+            assert all(rk.stage(1, pay) == b"" for rk in ranks)
+        pay = [rk.stage(3) for rk in ranks]                          # refine + soft bits
+        pay = [rk.stage(4, pay) for rk in ranks]                     # viterbi (jobs dealt round-robin)
+        docs = [json.loads(rk.stage(5, pay).decode()) for rk in ranks]
+        assert all(d == doc for d in docs)
+    finally:
+        for rk in ranks:
+            rk.close()
+        H.set_params()
+
+
+def test_balanced_get_entry_point_single_rank():
+    """hostapi.balanced_get without a communicator is a world of one: same document as hostapi.get, for float and 16 bit PCM"""
+    x = T.noise(300.0, 2, seed=24)
+    H.set_params(chunk_size_min=4.0)
+    try:
+        y = H.add(x, T.PAYLOAD)
+        assert H.balanced_get(y, 0, y.shape[0]) == H.get(y)
+        import awm_oracle as O
+        y16 = O.quantize_sndfile16(y)
+        assert H.balanced_get(y16, 0, y16.shape[0]) == H.get_s16(y16)
+    finally:
+        H.set_params()

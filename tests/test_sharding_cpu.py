@@ -106,11 +106,6 @@ lo, hi = S.assign_chunks(len(plan), dist.get_world_size())[rank]
 blobs = [(c, bytes([c]) * (100 * (c + 1) + rank)) for c in range(lo, hi)]
 allb = S.gather_blobs(blobs)
 flat = sorted((c, len(b), b[:1]) for per_rank in allb for c, b in per_rank)
-# single-collective byte gather (frame-balanced get): small and oversized payloads
-for size in (0, 10, (1 << 12) + rank):
-    got = S.allgather_bytes(bytes([rank + 1]) * size, cap=1 << 12)
-    assert [len(g) for g in got] == [size if size < (1 << 12) else (1 << 12) + r for r in range(dist.get_world_size())], [len(g) for g in got]
-    assert all(g == bytes([r + 1]) * len(g) for r, g in enumerate(got))
 assert [c for c, _, _ in flat] == list(range(len(plan))), flat
 assert all(b == bytes([c]) for c, _, b in flat)
 if rank == 0:
@@ -162,23 +157,22 @@ def test_every_start_frame_has_exactly_one_owner_up_to_8_ranks():
                         assert sl.lo == cs + sl.a * S.FRAME and sl.hi <= cs + cn and sl.hi >= min(cs + (sl.b + S.T_BLOCK + 1) * S.FRAME, cs + cn)
 
 
-def test_balanced_merge_accepts_per_chunk_blobs_from_the_viterbi_owners():
-    """frame-balanced get, last stage: every chunk's records arrive packed by the rank that decoded them (chunk mod world);
-    the merge on rank 0 must equal merging the same records directly (host code only, no GPU context)"""
-    rng = np.random.default_rng(4)
-    n_total = 2 * 158760000
-    plan = S.chunk_plan(n_total, 79380000, 5926502)
-    payload = O.parse_payload("0123456789abcdef0011223344556677", P)
-    blobs = []
-    for c in range(len(plan)):
-        pats = [(5.8 + 51.688 * k, float(rng.uniform(0.4, 1.4)), int((5.8 + 51.688 * k) * 44100), float(np.float32(rng.uniform(0.05, 0.3))), k & 1, 0, 1.0, payload)
-                for k in range(4)]
-        blobs.append(_records(pats))
-    world = 2
-    payloads = [S._pack({c: blobs[c] for c in range(len(plan)) if c % world == r}) for r in range(world)]
-    job = object.__new__(S.BalancedGet)                       # host-side state only
-    job.plan, job.H, job.key, job.n_total, job.rate, job.rank, job.world = plan, H, bytes(16), n_total, 44100, 0, world
-    assert [job.viterbi_rank(c) for c in range(len(plan))] == [c % world for c in range(len(plan))]
-    got = job.stage_merge(payloads)
-    want = H.merge_chunks(blobs, [p[2] for p in plan], n_total / 44100.0)
-    assert got == want and len(got["matches"]) >= 4
+def test_cpp_plan_functions_agree_with_their_python_restatement():
+    """the C++ driver of the sharded get (host/awm_balanced.cc) and bench.py's Python plan functions must cut the stream the same
+    way: chunks, slices of every rank and the owner of an index, for the world sizes the bench runs and ragged lengths"""
+    H.set_params()
+    mx, ov = H.chunk_geometry(44100)
+    rng = np.random.default_rng(6)
+    for hours, world in ((1, 1), (2, 2), (4, 4), (8, 8), (1.37, 3), (0.2, 8)):
+        n_total = int(hours * 3600 * 44100)
+        plan = S.chunk_plan(n_total, mx, ov)
+        for r in range(world):
+            chunks, slices = H.balanced_plan(n_total, r, world)
+            assert [(a, b) for a, b, _ in chunks] == [(a, b) for a, b, _ in plan]
+            assert np.allclose([t for _, _, t in chunks], [t for _, _, t in plan], rtol=0, atol=1e-9)
+            want = [(sl.chunk, sl.sa, sl.sb, sl.a, sl.b, sl.lo, sl.hi) for sl in S.rank_slices(plan, r, world, n_total)]
+            assert slices == want, (hours, world, r)
+        for c, (cs, cn, _) in enumerate(plan):
+            idx = rng.integers(0, cn, 20)
+            own = S.index_owners(plan, n_total, world, c, idx)
+            assert [H.balanced_owner(n_total, world, c, int(i)) for i in idx] == [int(o) for o in own]
