@@ -170,8 +170,8 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
                     {
                       const float2 v = xp[32 * j];
                       const float wn = s.win[32 * j + lane];
-                      re[j] = v.x * wn;
-                      im[j] = v.y * wn;
+                      re[j] = __fmul_rn (v.x, wn);
+                      im[j] = __fmul_rn (v.y, wn);
                     }
                   __syncwarp();                                   // all lanes hold their samples before the transposes reuse the buffer
                   fft1024_warp (re, im, s.tw, s.xbuf, lane, [&] { if (nxt_tma) prefetch (nxt); });

@@ -139,8 +139,8 @@ k_embed_strip (EmbedArgs A, int strip_len)
             {
               const float wn = s.win[32 * j + lane];
               const float2 v = pcmbuf[32 * j + lane];
-              re[j] = v.x * wn;
-              im[j] = v.y * wn;
+              re[j] = __fmul_rn (v.x, wn);
+              im[j] = __fmul_rn (v.y, wn);
             }
           fft1024_warp (re, im, s.tw, s.xbuf, lane);
           const long long r = (A.frame_number0 + m) % (2LL * A.fpb);

@@ -56,8 +56,8 @@ load_pair (const float *__restrict__ pcm, long long n_frames, int C, long long s
         {
           const float2 v = __ldg (p + 32 * j);
           const float w = win[32 * j + lane];
-          re[j] = v.x * w;
-          im[j] = v.y * w;
+          re[j] = __fmul_rn (v.x, w);            /* spelled out: not to be fused into the first butterfly */
+          im[j] = __fmul_rn (v.y, w);
         }
     }
   else if (C == 2 && chB == 1)
@@ -72,8 +72,8 @@ load_pair (const float *__restrict__ pcm, long long n_frames, int C, long long s
           if (pos >= 0 && pos < n_frames)
             v = __ldg (p2 + pos);
           const float w = win[n];
-          re[j] = v.x * w;
-          im[j] = v.y * w;
+          re[j] = __fmul_rn (v.x, w);            /* spelled out: not to be fused into the first butterfly */
+          im[j] = __fmul_rn (v.y, w);
         }
     }
   else
@@ -91,8 +91,8 @@ load_pair (const float *__restrict__ pcm, long long n_frames, int C, long long s
                 b = __ldg (pcm + pos * C + chB);
             }
           const float w = win[n];
-          re[j] = a * w;
-          im[j] = b * w;
+          re[j] = __fmul_rn (a, w);
+          im[j] = __fmul_rn (b, w);
         }
     }
 }

@@ -398,13 +398,15 @@ def balanced_get(pcm, pcm_start: int, n_total: int, key=None, n_frames=None, cha
 class BalancedStages:
     """one rank of the sharded get with the stages callable one by one (tests run several ranks in one process on one GPU)"""
 
-    def __init__(self, rank, world, n_total, pcm: np.ndarray, pcm_start, key=None, sample_rate=44100):
-        self.pcm = np.ascontiguousarray(pcm, np.float32)
+    def __init__(self, rank, world, n_total, pcm_device_ptr: int, pcm_frames: int, channels: int, pcm_start, key=None, sample_rate=44100):
+        """pcm_device_ptr: float32 [pcm_frames, channels] in device memory that stays valid while the object lives (several ranks in
+        one process share the context, so each needs its own device copy -- a host buffer would land in the context's single
+        upload buffer)"""
         self.n_total = n_total
         L = load()
         L.awmh_bg_create.restype = ctypes.c_void_p
-        self.h = L.awmh_bg_create(_key(key), ctypes.c_int(rank), ctypes.c_int(world), _ptr(self.pcm), ctypes.c_uint64(pcm_start), ctypes.c_uint64(self.pcm.shape[0]),
-                                  ctypes.c_uint64(n_total), ctypes.c_int(self.pcm.shape[1]), ctypes.c_int(sample_rate))
+        self.h = L.awmh_bg_create(_key(key), ctypes.c_int(rank), ctypes.c_int(world), ctypes.c_void_p(pcm_device_ptr), ctypes.c_uint64(pcm_start),
+                                  ctypes.c_uint64(pcm_frames), ctypes.c_uint64(n_total), ctypes.c_int(channels), ctypes.c_int(sample_rate))
         if not self.h:
             raise RuntimeError("awmh_bg_create failed; see stderr")
 

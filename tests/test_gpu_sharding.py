@@ -76,11 +76,15 @@ def test_frame_balanced_get_equals_single_process(world):
     y = H.add(x, T.PAYLOAD)
     doc = H.get(y)
     n = y.shape[0]
-    ranks = []
+    torch = pytest.importorskip("torch")
+    ranks, keep = [], []
     for r in range(world):
         _, slices = H.balanced_plan(n, r, world)
         lo, hi = min(s[5] for s in slices), max(s[6] for s in slices)
-        ranks.append(H.BalancedStages(r, world, n, y[lo:hi], lo))
+        part = torch.from_numpy(np.ascontiguousarray(y[lo:hi])).cuda()      # every simulated rank holds its own device copy
+        keep.append(part)
+        torch.cuda.synchronize()
+        ranks.append(H.BalancedStages(r, world, n, part.data_ptr(), hi - lo, 2, lo))
     try:
         pay = [rk.stage(0) for rk in ranks]                          # peaks
         retry = [rk.stage(1, pay) for rk in ranks]                   # select
