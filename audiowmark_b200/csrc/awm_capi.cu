@@ -732,7 +732,7 @@ namespace {
 int
 embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frames, int channels,
            uint64_t first_frame_number, int frames_pad_start, double water_delta,
-           int limiter_block, float limiter_ceiling, double *snr_power)
+           int limiter_block, float limiter_ceiling, double *snr_power, long long snr_pos0 = 0, long long snr_pos1 = LLONG_MAX)
 {
   const float *in = s16 ? nullptr : static_cast<const float *> (in_v);
   float *out = s16 ? nullptr : static_cast<float *> (out_v);
@@ -826,6 +826,8 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
   A.peaks = ctx->peaks.as<unsigned>();
   A.snr = snr_power ? ctx->snr.as<double>() : nullptr;
   A.snr_frames = limiter_block > 0 ? n_proc : n_real;   // frames the reference loop emits (src/wmadd.cc:539-546)
+  A.snr_pos0 = snr_pos0;
+  A.snr_pos1 = snr_pos1;
   A.delta_only = 0;
   A.tw = ctx->tw.as<float2>();
   A.win = ctx->win.as<float>();
@@ -846,7 +848,9 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
    * kernels of piece p and the D2H copy of piece p-1 overlap (three streams, events in between).  The arithmetic is
    * the same as for one launch: a piece only restricts which frames a launch emits, halo frames are read from the
    * (already copied) neighbour pieces, the limiter of a piece runs once the block peaks after it are final. */
-  const long long kPiece = 12288;                            // 1024-frames per piece (12.6 M sample-frames, 100 MB stereo)
+  long long kPiece = 12288;                                  // 1024-frames per piece (12.6 M sample-frames, 100 MB stereo)
+  if (const char *e = getenv ("AWM_PIECE"))                  // measurement aid: other piece sizes
+    kPiece = std::max (1024LL, atoll (e));
   const bool pipelined = !in_dev && !out_dev && !in16_dev && !out16_dev && n_proc > 2 * kPiece;
   const int n_pieces = pipelined ? int ((n_proc + kPiece - 1) / kPiece) : 1;
   auto piece_frames = [&] (int p, long long& fb, long long& fe) { fb = pipelined ? p * kPiece : 0; fe = pipelined ? std::min<long long> (fb + kPiece, n_proc) : n_proc; };
@@ -985,6 +989,15 @@ awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int chann
            int limiter_block, float limiter_ceiling, double *snr_power)
 {
   return embed_any (ctx, in, out, false, n_frames, channels, first_frame_number, frames_pad_start, water_delta, limiter_block, limiter_ceiling, snr_power);
+}
+
+int
+awm_embed_window (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels,
+                  uint64_t first_frame_number, int frames_pad_start, double water_delta,
+                  int limiter_block, float limiter_ceiling, uint64_t snr_first, uint64_t snr_last, double *snr_power)
+{
+  return embed_any (ctx, in, out, false, n_frames, channels, first_frame_number, frames_pad_start, water_delta, limiter_block, limiter_ceiling, snr_power,
+                    (long long) std::min<uint64_t> (snr_first, LLONG_MAX), (long long) std::min<uint64_t> (snr_last, LLONG_MAX));
 }
 
 int
@@ -2033,6 +2046,8 @@ awm_embed_resampled (awm_ctx *ctx, const float *in, float *out, size_t n_frames,
     A.peaks = nullptr;
     A.snr = nullptr;
     A.snr_frames = 0;
+    A.snr_pos0 = 0;
+    A.snr_pos1 = LLONG_MAX;
     A.delta_only = 1;
     A.tw = ctx->tw.as<float2>();
     A.win = ctx->win.as<float>();

@@ -190,7 +190,7 @@ k_embed_strip (EmbedArgs A, int strip_len)
                   const float oa = tail_orig[q].x, ob = tail_orig[q].y;
                   const float ya = A.delta_only ? wa : __fadd_rn (wa, oa), yb = A.delta_only ? wb : __fadd_rn (wb, ob);
                   const long long pos = (m - 1) * kFrame + x;
-                  if (A.snr && m - 1 < A.snr_frames)
+                  if (A.snr && m - 1 < A.snr_frames && pos >= A.snr_pos0 && pos < A.snr_pos1)
                     {
                       snr_d += double (wa) * double (wa) + double (wb) * double (wb);
                       snr_s += double (oa) * double (oa) + double (ob) * double (ob);
@@ -209,7 +209,7 @@ k_embed_strip (EmbedArgs A, int strip_len)
                   const float2 og = pcmbuf[x]; const float oa = og.x, ob = og.y;
                   const float ya = A.delta_only ? wa : __fadd_rn (wa, oa), yb = A.delta_only ? wb : __fadd_rn (wb, ob);
                   const long long pos = m * kFrame + x;
-                  if (A.snr && m < A.snr_frames)
+                  if (A.snr && m < A.snr_frames && pos >= A.snr_pos0 && pos < A.snr_pos1)
                     {
                       snr_d += double (wa) * double (wa) + double (wb) * double (wb);
                       snr_s += double (oa) * double (oa) + double (ob) * double (ob);
@@ -238,7 +238,7 @@ k_embed_strip (EmbedArgs A, int strip_len)
                   const float2 og = pcmbuf[x]; const float oa = og.x, ob = og.y;
                   const float ya = A.delta_only ? wa : __fadd_rn (wa, oa), yb = A.delta_only ? wb : __fadd_rn (wb, ob);
                   const long long pos = m * kFrame + x;
-                  if (A.snr && m < A.snr_frames)
+                  if (A.snr && m < A.snr_frames && pos >= A.snr_pos0 && pos < A.snr_pos1)
                     {
                       snr_d += double (wa) * double (wa) + double (wb) * double (wb);
                       snr_s += double (oa) * double (oa) + double (ob) * double (ob);

@@ -814,6 +814,7 @@ struct EmbedArgs
   unsigned *peaks;             // [n_blocks] float bits, atomicMax
   double *snr;                 // [2] or null
   long long snr_frames;        // frames that count for --snr (the reference loop stops earlier without limiter)
+  long long snr_pos0, snr_pos1; // ... and only positions [snr_pos0, snr_pos1) of this buffer (a window of a longer stream counts its own part)
   int delta_only;              // 1: write the watermark signal alone (WatermarkGen::run output), not input + watermark
   const float2 *tw;
   const float *win;
@@ -978,7 +979,7 @@ k_embed (EmbedArgs A)
                     }
                 }
               const float ya = A.delta_only ? wa : __fadd_rn (wa, oa), yb = A.delta_only ? wb : __fadd_rn (wb, ob);
-              if (A.snr && m < A.snr_frames)
+              if (A.snr && m < A.snr_frames && pos >= A.snr_pos0 && pos < A.snr_pos1)
                 {
                   snr_d += double (wa) * double (wa) + (chB >= 0 ? double (wb) * double (wb) : 0.0);
                   snr_s += double (oa) * double (oa) + (chB >= 0 ? double (ob) * double (ob) : 0.0);

@@ -9,6 +9,7 @@
 #include "awm_util.hh"
 
 #include <math.h>
+#include <functional>
 
 using std::string;
 using std::vector;
@@ -154,17 +155,135 @@ add_watermark_buffer_s16 (const Key& key, const int16_t *in, int16_t *out, size_
   return 0;
 }
 
+/* Part of the stream a window has to embed so that [own_start, own_end) comes out exactly as in a run over the whole stream:
+ * one 1024-frame before the first limiter block that influences the owned range (synthesis-window tail of the frame before) and
+ * everything up to the end of the limiter block after the last owned one (the gain ramp looks one block ahead), rounded to whole
+ * 1024-frames.  n_total = ~0 while the end of the stream is not known. */
+static void
+window_range (size_t own_start, size_t own_end, size_t n_total, size_t limiter_block, size_t& ext_start, size_t& ext_end)
+{
+  const size_t N = Params::frame_size;
+  if (own_start == 0)
+    ext_start = 0;
+  else
+    {
+      const size_t b = own_start / limiter_block;                   // first owned limiter block
+      const size_t lo = (b ? b - 1 : 0) * limiter_block;            // the block before it must be complete
+      ext_start = lo / N * N >= N ? lo / N * N - N : 0;
+    }
+  if (own_end >= n_total)
+    ext_end = n_total;
+  else
+    {
+      const size_t hi = ((own_end - 1) / limiter_block + 2) * limiter_block;
+      ext_end = std::min (ext_start + (hi - ext_start + N - 1) / N * N + N, n_total);
+    }
+}
+
+/* add_stream_watermark's loop (src/wmadd.cc:504-589) with bounded memory: the stream is embedded window by window.  A window
+ * is run through awm_embed with the halo window_range() asks for and with first_frame_number = its position in the stream, so the
+ * table row of every frame and the limiter blocks are those of a run over the whole stream and the owned part of the result
+ * is bit identical to it (tests/test_gpu_sharding.py checks exactly this property for sharded embedding).  Reads block only
+ * until one window + about two seconds of look-ahead are buffered: a pipe gets its first output after ~100 s of input, not at EOF.
+ * zero_frames: the input continues a stream that began zero_frames earlier with silence (HLS segments, src/wmadd.cc:504-519):
+ * positions, table rows and limiter blocks count from there, nothing is written for the silent part.
+ * window_frames = 0: default window (4096 1024-frames = 95 s); tests pass small windows. */
+int
+add_watermark_windowed (const Key& key, const std::function<Error (vector<float>&, size_t)>& read, const std::function<Error (const vector<float>&)>& write,
+                        int n_channels, int sample_rate, const string& bits, size_t zero_frames, size_t window_frames, AddStats *stats, size_t *frames_written)
+{
+  const size_t N = Params::frame_size, C = size_t (n_channels);
+  const size_t L = size_t (sample_rate) * size_t (Params::limiter_block_size_ms) / 1000;      // limiter block; also sizes the halo without limiter
+  const size_t W = (window_frames ? window_frames : 4096) * N;
+  const size_t unknown = ~size_t (0);
+  const vector<int> bitvec = parse_payload (bits);
+  if (bitvec.empty())
+    return 1;
+  awm_ctx *ctx = Engine::ctx();
+  if (!ctx || !Engine::set_embed_tables (key, bitvec))
+    return 1;
+  const int limiter_block = Params::test_no_limiter ? 0 : int (L);
+  vector<float> pending;                         // stream positions [p0, p1), interleaved
+  size_t p0 = 0, p1 = 0, own_start = zero_frames, written = 0;
+  double snr_delta = 0, snr_signal = 0;
+  {
+    /* the silent prefix is never materialised beyond what the first window's halo reaches into */
+    size_t e0, e1;
+    window_range (own_start, own_start + 1, unknown, L, e0, e1);
+    p0 = e0;
+    p1 = zero_frames;
+    pending.assign ((p1 - p0) * C, 0.f);
+  }
+  bool eof = false;
+  vector<float> block, out;
+  while (!eof || own_start < p1)
+    {
+      size_t e0, e1;
+      window_range (own_start, own_start + W, unknown, L, e0, e1);
+      while (!eof && p1 < e1)                    // the window and its look-ahead
+        {
+          const Error err = read (block, std::min<size_t> (e1 - p1, 1 << 16));
+          if (err)
+            {
+              error ("audiowmark: input stream read failed: %s\n", err.message());
+              return 1;
+            }
+          if (block.empty())
+            eof = true;
+          pending.insert (pending.end(), block.begin(), block.end());
+          p1 += block.size() / C;
+        }
+      const size_t n_total = eof ? p1 : unknown;
+      const size_t own_end = eof ? p1 : own_start + W;
+      if (own_end <= own_start)
+        break;
+      window_range (own_start, own_end, n_total, L, e0, e1);
+      out.resize ((e1 - e0) * C);
+      double snr_power[2] = { 0, 0 };
+      /* the --snr sums count the watermark signal before the limiter, over this window's own part (the last window also takes the
+       * zero padded frames after the end of the input, like the reference loop) */
+      if (awm_embed_window (ctx, pending.data() + (e0 - p0) * C, out.data(), e1 - e0, n_channels, e0 / N, Params::frames_pad_start, Params::water_delta,
+                            limiter_block, Params::limiter_ceiling, own_start - e0, eof ? ~uint64_t (0) : own_end - e0, (Params::snr || stats) ? snr_power : nullptr))
+        {
+          error ("audiowmark: embedding failed: %s\n", awm_last_error (ctx));
+          return 1;
+        }
+      snr_delta += snr_power[0];
+      snr_signal += snr_power[1];
+      const float *o = out.data() + (own_start - e0) * C;
+      const Error err = write (vector<float> (o, o + (own_end - own_start) * C));
+      if (err)
+        {
+          error ("audiowmark output write failed: %s\n", err.message());
+          return 1;
+        }
+      written += own_end - own_start;
+      own_start = own_end;
+      if (eof)
+        break;
+      window_range (own_start, own_start + 1, unknown, L, e0, e1);   // what the next window still needs of the buffer
+      pending.erase (pending.begin(), pending.begin() + (e0 - p0) * C);
+      p0 = e0;
+    }
+  if (frames_written)
+    *frames_written = written;
+  if (stats)
+    {
+      const size_t fpb = frames_per_block(), f0 = 2 * fpb - Params::frames_pad_start;
+      const size_t runs = gen_runs (p1, !Params::test_no_limiter, L);
+      const int blocks = int ((f0 + runs) / fpb - f0 / fpb);
+      stats->data_blocks = std::max (blocks - 1, 0);         // the first (partial B) block is padding
+      stats->snr_db = snr_delta > 0 ? 10 * log10 (snr_signal / snr_delta) : INFINITY;
+    }
+  return 0;
+}
+
 int
 add_stream_watermark (const Key& key, AudioInputStream *in_stream, AudioOutputStream *out_stream, const string& bits, size_t zero_frames)
 {
   auto bitvec = parse_payload (bits);
   if (bitvec.empty())
     return 1;
-  if (zero_frames)
-    {
-      error ("audiowmark: stream offsets (HLS segment watermarking) are not supported in this build\n");
-      return 1;
-    }
   if (in_stream->sample_rate() != out_stream->sample_rate())
     {
       error ("audiowmark: input sample rate (%d) and output sample rate (%d) don't match\n", in_stream->sample_rate(), out_stream->sample_rate());
@@ -187,29 +306,47 @@ add_stream_watermark (const Key& key, AudioInputStream *in_stream, AudioOutputSt
   info ("Sample Rate:  %d\n", in_stream->sample_rate());
   info ("Channels:     %d\n", in_stream->n_channels());
 
-  WavData wav;
-  Error err = wav.load (in_stream);
-  if (err)
-    {
-      error ("audiowmark: input stream read failed: %s\n", err.message());
-      return 1;
-    }
-  vector<float> out (wav.n_values());
   AddStats stats;
-  if (add_watermark_buffer (key, wav.samples().data(), out.data(), wav.n_frames(), wav.n_channels(), wav.sample_rate(), bits, &stats))
-    return 1;
-  vector<float>().swap (wav.mutable_samples());
-  err = out_stream->write_frames (out);
-  if (err)
+  size_t total_output_frames = 0;
+  Error err;
+  if (in_stream->sample_rate() != Params::mark_sample_rate)
     {
-      error ("audiowmark output write failed: %s\n", err.message());
-      return 1;
+      /* other sample rates go through the resamplers around the embedder (awm_embed_resampled): whole stream at once */
+      if (zero_frames)
+        {
+          error ("audiowmark: stream offsets are only supported at %d Hz\n", Params::mark_sample_rate);
+          return 1;
+        }
+      WavData wav;
+      err = wav.load (in_stream);
+      if (err)
+        {
+          error ("audiowmark: input stream read failed: %s\n", err.message());
+          return 1;
+        }
+      vector<float> out (wav.n_values());
+      if (add_watermark_buffer (key, wav.samples().data(), out.data(), wav.n_frames(), wav.n_channels(), wav.sample_rate(), bits, &stats))
+        return 1;
+      vector<float>().swap (wav.mutable_samples());
+      err = out_stream->write_frames (out);
+      if (err)
+        {
+          error ("audiowmark output write failed: %s\n", err.message());
+          return 1;
+        }
+      total_output_frames = out.size() / std::max (in_stream->n_channels(), 1);
+    }
+  else
+    {
+      auto read = [&] (vector<float>& samples, size_t count) { return in_stream->read_frames (samples, count); };
+      auto write = [&] (const vector<float>& samples) { return out_stream->write_frames (samples); };
+      if (add_watermark_windowed (key, read, write, in_stream->n_channels(), in_stream->sample_rate(), bits, zero_frames, 0, &stats, &total_output_frames))
+        return 1;
     }
   if (Params::snr)
     info ("SNR:          %f dB\n", stats.snr_db);
   info ("Data Blocks:  %d\n", stats.data_blocks);
 
-  const size_t total_output_frames = out.size() / std::max (in_stream->n_channels(), 1);
   if (in_stream->n_frames() != AudioInputStream::N_FRAMES_UNKNOWN && total_output_frames != in_stream->n_frames())
     {
       auto msg = string_printf ("unexpected EOF; input frames (%zd) != output frames (%zd)", in_stream->n_frames(), total_output_frames);

@@ -251,6 +251,39 @@ awmh_add_s16 (const unsigned char *key16, const int16_t *in, int16_t *out, size_
   return rc;
 }
 
+/* add_stream_watermark's bounded-memory loop (add_watermark_windowed) between two host buffers: `in` is read in small blocks like a
+ * pipe, the result is appended to `out` (n_frames frames); window_frames = 0 uses the default window.  zero_frames: the input continues
+ * a stream that began that many frames earlier with silence (src/wmadd.cc:504-519). */
+int
+awmh_add_windowed (const unsigned char *key16, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate, const char *payload_hex,
+                   size_t zero_frames, size_t window_frames, int *data_blocks, double *snr_db)
+{
+  size_t rpos = 0, wpos = 0;
+  auto read = [&] (std::vector<float>& samples, size_t count)
+    {
+      const size_t n = std::min (count, n_frames - rpos);
+      samples.assign (in + rpos * n_channels, in + (rpos + n) * n_channels);
+      rpos += n;
+      return Error (Error::Code::NONE);
+    };
+  auto write = [&] (const std::vector<float>& samples)
+    {
+      if (wpos * n_channels + samples.size() > n_frames * n_channels)
+        return Error ("output buffer too small");
+      memcpy (out + wpos * n_channels, samples.data(), samples.size() * sizeof (float));
+      wpos += samples.size() / n_channels;
+      return Error (Error::Code::NONE);
+    };
+  AddStats stats;
+  size_t written = 0;
+  const int rc = add_watermark_windowed (make_key (key16, ""), read, write, n_channels, sample_rate, payload_hex, zero_frames, window_frames, &stats, &written);
+  if (rc)
+    return rc;
+  if (data_blocks) *data_blocks = stats.data_blocks;
+  if (snr_db) *snr_db = stats.snr_db;
+  return written == n_frames ? 0 : -3;
+}
+
 static int result_json (ResultSet& result_set, size_t mark_rate_frames, char *json_out, size_t json_cap, int *n_patterns);
 
 int

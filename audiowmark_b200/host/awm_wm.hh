@@ -1,6 +1,7 @@
 // awm_wm.hh -- entry points of the watermark drivers, same names / argument meaning as the reference
 // (src/wmcommon.hh:226-228, src/syncfinder.hh:71-121).
 #pragma once
+#include <functional>
 #include <string>
 #include <vector>
 #include "awm_params.hh"
@@ -17,6 +18,11 @@ int get_watermark (const std::vector<Key>& key_list, const std::string& infile, 
 struct AddStats { int data_blocks = 0; double snr_db = 0; };
 int add_watermark_buffer (const Key& key, const float *in, float *out, size_t n_frames, int n_channels, int sample_rate,
                           const std::string& bits, AddStats *stats, uint64_t first_frame_number = 0);
+
+/* add_stream_watermark's loop with bounded memory (window by window; see awm_add.cc); callbacks read / write interleaved frames */
+int add_watermark_windowed (const Key& key, const std::function<Error (std::vector<float>&, size_t)>& read,
+                            const std::function<Error (const std::vector<float>&)>& write, int n_channels, int sample_rate, const std::string& bits,
+                            size_t zero_frames, size_t window_frames, AddStats *stats, size_t *frames_written);
 
 /* frame counts of the add loop for inputs that are not at the watermark rate (see awm_add.cc) */
 void resampled_add_plan (size_t n_frames, int sample_rate, bool limiter_on, size_t limiter_block, size_t& n_emit, size_t& gen_runs_out);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libawm_host.so")
 CLI_PATH = os.path.join(_HERE, "bin", "audiowmark")
 
 EXPORTS = ["awmh_set_params", "awmh_frames_per_block", "awmh_n_coded_bits", "awmh_random_u64", "awmh_gen_noise", "awmh_sync_table",
-           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16", "awmh_short_encode", "awmh_short_decode", "awmh_sync_trace", "awmh_sync_trace_fetch", "awmh_dist_unique_id", "awmh_dist_init", "awmh_balanced_get", "awmh_bg_create", "awmh_bg_destroy", "awmh_bg_stage", "awmh_bg_plan", "awmh_bg_owner"]
+           "awmh_mix_table", "awmh_frame_mod", "awmh_conv_encode", "awmh_add", "awmh_get", "awmh_get_chunk", "awmh_merge_chunks", "awmh_chunk_geometry", "awmh_ctx", "awmh_key_slot", "awmh_stage_select", "awmh_stage_final", "awmh_stage_jobs", "awmh_gpu_launches", "awmh_gpu_stream", "awmh_synchronize", "awmh_profile_enable", "awmh_profile_report", "awmh_shutdown", "awmh_set_speed_params", "awmh_detect_speed", "awmh_resample", "awmh_resample_stream_frames", "awmh_resample_stream_available", "awmh_resampled_add_plan", "awmh_set_short_payload", "awmh_add_s16", "awmh_get_s16", "awmh_short_encode", "awmh_short_decode", "awmh_sync_trace", "awmh_sync_trace_fetch", "awmh_dist_unique_id", "awmh_dist_init", "awmh_balanced_get", "awmh_bg_create", "awmh_bg_destroy", "awmh_bg_stage", "awmh_bg_plan", "awmh_bg_owner", "awmh_add_windowed"]
 
 _lib = None
 
@@ -162,6 +162,18 @@ def add(pcm_in, payload_hex: str, key=None, pcm_out=None, n_frames=None, channel
     if rc:
         raise RuntimeError("awmh_add failed (rc=%d); see stderr" % rc)
     return (pcm_out, blocks.value, snr.value) if want_stats else pcm_out
+
+
+def add_windowed(pcm_in: np.ndarray, payload_hex: str, key=None, zero_frames=0, window_frames=0, sample_rate=44100):
+    """the bounded-memory loop of `audiowmark add` (add_watermark_windowed) on a host buffer -> (output, data blocks, snr dB)"""
+    pcm_in = np.ascontiguousarray(pcm_in, np.float32)
+    out = np.empty_like(pcm_in)
+    blocks, snr = ctypes.c_int(), ctypes.c_double()
+    rc = load().awmh_add_windowed(_key(key), _ptr(pcm_in), _ptr(out), ctypes.c_size_t(pcm_in.shape[0]), ctypes.c_int(pcm_in.shape[1]), ctypes.c_int(sample_rate),
+                                  payload_hex.encode(), ctypes.c_size_t(zero_frames), ctypes.c_size_t(window_frames), ctypes.byref(blocks), ctypes.byref(snr))
+    if rc:
+        raise RuntimeError("awmh_add_windowed failed (rc=%d); see stderr" % rc)
+    return out, blocks.value, snr.value
 
 
 def get(pcm, keys=None, names=None, n_frames=None, channels=None, sample_rate=44100, parse=True):

@@ -134,6 +134,12 @@ const float *awm_pcm_device (awm_ctx *ctx, size_t *n_frames, int *channels);
 int awm_embed (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels,
                uint64_t first_frame_number, int frames_pad_start, double water_delta,
                int limiter_block, float limiter_ceiling, double *snr_power);
+/* awm_embed for one WINDOW of a longer stream (streaming `add` with bounded memory, add_stream_watermark's loop src/wmadd.cc:520-589
+ * taken window by window): the buffer holds the window plus its halo, first_frame_number places it in the stream; only positions
+ * [snr_first, snr_last) of the buffer (the part the caller keeps) enter the --snr sums.  Everything else as awm_embed. */
+int awm_embed_window (awm_ctx *ctx, const float *in, float *out, size_t n_frames, int channels,
+                      uint64_t first_frame_number, int frames_pad_start, double water_delta,
+                      int limiter_block, float limiter_ceiling, uint64_t snr_first, uint64_t snr_last, double *snr_power);
 /* the same for 16 bit PCM in and out (see awm_pcm_bind_s16): what `audiowmark add in16.wav out16.wav` computes between the files */
 int awm_embed_s16 (awm_ctx *ctx, const int16_t *in, int16_t *out, size_t n_frames, int channels,
                    uint64_t first_frame_number, int frames_pad_start, double water_delta,

@@ -114,3 +114,31 @@ def test_balanced_get_entry_point_single_rank():
         assert H.balanced_get(y16, 0, y16.shape[0]) == H.get_s16(y16)
     finally:
         H.set_params()
+
+
+@pytest.mark.parametrize("limiter", [True, False])
+def test_streaming_add_equals_whole_stream_add(limiter):
+    """`audiowmark add` reads, embeds and writes window by window (bounded memory, first output long before EOF; reference loop
+    src/wmadd.cc:520-589): identical bits, the same "Data Blocks" and --snr figures as embedding the whole stream at once, for
+    windows that are whole blocks, ragged, and shorter than a limiter block"""
+    x = T.noise(130.0, 2, seed=31, amp=1.0)
+    H.set_params(test_no_limiter=not limiter)
+    try:
+        whole, blocks, snr = H.add(x, T.PAYLOAD, want_stats=True)
+        for window in (0, 1000, 37, 3):
+            out, wblocks, wsnr = H.add_windowed(x, T.PAYLOAD, window_frames=window)
+            assert np.array_equal(out, whole), window
+            assert wblocks == blocks and abs(wsnr - snr) < 1e-9, (window, wblocks, blocks, wsnr, snr)
+    finally:
+        H.set_params()
+
+
+def test_streaming_add_with_stream_offset():
+    """zero_frames (HLS segments, src/wmadd.cc:504-519): the input continues a stream that began with that much silence -- the result is
+    what embedding silence + input gives, minus the silent part"""
+    x = T.noise(70.0, 2, seed=32)
+    H.set_params()
+    for zero_frames in (1024 * 300, 1024 * 300 + 517, 100):
+        full = H.add(np.concatenate([np.zeros((zero_frames, 2), np.float32), x]), T.PAYLOAD)
+        out, _, _ = H.add_windowed(x, T.PAYLOAD, zero_frames=zero_frames, window_frames=500)
+        assert np.array_equal(out, full[zero_frames:]), zero_frames
