@@ -1718,7 +1718,9 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits,
     }
   CK (cudaSetDevice (ctx->device));
   const size_t max_jobs = 512;
-  const size_t smem = size_t (steps) * 12 * sizeof (float);
+  const size_t smem = viterbi_smem_bytes (steps);
+  if (smem > 220 * 1024)
+    return fail (ctx, "awm_viterbi: %d message bits are more than the kernel holds in shared memory", n_msg_bits);
   if (set_smem (ctx, k_viterbi, smem)) return 1;
   for (size_t j0 = 0; j0 < n_jobs; j0 += max_jobs)
     {
@@ -1730,7 +1732,6 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits,
       CK (ctx->vit_raw.reserve (n_raw * sizeof (float)));
       CK (ctx->vit_off.reserve (nj * sizeof (long long)));
       CK (ctx->vit_types.reserve (nj * sizeof (int)));
-      CK (ctx->vit_delta.reserve (nj * 2 * kVitStates * sizeof (float)));
       CK (ctx->vit_dec.reserve (nj * steps * kVitWords * sizeof (uint32_t)));
       CK (ctx->vit_bits.reserve (nj * n_msg_bits));
       CK (ctx->vit_err.reserve (nj * sizeof (float)));
@@ -1739,8 +1740,7 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits,
       CK (cudaMemcpyAsync (ctx->vit_types.p, block_types + j0, nj * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
       PROF (ctx);
       k_viterbi<<<unsigned (nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), ctx->vit_off.as<long long>(), n_msg_bits, ctx->vit_types.as<int>(), hard,
-                                                                  steps,
-                                                                  ctx->vit_delta.as<float>(), ctx->vit_dec.as<uint32_t>(),
+                                                                  steps, ctx->vit_dec.as<uint32_t>(),
                                                                   ctx->vit_bits.as<unsigned char>(), ctx->vit_err.as<float>());
       LAUNCH_CHECK ("k_viterbi");
       CK (cudaMemcpyAsync (bits_out + j0 * n_msg_bits, ctx->vit_bits.p, nj * n_msg_bits, cudaMemcpyDeviceToHost, ctx->stream));

@@ -638,8 +638,13 @@ __host__ __device__ constexpr bool cparity (unsigned v) { v ^= v >> 16; v ^= v >
 // The output bit p of state ns is parity (ns & g_p) = parity (32u & g_p) ^ parity (q & g_p): the first factor
 // is a per-group constant (hi, bit p), the second a compile-time constant, so which of (c-0)^2 / (c-1)^2 is
 // added needs no instruction at all inside the unrolled loops.
+// shared-memory position of path metric n: four floats of padding after every 32, so that the float4 accesses of a quarter warp
+// (reads 64 bytes apart, writes 128 bytes apart in the unpadded array) fall into eight different bank groups
+__device__ __forceinline__ int vit_pos (int n) { return n + ((n >> 5) << 2); }
+constexpr int kVitPadded = kVitStates + kVitStates / 32 * 4;
+
 template<int TYPE> __device__ __forceinline__ uint32_t
-viterbi_step (const float *__restrict__ d_old, float *__restrict__ d_new, unsigned hi, const float *m0, const float *m1, int u)
+viterbi_step (const float *__restrict__ d_old, float (&outv)[32], unsigned hi, const float *m0, const float *m1, int u)
 {
   constexpr int RATE = TYPE == AWM_BLOCK_AB ? 12 : 6;
   float mA[RATE], mB[RATE];               // metric for output bit == hi-bit / != hi-bit
@@ -654,10 +659,9 @@ viterbi_step (const float *__restrict__ d_old, float *__restrict__ d_new, unsign
 #pragma unroll
   for (int v = 0; v < 4; v++)                                // 8 new states <- 4 + 4 predecessors
     {
-      const float4 x = *reinterpret_cast<const float4 *> (d_old + 16 * u + 4 * v);
-      const float4 y = *reinterpret_cast<const float4 *> (d_old + 16 * u + 4 * v + (kVitStates >> 1));
+      const float4 x = *reinterpret_cast<const float4 *> (d_old + vit_pos (16 * u + 4 * v));
+      const float4 y = *reinterpret_cast<const float4 *> (d_old + vit_pos (16 * u + 4 * v + (kVitStates >> 1)));
       const float a0[4] = { x.x, x.y, x.z, x.w }, a1[4] = { y.x, y.y, y.z, y.w };
-      float outv[8];
 #pragma unroll
       for (int q = 0; q < 8; q++)
         {
@@ -670,23 +674,25 @@ viterbi_step (const float *__restrict__ d_old, float *__restrict__ d_new, unsign
               d1 = __fadd_rn (d1, m);
             }
           const bool take1 = d1 < d0;
-          outv[q] = take1 ? d1 : d0;
+          outv[8 * v + q] = take1 ? d1 : d0;
           word |= (take1 ? 1u : 0u) << (8 * v + q);
         }
-      float4 *on = reinterpret_cast<float4 *> (d_new + 32 * u + 8 * v);
-      on[0] = make_float4 (outv[0], outv[1], outv[2], outv[3]);
-      on[1] = make_float4 (outv[4], outv[5], outv[6], outv[7]);
     }
   return word;
 }
 
+// The 2^15 path metrics of a code word live in shared memory (128 KB).  A trellis step reads the two predecessors of every new
+// state, so the update cannot be done in place state by state; instead every thread keeps the 64 new metrics of its two groups in
+// registers until the whole CTA has read the old ones (barrier), then stores them over the old array (barrier).  No metric ever
+// travels to L2 / HBM; only the decision bits (4 KB per step, read back once by the traceback) are written to global memory.
 template<int TYPE> __device__ __forceinline__ void
-viterbi_run (float *d_old, float *d_new, uint32_t *dec, const float *coded, float *m0, float *m1, int steps, int tid)
+viterbi_run (float *dm, uint32_t *dec, const float *coded, float *m0, float *m1, int steps, int tid)
 {
   constexpr int RATE = TYPE == AWM_BLOCK_AB ? 12 : 6;
-  unsigned hi[kVitWords / kVitThreads];
+  constexpr int kGroups = kVitWords / kVitThreads;
+  unsigned hi[kGroups];
 #pragma unroll
-  for (int g = 0; g < kVitWords / kVitThreads; g++)
+  for (int g = 0; g < kGroups; g++)
     {
       const unsigned base = 32u * unsigned (tid + g * kVitThreads);
       hi[g] = 0;
@@ -702,25 +708,37 @@ viterbi_run (float *d_old, float *d_new, uint32_t *dec, const float *coded, floa
           m0[tid] = __fmul_rn (c, c);                       // (c - 0)^2
           m1[tid] = __fmul_rn (c - 1.0f, c - 1.0f);         // (c - 1)^2
         }
-      __syncthreads();
+      __syncthreads();                                      // metrics of the previous step stored, m0 / m1 ready
+      float outv[kGroups][32];
 #pragma unroll
-      for (int g = 0; g < kVitWords / kVitThreads; g++)
+      for (int g = 0; g < kGroups; g++)
         {
           const int u = tid + g * kVitThreads;
-          dec[(size_t) t * kVitWords + u] = viterbi_step<TYPE> (d_old, d_new, hi[g], m0, m1, u);
+          dec[(size_t) t * kVitWords + u] = viterbi_step<TYPE> (dm, outv[g], hi[g], m0, m1, u);
         }
-      __syncthreads();
-      float *tmp = d_old; d_old = d_new; d_new = tmp;
+      __syncthreads();                                      // every thread has read its predecessors
+#pragma unroll
+      for (int g = 0; g < kGroups; g++)
+        {
+          float4 *on = reinterpret_cast<float4 *> (dm + vit_pos (32 * (tid + g * kVitThreads)));
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            on[k] = make_float4 (outv[g][4 * k], outv[g][4 * k + 1], outv[g][4 * k + 2], outv[g][4 * k + 3]);
+        }
     }
+  __syncthreads();
 }
+
+constexpr size_t viterbi_smem_bytes (int steps) { return size_t (kVitPadded) * sizeof (float) + size_t (steps) * 12 * sizeof (float); }
 
 __global__ void __launch_bounds__ (kVitThreads)
 k_viterbi (const float *__restrict__ raw, const long long *__restrict__ raw_off, int n_msg, const int *__restrict__ block_types, int hard,
-           int max_steps, float *__restrict__ delta_buf /* [job][2][32768] */, uint32_t *__restrict__ dec_buf /* [job][steps][kVitWords] */,
+           int max_steps, uint32_t *__restrict__ dec_buf /* [job][steps][kVitWords] */,
            unsigned char *__restrict__ bits_out, float *__restrict__ err_out)
 {
   extern __shared__ __align__ (16) unsigned char smem[];
-  float *coded = reinterpret_cast<float *> (smem);          // [n_coded] normalised soft bits
+  float *dm = reinterpret_cast<float *> (smem);             // [2^15] path metrics (padded, vit_pos)
+  float *coded = dm + kVitPadded;                           // [n_coded] normalised soft bits
   __shared__ float m0[12], m1[12];
   __shared__ double s_mean;
   const int job = blockIdx.x, tid = threadIdx.x;
@@ -753,25 +771,20 @@ k_viterbi (const float *__restrict__ raw, const long long *__restrict__ raw_off,
   for (int i = tid; i < n_coded; i += blockDim.x)
     coded[i] = hard ? (rj[i] > 0 ? 1.0f : 0.0f) : float (0.5 * (double (rj[i]) / s_mean + 1));
 
-  float *d_old = delta_buf + (size_t) job * 2 * kVitStates, *d_new = d_old + kVitStates;
   uint32_t *dec = dec_buf + (size_t) job * max_steps * kVitWords;
   for (int i = tid; i < kVitStates; i += blockDim.x)
-    d_old[i] = (i == 0) ? 0.f : INFINITY;
+    dm[vit_pos (i)] = (i == 0) ? 0.f : INFINITY;
   __syncthreads();
 
   if (btype == AWM_BLOCK_A)
-    viterbi_run<AWM_BLOCK_A> (d_old, d_new, dec, coded, m0, m1, steps, tid);
+    viterbi_run<AWM_BLOCK_A> (dm, dec, coded, m0, m1, steps, tid);
   else if (btype == AWM_BLOCK_B)
-    viterbi_run<AWM_BLOCK_B> (d_old, d_new, dec, coded, m0, m1, steps, tid);
+    viterbi_run<AWM_BLOCK_B> (dm, dec, coded, m0, m1, steps, tid);
   else
-    viterbi_run<AWM_BLOCK_AB> (d_old, d_new, dec, coded, m0, m1, steps, tid);
-  if (steps & 1)
-    {
-      float *tmp = d_old; d_old = d_new; d_new = tmp;
-    }
+    viterbi_run<AWM_BLOCK_AB> (dm, dec, coded, m0, m1, steps, tid);
   if (tid == 0)
     {
-      err_out[job] = d_old[0] / float (n_coded);
+      err_out[job] = dm[0] / float (n_coded);
       unsigned state = 0;
       for (int t = steps; t > 0; t--)
         {
