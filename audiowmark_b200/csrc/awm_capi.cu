@@ -1170,24 +1170,35 @@ awm_sync_peaks (awm_ctx *ctx, double min_abs_quality, awm_search_score *out, siz
   if (!ctx->n_scores_dev)
     return 0;
   CK (cudaSetDevice (ctx->device));
-  CK (ctx->peaks_out.reserve (std::max<size_t> (max, 1) * sizeof (awm_search_score)));
-  CK (ctx->peaks_cnt.reserve (sizeof (unsigned long long)));
-  CK (cudaMemsetAsync (ctx->peaks_cnt.p, 0, sizeof (unsigned long long), ctx->stream));
+  /* counter and entries share one buffer ([u64 count, u64 pad][entries]) so that the usual case -- a few dozen peaks -- comes back
+   * with ONE device-to-host copy and one synchronisation instead of two of each */
+  constexpr size_t kHead = 16, kFirst = 2048;
+  CK (ctx->peaks_out.reserve (kHead + std::max<size_t> (max, 1) * sizeof (awm_search_score)));
+  unsigned char *base = ctx->peaks_out.as<unsigned char>();
+  CK (cudaMemsetAsync (base, 0, kHead, ctx->stream));
   const long long ns = (long long) ctx->n_scores_dev;
   PROF (ctx);
   k_peaks<<<unsigned ((ns + 255) / 256), 256, 0, ctx->stream>>> (ctx->scores.as<awm_search_score>(), ns, min_abs_quality,
-                                                                ctx->peaks_out.as<awm_search_score>(), (unsigned long long) max,
-                                                                ctx->peaks_cnt.as<unsigned long long>());
+                                                                reinterpret_cast<awm_search_score *> (base + kHead), (unsigned long long) max,
+                                                                reinterpret_cast<unsigned long long *> (base));
   LAUNCH_CHECK ("k_peaks");
-  unsigned long long cnt = 0;
-  CK (cudaMemcpyAsync (&cnt, ctx->peaks_cnt.p, sizeof (cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  static thread_local std::vector<unsigned char> stage;
+  const size_t first = std::min (max, kFirst);
+  stage.resize (kHead + first * sizeof (awm_search_score));
+  CK (cudaMemcpyAsync (stage.data(), base, stage.size(), cudaMemcpyDeviceToHost, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
+  unsigned long long cnt = 0;
+  memcpy (&cnt, stage.data(), sizeof (cnt));
   *n = size_t (cnt);
   const size_t got = std::min<size_t> (cnt, max);
   if (got)
     {
-      CK (cudaMemcpyAsync (out, ctx->peaks_out.p, got * sizeof (awm_search_score), cudaMemcpyDeviceToHost, ctx->stream));
-      CK (cudaStreamSynchronize (ctx->stream));
+      memcpy (out, stage.data() + kHead, std::min (got, first) * sizeof (awm_search_score));
+      if (got > first)
+        {
+          CK (cudaMemcpyAsync (out + first, base + kHead + first * sizeof (awm_search_score), (got - first) * sizeof (awm_search_score), cudaMemcpyDeviceToHost, ctx->stream));
+          CK (cudaStreamSynchronize (ctx->stream));
+        }
       std::sort (out, out + got, [] (const awm_search_score& a, const awm_search_score& b) { return a.index < b.index; });
     }
   return 0;
@@ -1397,9 +1408,14 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
           /* the re-scored offsets of a candidate lie within 512 samples of each other: its window is compulsory traffic once */
           prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
           PROF (ctx);
-          k_refine_exact_sum<<<unsigned ((np * n_bits * 2 + 63) / 64), 64, 0, ctx->stream>>> (
+          int max_bit_frames = 1;
+          for (int b = 0; b < n_bits; b++)
+            max_bit_frames = std::max (max_bit_frames, t.h_off[b + 1] - t.h_off[b]);
+          const size_t sum_smem = size_t (kExactSumWarps) * max_bit_frames * kUD * sizeof (float);
+          if (set_smem (ctx, k_refine_exact_sum, sum_smem)) return 1;
+          k_refine_exact_sum<<<unsigned ((np * n_bits * 2 + kExactSumWarps - 1) / kExactSumWarps), kExactSumWarps * 32, sum_smem, ctx->stream>>> (
             ctx->r_ent_ud.as<float>(), ctx->cand_start.as<long long>(), int (np), (long long) ctx->pcm_frames, ctx->pcm_ch, t.ent.as<awm_sync_entry>(), t.n_ent,
-            t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last, ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>());
+            t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last, max_bit_frames, ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>());
           LAUNCH_CHECK ("k_refine_exact_sum");
           CK (cudaMemcpyAsync (e_ud.data(), ctx->r_ud.p, e_ud.size() * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
           CK (cudaMemcpyAsync (e_cnt.data(), ctx->r_cnt.p, e_cnt.size() * sizeof (int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -289,55 +289,49 @@ k_refine_exact_fft (const float *__restrict__ pcm, long long n_frames, int C, co
     }
 }
 
-__global__ void
+// One warp per (pair, sync bit, up / down): the 30 band values of every frame of the bit are first staged in shared memory by the
+// whole warp (coalesced), then lane 0 adds them one after the other in the reference's order -- the chain of ~2550 dependent float
+// additions is what this kernel's time consists of, the loads no longer sit between them.
+constexpr int kExactSumWarps = 4;
+
+__global__ void __launch_bounds__ (kExactSumWarps * 32)
 k_refine_exact_sum (const float *__restrict__ vals, const long long *__restrict__ pair_start, int n_pairs, long long n_frames, int C,
                     const awm_sync_entry *__restrict__ g_ent, int n_ent, const int *__restrict__ g_bit_off, int n_bits, int total_frame_count,
-                    long long wav_first, long long wav_last, float *__restrict__ out_ud /* [pair][n_bits][2] */, int *__restrict__ out_cnt,
-                    unsigned char *__restrict__ out_valid)
+                    long long wav_first, long long wav_last, int max_bit_frames,
+                    float *__restrict__ out_ud /* [pair][n_bits][2] */, int *__restrict__ out_cnt, unsigned char *__restrict__ out_valid)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__ (16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *stage = reinterpret_cast<float *> (smem) + size_t (w) * max_bit_frames * kUD;
+  const int i = blockIdx.x * kExactSumWarps + w;
   if (i >= n_pairs * n_bits * 2)
     return;
   const int p = i / (n_bits * 2), bit = (i / 2) % n_bits, which = i & 1;       // which: 0 = up bands, 1 = down bands
   const long long fine = pair_start[p];
   const bool valid = fine + (long long) total_frame_count * kFrame <= n_frames;
-  if (bit == 0 && which == 0)
+  if (bit == 0 && which == 0 && lane == 0)
     out_valid[p] = valid ? 1 : 0;
   if (!valid)
     return;
+  const int e0 = g_bit_off[bit], e1 = g_bit_off[bit + 1];
+  for (int k = lane; k < (e1 - e0) * kUD; k += 32)
+    stage[k] = __ldg (vals + ((size_t) p * n_ent + e0 + k / kUD) * (2 * kUD) + which * kUD + k % kUD);
+  __syncwarp();
+  if (lane != 0)
+    return;
   float mag = 0.f;
   int cnt = 0;
-  const int e0 = g_bit_off[bit], e1 = g_bit_off[bit + 1];
-  // the values of frame e + 1 are fetched (15 x 8 bytes, 8-byte aligned) while those of frame e are added one after the other
-  float2 cur[kUD / 2], nxt[kUD / 2];
-  auto fetch = [&] (int e, float2 (&r)[kUD / 2])
-    {
-      const float2 *v2 = reinterpret_cast<const float2 *> (vals + ((size_t) p * n_ent + e) * (2 * kUD) + which * kUD);
-#pragma unroll
-      for (int k = 0; k < kUD / 2; k++)
-        r[k] = __ldg (v2 + k);
-    };
-  if (e0 < e1)
-    fetch (e0, cur);
   for (int e = e0; e < e1; e++)
     {
-      if (e + 1 < e1)
-        fetch (e + 1, nxt);
       const long long start = fine + (long long) g_ent[e].frame * kFrame;
       const long long f_first = start * C, f_last = (start + kFrame) * C;
-      if (!(f_last < wav_first || f_first > wav_last))     // frames in digital silence are not counted
-        {
+      if (f_last < wav_first || f_first > wav_last)        // frames in digital silence are not counted
+        continue;
+      const float *v = stage + (e - e0) * kUD;
 #pragma unroll
-          for (int k = 0; k < kUD / 2; k++)
-            {
-              mag = __fadd_rn (mag, cur[k].x);
-              mag = __fadd_rn (mag, cur[k].y);
-            }
-          cnt++;
-        }
-#pragma unroll
-      for (int k = 0; k < kUD / 2; k++)
-        cur[k] = nxt[k];
+      for (int k = 0; k < kUD; k++)
+        mag = __fadd_rn (mag, v[k]);
+      cnt++;
     }
   out_ud[((size_t) p * n_bits + bit) * 2 + which] = mag;
   if (which == 0)
