@@ -59,6 +59,50 @@ struct DevBuf
   template<class T> T *as() { return static_cast<T *> (p); }
 };
 
+/* page-locked staging memory for the small lists that go back and forth between the stages of a `get` (candidate lists, per-offset
+ * sums, soft bits, code words): copies from / to pageable memory are staged by the driver and block the host; with pinned memory
+ * the copies of a stage are queued back to back and cost one synchronisation.  Bump allocator, reset at the start of an API call. */
+struct PinArena
+{
+  struct Chunk { unsigned char *p; size_t cap; };
+  std::vector<Chunk> chunks;
+  size_t cur = 0, off = 0;
+  void reset() { cur = 0; off = 0; }
+  void *alloc (size_t n)
+  {
+    n = (n + 63) & ~size_t (63);
+    for (;;)
+      {
+        if (cur < chunks.size() && off + n <= chunks[cur].cap)
+          {
+            void *r = chunks[cur].p + off;
+            off += n;
+            return r;
+          }
+        if (cur + 1 < chunks.size())
+          {
+            cur++;
+            off = 0;
+            continue;
+          }
+        Chunk c { nullptr, std::max<size_t> (n, size_t (4) << 20) };
+        if (cudaMallocHost (reinterpret_cast<void **> (&c.p), c.cap) != cudaSuccess)
+          return nullptr;
+        chunks.push_back (c);
+        cur = chunks.size() - 1;
+        off = 0;
+      }
+  }
+  template<class T> T *get (size_t count) { return static_cast<T *> (alloc (std::max<size_t> (count, 1) * sizeof (T))); }
+  void release()
+  {
+    for (auto& c : chunks)
+      cudaFreeHost (c.p);
+    chunks.clear();
+    reset();
+  }
+};
+
 struct SyncTab
 {
   DevBuf ent, off, sorted, groups;
@@ -108,6 +152,8 @@ struct awm_ctx
   DevBuf blk_start, D, raw;          // decode
   DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
   DevBuf emb_in, emb_out, emb_in16, emb_out16, peaks, snr;
+
+  PinArena pin;
 
   // multi-GPU exchange (awm_dist_*): NCCL communicator of the sharded run + staging buffers
   void *nccl_comm = nullptr;
@@ -247,7 +293,13 @@ init_tables (awm_ctx *ctx)
 template<class K> int
 set_smem (awm_ctx *ctx, K kernel, size_t bytes)
 {
+  /* the attribute sticks to the function: one driver call per kernel (and size), not one per launch */
+  static std::map<std::pair<const void *, int>, size_t> done;
+  size_t& have = done[{ reinterpret_cast<const void *> (kernel), ctx->device }];
+  if (have >= bytes && have)
+    return 0;
   CK (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int (bytes)));
+  have = bytes;
   return 0;
 }
 
@@ -299,6 +351,7 @@ awm_destroy (awm_ctx *ctx)
                      &ctx->win512, &ctx->sp_clip, &ctx->sp_sub, &ctx->sp_mags, &ctx->sp_mag_jobs, &ctx->sp_cmp_jobs, &ctx->sp_best };
   for (DevBuf *b : bufs)
     b->release();
+  ctx->pin.release();
   ctx->dist_send.release();
   ctx->dist_recv.release();
   if (ctx->dist_hsend) cudaFreeHost (ctx->dist_hsend);
@@ -1182,18 +1235,20 @@ awm_sync_peaks (awm_ctx *ctx, double min_abs_quality, awm_search_score *out, siz
                                                                 reinterpret_cast<awm_search_score *> (base + kHead), (unsigned long long) max,
                                                                 reinterpret_cast<unsigned long long *> (base));
   LAUNCH_CHECK ("k_peaks");
-  static thread_local std::vector<unsigned char> stage;
   const size_t first = std::min (max, kFirst);
-  stage.resize (kHead + first * sizeof (awm_search_score));
-  CK (cudaMemcpyAsync (stage.data(), base, stage.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->pin.reset();
+  unsigned char *stage = ctx->pin.get<unsigned char> (kHead + first * sizeof (awm_search_score));
+  if (!stage)
+    return fail (ctx, "awm_sync_peaks: out of page-locked memory");
+  CK (cudaMemcpyAsync (stage, base, kHead + first * sizeof (awm_search_score), cudaMemcpyDeviceToHost, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
   unsigned long long cnt = 0;
-  memcpy (&cnt, stage.data(), sizeof (cnt));
+  memcpy (&cnt, stage, sizeof (cnt));
   *n = size_t (cnt);
   const size_t got = std::min<size_t> (cnt, max);
   if (got)
     {
-      memcpy (out, stage.data() + kHead, std::min (got, first) * sizeof (awm_search_score));
+      memcpy (out, stage + kHead, std::min (got, first) * sizeof (awm_search_score));
       if (got > first)
         {
           CK (cudaMemcpyAsync (out + first, base + kHead + first * sizeof (awm_search_score), (got - first) * sizeof (awm_search_score), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1231,8 +1286,11 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
   CK (ctx->r_ud.reserve (nc * kOffsets * n_bits * 2 * sizeof (float)));
   CK (ctx->r_cnt.reserve (nc * kOffsets * n_bits * sizeof (int)));
   CK (ctx->rvalid.reserve (nc * kOffsets));
-  std::vector<long long> h_start (nc);
-  std::vector<int> h_noff (nc);
+  ctx->pin.reset();
+  long long *h_start = ctx->pin.get<long long> (nc);
+  int *h_noff = ctx->pin.get<int> (nc);
+  if (!h_start || !h_noff)
+    return fail (ctx, "awm_sync_refine: out of page-locked memory");
   for (size_t c = 0; c < nc; c++)
     {
       // int start = max (int (index) - sync_search_step, 0); end = index + sync_search_step; step sync_search_fine
@@ -1241,8 +1299,8 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
       h_start[c] = start;
       h_noff[c] = int (std::min<long long> ((end - start) / 8 + 1, kOffsets));
     }
-  CK (cudaMemcpyAsync (ctx->cand_start.p, h_start.data(), nc * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
-  CK (cudaMemcpyAsync (ctx->cand_noff.p, h_noff.data(), nc * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaMemcpyAsync (ctx->cand_start.p, h_start, nc * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK (cudaMemcpyAsync (ctx->cand_noff.p, h_noff, nc * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
   /* default: sliding DFT over the 65 offsets (awm_refine_slide.cuh); AWM_REFINE=fft selects the kernel that transforms every
    * frame of every offset afresh (also used for more than two channels) */
   static const bool force_fft = [] { const char *e = getenv ("AWM_REFINE"); return e && !strcmp (e, "fft"); } ();
@@ -1305,12 +1363,15 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
        * offsets) is read once -- the 65 offsets x 6 bits re-read it from L2 */
       prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
     }
-  std::vector<float> h_ud (nc * kOffsets * n_bits * 2);
-  std::vector<int> h_cnt (nc * kOffsets * n_bits);
-  std::vector<unsigned char> h_valid (nc * kOffsets);
-  CK (cudaMemcpyAsync (h_ud.data(), ctx->r_ud.p, h_ud.size() * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
-  CK (cudaMemcpyAsync (h_cnt.data(), ctx->r_cnt.p, h_cnt.size() * sizeof (int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK (cudaMemcpyAsync (h_valid.data(), ctx->rvalid.p, h_valid.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t n_ud = nc * kOffsets * n_bits * 2, n_cnt = nc * kOffsets * n_bits, n_val = nc * kOffsets;
+  float *h_ud = ctx->pin.get<float> (n_ud);
+  int *h_cnt = ctx->pin.get<int> (n_cnt);
+  unsigned char *h_valid = ctx->pin.get<unsigned char> (n_val);
+  if (!h_ud || !h_cnt || !h_valid)
+    return fail (ctx, "awm_sync_refine: out of page-locked memory");
+  CK (cudaMemcpyAsync (h_ud, ctx->r_ud.p, n_ud * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaMemcpyAsync (h_cnt, ctx->r_cnt.p, n_cnt * sizeof (int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK (cudaMemcpyAsync (h_valid, ctx->rvalid.p, n_val, cudaMemcpyDeviceToHost, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
   // sync_decode epilogue (src/syncfinder.cc:94-114,144-152) from the per-bit float sums
   auto quality_of = [&] (const float *ud, const int *cnt, size_t base) -> double
@@ -1342,7 +1403,7 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
           {
             const bool v = o < h_noff[c] && h_valid[c * kOffsets + o];
             valid_out[c * kOffsets + o] = v ? 1 : 0;
-            q_out[c * kOffsets + o] = v ? quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o) : 0.0;
+            q_out[c * kOffsets + o] = v ? quality_of (h_ud, h_cnt, c * kOffsets + o) : 0.0;
           }
       return 0;
     }
@@ -1363,7 +1424,7 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
           std::vector<std::pair<double, int>> ranked;          // (-|q - local_mean|, offset): ascending sort = best first, lower offset first
           for (int o = 0; o < h_noff[c]; o++)
             if (h_valid[c * kOffsets + o])
-              ranked.push_back ({ -fabs (quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o) - scores[c].local_mean), o });
+              ranked.push_back ({ -fabs (quality_of (h_ud, h_cnt, c * kOffsets + o) - scores[c].local_mean), o });
           std::sort (ranked.begin(), ranked.end());
           size_t keep = 0;
           while (keep < ranked.size() && ranked[keep].first <= ranked[0].first + kVerifyMargin)
@@ -1386,9 +1447,13 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
             }
         }
       const size_t np = p_start.size();
-      std::vector<float> e_ud (np * n_bits * 2);
-      std::vector<int> e_cnt (np * n_bits);
-      std::vector<unsigned char> e_valid (np);
+      float *e_ud = ctx->pin.get<float> (np * n_bits * 2);
+      int *e_cnt = ctx->pin.get<int> (np * n_bits);
+      unsigned char *e_valid = ctx->pin.get<unsigned char> (np);
+      long long *e_start = ctx->pin.get<long long> (np);
+      if (!e_ud || !e_cnt || !e_valid || !e_start)
+        return fail (ctx, "awm_sync_refine: out of page-locked memory");
+      std::copy (p_start.begin(), p_start.end(), e_start);
       if (np)
         {
           CK (ctx->cand_start.reserve (np * sizeof (long long)));
@@ -1396,7 +1461,7 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
           CK (ctx->r_ud.reserve (np * n_bits * 2 * sizeof (float)));
           CK (ctx->r_cnt.reserve (np * n_bits * sizeof (int)));
           CK (ctx->rvalid.reserve (np));
-          CK (cudaMemcpyAsync (ctx->cand_start.p, p_start.data(), np * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+          CK (cudaMemcpyAsync (ctx->cand_start.p, e_start, np * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
           const size_t smem = fft_smem_bytes (kExactWarps) + kExactWarps * 96 * sizeof (float);
           if (set_smem (ctx, k_refine_exact_fft, smem)) return 1;
           const long long jobs = (long long) np * t.n_ent;
@@ -1417,9 +1482,9 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
             ctx->r_ent_ud.as<float>(), ctx->cand_start.as<long long>(), int (np), (long long) ctx->pcm_frames, ctx->pcm_ch, t.ent.as<awm_sync_entry>(), t.n_ent,
             t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last, max_bit_frames, ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>());
           LAUNCH_CHECK ("k_refine_exact_sum");
-          CK (cudaMemcpyAsync (e_ud.data(), ctx->r_ud.p, e_ud.size() * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
-          CK (cudaMemcpyAsync (e_cnt.data(), ctx->r_cnt.p, e_cnt.size() * sizeof (int), cudaMemcpyDeviceToHost, ctx->stream));
-          CK (cudaMemcpyAsync (e_valid.data(), ctx->rvalid.p, e_valid.size(), cudaMemcpyDeviceToHost, ctx->stream));
+          CK (cudaMemcpyAsync (e_ud, ctx->r_ud.p, np * n_bits * 2 * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+          CK (cudaMemcpyAsync (e_cnt, ctx->r_cnt.p, np * n_bits * sizeof (int), cudaMemcpyDeviceToHost, ctx->stream));
+          CK (cudaMemcpyAsync (e_valid, ctx->rvalid.p, np, cudaMemcpyDeviceToHost, ctx->stream));
           CK (cudaStreamSynchronize (ctx->stream));
         }
       std::vector<double> best_quality (nc);
@@ -1431,12 +1496,12 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
         }
       for (size_t p = 0; p < np; p++)               // starting value: the exact quality at the approx index
         if (e_valid[p] && uint64_t (p_start[p]) == scores[p_cand[p]].index)
-          best_quality[p_cand[p]] = quality_of (e_ud.data(), e_cnt.data(), p);
+          best_quality[p_cand[p]] = quality_of (e_ud, e_cnt, p);
       for (size_t p = 0; p < np; p++)               // per candidate in ascending offset order
         if (e_valid[p])
           {
             const size_t c = size_t (p_cand[p]);
-            const double q = quality_of (e_ud.data(), e_cnt.data(), p);
+            const double q = quality_of (e_ud, e_cnt, p);
             if (fabs (q - scores[c].local_mean) > fabs (best_quality[c] - scores[c].local_mean))   // src/syncfinder.cc:436-440
               {
                 best_quality[c] = q;
@@ -1457,11 +1522,11 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
       uint64_t best_index = sc.index;
       const int o_self = int (((long long) sc.index - h_start[c]) / 8);      // starting value: the exact quality at the approx index (see above)
       if (o_self < h_noff[c] && h_valid[c * kOffsets + o_self])
-        best_quality = quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o_self);
+        best_quality = quality_of (h_ud, h_cnt, c * kOffsets + o_self);
       for (int o = 0; o < h_noff[c]; o++)
         if (h_valid[c * kOffsets + o])
           {
-            const double q = quality_of (h_ud.data(), h_cnt.data(), c * kOffsets + o);
+            const double q = quality_of (h_ud, h_cnt, c * kOffsets + o);
             if (fabs (q - sc.local_mean) > fabs (best_quality - sc.local_mean))   // src/syncfinder.cc:436-440
               {
                 best_quality = q;
@@ -1684,14 +1749,19 @@ awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size_t n
   size_t batch = std::max<size_t> (1, (size_t (1) << 30) / per_blk);
   const size_t smem = fft_smem_bytes (kDecodeWarps);
   if (set_smem (ctx, k_decode_fft, smem)) return 1;
-  std::vector<float> h_raw;
+  ctx->pin.reset();
   for (size_t b0 = 0; b0 < starts.size(); b0 += batch)
     {
       const size_t nb = std::min (batch, starts.size() - b0);
+      long long *h_starts = ctx->pin.get<long long> (nb);
+      float *h_raw = ctx->pin.get<float> (nb * k.n_coded);
+      if (!h_starts || !h_raw)
+        return fail (ctx, "awm_decode_blocks: out of page-locked memory");
+      std::copy (starts.begin() + b0, starts.begin() + b0 + nb, h_starts);
       CK (ctx->D.reserve (nb * per_blk));
       CK (ctx->blk_start.reserve (nb * sizeof (long long)));
       CK (ctx->raw.reserve (nb * k.n_coded * sizeof (float)));
-      CK (cudaMemcpyAsync (ctx->blk_start.p, starts.data() + b0, nb * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+      CK (cudaMemcpyAsync (ctx->blk_start.p, h_starts, nb * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
       const int pairs = (C + 1) / 2;
       const long long jobs = (long long) nb * k.fpb * pairs;
       PROF (ctx);
@@ -1705,11 +1775,10 @@ awm_decode_blocks (awm_ctx *ctx, int key_slot, const uint64_t *indices, size_t n
       k_mix_decode<<<grid, 128, 0, ctx->stream>>> (ctx->D.as<float>(), int (nb), C, k.fpb, k.mix.as<awm_mix_entry>(), k.frames_per_bit,
                                                    k.n_coded, k.order.as<uint16_t>(), ctx->raw.as<float>());
       LAUNCH_CHECK ("k_mix_decode");
-      h_raw.resize (nb * k.n_coded);
-      CK (cudaMemcpyAsync (h_raw.data(), ctx->raw.p, nb * k.n_coded * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaMemcpyAsync (h_raw, ctx->raw.p, nb * k.n_coded * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
       CK (cudaStreamSynchronize (ctx->stream));
       for (size_t b = 0; b < nb; b++)
-        memcpy (raw_bits_out + which[b0 + b] * k.n_coded, h_raw.data() + b * k.n_coded, k.n_coded * sizeof (float));
+        memcpy (raw_bits_out + which[b0 + b] * k.n_coded, h_raw + b * k.n_coded, k.n_coded * sizeof (float));
     }
   return 0;
 }
@@ -1751,17 +1820,34 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits,
       CK (ctx->vit_dec.reserve (nj * steps * kVitWords * sizeof (uint32_t)));
       CK (ctx->vit_bits.reserve (nj * n_msg_bits));
       CK (ctx->vit_err.reserve (nj * sizeof (float)));
-      CK (cudaMemcpyAsync (ctx->vit_raw.p, raw_bits + base, n_raw * sizeof (float), cudaMemcpyDefault, ctx->stream));
-      CK (cudaMemcpyAsync (ctx->vit_off.p, rel.data(), nj * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
-      CK (cudaMemcpyAsync (ctx->vit_types.p, block_types + j0, nj * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+      /* host inputs / outputs pass through page-locked staging: the three uploads, the launch and the two downloads queue up
+       * without the host waiting in between */
+      ctx->pin.reset();
+      const bool raw_on_device = is_device_ptr (raw_bits);
+      float *h_in = raw_on_device ? nullptr : ctx->pin.get<float> (size_t (n_raw));
+      long long *h_rel = ctx->pin.get<long long> (nj);
+      int *h_types = ctx->pin.get<int> (nj);
+      unsigned char *h_bits = ctx->pin.get<unsigned char> (nj * n_msg_bits);
+      float *h_err = ctx->pin.get<float> (nj);
+      if ((!raw_on_device && !h_in) || !h_rel || !h_types || !h_bits || !h_err)
+        return fail (ctx, "awm_viterbi: out of page-locked memory");
+      if (h_in)
+        memcpy (h_in, raw_bits + base, size_t (n_raw) * sizeof (float));
+      std::copy (rel.begin(), rel.end(), h_rel);
+      std::copy (block_types + j0, block_types + j0 + nj, h_types);
+      CK (cudaMemcpyAsync (ctx->vit_raw.p, h_in ? h_in : raw_bits + base, n_raw * sizeof (float), cudaMemcpyDefault, ctx->stream));
+      CK (cudaMemcpyAsync (ctx->vit_off.p, h_rel, nj * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+      CK (cudaMemcpyAsync (ctx->vit_types.p, h_types, nj * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
       PROF (ctx);
       k_viterbi<<<unsigned (nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), ctx->vit_off.as<long long>(), n_msg_bits, ctx->vit_types.as<int>(), hard,
                                                                   steps, ctx->vit_dec.as<uint32_t>(),
                                                                   ctx->vit_bits.as<unsigned char>(), ctx->vit_err.as<float>());
       LAUNCH_CHECK ("k_viterbi");
-      CK (cudaMemcpyAsync (bits_out + j0 * n_msg_bits, ctx->vit_bits.p, nj * n_msg_bits, cudaMemcpyDeviceToHost, ctx->stream));
-      CK (cudaMemcpyAsync (error_out + j0, ctx->vit_err.p, nj * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaMemcpyAsync (h_bits, ctx->vit_bits.p, nj * n_msg_bits, cudaMemcpyDeviceToHost, ctx->stream));
+      CK (cudaMemcpyAsync (h_err, ctx->vit_err.p, nj * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));
       CK (cudaStreamSynchronize (ctx->stream));
+      memcpy (bits_out + j0 * n_msg_bits, h_bits, nj * n_msg_bits);
+      memcpy (error_out + j0, h_err, nj * sizeof (float));
     }
   return 0;
 }
