@@ -150,7 +150,7 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
         {
           const int shift_idx = cur.t & 3, f0 = (cur.t >> 2) * kTcTile;
           const int a = it % A_BUFS, use = it / A_BUFS;
-          mbar_wait (&a_empty[a], (use & 1) ^ 1);                 // the MMAs that read this buffer last time are done
+          mbar_wait_relaxed (&a_empty[a], (use & 1) ^ 1);         // the MMAs that read this buffer last time are done
           unsigned char *A = abuf + size_t (a) * kTcABytes;
           const int t_now = cur.t;
           for (; cur.t == t_now; )
@@ -175,15 +175,18 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
                     }
                   __syncwarp();                                   // all lanes hold their samples before the transposes reuse the buffer
                   fft1024_warp (re, im, s.tw, s.xbuf, lane, [&] { if (nxt_tma) prefetch (nxt); });
+                  // dB with MUFU.LG2 (__log2f): its error (~2e-7 relative) is two orders below the 2^-16 absolute resolution the
+                  // value is about to be stored with (fp16 hi + lo), and saves ~170 of the ~2000 instructions of a frame
+                  auto db = [] (float re_, float im_) { const float a2 = __fmaf_rn (re_, re_, __fmul_rn (im_, im_)); return a2 > 0.0f ? __log2f (a2) * 3.01029995663981f : -96.f; };
                   float ar, ai, br, bi;
                   unpack_pair<0> (re, im, lane, ar, ai, br, bi);
-                  acc[0] = db_from_complex (ar, ai, -96.f) + db_from_complex (br, bi, -96.f);
+                  acc[0] = db (ar, ai) + db (br, bi);
                   unpack_pair<1> (re, im, lane, ar, ai, br, bi);
-                  acc[1] = db_from_complex (ar, ai, -96.f) + db_from_complex (br, bi, -96.f);
+                  acc[1] = db (ar, ai) + db (br, bi);
                   unpack_pair<2> (re, im, lane, ar, ai, br, bi);
-                  acc[2] = db_from_complex (ar, ai, -96.f) + db_from_complex (br, bi, -96.f);
+                  acc[2] = db (ar, ai) + db (br, bi);
                   unpack_pair<3> (re, im, lane, ar, ai, br, bi);
-                  acc[3] = db_from_complex (ar, ai, -96.f) + db_from_complex (br, bi, -96.f);
+                  acc[3] = db (ar, ai) + db (br, bi);
                 }
               else
                 {
@@ -263,14 +266,14 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
           for (int c = 0; c < n_chunks; c++, g++)
             {
               if (g > 0)
-                mbar_wait_relaxed (b_free, (g - 1) & 1, 64);                  // the MMAs of the previous chunk have read the B buffer
+                mbar_wait_relaxed (b_free, (g - 1) & 1);                      // the MMAs of the previous chunk have read the B buffer
               mbar_arrive_expect_tx (b_full, kTcBBytes);
               bulk_load (bbuf, masks + size_t (c) * kTcBBytes, kTcBBytes, b_full);
               if (c == 0)
                 mbar_wait_relaxed (&a_full[a], use & 1);                // all FFT warps have delivered their rows of the tile
-              mbar_wait_relaxed (b_full, g & 1, 64);
+              mbar_wait_relaxed (b_full, g & 1);
               const int tb = g & 1;
-              mbar_wait_relaxed (&tmem_empty[tb], ((g >> 1) & 1) ^ 1, 64);    // the epilogue has drained this accumulator
+              mbar_wait_relaxed (&tmem_empty[tb], ((g >> 1) & 1) ^ 1);    // the epilogue has drained this accumulator
               tc_fence_after_sync();
 #pragma unroll
               for (int sp = 0; sp < 2; sp++)

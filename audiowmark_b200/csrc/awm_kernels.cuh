@@ -5,6 +5,7 @@
 // per kernel (paths relative to the reference tree).
 #pragma once
 #include "awm_fft.cuh"
+#include "awm_f32x2.cuh"
 #include "../../include/awm_b200.h"
 #include <math.h>
 
@@ -647,13 +648,17 @@ template<int TYPE> __device__ __forceinline__ uint32_t
 viterbi_step (const float *__restrict__ d_old, float (&outv)[32], unsigned hi, const float *m0, const float *m1, int u)
 {
   constexpr int RATE = TYPE == AWM_BLOCK_AB ? 12 : 6;
-  float mA[RATE], mB[RATE];               // metric for output bit == hi-bit / != hi-bit
+  // The two candidates of a new state -- coming from predecessor ps0 and from ps1 -- add the SAME branch metrics in the same order,
+  // so they travel as one packed pair (d0, d1) and every step of the sum is one FADD2 (add.rn.f32x2: both halves rounded exactly like
+  // __fadd_rn) instead of two FADDs: the add-compare-select loop issues half the instructions, bit-identical metrics.
+  f2 mA[RATE], mB[RATE];                  // (m, m): metric for output bit == hi-bit / != hi-bit
 #pragma unroll
   for (int p = 0; p < RATE; p++)
     {
       const bool h = (hi >> p) & 1u;
-      mA[p] = h ? m1[p] : m0[p];
-      mB[p] = h ? m0[p] : m1[p];
+      const float a = h ? m1[p] : m0[p], b = h ? m0[p] : m1[p];
+      mA[p] = f2_make (a, a);
+      mB[p] = f2_make (b, b);
     }
   uint32_t word = 0;
 #pragma unroll
@@ -661,18 +666,16 @@ viterbi_step (const float *__restrict__ d_old, float (&outv)[32], unsigned hi, c
     {
       const float4 x = *reinterpret_cast<const float4 *> (d_old + vit_pos (16 * u + 4 * v));
       const float4 y = *reinterpret_cast<const float4 *> (d_old + vit_pos (16 * u + 4 * v + (kVitStates >> 1)));
-      const float a0[4] = { x.x, x.y, x.z, x.w }, a1[4] = { y.x, y.y, y.z, y.w };
+      const f2 a01[4] = { f2_make (x.x, y.x), f2_make (x.y, y.y), f2_make (x.z, y.z), f2_make (x.w, y.w) };
 #pragma unroll
       for (int q = 0; q < 8; q++)
         {
-          float d0 = a0[q >> 1], d1 = a1[q >> 1];
+          f2 d = a01[q >> 1];
 #pragma unroll
           for (int p = 0; p < RATE; p++)
-            {
-              const float m = cparity (unsigned (8 * v + q) & type_generator<TYPE> (p)) ? mB[p] : mA[p];
-              d0 = __fadd_rn (d0, m);
-              d1 = __fadd_rn (d1, m);
-            }
+            d = f2_add (d, cparity (unsigned (8 * v + q) & type_generator<TYPE> (p)) ? mB[p] : mA[p]);
+          float d0, d1;
+          f2_split (d, d0, d1);
           const bool take1 = d1 < d0;
           outv[8 * v + q] = take1 ? d1 : d0;
           word |= (take1 ? 1u : 0u) << (8 * v + q);

@@ -118,9 +118,45 @@ k_refine_slide (const float *__restrict__ pcm, long long n_frames,
       m_dn[b] = md;
     }
 
+  // The 16 samples that enter / leave the frame at the next slide are loaded one iteration ahead: their latency hides behind the Hann /
+  // dB / reduction work of the current offset instead of stalling the first subtraction of the slide (17 % of this kernel's stall
+  // samples before).  The address is clamped to the last slide that exists, so the load itself needs no predicate.
+  auto load_delta = [&] (long long m, float (&dl)[8], float (&dr)[8])
+    {
+      const long long mm = m + 1 < n_valid ? m : (n_valid >= 2 ? n_valid - 2 : 0);
+      const long long start = p0 + 8 * mm;
+      if (C == 2)
+        {
+          const float2 *po = reinterpret_cast<const float2 *> (pcm) + start;
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            {
+              const float2 xo = __ldg (po + j), xi = __ldg (po + kFrame + j);
+              dl[j] = xi.x - xo.x;
+              dr[j] = xi.y - xo.y;
+            }
+        }
+      else
+        {
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            {
+              dl[j] = __ldg (pcm + start + kFrame + j) - __ldg (pcm + start + j);
+              dr[j] = 0.f;
+            }
+        }
+    };
+  // dB for RANKING the offsets: MUFU.LG2 (__log2f, abs. error ~1e-7 on these magnitudes -- an order below the float sliding DFT's own
+  // error) instead of the ~22-instruction log2f; the offsets that matter are scored again exactly by k_refine_exact_*
+  auto db_fast = [] (float abs2) { return abs2 > 0.0f ? __log2f (abs2) * 3.01029995663981f : -96.0f; };
+  if (n_valid > 1 && p0 + 8 * (n_valid - 2) + kFrame + 8 > n_frames)       // cannot happen (n_valid is cut to the stream above); keeps the loads in bounds
+    return;
   for (long long m = 0; m < n_valid; m++)
     {
       const long long start = p0 + 8 * m;
+      float dl[8], dr[8];
+      if (n_valid > 1)
+        load_delta (m, dl, dr);
       // ---- Hann in the frequency domain + dB + band sums
       const float ll_re = __shfl_up_sync (0xffffffffu, rl_re[2], 1), ll_im = __shfl_up_sync (0xffffffffu, rl_im[2], 1);
       const float nl_re = __shfl_down_sync (0xffffffffu, rl_re[0], 1), nl_im = __shfl_down_sync (0xffffffffu, rl_im[0], 1);
@@ -138,13 +174,13 @@ k_refine_slide (const float *__restrict__ pcm, long long n_frames,
           const float ql_re = b == kSlideBins - 1 ? nl_re : rl_re[b + 1], ql_im = b == kSlideBins - 1 ? nl_im : rl_im[b + 1];
           const float hl_re = rl_re[b] - 0.5f * (pl_re + ql_re), hl_im = rl_im[b] - 0.5f * (pl_im + ql_im);
           // (1/512)^2 on the squared magnitude: exact power of two, same value as scaling the spectrum first
-          float db = db_from_complex_abs2 ((hl_re * hl_re + hl_im * hl_im) * 3.814697265625e-06f);
+          float db = db_fast ((hl_re * hl_re + hl_im * hl_im) * 3.814697265625e-06f);
           if (C == 2)
             {
               const float pr_re = b == 0 ? lr_re : rr_re[b - 1], pr_im = b == 0 ? lr_im : rr_im[b - 1];
               const float qr_re = b == kSlideBins - 1 ? nr_re : rr_re[b + 1], qr_im = b == kSlideBins - 1 ? nr_im : rr_im[b + 1];
               const float hr_re = rr_re[b] - 0.5f * (pr_re + qr_re), hr_im = rr_im[b] - 0.5f * (pr_im + qr_im);
-              db += db_from_complex_abs2 ((hr_re * hr_re + hr_im * hr_im) * 3.814697265625e-06f);
+              db += db_fast ((hr_re * hr_re + hr_im * hr_im) * 3.814697265625e-06f);
             }
           u = fmaf (db, m_up[b], u);
           d = fmaf (db, m_dn[b], d);
@@ -166,27 +202,6 @@ k_refine_slide (const float *__restrict__ pcm, long long n_frames,
       if (m + 1 >= n_valid)
         break;
       // ---- slide by 8 samples
-      float dl[8], dr[8];
-      if (C == 2)
-        {
-          const float2 *po = reinterpret_cast<const float2 *> (pcm) + start;
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            {
-              const float2 xo = __ldg (po + j), xi = __ldg (po + kFrame + j);
-              dl[j] = xi.x - xo.x;
-              dr[j] = xi.y - xo.y;
-            }
-        }
-      else
-        {
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            {
-              dl[j] = __ldg (pcm + start + kFrame + j) - __ldg (pcm + start + j);
-              dr[j] = 0.f;
-            }
-        }
 #pragma unroll
       for (int b = 0; b < kSlideBins; b++)
         {

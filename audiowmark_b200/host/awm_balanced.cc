@@ -158,6 +158,13 @@ Get::Get (int rank, int world, size_t n_total, const float *pcm, const int16_t *
   m_slot = Engine::key_slot (key);
   if (m_slot < 0)
     return;
+  /* inputs short enough for the reference's ClipDecoder (src/wmget.cc:764-884: fewer than 3.1 blocks) are a few seconds of work on one
+   * GPU; the sharded driver only runs the block decoder, so it refuses them instead of returning a document without CLIP patterns */
+  if (double (n_total / Params::frame_size) < double (frames_per_block()) * 3.1)
+    {
+      error ("audiowmark: sharded get: input of %zu frames is clip sized (under 3.1 blocks); use the single GPU get\n", n_total);
+      return;
+    }
   m_plan = chunk_plan (n_total, sample_rate);
   m_slices = rank_slices (m_plan, rank, world, n_total);
   for (const Slice& sl : m_slices)

@@ -116,6 +116,15 @@ def test_balanced_get_entry_point_single_rank():
         H.set_params()
 
 
+def test_balanced_get_refuses_clip_sized_input():
+    """inputs under 3.1 blocks go through the reference's ClipDecoder (src/wmget.cc:764-884), which the sharded driver does not run:
+    it must refuse them loudly instead of returning a document without CLIP patterns"""
+    y = T.noise(100.0, 2, seed=25)
+    with pytest.raises(RuntimeError):
+        H.balanced_get(y, 0, y.shape[0])
+    assert any(m["type"].startswith("CLIP") for m in H.get(H.add(y, T.PAYLOAD))["matches"])    # the single GPU get does run it
+
+
 @pytest.mark.parametrize("limiter", [True, False])
 def test_streaming_add_equals_whole_stream_add(limiter):
     """`audiowmark add` reads, embeds and writes window by window (bounded memory, first output long before EOF; reference loop
