@@ -737,15 +737,33 @@ pcm_prefetch_any (awm_ctx *ctx, const void *pcm, bool s16, size_t n_frames, int 
   CK (pf.buf.reserve (n_val * sizeof (float)));
   if (!pf.done)
     CK (cudaEventCreateWithFlags (&pf.done, cudaEventDisableTiming));
-  if (s16)
+  /* Consecutive chunks of `get` overlap (WavChunkLoader: 134 s of 30 min).  When this span starts inside the span that was prefetched
+   * just before it and is still waiting to be bound, its head is already on the device: it is copied from there (device to device,
+   * ordered behind that upload on the same stream) and only the rest crosses PCIe -- 7 % fewer bytes for a 1 h stream. */
+  size_t head = 0;                              // frames taken from the previous prefetch
+  {
+    awm_ctx::Prefetch& prev = ctx->pref[ctx->pref_next ^ 1];
+    const size_t esz = (s16 ? sizeof (int16_t) : sizeof (float)) * size_t (channels);
+    const char *b0 = static_cast<const char *> (prev.src), *p0 = static_cast<const char *> (pcm);
+    if (prev.valid && prev.s16 == s16 && prev.ch == channels && b0 && p0 > b0 && p0 < b0 + prev.n_frames * esz && size_t (p0 - b0) % esz == 0)
+      {
+        const size_t first = size_t (p0 - b0) / esz;
+        head = std::min (prev.n_frames - first, n_frames);
+        if ((head * channels) & 1)                // the conversion kernel stores float pairs: keep the rest 8-byte aligned
+          head--;
+        CK (cudaMemcpyAsync (pf.buf.p, prev.buf.as<float>() + first * channels, head * channels * sizeof (float), cudaMemcpyDeviceToDevice, ctx->s_in));
+      }
+  }
+  const size_t rest = (n_frames - head) * channels, head_val = head * channels;
+  if (rest && s16)
     {
       CK (pf.buf16.reserve (n_val * sizeof (int16_t)));
-      CK (cudaMemcpyAsync (pf.buf16.p, pcm, n_val * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->s_in));
-      k_s16_to_f32<<<unsigned (((n_val + 1) / 2 + 255) / 256), 256, 0, ctx->s_in>>> (pf.buf16.as<int16_t>(), pf.buf.as<float>(), (long long) n_val);
+      CK (cudaMemcpyAsync (pf.buf16.p, static_cast<const int16_t *> (pcm) + head_val, rest * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->s_in));
+      k_s16_to_f32<<<unsigned (((rest + 1) / 2 + 255) / 256), 256, 0, ctx->s_in>>> (pf.buf16.as<int16_t>(), pf.buf.as<float>() + head_val, (long long) rest);
       LAUNCH_CHECK ("k_s16_to_f32");
     }
-  else
-    CK (cudaMemcpyAsync (pf.buf.p, pcm, n_val * sizeof (float), cudaMemcpyHostToDevice, ctx->s_in));
+  else if (rest)
+    CK (cudaMemcpyAsync (pf.buf.as<float>() + head_val, static_cast<const float *> (pcm) + head_val, rest * sizeof (float), cudaMemcpyHostToDevice, ctx->s_in));
   CK (cudaEventRecord (pf.done, ctx->s_in));
   pf.src = pcm;
   pf.n_frames = n_frames;

@@ -107,7 +107,9 @@ int awm_set_mix_tables (awm_ctx *ctx, int key_slot, const awm_mix_entry *entries
 int awm_pcm_bind (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end);
 /* optional: start copying a HOST buffer that will be bound next (the following chunk of a long file) on a separate
  * stream while the kernels of the current chunk run; a later awm_pcm_bind with the same pointer / size / channels and
- * no padding picks the copy up instead of transferring again.  Two prefetches may be outstanding. */
+ * no padding picks the copy up instead of transferring again.  Two prefetches may be outstanding.  A span that starts inside
+ * the span prefetched just before it (the overlapping chunks of WavChunkLoader, src/wavchunkloader.cc:54-163) takes its head from
+ * that device copy and only transfers the rest; the host memory of an unbound prefetch must not change meanwhile. */
 int awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels);
 
 /* 16 bit PCM variants: the buffers hold interleaved int16 (what a 16 bit WAV file holds); conversion to / from the float
