@@ -29,42 +29,47 @@ namespace awm {
 
 constexpr int kTcTile = 128;                 // frames per tile = UMMA M
 constexpr int kTcK = 96;                     // 81 bands padded to a multiple of the UMMA K (16)
-constexpr int kTcChunkEnt = 128;             // sync entries per B chunk
-constexpr int kTcN = 2 * kTcChunkEnt;        // UMMA N: U and D column of every entry
 constexpr uint32_t kTcASplit = kTcTile * kTcK * 2;        // bytes of one fp16 term of the A tile (24 KB)
 constexpr uint32_t kTcABytes = 2 * kTcASplit;             // hi + lo
-constexpr uint32_t kTcBBytes = kTcN * kTcK * 2;           // one B chunk (48 KB)
 constexpr int kTcEpiWarps = 4;
+// CHUNK_ENT sync entries per B chunk -> UMMA N = 2 CHUNK_ENT (U and D column of every entry), chunk of N x 96 fp16.
+// 128 entries (N = 256, 48 KB) with eight FFT warps; 48 entries (N = 96, 18 KB) leave room for twelve FFT warps AND two A buffers.
+__host__ __device__ constexpr uint32_t tc_b_bytes (int chunk_ent) { return uint32_t (2 * chunk_ent) * kTcK * 2; }
+__host__ __device__ constexpr int tc_tmem_columns (int chunk_ent) { return 4 * chunk_ent <= 32 ? 32 : 4 * chunk_ent <= 64 ? 64 : 4 * chunk_ent <= 128 ? 128 : 4 * chunk_ent <= 256 ? 256 : 512; }
 
-template<int FFT_WARPS, int A_BUFS> constexpr size_t
-tc_smem_bytes() { return fft_smem_bytes (FFT_WARPS) + size_t (A_BUFS) * kTcABytes + kTcBBytes + 256; }
+template<int FFT_WARPS, int A_BUFS, int CHUNK_ENT> constexpr size_t
+tc_smem_bytes() { return fft_smem_bytes (FFT_WARPS) + size_t (A_BUFS) * kTcABytes + tc_b_bytes (CHUNK_ENT) + 256; }
 
-// host side: the 0/1 masks of all entries in operand layout, chunk after chunk ([ceil (n_ent / 128)][kTcBBytes])
+// host side: the 0/1 masks of all entries in operand layout, chunk after chunk ([ceil (n_ent / chunk_ent)][tc_b_bytes (chunk_ent)])
 inline void
-tc_build_masks (const awm_sync_entry *ent, int n_ent, std::vector<unsigned char>& out)
+tc_build_masks (const awm_sync_entry *ent, int n_ent, int chunk_ent, std::vector<unsigned char>& out)
 {
-  const int n_chunks = (n_ent + kTcChunkEnt - 1) / kTcChunkEnt;
-  out.assign (size_t (n_chunks) * kTcBBytes, 0);
+  const int n_chunks = (n_ent + chunk_ent - 1) / chunk_ent;
+  const size_t b_bytes = tc_b_bytes (chunk_ent);
+  out.assign (size_t (n_chunks) * b_bytes, 0);
   const uint16_t one = 0x3c00;               // 1.0 in fp16
   for (int e = 0; e < n_ent; e++)
     {
-      unsigned char *chunk = out.data() + size_t (e / kTcChunkEnt) * kTcBBytes;
-      const int col = 2 * (e % kTcChunkEnt);
+      unsigned char *chunk = out.data() + size_t (e / chunk_ent) * b_bytes;
+      const int col = 2 * (e % chunk_ent);
       for (int i = 0; i < kUD; i++)
         {
-          memcpy (chunk + tc::operand_offset (kTcN, col, ent[e].up[i]), &one, 2);
-          memcpy (chunk + tc::operand_offset (kTcN, col + 1, ent[e].down[i]), &one, 2);
+          memcpy (chunk + tc::operand_offset (2 * chunk_ent, col, ent[e].up[i]), &one, 2);
+          memcpy (chunk + tc::operand_offset (2 * chunk_ent, col + 1, ent[e].down[i]), &one, 2);
         }
     }
 }
 
-template<int FFT_WARPS, int A_BUFS> __global__ void __launch_bounds__ ((FFT_WARPS + kTcEpiWarps + 1) * 32, 1)
+template<int FFT_WARPS, int A_BUFS, int CHUNK_ENT> __global__ void __launch_bounds__ ((FFT_WARPS + kTcEpiWarps + 1) * 32, 1)
 k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_out, int ld,
-                const unsigned char *__restrict__ masks /* [n_chunks][kTcBBytes] */, int n_ent, int n_chunks,
+                const unsigned char *__restrict__ masks /* [n_chunks][tc_b_bytes (CHUNK_ENT)] */, int n_ent, int n_chunks,
                 float2 *__restrict__ mags /* [4][n_ent][ld] */, unsigned char *__restrict__ have,
                 long long wav_first, long long wav_last, const float2 *g_tw, const float *g_win, int tma_ok /* stereo, pcm 16-byte aligned */)
 {
   using namespace tc;
+  constexpr int kTcChunkEnt = CHUNK_ENT, kTcN = 2 * CHUNK_ENT;
+  constexpr uint32_t kTcBBytes = tc_b_bytes (CHUNK_ENT);
+  constexpr int kTmemCols = tc_tmem_columns (CHUNK_ENT);
   extern __shared__ __align__ (16) unsigned char smem[];
   FftSmem s = fft_smem_setup (smem, g_tw, g_win, FFT_WARPS);
   unsigned char *abuf = reinterpret_cast<unsigned char *> (s.extra);
@@ -92,7 +97,7 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
       fence_mbar_init();
     }
   if (w == kMmaWarp)
-    tmem_alloc (tmem_slot, 512);
+    tmem_alloc (tmem_slot, kTmemCols);
   // band columns 81 .. 95 of A are never written again and must be finite: clear everything once
   for (uint32_t i = threadIdx.x; i < A_BUFS * kTcABytes / 16; i += blockDim.x)
     reinterpret_cast<uint4 *> (abuf)[i] = make_uint4 (0, 0, 0, 0);
@@ -293,7 +298,7 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
   if (w == kMmaWarp)
     {
       tc_fence_after_sync();
-      tmem_dealloc (tmem, 512);
+      tmem_dealloc (tmem, kTmemCols);
     }
 }
 

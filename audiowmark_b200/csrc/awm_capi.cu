@@ -8,6 +8,7 @@
 #include "awm_refine_slide.cuh"
 #include "awm_approx_mags.cuh"
 #include <vector>
+#include <time.h>
 #include <string.h>
 #include "awm_approx_tc.cuh"
 #include "awm_embed_strip.cuh"
@@ -103,11 +104,19 @@ struct PinArena
   }
 };
 
+inline double
+wall_now()
+{
+  timespec ts;
+  clock_gettime (CLOCK_MONOTONIC, &ts);
+  return double (ts.tv_sec) + 1e-9 * double (ts.tv_nsec);
+}
+
 struct SyncTab
 {
   DevBuf ent, off, sorted, groups;
-  DevBuf masks;                       // 0/1 band masks of the entries as tcgen05 B operand chunks (awm_approx_tc.cuh)
-  int n_chunks = 0;
+  DevBuf masks, masks48;              // 0/1 band masks of the entries as tcgen05 B operand chunks of 128 / 48 entries (awm_approx_tc.cuh)
+  int n_chunks = 0, n_chunks48 = 0;
   int n_groups = 0;
   int n_ent = 0, n_bits = 0, total_frames = 0;
   std::vector<awm_sync_entry> h_ent;
@@ -145,6 +154,11 @@ struct awm_ctx
   struct Prefetch { DevBuf buf, buf16; bool s16 = false; const void *src = nullptr; size_t n_frames = 0; int ch = 0; cudaEvent_t done = nullptr; bool valid = false; };
   Prefetch pref[2];
   int pref_next = 0;
+  /* awm_pcm_stage: a host stream on its way into `staged` piece by piece */
+  DevBuf staged, staged16;
+  std::vector<cudaEvent_t> stage_done;           // one per piece, recorded on s_in
+  size_t stage_piece = 0, stage_frames = 0;
+  int stage_ch = 0;
 
   DevBuf dbT, have, q, scores, a_ud, a_cnt, peaks_out, peaks_cnt, a_mags;       // approx
   size_t n_scores_dev = 0;
@@ -373,6 +387,7 @@ awm_destroy (awm_ctx *ctx)
         {
           s.ent.release();
           s.masks.release();
+          s.masks48.release();
           s.off.release();
           s.sorted.release();
           s.groups.release();
@@ -380,6 +395,8 @@ awm_destroy (awm_ctx *ctx)
       k.mix.release();
       k.order.release();
     }
+  for (cudaEvent_t e : ctx->stage_done)
+    cudaEventDestroy (e);
   if (ctx->s_in)
     cudaStreamDestroy (ctx->s_in);
   if (ctx->s_out)
@@ -606,12 +623,16 @@ awm_set_sync_tables (awm_ctx *ctx, int key_slot, int mode, const awm_sync_entry 
   CK (cudaMemcpyAsync (t.groups.p, group_end.data(), group_end.size() * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
   {
-    std::vector<unsigned char> masks;
-    tc_build_masks (entries, n_entries, masks);
+    std::vector<unsigned char> masks, masks48;
+    tc_build_masks (entries, n_entries, 128, masks);
+    tc_build_masks (entries, n_entries, 48, masks48);
     CK (t.masks.reserve (masks.size()));
+    CK (t.masks48.reserve (masks48.size()));
     CK (cudaMemcpyAsync (t.masks.p, masks.data(), masks.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK (cudaMemcpyAsync (t.masks48.p, masks48.data(), masks48.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK (cudaStreamSynchronize (ctx->stream));
-    t.n_chunks = int (masks.size() / kTcBBytes);
+    t.n_chunks = int (masks.size() / tc_b_bytes (128));
+    t.n_chunks48 = int (masks48.size() / tc_b_bytes (48));
   }
   t.n_groups = int (group_end.size());
   t.n_ent = n_entries;
@@ -781,6 +802,70 @@ int awm_pcm_bind_s16 (awm_ctx *ctx, const int16_t *pcm, size_t n_frames, int cha
 int awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int channels) { return pcm_prefetch_any (ctx, pcm, false, n_frames, channels); }
 int awm_pcm_prefetch_s16 (awm_ctx *ctx, const int16_t *pcm, size_t n_frames, int channels) { return pcm_prefetch_any (ctx, pcm, true, n_frames, channels); }
 
+/* awm_pcm_stage / awm_pcm_stage_wait: see include/awm_b200.h */
+int
+awm_pcm_stage (awm_ctx *ctx, const void *pcm, int is_s16, size_t n_frames, int channels, size_t piece_frames, const float **device_out)
+{
+  if (!ctx || !pcm || !n_frames || channels <= 0 || !piece_frames || !device_out)
+    return fail (ctx, "awm_pcm_stage: bad arguments");
+  CK (cudaSetDevice (ctx->device));
+  if (is_device_ptr (pcm))
+    return fail (ctx, "awm_pcm_stage: the stream is already in device memory");
+  if (!ctx->s_in)
+    {
+      CK (cudaStreamCreateWithFlags (&ctx->s_in, cudaStreamNonBlocking));
+      CK (cudaStreamCreateWithFlags (&ctx->s_out, cudaStreamNonBlocking));
+    }
+  /* kernels in flight may still read the previous contents of the staging buffer: order the copies behind them */
+  cudaEvent_t busy;
+  CK (cudaEventCreateWithFlags (&busy, cudaEventDisableTiming));
+  CK (cudaEventRecord (busy, ctx->stream));
+  CK (cudaStreamWaitEvent (ctx->s_in, busy, 0));
+  CK (cudaEventDestroy (busy));
+  const size_t n_val = n_frames * channels;
+  CK (ctx->staged.reserve (n_val * sizeof (float)));
+  if (is_s16)
+    CK (ctx->staged16.reserve (n_val * sizeof (int16_t)));
+  piece_frames = (piece_frames + 1) & ~size_t (1);               // even: the conversion kernel stores float pairs
+  const size_t n_pieces = (n_frames + piece_frames - 1) / piece_frames;
+  while (ctx->stage_done.size() < n_pieces)
+    {
+      cudaEvent_t e;
+      CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+      ctx->stage_done.push_back (e);
+    }
+  for (size_t p = 0; p < n_pieces; p++)
+    {
+      const size_t f0 = p * piece_frames, f1 = std::min (f0 + piece_frames, n_frames);
+      const size_t v0 = f0 * channels, nv = (f1 - f0) * channels;
+      if (is_s16)
+        {
+          CK (cudaMemcpyAsync (ctx->staged16.as<int16_t>() + v0, static_cast<const int16_t *> (pcm) + v0, nv * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->s_in));
+          k_s16_to_f32<<<unsigned (((nv + 1) / 2 + 255) / 256), 256, 0, ctx->s_in>>> (ctx->staged16.as<int16_t>() + v0, ctx->staged.as<float>() + v0, (long long) nv);
+          LAUNCH_CHECK ("k_s16_to_f32");
+        }
+      else
+        CK (cudaMemcpyAsync (ctx->staged.as<float>() + v0, static_cast<const float *> (pcm) + v0, nv * sizeof (float), cudaMemcpyHostToDevice, ctx->s_in));
+      CK (cudaEventRecord (ctx->stage_done[p], ctx->s_in));
+    }
+  ctx->stage_piece = piece_frames;
+  ctx->stage_frames = n_frames;
+  ctx->stage_ch = channels;
+  *device_out = ctx->staged.as<float>();
+  return 0;
+}
+
+int
+awm_pcm_stage_wait (awm_ctx *ctx, size_t n_frames)
+{
+  if (!ctx || !ctx->stage_piece || n_frames > ctx->stage_frames)
+    return fail (ctx, "awm_pcm_stage_wait: nothing staged / beyond the staged stream");
+  if (!n_frames)
+    return 0;
+  CK (cudaStreamWaitEvent (ctx->stream, ctx->stage_done[(n_frames - 1) / ctx->stage_piece], 0));
+  return 0;
+}
+
 /* the device copy of the bound PCM (float, [frames][channels]): lets a caller that bound 16 bit or host audio run device-pointer
  * entry points (awm_speed_scan, awm_gather) on it without another transfer */
 const float *
@@ -927,6 +1012,9 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
   auto piece_frames = [&] (int p, long long& fb, long long& fe) { fb = pipelined ? p * kPiece : 0; fe = pipelined ? std::min<long long> (fb + kPiece, n_proc) : n_proc; };
   auto piece_samples = [&] (int p, long long& s0, long long& s1) { long long fb, fe; piece_frames (p, fb, fe); s0 = std::min<long long> (fb * kFrame, n_frames); s1 = std::min<long long> (fe * kFrame, n_frames); };
   std::vector<cudaEvent_t> ev_in (n_pieces), ev_out (n_pieces);
+  const bool trace_pipe = pipelined && getenv ("AWM_TRACE");     // device-side timeline of the three streams
+  cudaEvent_t tr[4] = { nullptr, nullptr, nullptr, nullptr };
+  const double t_host0 = wall_now();
   if (pipelined)
     {
       if (!ctx->s_in)
@@ -944,6 +1032,12 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
       CK (cudaEventRecord (ev_start, ctx->stream));          // copies must not overtake earlier work on the context stream
       CK (cudaStreamWaitEvent (ctx->s_in, ev_start, 0));
       CK (cudaEventDestroy (ev_start));
+      if (trace_pipe)
+        {
+          for (cudaEvent_t& e : tr)
+            CK (cudaEventCreate (&e));
+          CK (cudaEventRecord (tr[0], ctx->s_in));
+        }
       for (int p = 0; p < n_pieces; p++)
         {
           long long s0, s1;
@@ -953,13 +1047,15 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
                                  cudaMemcpyHostToDevice, ctx->s_in));
           if (s1 > s0 && s16)
             {
+              /* only the copy goes to the copy stream: a conversion kernel between two copies would leave the copy engine idle
+               * while it runs (13 gaps per hour of audio); the conversion happens on the context stream once the piece is there */
               CK (cudaMemcpyAsync (ctx->emb_in16.as<int16_t>() + s0 * channels, in16 + s0 * channels, size_t (s1 - s0) * channels * sizeof (int16_t),
                                    cudaMemcpyHostToDevice, ctx->s_in));
-              if (to_float (s0 * channels, s1 * channels, ctx->s_in))
-                return 1;
             }
           CK (cudaEventRecord (ev_in[p], ctx->s_in));
         }
+      if (trace_pipe)
+        CK (cudaEventRecord (tr[1], ctx->s_in));
     }
   else if (s16)
     {
@@ -984,25 +1080,34 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
         }
       if (pipelined)
         {
+          if (s1 > s0 && s16 && to_s16 (s0 * channels, s1 * channels, ctx->stream))      // the copy stream carries copies only
+            return 1;
           CK (cudaEventRecord (ev_out[p], ctx->stream));
           CK (cudaStreamWaitEvent (ctx->s_out, ev_out[p], 0));
           if (s1 > s0 && !s16)
             CK (cudaMemcpyAsync (out + s0 * channels, d_out + s0 * channels, size_t (s1 - s0) * channels * sizeof (float),
                                  cudaMemcpyDeviceToHost, ctx->s_out));
           if (s1 > s0 && s16)
-            {
-              if (to_s16 (s0 * channels, s1 * channels, ctx->s_out))
-                return 1;
-              CK (cudaMemcpyAsync (out16 + s0 * channels, d_out16 + s0 * channels, size_t (s1 - s0) * channels * sizeof (int16_t),
-                                   cudaMemcpyDeviceToHost, ctx->s_out));
-            }
+            CK (cudaMemcpyAsync (out16 + s0 * channels, d_out16 + s0 * channels, size_t (s1 - s0) * channels * sizeof (int16_t),
+                                 cudaMemcpyDeviceToHost, ctx->s_out));
         }
       return 0;
     };
+  int n_converted = 0;                                       // pieces of 16 bit input already turned into floats
   for (int p = 0; p < n_pieces; p++)
     {
       if (pipelined)
-        CK (cudaStreamWaitEvent (ctx->stream, ev_in[std::min (p + 1, n_pieces - 1)], 0));   // halo frame of the next piece
+        {
+          const int need = std::min (p + 1, n_pieces - 1);    // halo frame of the next piece
+          CK (cudaStreamWaitEvent (ctx->stream, ev_in[need], 0));
+          for (; s16 && n_converted <= need; n_converted++)
+            {
+              long long s0, s1;
+              piece_samples (n_converted, s0, s1);
+              if (to_float (s0 * channels, s1 * channels, ctx->stream))
+                return 1;
+            }
+        }
       piece_frames (p, A.frame_begin, A.frame_end);
       if (use_strip)
         {
@@ -1029,7 +1134,23 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
     return 1;
   if (pipelined)
     {
+      if (trace_pipe)
+        {
+          CK (cudaEventRecord (tr[2], ctx->stream));
+          CK (cudaEventRecord (tr[3], ctx->s_out));
+        }
       CK (cudaStreamSynchronize (ctx->s_out));
+      if (trace_pipe)
+        {
+          float t_in = 0, t_k = 0, t_out = 0;
+          cudaEventElapsedTime (&t_in, tr[0], tr[1]);
+          cudaEventElapsedTime (&t_k, tr[0], tr[2]);
+          cudaEventElapsedTime (&t_out, tr[0], tr[3]);
+          fprintf (stderr, "[trace] embed pipeline (%d pieces): last H2D done %.2f ms, last kernel %.2f ms, last D2H %.2f ms, host issue %.2f ms\n",
+                   n_pieces, t_in, t_k, t_out, (wall_now() - t_host0) * 1e3);
+          for (cudaEvent_t e : tr)
+            cudaEventDestroy (e);
+        }
       for (int p = 0; p < n_pieces; p++)
         {
           cudaEventDestroy (ev_in[p]);
@@ -1117,11 +1238,12 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
   if (!force_ring && t.n_ent <= kGatherMaxEntries)
     {
       CK (ctx->a_mags.reserve (size_t (4) * t.n_ent * ld * sizeof (float2)));
-      /* entry sums on the tensor cores (k_stft_mags_tc); AWM_APPROX=simt keeps them on the fp32 pipes (k_stft_mags), AWM_TC=12x1
-       * selects the variant with twelve FFT warps and a single A buffer */
+      /* entry sums on the tensor cores (k_stft_mags_tc); AWM_APPROX=simt keeps them on the fp32 pipes (k_stft_mags).  Variants
+       * (AWM_TC): default 12x2 = twelve FFT warps, two A buffers, mask chunks of 48 entries; 8x2 = eight FFT warps, chunks of 128
+       * entries; 12x1 = twelve FFT warps, one A buffer, chunks of 128 */
       const char *env_approx = getenv ("AWM_APPROX"), *env_tc = getenv ("AWM_TC");       // read per call: tests compare the variants in one process
       const bool force_simt = env_approx && !strcmp (env_approx, "simt");
-      const bool tc_12x1 = env_tc && !strcmp (env_tc, "12x1");
+      const bool tc_12x1 = env_tc && !strcmp (env_tc, "12x1"), tc_8x2 = env_tc && !strcmp (env_tc, "8x2");
       if (!force_simt)
         {
           if (!ctx->n_sms)
@@ -1130,24 +1252,22 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
           const unsigned grid = unsigned (std::min (n_tiles, ctx->n_sms));
           const char *env_tma = getenv ("AWM_TC_PCM");                      // AWM_TC_PCM=ldg: frames by global loads instead of bulk copies
           const int tma_ok = ctx->pcm_ch == 2 && (reinterpret_cast<uintptr_t> (ctx->pcm) & 15) == 0 && !(env_tma && !strcmp (env_tma, "ldg"));
+#define AWM_LAUNCH_TC(FW, AB, CE, MASKS, NCH)                                                                                              \
+          {                                                                                                                                 \
+            const size_t smem = tc_smem_bytes<FW, AB, CE>();                                                                                \
+            if (set_smem (ctx, k_stft_mags_tc<FW, AB, CE>, smem)) return 1;                                                                 \
+            PROF (ctx);                                                                                                                     \
+            k_stft_mags_tc<FW, AB, CE><<<grid, (FW + kTcEpiWarps + 1) * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames,    \
+              ctx->pcm_ch, int (n_out), ld, MASKS.as<unsigned char>(), t.n_ent, NCH, ctx->a_mags.as<float2>(),                              \
+              ctx->have.as<unsigned char>(), (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>(), tma_ok); \
+          }
           if (tc_12x1)
-            {
-              const size_t smem = tc_smem_bytes<12, 1>();
-              if (set_smem (ctx, k_stft_mags_tc<12, 1>, smem)) return 1;
-              PROF (ctx);
-              k_stft_mags_tc<12, 1><<<grid, (12 + kTcEpiWarps + 1) * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
-                t.masks.as<unsigned char>(), t.n_ent, t.n_chunks, ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(),
-                (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>(), tma_ok);
-            }
+            AWM_LAUNCH_TC (12, 1, 128, t.masks, t.n_chunks)
+          else if (tc_8x2)
+            AWM_LAUNCH_TC (8, 2, 128, t.masks, t.n_chunks)
           else
-            {
-              const size_t smem = tc_smem_bytes<8, 2>();
-              if (set_smem (ctx, k_stft_mags_tc<8, 2>, smem)) return 1;
-              PROF (ctx);
-              k_stft_mags_tc<8, 2><<<grid, (8 + kTcEpiWarps + 1) * 32, smem, ctx->stream>>> (ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, int (n_out), ld,
-                t.masks.as<unsigned char>(), t.n_ent, t.n_chunks, ctx->a_mags.as<float2>(), ctx->have.as<unsigned char>(),
-                (long long) wav_first, (long long) wav_last, ctx->tw.as<float2>(), ctx->win.as<float>(), tma_ok);
-            }
+            AWM_LAUNCH_TC (12, 2, 48, t.masks48, t.n_chunks48)
+#undef AWM_LAUNCH_TC
           LAUNCH_CHECK ("k_stft_mags_tc");
           prof_bytes (ctx, double (ctx->pcm_frames) * ctx->pcm_ch * sizeof (float) + double (4) * t.n_ent * n_out * sizeof (float2));   /* PCM in, entry sums out */
         }
@@ -1432,7 +1552,7 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
        * computes), and the reference's rule picks among those exact values E.  If |S - E| <= d for all offsets, the exact arg-max o*
        * satisfies S(o*) >= E(o*) - d >= E(o') - d >= S(o') - 2d for the sliding arg-max o', so with kVerifyMargin >= 2d the exact
        * arg-max is always re-scored and index / quality are those of the exact kernel.  d is measured by
-       * tests/test_gpu_stages.py::test_refine_slide_error_bound (< kVerifyMargin / 2 on every golden candidate); neighbouring offsets
+       * tests/test_gpu_stages.py::test_sync_refine_vs_oracle (asserted < kVerifyMargin / 4 on all 65 offsets of every golden candidate); neighbouring offsets
        * of a real peak differ by ~3e-3, so usually one or two offsets are re-scored. */
       constexpr double kVerifyMargin = 1e-3;
       std::vector<long long> p_start;

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 using std::map;
 using std::string;
@@ -53,6 +54,25 @@ struct Reader
     memcpy (&v, s.data() + pos, sizeof (T));
     pos += sizeof (T);
     return v;
+  }
+  template<class T> void skip_vec()
+  {
+    const uint32_t n = get<uint32_t>();
+    if (bad || pos + size_t (n) * sizeof (T) > s.size())
+      bad = true;
+    else
+      pos += size_t (n) * sizeof (T);
+  }
+  const char *raw (size_t n)
+  {
+    if (bad || pos + n > s.size())
+      {
+        bad = true;
+        return nullptr;
+      }
+    const char *p = s.data() + pos;
+    pos += n;
+    return p;
   }
   template<class T> vector<T> get_vec()
   {
@@ -167,23 +187,27 @@ Get::Get (int rank, int world, size_t n_total, const float *pcm, const int16_t *
     }
   m_plan = chunk_plan (n_total, sample_rate);
   m_slices = rank_slices (m_plan, rank, world, n_total);
+  for (int r = 0; r < world; r++)                // which ranks search a slice of which chunk (ascending rank order)
+    for (const Slice& sl : rank_slices (m_plan, r, world, n_total))
+      m_sharers[sl.chunk].push_back (r);
   for (const Slice& sl : m_slices)
     if (sl.lo < pcm_start || sl.hi > pcm_start + pcm_frames)
       {
         error ("audiowmark: sharded get: rank %d needs stream frames [%zu, %zu), its buffer holds [%zu, %zu)\n", rank, sl.lo, sl.hi, pcm_start, pcm_start + pcm_frames);
         return;
       }
-  /* one upload for all stages: host audio (float or 16 bit) is bound once, every stage then binds slices of the device copy */
+  /* one upload for all stages, piece by piece: the stages bind slices of the device copy, a slice waits only for the pieces it reads */
   if (pcm && Engine::is_device_pointer (pcm))
     m_dev = pcm;
   else
     {
-      const int rc = pcm16 ? awm_pcm_bind_s16 (ctx, pcm16, pcm_frames, channels, 0, 0) : awm_pcm_bind (ctx, pcm, pcm_frames, channels, 0, 0);
-      if (rc || !(m_dev = awm_pcm_device (ctx, nullptr, nullptr)))
+      const size_t piece = size_t (8) << 20;                       // sample-frames per piece (32 MB of 16 bit stereo)
+      if (awm_pcm_stage (ctx, pcm16 ? static_cast<const void *> (pcm16) : pcm, pcm16 ? 1 : 0, pcm_frames, channels, piece, &m_dev))
         {
           error ("audiowmark: %s\n", awm_last_error (ctx));
           return;
         }
+      m_staged = true;
     }
   m_ok = true;
 }
@@ -201,12 +225,31 @@ bool
 Get::bind (const Slice& sl)
 {
   awm_ctx *ctx = Engine::ctx();
-  if (awm_pcm_bind (ctx, m_dev + (sl.lo - m_pcm_start) * m_channels, sl.hi - sl.lo, m_channels, 0, 0))
+  if ((m_staged && awm_pcm_stage_wait (ctx, sl.hi - m_pcm_start))
+      || awm_pcm_bind (ctx, m_dev + (sl.lo - m_pcm_start) * m_channels, sl.hi - sl.lo, m_channels, 0, 0))
     {
       error ("audiowmark: %s\n", awm_last_error (ctx));
       return false;
     }
   return true;
+}
+
+namespace {
+/* AWM_TRACE=2: time stamps inside the stages (rank 0) */
+struct FineTrace
+{
+  bool on;
+  double t;
+  explicit FineTrace (int rank) : on (rank == 0 && getenv ("AWM_TRACE") && atoi (getenv ("AWM_TRACE")) >= 2), t (get_time()) {}
+  void mark (const char *what, long detail = -1)
+  {
+    if (!on)
+      return;
+    const double now = get_time();
+    fprintf (stderr, "[trace]     %s%s %.3f ms\n", what, detail >= 0 ? string_printf (" %ld", detail).c_str() : "", (now - t) * 1e3);
+    t = now;
+  }
+};
 }
 
 /* ---- stage 1: approximate search on my slices -> the local maxima above an (adaptive) floor, in chunk coordinates
@@ -219,6 +262,7 @@ Get::stage_peaks (const map<int, double>& floors, string& out)
   const size_t F = Params::frame_size;
   static vector<awm_search_score> buf (size_t (1) << 18);
   Writer w;
+  FineTrace ft (m_rank);
   for (const Slice& sl : m_slices)
     {
       if (!floors.empty() && !floors.count (sl.chunk))
@@ -231,7 +275,10 @@ Get::stage_peaks (const map<int, double>& floors, string& out)
           error ("audiowmark: sync search failed: %s\n", awm_last_error (ctx));
           return false;
         }
-      vector<double> seq = { thr1, thr1 * 0.6, thr1 * 0.35, thr1 * 0.15, -1.0 };
+      ft.mark ("approx launched, slice of chunk", sl.chunk);
+      /* lowered step by step until the slice has 64 maxima above the floor: the steps are fine enough that the list does not jump from a
+       * few dozen watermark peaks to thousands of noise peaks (every rank sorts and scans the gathered lists of all chunks) */
+      vector<double> seq = { thr1, thr1 * 0.6, thr1 * 0.35, thr1 * 0.25, thr1 * 0.2, thr1 * 0.15, thr1 * 0.1, thr1 * 0.05, -1.0 };
       if (floors.count (sl.chunk))
         seq = { floors.at (sl.chunk) };
       vector<awm_search_score> own;
@@ -250,6 +297,7 @@ Get::stage_peaks (const map<int, double>& floors, string& out)
             if (buf[i].index >= lo && buf[i].index < hi)
               own.push_back (buf[i]);
           used = floor_q;
+          ft.mark ("peaks above floor:", long (n));
           if (own.size() >= 64 || floor_q < 0)
             break;
         }
@@ -362,21 +410,27 @@ Get::stage_refine_decode (string& out)
   return true;
 }
 
-/* ---- stage 4: per chunk the final scores (threshold2 / n-best on the refined candidates) and the code words of the block
- * decoder; then the Viterbi decoder for every world-th job
- * payload: vec<u32> job number, vec<f32> error, vec<u8> bits */
+/* ---- stage 4: the final scores (threshold2 / n-best on the refined candidates) and the code words of the block decoder, for the
+ * chunks this rank searched a slice of; the ranks that share a chunk build the same job list and deal it out among themselves
+ * (job j of the chunk goes to the (j mod k)-th of its k ranks), so the host work of a rank does not grow with the length of the stream
+ * and the Viterbi launches stay balanced.  What rank 0 needs to print a decoded word travels with it:
+ * payload: per job { i32 chunk, u32 job number inside the chunk, f64 time, u64 index, f64 quality, u8 score block type, u8 pattern type,
+ *                    u16 pad, f32 error, u8 bits[n_msg] } */
 bool
 Get::stage_viterbi (const vector<string>& all, string& out)
 {
   const size_t n_coded = code_size (ConvBlockType::a, Params::payload_size);
   struct Refined { vector<awm_search_score> score; vector<vector<float>> soft; vector<int> valid; };
   map<int, Refined> refined;
-  for (const auto& kv : m_cands)
+  for (const Slice& sl : m_slices)
     {
-      Refined& r = refined[kv.first];
-      r.score = kv.second;
-      r.soft.assign (kv.second.size(), vector<float>());
-      r.valid.assign (kv.second.size(), 0);
+      auto it = m_cands.find (sl.chunk);
+      if (it == m_cands.end())
+        continue;
+      Refined& r = refined[sl.chunk];
+      r.score = it->second;
+      r.soft.assign (it->second.size(), vector<float>());
+      r.valid.assign (it->second.size(), 0);
     }
   for (const string& payload : all)
     {
@@ -384,11 +438,21 @@ Get::stage_viterbi (const vector<string>& all, string& out)
       while (!r.done())
         {
           const int chunk = r.get<int32_t>();
+          if (!refined.count (chunk))               // not my chunk: step over the record
+            {
+              r.skip_vec<uint32_t>();
+              r.skip_vec<awm_search_score>();
+              r.skip_vec<int32_t>();
+              r.skip_vec<float>();
+              if (r.bad)
+                return false;
+              continue;
+            }
           const vector<uint32_t> pos = r.get_vec<uint32_t>();
           const vector<awm_search_score> sc = r.get_vec<awm_search_score>();
           const vector<int32_t> valid = r.get_vec<int32_t>();
           const vector<float> soft = r.get_vec<float>();
-          if (r.bad || !refined.count (chunk) || sc.size() != pos.size() || valid.size() != pos.size() || soft.size() != pos.size() * n_coded)
+          if (r.bad || sc.size() != pos.size() || valid.size() != pos.size() || soft.size() != pos.size() * n_coded)
             return false;
           Refined& dst = refined[chunk];
           for (size_t i = 0; i < pos.size(); i++)
@@ -402,6 +466,7 @@ Get::stage_viterbi (const vector<string>& all, string& out)
         }
     }
   m_jobs.clear();
+  vector<uint32_t> job_number;                   // position of m_jobs[i] in its chunk's job list
   for (auto& kv : refined)                       // chunk order
     {
       Refined& r = kv.second;
@@ -420,63 +485,86 @@ Get::stage_viterbi (const vector<string>& all, string& out)
                 && (q > 0 ? ConvBlockType::a : ConvBlockType::b) == final_scores[f].block_type)
               {
                 taken[c] = 1;
-                soft[f] = r.soft[c];
-                valid[f] = r.valid[c] && !r.soft[c].empty();
+                soft[f].swap (r.soft[c]);
+                valid[f] = r.valid[c] && !soft[f].empty();
                 break;
               }
           }
-      build_block_jobs (m_key, final_scores, soft, valid, m_rate, kv.first, 1.0, m_jobs);
+      vector<VitJob> chunk_jobs;
+      build_block_jobs (m_key, final_scores, soft, valid, m_rate, kv.first, 1.0, chunk_jobs);
+      const vector<int>& sharers = m_sharers[kv.first];
+      for (size_t j = 0; j < chunk_jobs.size(); j++)
+        if (sharers[j % sharers.size()] == m_rank)
+          {
+            m_jobs.push_back (std::move (chunk_jobs[j]));
+            job_number.push_back (uint32_t (j));
+          }
     }
   vector<const VitJob *> mine;
-  vector<uint32_t> numbers;
-  for (size_t j = size_t (m_rank); j < m_jobs.size(); j += size_t (m_world))
-    {
-      mine.push_back (&m_jobs[j]);
-      numbers.push_back (uint32_t (j));
-    }
+  for (const VitJob& j : m_jobs)
+    mine.push_back (&j);
   vector<uint8_t> bits;
   vector<float> err;
   if (!viterbi_decode (mine, bits, err))
     return false;
+  const size_t n_msg = code_message_bits();
   Writer w;
-  w.put_vec (numbers);
-  w.put_vec (err);
-  w.put_vec (bits);
+  for (size_t i = 0; i < m_jobs.size(); i++)
+    {
+      const VitJob& j = m_jobs[i];
+      w.put (int32_t (j.chunk));
+      w.put (job_number[i]);
+      w.put (double (j.time));
+      w.put (uint64_t (j.score.index));
+      w.put (double (j.score.quality));
+      w.put (uint8_t (j.score.block_type == ConvBlockType::a ? AWM_BLOCK_A : j.score.block_type == ConvBlockType::b ? AWM_BLOCK_B : AWM_BLOCK_AB));
+      w.put (uint8_t (j.type));
+      w.put (uint16_t (0));
+      w.put (float (err[i]));
+      w.s.append (reinterpret_cast<const char *> (bits.data() + i * n_msg), n_msg);
+    }
   out.swap (w.s);
   return true;
 }
 
-/* ---- stage 5: decoded words -> patterns per chunk -> the reference's merge in chunk order */
+/* ---- stage 5 (rank 0): decoded words -> patterns per chunk, in the order the block decoder queued them -> the reference's merge in
+ * chunk order */
 bool
 Get::stage_merge (const vector<string>& all, ResultSet& result)
 {
   const size_t n_msg = code_message_bits();
-  vector<const uint8_t *> word (m_jobs.size(), nullptr);
-  vector<float> word_err (m_jobs.size(), 0.f);
-  vector<vector<uint8_t>> keep;
+  struct Word { int chunk; uint32_t number; VitJob job; float err; const uint8_t *bits; };
+  vector<Word> words;
   for (const string& payload : all)
     {
       Reader r (payload);
-      const vector<uint32_t> numbers = r.get_vec<uint32_t>();
-      const vector<float> err = r.get_vec<float>();
-      keep.push_back (r.get_vec<uint8_t>());
-      if (r.bad || err.size() != numbers.size() || keep.back().size() != numbers.size() * n_msg)
-        return false;
-      for (size_t i = 0; i < numbers.size(); i++)
+      while (!r.done())
         {
-          if (numbers[i] >= m_jobs.size())
+          Word wd;
+          wd.chunk = r.get<int32_t>();
+          wd.number = r.get<uint32_t>();
+          wd.job.time = r.get<double>();
+          wd.job.score.index = size_t (r.get<uint64_t>());
+          wd.job.score.quality = r.get<double>();
+          const uint8_t bt = r.get<uint8_t>();
+          wd.job.score.block_type = bt == AWM_BLOCK_A ? ConvBlockType::a : bt == AWM_BLOCK_B ? ConvBlockType::b : ConvBlockType::ab;
+          wd.job.type = ResultSet::Type (r.get<uint8_t>());
+          r.get<uint16_t>();
+          wd.err = r.get<float>();
+          wd.bits = reinterpret_cast<const uint8_t *> (r.raw (n_msg));
+          if (r.bad || wd.chunk < 0 || wd.chunk >= int (m_plan.size()))
             return false;
-          word[numbers[i]] = keep.back().data() + i * n_msg;
-          word_err[numbers[i]] = err[i];
+          wd.job.block_type = wd.job.score.block_type;
+          wd.job.key = m_key;
+          wd.job.chunk = wd.chunk;
+          wd.job.speed = 1.0;
+          words.push_back (std::move (wd));
         }
     }
+  std::stable_sort (words.begin(), words.end(), [] (const Word& x, const Word& y) { return x.chunk != y.chunk ? x.chunk < y.chunk : x.number < y.number; });
   vector<ResultSet> chunk_results (m_plan.size());
-  for (size_t j = 0; j < m_jobs.size(); j++)
-    {
-      if (!word[j])
-        return false;
-      add_decoded_pattern (m_jobs[j], word[j], word_err[j], chunk_results[m_jobs[j].chunk]);
-    }
+  for (const Word& wd : words)
+    add_decoded_pattern (wd.job, wd.bits, wd.err, chunk_results[wd.chunk]);
   for (size_t c = 0; c < chunk_results.size(); c++)
     {
       chunk_results[c].apply_time_offset (m_plan[c].time_offset);
@@ -495,18 +583,26 @@ Get::run (const Exchange& exchange, ResultSet& result)
   double t = get_time();
   auto mark = [&] (const char *what)
     {
-      if (trace && m_rank == 0)
+      if (trace)
         {
           const double now = get_time();
-          fprintf (stderr, "[trace] sharded get: %s %.2f ms\n", what, (now - t) * 1e3);
+          fprintf (stderr, "[trace] rank %d sharded get: %s %.2f ms\n", m_rank, what, (now - t) * 1e3);
           t = now;
         }
     };
   string mine;
   vector<string> all;
   map<int, double> retry;
-  if (!stage_peaks ({}, mine) || !exchange (mine, all) || !stage_select (all, retry))
+  FineTrace ft (m_rank);
+  if (!stage_peaks ({}, mine))
     return false;
+  ft.mark ("stage_peaks, payload bytes", long (mine.size()));
+  if (!exchange (mine, all))
+    return false;
+  ft.mark ("exchange");
+  if (!stage_select (all, retry))
+    return false;
+  ft.mark ("stage_select, chunks to retry:", long (retry.size()));
   mark ("peaks + select");
   if (!retry.empty())                            // identical on every rank: all of them take part in the second round
     {

@@ -67,11 +67,12 @@ private:
   size_t m_n_total, m_pcm_start, m_pcm_frames;
   const float *m_dev = nullptr;    // device copy of this rank's PCM
   Key    m_key;
-  bool   m_ok = false;
+  bool   m_ok = false, m_staged = false;
   std::vector<Chunk> m_plan;
   std::vector<Slice> m_slices;
   std::map<int, std::vector<awm_search_score>> m_cands;     // per chunk: selected candidates (identical on every rank)
-  std::vector<get_detail::VitJob> m_jobs;                   // every code word of the run, chunk major (identical on every rank)
+  std::map<int, std::vector<int>> m_sharers;                // per chunk: the ranks that search a slice of it
+  std::vector<get_detail::VitJob> m_jobs;                   // the code words this rank decodes
 };
 
 }

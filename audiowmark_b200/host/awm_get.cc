@@ -25,225 +25,6 @@ frame_count (const WavData& wav_data)
   return wav_data.n_values() / wav_data.n_channels() / Params::frame_size;
 }
 
-/* ---------------------------------------------------------------- ResultSet */
-
-bool
-ResultSet::Pattern::approx_match (const Pattern& p) const
-{
-  const double time_delta = Params::frame_size / double (Params::mark_sample_rate);
-  const double speed_delta = 0.01;
-  return key == p.key && (fabs (time - p.time) < time_delta || type == Type::ALL) && bit_vec == p.bit_vec
-      && sync_score.block_type == p.sync_score.block_type && type == p.type && fabs (speed - p.speed) < speed_delta;
-}
-
-void
-ResultSet::add_pattern (const Key& key, double time, SyncFinder::Score sync_score, const vector<int>& bit_vec, float decode_error, Type pattern_type, double speed)
-{
-  Pattern p;
-  p.key = key;
-  p.time = time;
-  p.sync_score = sync_score;
-  p.bit_vec = bit_vec;
-  p.decode_error = decode_error;
-  p.type = pattern_type;
-  p.speed = speed;
-  patterns.push_back (p);
-}
-
-void
-ResultSet::apply_time_offset (double time_offset)
-{
-  for (auto& p : patterns)
-    p.time += time_offset;
-}
-
-void
-ResultSet::rate_patterns (const Key& key)
-{
-  /* rating = sum of sync qualities of all patterns with the same bits; "all" patterns count twice */
-  std::map<string, float> rating;
-  for (const auto& p : patterns)
-    if (p.key == key)
-      rating[bit_vec_to_str (p.bit_vec)] += p.sync_score.quality * ((p.type == Type::ALL) ? 2.f : 1.f);
-  for (auto& p : patterns)
-    if (p.key == key)
-      p.rating = rating[bit_vec_to_str (p.bit_vec)];
-}
-
-static int
-ab_rank (const ResultSet::Pattern& p)
-{
-  switch (p.sync_score.block_type)
-    {
-      case ConvBlockType::a:  return 0;
-      case ConvBlockType::b:  return 1;
-      case ConvBlockType::ab: return 2;
-    }
-  return 99;
-}
-
-void
-ResultSet::sort (const vector<Key>& key_list)
-{
-  for (const auto& key : key_list)
-    rate_patterns (key);
-  std::sort (patterns.begin(), patterns.end(), [] (const Pattern& p1, const Pattern& p2)
-    {
-      const int all1 = p1.type == Type::ALL, all2 = p2.type == Type::ALL;
-      if (p1.key.name() != p2.key.name())
-        return p1.key.name() < p2.key.name();
-      if (p1.rating != p2.rating)
-        return p1.rating > p2.rating;
-      if (all1 != all2)
-        return all1 < all2;
-      if (p1.time != p2.time)
-        return p1.time < p2.time;
-      if (ab_rank (p1) != ab_rank (p2))
-        return ab_rank (p1) < ab_rank (p2);
-      return bit_vec_to_str (p1.bit_vec) < bit_vec_to_str (p2.bit_vec);
-    });
-}
-
-void
-ResultSet::merge (ResultSet& other)
-{
-  vector<Pattern> to_merge = other.patterns;
-  std::stable_sort (to_merge.begin(), to_merge.end(), [] (const Pattern& p1, const Pattern& p2) { return p1.time < p2.time; });
-  for (const auto& p : to_merge)
-    {
-      bool is_new = true;
-      for (auto& mine : patterns)
-        if (mine.approx_match (p))
-          is_new = false;
-      if (is_new)
-        patterns.push_back (p);
-    }
-  if (debug_sync.empty())
-    debug_sync = other.debug_sync;
-}
-
-static string
-json_escape (const string& s)
-{
-  string result;
-  for (unsigned char ch : s)
-    {
-      if (ch == '"' || ch == '\\')
-        {
-          result += '\\';
-          result += ch;
-        }
-      else if (ch < 32)
-        result += string_printf ("\\u%04x", ch);
-      else
-        result += ch;
-    }
-  return result;
-}
-
-static string
-pattern_type_str (const ResultSet::Pattern& pattern, bool json)
-{
-  string btype;
-  switch (pattern.sync_score.block_type)
-    {
-      case ConvBlockType::a:  btype = "A";  break;
-      case ConvBlockType::b:  btype = "B";  break;
-      case ConvBlockType::ab: btype = "AB"; break;
-    }
-  if (json && pattern.type == ResultSet::Type::ALL)
-    btype = "ALL";
-  if (pattern.type == ResultSet::Type::CLIP)
-    btype = "CLIP-" + btype;
-  if (pattern.speed != 1)
-    btype += "-SPEED";
-  return btype;
-}
-
-void
-ResultSet::print_json (FILE *outfile, size_t time_length)
-{
-  fprintf (outfile, "{ \"length\": \"%ld:%02ld\",\n", long (time_length / 60), long (time_length % 60));
-  fprintf (outfile, "  \"matches\": [\n");
-  int nth = 0;
-  for (const auto& pattern : patterns)
-    {
-      if (nth++ != 0)
-        fprintf (outfile, ",\n");
-      const int seconds = pattern.time;
-      fprintf (outfile, "    { \"key\": \"%s\", \"pos\": \"%d:%02d\", \"bits\": \"%s\", \"quality\": %.5f, \"error\": %.6f, \"rating\": %.5f, \"type\": \"%s\", \"speed\": %.6f }",
-               json_escape (pattern.key.name()).c_str(), seconds / 60, seconds % 60, bit_vec_to_str (pattern.bit_vec).c_str(),
-               pattern.sync_score.quality, pattern.decode_error, pattern.rating, pattern_type_str (pattern, true).c_str(), pattern.speed);
-    }
-  fprintf (outfile, " ]\n}\n");
-}
-
-void
-ResultSet::print_json (size_t time_length, const string& json_file)
-{
-  FILE *outfile = fopen (json_file == "-" ? "/dev/stdout" : json_file.c_str(), "w");
-  if (!outfile)
-    {
-      perror (("audiowmark: failed to open \"" + json_file + "\":").c_str());
-      exit (127);
-    }
-  print_json (outfile, time_length);
-  fclose (outfile);
-}
-
-void
-ResultSet::print (FILE *out)
-{
-  string last_key_name;
-  bool print_speed = true;
-  for (const auto& pattern : patterns)
-    {
-      if (pattern.key.name() != last_key_name)
-        {
-          fprintf (out, "key %s\n", pattern.key.name().c_str());
-          last_key_name = pattern.key.name();
-          print_speed = true;
-        }
-      if (print_speed)
-        {
-          for (const auto& p : patterns)
-            if (p.key == pattern.key && p.speed != 1)
-              {
-                fprintf (out, "speed %.6f\n", p.speed);
-                break;
-              }
-          print_speed = false;
-        }
-      if (pattern.type == Type::ALL)
-        fprintf (out, "pattern   all %s %.3f %.3f%s\n", bit_vec_to_str (pattern.bit_vec).c_str(), pattern.sync_score.quality,
-                 pattern.decode_error, pattern.speed != 1 ? " SPEED" : "");
-      else
-        {
-          const int seconds = pattern.time;
-          fprintf (out, "pattern %2d:%02d %s %.3f %.3f %s\n", seconds / 60, seconds % 60, bit_vec_to_str (pattern.bit_vec).c_str(),
-                   pattern.sync_score.quality, pattern.decode_error, pattern_type_str (pattern, false).c_str());
-        }
-    }
-}
-
-int
-ResultSet::match_count (const vector<int>& orig_bits) const
-{
-  int n = 0;
-  for (const auto& p : patterns)
-    if (p.bit_vec == orig_bits)
-      n++;
-  return n;
-}
-
-int
-ResultSet::print_match_count (const vector<int>& orig_bits)
-{
-  const int n = match_count (orig_bits);
-  printf ("match_count %d %zd\n", n, patterns.size());
-  return n;
-}
-
 /* ---------------------------------------------------------------- GPU helpers */
 
 namespace get_detail {

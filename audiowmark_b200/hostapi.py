@@ -387,9 +387,9 @@ def dist_init_from_torch():
     dist_init(rank, world, bytes(t.cpu().numpy().tobytes()))
 
 
-def balanced_get(pcm, pcm_start: int, n_total: int, key=None, n_frames=None, channels=None, sample_rate=44100):
-    """this rank's part of the stream (numpy float32 / int16 [n, ch], or a float32 device pointer) -> the --json document on rank 0,
-    None on the other ranks"""
+def balanced_get(pcm, pcm_start: int, n_total: int, key=None, n_frames=None, channels=None, sample_rate=44100, parse=True):
+    """this rank's part of the stream (numpy float32 / int16 [n, ch], or a float32 device pointer) -> the --json document on rank 0
+    (parse=False: its text, as `audiowmark get --json` writes it), None on the other ranks"""
     is_s16 = 0
     if isinstance(pcm, np.ndarray):
         if pcm.dtype == np.int16:
@@ -404,7 +404,10 @@ def balanced_get(pcm, pcm_start: int, n_total: int, key=None, n_frames=None, cha
                                   ctypes.c_int(channels), ctypes.c_int(sample_rate), buf, ctypes.c_size_t(cap), ctypes.byref(n_pat))
     if rc:
         raise RuntimeError("awmh_balanced_get failed (rc=%d); see stderr" % rc)
-    return json.loads(buf.value.decode()) if n_pat.value >= 0 else None
+    if n_pat.value < 0:
+        return None
+    text = buf.value.decode()
+    return json.loads(text) if parse else text
 
 
 class BalancedStages:

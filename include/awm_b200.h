@@ -118,6 +118,13 @@ int awm_pcm_prefetch (awm_ctx *ctx, const float *pcm, size_t n_frames, int chann
  * so results are identical to converting on the host, at half the PCIe traffic. */
 int awm_pcm_bind_s16 (awm_ctx *ctx, const int16_t *pcm, size_t n_frames, int channels, size_t pad_start, size_t pad_end);
 int awm_pcm_prefetch_s16 (awm_ctx *ctx, const int16_t *pcm, size_t n_frames, int channels);
+/* A long HOST stream (float or 16 bit PCM) on its way to the device piece by piece, for callers that work on parts of it while the
+ * rest is still crossing PCIe (the sharded get: a rank searches its first chunk slice while its later slices arrive; replaces the
+ * read-ahead of WavChunkLoader, src/wavchunkloader.cc:54-163).  awm_pcm_stage starts the copies on a copy stream and returns the
+ * device address of the float copy at once; awm_pcm_stage_wait (n) orders everything issued on the context stream afterwards
+ * behind the arrival of the first n sample-frames.  Bind parts with awm_pcm_bind (device pointer + offset). */
+int awm_pcm_stage (awm_ctx *ctx, const void *pcm, int is_s16, size_t n_frames, int channels, size_t piece_frames, const float **device_out);
+int awm_pcm_stage_wait (awm_ctx *ctx, size_t n_frames);
 /* device copy (float) of the bound PCM incl. padding; NULL if nothing is bound */
 const float *awm_pcm_device (awm_ctx *ctx, size_t *n_frames, int *channels);
 
