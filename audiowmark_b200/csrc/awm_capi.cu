@@ -151,14 +151,15 @@ struct awm_ctx
   // bound PCM
   const float *pcm = nullptr; size_t pcm_frames = 0; int pcm_ch = 0;
   DevBuf pcm_own, pcm16_own;
-  struct Prefetch { DevBuf buf, buf16; bool s16 = false; const void *src = nullptr; size_t n_frames = 0; int ch = 0; cudaEvent_t done = nullptr; bool valid = false; };
+  struct Prefetch { DevBuf buf, buf16; bool s16 = false; const void *src = nullptr; size_t n_frames = 0; int ch = 0; cudaEvent_t done = nullptr; bool valid = false; };   // s16: buf16 holds the copy, it becomes float in buf when it is bound
   Prefetch pref[2];
   int pref_next = 0;
   /* awm_pcm_stage: a host stream on its way into `staged` piece by piece */
   DevBuf staged, staged16;
   std::vector<cudaEvent_t> stage_done;           // one per piece, recorded on s_in
-  size_t stage_piece = 0, stage_frames = 0;
+  size_t stage_piece = 0, stage_frames = 0, stage_converted = 0;
   int stage_ch = 0;
+  bool stage_s16 = false;
 
   DevBuf dbT, have, q, scores, a_ud, a_cnt, peaks_out, peaks_cnt, a_mags;       // approx
   size_t n_scores_dev = 0;
@@ -692,6 +693,13 @@ pcm_bind_any (awm_ctx *ctx, const void *pcm_v, bool s16, size_t n_frames, int ch
   if (hit)
     {
       CK (cudaStreamWaitEvent (ctx->stream, hit->done, 0));   // the prefetched copy becomes the bound PCM
+      if (hit->s16)
+        {
+          const long long n_val = (long long) (n_frames * channels);
+          PROF (ctx);
+          k_s16_to_f32<<<unsigned (((n_val + 1) / 2 + 255) / 256), 256, 0, ctx->stream>>> (hit->buf16.as<int16_t>(), hit->buf.as<float>(), n_val);
+          LAUNCH_CHECK ("k_s16_to_f32");
+        }
       ctx->pcm = hit->buf.as<float>();
       hit->valid = false;
     }
@@ -762,6 +770,8 @@ pcm_prefetch_any (awm_ctx *ctx, const void *pcm, bool s16, size_t n_frames, int 
    * just before it and is still waiting to be bound, its head is already on the device: it is copied from there (device to device,
    * ordered behind that upload on the same stream) and only the rest crosses PCIe -- 7 % fewer bytes for a 1 h stream. */
   size_t head = 0;                              // frames taken from the previous prefetch
+  if (s16)
+    CK (pf.buf16.reserve (n_val * sizeof (int16_t)));
   {
     awm_ctx::Prefetch& prev = ctx->pref[ctx->pref_next ^ 1];
     const size_t esz = (s16 ? sizeof (int16_t) : sizeof (float)) * size_t (channels);
@@ -770,19 +780,17 @@ pcm_prefetch_any (awm_ctx *ctx, const void *pcm, bool s16, size_t n_frames, int 
       {
         const size_t first = size_t (p0 - b0) / esz;
         head = std::min (prev.n_frames - first, n_frames);
-        if ((head * channels) & 1)                // the conversion kernel stores float pairs: keep the rest 8-byte aligned
-          head--;
-        CK (cudaMemcpyAsync (pf.buf.p, prev.buf.as<float>() + first * channels, head * channels * sizeof (float), cudaMemcpyDeviceToDevice, ctx->s_in));
+        if (s16)            // 16 bit audio stays 16 bit until it is bound (see below)
+          CK (cudaMemcpyAsync (pf.buf16.p, prev.buf16.as<int16_t>() + first * channels, head * channels * sizeof (int16_t), cudaMemcpyDeviceToDevice, ctx->s_in));
+        else
+          CK (cudaMemcpyAsync (pf.buf.p, prev.buf.as<float>() + first * channels, head * channels * sizeof (float), cudaMemcpyDeviceToDevice, ctx->s_in));
       }
   }
+  /* the copy stream carries copies only: the int -> float conversion of 16 bit audio runs on the context stream when the chunk is
+   * bound (pcm_bind_any), so the copy of the next chunk starts the moment this one has arrived */
   const size_t rest = (n_frames - head) * channels, head_val = head * channels;
   if (rest && s16)
-    {
-      CK (pf.buf16.reserve (n_val * sizeof (int16_t)));
-      CK (cudaMemcpyAsync (pf.buf16.p, static_cast<const int16_t *> (pcm) + head_val, rest * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->s_in));
-      k_s16_to_f32<<<unsigned (((rest + 1) / 2 + 255) / 256), 256, 0, ctx->s_in>>> (pf.buf16.as<int16_t>(), pf.buf.as<float>() + head_val, (long long) rest);
-      LAUNCH_CHECK ("k_s16_to_f32");
-    }
+    CK (cudaMemcpyAsync (pf.buf16.as<int16_t>() + head_val, static_cast<const int16_t *> (pcm) + head_val, rest * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->s_in));
   else if (rest)
     CK (cudaMemcpyAsync (pf.buf.as<float>() + head_val, static_cast<const float *> (pcm) + head_val, rest * sizeof (float), cudaMemcpyHostToDevice, ctx->s_in));
   CK (cudaEventRecord (pf.done, ctx->s_in));
@@ -838,12 +846,8 @@ awm_pcm_stage (awm_ctx *ctx, const void *pcm, int is_s16, size_t n_frames, int c
     {
       const size_t f0 = p * piece_frames, f1 = std::min (f0 + piece_frames, n_frames);
       const size_t v0 = f0 * channels, nv = (f1 - f0) * channels;
-      if (is_s16)
-        {
-          CK (cudaMemcpyAsync (ctx->staged16.as<int16_t>() + v0, static_cast<const int16_t *> (pcm) + v0, nv * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->s_in));
-          k_s16_to_f32<<<unsigned (((nv + 1) / 2 + 255) / 256), 256, 0, ctx->s_in>>> (ctx->staged16.as<int16_t>() + v0, ctx->staged.as<float>() + v0, (long long) nv);
-          LAUNCH_CHECK ("k_s16_to_f32");
-        }
+      if (is_s16)       /* copies only on the copy stream; a piece becomes float on the context stream when somebody waits for it */
+        CK (cudaMemcpyAsync (ctx->staged16.as<int16_t>() + v0, static_cast<const int16_t *> (pcm) + v0, nv * sizeof (int16_t), cudaMemcpyHostToDevice, ctx->s_in));
       else
         CK (cudaMemcpyAsync (ctx->staged.as<float>() + v0, static_cast<const float *> (pcm) + v0, nv * sizeof (float), cudaMemcpyHostToDevice, ctx->s_in));
       CK (cudaEventRecord (ctx->stage_done[p], ctx->s_in));
@@ -851,6 +855,8 @@ awm_pcm_stage (awm_ctx *ctx, const void *pcm, int is_s16, size_t n_frames, int c
   ctx->stage_piece = piece_frames;
   ctx->stage_frames = n_frames;
   ctx->stage_ch = channels;
+  ctx->stage_s16 = is_s16 != 0;
+  ctx->stage_converted = 0;
   *device_out = ctx->staged.as<float>();
   return 0;
 }
@@ -862,7 +868,17 @@ awm_pcm_stage_wait (awm_ctx *ctx, size_t n_frames)
     return fail (ctx, "awm_pcm_stage_wait: nothing staged / beyond the staged stream");
   if (!n_frames)
     return 0;
-  CK (cudaStreamWaitEvent (ctx->stream, ctx->stage_done[(n_frames - 1) / ctx->stage_piece], 0));
+  const size_t last = (n_frames - 1) / ctx->stage_piece;
+  CK (cudaStreamWaitEvent (ctx->stream, ctx->stage_done[last], 0));
+  for (; ctx->stage_s16 && ctx->stage_converted <= last; ctx->stage_converted++)
+    {
+      const size_t f0 = ctx->stage_converted * ctx->stage_piece, f1 = std::min (f0 + ctx->stage_piece, ctx->stage_frames);
+      const size_t v0 = f0 * ctx->stage_ch;
+      const long long nv = (long long) ((f1 - f0) * ctx->stage_ch);
+      PROF (ctx);
+      k_s16_to_f32<<<unsigned (((nv + 1) / 2 + 255) / 256), 256, 0, ctx->stream>>> (ctx->staged16.as<int16_t>() + v0, ctx->staged.as<float>() + v0, nv);
+      LAUNCH_CHECK ("k_s16_to_f32");
+    }
   return 0;
 }
 
@@ -1004,7 +1020,7 @@ embed_any (awm_ctx *ctx, const void *in_v, void *out_v, bool s16, size_t n_frame
    * kernels of piece p and the D2H copy of piece p-1 overlap (three streams, events in between).  The arithmetic is
    * the same as for one launch: a piece only restricts which frames a launch emits, halo frames are read from the
    * (already copied) neighbour pieces, the limiter of a piece runs once the block peaks after it are final. */
-  long long kPiece = 12288;                                  // 1024-frames per piece (12.6 M sample-frames, 100 MB stereo)
+  long long kPiece = 6144;                                   // 1024-frames per piece (6.3 M sample-frames, 25 MB of 16 bit stereo): measured best of 3072 .. 24576
   if (const char *e = getenv ("AWM_PIECE"))                  // measurement aid: other piece sizes
     kPiece = std::max (1024LL, atoll (e));
   const bool pipelined = !in_dev && !out_dev && !in16_dev && !out16_dev && n_proc > 2 * kPiece;

@@ -483,7 +483,7 @@ def main_gpu(args):
     if dominant:
         k = kernels[dominant]
         a = k["algo_GBps"] or 0.0
-        limiter = {"k_stft_mags_tc": "fp32 issue rate of the FFT warps (8 of the 13 warps; ~1900 warp instructions per 1024-point stereo transform); the tensor-core contraction, the TMA copies and the epilogue stores run underneath",
+        limiter = {"k_stft_mags_tc": "instruction latency / fp32 issue of the FFT warps (12 of the 17 warps, 3 per scheduler; ~1800 warp instructions per 1024-point stereo transform); the tcgen05 contraction, the TMA copies and the epilogue stores run underneath",
                    "k_refine_slide": "fp32 issue rate; the PCM window is re-read from L2",
                    "k_sync_gather": "HBM: one streaming pass over the entry-sum matrix",
                    "k_embed": "fp32 issue rate / latency of two FFTs per frame",

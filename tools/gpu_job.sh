@@ -1,4 +1,10 @@
 #!/bin/bash
 # scratch job of the current gpurun call (edited per call)
-timeout 600 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_sharding.py -x -q 2>&1 | tail -3
-AWM_TRACE=1 python tools/trace_add.py 12288 6144 4096 3072 2>&1 | grep -E "embed pipeline|add_s16|copy" | awk '/embed pipeline/ {last=$0} /add_s16/ {print last; print} /copy/ {print}'
+timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_sharding.py tests/test_gpu_zz_fullsize.py -x -q 2>&1 | tail -3
+python bench.py --no-cpu-baseline > gpurun_out/r2j_bench.json 2>gpurun_out/r2j_bench.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r2j_bench.json"))
+print(d["ms_per_step"], d["e2e"]["ms_per_step"], d["e2e_f32"]["ms_per_step"], d["payload_ok"], d["host_wall_ms_per_step"])
+print(d["add_get"])
+PY
