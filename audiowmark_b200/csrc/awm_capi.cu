@@ -1494,7 +1494,9 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
             ctx->tw.as<float2>(), ctx->tw1024.as<float2>());
         }
       LAUNCH_CHECK ("k_refine_slide");
-      prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
+      /* what the kernel has to read: of every candidate's block only the SYNC frames (n_ent of the 2226), each with the 512 samples the
+       * 64 slides walk over -- not the whole block */
+      prof_bytes (ctx, double (nc) * double (t.n_ent) * (double (kFrame) + 512.0) * ctx->pcm_ch * sizeof (float));
       const long long n_red = (long long) nc * kOffsets * n_bits;
       PROF (ctx);
       k_refine_reduce<<<unsigned ((n_red + 127) / 128), 128, 0, ctx->stream>>> (ctx->r_ent_ud.as<float2>(), ctx->r_ent_flag.as<unsigned char>(), int (nc), t.n_ent,
@@ -1513,9 +1515,9 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
         t.ent.as<awm_sync_entry>(), t.off.as<int>(), n_bits, total, (long long) wav_first, (long long) wav_last,
         ctx->r_ud.as<float>(), ctx->r_cnt.as<int>(), ctx->rvalid.as<unsigned char>(), ctx->tw.as<float2>(), ctx->win.as<float>());
       LAUNCH_CHECK ("k_refine");
-      /* compulsory traffic: every candidate's window of sync frames (one block, two in CLIP mode, + the +-256 samples of the
-       * offsets) is read once -- the 65 offsets x 6 bits re-read it from L2 */
-      prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
+      /* compulsory traffic: the sync frames of every candidate (+ the +-256 samples of the offsets) are read once -- the 65 offsets
+       * x 6 bits re-read them from L2 */
+      prof_bytes (ctx, double (nc) * double (t.n_ent) * (double (kFrame) + 512.0) * ctx->pcm_ch * sizeof (float));
     }
   const size_t n_ud = nc * kOffsets * n_bits * 2, n_cnt = nc * kOffsets * n_bits, n_val = nc * kOffsets;
   float *h_ud = ctx->pin.get<float> (n_ud);
@@ -1624,8 +1626,9 @@ refine_impl (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint64_t 
             ctx->pcm, (long long) ctx->pcm_frames, ctx->pcm_ch, ctx->cand_start.as<long long>(), int (np), t.ent.as<awm_sync_entry>(), t.n_ent,
             ctx->r_ent_ud.as<float>(), ctx->tw.as<float2>(), ctx->win.as<float>());
           LAUNCH_CHECK ("k_refine_exact_fft");
-          /* the re-scored offsets of a candidate lie within 512 samples of each other: its window is compulsory traffic once */
-          prof_bytes (ctx, double (nc) * (double (total) * kFrame + 512.0) * ctx->pcm_ch * sizeof (float));
+          /* the re-scored offsets of a candidate lie within 512 samples of each other: its sync frames are compulsory traffic once
+           * (and were read by the sliding pass a moment ago: they come from L2) */
+          prof_bytes (ctx, double (nc) * double (t.n_ent) * (double (kFrame) + 512.0) * ctx->pcm_ch * sizeof (float));
           PROF (ctx);
           int max_bit_frames = 1;
           for (int b = 0; b < n_bits; b++)

@@ -786,16 +786,42 @@ k_viterbi (const float *__restrict__ raw, const long long *__restrict__ raw_off,
   else
     viterbi_run<AWM_BLOCK_AB> (dm, dec, coded, m0, m1, steps, tid);
   if (tid == 0)
+    err_out[job] = dm[0] / float (n_coded);
+  /* Traceback (src/convcode.cc:192-211) by warp 0.  Going back one step reads ONE decision bit, but which word of the previous step
+   * holds it depends on the bit just read: done by one thread this is a chain of 143 dependent global loads (~0.1 ms, an eighth of
+   * the kernel).  The word index of step t - 1 - k is (state >> (5 + k)) | (the k decisions in between) << (10 - k): the warp loads
+   * the word of step t - 1 and all 2 + 4 + 8 + 16 candidate words of the four steps before it at once (31 lanes, one load latency),
+   * then walks the five steps through shuffles. */
+  if (tid < 32)
     {
-      err_out[job] = dm[0] / float (n_coded);
       unsigned state = 0;
-      for (int t = steps; t > 0; t--)
+      int t = steps;
+      while (t > 0)
         {
-          const uint32_t word = dec[(size_t) (t - 1) * kVitWords + (state >> 5)];
-          const unsigned sel = (word >> (state & 31)) & 1u;
-          if (t - 1 < n_msg)
-            bits_out[(size_t) job * n_msg + (t - 1)] = state & 1u;
-          state = (state >> 1) | (sel << (AWM_VITERBI_ORDER - 1));
+          const int depth = t < 5 ? t : 5;                  // steps resolved in this round
+          /* lane 2^k - 1 + c (k = 0 .. 4, c < 2^k): candidate c of step t - 1 - k, c = the k decisions read so far, newest in the lowest bit */
+          int k = 31 - __clz (tid + 1);
+          const unsigned c = unsigned (tid + 1) - (1u << k);
+          uint32_t word = 0;
+          if (tid < 31 && k < depth)
+            {
+              unsigned rev = 0;                               // decisions enter the state from the top: oldest decision lowest
+              for (int i = 0; i < k; i++)
+                rev |= ((c >> i) & 1u) << (k - 1 - i);
+              const unsigned widx = ((state >> (5 + k)) | (rev << (10 - k))) & (kVitWords - 1);
+              word = dec[(size_t) (t - 1 - k) * kVitWords + widx];
+            }
+          unsigned path = 0;                                  // decisions of this round, newest in the lowest bit
+          for (k = 0; k < depth; k++)
+            {
+              const uint32_t w = __shfl_sync (0xffffffffu, word, (1 << k) - 1 + int (path));
+              const unsigned sel = (w >> (state & 31)) & 1u;
+              if (tid == 0 && t - 1 - k < n_msg)
+                bits_out[(size_t) job * n_msg + (t - 1 - k)] = state & 1u;
+              state = (state >> 1) | (sel << (AWM_VITERBI_ORDER - 1));
+              path = (path << 1) | sel;
+            }
+          t -= depth;
         }
     }
 }

@@ -498,7 +498,9 @@ awmh_balanced_get (const unsigned char *key16, const void *pcm, int is_s16, uint
     return 1;
   std::vector<unsigned char> recv;
   std::vector<size_t> lens (world);
-  size_t slot = 256 * 1024;
+  /* bytes per rank in an exchange: the refined scores + soft bits of a rank's candidates are ~0.4 MB per hour of audio; a payload that
+   * does not fit costs a second round, so the size that was needed once is kept for the following calls */
+  static size_t slot = 1024 * 1024;
   auto exchange = [&] (const std::string& mine, std::vector<std::string>& all)
     {
       for (;;)

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <map>
+#include <unordered_map>
+#include <stdint.h>
 #include <math.h>
 #include <stdlib.h>
 #include <tuple>
@@ -113,6 +115,7 @@ void
 ResultSet::apply_time_offset (double time_offset)
 {
   std::for_each (patterns.begin(), patterns.end(), [time_offset] (Pattern& p) { p.time += time_offset; });
+  forget_index();
 }
 
 /* rating of a pattern = summed sync quality of every pattern of the key that decoded to the same bits; combined ("all") patterns
@@ -150,6 +153,7 @@ ResultSet::sort (const vector<Key>& key_list)
   for (const auto& o : order)
     sorted.push_back (std::move (patterns[o.second]));
   patterns.swap (sorted);
+  forget_index();
 }
 
 /* add the patterns of the next chunk (in time order) unless this set already holds the same detection (approx_match).  Only a
@@ -160,23 +164,30 @@ void
 ResultSet::merge (ResultSet& other)
 {
   const double one_frame = Params::frame_size / double (Params::mark_sample_rate);
-  vector<Pattern> incoming (other.patterns);
+  auto bits_hash = [] (const vector<int>& bits)      /* FNV-1a over the payload bits: equal payloads are confirmed by approx_match */
+    {
+      uint64_t h = 1469598103934665603ull;
+      for (int b : bits)
+        h = (h ^ uint64_t (b & 1)) * 1099511628211ull;
+      return h;
+    };
+  vector<Pattern> incoming;
+  incoming.swap (other.patterns);                    /* the chunk result is consumed */
   std::stable_sort (incoming.begin(), incoming.end(), [] (const Pattern& x, const Pattern& y) { return x.time < y.time; });
-  struct Known { std::multimap<double, size_t> positioned; vector<size_t> combined; };
-  std::map<vector<int>, Known> by_bits;
   auto remember = [&] (size_t i)
     {
-      Known& k = by_bits[patterns[i].bit_vec];
+      Known& k = by_bits[bits_hash (patterns[i].bit_vec)];
       if (patterns[i].type == Type::ALL)
         k.combined.push_back (i);
       else
         k.positioned.emplace (patterns[i].time, i);
     };
-  for (size_t i = 0; i < patterns.size(); i++)
-    remember (i);
-  for (const Pattern& p : incoming)
+  for (; indexed < patterns.size(); indexed++)      /* what earlier merges / add_pattern calls appended since the index was last complete */
+    remember (indexed);
+  patterns.reserve (patterns.size() + incoming.size());
+  for (Pattern& p : incoming)
     {
-      const Known& k = by_bits[p.bit_vec];
+      const Known& k = by_bits[bits_hash (p.bit_vec)];
       bool have = false;
       if (p.type == Type::ALL)
         have = std::any_of (k.combined.begin(), k.combined.end(), [&] (size_t i) { return patterns[i].approx_match (p); });
@@ -185,8 +196,8 @@ ResultSet::merge (ResultSet& other)
           have = patterns[it->second].approx_match (p);
       if (!have)
         {
-          patterns.push_back (p);
-          remember (patterns.size() - 1);
+          patterns.push_back (std::move (p));
+          remember (indexed++);
         }
     }
   if (debug_sync.empty())

@@ -1,7 +1,10 @@
 // awm_results.hh -- ResultSet of `audiowmark get` (reference src/wmget.cc:163-474): pattern list,
 // rating, ordering, chunk merge and the text / JSON printers whose format is the public output API.
 #pragma once
+#include <map>
+#include <stdint.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "awm_wm.hh"
 
@@ -38,4 +41,10 @@ private:
   std::vector<Pattern> patterns;
   std::string          debug_sync;
   void rate_patterns (const Key& key);
+  /* merge index: patterns [0, indexed) by payload hash -> stream positions / combined patterns; rebuilt after anything that moves
+   * or re-times patterns (sort, apply_time_offset) */
+  struct Known { std::multimap<double, size_t> positioned; std::vector<size_t> combined; };
+  std::unordered_map<uint64_t, Known> by_bits;
+  size_t indexed = 0;
+  void forget_index() { by_bits.clear(); indexed = 0; }
 };
