@@ -79,7 +79,7 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
   uint64_t *pcm_bars = bars + 10;                                  // one per FFT warp: its next frame has landed in its transpose buffer
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *> (pcm_bars + FFT_WARPS);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  constexpr int kEpi0 = FFT_WARPS, kMmaWarp = FFT_WARPS + kTcEpiWarps;
+  constexpr int kMmaWarp = FFT_WARPS + kTcEpiWarps;
 
   if (threadIdx.x == 0)
     {
@@ -227,7 +227,7 @@ k_stft_mags_tc (const float *__restrict__ pcm, long long n_frames, int C, int n_
   else if (w < kMmaWarp)
     {
       // ===================================================================================== epilogue warps
-      const int q = w - kEpi0;                                    // == w % 4 (FFT_WARPS is a multiple of 4): TMEM lanes 32 q .. 32 q + 31
+      const int q = w & 3;                                        // a warp reaches the TMEM lanes of its quadrant only: 32 q .. 32 q + 31 (the four epilogue warps are consecutive, so every quadrant is served)
       int g = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
         {

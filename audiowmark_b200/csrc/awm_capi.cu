@@ -115,8 +115,8 @@ wall_now()
 struct SyncTab
 {
   DevBuf ent, off, sorted, groups;
-  DevBuf masks, masks48;              // 0/1 band masks of the entries as tcgen05 B operand chunks of 128 / 48 entries (awm_approx_tc.cuh)
-  int n_chunks = 0, n_chunks48 = 0;
+  DevBuf masks, masks48, masks64;     // 0/1 band masks of the entries as tcgen05 B operand chunks of 128 / 48 / 64 entries (awm_approx_tc.cuh)
+  int n_chunks = 0, n_chunks48 = 0, n_chunks64 = 0;
   int n_groups = 0;
   int n_ent = 0, n_bits = 0, total_frames = 0;
   std::vector<awm_sync_entry> h_ent;
@@ -389,6 +389,7 @@ awm_destroy (awm_ctx *ctx)
           s.ent.release();
           s.masks.release();
           s.masks48.release();
+          s.masks64.release();
           s.off.release();
           s.sorted.release();
           s.groups.release();
@@ -624,16 +625,20 @@ awm_set_sync_tables (awm_ctx *ctx, int key_slot, int mode, const awm_sync_entry 
   CK (cudaMemcpyAsync (t.groups.p, group_end.data(), group_end.size() * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
   CK (cudaStreamSynchronize (ctx->stream));
   {
-    std::vector<unsigned char> masks, masks48;
+    std::vector<unsigned char> masks, masks48, masks64;
     tc_build_masks (entries, n_entries, 128, masks);
     tc_build_masks (entries, n_entries, 48, masks48);
+    tc_build_masks (entries, n_entries, 64, masks64);
     CK (t.masks.reserve (masks.size()));
     CK (t.masks48.reserve (masks48.size()));
+    CK (t.masks64.reserve (masks64.size()));
     CK (cudaMemcpyAsync (t.masks.p, masks.data(), masks.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK (cudaMemcpyAsync (t.masks48.p, masks48.data(), masks48.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK (cudaMemcpyAsync (t.masks64.p, masks64.data(), masks64.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK (cudaStreamSynchronize (ctx->stream));
     t.n_chunks = int (masks.size() / tc_b_bytes (128));
     t.n_chunks48 = int (masks48.size() / tc_b_bytes (48));
+    t.n_chunks64 = int (masks64.size() / tc_b_bytes (64));
   }
   t.n_groups = int (group_end.size());
   t.n_ent = n_entries;
@@ -1259,7 +1264,7 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
        * entries; 12x1 = twelve FFT warps, one A buffer, chunks of 128 */
       const char *env_approx = getenv ("AWM_APPROX"), *env_tc = getenv ("AWM_TC");       // read per call: tests compare the variants in one process
       const bool force_simt = env_approx && !strcmp (env_approx, "simt");
-      const bool tc_12x1 = env_tc && !strcmp (env_tc, "12x1"), tc_8x2 = env_tc && !strcmp (env_tc, "8x2");
+      const bool tc_12x1 = env_tc && !strcmp (env_tc, "12x1"), tc_8x2 = env_tc && !strcmp (env_tc, "8x2"), tc_11x2 = env_tc && !strcmp (env_tc, "11x2");
       if (!force_simt)
         {
           if (!ctx->n_sms)
@@ -1281,6 +1286,8 @@ awm_sync_approx (awm_ctx *ctx, int key_slot, int mode, uint64_t wav_first, uint6
             AWM_LAUNCH_TC (12, 1, 128, t.masks, t.n_chunks)
           else if (tc_8x2)
             AWM_LAUNCH_TC (8, 2, 128, t.masks, t.n_chunks)
+          else if (tc_11x2)        /* 16 warps: four per scheduler, 128 registers each (17 warps put five on one scheduler: 96 registers, spills) */
+            AWM_LAUNCH_TC (11, 2, 64, t.masks64, t.n_chunks64)
           else
             AWM_LAUNCH_TC (12, 2, 48, t.masks48, t.n_chunks48)
 #undef AWM_LAUNCH_TC

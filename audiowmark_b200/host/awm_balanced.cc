@@ -276,9 +276,13 @@ Get::stage_peaks (const map<int, double>& floors, string& out)
           return false;
         }
       ft.mark ("approx launched, slice of chunk", sl.chunk);
-      /* lowered step by step until the slice has 64 maxima above the floor: the steps are fine enough that the list does not jump from a
-       * few dozen watermark peaks to thousands of noise peaks (every rank sorts and scans the gathered lists of all chunks) */
-      vector<double> seq = { thr1, thr1 * 0.6, thr1 * 0.35, thr1 * 0.25, thr1 * 0.2, thr1 * 0.15, thr1 * 0.1, thr1 * 0.05, -1.0 };
+      /* lowered step by step until the slice has three times n-best maxima above the floor (the selection keeps everything above the
+       * threshold, or the n best: with that many in hand it can decide; if masking leaves too few the run asks again for all maxima).
+       * The steps are fine enough that a list does not jump from a few dozen watermark peaks to thousands of noise peaks -- every rank
+       * sorts and scans the gathered lists of ALL chunks, so short lists keep that replicated work small */
+      vector<double> seq = { thr1, thr1 * 0.8, thr1 * 0.6, thr1 * 0.5, thr1 * 0.4, thr1 * 0.35, thr1 * 0.3, thr1 * 0.25, thr1 * 0.2, thr1 * 0.15, thr1 * 0.1,
+                             thr1 * 0.05, -1.0 };
+      const size_t enough = size_t (std::max (3 * Params::get_n_best, 24));
       if (floors.count (sl.chunk))
         seq = { floors.at (sl.chunk) };
       vector<awm_search_score> own;
@@ -298,7 +302,7 @@ Get::stage_peaks (const map<int, double>& floors, string& out)
               own.push_back (buf[i]);
           used = floor_q;
           ft.mark ("peaks above floor:", long (n));
-          if (own.size() >= 64 || floor_q < 0)
+          if (own.size() >= enough || floor_q < 0)
             break;
         }
       for (auto& p : own)
