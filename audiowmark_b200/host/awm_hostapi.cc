@@ -664,6 +664,103 @@ awmh_key_slot (const unsigned char *key16)
   return Engine::key_slot (make_key (key16, ""));
 }
 
+/* test aid (CPU): ResultSet::merge and ResultSet::sort against their literal definitions (src/wmget.cc:268-312: scan everything found so
+ * far with approx_match; compare name / rating / all-last / time / A-B-AB / bits one after the other) on random chunk results: a few
+ * payloads, positions that collide within a frame across chunks, combined patterns, stretched speeds, two keys.  Returns 0 when the
+ * merged and sorted documents are identical, else the number of the first failing round + 1. */
+int
+awmh_selftest_results (uint64_t seed, int rounds)
+{
+  uint64_t state = seed * 6364136223846793005ull + 1442695040888963407ull;
+  auto rnd = [&] (uint32_t n) { state = state * 6364136223846793005ull + 1442695040888963407ull; return uint32_t ((state >> 33) % n); };
+  const double frame = Params::frame_size / double (Params::mark_sample_rate);
+  Key keys[2];
+  keys[0] = make_key (reinterpret_cast<const unsigned char *> ("0123456789abcdef"), "alpha");
+  keys[1] = make_key (reinterpret_cast<const unsigned char *> ("fedcba9876543210"), "beta");
+  size_t n_in = 0, n_kept = 0;
+  for (int round = 0; round < rounds; round++)
+    {
+      std::vector<std::vector<int>> payloads (3 + rnd (3), std::vector<int> (16));
+      for (auto& pl : payloads)
+        for (int& b : pl)
+          b = int (rnd (2));
+      const int n_chunks = 2 + int (rnd (4));
+      std::vector<ResultSet> chunks (n_chunks), chunks_copy;
+      for (int c = 0; c < n_chunks; c++)
+        for (int i = 0, n = int (rnd (40)); i < n; i++)
+          {
+            const ResultSet::Type type = rnd (10) == 0 ? ResultSet::Type::ALL : rnd (8) == 0 ? ResultSet::Type::CLIP : ResultSet::Type::BLOCK;
+            const ConvBlockType bt = ConvBlockType (rnd (3));
+            /* positions on a coarse grid + a jitter around one frame, so that patterns of neighbouring chunks fall inside and just outside the match window */
+            /* + a unique 1e-7 s: no two patterns tie in every sort key (std::sort leaves the order of ties open, in the reference too) */
+            const double time = double (rnd (12)) * 7.0 + (double (rnd (5)) - 2.0) * frame * 0.6 + 1e-7 * double (c * 64 + i);
+            const double speed = rnd (6) == 0 ? 1.0 + (double (rnd (5)) - 2.0) * 0.006 : 1.0;
+            chunks[c].add_pattern (keys[rnd (2)], time, SyncFinder::Score { size_t (rnd (100000)), double (rnd (1000)) / 1000.0, bt }, payloads[rnd (uint32_t (payloads.size()))],
+                                   float (rnd (100)) / 100.f, type, speed);
+          }
+      chunks_copy = chunks;
+      /* the library */
+      ResultSet merged;
+      for (int c = 0; c < n_chunks; c++)
+        {
+          chunks[c].apply_time_offset (0.4 * frame * c);
+          merged.merge (chunks[c]);
+        }
+      merged.sort ({ keys[0], keys[1] });
+      /* the definition */
+      std::vector<ResultSet::Pattern> ref;
+      for (int c = 0; c < n_chunks; c++)
+        {
+          chunks_copy[c].apply_time_offset (0.4 * frame * c);
+          std::vector<ResultSet::Pattern> in = chunks_copy[c].all();
+          std::stable_sort (in.begin(), in.end(), [] (const ResultSet::Pattern& a, const ResultSet::Pattern& b) { return a.time < b.time; });
+          for (const auto& p : in)
+            {
+              bool is_new = true;
+              for (const auto& have : ref)
+                if (have.approx_match (p))
+                  is_new = false;
+              if (is_new)
+                ref.push_back (p);
+            }
+        }
+      for (const Key& key : keys)
+        {
+          std::map<std::string, float> rating;
+          for (const auto& p : ref)
+            if (p.key == key)
+              rating[bit_vec_to_str (p.bit_vec)] += p.sync_score.quality * (p.type == ResultSet::Type::ALL ? 2.f : 1.f);
+          for (auto& p : ref)
+            if (p.key == key)
+              p.rating = rating[bit_vec_to_str (p.bit_vec)];
+        }
+      auto rank_of = [] (const ResultSet::Pattern& p) { return p.sync_score.block_type == ConvBlockType::a ? 0 : p.sync_score.block_type == ConvBlockType::b ? 1 : 2; };
+      std::sort (ref.begin(), ref.end(), [&] (const ResultSet::Pattern& a, const ResultSet::Pattern& b)
+        {
+          const int all_a = a.type == ResultSet::Type::ALL, all_b = b.type == ResultSet::Type::ALL;
+          if (a.key.name() != b.key.name()) return a.key.name() < b.key.name();
+          if (a.rating != b.rating) return a.rating > b.rating;
+          if (all_a != all_b) return all_a < all_b;
+          if (a.time != b.time) return a.time < b.time;
+          if (rank_of (a) != rank_of (b)) return rank_of (a) < rank_of (b);
+          return bit_vec_to_str (a.bit_vec) < bit_vec_to_str (b.bit_vec);
+        });
+      const auto& got = merged.all();
+      bool same = got.size() == ref.size();
+      for (size_t i = 0; same && i < ref.size(); i++)
+        same = got[i].key == ref[i].key && got[i].time == ref[i].time && got[i].bit_vec == ref[i].bit_vec && got[i].type == ref[i].type
+            && got[i].sync_score.block_type == ref[i].sync_score.block_type && got[i].sync_score.quality == ref[i].sync_score.quality
+            && got[i].speed == ref[i].speed && got[i].rating == ref[i].rating && got[i].decode_error == ref[i].decode_error;
+      if (!same)
+        return round + 1;
+      for (const ResultSet& cr : chunks_copy)
+        n_in += cr.all().size();
+      n_kept += ref.size();
+    }
+  /* the test has teeth only if the merge did drop detections and keep others */
+  return (n_kept < n_in && n_kept * 10 > n_in) ? 0 : -1;
+}
+
 /* test aid: sync positions.  awmh_sync_trace (1) starts recording what every SyncFinder::search call returns, awmh_sync_trace_fetch
  * copies the records out as rows of 5 doubles {search number, mode (0 BLOCK / 1 CLIP), searched frames, -1, -1} (one header row per
  * search) and {search number, index, quality, block type (0 A / 1 B), 0} (one row per score) and clears the trace */

@@ -468,9 +468,10 @@ def main_gpu(args):
         "k_embed": 4.0 * ch * 2 * n,
         "k_embed_strip": 4.0 * ch * 2 * n,
     }
-    # dram__bytes_read.sum + dram__bytes_write.sum per PCM frame of kernel input, ncu --set full on a 10 min launch (profiles/r2_ncu_*.md)
-    dram_per_frame = {"k_stft_mags_tc": (213.49e6 + 364.98e6) / 26.46e6, "k_embed": (213.32e6 + 170.57e6) / 26.46e6,
-                      "k_embed_strip": (232.36e6 + 169.68e6) / 26.46e6}
+    # dram__bytes_read.sum + dram__bytes_write.sum per PCM frame of kernel input, ncu --set full on a 10 min launch
+    # (profiles/r2_ncu_full_final_add_get_10min.md; k_embed from profiles/r1_ncu_full_v4_all_kernels_10min.md)
+    dram_per_frame = {"k_stft_mags_tc": (213.25e6 + 365.00e6) / 26.46e6, "k_embed": (213.32e6 + 170.57e6) / 26.46e6,
+                      "k_embed_strip": (239.64e6 + 171.13e6) / 26.46e6}
     kernels = {}
     for name, r in (prof or {}).items():
         per_launch_ms = r["ms"] / max(r["launches"], 1)

@@ -195,3 +195,13 @@ def test_cli_option_handling_of_speed_and_short_modes(tmp_path):
         out = subprocess.check_output([cli, "test-speed", "--test-key", "7", str(seed)], text=True)
         r = O.Random(O.Key.test_key(7), seed, O.STREAM_DATA_UP_DOWN)
         assert out == "%.6f\n" % (0.85 + (r() / float(2 ** 64 - 1)) * (1.15 - 0.85))
+
+
+def test_result_set_merge_and_sort_against_their_definitions():
+    """the indexed chunk merge and the tuple sort of host/awm_results.cc vs the literal definitions (scan with approx_match, compare
+    key by key; src/wmget.cc:268-312) on random chunk results with colliding positions, combined patterns, two keys, stretched speeds"""
+    import ctypes
+    L = H.load()
+    L.awmh_selftest_results.restype = ctypes.c_int
+    for seed in (1, 2, 3, 4):
+        assert L.awmh_selftest_results(ctypes.c_uint64(seed), ctypes.c_int(200)) == 0
