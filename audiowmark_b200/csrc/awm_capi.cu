@@ -12,6 +12,7 @@
 #include <string.h>
 #include "awm_approx_tc.cuh"
 #include "awm_embed_strip.cuh"
+#include "awm_viterbi_pair.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -165,7 +166,7 @@ struct awm_ctx
   size_t n_scores_dev = 0;
   DevBuf cand_start, cand_noff, r_ud, r_cnt, rvalid, r_ent_ud, r_ent_flag, tw1024;   // refine
   DevBuf blk_start, D, raw;          // decode
-  DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err;
+  DevBuf vit_raw, vit_off, vit_types, vit_delta, vit_dec, vit_bits, vit_err, vit_order;
   DevBuf emb_in, emb_out, emb_in16, emb_out16, peaks, snr;
 
   PinArena pin;
@@ -361,7 +362,7 @@ awm_destroy (awm_ctx *ctx)
   cudaStreamSynchronize (ctx->stream);
   DevBuf *bufs[] = { &ctx->tw, &ctx->win, &ctx->synth, &ctx->frame_mod, &ctx->pcm_own, &ctx->pcm16_own, &ctx->dbT, &ctx->have, &ctx->q, &ctx->scores, &ctx->a_ud, &ctx->a_cnt, &ctx->peaks_out, &ctx->peaks_cnt, &ctx->a_mags,
                      &ctx->cand_start, &ctx->cand_noff, &ctx->r_ud, &ctx->r_cnt, &ctx->rvalid, &ctx->r_ent_ud, &ctx->r_ent_flag, &ctx->tw1024, &ctx->vit_off, &ctx->blk_start, &ctx->D, &ctx->raw,
-                     &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err,
+                     &ctx->vit_raw, &ctx->vit_types, &ctx->vit_delta, &ctx->vit_dec, &ctx->vit_bits, &ctx->vit_err, &ctx->vit_order,
                      &ctx->emb_in, &ctx->emb_out, &ctx->emb_in16, &ctx->emb_out16, &ctx->peaks, &ctx->snr, &ctx->rs_in, &ctx->rs_out, &ctx->rs_jobs, &ctx->pcm_rs,
                      &ctx->win512, &ctx->sp_clip, &ctx->sp_sub, &ctx->sp_mags, &ctx->sp_mag_jobs, &ctx->sp_cmp_jobs, &ctx->sp_best };
   for (DevBuf *b : bufs)
@@ -1967,10 +1968,15 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits,
     }
   CK (cudaSetDevice (ctx->device));
   const size_t max_jobs = 512;
-  const size_t smem = viterbi_smem_bytes (steps);
+  /* default: one CTA per code word (k_viterbi).  AWM_VITERBI=pair: a cluster of two CTAs per word with the metrics exchanged through
+   * distributed shared memory (k_viterbi_pair, awm_viterbi_pair.cuh) -- same bits, but measured SLOWER on 110 words (1.16 vs 0.72 ms):
+   * the cluster barrier of every trellis step costs ~3 us (release / acquire at cluster scope = MEMBAR.ALL.GPU in SASS) */
+  const char *env_vit = getenv ("AWM_VITERBI");
+  const bool use_pair = env_vit && !strcmp (env_vit, "pair");
+  const size_t smem = use_pair ? viterbi_pair_smem_bytes (steps) : viterbi_smem_bytes (steps);
   if (smem > 220 * 1024)
     return fail (ctx, "awm_viterbi: %d message bits are more than the kernel holds in shared memory", n_msg_bits);
-  if (set_smem (ctx, k_viterbi, smem)) return 1;
+  if (use_pair ? set_smem (ctx, k_viterbi_pair, smem) : set_smem (ctx, k_viterbi, smem)) return 1;
   for (size_t j0 = 0; j0 < n_jobs; j0 += max_jobs)
     {
       const size_t nj = std::min (max_jobs, n_jobs - j0);
@@ -1984,6 +1990,7 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits,
       CK (ctx->vit_dec.reserve (nj * steps * kVitWords * sizeof (uint32_t)));
       CK (ctx->vit_bits.reserve (nj * n_msg_bits));
       CK (ctx->vit_err.reserve (nj * sizeof (float)));
+      CK (ctx->vit_order.reserve (nj * sizeof (int)));
       /* host inputs / outputs pass through page-locked staging: the three uploads, the launch and the two downloads queue up
        * without the host waiting in between */
       ctx->pin.reset();
@@ -1991,21 +1998,38 @@ awm_viterbi (awm_ctx *ctx, const float *raw_bits, size_t n_jobs, int n_msg_bits,
       float *h_in = raw_on_device ? nullptr : ctx->pin.get<float> (size_t (n_raw));
       long long *h_rel = ctx->pin.get<long long> (nj);
       int *h_types = ctx->pin.get<int> (nj);
+      int *h_order = ctx->pin.get<int> (nj);
       unsigned char *h_bits = ctx->pin.get<unsigned char> (nj * n_msg_bits);
       float *h_err = ctx->pin.get<float> (nj);
-      if ((!raw_on_device && !h_in) || !h_rel || !h_types || !h_bits || !h_err)
+      if ((!raw_on_device && !h_in) || !h_rel || !h_types || !h_order || !h_bits || !h_err)
         return fail (ctx, "awm_viterbi: out of page-locked memory");
       if (h_in)
         memcpy (h_in, raw_bits + base, size_t (n_raw) * sizeof (float));
       std::copy (rel.begin(), rel.end(), h_rel);
       std::copy (block_types + j0, block_types + j0 + nj, h_types);
+      {
+        /* AB words (twice the adds of an A or B word) go first in the grid, the shorter words fill the SMs they free */
+        size_t k = 0;
+        for (size_t j = 0; j < nj; j++)
+          if (h_types[j] == AWM_BLOCK_AB)
+            h_order[k++] = int (j);
+        for (size_t j = 0; j < nj; j++)
+          if (h_types[j] != AWM_BLOCK_AB)
+            h_order[k++] = int (j);
+      }
       CK (cudaMemcpyAsync (ctx->vit_raw.p, h_in ? h_in : raw_bits + base, n_raw * sizeof (float), cudaMemcpyDefault, ctx->stream));
       CK (cudaMemcpyAsync (ctx->vit_off.p, h_rel, nj * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
       CK (cudaMemcpyAsync (ctx->vit_types.p, h_types, nj * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
+      CK (cudaMemcpyAsync (ctx->vit_order.p, h_order, nj * sizeof (int), cudaMemcpyHostToDevice, ctx->stream));
       PROF (ctx);
-      k_viterbi<<<unsigned (nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), ctx->vit_off.as<long long>(), n_msg_bits, ctx->vit_types.as<int>(), hard,
-                                                                  steps, ctx->vit_dec.as<uint32_t>(),
-                                                                  ctx->vit_bits.as<unsigned char>(), ctx->vit_err.as<float>());
+      if (use_pair)
+        k_viterbi_pair<<<unsigned (2 * nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), ctx->vit_off.as<long long>(), n_msg_bits, ctx->vit_types.as<int>(),
+                                                                         hard, steps, ctx->vit_order.as<int>(), ctx->vit_dec.as<uint32_t>(),
+                                                                         ctx->vit_bits.as<unsigned char>(), ctx->vit_err.as<float>());
+      else
+        k_viterbi<<<unsigned (nj), kVitThreads, smem, ctx->stream>>> (ctx->vit_raw.as<float>(), ctx->vit_off.as<long long>(), n_msg_bits, ctx->vit_types.as<int>(), hard,
+                                                                    steps, ctx->vit_dec.as<uint32_t>(),
+                                                                    ctx->vit_bits.as<unsigned char>(), ctx->vit_err.as<float>());
       LAUNCH_CHECK ("k_viterbi");
       CK (cudaMemcpyAsync (h_bits, ctx->vit_bits.p, nj * n_msg_bits, cudaMemcpyDeviceToHost, ctx->stream));
       CK (cudaMemcpyAsync (h_err, ctx->vit_err.p, nj * sizeof (float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -644,8 +644,10 @@ __host__ __device__ constexpr bool cparity (unsigned v) { v ^= v >> 16; v ^= v >
 __device__ __forceinline__ int vit_pos (int n) { return n + ((n >> 5) << 2); }
 constexpr int kVitPadded = kVitStates + kVitStates / 32 * 4;
 
+// d_lo / d_hi: the path metrics of the predecessors ps0 = 16 u + .. (lower half of the states) and ps1 = ps0 + 2^14 (upper half),
+// both addressed with vit_pos (16 u + ..)
 template<int TYPE> __device__ __forceinline__ uint32_t
-viterbi_step (const float *__restrict__ d_old, float (&outv)[32], unsigned hi, const float *m0, const float *m1, int u)
+viterbi_step (const float *__restrict__ d_lo, const float *__restrict__ d_hi, float (&outv)[32], unsigned hi, const float *m0, const float *m1, int u)
 {
   constexpr int RATE = TYPE == AWM_BLOCK_AB ? 12 : 6;
   // The two candidates of a new state -- coming from predecessor ps0 and from ps1 -- add the SAME branch metrics in the same order,
@@ -664,8 +666,8 @@ viterbi_step (const float *__restrict__ d_old, float (&outv)[32], unsigned hi, c
 #pragma unroll
   for (int v = 0; v < 4; v++)                                // 8 new states <- 4 + 4 predecessors
     {
-      const float4 x = *reinterpret_cast<const float4 *> (d_old + vit_pos (16 * u + 4 * v));
-      const float4 y = *reinterpret_cast<const float4 *> (d_old + vit_pos (16 * u + 4 * v + (kVitStates >> 1)));
+      const float4 x = *reinterpret_cast<const float4 *> (d_lo + vit_pos (16 * u + 4 * v));
+      const float4 y = *reinterpret_cast<const float4 *> (d_hi + vit_pos (16 * u + 4 * v));
       const f2 a01[4] = { f2_make (x.x, y.x), f2_make (x.y, y.y), f2_make (x.z, y.z), f2_make (x.w, y.w) };
 #pragma unroll
       for (int q = 0; q < 8; q++)
@@ -717,7 +719,7 @@ viterbi_run (float *dm, uint32_t *dec, const float *coded, float *m0, float *m1,
       for (int g = 0; g < kGroups; g++)
         {
           const int u = tid + g * kVitThreads;
-          dec[(size_t) t * kVitWords + u] = viterbi_step<TYPE> (dm, outv[g], hi[g], m0, m1, u);
+          dec[(size_t) t * kVitWords + u] = viterbi_step<TYPE> (dm, dm + vit_pos (kVitStates >> 1), outv[g], hi[g], m0, m1, u);
         }
       __syncthreads();                                      // every thread has read its predecessors
 #pragma unroll
@@ -730,6 +732,45 @@ viterbi_run (float *dm, uint32_t *dec, const float *coded, float *m0, float *m1,
         }
     }
   __syncthreads();
+}
+
+/* Traceback (src/convcode.cc:192-211) by one warp.  Going back one step reads ONE decision bit, but which word of the previous step
+ * holds it depends on the bit just read: done by one thread this is a chain of 143 dependent global loads.  The word index of step
+ * t - 1 - k is (state >> (5 + k)) | (the k decisions in between) << (10 - k): the warp loads the word of step t - 1 and all
+ * 2 + 4 + 8 + 16 candidate words of the four steps before it at once (31 lanes, one load latency), then walks the five steps through
+ * shuffles. */
+__device__ __forceinline__ void
+viterbi_traceback (const uint32_t *dec, int steps, int n_msg, unsigned char *bits_out, int lane)
+{
+  unsigned state = 0;
+  int t = steps;
+  while (t > 0)
+    {
+      const int depth = t < 5 ? t : 5;                  // steps resolved in this round
+      /* lane 2^k - 1 + c (k = 0 .. 4, c < 2^k): candidate c of step t - 1 - k, c = the k decisions read so far, newest in the lowest bit */
+      int k = 31 - __clz (lane + 1);
+      const unsigned c = unsigned (lane + 1) - (1u << k);
+      uint32_t word = 0;
+      if (lane < 31 && k < depth)
+        {
+          unsigned rev = 0;                               // decisions enter the state from the top: oldest decision lowest
+          for (int i = 0; i < k; i++)
+            rev |= ((c >> i) & 1u) << (k - 1 - i);
+          const unsigned widx = ((state >> (5 + k)) | (rev << (10 - k))) & (kVitWords - 1);
+          word = dec[(size_t) (t - 1 - k) * kVitWords + widx];
+        }
+      unsigned path = 0;                                  // decisions of this round, newest in the lowest bit
+      for (k = 0; k < depth; k++)
+        {
+          const uint32_t w = __shfl_sync (0xffffffffu, word, (1 << k) - 1 + int (path));
+          const unsigned sel = (w >> (state & 31)) & 1u;
+          if (lane == 0 && t - 1 - k < n_msg)
+            bits_out[t - 1 - k] = state & 1u;
+          state = (state >> 1) | (sel << (AWM_VITERBI_ORDER - 1));
+          path = (path << 1) | sel;
+        }
+      t -= depth;
+    }
 }
 
 constexpr size_t viterbi_smem_bytes (int steps) { return size_t (kVitPadded) * sizeof (float) + size_t (steps) * 12 * sizeof (float); }
@@ -787,43 +828,8 @@ k_viterbi (const float *__restrict__ raw, const long long *__restrict__ raw_off,
     viterbi_run<AWM_BLOCK_AB> (dm, dec, coded, m0, m1, steps, tid);
   if (tid == 0)
     err_out[job] = dm[0] / float (n_coded);
-  /* Traceback (src/convcode.cc:192-211) by warp 0.  Going back one step reads ONE decision bit, but which word of the previous step
-   * holds it depends on the bit just read: done by one thread this is a chain of 143 dependent global loads (~0.1 ms, an eighth of
-   * the kernel).  The word index of step t - 1 - k is (state >> (5 + k)) | (the k decisions in between) << (10 - k): the warp loads
-   * the word of step t - 1 and all 2 + 4 + 8 + 16 candidate words of the four steps before it at once (31 lanes, one load latency),
-   * then walks the five steps through shuffles. */
   if (tid < 32)
-    {
-      unsigned state = 0;
-      int t = steps;
-      while (t > 0)
-        {
-          const int depth = t < 5 ? t : 5;                  // steps resolved in this round
-          /* lane 2^k - 1 + c (k = 0 .. 4, c < 2^k): candidate c of step t - 1 - k, c = the k decisions read so far, newest in the lowest bit */
-          int k = 31 - __clz (tid + 1);
-          const unsigned c = unsigned (tid + 1) - (1u << k);
-          uint32_t word = 0;
-          if (tid < 31 && k < depth)
-            {
-              unsigned rev = 0;                               // decisions enter the state from the top: oldest decision lowest
-              for (int i = 0; i < k; i++)
-                rev |= ((c >> i) & 1u) << (k - 1 - i);
-              const unsigned widx = ((state >> (5 + k)) | (rev << (10 - k))) & (kVitWords - 1);
-              word = dec[(size_t) (t - 1 - k) * kVitWords + widx];
-            }
-          unsigned path = 0;                                  // decisions of this round, newest in the lowest bit
-          for (k = 0; k < depth; k++)
-            {
-              const uint32_t w = __shfl_sync (0xffffffffu, word, (1 << k) - 1 + int (path));
-              const unsigned sel = (w >> (state & 31)) & 1u;
-              if (tid == 0 && t - 1 - k < n_msg)
-                bits_out[(size_t) job * n_msg + (t - 1 - k)] = state & 1u;
-              state = (state >> 1) | (sel << (AWM_VITERBI_ORDER - 1));
-              path = (path << 1) | sel;
-            }
-          t -= depth;
-        }
-    }
+    viterbi_traceback (dec, steps, n_msg, bits_out + (size_t) job * n_msg, tid);
 }
 
 // =============================================================================================

@@ -193,7 +193,11 @@ def test_decode_blocks_vs_oracle(ctx, marked):
     assert O.bit_vec_to_str(list(bits[0])) == T.PAYLOAD
 
 
-def test_viterbi_vs_oracle(ctx):
+@pytest.mark.parametrize("variant", ["single", "pair"])
+def test_viterbi_vs_oracle(ctx, monkeypatch, variant):
+    """k_viterbi (one CTA per code word, the default) and k_viterbi_pair (a 2-CTA cluster per word, metrics exchanged through
+    distributed shared memory; AWM_VITERBI=pair) against the oracle: identical bits, error within 1e-5"""
+    monkeypatch.setenv("AWM_VITERBI", variant)
     rng = np.random.default_rng(5)
     msg = [int(b) for b in rng.integers(0, 2, 128)]
     for bt, cbt in ((O.A, capi.BLOCK_A), (O.B, capi.BLOCK_B), (O.AB, capi.BLOCK_AB)):
