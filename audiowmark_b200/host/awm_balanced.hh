@@ -7,7 +7,8 @@
 // by every rank identically -- the result is the single-GPU document, pattern for pattern.  Three small exchanges per run:
 //   peaks                    the local maxima of the approximate search above an adaptive floor
 //   refined scores + bits    every candidate a rank owns, refined and decoded to soft bits
-//   decoded words            the Viterbi results of the code words a rank decoded (jobs are dealt out round-robin)
+//   decoded words            the Viterbi results of the code words a rank decoded (the ranks that share a chunk deal its jobs out
+//                            among themselves), with what rank 0 needs to print them
 // No PCM crosses NVLink.  The exchange itself is a callback: NCCL (awm_dist_allgather) in production, an in-process stand-in when
 // tests run several ranks on one GPU.
 #pragma once

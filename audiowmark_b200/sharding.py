@@ -1,10 +1,11 @@
-"""Multi-GPU sharding of one long stream (one process per GPU, torch.distributed).
+"""Plan functions of the multi-GPU run of one long stream (one process per GPU, torch.distributed).
 
-`get` shards by the reference's own chunks (WavChunkLoader: 30 min, 134.4 s overlap; src/wavchunkloader.cc:54-163) so
-every per-chunk statistic (local mean, n-best, "all" pattern) is identical to the single-process run; `add` shards by
-frame blocks with a recomputed halo (one 1024-frame for the synthesis window tails, two limiter blocks for the gain ramp)
-so the interior of every shard is identical to the unsharded output.  Nothing is exchanged on the data path; the only
-collective is the final gather of the chunk results (a few hundred bytes per detection).
+The sharded `get` itself is C++ (host/awm_balanced.cc: every rank searches an equal slice of the start frames of every chunk its span
+of positions overlaps; three ncclAllGather exchanges of small lists; hostapi.balanced_get).  What lives here is what bench.py and the
+CPU tests need around it: the reference's chunk walk (WavChunkLoader: 30 min, 134.4 s overlap; src/wavchunkloader.cc:54-163), the
+slices of a rank (a mirror of the C++ planner, tests/test_sharding_cpu.py holds the two equal), the range a rank has to embed so that
+its slices read exactly what the unsharded `add` would have written (`add` shards by frame blocks with a recomputed halo: one
+1024-frame for the synthesis window tails, two limiter blocks for the gain ramp), and the blob helpers of the chunk-granular variant.
 """
 from __future__ import annotations
 

@@ -93,7 +93,7 @@ def test_frame_balanced_get_equals_single_process(world):
             pay = [rk.stage(2, [retry[0]]) for rk in ranks]
             assert all(rk.stage(1, pay) == b"" for rk in ranks)
         pay = [rk.stage(3) for rk in ranks]                          # refine + soft bits
-        pay = [rk.stage(4, pay) for rk in ranks]                     # viterbi (jobs dealt round-robin)
+        pay = [rk.stage(4, pay) for rk in ranks]                     # viterbi (the sharers of a chunk deal its jobs out among themselves)
         docs = [json.loads(rk.stage(5, pay).decode()) for rk in ranks]
         assert all(d == doc for d in docs)
     finally:
