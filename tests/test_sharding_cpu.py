@@ -176,3 +176,41 @@ def test_cpp_plan_functions_agree_with_their_python_restatement():
             idx = rng.integers(0, cn, 20)
             own = S.index_owners(plan, n_total, world, c, idx)
             assert [H.balanced_owner(n_total, world, c, int(i)) for i in idx] == [int(o) for o in own]
+
+
+@pytest.mark.parametrize("frames_per_bit,short", [(2, 0), (3, 0), (2, 12), (2, 20), (1, 16)])
+def test_cpp_planner_follows_the_block_length_of_the_parameters(frames_per_bit, short):
+    """--frames-per-bit and --short change the block length (sync + data frames); the C++ planner of the sharded get takes it from the
+    parameters: for every world size the owned start-frame ranges of the ranks tile every chunk exactly, every slice carries the PCM
+    its searched range needs (one block + one frame beyond it), and the owner rule sends an index to the rank whose range holds it"""
+    H.set_params(frames_per_bit=frames_per_bit)
+    H.set_short_payload(short)
+    try:
+        T_blk = H.frames_per_block()
+        if short == 0:
+            assert T_blk == 85 * 6 + 858 * frames_per_bit       # 510 sync frames + one data frame group per coded bit
+        rng = np.random.default_rng(7)
+        for hours, world in ((1, 1), (2, 2), (3.3, 4), (8, 8), (0.4, 3)):
+            n_total = int(hours * 3600 * 44100)
+            per_rank = [H.balanced_plan(n_total, r, world) for r in range(world)]
+            chunks = per_rank[0][0]
+            for c, (cs, cn, _) in enumerate(chunks):
+                n_starts = max(int(cn) // 1024 - T_blk - 1, 0)
+                owned = sorted((sl[1], sl[2], r) for r, (_, sls) in enumerate(per_rank) for sl in sls if sl[0] == c)
+                if n_starts == 0:
+                    assert not owned
+                    continue
+                assert owned[0][0] == 0 and owned[-1][1] == n_starts, (frames_per_bit, short, hours, world, c)
+                assert all(a[1] == b[0] for a, b in zip(owned, owned[1:]))
+                for r, (_, sls) in enumerate(per_rank):
+                    for chunk, sa, sb, a, b, lo, hi in sls:
+                        if chunk == c:
+                            assert a <= sa < sb <= b and lo == cs + a * 1024
+                            assert hi <= cs + cn and hi >= min(cs + (b + T_blk + 1) * 1024, cs + cn)
+                for i in rng.integers(0, int(cn), 12):
+                    s = min(int(i) // 1024, n_starts - 1)
+                    r = H.balanced_owner(n_total, world, c, int(i))
+                    assert any(x <= s < y and rr == r for x, y, rr in owned)
+    finally:
+        H.set_short_payload(0)
+        H.set_params()
