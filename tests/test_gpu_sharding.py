@@ -116,6 +116,43 @@ def test_balanced_get_entry_point_single_rank():
         H.set_params()
 
 
+@pytest.mark.parametrize("short,frames_per_bit", [(16, 2), (0, 3)])
+def test_balanced_get_with_other_block_lengths(short, frames_per_bit):
+    """--short / --frames-per-bit change the block length; the sharded driver takes it from the parameters (host/awm_balanced.cc:
+    frames_per_block): same document as the single GPU get, three simulated ranks"""
+    payload = "beef" if short else T.PAYLOAD
+    H.set_params(chunk_size_min=4.0, frames_per_bit=frames_per_bit)
+    H.set_short_payload(short)
+    torch = pytest.importorskip("torch")
+    ranks, keep = [], []
+    try:
+        y = H.add(T.noise(500.0, 2, seed=26), payload)
+        doc = H.get(y)
+        assert sum(m["bits"] == payload for m in doc["matches"]) >= 3
+        n, world = y.shape[0], 3
+        for r in range(world):
+            _, slices = H.balanced_plan(n, r, world)
+            lo, hi = min(s[5] for s in slices), max(s[6] for s in slices)
+            part = torch.from_numpy(np.ascontiguousarray(y[lo:hi])).cuda()
+            keep.append(part)
+            torch.cuda.synchronize()
+            ranks.append(H.BalancedStages(r, world, n, part.data_ptr(), hi - lo, 2, lo))
+        pay = [rk.stage(0) for rk in ranks]
+        retry = [rk.stage(1, pay) for rk in ranks]
+        assert all(rt == retry[0] for rt in retry)
+        if retry[0]:
+            pay = [rk.stage(2, [retry[0]]) for rk in ranks]
+            assert all(rk.stage(1, pay) == b"" for rk in ranks)
+        pay = [rk.stage(3) for rk in ranks]
+        pay = [rk.stage(4, pay) for rk in ranks]
+        assert json.loads(ranks[0].stage(5, pay).decode()) == doc
+    finally:
+        for rk in ranks:
+            rk.close()
+        H.set_short_payload(0)
+        H.set_params()
+
+
 def test_balanced_get_refuses_clip_sized_input():
     """inputs under 3.1 blocks go through the reference's ClipDecoder (src/wmget.cc:764-884), which the sharded driver does not run:
     it must refuse them loudly instead of returning a document without CLIP patterns"""
