@@ -262,6 +262,7 @@ def main_gpu(args):
     n_total = n * world
     mx, ov = H.chunk_geometry(RATE)
     plan = S.chunk_plan(n_total, mx, ov, RATE)
+    assert H.frames_per_block() == S.T_BLOCK          # the Python plan functions below are written for the default block length
     if world == 1:
         e0, e1, ffn = 0, n, 0
     else:
